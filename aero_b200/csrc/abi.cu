@@ -1,0 +1,1287 @@
+// C ABI (include/aero_b200.h) over the sm_100a kernels: context, transform plans, segment / FRI
+// handles.  Host-side work here is bookkeeping only (table construction, index lists for openings,
+// byte packing); every field/hash operation over trace-sized data runs in a CUDA kernel.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/aero_b200.h"
+#include "kernels.cuh"
+#include "ntt.cuh"
+
+using namespace aero;
+
+namespace aero {
+unsigned long long g_launch_count = 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// context
+// -------------------------------------------------------------------------------------------------
+struct PhaseStat {
+    int calls = 0;
+    double ms = 0;
+};
+struct PendingEvent {
+    std::string name;
+    cudaEvent_t a, b;
+};
+struct PowTableOwned {
+    uint64_t *lo = nullptr, *hi = nullptr;
+    int lo_bits = 0;
+    PowTable view() const { return PowTable{lo, hi, lo_bits}; }
+};
+
+struct aero_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    int form = AERO_FORM_MONTGOMERY;
+    std::string err;
+    bool profile = false;
+    std::map<std::string, PhaseStat> stats;
+    std::vector<PendingEvent> pending;
+    std::map<std::string, DftTables> plans;
+    std::map<std::string, PowTableOwned> pow_tables;
+    std::vector<void *> owned;  // device allocations freed with the context
+    size_t lde_batch_bytes = (size_t)1 << 30;  // NTT scratch budget per column batch
+};
+
+#define CTX_FAIL(ctx, code, ...)                         \
+    do {                                                 \
+        char _b[512];                                    \
+        snprintf(_b, sizeof _b, __VA_ARGS__);            \
+        (ctx)->err = _b;                                 \
+        return (code);                                   \
+    } while (0)
+#define CUDA_TRY(ctx, expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            CTX_FAIL(ctx, _e == cudaErrorMemoryAllocation ? AERO_ERR_NOMEM : AERO_ERR_CUDA, "%s: %s", #expr, \
+                     cudaGetErrorString(_e));                                                        \
+    } while (0)
+#define TRY(expr)                        \
+    do {                                 \
+        aero_status _s = (expr);         \
+        if (_s != AERO_OK) return _s;    \
+    } while (0)
+
+static bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+static int ilog2(uint64_t x) {
+    int l = 0;
+    while ((1ULL << l) < x) l++;
+    return l;
+}
+
+struct PhaseTimer {
+    aero_ctx *ctx;
+    PendingEvent ev;
+    bool on;
+    PhaseTimer(aero_ctx *c, const char *name) : ctx(c), on(c->profile) {
+        if (!on) return;
+        ev.name = name;
+        cudaEventCreate(&ev.a);
+        cudaEventCreate(&ev.b);
+        cudaEventRecord(ev.a, ctx->stream);
+    }
+    ~PhaseTimer() {
+        if (!on) return;
+        cudaEventRecord(ev.b, ctx->stream);
+        ctx->pending.push_back(ev);
+    }
+};
+static void profile_flush(aero_ctx *ctx) {
+    for (auto &p : ctx->pending) {
+        cudaEventSynchronize(p.b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        auto &s = ctx->stats[p.name];
+        s.calls++;
+        s.ms += ms;
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    ctx->pending.clear();
+}
+
+static aero_status dev_alloc(aero_ctx *ctx, void **p, size_t bytes) {
+    if (bytes == 0) bytes = 8;
+    CUDA_TRY(ctx, cudaMallocAsync(p, bytes, ctx->stream));
+    return AERO_OK;
+}
+static void dev_free(aero_ctx *ctx, void *p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+template <typename T>
+static aero_status upload_vec(aero_ctx *ctx, T **d, const std::vector<T> &h, bool own = true) {
+    void *p = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&p, std::max<size_t>(8, h.size() * sizeof(T))));
+    CUDA_TRY(ctx, cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (own) ctx->owned.push_back(p);
+    *d = (T *)p;
+    return AERO_OK;
+}
+
+static inline uint64_t to_canon(const aero_ctx *ctx, uint64_t x) {
+    return ctx->form == AERO_FORM_MONTGOMERY ? gl::mont_to_canon(x) : gl::canon(x);
+}
+static inline uint64_t from_canon(const aero_ctx *ctx, uint64_t x) {
+    return ctx->form == AERO_FORM_MONTGOMERY ? gl::canon_to_mont(x) : x;
+}
+
+// -------------------------------------------------------------------------------------------------
+// transform plans
+// -------------------------------------------------------------------------------------------------
+// stage table for an M-point DIT evaluating on the coset sigma*<w_M>: tw[m/2 + k] = sigma^(M/m) w_m^k
+static void fill_stage_table(uint64_t *tw, int logM, uint64_t sigma, uint64_t wM) {
+    const uint64_t M = 1ULL << logM;
+    tw[0] = 0;
+    for (int s = 0; s < logM; s++) {
+        const uint64_t m = 2ULL << s;              // sub-transform size
+        const uint64_t sg = gl::pow(sigma, M / m);  // sigma^(M/m)
+        const uint64_t wm = gl::pow(wM, M / m);     // primitive m-th root
+        uint64_t x = sg;
+        for (uint64_t k = 0; k < m / 2; k++) {
+            tw[m / 2 + k] = x;
+            x = gl::mul(x, wm);
+        }
+    }
+}
+static void fill_pow_table(std::vector<uint64_t> &lo, std::vector<uint64_t> &hi, uint64_t base, int total_bits,
+                           int lo_bits, uint64_t hi_scale) {
+    lo.resize(1ULL << lo_bits);
+    hi.resize(1ULL << std::max(0, total_bits - lo_bits));
+    uint64_t x = 1;
+    for (auto &v : lo) {
+        v = x;
+        x = gl::mul(x, base);
+    }
+    const uint64_t step = gl::pow(base, 1ULL << lo_bits);
+    x = hi_scale;
+    for (auto &v : hi) {
+        v = x;
+        x = gl::mul(x, step);
+    }
+}
+
+// shifts: per-coset input shift s_r (evaluate p on s_r * <w_n>), or all 1.
+// scale_c: constant folded into the result.  post_base != 0: out[i] *= post_base^i.
+static aero_status get_plan(aero_ctx *ctx, const std::string &key, int logn, bool inverse,
+                            const std::vector<uint64_t> &shifts, uint64_t scale_c, uint64_t post_base,
+                            const DftTables **out) {
+    auto it = ctx->plans.find(key);
+    if (it != ctx->plans.end()) {
+        *out = &it->second;
+        return AERO_OK;
+    }
+    if (logn < 1 || logn > NTT_MAX_LOG) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "transform size 2^%d unsupported (1..%d)", logn, NTT_MAX_LOG);
+    DftTables t;
+    t.logn = logn;
+    t.ncosets = (int)shifts.size();
+    const uint64_t n = 1ULL << logn;
+    uint64_t w = gl::root_of_unity(logn);
+    if (inverse) w = gl::inv(w);
+    if (logn <= NTT_SINGLE_MAX_LOG) {
+        t.log1 = 0;
+        t.log2 = logn;
+        std::vector<uint64_t> st((size_t)t.ncosets * n);
+        for (int r = 0; r < t.ncosets; r++) fill_stage_table(st.data() + (size_t)r * n, logn, shifts[r], w);
+        TRY(upload_vec(ctx, &t.stage2, st));
+        t.single_scale = scale_c;
+        if (post_base) {
+            std::vector<uint64_t> pu(n);
+            uint64_t x = scale_c;
+            for (auto &v : pu) {
+                v = x;
+                x = gl::mul(x, post_base);
+            }
+            TRY(upload_vec(ctx, &t.post_u, pu));
+        }
+    } else {
+        t.log2 = logn / 2;
+        t.log1 = logn - t.log2;
+        const uint64_t n1 = 1ULL << t.log1, n2 = 1ULL << t.log2;
+        const uint64_t w1 = gl::pow(w, n2), w2 = gl::pow(w, n1);
+        std::vector<uint64_t> st1((size_t)t.ncosets * n1), st2(n2), ib((size_t)t.ncosets * n2);
+        for (int r = 0; r < t.ncosets; r++) {
+            fill_stage_table(st1.data() + (size_t)r * n1, t.log1, gl::pow(shifts[r], n2), w1);
+            uint64_t x = scale_c;
+            for (uint64_t j2 = 0; j2 < n2; j2++) {
+                ib[(size_t)r * n2 + j2] = x;
+                x = gl::mul(x, shifts[r]);
+            }
+        }
+        fill_stage_table(st2.data(), t.log2, 1, w2);
+        TRY(upload_vec(ctx, &t.stage1, st1));
+        TRY(upload_vec(ctx, &t.stage2, st2));
+        TRY(upload_vec(ctx, &t.inter_b, ib));
+        t.lo_bits = (logn + 1) / 2;
+        std::vector<uint64_t> lo, hi;
+        fill_pow_table(lo, hi, w, logn, t.lo_bits, 1);
+        TRY(upload_vec(ctx, &t.wlo, lo));
+        TRY(upload_vec(ctx, &t.whi, hi));
+        if (post_base) {
+            std::vector<uint64_t> pu(n1), pv(n2);
+            uint64_t x = 1;
+            for (auto &v : pu) {
+                v = x;
+                x = gl::mul(x, post_base);
+            }
+            const uint64_t pb1 = gl::pow(post_base, n1);
+            x = 1;
+            for (auto &v : pv) {
+                v = x;
+                x = gl::mul(x, pb1);
+            }
+            TRY(upload_vec(ctx, &t.post_u, pu));
+            TRY(upload_vec(ctx, &t.post_v, pv));
+        }
+    }
+    auto ins = ctx->plans.emplace(key, t);
+    *out = &ins.first->second;
+    return AERO_OK;
+}
+
+static aero_status plan_intt(aero_ctx *ctx, int logn, bool input_mont, const DftTables **out) {
+    char key[64];
+    snprintf(key, sizeof key, "intt/%d/%d", logn, (int)input_mont);
+    uint64_t c = gl::inv((1ULL << logn) % gl::P);
+    if (input_mont) c = gl::mul(c, gl::MONT_R_INV);  // the DFT is linear: fold x*2^-64 into 1/n
+    return get_plan(ctx, key, logn, true, {1}, c, 0, out);
+}
+static std::vector<uint64_t> coset_shifts(int logn, int log_blowup, uint64_t offset) {
+    // coset r holds natural rows k = B*i + r : x = offset * g_N^(B*i + r) = (offset * g_N^r) * g_n^i
+    const uint64_t gN = gl::root_of_unity(logn + log_blowup);
+    std::vector<uint64_t> s(1ULL << log_blowup);
+    uint64_t x = offset;
+    for (auto &v : s) {
+        v = x;
+        x = gl::mul(x, gN);
+    }
+    return s;
+}
+static aero_status plan_lde(aero_ctx *ctx, int logn, int log_blowup, bool input_mont, const DftTables **out) {
+    char key[64];
+    snprintf(key, sizeof key, "lde/%d/%d/%d", logn, log_blowup, (int)input_mont);
+    return get_plan(ctx, key, logn, false, coset_shifts(logn, log_blowup, gl::GENERATOR),
+                    input_mont ? gl::MONT_R_INV : 1, 0, out);
+}
+// interpolate_poly_with_offset (fft/serial.rs:86-103): coeff[i] = (1/N) offset^-i IDFT(ev)[i]
+static aero_status plan_coset_intt(aero_ctx *ctx, int logN, bool input_mont, const DftTables **out) {
+    char key[64];
+    snprintf(key, sizeof key, "cintt/%d/%d", logN, (int)input_mont);
+    uint64_t c = gl::inv((1ULL << logN) % gl::P);
+    if (input_mont) c = gl::mul(c, gl::MONT_R_INV);
+    return get_plan(ctx, key, logN, true, {1}, c, gl::inv(gl::GENERATOR), out);
+}
+static aero_status get_pow_table(aero_ctx *ctx, const std::string &key, uint64_t base, int total_bits,
+                                 uint64_t hi_scale, PowTable *out) {
+    auto it = ctx->pow_tables.find(key);
+    if (it == ctx->pow_tables.end()) {
+        PowTableOwned o;
+        o.lo_bits = (total_bits + 1) / 2;
+        std::vector<uint64_t> lo, hi;
+        fill_pow_table(lo, hi, base, total_bits, o.lo_bits, hi_scale);
+        TRY(upload_vec(ctx, &o.lo, lo));
+        TRY(upload_vec(ctx, &o.hi, hi));
+        it = ctx->pow_tables.emplace(key, o).first;
+    }
+    *out = it->second.view();
+    return AERO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// segment
+// -------------------------------------------------------------------------------------------------
+struct aero_segment {
+    aero_ctx *ctx = nullptr;
+    int ncols = 0, logn = 0, log_blowup = -1;  // log_blowup < 0: polys only, not yet extended
+    uint64_t *polys = nullptr;                 // ncols x n, canonical coefficients
+    uint64_t *lde = nullptr;                   // ncols x N, coset-major (coset r, i) -> natural B*i + r
+    uint32_t *full = nullptr;                  // 2N digests, heap layout, leaf k at N + k
+    uint64_t n() const { return 1ULL << logn; }
+    uint64_t N() const { return 1ULL << (logn + log_blowup); }
+};
+
+static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint8_t root[32]) {
+    aero_ctx *ctx = seg->ctx;
+    if (seg->lde) CTX_FAIL(ctx, AERO_ERR_STATE, "segment already committed");
+    if (log_blowup < 1 || log_blowup > 6) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "blowup must be 2..64");
+    if (seg->logn + log_blowup > 31) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "LDE domain too large");
+    seg->log_blowup = log_blowup;
+    const uint64_t n = seg->n(), N = seg->N();
+    const int B = 1 << log_blowup;
+    TRY(dev_alloc(ctx, (void **)&seg->lde, (size_t)seg->ncols * N * 8));
+    TRY(dev_alloc(ctx, (void **)&seg->full, (size_t)2 * N * 32));
+    const DftTables *plan;
+    TRY(plan_lde(ctx, seg->logn, log_blowup, false, &plan));
+    {
+        char nm[32];
+        snprintf(nm, sizeof nm, "lde_w%d", seg->ncols);
+        PhaseTimer t(ctx, nm);
+        int batch = seg->ncols;
+        uint64_t *tmp = nullptr;
+        if (plan->log1 != 0) {
+            batch = (int)std::max<size_t>(1, ctx->lde_batch_bytes / ((size_t)B * n * 8));
+            batch = std::min(batch, seg->ncols);
+            TRY(dev_alloc(ctx, (void **)&tmp, (size_t)batch * B * n * 8));
+        }
+        for (int c0 = 0; c0 < seg->ncols; c0 += batch) {
+            DftLaunch l;
+            l.src = seg->polys + (size_t)c0 * n;
+            l.dst = seg->lde + (size_t)c0 * N;
+            l.tmp = tmp;
+            l.src_col_stride = n;
+            l.dst_col_stride = N;
+            l.ncols = std::min(batch, seg->ncols - c0);
+            l.deinterleave_log = 0;
+            dft_run(*plan, l, ctx->stream);
+        }
+        dev_free(ctx, tmp);
+    }
+    {
+        char nm[32];
+        snprintf(nm, sizeof nm, "hash_rows_w%d", seg->ncols);
+        PhaseTimer t(ctx, nm);
+        hash_rows_lde(seg->lde, N, seg->ncols, seg->logn, log_blowup, 0, (uint32_t)N, seg->full + (size_t)N * 8,
+                      ctx->stream);
+    }
+    {
+        PhaseTimer t(ctx, "merkle");
+        CUDA_TRY(ctx, cudaMemsetAsync(seg->full, 0, 64, ctx->stream));
+        merkle_build(seg->full, N, ctx->stream);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (root) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(root, seg->full + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return AERO_OK;
+}
+
+// d_src: ncols columns (stride src_stride) of n values in ABI form, on the device
+static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, size_t src_stride, uint32_t n_cols,
+                                       uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
+                                       uint8_t root[32]) {
+    if (!out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null output handle");
+    if (n_cols == 0 || n_cols > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of columns must be 1..255, got %u", n_cols);
+    // Matrix::new (prover/src/matrix.rs:41-64): at least two rows, power of two
+    if (n_rows < 2 || !is_pow2(n_rows)) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of rows must be a power of two >= 2, got %llu", (unsigned long long)n_rows);
+    if (!is_pow2(blowup) || blowup < 2) CTX_FAIL(ctx, AERO_ERR_INVALID, "blowup factor must be a power of two >= 2, got %u", blowup);
+    const int logn = ilog2(n_rows);
+    if (logn > NTT_MAX_LOG) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "trace length 2^%d unsupported (max 2^%d)", logn, NTT_MAX_LOG);
+    aero_segment *seg = new aero_segment();
+    seg->ctx = ctx;
+    seg->ncols = (int)n_cols;
+    seg->logn = logn;
+    const bool mont = ctx->form == AERO_FORM_MONTGOMERY;
+    aero_status st = dev_alloc(ctx, (void **)&seg->polys, (size_t)n_cols * n_rows * 8);
+    if (st == AERO_OK) {
+        if (input_is_coeffs) {
+            PhaseTimer t(ctx, "convert");
+            if (src_stride == n_rows) {
+                if (mont) convert_form(d_src, seg->polys, (size_t)n_cols * n_rows, 0, ctx->stream);
+                else st = cudaMemcpyAsync(seg->polys, d_src, (size_t)n_cols * n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream) == cudaSuccess ? AERO_OK : AERO_ERR_CUDA;
+            } else {
+                for (uint32_t c = 0; c < n_cols; c++) {
+                    if (mont) convert_form(d_src + c * src_stride, seg->polys + (size_t)c * n_rows, n_rows, 0, ctx->stream);
+                    else cudaMemcpyAsync(seg->polys + (size_t)c * n_rows, d_src + c * src_stride, n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+                }
+            }
+        } else {
+            const DftTables *plan;
+            st = plan_intt(ctx, logn, mont, &plan);
+            if (st == AERO_OK) {
+                char nm[32];
+                snprintf(nm, sizeof nm, "interpolate_w%d", (int)n_cols);
+                PhaseTimer t(ctx, nm);
+                uint64_t *tmp = nullptr;
+                if (plan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp, (size_t)n_cols * n_rows * 8);
+                if (st == AERO_OK) {
+                    DftLaunch l;
+                    l.src = d_src;
+                    l.dst = seg->polys;
+                    l.tmp = tmp;
+                    l.src_col_stride = src_stride;
+                    l.dst_col_stride = n_rows;
+                    l.ncols = (int)n_cols;
+                    l.deinterleave_log = 0;
+                    dft_run(*plan, l, ctx->stream);
+                    dev_free(ctx, tmp);
+                }
+            }
+        }
+    }
+    if (st == AERO_OK && blowup) st = segment_extend_commit(seg, ilog2(blowup), root);
+    if (st != AERO_OK) {
+        aero_segment_destroy(seg);
+        return st;
+    }
+    *out = seg;
+    return AERO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Merkle batch-proof index list (crypto/src/merkle/mod.rs:188-250 restated over heap indices:
+// leaf i is full[N + i], internal node j is full[j])
+// -------------------------------------------------------------------------------------------------
+static aero_status batch_proof_indices(aero_ctx *ctx, const uint64_t *positions, uint32_t n_pos, uint64_t N,
+                                       std::vector<std::vector<uint32_t>> &out) {
+    if (n_pos == 0) CTX_FAIL(ctx, AERO_ERR_INVALID, "at least one index is required");          // TooFewLeafIndexes
+    if (n_pos > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "at most 255 indexes are allowed");        // TooManyLeafIndexes
+    std::set<uint64_t> index_set;
+    for (uint32_t i = 0; i < n_pos; i++) {
+        if (positions[i] >= N) CTX_FAIL(ctx, AERO_ERR_INVALID, "leaf index %llu out of bounds (%llu leaves)", (unsigned long long)positions[i], (unsigned long long)N);
+        if (!index_set.insert(positions[i]).second) CTX_FAIL(ctx, AERO_ERR_INVALID, "duplicate leaf index %llu", (unsigned long long)positions[i]);
+    }
+    std::set<uint64_t> norm;
+    for (uint32_t i = 0; i < n_pos; i++) norm.insert(positions[i] & ~1ULL);
+    out.clear();
+    std::vector<uint64_t> next;
+    for (uint64_t index : norm) {
+        std::vector<uint32_t> v;
+        for (uint64_t i = index; i < index + 2; i++)
+            if (!index_set.count(i)) v.push_back((uint32_t)(N + i));
+        out.push_back(v);
+        next.push_back((index + N) >> 1);
+    }
+    const int depth = ilog2(N);
+    for (int d = 1; d < depth; d++) {
+        std::vector<uint64_t> cur;
+        cur.swap(next);
+        for (size_t i = 0; i < cur.size(); i++) {
+            const uint64_t sib = cur[i] ^ 1;
+            if (i + 1 < cur.size() && cur[i + 1] == sib) {
+                i++;
+            } else {
+                out[i].push_back((uint32_t)sib);
+            }
+            next.push_back(sib >> 1);
+        }
+    }
+    return AERO_OK;
+}
+// NOTE: in the reference loop `nodes[i].push(...)` uses the position i inside the *current* level's
+// index list (merkle/mod.rs:226-240), including after `i += 1` skipped a sibling; the loop above
+// mirrors that: when a sibling pair is merged, `i` has already advanced, exactly as in the Rust.
+
+static aero_status fetch_batch_proof(aero_ctx *ctx, const uint32_t *full, const std::vector<std::vector<uint32_t>> &idx,
+                                     std::vector<uint8_t> &bytes) {
+    std::vector<uint32_t> flat;
+    for (auto &v : idx) flat.insert(flat.end(), v.begin(), v.end());
+    std::vector<uint8_t> dig(flat.size() * 32);
+    if (!flat.empty()) {
+        uint32_t *d_idx = nullptr, *d_out = nullptr;
+        TRY(dev_alloc(ctx, (void **)&d_idx, flat.size() * 4));
+        TRY(dev_alloc(ctx, (void **)&d_out, flat.size() * 32));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_idx, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        gather_digests(full, d_idx, (int)flat.size(), d_out, ctx->stream);
+        CUDA_TRY(ctx, cudaMemcpyAsync(dig.data(), d_out, dig.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        dev_free(ctx, d_idx);
+        dev_free(ctx, d_out);
+    }
+    // BatchMerkleProof::serialize_nodes (merkle/proofs.rs:421-439)
+    bytes.clear();
+    bytes.push_back((uint8_t)idx.size());
+    size_t off = 0;
+    for (auto &v : idx) {
+        if (v.size() > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "too many nodes in a batch proof vector");
+        bytes.push_back((uint8_t)v.size());
+        bytes.insert(bytes.end(), dig.begin() + off * 32, dig.begin() + (off + v.size()) * 32);
+        off += v.size();
+    }
+    return AERO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// FRI handle
+// -------------------------------------------------------------------------------------------------
+struct FriLayerDev {
+    uint64_t *evals = nullptr;  // M evaluations
+    uint32_t M = 0;
+    int log_cosets = 0;         // storage layout of evals
+    uint32_t *full = nullptr;   // 2*rows digests
+};
+struct aero_fri {
+    aero_ctx *ctx = nullptr;
+    std::vector<FriLayerDev> layers;  // committed layers
+    uint64_t *cur = nullptr;
+    uint32_t curM = 0;
+    int cur_log_cosets = 0;
+    bool cur_committed = false;
+};
+
+// -------------------------------------------------------------------------------------------------
+// extern "C"
+// -------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *aero_version(void) { return "aero_b200 0.1 (sm_100a)"; }
+uint64_t aero_launch_count(void) { return aero::g_launch_count; }
+
+aero_status aero_ctx_create(const int *device_ids, int n_devices, aero_ctx **out) {
+    if (!out) return AERO_ERR_INVALID;
+    *out = nullptr;
+    if (n_devices != 1 && !(n_devices == 0 && device_ids == nullptr)) return AERO_ERR_UNSUPPORTED;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return AERO_ERR_CUDA;  // no CPU fallback
+    int dev = 0;
+    if (device_ids) dev = device_ids[0];
+    else if (cudaGetDevice(&dev) != cudaSuccess) return AERO_ERR_CUDA;
+    if (dev < 0 || dev >= count) return AERO_ERR_INVALID;
+    if (cudaSetDevice(dev) != cudaSuccess) return AERO_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return AERO_ERR_CUDA;
+    if (prop.major < 10) return AERO_ERR_UNSUPPORTED;  // kernels are built for sm_100a only
+    aero_ctx *ctx = new aero_ctx();
+    ctx->device = dev;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = ~0ULL;  // keep freed blocks cached: segments are re-created every proof
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return AERO_OK;
+}
+void aero_ctx_destroy(aero_ctx *ctx) {
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    profile_flush(ctx);
+    for (void *p : ctx->owned) cudaFree(p);
+    delete ctx;
+}
+const char *aero_last_error(aero_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+aero_status aero_ctx_set_stream(aero_ctx *ctx, void *s) {
+    if (!ctx) return AERO_ERR_INVALID;
+    ctx->stream = (cudaStream_t)s;
+    return AERO_OK;
+}
+aero_status aero_ctx_set_form(aero_ctx *ctx, int form) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (form != AERO_FORM_MONTGOMERY && form != AERO_FORM_CANONICAL) CTX_FAIL(ctx, AERO_ERR_INVALID, "unknown element form %d", form);
+    ctx->form = form;
+    return AERO_OK;
+}
+int aero_ctx_get_form(aero_ctx *ctx) { return ctx ? ctx->form : -1; }
+void aero_ctx_set_error(aero_ctx *ctx, const char *msg) {
+    if (ctx) ctx->err = msg ? msg : "";
+}
+aero_status aero_ctx_profile_enable(aero_ctx *ctx, int enable) {
+    if (!ctx) return AERO_ERR_INVALID;
+    ctx->profile = enable != 0;
+    return AERO_OK;
+}
+aero_status aero_ctx_profile_read(aero_ctx *ctx, char *json_out, size_t *len) {
+    if (!ctx || !len) return AERO_ERR_INVALID;
+    profile_flush(ctx);
+    std::string s = "{";
+    bool first = true;
+    for (auto &kv : ctx->stats) {
+        char b[160];
+        snprintf(b, sizeof b, "%s\"%s\": [%d, %.6f]", first ? "" : ", ", kv.first.c_str(), kv.second.calls, kv.second.ms);
+        s += b;
+        first = false;
+    }
+    s += "}";
+    if (!json_out || *len < s.size() + 1) {
+        *len = s.size() + 1;
+        CTX_FAIL(ctx, AERO_ERR_BUFFER, "profile buffer too small");
+    }
+    memcpy(json_out, s.c_str(), s.size() + 1);
+    *len = s.size() + 1;
+    ctx->stats.clear();
+    return AERO_OK;
+}
+
+aero_status aero_device_alloc(aero_ctx *ctx, size_t bytes, void **d_ptr) {
+    if (!ctx || !d_ptr) return AERO_ERR_INVALID;
+    CUDA_TRY(ctx, cudaMalloc(d_ptr, bytes ? bytes : 8));
+    return AERO_OK;
+}
+aero_status aero_device_free(aero_ctx *ctx, void *d_ptr) {
+    if (!ctx) return AERO_ERR_INVALID;
+    CUDA_TRY(ctx, cudaFree(d_ptr));
+    return AERO_OK;
+}
+aero_status aero_device_upload(aero_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    if (!ctx) return AERO_ERR_INVALID;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return AERO_OK;
+}
+aero_status aero_device_download(aero_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+    if (!ctx) return AERO_ERR_INVALID;
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return AERO_OK;
+}
+aero_status aero_device_sync(aero_ctx *ctx) {
+    if (!ctx) return AERO_ERR_INVALID;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return AERO_OK;
+}
+
+// ---- segments -------------------------------------------------------------------------------
+aero_status aero_segment_commit_device(aero_ctx *ctx, const uint64_t *d_cols, size_t col_stride, uint32_t n_cols,
+                                       uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
+                                       uint8_t root[32]) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (!d_cols) CTX_FAIL(ctx, AERO_ERR_INVALID, "null matrix");
+    if (col_stride < n_rows) CTX_FAIL(ctx, AERO_ERR_INVALID, "column stride smaller than the number of rows");
+    return segment_from_device(ctx, d_cols, col_stride, n_cols, n_rows, blowup, input_is_coeffs, out, root);
+}
+
+aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint32_t n_cols, uint64_t n_rows,
+                                uint32_t blowup, int input_is_coeffs, aero_segment **out, uint8_t root[32]) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (!cols) CTX_FAIL(ctx, AERO_ERR_INVALID, "null matrix");
+    if (n_cols == 0 || n_cols > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of columns must be 1..255, got %u", n_cols);
+    if (n_rows < 2 || !is_pow2(n_rows)) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of rows must be a power of two >= 2, got %llu", (unsigned long long)n_rows);
+    uint64_t *stage = nullptr;
+    TRY(dev_alloc(ctx, (void **)&stage, (size_t)n_cols * n_rows * 8));
+    {
+        PhaseTimer t(ctx, "h2d");
+        for (uint32_t c = 0; c < n_cols; c++) {
+            if (!cols[c]) {
+                dev_free(ctx, stage);
+                CTX_FAIL(ctx, AERO_ERR_INVALID, "null column %u", c);
+            }
+            CUDA_TRY(ctx, cudaMemcpyAsync(stage + (size_t)c * n_rows, cols[c], n_rows * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    aero_status st = segment_from_device(ctx, stage, n_rows, n_cols, n_rows, blowup, input_is_coeffs, out, root);
+    dev_free(ctx, stage);
+    return st;
+}
+
+void aero_segment_destroy(aero_segment *seg) {
+    if (!seg) return;
+    dev_free(seg->ctx, seg->polys);
+    dev_free(seg->ctx, seg->lde);
+    dev_free(seg->ctx, seg->full);
+    delete seg;
+}
+aero_status aero_segment_info(aero_segment *seg, uint32_t *n_cols, uint64_t *n_rows, uint32_t *blowup) {
+    if (!seg) return AERO_ERR_INVALID;
+    if (n_cols) *n_cols = (uint32_t)seg->ncols;
+    if (n_rows) *n_rows = seg->n();
+    if (blowup) *blowup = seg->log_blowup < 0 ? 0 : (1u << seg->log_blowup);
+    return AERO_OK;
+}
+aero_status aero_segment_commit_polys(aero_segment *seg, uint32_t blowup, uint8_t root[32]) {
+    if (!seg) return AERO_ERR_INVALID;
+    if (!is_pow2(blowup) || blowup < 2) CTX_FAIL(seg->ctx, AERO_ERR_INVALID, "blowup factor must be a power of two >= 2, got %u", blowup);
+    return segment_extend_commit(seg, ilog2(blowup), root);
+}
+
+aero_status aero_segment_download_lde(aero_segment *seg, uint64_t *const *cols_out) {
+    if (!seg || !cols_out) return AERO_ERR_INVALID;
+    aero_ctx *ctx = seg->ctx;
+    if (!seg->lde) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no LDE");
+    const uint64_t N = seg->N();
+    PhaseTimer t(ctx, "download_lde");
+    uint64_t *tmp = nullptr;
+    TRY(dev_alloc(ctx, (void **)&tmp, N * 8));
+    for (int c = 0; c < seg->ncols; c++) {
+        lde_to_natural(seg->lde + (size_t)c * N, tmp, seg->logn, seg->log_blowup, ctx->form == AERO_FORM_MONTGOMERY, ctx->stream);
+        CUDA_TRY(ctx, cudaMemcpyAsync(cols_out[c], tmp, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, tmp);
+    return AERO_OK;
+}
+aero_status aero_segment_download_polys(aero_segment *seg, uint64_t *const *cols_out) {
+    if (!seg || !cols_out) return AERO_ERR_INVALID;
+    aero_ctx *ctx = seg->ctx;
+    const uint64_t n = seg->n();
+    uint64_t *tmp = nullptr;
+    const bool mont = ctx->form == AERO_FORM_MONTGOMERY;
+    if (mont) TRY(dev_alloc(ctx, (void **)&tmp, n * 8));
+    for (int c = 0; c < seg->ncols; c++) {
+        const uint64_t *src = seg->polys + (size_t)c * n;
+        if (mont) {
+            convert_form(src, tmp, n, 1, ctx->stream);
+            src = tmp;
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(cols_out[c], src, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, tmp);
+    return AERO_OK;
+}
+aero_status aero_segment_download_leaves(aero_segment *seg, uint8_t *leaves_out) {
+    if (!seg || !leaves_out) return AERO_ERR_INVALID;
+    aero_ctx *ctx = seg->ctx;
+    if (!seg->full) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no commitment");
+    const uint64_t N = seg->N();
+    CUDA_TRY(ctx, cudaMemcpyAsync(leaves_out, seg->full + (size_t)N * 8, N * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return AERO_OK;
+}
+
+aero_status aero_segment_open(aero_segment *seg, const uint64_t *positions, uint32_t n_pos, uint64_t *rows_out,
+                              uint8_t *batch_nodes_out, size_t *len) {
+    if (!seg || !positions || !len) return AERO_ERR_INVALID;
+    aero_ctx *ctx = seg->ctx;
+    if (!seg->full) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no commitment");
+    const uint64_t N = seg->N();
+    std::vector<std::vector<uint32_t>> idx;
+    TRY(batch_proof_indices(ctx, positions, n_pos, N, idx));
+    std::vector<uint8_t> bytes;
+    TRY(fetch_batch_proof(ctx, seg->full, idx, bytes));
+    if (!batch_nodes_out || *len < bytes.size()) {
+        *len = bytes.size();
+        CTX_FAIL(ctx, AERO_ERR_BUFFER, "batch proof needs %zu bytes", bytes.size());
+    }
+    memcpy(batch_nodes_out, bytes.data(), bytes.size());
+    *len = bytes.size();
+    if (rows_out) {
+        std::vector<uint32_t> pos(n_pos);
+        for (uint32_t i = 0; i < n_pos; i++) pos[i] = (uint32_t)positions[i];
+        uint32_t *d_pos = nullptr;
+        uint64_t *d_rows = nullptr;
+        TRY(dev_alloc(ctx, (void **)&d_pos, n_pos * 4));
+        TRY(dev_alloc(ctx, (void **)&d_rows, (size_t)n_pos * seg->ncols * 8));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_pos, pos.data(), n_pos * 4, cudaMemcpyHostToDevice, ctx->stream));
+        gather_rows(seg->lde, N, seg->ncols, seg->logn, seg->log_blowup, d_pos, (int)n_pos, d_rows, ctx->stream);
+        CUDA_TRY(ctx, cudaMemcpyAsync(rows_out, d_rows, (size_t)n_pos * seg->ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        dev_free(ctx, d_pos);
+        dev_free(ctx, d_rows);
+    }
+    return AERO_OK;
+}
+
+aero_status aero_commit_rows_device(aero_ctx *ctx, const uint64_t *d_m, size_t col_stride, uint32_t n_cols,
+                                    uint64_t n_rows, uint8_t root[32]) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (!d_m || !root) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (n_cols == 0) CTX_FAIL(ctx, AERO_ERR_INVALID, "matrix must have at least one column");
+    // MerkleTree::new (crypto/src/merkle/mod.rs:108-114): >= 2 leaves, power of two
+    if (n_rows < 2) CTX_FAIL(ctx, AERO_ERR_INVALID, "a Merkle tree needs at least two leaves, got %llu", (unsigned long long)n_rows);
+    if (!is_pow2(n_rows)) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of leaves must be a power of two, got %llu", (unsigned long long)n_rows);
+    if (n_rows > (1ULL << 31)) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "too many rows");
+    uint32_t *full = nullptr;
+    TRY(dev_alloc(ctx, (void **)&full, (size_t)2 * n_rows * 32));
+    {
+        PhaseTimer t(ctx, "hash_rows");
+        hash_rows_natural(d_m, col_stride, (int)n_cols, (uint32_t)n_rows, full + (size_t)n_rows * 8, ctx->stream);
+    }
+    {
+        PhaseTimer t(ctx, "merkle");
+        merkle_build(full, n_rows, ctx->stream);
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(root, full + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, full);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return AERO_OK;
+}
+
+// ---- constraints ----------------------------------------------------------------------------
+aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_eval_cols, size_t col_stride,
+                                              const aero_divisor *divs, uint32_t n_div, uint64_t ce_domain_size,
+                                              uint64_t trace_len, aero_segment **out) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (!d_eval_cols || !divs || !out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (col_stride < ce_domain_size) CTX_FAIL(ctx, AERO_ERR_INVALID, "column stride smaller than the domain");
+    if (n_div == 0 || n_div > 8) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of divisors must be 1..8, got %u", n_div);
+    if (!is_pow2(ce_domain_size) || !is_pow2(trace_len)) CTX_FAIL(ctx, AERO_ERR_INVALID, "domain sizes must be powers of two");
+    // CompositionPoly::new (composition_poly.rs:21-35): trace length smaller than the polynomial
+    if (trace_len >= ce_domain_size) CTX_FAIL(ctx, AERO_ERR_INVALID, "trace length must be smaller than the constraint evaluation domain");
+    const int logN = ilog2(ce_domain_size), logn = ilog2(trace_len);
+    const uint64_t N = ce_domain_size;
+    const int ncols = (int)(N / trace_len);
+    if (ncols > 64) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "constraint blowup > 64");
+    const bool mont = ctx->form == AERO_FORM_MONTGOMERY;
+    PowTable gN;
+    {
+        char key[32];
+        snprintf(key, sizeof key, "g/%d", logN);
+        TRY(get_pow_table(ctx, key, gl::root_of_unity(logN), logN, 1, &gN));
+    }
+    const uint64_t *cols = d_eval_cols;
+    uint64_t *combined = nullptr;
+    TRY(dev_alloc(ctx, (void **)&combined, N * 8));
+    std::vector<DivisorDev> dd(n_div);
+    std::vector<uint64_t *> zbufs;
+    aero_status st = AERO_OK;
+    {
+        PhaseTimer t(ctx, "constraint_combine");
+        for (uint32_t d = 0; d < n_div && st == AERO_OK; d++) {
+            const aero_divisor &v = divs[d];
+            if (v.a == 0 || !is_pow2(v.a) || v.a > N) { ctx->err = "divisor degree must be a power of two <= domain size"; st = AERO_ERR_INVALID; break; }
+            if (v.n_exemptions > 8) { ctx->err = "at most 8 exemption points"; st = AERO_ERR_INVALID; break; }
+            DivisorDev &o = dd[d];
+            o.a = v.a;
+            o.b = to_canon(ctx, v.b);
+            o.off_pow_a = gl::pow(gl::GENERATOR, v.a);
+            o.nex = v.n_exemptions;
+            for (uint32_t k = 0; k < 8; k++) o.ex[k] = k < v.n_exemptions ? to_canon(ctx, v.exemptions[k]) : 0;
+            o.zn = (uint32_t)(N / v.a);
+            uint64_t *z = nullptr;
+            st = dev_alloc(ctx, (void **)&z, (size_t)o.zn * 8);
+            if (st != AERO_OK) break;
+            zbufs.push_back(z);
+            divisor_inverses(o, z, logN, gN, ctx->stream);
+            o.zinv = z;
+        }
+        if (st == AERO_OK) constraint_combine(cols, col_stride, dd.data(), (int)n_div, logN, gl::GENERATOR, gN, combined, ctx->stream);
+    }
+    aero_segment *seg = nullptr;
+    if (st == AERO_OK) {
+        seg = new aero_segment();
+        seg->ctx = ctx;
+        seg->ncols = ncols;
+        seg->logn = logn;
+        st = dev_alloc(ctx, (void **)&seg->polys, N * 8);
+    }
+    if (st == AERO_OK) {
+        const DftTables *plan;
+        st = plan_coset_intt(ctx, logN, mont, &plan);
+        if (st == AERO_OK) {
+            PhaseTimer t(ctx, "composition_poly");
+            uint64_t *tmp = nullptr;
+            if (plan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp, N * 8);
+            if (st == AERO_OK) {
+                DftLaunch l;
+                l.src = combined;
+                l.dst = seg->polys;
+                l.tmp = tmp;
+                l.src_col_stride = N;
+                l.dst_col_stride = N;
+                l.ncols = 1;
+                l.deinterleave_log = ilog2((uint64_t)ncols);  // coefficient i -> column i % ncols, row i / ncols
+                dft_run(*plan, l, ctx->stream);
+                dev_free(ctx, tmp);
+            }
+        }
+    }
+    for (auto z : zbufs) dev_free(ctx, z);
+    dev_free(ctx, combined);
+    if (st == AERO_OK && cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch failed in constraints_into_poly"; st = AERO_ERR_CUDA; }
+    if (st != AERO_OK) {
+        aero_segment_destroy(seg);
+        return st;
+    }
+    *out = seg;
+    return AERO_OK;
+}
+
+aero_status aero_constraints_into_poly(aero_ctx *ctx, const uint64_t *const *eval_cols, const aero_divisor *divs,
+                                       uint32_t n_div, uint64_t ce_domain_size, uint64_t trace_len,
+                                       aero_segment **out) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (!eval_cols || !divs || !out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (n_div == 0 || n_div > 8) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of divisors must be 1..8, got %u", n_div);
+    if (!is_pow2(ce_domain_size)) CTX_FAIL(ctx, AERO_ERR_INVALID, "domain sizes must be powers of two");
+    const uint64_t N = ce_domain_size;
+    uint64_t *cols = nullptr;
+    TRY(dev_alloc(ctx, (void **)&cols, (size_t)n_div * N * 8));
+    {
+        PhaseTimer t(ctx, "h2d");
+        for (uint32_t d = 0; d < n_div; d++)
+            CUDA_TRY(ctx, cudaMemcpyAsync(cols + (size_t)d * N, eval_cols[d], N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    aero_status st = aero_constraints_into_poly_device(ctx, cols, N, divs, n_div, ce_domain_size, trace_len, out);
+    dev_free(ctx, cols);
+    return st;
+}
+
+// ---- OOD + DEEP -----------------------------------------------------------------------------
+static aero_status ood_one(aero_ctx *ctx, aero_segment *seg, const std::vector<uint64_t> &points, uint64_t *host_out /* npoints x ncols */) {
+    const int logn = seg->logn;
+    const int np = (int)points.size();
+    const uint64_t n = seg->n();
+    const int chunk_len = n < 4096 ? (int)n : 4096;
+    const int nchunks = (int)(n / chunk_len);
+    const int stride = 257 + nchunks;
+    std::vector<uint64_t> tab((size_t)np * stride);
+    for (int p = 0; p < np; p++) {
+        uint64_t *t = tab.data() + (size_t)p * stride;
+        uint64_t x = 1;
+        for (int i = 0; i <= 256; i++) {
+            t[i] = x;
+            x = gl::mul(x, points[p]);
+        }
+        const uint64_t xc = gl::pow(points[p], (uint64_t)chunk_len);
+        x = 1;
+        for (int c = 0; c < nchunks; c++) {
+            t[257 + c] = x;
+            x = gl::mul(x, xc);
+        }
+    }
+    uint64_t *d_tab = nullptr, *d_out = nullptr, *d_scr = nullptr;
+    TRY(dev_alloc(ctx, (void **)&d_tab, tab.size() * 8));
+    TRY(dev_alloc(ctx, (void **)&d_out, (size_t)seg->ncols * np * 8));
+    TRY(dev_alloc(ctx, (void **)&d_scr, ood_scratch_elems(seg->ncols, logn, np) * 8));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ood_eval(seg->polys, n, seg->ncols, logn, d_tab, np, d_out, d_scr, ctx->stream);
+    std::vector<uint64_t> res((size_t)seg->ncols * np);
+    CUDA_TRY(ctx, cudaMemcpyAsync(res.data(), d_out, res.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < seg->ncols; c++)
+        for (int p = 0; p < np; p++) host_out[(size_t)p * seg->ncols + c] = res[(size_t)c * np + p];
+    dev_free(ctx, d_tab);
+    dev_free(ctx, d_out);
+    dev_free(ctx, d_scr);
+    return AERO_OK;
+}
+
+aero_status aero_ood_eval(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs, aero_segment *comp,
+                          uint64_t z, uint64_t *out_trace, uint64_t *out_comp) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (n_trace_segs && (!trace_segs || !out_trace)) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    PhaseTimer t(ctx, "ood_eval");
+    const uint64_t zc = to_canon(ctx, z);
+    if (n_trace_segs) {
+        int W = 0;
+        for (uint32_t s = 0; s < n_trace_segs; s++) {
+            if (!trace_segs[s] || trace_segs[s]->logn != trace_segs[0]->logn) CTX_FAIL(ctx, AERO_ERR_INVALID, "trace segments must have equal length");
+            W += trace_segs[s]->ncols;
+        }
+        const uint64_t g = gl::root_of_unity(trace_segs[0]->logn);
+        std::vector<uint64_t> pts = {zc, gl::mul(zc, g)};
+        int off = 0;
+        for (uint32_t s = 0; s < n_trace_segs; s++) {
+            std::vector<uint64_t> tmp((size_t)2 * trace_segs[s]->ncols);
+            TRY(ood_one(ctx, trace_segs[s], pts, tmp.data()));
+            for (int c = 0; c < trace_segs[s]->ncols; c++) {
+                out_trace[off + c] = from_canon(ctx, tmp[c]);
+                out_trace[W + off + c] = from_canon(ctx, tmp[trace_segs[s]->ncols + c]);
+            }
+            off += trace_segs[s]->ncols;
+        }
+    }
+    if (comp) {
+        if (!out_comp) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+        std::vector<uint64_t> pts = {gl::pow(zc, (uint64_t)comp->ncols)};
+        std::vector<uint64_t> tmp(comp->ncols);
+        TRY(ood_one(ctx, comp, pts, tmp.data()));
+        for (int c = 0; c < comp->ncols; c++) out_comp[c] = from_canon(ctx, tmp[c]);
+    }
+    return AERO_OK;
+}
+
+aero_status aero_deep_compose(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs,
+                              aero_segment *comp, uint64_t z, const uint64_t *ood_trace, const uint64_t *ood_comp,
+                              const uint64_t *cc, aero_fri **out) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (!trace_segs || !n_trace_segs || !comp || !ood_trace || !ood_comp || !cc || !out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (n_trace_segs > 4) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "at most 4 trace segments");
+    const int logn = trace_segs[0]->logn;
+    const int log_blowup = trace_segs[0]->log_blowup;
+    if (log_blowup < 1) CTX_FAIL(ctx, AERO_ERR_STATE, "trace segments must be committed first");
+    int W = 0;
+    for (uint32_t s = 0; s < n_trace_segs; s++) {
+        if (trace_segs[s]->logn != logn) CTX_FAIL(ctx, AERO_ERR_INVALID, "trace segments must have equal length");
+        W += trace_segs[s]->ncols;
+    }
+    if (comp->logn != logn) CTX_FAIL(ctx, AERO_ERR_INVALID, "composition columns must have trace length");
+    const int m = comp->ncols;
+    const uint64_t n = 1ULL << logn;
+    const uint64_t zc = to_canon(ctx, z);
+    const uint64_t g = gl::root_of_unity(logn);
+    const uint64_t zg = gl::mul(zc, g), zm = gl::pow(zc, (uint64_t)m);
+    // coefficient vector for the kernel: (cc_i.0, cc_i.1) per trace column, then cc'_j
+    std::vector<uint64_t> h_cc((size_t)2 * W + m);
+    uint64_t k1 = 0, k2 = 0, kh = 0;
+    for (int i = 0; i < W; i++) {
+        const uint64_t c0 = to_canon(ctx, cc[3 * i]), c1 = to_canon(ctx, cc[3 * i + 1]);
+        h_cc[2 * i] = c0;
+        h_cc[2 * i + 1] = c1;
+        k1 = gl::add(k1, gl::mul(c0, to_canon(ctx, ood_trace[i])));       // acc_trace_poly, composer/mod.rs:286
+        k2 = gl::add(k2, gl::mul(c1, to_canon(ctx, ood_trace[W + i])));
+    }
+    for (int j = 0; j < m; j++) {
+        const uint64_t c = to_canon(ctx, cc[3 * W + j]);
+        h_cc[2 * W + j] = c;
+        kh = gl::add(kh, gl::mul(c, to_canon(ctx, ood_comp[j])));
+    }
+    const uint64_t d0 = to_canon(ctx, cc[3 * W + m]), d1 = to_canon(ctx, cc[3 * W + m + 1]);
+    const uint64_t h_consts[3] = {k1, k2, kh};
+
+    uint64_t *d_cc = nullptr, *d_consts = nullptr, *t1 = nullptr, *t2 = nullptr, *hh = nullptr, *carry = nullptr, *coeffs = nullptr;
+    TRY(dev_alloc(ctx, (void **)&d_cc, h_cc.size() * 8));
+    TRY(dev_alloc(ctx, (void **)&d_consts, 3 * 8));
+    TRY(dev_alloc(ctx, (void **)&t1, n * 8));
+    TRY(dev_alloc(ctx, (void **)&t2, n * 8));
+    TRY(dev_alloc(ctx, (void **)&hh, n * 8));
+    TRY(dev_alloc(ctx, (void **)&coeffs, n * 8));
+    TRY(dev_alloc(ctx, (void **)&carry, (6 * (n / 256 + 1)) * 8));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_cc, h_cc.data(), h_cc.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_consts, h_consts, 24, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        PhaseTimer t(ctx, "deep_compose");
+        DeepSegs segs;
+        segs.nseg = (int)n_trace_segs;
+        for (uint32_t s = 0; s < n_trace_segs; s++) {
+            segs.p[s] = trace_segs[s]->polys;
+            segs.ncols[s] = trace_segs[s]->ncols;
+        }
+        deep_accumulate(segs, comp->polys, m, logn, d_cc, d_consts, t1, t2, hh, ctx->stream);
+        const uint64_t bs[3] = {zc, zg, zm};
+        syn_div3(t1, t2, hh, logn, bs, carry, ctx->stream);
+        deep_finish(t1, t2, hh, logn, d0, d1, coeffs, ctx->stream);
+    }
+    aero_fri *fri = new aero_fri();
+    fri->ctx = ctx;
+    const uint64_t N = n << log_blowup;
+    aero_status st = dev_alloc(ctx, (void **)&fri->cur, N * 8);
+    if (st == AERO_OK) {
+        const DftTables *plan;
+        st = plan_lde(ctx, logn, log_blowup, false, &plan);
+        if (st == AERO_OK) {
+            PhaseTimer t(ctx, "deep_lde");
+            uint64_t *tmp = nullptr;
+            if (plan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp, N * 8);
+            if (st == AERO_OK) {
+                DftLaunch l;
+                l.src = coeffs;
+                l.dst = fri->cur;
+                l.tmp = tmp;
+                l.src_col_stride = n;
+                l.dst_col_stride = N;
+                l.ncols = 1;
+                l.deinterleave_log = 0;
+                dft_run(*plan, l, ctx->stream);
+                dev_free(ctx, tmp);
+            }
+        }
+    }
+    fri->curM = (uint32_t)N;
+    fri->cur_log_cosets = log_blowup;
+    dev_free(ctx, d_cc);
+    dev_free(ctx, d_consts);
+    dev_free(ctx, t1);
+    dev_free(ctx, t2);
+    dev_free(ctx, hh);
+    dev_free(ctx, carry);
+    dev_free(ctx, coeffs);
+    if (st == AERO_OK && cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch failed in deep_compose"; st = AERO_ERR_CUDA; }
+    if (st != AERO_OK) {
+        aero_fri_destroy(fri);
+        return st;
+    }
+    *out = fri;
+    return AERO_OK;
+}
+
+// ---- FRI ------------------------------------------------------------------------------------
+aero_status aero_fri_from_evaluations(aero_ctx *ctx, const uint64_t *evaluations, uint64_t count, aero_fri **out) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (!evaluations || !out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (!is_pow2(count) || count < 16 || count > (1ULL << 31)) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of evaluations must be a power of two >= 16");
+    aero_fri *fri = new aero_fri();
+    fri->ctx = ctx;
+    aero_status st = dev_alloc(ctx, (void **)&fri->cur, count * 8);
+    if (st != AERO_OK) { delete fri; return st; }
+    CUDA_TRY(ctx, cudaMemcpyAsync(fri->cur, evaluations, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->form == AERO_FORM_MONTGOMERY) convert_form(fri->cur, fri->cur, count, 0, ctx->stream);
+    fri->curM = (uint32_t)count;
+    fri->cur_log_cosets = 0;
+    *out = fri;
+    return AERO_OK;
+}
+aero_status aero_fri_download_evaluations(aero_fri *fri, uint64_t *out, uint64_t *count) {
+    if (!fri || !count) return AERO_ERR_INVALID;
+    aero_ctx *ctx = fri->ctx;
+    if (!out || *count < fri->curM) {
+        *count = fri->curM;
+        CTX_FAIL(ctx, AERO_ERR_BUFFER, "need room for %u evaluations", fri->curM);
+    }
+    *count = fri->curM;
+    uint64_t *tmp = nullptr;
+    TRY(dev_alloc(ctx, (void **)&tmp, (size_t)fri->curM * 8));
+    const bool mont = ctx->form == AERO_FORM_MONTGOMERY;
+    if (fri->cur_log_cosets) {
+        lde_to_natural(fri->cur, tmp, ilog2(fri->curM) - fri->cur_log_cosets, fri->cur_log_cosets, mont, ctx->stream);
+    } else if (mont) {
+        convert_form(fri->cur, tmp, fri->curM, 1, ctx->stream);
+    } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(tmp, fri->cur, (size_t)fri->curM * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, tmp, (size_t)fri->curM * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, tmp);
+    return AERO_OK;
+}
+
+aero_status aero_fri_commit_layer(aero_fri *fri, uint8_t root[32]) {
+    if (!fri || !root) return AERO_ERR_INVALID;
+    aero_ctx *ctx = fri->ctx;
+    if (!fri->cur) CTX_FAIL(ctx, AERO_ERR_STATE, "no evaluations to commit");
+    if (fri->cur_committed) CTX_FAIL(ctx, AERO_ERR_STATE, "layer already committed; fold first");
+    const uint32_t rows = fri->curM / 8;
+    if (rows < 2) CTX_FAIL(ctx, AERO_ERR_INVALID, "FRI layer of %u evaluations is too small to commit", fri->curM);
+    if (fri->cur_log_cosets && (rows >> fri->cur_log_cosets) == 0) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "layer too small for coset-major layout");
+    FriLayerDev L;
+    L.evals = fri->cur;
+    L.M = fri->curM;
+    L.log_cosets = fri->cur_log_cosets;
+    TRY(dev_alloc(ctx, (void **)&L.full, (size_t)2 * rows * 32));
+    {
+        PhaseTimer t(ctx, "fri_commit");
+        CUDA_TRY(ctx, cudaMemsetAsync(L.full, 0, 64, ctx->stream));
+        fri_leaf_hash(L.evals, rows, L.log_cosets, L.full + (size_t)rows * 8, ctx->stream);
+        merkle_build(L.full, rows, ctx->stream);
+    }
+    fri->layers.push_back(L);
+    fri->cur_committed = true;
+    CUDA_TRY(ctx, cudaMemcpyAsync(root, L.full + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return AERO_OK;
+}
+
+aero_status aero_fri_fold(aero_fri *fri, uint64_t alpha) {
+    if (!fri) return AERO_ERR_INVALID;
+    aero_ctx *ctx = fri->ctx;
+    if (!fri->cur_committed) CTX_FAIL(ctx, AERO_ERR_STATE, "commit the layer before folding it");
+    const uint32_t M = fri->curM, rows = M / 8;
+    const int logM = ilog2(M);
+    PowTable xinv;
+    {
+        // x_j^-1 = (7 * g_M^j)^-1 = 7^-1 * (g_M^-1)^j,  j < rows
+        char key[32];
+        snprintf(key, sizeof key, "xinv/%d", logM);
+        TRY(get_pow_table(ctx, key, gl::inv(gl::root_of_unity(logM)), logM - 3, gl::inv(gl::GENERATOR), &xinv));
+    }
+    const uint64_t w8i = gl::inv(gl::root_of_unity(3));
+    const uint64_t w[4] = {1, w8i, gl::mul(w8i, w8i), gl::mul(gl::mul(w8i, w8i), w8i)};
+    uint64_t *next = nullptr;
+    TRY(dev_alloc(ctx, (void **)&next, (size_t)rows * 8));
+    {
+        PhaseTimer t(ctx, "fri_fold");
+        fri_fold(fri->cur, rows, fri->cur_log_cosets, to_canon(ctx, alpha), xinv, w, gl::inv(8), next, ctx->stream);
+    }
+    fri->cur = next;  // the committed layer keeps ownership of the old buffer
+    fri->curM = rows;
+    fri->cur_log_cosets = 0;
+    fri->cur_committed = false;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return AERO_OK;
+}
+
+// fold_positions (fri/src/folding/mod.rs:159-176)
+static std::vector<uint64_t> fold_positions(const std::vector<uint64_t> &pos, uint64_t source, uint64_t ff) {
+    const uint64_t target = source / ff;
+    std::vector<uint64_t> r;
+    for (uint64_t p : pos) {
+        p %= target;
+        if (std::find(r.begin(), r.end(), p) == r.end()) r.push_back(p);
+    }
+    return r;
+}
+
+aero_status aero_fri_open(aero_fri *fri, const uint64_t *positions, uint32_t n_pos, uint8_t *out_bytes, size_t *len) {
+    if (!fri || !positions || !len) return AERO_ERR_INVALID;
+    aero_ctx *ctx = fri->ctx;
+    if (fri->layers.empty()) CTX_FAIL(ctx, AERO_ERR_STATE, "FRI layers have not been built yet");  // prover/mod.rs:232-235
+    if (n_pos == 0 || n_pos > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of positions must be 1..255");
+    std::vector<uint64_t> pos(positions, positions + n_pos);
+    for (uint64_t p : pos)
+        if (p >= fri->layers[0].M) CTX_FAIL(ctx, AERO_ERR_INVALID, "query position out of range");
+    std::vector<uint8_t> bytes;
+    const size_t nl = fri->layers.size() - 1;
+    bytes.push_back((uint8_t)nl);
+    uint64_t domain = fri->layers[0].M;
+    for (size_t i = 0; i < nl; i++) {
+        const FriLayerDev &L = fri->layers[i];
+        pos = fold_positions(pos, domain, 8);
+        const uint32_t rows = L.M / 8;
+        // queried values: [E; 8] rows at the folded positions, canonical bytes
+        std::vector<uint32_t> p32(pos.begin(), pos.end());
+        uint32_t *d_pos = nullptr;
+        uint64_t *d_vals = nullptr;
+        TRY(dev_alloc(ctx, (void **)&d_pos, p32.size() * 4));
+        TRY(dev_alloc(ctx, (void **)&d_vals, p32.size() * 64));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_pos, p32.data(), p32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        gather_fri_rows(L.evals, rows, L.log_cosets, d_pos, (int)p32.size(), d_vals, ctx->stream);
+        std::vector<uint64_t> vals(p32.size() * 8);
+        CUDA_TRY(ctx, cudaMemcpyAsync(vals.data(), d_vals, vals.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        dev_free(ctx, d_pos);
+        dev_free(ctx, d_vals);
+        std::vector<std::vector<uint32_t>> idx;
+        TRY(batch_proof_indices(ctx, pos.data(), (uint32_t)pos.size(), rows, idx));
+        std::vector<uint8_t> paths;
+        TRY(fetch_batch_proof(ctx, L.full, idx, paths));
+        // FriProofLayer::write_into (fri/src/proof.rs:351-359)
+        const uint32_t vlen = (uint32_t)(vals.size() * 8), plen = (uint32_t)paths.size();
+        bytes.insert(bytes.end(), (uint8_t *)&vlen, (uint8_t *)&vlen + 4);
+        bytes.insert(bytes.end(), (uint8_t *)vals.data(), (uint8_t *)vals.data() + vlen);
+        bytes.insert(bytes.end(), (uint8_t *)&plen, (uint8_t *)&plen + 4);
+        bytes.insert(bytes.end(), paths.begin(), paths.end());
+        domain /= 8;
+    }
+    {
+        // remainder = last committed layer in natural order (prover/mod.rs:258-268 un-transposes
+        // the stored transposed copy; ours is stored natural already)
+        const FriLayerDev &L = fri->layers.back();
+        if (L.log_cosets) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "remainder layer cannot be the DEEP layer");
+        if ((size_t)L.M * 8 > 0xFFFF) CTX_FAIL(ctx, AERO_ERR_INVALID, "remainder too large for the wire format");
+        std::vector<uint64_t> rem(L.M);
+        CUDA_TRY(ctx, cudaMemcpyAsync(rem.data(), L.evals, (size_t)L.M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        const uint16_t rl = (uint16_t)(L.M * 8);
+        bytes.insert(bytes.end(), (uint8_t *)&rl, (uint8_t *)&rl + 2);
+        bytes.insert(bytes.end(), (uint8_t *)rem.data(), (uint8_t *)rem.data() + rl);
+        bytes.push_back(0);  // log2(num_partitions = 1), fri/src/proof.rs:50-52
+    }
+    if (!out_bytes || *len < bytes.size()) {
+        *len = bytes.size();
+        CTX_FAIL(ctx, AERO_ERR_BUFFER, "FRI proof needs %zu bytes", bytes.size());
+    }
+    memcpy(out_bytes, bytes.data(), bytes.size());
+    *len = bytes.size();
+    return AERO_OK;
+}
+
+void aero_fri_destroy(aero_fri *fri) {
+    if (!fri) return;
+    bool cur_owned_by_layer = false;
+    for (auto &L : fri->layers) {
+        if (L.evals == fri->cur) cur_owned_by_layer = true;
+        dev_free(fri->ctx, L.evals);
+        dev_free(fri->ctx, L.full);
+    }
+    if (!cur_owned_by_layer) dev_free(fri->ctx, fri->cur);
+    delete fri;
+}
+
+// ---- grinding -------------------------------------------------------------------------------
+aero_status aero_pow_min_nonce(aero_ctx *ctx, const uint8_t seed[32], uint32_t grinding_bits, uint64_t *nonce) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (!seed || !nonce) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (grinding_bits > 40) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "grinding factor above 40 bits");
+    PhaseTimer t(ctx, "grind");
+    uint32_t *d_seed = nullptr;
+    unsigned long long *d_best = nullptr;
+    TRY(dev_alloc(ctx, (void **)&d_seed, 32));
+    TRY(dev_alloc(ctx, (void **)&d_best, 8));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_seed, seed, 32, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_best, 0xFF, 8, ctx->stream));
+    const uint32_t batch = 1u << 18;
+    uint64_t base = 1;
+    unsigned long long best = ~0ULL;
+    for (;;) {
+        pow_search(d_seed, base, batch, grinding_bits, d_best, ctx->stream);
+        CUDA_TRY(ctx, cudaMemcpyAsync(&best, d_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (best != ~0ULL) break;
+        base += batch;
+    }
+    dev_free(ctx, d_seed);
+    dev_free(ctx, d_best);
+    *nonce = best;
+    return AERO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// Goldilocks field arithmetic for sm_100a kernels and for the host-side driver.
+//
+// p = 2^64 - 2^32 + 1.  The reference (winterfell/math/src/field/f64/mod.rs:37-61) keeps elements
+// in Montgomery form x*2^64 mod p; on the device we keep CANONICAL values in [0, p) because the
+// special form of p makes the plain 128-bit product cheap to reduce (2^64 = 2^32-1, 2^96 = -1
+// mod p) and because hashing (blake2s/mod.rs:52-77) needs canonical bytes anyway.  Conversion
+// happens once at the C-ABI boundary (mont_to_canon / canon_to_mont below, replacing
+// f64/mod.rs:59-61 `new` and :234 `as_int`).  All results are exact, so they equal the
+// reference's canonical values bit for bit.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define GL_HD __host__ __device__ __forceinline__
+#else
+#define GL_HD inline
+#endif
+
+namespace gl {
+
+constexpr uint64_t P = 0xFFFFFFFF00000001ULL;
+constexpr uint64_t EPS = 0xFFFFFFFFULL;            // 2^64 mod p
+constexpr uint64_t GENERATOR = 7;                  // f64/mod.rs:218 (also the LDE/FRI coset offset)
+constexpr uint64_t TWO_ADIC_ROOT = 1753635133440165772ULL;  // f64/mod.rs:43, order 2^32
+constexpr uint64_t MONT_R_INV = 18446744065119617025ULL;    // 2^-64 mod p
+// (2^-64 = 2^128 since 2^192 = 1;  2^128 = (2^96)*(2^32) = -2^32 = p - 2^32)
+
+GL_HD uint64_t add(uint64_t a, uint64_t b) {  // a, b canonical -> canonical  (f64/mod.rs:273)
+    uint64_t s = a + b;
+    bool wrap = (s < a) | (s >= P);
+    return s + (wrap ? EPS : 0ULL);  // s - p == s + EPS (mod 2^64)
+}
+GL_HD uint64_t sub(uint64_t a, uint64_t b) {  // f64/mod.rs:293
+    uint64_t d = a - b;
+    return d - ((a < b) ? EPS : 0ULL);  // d + p == d - EPS (mod 2^64)
+}
+GL_HD uint64_t neg(uint64_t a) { return a ? P - a : 0ULL; }
+
+// 128-bit product {hi,lo} -> canonical.  hi = hh*2^32 + hl:  x = lo - hh + hl*(2^32-1) (mod p)
+GL_HD uint64_t reduce128(uint64_t lo, uint64_t hi) {
+    uint64_t hh = hi >> 32, hl = hi & EPS;
+    uint64_t t0 = lo - hh;
+    if (lo < hh) t0 -= EPS;              // borrow: +p
+    uint64_t t1 = (hl << 32) - hl;       // hl * (2^32-1) < 2^64
+    uint64_t r = t0 + t1;
+    if (r < t0) r += EPS;                // carry: 2^64 = EPS (cannot carry twice: see DESIGN.md)
+    return r >= P ? r - P : r;
+}
+
+GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t &lo, uint64_t &hi) {
+#if defined(__CUDA_ARCH__)
+    // four IMAD.WIDE.U32 with 64-bit accumulate; no partial sum can overflow 64 bits
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    uint64_t p00 = (uint64_t)a0 * b0;
+    uint64_t t = (uint64_t)a0 * b1 + (p00 >> 32);
+    uint64_t u = (uint64_t)a1 * b0 + (t & EPS);
+    hi = (uint64_t)a1 * b1 + (t >> 32) + (u >> 32);
+    lo = (p00 & EPS) | (u << 32);
+#else
+    unsigned __int128 x = (unsigned __int128)a * b;
+    lo = (uint64_t)x;
+    hi = (uint64_t)(x >> 64);
+#endif
+}
+
+GL_HD uint64_t mul(uint64_t a, uint64_t b) {  // f64/mod.rs:311
+    uint64_t lo, hi;
+    mul_wide(a, b, lo, hi);
+    return reduce128(lo, hi);
+}
+GL_HD uint64_t sqr(uint64_t a) { return mul(a, a); }
+
+GL_HD uint64_t pow(uint64_t b, uint64_t e) {  // f64/mod.rs:103 (exp)
+    uint64_t r = 1;
+    while (e) {
+        if (e & 1) r = mul(r, b);
+        b = mul(b, b);
+        e >>= 1;
+    }
+    return r;
+}
+GL_HD uint64_t inv(uint64_t a) { return pow(a, P - 2); }  // f64/mod.rs:120
+
+// StarkField::get_root_of_unity (math/src/field/traits.rs:224-233)
+GL_HD uint64_t root_of_unity(uint32_t log_order) { return pow(TWO_ADIC_ROOT, 1ULL << (32 - log_order)); }
+
+// Boundary conversions.  Rust memory may hold any u64 < 2^64 (f64/mod.rs:56 "stored in the range
+// [0, 2^64)"), so reduce first.
+GL_HD uint64_t canon(uint64_t x) { return x >= P ? x - P : x; }
+GL_HD uint64_t mont_to_canon(uint64_t x) { return mul(canon(x), MONT_R_INV); }
+GL_HD uint64_t canon_to_mont(uint64_t x) { return mul(x, EPS); }
+
+}  // namespace gl

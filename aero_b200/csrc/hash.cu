@@ -1,0 +1,190 @@
+// blake2s row hashing (K3), Merkle levels (K4), FRI leaf hashing (part of K8), grinding (K10).
+//
+// K3 replaces Matrix::commit_to_rows' row loop (winterfell/prover/src/matrix.rs:222-242) +
+// Blake2s_256::hash_elements (winterfell/crypto/src/hash/blake2s/mod.rs:52-77).
+// K4 replaces build_merkle_nodes (winterfell/crypto/src/merkle/mod.rs:316-340).
+// K10 replaces ProverChannel::grind_query_seed (winterfell/prover/src/channel.rs:151-167).
+#include "blake2s.cuh"
+#include "kernels.cuh"
+
+namespace aero {
+
+__device__ __forceinline__ void store_digest(uint32_t *dst, const uint32_t h[8]) {
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    d[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    d[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+__device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t h[8]) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 a = s[0], b = s[1];
+    h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w;
+    h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
+}
+
+// One thread per LDE row.  The LDE is stored coset-major: storage row rho = r*n + i holds natural
+// row k = B*i + r (B = blowup), so thread rho reads column c at lde[c*col_stride + rho]: a fully
+// coalesced 8-byte-per-lane stream.  The digest goes to the natural slot leaves[k].
+__global__ void __launch_bounds__(256) hash_rows_kernel(const uint64_t *__restrict__ lde, size_t col_stride, int ncols,
+                                                        uint32_t nrows, int logn, int log_blowup,
+                                                        uint32_t row_begin, uint32_t *__restrict__ leaves) {
+    const uint32_t rho = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (rho >= nrows) return;
+    uint32_t h[8];
+    b2s::init(h);
+    const uint64_t *p = lde + rho;
+    const int nblocks = (ncols + 1) >> 1;
+    uint64_t e0 = __ldg(p), e1 = ncols > 1 ? __ldg(p + col_stride) : 0ULL;
+    for (int b = 0; b < nblocks; b++) {
+        uint64_t n0 = 0, n1 = 0;
+        if (b + 1 < nblocks) {  // prefetch the next pair while this block is compressed
+            n0 = __ldg(p + (size_t)(2 * b + 2) * col_stride);
+            if (2 * b + 3 < ncols) n1 = __ldg(p + (size_t)(2 * b + 3) * col_stride);
+        }
+        const bool last = (b + 1 == nblocks);
+        const uint32_t t = last ? 32u * (uint32_t)ncols : 64u * (uint32_t)(b + 1);
+        b2s::compress_pair(h, e0, e1, t, last);
+        e0 = n0;
+        e1 = n1;
+    }
+    const uint32_t n_mask = (1u << logn) - 1;
+    const uint32_t k = ((rho & n_mask) << log_blowup) | (rho >> logn);
+    store_digest(leaves + (size_t)k * 8, h);
+}
+
+// Generic variant: rows of a plain column-major matrix in natural order (used for small inputs /
+// tests): leaf k = hash(m[c][k]).
+__global__ void __launch_bounds__(256) hash_rows_natural_kernel(const uint64_t *__restrict__ m, size_t col_stride,
+                                                                int ncols, uint32_t nrows,
+                                                                uint32_t *__restrict__ leaves) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nrows) return;
+    uint32_t h[8];
+    b2s::init(h);
+    const int nblocks = (ncols + 1) >> 1;
+    for (int b = 0; b < nblocks; b++) {
+        const uint64_t e0 = m[(size_t)(2 * b) * col_stride + k];
+        const uint64_t e1 = (2 * b + 1 < ncols) ? m[(size_t)(2 * b + 1) * col_stride + k] : 0ULL;
+        const bool last = (b + 1 == nblocks);
+        const uint32_t t = last ? 32u * (uint32_t)ncols : 64u * (uint32_t)(b + 1);
+        b2s::compress_pair(h, e0, e1, t, last);
+    }
+    store_digest(leaves + (size_t)k * 8, h);
+}
+
+// Merkle tree over `full` = 2*N digests: full[N + k] = leaf k, full[i] = merge(full[2i], full[2i+1])
+// for 1 <= i < N (heap layout of merkle/mod.rs:316-340; full[1] is the root, full[0] unused/zero).
+// Block b builds the height-`levels` subtree whose top node is (top_lo + b): 2^(levels-1) nodes
+// from global children, then up through shared memory; every level is also written to `full`.
+constexpr int MERKLE_MAX_LEVELS = 9;
+__global__ void __launch_bounds__(256) merkle_subtree_kernel(uint32_t *__restrict__ full, uint32_t top_lo, int levels) {
+    __shared__ uint32_t sbuf[2][256 * 8];
+    const uint32_t top = top_lo + blockIdx.x;
+    int width = 1 << (levels - 1);  // nodes at the current level inside this subtree
+    int cur = 0;
+    // bottom level: children from global memory
+    {
+        const uint32_t first = top << (levels - 1);
+        for (int t = threadIdx.x; t < width; t += blockDim.x) {
+            const uint32_t node = first + t;
+            uint32_t a[8], b[8], o[8];
+            load_digest(full + (size_t)(2 * node) * 8, a);
+            load_digest(full + (size_t)(2 * node + 1) * 8, b);
+            b2s::merge(a, b, o);
+            store_digest(full + (size_t)node * 8, o);
+#pragma unroll
+            for (int i = 0; i < 8; i++) sbuf[cur][t * 8 + i] = o[i];
+        }
+    }
+    for (int l = levels - 2; l >= 0; l--) {
+        __syncthreads();
+        width >>= 1;
+        const uint32_t first = top << l;
+        for (int t = threadIdx.x; t < width; t += blockDim.x) {
+            uint32_t a[8], b[8], o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                a[i] = sbuf[cur][(2 * t) * 8 + i];
+                b[i] = sbuf[cur][(2 * t + 1) * 8 + i];
+            }
+            b2s::merge(a, b, o);
+            store_digest(full + (size_t)(first + t) * 8, o);
+#pragma unroll
+            for (int i = 0; i < 8; i++) sbuf[cur ^ 1][t * 8 + i] = o[i];
+        }
+        cur ^= 1;
+    }
+}
+
+void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s) {
+    // node levels have sizes num_leaves/2, ..., 1 ; level of size L occupies indices [L, 2L)
+    uint64_t level = num_leaves / 2;  // size of the lowest node level still to compute
+    while (level >= 1) {
+        int remaining = 0;
+        for (uint64_t l = level; l >= 1; l >>= 1) remaining++;
+        const int levels = remaining < MERKLE_MAX_LEVELS ? remaining : MERKLE_MAX_LEVELS;
+        const uint32_t top_lo = (uint32_t)(level >> (levels - 1));
+        AERO_COUNT_LAUNCH(1);
+        merkle_subtree_kernel<<<top_lo, 256, 0, s>>>(full, top_lo, levels);
+        if (top_lo == 1) break;
+        level = top_lo >> 1;
+    }
+}
+
+void hash_rows_lde(const uint64_t *lde, size_t col_stride, int ncols, int logn, int log_blowup, uint32_t row_begin,
+                   uint32_t row_end, uint32_t *leaves, cudaStream_t s) {
+    const uint32_t count = row_end - row_begin;
+    if (count == 0) return;
+    AERO_COUNT_LAUNCH(1);
+    hash_rows_kernel<<<(count + 255) / 256, 256, 0, s>>>(lde, col_stride, ncols, row_end, logn, log_blowup, row_begin,
+                                                         leaves);
+}
+void hash_rows_natural(const uint64_t *m, size_t col_stride, int ncols, uint32_t nrows, uint32_t *leaves,
+                       cudaStream_t s) {
+    AERO_COUNT_LAUNCH(1);
+    hash_rows_natural_kernel<<<(nrows + 255) / 256, 256, 0, s>>>(m, col_stride, ncols, nrows, leaves);
+}
+
+// FRI leaf j (j < rows = M/8) = hash_elements(f[j + k*rows], k = 0..7): 256-byte message, 4 blocks
+// (fri/src/prover/mod.rs:202-203: transpose_slice + hash_values).  `log_cosets` > 0 means f is
+// stored coset-major (natural q at (q & (B-1))*(M/B) + (q >> b)), as the DEEP LDE is.
+__global__ void __launch_bounds__(256) fri_leaf_hash_kernel(const uint64_t *__restrict__ f, uint32_t rows,
+                                                            int log_cosets, uint32_t *__restrict__ leaves) {
+    const uint32_t tau = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tau >= rows) return;
+    uint64_t v[8];
+    uint32_t j;
+    fri_gather8(f, rows, log_cosets, tau, j, v);
+    uint32_t h[8];
+    b2s::init(h);
+    b2s::compress_pair(h, v[0], v[1], 64u, false);
+    b2s::compress_pair(h, v[2], v[3], 128u, false);
+    b2s::compress_pair(h, v[4], v[5], 192u, false);
+    b2s::compress_pair(h, v[6], v[7], 256u, true);
+    store_digest(leaves + (size_t)j * 8, h);
+}
+void fri_leaf_hash(const uint64_t *f, uint32_t rows, int log_cosets, uint32_t *leaves, cudaStream_t s) {
+    AERO_COUNT_LAUNCH(1);
+    fri_leaf_hash_kernel<<<(rows + 255) / 256, 256, 0, s>>>(f, rows, log_cosets, leaves);
+}
+
+// Grinding: smallest nonce >= 1 whose digest head has >= `bits` trailing zero bits.  Batches are
+// scanned in ascending order; inside a batch atomicMin keeps the smallest hit, so the result is
+// the global minimum, matching the reference's serial `find` (channel.rs:154-157).
+__global__ void __launch_bounds__(256) pow_search_kernel(const uint32_t *__restrict__ seed, uint64_t base,
+                                                         uint32_t bits, unsigned long long *__restrict__ best) {
+    const uint64_t nonce = base + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t s[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = seed[i];
+    b2s::merge_with_int(s, nonce, o);
+    const uint64_t head = ((uint64_t)o[1] << 32) | o[0];
+    const uint32_t tz = head ? (uint32_t)(__ffsll((long long)head) - 1) : 64u;
+    if (tz >= bits) atomicMin(best, (unsigned long long)nonce);
+}
+void pow_search(const uint32_t *seed, uint64_t base, uint32_t count, uint32_t bits, unsigned long long *best,
+                cudaStream_t s) {
+    AERO_COUNT_LAUNCH(1);
+    pow_search_kernel<<<count / 256, 256, 0, s>>>(seed, base, bits, best);
+}
+
+}  // namespace aero

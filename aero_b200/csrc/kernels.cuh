@@ -1,0 +1,102 @@
+// Shared declarations for the aero_b200 CUDA kernels (host-callable launchers + device helpers).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "gl.cuh"
+
+namespace aero {
+
+extern unsigned long long g_launch_count;  // kernels launched by this library (aero_launch_count)
+#define AERO_COUNT_LAUNCH(n) (aero::g_launch_count += (n))
+
+// Two-level table for powers of a fixed base: base^e = lo[e & (2^lo_bits-1)] * hi[e >> lo_bits].
+// `hi` may carry an extra constant factor (folded scale).
+struct PowTable {
+    const uint64_t *lo = nullptr;
+    const uint64_t *hi = nullptr;
+    int lo_bits = 0;
+};
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint64_t pow_lookup(const PowTable &t, uint32_t e) {
+    return gl::mul(__ldg(t.lo + (e & ((1u << t.lo_bits) - 1))), __ldg(t.hi + (e >> t.lo_bits)));
+}
+
+// Gather the 8 evaluations of FRI leaf j = {f[j + k*rows]} (fri transpose_slice,
+// utils/core/src/lib.rs:574-581).  Thread index tau maps to leaf j so that loads are coalesced:
+// natural layout: j = tau; coset-major layout (B = 2^log_cosets cosets of M/B entries, natural q at
+// (q & (B-1))*(M/B) + (q >> b)): j = B*a + r with tau = r*(rows/B) + a (rows % B == 0).
+__device__ __forceinline__ void fri_gather8(const uint64_t *__restrict__ f, uint32_t rows, int log_cosets,
+                                            uint32_t tau, uint32_t &j, uint64_t v[8]) {
+    if (log_cosets == 0) {
+        j = tau;
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = __ldg(f + (size_t)j + (size_t)k * rows);
+    } else {
+        const uint32_t per = rows >> log_cosets;     // rows / B
+        const uint32_t r = tau / per, a = tau - r * per;
+        j = (a << log_cosets) | r;
+        const size_t coset_len = ((size_t)rows * 8) >> log_cosets;  // M / B
+        const uint64_t *p = f + (size_t)r * coset_len + a;
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = __ldg(p + (size_t)k * per);
+    }
+}
+#endif
+
+// hash.cu
+void hash_rows_lde(const uint64_t *lde, size_t col_stride, int ncols, int logn, int log_blowup, uint32_t row_begin,
+                   uint32_t row_end, uint32_t *leaves, cudaStream_t s);
+void hash_rows_natural(const uint64_t *m, size_t col_stride, int ncols, uint32_t nrows, uint32_t *leaves,
+                       cudaStream_t s);
+void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s);
+void fri_leaf_hash(const uint64_t *f, uint32_t rows, int log_cosets, uint32_t *leaves, cudaStream_t s);
+void pow_search(const uint32_t *seed, uint64_t base, uint32_t count, uint32_t bits, unsigned long long *best,
+                cudaStream_t s);
+
+// poly.cu
+void convert_form(const uint64_t *src, uint64_t *dst, size_t count, int to_montgomery, cudaStream_t s);
+void lde_to_natural(const uint64_t *lde_cm, uint64_t *out, int logn, int log_blowup, int to_montgomery,
+                    cudaStream_t s);
+// out[p*2 + 0/1] partial sums; see poly.cu
+void ood_eval(const uint64_t *polys, size_t col_stride, int ncols, int logn, const uint64_t *d_points, int npoints,
+              uint64_t *d_out /* ncols*npoints */, uint64_t *d_scratch, cudaStream_t s);
+size_t ood_scratch_elems(int ncols, int logn, int npoints);
+struct DeepSegs {  // trace segments in order (main, aux...): column c of segment s at p[s] + c*n
+    const uint64_t *p[4];
+    int ncols[4];
+    int nseg;
+};
+void deep_accumulate(const DeepSegs &segs, const uint64_t *comp_polys, int m, int logn,
+                     const uint64_t *d_cc /* W*2 + m */,
+                     const uint64_t *d_consts /* 3: subtract from coefficient 0 of t1,t2,h */, uint64_t *t1,
+                     uint64_t *t2, uint64_t *h, cudaStream_t s);
+void syn_div3(uint64_t *t1, uint64_t *t2, uint64_t *h, int logn, const uint64_t b[3], uint64_t *d_carry,
+              cudaStream_t s);
+void deep_finish(const uint64_t *t1, const uint64_t *t2, const uint64_t *h, int logn, uint64_t d0, uint64_t d1,
+                 uint64_t *out, cudaStream_t s);
+void gather_rows(const uint64_t *lde_cm, size_t col_stride, int ncols, int logn, int log_blowup,
+                 const uint32_t *d_positions, int npos, uint64_t *d_out, cudaStream_t s);
+void gather_fri_rows(const uint64_t *f, uint32_t rows, int log_cosets, const uint32_t *d_positions, int npos,
+                     uint64_t *d_out, cudaStream_t s);
+void gather_digests(const uint32_t *full, const uint32_t *d_idx, int count, uint32_t *d_out, cudaStream_t s);
+
+struct DivisorDev {
+    uint64_t a;            // numerator degree: (x^a - b)
+    uint64_t b;
+    uint64_t off_pow_a;    // offset^a
+    uint32_t nex;
+    uint64_t ex[8];
+    const uint64_t *zinv;  // device: 1/(x^a - b) over the N/a distinct values
+    uint32_t zn;           // N / a
+};
+void divisor_inverses(const DivisorDev &d, uint64_t *zinv_out, int logN, PowTable gN, cudaStream_t s);
+void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDev *divs, int ndiv, int logN,
+                        uint64_t offset, PowTable gN, uint64_t *combined, cudaStream_t s);
+
+// fri.cu
+void fri_fold(const uint64_t *f, uint32_t rows, int log_cosets, uint64_t alpha, PowTable xinv /* (7 g_M^j)^-1 */,
+              const uint64_t w8inv[4], uint64_t inv8, uint64_t *out, cudaStream_t s);
+
+}  // namespace aero

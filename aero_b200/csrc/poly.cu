@@ -1,0 +1,418 @@
+// Polynomial kernels: boundary conversions, OOD evaluation (K7), DEEP composition in coefficient
+// form (K6), constraint combination (front half of K5), query gathers (K9).
+#include "kernels.cuh"
+
+namespace aero {
+
+// ---------------------------------------------------------------------------------------------
+// Montgomery <-> canonical at the ABI boundary (winterfell/math/src/field/f64/mod.rs:59-61, :234)
+// ---------------------------------------------------------------------------------------------
+__global__ void convert_form_kernel(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, size_t count,
+                                    int to_mont) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = to_mont ? gl::canon_to_mont(src[i]) : gl::mont_to_canon(src[i]);
+}
+void convert_form(const uint64_t *src, uint64_t *dst, size_t count, int to_montgomery, cudaStream_t s) {
+    if (!count) return;
+    size_t blocks = (count + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    AERO_COUNT_LAUNCH(1);
+    convert_form_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dst, count, to_montgomery);
+}
+
+// coset-major LDE column (B cosets of n) -> natural order out[B*i + r] = lde[r*n + i]
+// (the order Matrix::evaluate_columns_over returns, matrix.rs:189-201)
+__global__ void lde_to_natural_kernel(const uint64_t *__restrict__ lde, uint64_t *__restrict__ out, int logn,
+                                      int log_blowup, int to_mont) {
+    const size_t N = (size_t)1 << (logn + log_blowup);
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = k & (((size_t)1 << log_blowup) - 1), i = k >> log_blowup;
+        const uint64_t v = lde[(r << logn) + i];
+        out[k] = to_mont ? gl::canon_to_mont(v) : v;
+    }
+}
+void lde_to_natural(const uint64_t *lde_cm, uint64_t *out, int logn, int log_blowup, int to_montgomery,
+                    cudaStream_t s) {
+    const size_t N = (size_t)1 << (logn + log_blowup);
+    size_t blocks = (N + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    AERO_COUNT_LAUNCH(1);
+    lde_to_natural_kernel<<<(unsigned)blocks, 256, 0, s>>>(lde_cm, out, logn, log_blowup, to_montgomery);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-wide helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t block_sum(uint64_t v, uint64_t *sm /* >= 32 */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = gl::add(v, __shfl_down_sync(0xffffffffu, v, o));
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? sm[threadIdx.x] : 0ULL;
+    if (wid == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = gl::add(v, __shfl_down_sync(0xffffffffu, v, o));
+    }
+    return v;  // valid in thread 0
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: OOD evaluation.  TracePolyTable::get_ood_frame (prover/src/trace/poly_table.rs:59-72) and
+// CompositionPoly::evaluate_at (constraints/composition_poly.rs:93-96) are Horner evaluations
+// (math/src/polynom/mod.rs:53-62); here sum_j p[j] x^j is split into chunks of CH coefficients:
+// thread t takes j = j0 + t + 256*l (coalesced), Horner in x^256, times x^t, block-reduced, times
+// x^j0; a second tiny kernel adds the chunk partials.
+// d_tab layout per point p (stride tab_stride): [0..255] x^t ; [256] x^256 ; [257 + chunk] x^(chunk*CH)
+// ---------------------------------------------------------------------------------------------
+constexpr int OOD_THREADS = 256;
+constexpr int OOD_L = 16;
+__global__ void __launch_bounds__(OOD_THREADS) ood_partial_kernel(const uint64_t *__restrict__ polys, size_t col_stride,
+                                                                  int logn, const uint64_t *__restrict__ d_tab,
+                                                                  int tab_stride, int npoints, int chunk_len,
+                                                                  uint64_t *__restrict__ partial) {
+    __shared__ uint64_t sm[32];
+    const int chunk = blockIdx.x, col = blockIdx.y, nchunks = gridDim.x;
+    const uint64_t *p = polys + (size_t)col * col_stride + (size_t)chunk * chunk_len;
+    const int t = threadIdx.x;
+    const int L = chunk_len / OOD_THREADS > 0 ? chunk_len / OOD_THREADS : 1;
+    uint64_t c[OOD_L];
+#pragma unroll
+    for (int l = 0; l < OOD_L; l++) c[l] = (l < L && t + OOD_THREADS * l < chunk_len) ? __ldg(p + t + OOD_THREADS * l) : 0ULL;
+    for (int pt = 0; pt < npoints; pt++) {
+        const uint64_t *tab = d_tab + (size_t)pt * tab_stride;
+        const uint64_t x256 = tab[256];
+        uint64_t acc = 0;
+#pragma unroll
+        for (int l = OOD_L - 1; l >= 0; l--) acc = gl::add(gl::mul(acc, x256), c[l]);
+        acc = gl::mul(acc, tab[t]);
+        acc = block_sum(acc, sm);
+        if (t == 0) partial[((size_t)col * npoints + pt) * nchunks + chunk] = gl::mul(acc, tab[257 + chunk]);
+    }
+}
+__global__ void ood_final_kernel(const uint64_t *__restrict__ partial, int nchunks, int total,
+                                 uint64_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint64_t acc = 0;
+    for (int c = 0; c < nchunks; c++) acc = gl::add(acc, partial[(size_t)i * nchunks + c]);
+    out[i] = acc;
+}
+static int ood_chunk_len(int logn) {
+    const int n = 1 << logn;
+    return n < OOD_THREADS * OOD_L ? n : OOD_THREADS * OOD_L;
+}
+size_t ood_scratch_elems(int ncols, int logn, int npoints) {
+    const int nchunks = (1 << logn) / ood_chunk_len(logn);
+    return (size_t)ncols * npoints * nchunks;
+}
+// d_points here is the device table described above (built by the host driver).
+void ood_eval(const uint64_t *polys, size_t col_stride, int ncols, int logn, const uint64_t *d_tab, int npoints,
+              uint64_t *d_out, uint64_t *d_scratch, cudaStream_t s) {
+    const int chunk_len = ood_chunk_len(logn);
+    const int nchunks = (1 << logn) / chunk_len;
+    const int tab_stride = 257 + nchunks;
+    dim3 g(nchunks, ncols);
+    AERO_COUNT_LAUNCH(2);
+    ood_partial_kernel<<<g, OOD_THREADS, 0, s>>>(polys, col_stride, logn, d_tab, tab_stride, npoints, chunk_len,
+                                                 d_scratch);
+    const int total = ncols * npoints;
+    ood_final_kernel<<<(total + 127) / 128, 128, 0, s>>>(d_scratch, nchunks, total, d_out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: DEEP composition, coefficient form (prover/src/composer/mod.rs:71-238).
+//   t1 = sum_i cc_i.0 * T_i  - [x^0] sum_i cc_i.0 * T_i(z)         (acc_trace_poly, :280-288)
+//   t2 = sum_i cc_i.1 * T_i  - [x^0] sum_i cc_i.1 * T_i(z g)
+//   h  = sum_j cc'_j  * H_j  - [x^0] sum_j cc'_j  * H_j(z^m)       (add_composition_poly, :184-214;
+//        division is linear, so the m divisions by (x - z^m) collapse into one)
+// then t1/(x-z) + t2/(x-zg) + h/(x-z^m) (syn_div_in_place, math/src/polynom/mod.rs:535-542), and
+// out[j] = d0*c[j] + d1*c[j-1] (adjust_degree, :222-238).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) deep_accumulate_kernel(DeepSegs segs, const uint64_t *__restrict__ cp, int m,
+                                                              uint32_t n, const uint64_t *__restrict__ cc,
+                                                              const uint64_t *__restrict__ consts,
+                                                              uint64_t *__restrict__ t1, uint64_t *__restrict__ t2,
+                                                              uint64_t *__restrict__ h) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint64_t a1 = 0, a2 = 0, ah = 0;
+    int i = 0;  // running trace-column index across segments (composer/mod.rs:96-99)
+    for (int s = 0; s < segs.nseg; s++) {
+        const uint64_t *tp = segs.p[s] + j;
+        for (int c = 0; c < segs.ncols[s]; c++, i++) {
+            const uint64_t v = __ldg(tp + (size_t)c * n);
+            a1 = gl::add(a1, gl::mul(v, __ldg(cc + 2 * i)));
+            a2 = gl::add(a2, gl::mul(v, __ldg(cc + 2 * i + 1)));
+        }
+    }
+    for (int c = 0; c < m; c++) ah = gl::add(ah, gl::mul(__ldg(cp + (size_t)c * n + j), __ldg(cc + 2 * i + c)));
+    if (j == 0) {
+        a1 = gl::sub(a1, consts[0]);
+        a2 = gl::sub(a2, consts[1]);
+        ah = gl::sub(ah, consts[2]);
+    }
+    t1[j] = a1;
+    t2[j] = a2;
+    h[j] = ah;
+}
+void deep_accumulate(const DeepSegs &segs, const uint64_t *comp_polys, int m, int logn, const uint64_t *d_cc,
+                     const uint64_t *d_consts, uint64_t *t1, uint64_t *t2, uint64_t *h, cudaStream_t s) {
+    const uint32_t n = 1u << logn;
+    AERO_COUNT_LAUNCH(1);
+    deep_accumulate_kernel<<<(n + 255) / 256, 256, 0, s>>>(segs, comp_polys, m, n, d_cc, d_consts, t1, t2, h);
+}
+
+// Synthetic division by (x - b) as a suffix recurrence c <- p[i] + b*c, q[i] = previous c.
+// Blocks own chunks of SYN_T*SYN_L coefficients; a thread owns SYN_L consecutive ones.
+//   pass A: chunk totals Tot[ch] = sum_{k in chunk} p[k] b^(k-lo)
+//   pass B: CarryIn[ch] = sum_{ch' > ch} Tot[ch'] b^(C (ch'-ch-1))          (one thread per polynomial)
+//   pass C: thread totals + block suffix scan (carry appended) -> rerun the recurrence, write q.
+constexpr int SYN_T = 256;
+constexpr int SYN_L = 16;
+struct SynParams {
+    uint64_t *p[3];
+    uint64_t b[3];
+    uint64_t bl_pow[3][9];  // b^(L * 2^s), s = 0..8
+    uint64_t bc[3];         // b^(chunk_len)
+    uint32_t n, chunk_len, L;
+};
+// inclusive suffix scan over SYN_T+1 values with multiplier b^L: S[t] = v[t] + b^L * S[t+1]
+__device__ __forceinline__ void block_suffix_scan(uint64_t *sv /* SYN_T+1 */, const uint64_t *blp) {
+    const int t = threadIdx.x;
+    int s = 0;
+    for (int d = 1; d <= SYN_T; d <<= 1, s++) {
+        __syncthreads();
+        uint64_t add0 = 0;
+        if (t + d <= SYN_T) add0 = gl::mul(sv[t + d], blp[s]);
+        __syncthreads();
+        if (t + d <= SYN_T) sv[t] = gl::add(sv[t], add0);
+    }
+    __syncthreads();
+}
+template <bool APPLY>
+__global__ void __launch_bounds__(SYN_T) syn_div_kernel(SynParams sp, uint64_t *__restrict__ tot /* [3][nchunks] */,
+                                                        const uint64_t *__restrict__ carry_in /* [3][nchunks] */) {
+    __shared__ uint64_t sv[SYN_T + 1];
+    const int which = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    uint64_t *p = sp.p[which] + (size_t)chunk * sp.chunk_len;
+    const uint64_t b = sp.b[which];
+    const int t = threadIdx.x;
+    const uint32_t L = sp.L;
+    const uint32_t start = t * L;
+    uint64_t vals[SYN_L];
+    uint64_t c = 0;
+    const bool active = start < sp.chunk_len;
+#pragma unroll
+    for (int l = SYN_L - 1; l >= 0; l--) {
+        vals[l] = (active && (uint32_t)l < L) ? p[start + l] : 0ULL;
+        if (active && (uint32_t)l < L) c = gl::add(vals[l], gl::mul(b, c));
+    }
+    sv[t] = active ? c : 0ULL;
+    if (t == 0) sv[SYN_T] = APPLY ? carry_in[(size_t)which * nchunks + chunk] : 0ULL;
+    // inactive threads (chunk shorter than SYN_T*L) hold zero totals but still shift the carry by
+    // b^L per slot; chunk_len is always SYN_T*L or (n < SYN_T*SYN_L) n with L = 1 and n >= SYN_T?
+    // -> the launcher guarantees chunk_len == SYN_T * L.
+    block_suffix_scan(sv, sp.bl_pow[which]);
+    if (!APPLY) {
+        if (t == 0) tot[(size_t)which * nchunks + chunk] = sv[0];
+        return;
+    }
+    c = sv[t + 1];
+#pragma unroll
+    for (int l = SYN_L - 1; l >= 0; l--) {
+        if (active && (uint32_t)l < L) {
+            const uint64_t v = gl::add(vals[l], gl::mul(b, c));
+            p[start + l] = c;
+            c = v;
+        }
+    }
+}
+__global__ void syn_carry_kernel(const uint64_t *__restrict__ tot, uint64_t *__restrict__ carry_in, int nchunks,
+                                 SynParams sp) {
+    const int which = threadIdx.x;
+    if (which >= 3) return;
+    uint64_t c = 0;
+    for (int ch = nchunks - 1; ch >= 0; ch--) {
+        carry_in[(size_t)which * nchunks + ch] = c;
+        c = gl::add(tot[(size_t)which * nchunks + ch], gl::mul(sp.bc[which], c));
+    }
+}
+void syn_div3(uint64_t *t1, uint64_t *t2, uint64_t *h, int logn, const uint64_t b[3], uint64_t *d_carry,
+              cudaStream_t s) {
+    SynParams sp;
+    sp.n = 1u << logn;
+    // chunk_len == SYN_T * L always; small inputs shrink L and, below SYN_T, pad with a single
+    // chunk handled by L = 1 and inactive threads contributing zero (their slots still carry
+    // powers of b^L, which is harmless because everything to their right is zero).
+    if (sp.n >= (uint32_t)SYN_T * SYN_L) {
+        sp.L = SYN_L;
+    } else if (sp.n >= (uint32_t)SYN_T) {
+        sp.L = sp.n / SYN_T;
+    } else {
+        sp.L = 1;
+    }
+    sp.chunk_len = sp.n >= (uint32_t)SYN_T ? SYN_T * sp.L : sp.n;
+    const int nchunks = sp.n / sp.chunk_len;
+    uint64_t *ps[3] = {t1, t2, h};
+    for (int i = 0; i < 3; i++) {
+        sp.p[i] = ps[i];
+        sp.b[i] = b[i];
+        uint64_t bl = gl::pow(b[i], sp.L);
+        for (int k = 0; k < 9; k++) {
+            sp.bl_pow[i][k] = bl;
+            bl = gl::mul(bl, bl);
+        }
+        // the carry crosses SYN_T thread slots of L coefficients each, even when n < SYN_T
+        sp.bc[i] = gl::pow(b[i], (uint64_t)SYN_T * sp.L);
+    }
+    uint64_t *tot = d_carry, *carry = d_carry + 3 * (size_t)nchunks;
+    dim3 g(nchunks, 3);
+    AERO_COUNT_LAUNCH(3);
+    syn_div_kernel<false><<<g, SYN_T, 0, s>>>(sp, tot, carry);
+    syn_carry_kernel<<<1, 32, 0, s>>>(tot, carry, nchunks, sp);
+    syn_div_kernel<true><<<g, SYN_T, 0, s>>>(sp, tot, carry);
+}
+
+__global__ void deep_finish_kernel(const uint64_t *__restrict__ q1, const uint64_t *__restrict__ q2,
+                                   const uint64_t *__restrict__ q3, uint32_t n, uint64_t d0, uint64_t d1,
+                                   uint64_t *__restrict__ out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t c = gl::add(gl::add(q1[j], q2[j]), q3[j]);
+    uint64_t r = gl::mul(c, d0);
+    if (j > 0) {
+        const uint64_t cm = gl::add(gl::add(q1[j - 1], q2[j - 1]), q3[j - 1]);
+        r = gl::add(r, gl::mul(cm, d1));
+    }
+    out[j] = r;
+}
+void deep_finish(const uint64_t *t1, const uint64_t *t2, const uint64_t *h, int logn, uint64_t d0, uint64_t d1,
+                 uint64_t *out, cudaStream_t s) {
+    const uint32_t n = 1u << logn;
+    AERO_COUNT_LAUNCH(1);
+    deep_finish_kernel<<<(n + 255) / 256, 256, 0, s>>>(t1, t2, h, n, d0, d1, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9: query gathers (prover/src/trace/commitment.rs:115-140, constraints/commitment.rs:54-70,
+// fri/src/prover/mod.rs:282-302, crypto/src/merkle/mod.rs:188-250 for the node list)
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const uint64_t *__restrict__ lde, size_t col_stride, int ncols, int logn,
+                                   int log_blowup, const uint32_t *__restrict__ pos, int npos,
+                                   uint64_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npos * ncols) return;
+    const int p = i / ncols, c = i - p * ncols;
+    const uint32_t k = pos[p];
+    const size_t rho = ((size_t)(k & ((1u << log_blowup) - 1)) << logn) + (k >> log_blowup);
+    out[i] = lde[(size_t)c * col_stride + rho];
+}
+void gather_rows(const uint64_t *lde_cm, size_t col_stride, int ncols, int logn, int log_blowup,
+                 const uint32_t *d_positions, int npos, uint64_t *d_out, cudaStream_t s) {
+    const int total = npos * ncols;
+    AERO_COUNT_LAUNCH(1);
+    gather_rows_kernel<<<(total + 127) / 128, 128, 0, s>>>(lde_cm, col_stride, ncols, logn, log_blowup, d_positions,
+                                                           npos, d_out);
+}
+__global__ void gather_fri_rows_kernel(const uint64_t *__restrict__ f, uint32_t rows, int log_cosets,
+                                       const uint32_t *__restrict__ pos, int npos, uint64_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npos * 8) return;
+    const int p = i >> 3, k = i & 7;
+    const size_t q = (size_t)pos[p] + (size_t)k * rows;  // natural index into the layer
+    size_t addr = q;
+    if (log_cosets) {
+        const size_t coset_len = ((size_t)rows * 8) >> log_cosets;
+        addr = (q & (((size_t)1 << log_cosets) - 1)) * coset_len + (q >> log_cosets);
+    }
+    out[i] = f[addr];
+}
+void gather_fri_rows(const uint64_t *f, uint32_t rows, int log_cosets, const uint32_t *d_positions, int npos,
+                     uint64_t *d_out, cudaStream_t s) {
+    AERO_COUNT_LAUNCH(1);
+    gather_fri_rows_kernel<<<(npos * 8 + 127) / 128, 128, 0, s>>>(f, rows, log_cosets, d_positions, npos, d_out);
+}
+__global__ void gather_digests_kernel(const uint32_t *__restrict__ full, const uint32_t *__restrict__ idx, int count,
+                                      uint32_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count * 8) return;
+    out[i] = full[(size_t)idx[i >> 3] * 8 + (i & 7)];
+}
+void gather_digests(const uint32_t *full, const uint32_t *d_idx, int count, uint32_t *d_out, cudaStream_t s) {
+    if (!count) return;
+    AERO_COUNT_LAUNCH(1);
+    gather_digests_kernel<<<(count * 8 + 127) / 128, 128, 0, s>>>(full, d_idx, count, d_out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5 front half: ConstraintEvaluationTable::into_poly's accumulation
+// (prover/src/constraints/evaluation_table.rs:166-190, acc_column :330-380,
+// get_inv_evaluation :383-419).  x_i = offset * g_N^i ; divisor d = (x^a - b) / prod (x - ex_k).
+// ---------------------------------------------------------------------------------------------
+constexpr int INV_BATCH = 8;
+__global__ void __launch_bounds__(256) divisor_inverses_kernel(DivisorDev d, uint64_t *__restrict__ zinv, PowTable gN) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i0 = t * INV_BATCH;
+    if (i0 >= d.zn) return;
+    uint64_t v[INV_BATCH], pre[INV_BATCH];
+    uint64_t acc = 1;
+#pragma unroll
+    for (int k = 0; k < INV_BATCH; k++) {
+        const uint32_t i = i0 + k;
+        v[k] = 0;
+        if (i < d.zn) v[k] = gl::sub(gl::mul(pow_lookup(gN, (uint32_t)((uint64_t)i * d.a)), d.off_pow_a), d.b);
+        pre[k] = acc;
+        if (v[k]) acc = gl::mul(acc, v[k]);
+    }
+    acc = gl::inv(acc);
+#pragma unroll
+    for (int k = INV_BATCH - 1; k >= 0; k--) {
+        const uint32_t i = i0 + k;
+        uint64_t r = 0;
+        if (v[k]) {  // zero maps to zero: serial_batch_inversion, math/src/utils/mod.rs:218-238
+            r = gl::mul(acc, pre[k]);
+            acc = gl::mul(acc, v[k]);
+        }
+        if (i < d.zn) zinv[i] = r;
+    }
+}
+void divisor_inverses(const DivisorDev &d, uint64_t *zinv_out, int logN, PowTable gN, cudaStream_t s) {
+    (void)logN;
+    const uint32_t threads = (d.zn + INV_BATCH - 1) / INV_BATCH;
+    AERO_COUNT_LAUNCH(1);
+    divisor_inverses_kernel<<<(threads + 255) / 256, 256, 0, s>>>(d, zinv_out, gN);
+}
+
+struct DivisorSet {
+    DivisorDev d[8];
+    int n;
+};
+__global__ void __launch_bounds__(256) constraint_combine_kernel(const uint64_t *__restrict__ cols, size_t col_stride,
+                                                                 DivisorSet ds, uint32_t N, uint64_t offset,
+                                                                 PowTable gN, uint64_t *__restrict__ combined) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint64_t x = gl::mul(pow_lookup(gN, i), offset);  // domain.get_ce_x_at, domain.rs:101-103
+    uint64_t acc = 0;
+    for (int k = 0; k < ds.n; k++) {
+        const DivisorDev &d = ds.d[k];
+        uint64_t z = __ldg(d.zinv + (i % d.zn));
+        for (uint32_t e = 0; e < d.nex; e++) z = gl::mul(z, gl::sub(x, d.ex[e]));
+        acc = gl::add(acc, gl::mul(__ldg(cols + (size_t)k * col_stride + i), z));
+    }
+    combined[i] = acc;
+}
+void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDev *divs, int ndiv, int logN,
+                        uint64_t offset, PowTable gN, uint64_t *combined, cudaStream_t s) {
+    DivisorSet ds;
+    ds.n = ndiv;
+    for (int i = 0; i < ndiv; i++) ds.d[i] = divs[i];
+    const uint32_t N = 1u << logN;
+    AERO_COUNT_LAUNCH(1);
+    constraint_combine_kernel<<<(N + 255) / 256, 256, 0, s>>>(cols, col_stride, ds, N, offset, gN, combined);
+}
+
+}  // namespace aero

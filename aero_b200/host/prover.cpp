@@ -1,0 +1,461 @@
+// Host-side prover driver; see prover.hpp for the mapping to winter-prover.
+#include "prover.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+#include "../csrc/blake2s.cuh"
+#include "../csrc/gl.cuh"
+
+namespace aero {
+namespace host {
+
+// ---------------------------------------------------------------------------------------------
+// hashing (host copies of the single-block helpers used by Fiat-Shamir)
+// ---------------------------------------------------------------------------------------------
+static Digest to_digest(const uint32_t h[8]) {
+    Digest d(32);
+    memcpy(d.data(), h, 32);
+    return d;
+}
+Digest blake2s(const uint8_t *data, size_t len) {
+    uint32_t h[8], m[16];
+    b2s::init(h);
+    size_t off = 0;
+    while (len - off > 64) {
+        memcpy(m, data + off, 64);
+        off += 64;
+        b2s::compress(h, m, (uint32_t)off, false);
+    }
+    uint8_t last[64] = {0};
+    if (len - off) memcpy(last, data + off, len - off);
+    memcpy(m, last, 64);
+    b2s::compress(h, m, (uint32_t)len, true);
+    return to_digest(h);
+}
+Digest hash_elements(const std::vector<uint64_t> &e) {
+    uint32_t h[8];
+    b2s::init(h);
+    const size_t nblocks = (e.size() + 1) / 2;
+    for (size_t b = 0; b < nblocks; b++) {
+        const bool last = b + 1 == nblocks;
+        const uint64_t e1 = 2 * b + 1 < e.size() ? e[2 * b + 1] : 0;
+        b2s::compress_pair(h, e[2 * b], e1, last ? (uint32_t)(32 * e.size()) : (uint32_t)(64 * (b + 1)), last);
+    }
+    return to_digest(h);
+}
+Digest merge(const Digest &a, const Digest &b) {
+    uint32_t x[8], y[8], o[8];
+    memcpy(x, a.data(), 32);
+    memcpy(y, b.data(), 32);
+    b2s::merge(x, y, o);
+    return to_digest(o);
+}
+Digest merge_with_int(const Digest &seed, uint64_t v) {
+    uint32_t s[8], o[8];
+    memcpy(s, seed.data(), 32);
+    b2s::merge_with_int(s, v, o);
+    return to_digest(o);
+}
+static uint64_t head64(const Digest &d) {
+    uint64_t v;
+    memcpy(&v, d.data(), 8);
+    return v;
+}
+static uint32_t tz64(uint64_t x) { return x ? (uint32_t)__builtin_ctzll(x) : 64u; }
+
+// ---------------------------------------------------------------------------------------------
+// RandomCoin
+// ---------------------------------------------------------------------------------------------
+RandomCoin::RandomCoin(const uint8_t *seed, size_t len) : seed_(blake2s(seed, len)) {}
+void RandomCoin::reseed(const Digest &data) {
+    seed_ = merge(seed_, data);
+    counter_ = 0;
+}
+void RandomCoin::reseed_with_int(uint64_t value) {
+    seed_ = merge_with_int(seed_, value);
+    counter_ = 0;
+}
+uint32_t RandomCoin::leading_zeros() const { return tz64(head64(seed_)); }
+uint32_t RandomCoin::check_leading_zeros(uint64_t value) const { return tz64(head64(merge_with_int(seed_, value))); }
+Digest RandomCoin::next() {
+    counter_ += 1;
+    return merge_with_int(seed_, counter_);
+}
+bool RandomCoin::draw(uint64_t *out) {
+    for (int i = 0; i < 1000; i++) {
+        const uint64_t v = head64(next());
+        if (v < gl::P) {  // from_random_bytes rejects non-canonical values (f64/mod.rs:438-454)
+            *out = v;
+            return true;
+        }
+    }
+    return false;
+}
+bool RandomCoin::draw_integers(size_t num_values, uint64_t domain_size, std::vector<uint64_t> *out) {
+    out->clear();
+    if (domain_size == 0 || (domain_size & (domain_size - 1)) || num_values >= domain_size) return false;
+    const uint64_t mask = domain_size - 1;
+    for (int i = 0; i < 1000; i++) {
+        const uint64_t v = head64(next()) & mask;
+        if (std::find(out->begin(), out->end(), v) != out->end()) continue;
+        out->push_back(v);
+        if (out->size() == num_values) return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// wire format
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static void put(std::vector<uint8_t> &o, T v) {
+    const uint8_t *p = (const uint8_t *)&v;
+    o.insert(o.end(), p, p + sizeof(T));
+}
+static void put_bytes(std::vector<uint8_t> &o, const std::vector<uint8_t> &b) { o.insert(o.end(), b.begin(), b.end()); }
+static void put_elems(std::vector<uint8_t> &o, const std::vector<uint64_t> &e) {
+    for (uint64_t v : e) put<uint64_t>(o, v);
+}
+static int ilog2(uint64_t x) {
+    int l = 0;
+    while ((1ULL << l) < x) l++;
+    return l;
+}
+std::vector<uint8_t> ProofOptions::to_bytes() const {
+    return {o.num_queries, o.blowup_factor, o.grinding_factor, o.hash_fn, o.field_extension, o.fri_folding_factor,
+            (uint8_t)ilog2(o.fri_max_remainder_size)};
+}
+size_t ProofOptions::num_fri_layers(uint64_t domain) const {
+    size_t r = 0;
+    while (domain > o.fri_max_remainder_size) {
+        domain /= o.fri_folding_factor;
+        r++;
+    }
+    return r;
+}
+void Queries::write_into(std::vector<uint8_t> &out) const {
+    put<uint32_t>(out, (uint32_t)values.size());
+    put_bytes(out, values);
+    put<uint32_t>(out, (uint32_t)paths.size());
+    put_bytes(out, paths);
+}
+std::vector<uint8_t> StarkProof::to_bytes() const {
+    std::vector<uint8_t> r;
+    put_bytes(r, context);
+    put<uint16_t>(r, (uint16_t)commitments.size());  // commitments.rs:84-90
+    put_bytes(r, commitments);
+    for (auto &q : trace_queries) q.write_into(r);
+    constraint_queries.write_into(r);
+    put<uint16_t>(r, (uint16_t)ood_trace_states.size());  // ood_frame.rs:113-122
+    put_bytes(r, ood_trace_states);
+    put<uint16_t>(r, (uint16_t)ood_evaluations.size());
+    put_bytes(r, ood_evaluations);
+    put_bytes(r, fri_proof);
+    put<uint64_t>(r, pow_nonce);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ProverChannel
+// ---------------------------------------------------------------------------------------------
+ProverChannel::ProverChannel(aero_ctx *ctx, const aero_prove_inputs &in)
+    : ctx_(ctx), options_{in.options}, lde_domain_size_(in.trace_len * in.options.blowup_factor),
+      coin_(in.pub_inputs_bytes, in.pub_inputs_len) {
+    // Context::write_into (air/src/proof/context.rs:98-107) + TraceLayout (trace_info.rs:274-290)
+    context_.push_back((uint8_t)in.main_width);
+    context_.push_back((uint8_t)in.aux_width);
+    context_.push_back((uint8_t)(in.aux_width ? in.aux_rands : 0));
+    context_.push_back((uint8_t)ilog2(in.trace_len));
+    put<uint16_t>(context_, in.trace_meta_len);
+    if (in.trace_meta_len) context_.insert(context_.end(), in.trace_meta, in.trace_meta + in.trace_meta_len);
+    context_.push_back(8);
+    put<uint64_t>(context_, gl::P);
+    put_bytes(context_, options_.to_bytes());
+}
+void ProverChannel::commit_trace(const Digest &root) {
+    put_bytes(commitments_, root);
+    coin_.reseed(root);
+}
+void ProverChannel::commit_constraints(const Digest &root) {
+    put_bytes(commitments_, root);
+    coin_.reseed(root);
+}
+void ProverChannel::send_ood_trace_states(const std::vector<std::vector<uint64_t>> &rows) {
+    for (auto &row : rows) {
+        put_elems(ood_trace_, row);
+        coin_.reseed(hash_elements(row));
+    }
+}
+void ProverChannel::send_ood_constraint_evaluations(const std::vector<uint64_t> &evals) {
+    put_elems(ood_evals_, evals);
+    coin_.reseed(hash_elements(evals));
+}
+bool ProverChannel::draw_elements(size_t n, std::vector<uint64_t> *out) {
+    out->resize(n);
+    for (size_t i = 0; i < n; i++)
+        if (!coin_.draw(&(*out)[i])) return false;
+    return true;
+}
+void ProverChannel::commit_fri_layer(const Digest &root) {
+    put_bytes(commitments_, root);
+    coin_.reseed(root);
+}
+aero_status ProverChannel::grind_query_seed() {
+    uint64_t nonce = 0;
+    aero_status st = aero_pow_min_nonce(ctx_, coin_.seed().data(), options_.o.grinding_factor, &nonce);
+    if (st != AERO_OK) return st;
+    pow_nonce_ = nonce;
+    coin_.reseed_with_int(nonce);
+    return AERO_OK;
+}
+bool ProverChannel::get_query_positions(std::vector<uint64_t> *out) {
+    return coin_.draw_integers(options_.o.num_queries, lde_domain_size_, out);
+}
+StarkProof ProverChannel::build_proof(std::vector<Queries> trace_queries, Queries constraint_queries,
+                                      std::vector<uint8_t> fri_proof) {
+    StarkProof p;
+    p.context = context_;
+    p.commitments = commitments_;
+    p.ood_trace_states = ood_trace_;
+    p.ood_evaluations = ood_evals_;
+    p.trace_queries = std::move(trace_queries);
+    p.constraint_queries = std::move(constraint_queries);
+    p.fri_proof = std::move(fri_proof);
+    p.pow_nonce = pow_nonce_;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Prover
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Handles {  // RAII for the device handles of one proof
+    std::vector<aero_segment *> segs;
+    aero_fri *fri = nullptr;
+    ~Handles() {
+        aero_fri_destroy(fri);
+        for (auto s : segs) aero_segment_destroy(s);
+    }
+};
+#define P_TRY(expr)                                                      \
+    do {                                                                 \
+        aero_status _s = (expr);                                         \
+        if (_s != AERO_OK) {                                             \
+            if (err) *err = std::string(#expr) + ": " + aero_last_error(ctx); \
+            return _s;                                                   \
+        }                                                                \
+    } while (0)
+#define P_FAIL(code, msg)          \
+    do {                           \
+        if (err) *err = (msg);     \
+        return (code);             \
+    } while (0)
+}  // namespace
+
+extern "C" int aero_ctx_get_form(aero_ctx *ctx);
+
+// build_segment_queries (prover/src/trace/commitment.rs:115-140)
+static aero_status query_segment(aero_ctx *ctx, aero_segment *seg, const std::vector<uint64_t> &positions,
+                                 uint32_t width, Queries *q, std::string *err) {
+    std::vector<uint64_t> rows(positions.size() * width);
+    std::vector<uint8_t> paths(1 + positions.size() * (1 + 32 * 40));
+    size_t len = paths.size();
+    P_TRY(aero_segment_open(seg, positions.data(), (uint32_t)positions.size(), rows.data(), paths.data(), &len));
+    paths.resize(len);
+    q->values.assign((uint8_t *)rows.data(), (uint8_t *)rows.data() + rows.size() * 8);
+    q->paths = std::move(paths);
+    return AERO_OK;
+}
+
+aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_t> *proof_bytes, std::string *err) {
+    const aero_proof_options &o = in.options;
+    if (o.hash_fn != 4) P_FAIL(AERO_ERR_UNSUPPORTED, "only Blake2s_256 (hash_fn = 4) is supported");
+    if (o.field_extension != 1) P_FAIL(AERO_ERR_UNSUPPORTED, "only FieldExtension::None is supported");
+    if (o.fri_folding_factor != 8) P_FAIL(AERO_ERR_UNSUPPORTED, "only FRI folding factor 8 is supported");
+    if (!in.main_cols || in.main_width == 0) P_FAIL(AERO_ERR_INVALID, "main trace segment is required");
+    if (in.aux_width && !in.aux_builder && !in.aux_cols) P_FAIL(AERO_ERR_INVALID, "auxiliary segment columns are required");
+    if (!in.constraint_evaluator && !in.ce_cols) P_FAIL(AERO_ERR_INVALID, "constraint evaluations are required");
+    if (in.inputs_on_device && (in.aux_builder || in.constraint_evaluator)) P_FAIL(AERO_ERR_INVALID, "callbacks need host inputs");
+    const bool mont = aero_ctx_get_form(ctx) == AERO_FORM_MONTGOMERY;
+    auto to_abi = [&](uint64_t x) { return mont ? gl::canon_to_mont(x) : x; };
+    auto from_abi = [&](uint64_t x) { return mont ? gl::mont_to_canon(x) : gl::canon(x); };
+    const uint64_t n = in.trace_len, N = n * o.blowup_factor;
+    const uint32_t W = in.main_width + in.aux_width;
+
+    Handles H;
+    ProverChannel channel(ctx, in);
+    uint8_t root[32];
+
+    // 1 ----- commit to the execution trace (lib.rs:239-248, 269-348)
+    aero_segment *main_seg = nullptr;
+    if (in.inputs_on_device)
+        P_TRY(aero_segment_commit_device(ctx, in.main_cols[0], n, in.main_width, n, o.blowup_factor, 0, &main_seg, root));
+    else
+        P_TRY(aero_segment_commit(ctx, in.main_cols, in.main_width, n, o.blowup_factor, 0, &main_seg, root));
+    H.segs.push_back(main_seg);
+    channel.commit_trace(Digest(root, root + 32));
+
+    aero_segment *aux_seg = nullptr;
+    if (in.aux_width) {
+        std::vector<uint64_t> rand_elements;
+        if (!channel.draw_elements(in.aux_rands, &rand_elements)) P_FAIL(AERO_ERR_STATE, "failed to draw random elements");
+        std::vector<const uint64_t *> aux_ptrs(in.aux_width);
+        const uint64_t *const *aux_cols = in.aux_cols;
+        if (in.aux_builder) {
+            std::vector<uint64_t> abi(rand_elements.size());
+            for (size_t i = 0; i < abi.size(); i++) abi[i] = to_abi(rand_elements[i]);
+            aero_status st = in.aux_builder(in.user, abi.data(), (uint32_t)abi.size(), aux_ptrs.data());
+            if (st != AERO_OK) P_FAIL(st, "aux_builder callback failed");
+            aux_cols = aux_ptrs.data();
+        }
+        if (in.inputs_on_device)
+            P_TRY(aero_segment_commit_device(ctx, aux_cols[0], n, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root));
+        else
+            P_TRY(aero_segment_commit(ctx, aux_cols, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root));
+        H.segs.push_back(aux_seg);
+        channel.commit_trace(Digest(root, root + 32));
+    }
+
+    // 2 ----- evaluate constraints (lib.rs:350-382): coefficients are drawn here; evaluation itself
+    // stays with the caller (reference Rust path) or is supplied precomputed.
+    std::vector<uint64_t> coeffs;
+    if (!channel.draw_elements(in.n_constraint_coeffs, &coeffs)) P_FAIL(AERO_ERR_STATE, "failed to draw composition coefficients");
+    std::vector<const uint64_t *> ce_ptrs(in.n_div);
+    const uint64_t *const *ce_cols = in.ce_cols;
+    std::vector<std::vector<uint64_t>> lde_host;
+    if (in.constraint_evaluator) {
+        lde_host.resize(W);
+        std::vector<uint64_t *> ptrs(W);
+        for (uint32_t c = 0; c < W; c++) {
+            lde_host[c].resize(N);
+            ptrs[c] = lde_host[c].data();
+        }
+        P_TRY(aero_segment_download_lde(main_seg, ptrs.data()));
+        if (aux_seg) P_TRY(aero_segment_download_lde(aux_seg, ptrs.data() + in.main_width));
+        std::vector<uint64_t> abi(coeffs.size());
+        for (size_t i = 0; i < abi.size(); i++) abi[i] = to_abi(coeffs[i]);
+        aero_status st = in.constraint_evaluator(in.user, (const uint64_t *const *)ptrs.data(), W, N, abi.data(),
+                                                 (uint32_t)abi.size(), ce_ptrs.data());
+        if (st != AERO_OK) P_FAIL(st, "constraint_evaluator callback failed");
+        ce_cols = ce_ptrs.data();
+    }
+
+    // 3 ----- commit to constraint evaluations (lib.rs:396-419)
+    aero_segment *comp_seg = nullptr;
+    if (in.inputs_on_device)
+        P_TRY(aero_constraints_into_poly_device(ctx, ce_cols[0], N, in.divisors, in.n_div, N, n, &comp_seg));
+    else
+        P_TRY(aero_constraints_into_poly(ctx, ce_cols, in.divisors, in.n_div, N, n, &comp_seg));
+    H.segs.push_back(comp_seg);
+    lde_host.clear();
+    P_TRY(aero_segment_commit_polys(comp_seg, o.blowup_factor, root));
+    channel.commit_constraints(Digest(root, root + 32));
+
+    // 4 ----- OOD frame + DEEP composition polynomial (lib.rs:421-467)
+    uint64_t z;
+    if (!channel.coin().draw(&z)) P_FAIL(AERO_ERR_STATE, "failed to draw OOD point");
+    uint32_t m = 0;
+    P_TRY(aero_segment_info(comp_seg, &m, nullptr, nullptr));
+    std::vector<uint64_t> ood_trace(2 * W), ood_comp(m);
+    std::vector<aero_segment *> trace_segs = {main_seg};
+    if (aux_seg) trace_segs.push_back(aux_seg);
+    P_TRY(aero_ood_eval(ctx, trace_segs.data(), (uint32_t)trace_segs.size(), comp_seg, to_abi(z), ood_trace.data(), ood_comp.data()));
+    {
+        std::vector<std::vector<uint64_t>> rows(2, std::vector<uint64_t>(W));
+        for (uint32_t i = 0; i < W; i++) {
+            rows[0][i] = from_abi(ood_trace[i]);
+            rows[1][i] = from_abi(ood_trace[W + i]);
+        }
+        channel.send_ood_trace_states(rows);
+        std::vector<uint64_t> ev(m);
+        for (uint32_t i = 0; i < m; i++) ev[i] = from_abi(ood_comp[i]);
+        channel.send_ood_constraint_evaluations(ev);
+    }
+    // get_deep_composition_coefficients (air/src/air/mod.rs:537-561): W triples, m singles, one pair
+    std::vector<uint64_t> cc;
+    if (!channel.draw_elements((size_t)3 * W + m + 2, &cc)) P_FAIL(AERO_ERR_STATE, "failed to draw DEEP coefficients");
+    for (auto &v : cc) v = to_abi(v);
+    P_TRY(aero_deep_compose(ctx, trace_segs.data(), (uint32_t)trace_segs.size(), comp_seg, to_abi(z), ood_trace.data(),
+                            ood_comp.data(), cc.data(), &H.fri));
+
+    // 6 ----- FRI layers (fri/src/prover/mod.rs:166-191)
+    const size_t num_layers = ProofOptions{o}.num_fri_layers(N);
+    for (size_t l = 0; l < num_layers + 1; l++) {
+        P_TRY(aero_fri_commit_layer(H.fri, root));
+        channel.commit_fri_layer(Digest(root, root + 32));
+        uint64_t alpha;
+        if (!channel.coin().draw(&alpha)) P_FAIL(AERO_ERR_STATE, "failed to draw FRI alpha");
+        // the reference also folds the remainder layer and discards the result (prover/mod.rs:174-183)
+        if (l < num_layers) P_TRY(aero_fri_fold(H.fri, to_abi(alpha)));
+    }
+
+    // 7 ----- query positions (lib.rs:502-516)
+    P_TRY(channel.grind_query_seed());
+    std::vector<uint64_t> positions;
+    if (!channel.get_query_positions(&positions)) P_FAIL(AERO_ERR_STATE, "failed to draw query positions");
+
+    // 8 ----- proof object (lib.rs:518-539)
+    std::vector<uint8_t> fri_bytes(1 << 20);
+    size_t flen = fri_bytes.size();
+    P_TRY(aero_fri_open(H.fri, positions.data(), (uint32_t)positions.size(), fri_bytes.data(), &flen));
+    fri_bytes.resize(flen);
+    std::vector<Queries> tq(trace_segs.size());
+    P_TRY(query_segment(ctx, main_seg, positions, in.main_width, &tq[0], err));
+    if (aux_seg) P_TRY(query_segment(ctx, aux_seg, positions, in.aux_width, &tq[1], err));
+    Queries cq;
+    P_TRY(query_segment(ctx, comp_seg, positions, m, &cq, err));
+    *proof_bytes = channel.build_proof(std::move(tq), std::move(cq), std::move(fri_bytes)).to_bytes();
+    return AERO_OK;
+}
+
+}  // namespace host
+}  // namespace aero
+
+// ---------------------------------------------------------------------------------------------
+// C entry points (include/aero_prover.h)
+// ---------------------------------------------------------------------------------------------
+using namespace aero::host;
+struct aero_coin {
+    RandomCoin c;
+};
+extern "C" {
+void aero_ctx_set_error(aero_ctx *ctx, const char *msg);
+
+aero_status aero_prove(aero_ctx *ctx, const aero_prove_inputs *in, uint8_t *proof_out, size_t *len) {
+    if (!ctx || !in || !len) return AERO_ERR_INVALID;
+    std::vector<uint8_t> bytes;
+    std::string err;
+    aero_status st = prove(ctx, *in, &bytes, &err);
+    if (st != AERO_OK) {
+        aero_ctx_set_error(ctx, err.c_str());
+        return st;
+    }
+    if (!proof_out || *len < bytes.size()) {
+        *len = bytes.size();
+        aero_ctx_set_error(ctx, "proof buffer too small");
+        return AERO_ERR_BUFFER;
+    }
+    memcpy(proof_out, bytes.data(), bytes.size());
+    *len = bytes.size();
+    return AERO_OK;
+}
+void aero_host_blake2s(const uint8_t *data, size_t len, uint8_t out[32]) { memcpy(out, blake2s(data, len).data(), 32); }
+void aero_host_hash_elements(const uint64_t *e, size_t count, uint8_t out[32]) {
+    memcpy(out, hash_elements(std::vector<uint64_t>(e, e + count)).data(), 32);
+}
+aero_coin *aero_coin_new(const uint8_t *seed_bytes, size_t len) { return new aero_coin{RandomCoin(seed_bytes, len)}; }
+void aero_coin_free(aero_coin *c) { delete c; }
+void aero_coin_reseed(aero_coin *c, const uint8_t digest[32]) { c->c.reseed(Digest(digest, digest + 32)); }
+void aero_coin_reseed_with_int(aero_coin *c, uint64_t v) { c->c.reseed_with_int(v); }
+aero_status aero_coin_draw(aero_coin *c, uint64_t *out) { return c->c.draw(out) ? AERO_OK : AERO_ERR_STATE; }
+aero_status aero_coin_draw_integers(aero_coin *c, uint32_t num_values, uint64_t domain_size, uint64_t *out) {
+    std::vector<uint64_t> v;
+    if (!c->c.draw_integers(num_values, domain_size, &v)) return AERO_ERR_INVALID;
+    memcpy(out, v.data(), v.size() * 8);
+    return AERO_OK;
+}
+uint32_t aero_coin_leading_zeros(aero_coin *c) { return c->c.leading_zeros(); }
+uint32_t aero_coin_check_leading_zeros(aero_coin *c, uint64_t v) { return c->c.check_leading_zeros(v); }
+void aero_coin_seed(aero_coin *c, uint8_t out[32]) { memcpy(out, c->c.seed().data(), 32); }
+}

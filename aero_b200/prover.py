@@ -1,0 +1,384 @@
+"""Thin Python face of the C ABI, named after the winter-prover interfaces it stands in for.
+
+* :class:`Context`                      -> aero_ctx (one GPU, one proof at a time)
+* :func:`Context.build_trace_commitment` -> Prover::build_trace_commitment (prover/src/lib.rs:551-589)
+* :func:`Context.constraints_into_poly` -> ConstraintEvaluationTable::into_poly (evaluation_table.rs:166)
+* :class:`Segment`                      -> (Matrix lde, MerkleTree, Matrix polys) of one segment
+* :class:`FriProver`                    -> fri::FriProver (fri/src/prover/mod.rs:100-302)
+* :class:`RandomCoin`                   -> crypto::RandomCoin (host side; crypto/src/random/mod.rs)
+* :func:`Context.prove`                 -> Prover::prove (prover/src/lib.rs:161-194)
+
+Matrices are numpy uint64 arrays of shape (columns, rows), C-contiguous (column-major in the
+reference's sense).  Nothing here computes: every call goes to libaero_b200.so and raises
+:class:`AeroError` on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import (AERO_ERR_BUFFER, AERO_FORM_CANONICAL, AERO_FORM_MONTGOMERY, AERO_OK, Divisor, ProofOptions,
+                   ProveInputs, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p, p_u8, p_u64, pp_u64)
+
+
+class AeroError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__("%s: %s" % (_lib.STATUS_NAMES.get(status, status), message))
+        self.status = status
+
+
+def miden_options(**kw) -> ProofOptions:
+    """ProofOptions::with_96_bit_security (miden/air/src/options.rs:29-39)."""
+    o = ProofOptions(27, 8, 16, 4, 1, 8, 256)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def make_divisor(a: int, b: int, exemptions: Sequence[int] = ()) -> Divisor:
+    d = Divisor()
+    d.a, d.b, d.n_exemptions = a, b, len(exemptions)
+    for i, e in enumerate(exemptions):
+        d.exemptions[i] = e
+    return d
+
+
+def _cols(m: np.ndarray):
+    """(w, n) uint64 C-contiguous -> array of column pointers (keeps a reference to m)."""
+    assert m.dtype == np.uint64 and m.ndim == 2 and m.flags["C_CONTIGUOUS"], "expected (cols, rows) uint64 C array"
+    arr = (p_u64 * m.shape[0])()
+    base = m.ctypes.data
+    for c in range(m.shape[0]):
+        arr[c] = ctypes.cast(base + c * m.shape[1] * 8, p_u64)
+    return arr
+
+
+class Context:
+    def __init__(self, device: Optional[int] = None, form: int = AERO_FORM_MONTGOMERY):
+        self.lib = _lib.load()
+        h = c_void_p()
+        if device is None:
+            st = self.lib.aero_ctx_create(None, 0, ctypes.byref(h))
+        else:
+            ids = (ctypes.c_int * 1)(device)
+            st = self.lib.aero_ctx_create(ids, 1, ctypes.byref(h))
+        if st != AERO_OK:
+            raise AeroError(st, "aero_ctx_create failed (no usable sm_100 CUDA device; there is no CPU fallback)")
+        self.h = h
+        self.form = form
+        self._check(self.lib.aero_ctx_set_form(self.h, form))
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.aero_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int) -> None:
+        if st != AERO_OK:
+            raise AeroError(st, (self.lib.aero_last_error(self.h) or b"").decode())
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._check(self.lib.aero_ctx_set_stream(self.h, c_void_p(cuda_stream)))
+
+    def profile_enable(self, on: bool = True) -> None:
+        self._check(self.lib.aero_ctx_profile_enable(self.h, int(on)))
+
+    def profile_read(self) -> Dict[str, Tuple[int, float]]:
+        buf = ctypes.create_string_buffer(1 << 16)
+        ln = c_size_t(len(buf))
+        self._check(self.lib.aero_ctx_profile_read(self.h, buf, ctypes.byref(ln)))
+        return {k: (int(v[0]), float(v[1])) for k, v in json.loads(buf.value.decode()).items()}
+
+    def sync(self) -> None:
+        self._check(self.lib.aero_device_sync(self.h))
+
+    # ---- device staging helpers -----------------------------------------------------------------
+    def device_alloc(self, nbytes: int) -> int:
+        p = c_void_p()
+        self._check(self.lib.aero_device_alloc(self.h, nbytes, ctypes.byref(p)))
+        return p.value
+
+    def device_free(self, ptr: int) -> None:
+        self._check(self.lib.aero_device_free(self.h, c_void_p(ptr)))
+
+    def device_upload(self, ptr: int, a: np.ndarray) -> None:
+        a = np.ascontiguousarray(a)
+        self._check(self.lib.aero_device_upload(self.h, c_void_p(ptr), c_void_p(a.ctypes.data), a.nbytes))
+
+    def device_download(self, ptr: int, out: np.ndarray) -> None:
+        self._check(self.lib.aero_device_download(self.h, c_void_p(out.ctypes.data), c_void_p(ptr), out.nbytes))
+
+    # ---- segments ------------------------------------------------------------------------------
+    def build_trace_commitment(self, trace: np.ndarray, blowup: int = 8, input_is_coeffs: bool = False) -> "Segment":
+        seg, root = c_void_p(), (c_uint8 * 32)()
+        self._check(self.lib.aero_segment_commit(self.h, _cols(trace), trace.shape[0], trace.shape[1], blowup,
+                                                 int(input_is_coeffs), ctypes.byref(seg), root))
+        return Segment(self, seg, bytes(root))
+
+    def build_trace_commitment_device(self, d_ptr: int, n_cols: int, n_rows: int, blowup: int = 8,
+                                      input_is_coeffs: bool = False, col_stride: Optional[int] = None) -> "Segment":
+        seg, root = c_void_p(), (c_uint8 * 32)()
+        self._check(self.lib.aero_segment_commit_device(self.h, c_void_p(d_ptr), col_stride or n_rows, n_cols, n_rows,
+                                                        blowup, int(input_is_coeffs), ctypes.byref(seg), root))
+        return Segment(self, seg, bytes(root))
+
+    def commit_rows_device(self, d_ptr: int, n_cols: int, n_rows: int, col_stride: Optional[int] = None) -> bytes:
+        root = (c_uint8 * 32)()
+        self._check(self.lib.aero_commit_rows_device(self.h, c_void_p(d_ptr), col_stride or n_rows, n_cols, n_rows, root))
+        return bytes(root)
+
+    def constraints_into_poly(self, eval_cols: np.ndarray, divisors: Sequence[Divisor], trace_len: int) -> "Segment":
+        seg = c_void_p()
+        divs = (Divisor * len(divisors))(*divisors)
+        self._check(self.lib.aero_constraints_into_poly(self.h, _cols(eval_cols), divs, len(divisors),
+                                                        eval_cols.shape[1], trace_len, ctypes.byref(seg)))
+        return Segment(self, seg, None)
+
+    # ---- OOD / DEEP ----------------------------------------------------------------------------
+    def ood_eval(self, trace_segs: Sequence["Segment"], comp: Optional["Segment"], z: int):
+        W = sum(s.n_cols for s in trace_segs)
+        out_t = np.zeros(2 * W, np.uint64)
+        out_c = np.zeros(comp.n_cols if comp else 1, np.uint64)
+        hs = (c_void_p * len(trace_segs))(*[s.h for s in trace_segs])
+        self._check(self.lib.aero_ood_eval(self.h, hs, len(trace_segs), comp.h if comp else None, z,
+                                           out_t.ctypes.data_as(p_u64), out_c.ctypes.data_as(p_u64)))
+        return out_t[:W].copy(), out_t[W:].copy(), (out_c if comp else None)
+
+    def deep_compose(self, trace_segs: Sequence["Segment"], comp: "Segment", z: int, ood_trace: np.ndarray,
+                     ood_comp: np.ndarray, cc: np.ndarray) -> "FriProver":
+        hs = (c_void_p * len(trace_segs))(*[s.h for s in trace_segs])
+        fri = c_void_p()
+        ood_trace = np.ascontiguousarray(ood_trace, np.uint64)
+        ood_comp = np.ascontiguousarray(ood_comp, np.uint64)
+        cc = np.ascontiguousarray(cc, np.uint64)
+        self._check(self.lib.aero_deep_compose(self.h, hs, len(trace_segs), comp.h, z, ood_trace.ctypes.data_as(p_u64),
+                                               ood_comp.ctypes.data_as(p_u64), cc.ctypes.data_as(p_u64),
+                                               ctypes.byref(fri)))
+        return FriProver(self, fri)
+
+    def fri_from_evaluations(self, evaluations: np.ndarray) -> "FriProver":
+        ev = np.ascontiguousarray(evaluations, np.uint64)
+        fri = c_void_p()
+        self._check(self.lib.aero_fri_from_evaluations(self.h, ev.ctypes.data_as(p_u64), ev.size, ctypes.byref(fri)))
+        return FriProver(self, fri)
+
+    def pow_min_nonce(self, seed: bytes, grinding_bits: int) -> int:
+        s = (c_uint8 * 32).from_buffer_copy(seed)
+        nonce = c_uint64()
+        self._check(self.lib.aero_pow_min_nonce(self.h, s, grinding_bits, ctypes.byref(nonce)))
+        return nonce.value
+
+    # ---- whole proof ---------------------------------------------------------------------------
+    def prove(self, main_trace, aux_trace, ce_cols, divisors: Sequence[Divisor], pub_inputs_bytes: bytes,
+              options: Optional[ProofOptions] = None, aux_rands: int = 16, n_constraint_coeffs: int = 0,
+              on_device: Optional[dict] = None) -> bytes:
+        """Prover::prove.  Host mode: numpy matrices.  Device mode (``on_device`` = dict with
+        main/aux/ce device pointers and shapes): inputs already resident in HBM."""
+        inp = ProveInputs()
+        inp.options = options or miden_options()
+        keep = []
+        if on_device is None:
+            inp.trace_len = main_trace.shape[1]
+            inp.main_width = main_trace.shape[0]
+            inp.main_cols = _cols(main_trace)
+            if aux_trace is not None:
+                inp.aux_width = aux_trace.shape[0]
+                inp.aux_cols = _cols(aux_trace)
+            inp.ce_cols = _cols(ce_cols)
+            keep += [main_trace, aux_trace, ce_cols]
+        else:
+            inp.inputs_on_device = 1
+            inp.trace_len = on_device["trace_len"]
+            inp.main_width = on_device["main_width"]
+            inp.aux_width = on_device.get("aux_width", 0)
+            for name in ("main", "aux", "ce"):
+                arr = (p_u64 * 1)()
+                arr[0] = ctypes.cast(c_void_p(on_device.get(name, 0) or 0), p_u64)
+                setattr(inp, name + "_cols", arr)
+                keep.append(arr)
+        inp.aux_rands = aux_rands if inp.aux_width else 0
+        divs = (Divisor * len(divisors))(*divisors)
+        inp.divisors = divs
+        inp.n_div = len(divisors)
+        inp.n_constraint_coeffs = n_constraint_coeffs
+        pub = (c_uint8 * len(pub_inputs_bytes)).from_buffer_copy(pub_inputs_bytes)
+        inp.pub_inputs_bytes = pub
+        inp.pub_inputs_len = len(pub_inputs_bytes)
+        cap = 1 << 20
+        while True:
+            buf = (c_uint8 * cap)()
+            ln = c_size_t(cap)
+            st = self.lib.aero_prove(self.h, ctypes.byref(inp), buf, ctypes.byref(ln))
+            if st == AERO_ERR_BUFFER and ln.value > cap:
+                cap = ln.value
+                continue
+            self._check(st)
+            return bytes(buf[: ln.value])
+
+
+class Segment:
+    """One committed matrix: coefficient columns, coset LDE and row-hash Merkle tree on the GPU."""
+
+    def __init__(self, ctx: Context, h: c_void_p, root: Optional[bytes]):
+        self.ctx, self.h, self.root = ctx, h, root
+        nc, nr, bl = c_uint32(), c_uint64(), c_uint32()
+        ctx._check(ctx.lib.aero_segment_info(h, ctypes.byref(nc), ctypes.byref(nr), ctypes.byref(bl)))
+        self.n_cols, self.n_rows, self.blowup = nc.value, nr.value, bl.value
+
+    def commit(self, blowup: int = 8) -> bytes:
+        """CompositionPoly::evaluate + commit_to_rows for a coefficient-only segment."""
+        root = (c_uint8 * 32)()
+        self.ctx._check(self.ctx.lib.aero_segment_commit_polys(self.h, blowup, root))
+        self.blowup = blowup
+        self.root = bytes(root)
+        return self.root
+
+    def download_polys(self) -> np.ndarray:
+        out = np.empty((self.n_cols, self.n_rows), np.uint64)
+        self.ctx._check(self.ctx.lib.aero_segment_download_polys(self.h, _cols(out)))
+        return out
+
+    def download_lde(self) -> np.ndarray:
+        out = np.empty((self.n_cols, self.n_rows * self.blowup), np.uint64)
+        self.ctx._check(self.ctx.lib.aero_segment_download_lde(self.h, _cols(out)))
+        return out
+
+    def download_leaves(self) -> np.ndarray:
+        out = np.empty((self.n_rows * self.blowup, 32), np.uint8)
+        self.ctx._check(self.ctx.lib.aero_segment_download_leaves(self.h, out.ctypes.data_as(p_u8)))
+        return out
+
+    def open(self, positions: Sequence[int]) -> Tuple[np.ndarray, bytes]:
+        """TraceCommitment::query / ConstraintCommitment::query: (rows canonical, serialize_nodes bytes)."""
+        pos = np.array(list(positions), np.uint64)
+        rows = np.empty((len(pos), self.n_cols), np.uint64)
+        cap = 2 + len(pos) * (1 + 32 * 64)
+        buf = (c_uint8 * cap)()
+        ln = c_size_t(cap)
+        self.ctx._check(self.ctx.lib.aero_segment_open(self.h, pos.ctypes.data_as(p_u64), len(pos),
+                                                       rows.ctypes.data_as(p_u64), buf, ctypes.byref(ln)))
+        return rows, bytes(buf[: ln.value])
+
+    def destroy(self) -> None:
+        if self.h:
+            self.ctx.lib.aero_segment_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.destroy()
+        except Exception:
+            pass
+
+
+class FriProver:
+    def __init__(self, ctx: Context, h: c_void_p):
+        self.ctx, self.h = ctx, h
+
+    def evaluations(self) -> np.ndarray:
+        cnt = c_uint64(0)
+        st = self.ctx.lib.aero_fri_download_evaluations(self.h, None, ctypes.byref(cnt))
+        if st not in (AERO_OK, AERO_ERR_BUFFER):
+            self.ctx._check(st)
+        out = np.empty(cnt.value, np.uint64)
+        self.ctx._check(self.ctx.lib.aero_fri_download_evaluations(self.h, out.ctypes.data_as(p_u64), ctypes.byref(cnt)))
+        return out
+
+    def commit_layer(self) -> bytes:
+        root = (c_uint8 * 32)()
+        self.ctx._check(self.ctx.lib.aero_fri_commit_layer(self.h, root))
+        return bytes(root)
+
+    def fold(self, alpha: int) -> None:
+        self.ctx._check(self.ctx.lib.aero_fri_fold(self.h, alpha))
+
+    def open(self, positions: Sequence[int]) -> bytes:
+        pos = np.array(list(positions), np.uint64)
+        cap = 1 << 20
+        buf = (c_uint8 * cap)()
+        ln = c_size_t(cap)
+        self.ctx._check(self.ctx.lib.aero_fri_open(self.h, pos.ctypes.data_as(p_u64), len(pos), buf, ctypes.byref(ln)))
+        return bytes(buf[: ln.value])
+
+    def destroy(self) -> None:
+        if self.h:
+            self.ctx.lib.aero_fri_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.destroy()
+        except Exception:
+            pass
+
+
+class RandomCoin:
+    """Host Fiat-Shamir coin of the product (C++ aero::host::RandomCoin); canonical elements."""
+
+    def __init__(self, seed_bytes: bytes):
+        self.lib = _lib.load()
+        s = (c_uint8 * max(1, len(seed_bytes))).from_buffer_copy(seed_bytes or b"\0")
+        self.h = c_void_p(self.lib.aero_coin_new(s, len(seed_bytes)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.aero_coin_free(self.h)
+            self.h = None
+
+    def reseed(self, digest: bytes) -> None:
+        self.lib.aero_coin_reseed(self.h, (c_uint8 * 32).from_buffer_copy(digest))
+
+    def reseed_with_int(self, v: int) -> None:
+        self.lib.aero_coin_reseed_with_int(self.h, v)
+
+    def draw(self) -> int:
+        out = c_uint64()
+        if self.lib.aero_coin_draw(self.h, ctypes.byref(out)) != AERO_OK:
+            raise RuntimeError("failed to draw a field element")
+        return out.value
+
+    def draw_integers(self, num_values: int, domain_size: int) -> List[int]:
+        out = (c_uint64 * num_values)()
+        if self.lib.aero_coin_draw_integers(self.h, num_values, domain_size, out) != AERO_OK:
+            raise RuntimeError("failed to draw integers")
+        return list(out)
+
+    def leading_zeros(self) -> int:
+        return self.lib.aero_coin_leading_zeros(self.h)
+
+    def check_leading_zeros(self, v: int) -> int:
+        return self.lib.aero_coin_check_leading_zeros(self.h, v)
+
+    @property
+    def seed(self) -> bytes:
+        out = (c_uint8 * 32)()
+        self.lib.aero_coin_seed(self.h, out)
+        return bytes(out)
+
+
+def host_blake2s(data: bytes) -> bytes:
+    lib = _lib.load()
+    out = (c_uint8 * 32)()
+    buf = (c_uint8 * max(1, len(data))).from_buffer_copy(data or b"\0")
+    lib.aero_host_blake2s(buf, len(data), out)
+    return bytes(out)
+
+
+def host_hash_elements(elems: Sequence[int]) -> bytes:
+    lib = _lib.load()
+    a = np.array(list(elems), np.uint64)
+    out = (c_uint8 * 32)()
+    lib.aero_host_hash_elements(a.ctypes.data_as(p_u64), len(a), out)
+    return bytes(out)

@@ -1,0 +1,168 @@
+/*
+ * aero_b200.h -- C ABI of the B200-native LDE / row-commitment / DEEP / FRI core.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of the Miden/Winterfell prover that
+ * starkoracles/Aero drives.  The reference has no FFI for this path (it is all Rust); each entry
+ * point below names the Rust interface it replaces (paths relative to the Aero checkout, the
+ * `winterfell/` prefix omitted for winterfell crates).  INTEGRATION.md shows the Rust `extern "C"`
+ * shim a maintainer would add.
+ *
+ * Conventions
+ *  - Every call returns an aero_status; non-zero means failure and aero_last_error(ctx) holds a
+ *    message.  Nothing aborts or throws across the ABI (the reference asserts/panics instead:
+ *    prover/src/matrix.rs:42-61, math/src/fft/mod.rs:179-199).
+ *  - Field elements crossing the ABI are u64 in the form selected by aero_ctx_set_form():
+ *    AERO_FORM_MONTGOMERY (default; the in-memory image of math::fields::f64::BaseElement,
+ *    math/src/field/f64/mod.rs:59-61) or AERO_FORM_CANONICAL.  Outputs documented as "canonical"
+ *    are always canonical little-endian integers, as on the proof wire (f64/mod.rs:532-535).
+ *  - Digests are raw 32-byte BLAKE2s-256 values (crypto/src/hash/blake2s/mod.rs:33-46).
+ *  - Matrices are column-major like prover::Matrix (prover/src/matrix.rs:26-28).
+ *  - Caller owns host buffers; the library owns aero_* handles until the matching *_destroy.
+ *  - A context drives one GPU and one proof at a time; contexts are independent.
+ *  - There is no CPU fallback: every entry point fails with AERO_ERR_CUDA if no device is usable.
+ */
+#ifndef AERO_B200_H
+#define AERO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int aero_status;
+enum {
+    AERO_OK = 0,
+    AERO_ERR_INVALID = 1,     /* bad argument (non power of two, zero width, out-of-range index...) */
+    AERO_ERR_CUDA = 2,        /* CUDA runtime error or no device */
+    AERO_ERR_NOMEM = 3,
+    AERO_ERR_STATE = 4,       /* call sequence violated (e.g. fold before commit) */
+    AERO_ERR_UNSUPPORTED = 5, /* shape outside what the kernels implement */
+    AERO_ERR_BUFFER = 6       /* output buffer too small; required size is stored in *len */
+};
+enum { AERO_FORM_MONTGOMERY = 0, AERO_FORM_CANONICAL = 1 };
+
+typedef struct aero_ctx aero_ctx;
+typedef struct aero_segment aero_segment;
+typedef struct aero_fri aero_fri;
+
+/* (x^a - b) / prod_k (x - exemptions[k]) : air::ConstraintDivisor (air/src/air/divisor.rs:14-17) */
+typedef struct aero_divisor {
+    uint64_t a;
+    uint64_t b;              /* field element, ABI form */
+    uint32_t n_exemptions;   /* <= 8 */
+    uint64_t exemptions[8];  /* field elements, ABI form */
+} aero_divisor;
+
+/* ---- context --------------------------------------------------------------------------------- */
+/* n_devices must be 1 in this release (one process per GPU; multi-GPU is composed above the ABI,
+ * see DESIGN.md).  device_ids == NULL selects the current device. */
+aero_status aero_ctx_create(const int *device_ids, int n_devices, aero_ctx **out);
+void aero_ctx_destroy(aero_ctx *ctx);
+const char *aero_last_error(aero_ctx *ctx);
+/* Launch everything on this cudaStream_t (default: the legacy default stream). */
+aero_status aero_ctx_set_stream(aero_ctx *ctx, void *cuda_stream);
+aero_status aero_ctx_set_form(aero_ctx *ctx, int form);
+int aero_ctx_get_form(aero_ctx *ctx);
+/* Used by the host driver layered above this ABI to report its own failures through aero_last_error. */
+void aero_ctx_set_error(aero_ctx *ctx, const char *msg);
+/* Per-phase CUDA-event timing (mirrors the reference's debug! timers, prover/src/lib.rs:228-630).
+ * aero_ctx_profile_read writes a JSON object {"phase": [calls, total_ms], ...} and resets. */
+aero_status aero_ctx_profile_enable(aero_ctx *ctx, int enable);
+aero_status aero_ctx_profile_read(aero_ctx *ctx, char *json_out, size_t *len);
+/* Number of CUDA kernels this library has launched in this process. */
+uint64_t aero_launch_count(void);
+const char *aero_version(void);
+
+/* ---- trace / constraint segment: iNTT + coset LDE + row hashes + Merkle tree ------------------- */
+/* Replaces Prover::build_trace_commitment (prover/src/lib.rs:551-589) =
+ * Matrix::interpolate_columns (matrix.rs:151) + evaluate_columns_over (:189) + commit_to_rows
+ * (:222), and with input_is_coeffs != 0 Prover::build_constraint_commitment (lib.rs:599-632).
+ * cols: n_cols host pointers to n_rows elements each.  root receives MerkleTree::root(). */
+aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint32_t n_cols, uint64_t n_rows,
+                                uint32_t blowup, int input_is_coeffs, aero_segment **out, uint8_t root[32]);
+/* Same with the matrix already resident in device memory (column c at d_cols + c*col_stride). */
+aero_status aero_segment_commit_device(aero_ctx *ctx, const uint64_t *d_cols, size_t col_stride, uint32_t n_cols,
+                                       uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
+                                       uint8_t root[32]);
+void aero_segment_destroy(aero_segment *seg);
+aero_status aero_segment_info(aero_segment *seg, uint32_t *n_cols, uint64_t *n_rows, uint32_t *blowup);
+/* Natural-order LDE columns (lde[c][k] = poly_c(7 * g_N^k), matrix.rs:189-201) for the host-side
+ * AIR evaluator (TraceLde, prover/src/trace/trace_lde.rs:15-111). */
+aero_status aero_segment_download_lde(aero_segment *seg, uint64_t *const *cols_out);
+/* Coefficient columns (TracePolyTable, prover/src/trace/poly_table.rs:21-57). */
+aero_status aero_segment_download_polys(aero_segment *seg, uint64_t *const *cols_out);
+/* Leaf digests in natural order (MerkleTree::leaves, crypto/src/merkle/mod.rs:141-143). */
+aero_status aero_segment_download_leaves(aero_segment *seg, uint8_t *leaves_out);
+/* Queries: rows at `positions` (canonical, row-major n_pos x n_cols; trace/commitment.rs:115-140,
+ * constraints/commitment.rs:54-70) and the batch Merkle proof in BatchMerkleProof::serialize_nodes
+ * format (crypto/src/merkle/mod.rs:188-250, merkle/proofs.rs:421-439).  *len: in = capacity of
+ * batch_nodes_out, out = bytes written / required. */
+aero_status aero_segment_open(aero_segment *seg, const uint64_t *positions, uint32_t n_pos, uint64_t *rows_out,
+                              uint8_t *batch_nodes_out, size_t *len);
+
+/* ---- constraint evaluations -> composition polynomial columns ---------------------------------- */
+/* Replaces ConstraintEvaluationTable::into_poly + CompositionPoly::new
+ * (prover/src/constraints/evaluation_table.rs:166-190,330-419; composition_poly.rs:21-49,111-128).
+ * eval_cols: n_div host columns of ce_domain_size merged evaluations.  The result is a segment that
+ * holds ce_domain_size/trace_len coefficient columns; commit it with aero_segment_commit_polys. */
+aero_status aero_constraints_into_poly(aero_ctx *ctx, const uint64_t *const *eval_cols, const aero_divisor *divs,
+                                       uint32_t n_div, uint64_t ce_domain_size, uint64_t trace_len,
+                                       aero_segment **composition_polys);
+/* Same with the evaluation columns resident in device memory (column d at d_eval_cols + d*col_stride). */
+aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_eval_cols, size_t col_stride,
+                                              const aero_divisor *divs, uint32_t n_div, uint64_t ce_domain_size,
+                                              uint64_t trace_len, aero_segment **composition_polys);
+/* Extends + commits a coefficient-only segment: CompositionPoly::evaluate + commit_to_rows
+ * (prover/src/lib.rs:599-632). */
+aero_status aero_segment_commit_polys(aero_segment *seg, uint32_t blowup, uint8_t root[32]);
+
+/* ---- out-of-domain evaluation and DEEP composition --------------------------------------------- */
+/* TracePolyTable::get_ood_frame (prover/src/trace/poly_table.rs:69-72) and
+ * CompositionPoly::evaluate_at (constraints/composition_poly.rs:93-96).  out_trace: 2*W values,
+ * row z (segments in order) then row z*g_n; out_comp: m values at z^m.  comp may be NULL. */
+aero_status aero_ood_eval(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs, aero_segment *comp,
+                          uint64_t z, uint64_t *out_trace, uint64_t *out_comp);
+/* DeepCompositionPoly::{add_trace_polys, add_composition_poly, adjust_degree, evaluate}
+ * (prover/src/composer/mod.rs:71-252).  ood_trace: 2*W, ood_comp: m, cc: W triples, then m, then 2
+ * (air::DeepCompositionCoefficients, air/src/air/mod.rs:537-561).  The result is a FRI prover
+ * primed with the DEEP evaluations over the LDE domain. */
+aero_status aero_deep_compose(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs,
+                              aero_segment *comp, uint64_t z, const uint64_t *ood_trace, const uint64_t *ood_comp,
+                              const uint64_t *cc, aero_fri **out);
+/* DEEP polynomial coefficients / evaluations (natural order) for inspection and tests. */
+aero_status aero_fri_download_evaluations(aero_fri *fri, uint64_t *out, uint64_t *count);
+
+/* ---- FRI (folding factor 8), stepwise so Fiat-Shamir stays with the caller ---------------------- */
+/* FriProver::build_layer split at the channel round trip (fri/src/prover/mod.rs:197-218):
+ * commit = transpose_slice + hash_values + MerkleTree::new; fold = apply_drp with offset 7. */
+aero_status aero_fri_from_evaluations(aero_ctx *ctx, const uint64_t *evaluations, uint64_t count, aero_fri **out);
+aero_status aero_fri_commit_layer(aero_fri *fri, uint8_t root[32]);
+aero_status aero_fri_fold(aero_fri *fri, uint64_t alpha);
+/* FriProver::build_proof (fri/src/prover/mod.rs:231-275) in FriProof::write_into format
+ * (fri/src/proof.rs:201-214,351-359); the last committed layer is the remainder. */
+aero_status aero_fri_open(aero_fri *fri, const uint64_t *positions, uint32_t n_pos, uint8_t *fri_proof_bytes,
+                          size_t *len);
+void aero_fri_destroy(aero_fri *fri);
+
+/* ---- grinding ---------------------------------------------------------------------------------- */
+/* ProverChannel::grind_query_seed, serial build (prover/src/channel.rs:151-167): smallest nonce >= 1
+ * with trailing_zeros(LE64(merge_with_int(seed, nonce)[0..8])) >= grinding_bits. */
+aero_status aero_pow_min_nonce(aero_ctx *ctx, const uint8_t seed[32], uint32_t grinding_bits, uint64_t *nonce);
+
+/* ---- standalone primitives (microbenchmarks, tests) --------------------------------------------- */
+/* Matrix::commit_to_rows on a natural-order device matrix (column c at d_m + c*col_stride). */
+aero_status aero_commit_rows_device(aero_ctx *ctx, const uint64_t *d_m, size_t col_stride, uint32_t n_cols,
+                                    uint64_t n_rows, uint8_t root[32]);
+/* Device scratch helpers so callers without a CUDA runtime binding can stage data. */
+aero_status aero_device_alloc(aero_ctx *ctx, size_t bytes, void **d_ptr);
+aero_status aero_device_free(aero_ctx *ctx, void *d_ptr);
+aero_status aero_device_upload(aero_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+aero_status aero_device_download(aero_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+aero_status aero_device_sync(aero_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AERO_B200_H */

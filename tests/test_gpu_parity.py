@@ -1,0 +1,301 @@
+"""GPU parity tests: every C-ABI entry point against the CPU oracle, bit-exact (all arithmetic on
+this path is integer).  Modeled on the reference's own prover tests
+(winterfell/prover/src/tests/mod.rs, prover/src/trace/tests.rs:41-128, fri/src/prover/tests.rs,
+crypto/src/merkle/tests.rs)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import aero_b200
+from aero_b200 import AeroError, make_divisor
+
+pytestmark = pytest.mark.gpu
+P = 0xFFFFFFFF00000001
+
+
+def _nat_to_np(rows):
+    return np.array(rows, dtype=np.uint64)
+
+
+# ------------------------------------------------------------------------------------------------
+# segment commit: iNTT + coset LDE + row hashes + Merkle (K1-K4)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("logn,width", [(1, 1), (3, 2), (5, 3), (6, 9), (10, 72), (10, 9), (11, 8), (12, 5), (13, 9),
+                                         (14, 4), (16, 3)])
+def test_segment_commit_matches_oracle(ctx, oracle, logn, width):
+    n = 1 << logn
+    trace = oracle.synthetic_trace(width, n, 0xAE200000 + logn)
+    ref = oracle.build_trace_commitment(trace, 8)
+    seg = ctx.build_trace_commitment(trace, 8)
+    assert np.array_equal(seg.download_polys(), ref.polys), "interpolate_columns mismatch"
+    assert np.array_equal(seg.download_lde(), ref.lde), "evaluate_columns_over mismatch"
+    assert np.array_equal(seg.download_leaves(), ref.leaves), "row hashes mismatch"
+    assert seg.root == ref.root, "Merkle root mismatch"
+
+
+@pytest.mark.parametrize("blowup", [2, 4, 16])
+def test_segment_commit_other_blowups(ctx, oracle, blowup):
+    trace = oracle.synthetic_trace(3, 256, 77)
+    ref = oracle.build_trace_commitment(trace, blowup)
+    seg = ctx.build_trace_commitment(trace, blowup)
+    assert np.array_equal(seg.download_lde(), ref.lde)
+    assert seg.root == ref.root
+
+
+def test_segment_commit_montgomery_form(ctx_mont, oracle):
+    """The default ABI form is the Rust memory image (Montgomery); results must be identical."""
+    trace = oracle.synthetic_trace(5, 1 << 12, 5)
+    ref = oracle.build_trace_commitment(trace, 8)
+    seg = ctx_mont.build_trace_commitment(oracle.canon_to_mont(trace), 8)
+    assert seg.root == ref.root
+    assert np.array_equal(oracle.mont_to_canon(seg.download_polys()), ref.polys)
+    assert np.array_equal(oracle.mont_to_canon(seg.download_lde()), ref.lde)
+    # non-canonical Montgomery images (value + p still < 2^64) are accepted like the Rust type does
+    t2 = oracle.canon_to_mont(trace)
+    small = t2 < np.uint64(0xFFFFFFFF)
+    t2 = np.where(small, t2 + np.uint64(P), t2)
+    assert ctx_mont.build_trace_commitment(t2, 8).root == ref.root
+
+
+def test_commit_from_coefficients(ctx, oracle):
+    """build_constraint_commitment path: input columns are already coefficients."""
+    polys = oracle.synthetic_trace(8, 1 << 10, 99)
+    ref = oracle.commit_polys(polys, 8)
+    seg = ctx.build_trace_commitment(polys, 8, input_is_coeffs=True)
+    assert np.array_equal(seg.download_lde(), ref.lde)
+    assert seg.root == ref.root
+
+
+def test_lde_is_consistent_with_trace(ctx, oracle):
+    """prover/src/trace/tests.rs:41-77: every blowup-th LDE row... the LDE polynomial restricted to
+    the trace domain reproduces the trace (checked by naive evaluation at a few points)."""
+    n = 64
+    trace = oracle.synthetic_trace(2, n, 3)
+    seg = ctx.build_trace_commitment(trace, 8)
+    polys = seg.download_polys()
+    g = oracle.root_of_unity(6)
+    for c in range(2):
+        for k in (0, 1, 17, 63):
+            x = pow(g, k, P)
+            assert sum(int(polys[c][j]) * pow(x, j, P) for j in range(n)) % P == int(trace[c][k])
+    lde = seg.download_lde()
+    gN = oracle.root_of_unity(9)
+    for k in (0, 5, 100, 511):
+        x = 7 * pow(gN, k, P) % P
+        assert sum(int(polys[1][j]) * pow(x, j, P) for j in range(n)) % P == int(lde[1][k])
+
+
+def test_commit_rows_golden_fib_rows(ctx, oracle):
+    """SURVEY 'minimum slice' (b): the 27 main-trace rows opened in the reference's golden proof,
+    re-hashed by the GPU row-hash kernel, give the leaf digests the golden Merkle proof commits to."""
+    inp, proof = oracle.read_proof_file(os.path.join(os.path.dirname(__file__), "golden", "fib.bin"))
+    pr = oracle.StarkProof.from_bytes(proof)
+    vals = oracle._felts(pr.trace_queries[0].values)
+    rows = np.array(vals, np.uint64).reshape(27, 72)
+    padded = np.zeros((32, 72), np.uint64)
+    padded[:27] = rows
+    m = np.ascontiguousarray(padded.T)  # (72, 32) column-major
+    d = ctx.device_alloc(m.nbytes)
+    ctx.device_upload(d, m)
+    root = ctx.commit_rows_device(d, 72, 32)
+    ctx.device_free(d)
+    leaves = oracle.hash_rows(m)
+    assert root == oracle.build_merkle_nodes(leaves)[1].tobytes()
+    # and those leaves are exactly what the golden batch proof resolves from
+    rep = oracle.verify(proof, oracle.miden_pub_inputs_seed(inp))
+    got = oracle.batch_get_root([leaves[i].tobytes() for i in range(27)],
+                                oracle.deserialize_nodes(pr.trace_queries[0].paths), 13, rep.positions)
+    assert got == rep.roots[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# openings (K9)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("positions", [[5], [0, 1], [3, 2, 9, 8, 100, 511], [511, 0, 255, 256, 257],
+                                        list(range(0, 54, 2)), [7, 6, 5, 4, 3, 2, 1, 0]])
+def test_segment_open_matches_prove_batch(ctx, oracle, positions):
+    trace = oracle.synthetic_trace(3, 64, 11)
+    ref = oracle.build_trace_commitment(trace, 8)
+    seg = ctx.build_trace_commitment(trace, 8)
+    rows, paths = seg.open(positions)
+    assert np.array_equal(rows, ref.lde[:, positions].T)
+    assert paths == oracle.serialize_nodes(oracle.prove_batch(ref.leaves, ref.nodes, positions))
+    leaves = [oracle.hash_elements(r) for r in rows]
+    assert oracle.batch_get_root(leaves, oracle.deserialize_nodes(paths), 9, positions) == ref.root
+
+
+def test_segment_open_errors(ctx, oracle):
+    """MerkleTree::prove_batch error cases (crypto/src/merkle/mod.rs:188-199, tests.rs)."""
+    seg = ctx.build_trace_commitment(oracle.synthetic_trace(1, 8, 1), 8)
+    for bad in ([], [1, 1], [64], list(range(64)) * 5):
+        with pytest.raises(AeroError) as e:
+            seg.open(bad)
+        assert e.value.status == aero_b200.AERO_ERR_INVALID
+
+
+def test_matrix_shape_errors(ctx, oracle):
+    """Matrix::new / MerkleTree::new preconditions (matrix.rs:41-64, merkle/mod.rs:108-114)."""
+    with pytest.raises(AeroError):
+        ctx.build_trace_commitment(np.zeros((1, 6), np.uint64), 8)  # not a power of two
+    with pytest.raises(AeroError):
+        ctx.build_trace_commitment(np.zeros((1, 1), np.uint64), 8)  # fewer than two rows
+    with pytest.raises(AeroError):
+        ctx.build_trace_commitment(np.zeros((1, 8), np.uint64), 3)  # blowup not a power of two
+
+
+# ------------------------------------------------------------------------------------------------
+# constraints -> composition polynomial (K5)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("logn", [4, 8, 10])
+def test_constraints_into_poly(ctx, oracle, logn):
+    n = 1 << logn
+    N = 8 * n
+    g = oracle.root_of_unity(logn)
+    cols = oracle.synthetic_trace(3, N, 0xCE)
+    divs = [oracle.Divisor(n, 1, [pow(g, n - 1, P)]),      # transition: (x^n - 1)/(x - g^(n-1))
+            oracle.Divisor(1, 1, []),                        # boundary, first step: (x - 1)
+            oracle.Divisor(1, pow(g, n - 1, P), [])]         # boundary, last step
+    ref = oracle.constraints_into_poly(cols, divs, n)
+    seg = ctx.constraints_into_poly(cols, [make_divisor(d.a, d.b, d.exemptions) for d in divs], n)
+    assert np.array_equal(seg.download_polys(), ref)
+    root = seg.commit(8)
+    assert root == oracle.commit_polys(ref, 8).root
+
+
+# ------------------------------------------------------------------------------------------------
+# OOD + DEEP (K7, K6)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("logn,wm,wa", [(3, 2, 1), (6, 3, 2), (8, 5, 0), (10, 72, 9), (13, 7, 3)])
+def test_ood_and_deep(ctx, oracle, logn, wm, wa):
+    n = 1 << logn
+    main = oracle.synthetic_trace(wm, n, 1)
+    segs = [ctx.build_trace_commitment(main, 8)]
+    tp = [oracle.interpolate_columns(main)]
+    if wa:
+        aux = oracle.synthetic_trace(wa, n, 2)
+        segs.append(ctx.build_trace_commitment(aux, 8))
+        tp.append(oracle.interpolate_columns(aux))
+    trace_polys = np.concatenate(tp, axis=0)
+    comp_polys = oracle.synthetic_trace(8, n, 3)
+    comp = ctx.build_trace_commitment(comp_polys, 8, input_is_coeffs=True)
+    z = 0x1234567890ABCDEF % P
+    g = oracle.root_of_unity(logn)
+    ood_z, ood_zg, ood_c = ctx.ood_eval(segs, comp, z)
+    assert [int(v) for v in ood_z] == oracle.eval_columns_at(trace_polys, z)
+    assert [int(v) for v in ood_zg] == oracle.eval_columns_at(trace_polys, z * g % P)
+    assert [int(v) for v in ood_c] == oracle.eval_columns_at(comp_polys, pow(z, 8, P))
+    W = wm + wa
+    rng = oracle.splitmix64_column(0xDEE9, 3 * W + 8 + 2)
+    cc_trace = [tuple(int(v) for v in rng[3 * i:3 * i + 3]) for i in range(W)]
+    cc_comp = [int(v) for v in rng[3 * W:3 * W + 8]]
+    cc_deg = [int(v) for v in rng[3 * W + 8:]]
+    ref_coeffs = oracle.deep_compose(trace_polys, comp_polys, z, ood_z, ood_zg, ood_c, cc_trace, cc_comp, cc_deg)
+    ref_evals = oracle.evaluate_columns_over(ref_coeffs.reshape(1, n), 8)[0]
+    fri = ctx.deep_compose(segs, comp, z, np.concatenate([ood_z, ood_zg]), ood_c, rng)
+    assert np.array_equal(fri.evaluations(), ref_evals)
+
+
+# ------------------------------------------------------------------------------------------------
+# FRI (K8) -- fri/src/prover/tests.rs style: build layers, open, compare with the restated prover
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("logM", [7, 10, 13, 16])
+def test_fri_layers_and_proof(ctx, oracle, logM):
+    M = 1 << logM
+    evals = oracle.synthetic_trace(1, M, 0xF1)[0]
+    fri = ctx.fri_from_evaluations(evals)
+    opts = oracle.ProofOptions()
+    coin_o, coin_g = oracle.RandomCoin(b"fri"), aero_b200.RandomCoin(b"fri")
+    layers, cur = [], evals
+    nl = opts.num_fri_layers(M)
+    for l in range(nl + 1):
+        root = fri.commit_layer()
+        def alpha_fn(r):
+            coin_o.reseed(r)
+            return coin_o.draw()
+        layer, cur = oracle.fri_build_layer(cur, 8, alpha_fn)
+        assert root == layer.nodes[1].tobytes(), "layer %d root" % l
+        coin_g.reseed(root)
+        alpha = coin_g.draw()
+        layers.append(layer)
+        if l < nl:
+            fri.fold(alpha)
+            assert np.array_equal(fri.evaluations(), cur), "fold %d" % l
+    positions = oracle.RandomCoin(b"q").draw_integers(min(27, M // 8 - 1), M)
+    got = fri.open(positions)
+    # expected bytes per FriProof::write_into
+    exp = bytearray([nl])
+    pos, dom = list(positions), M
+    for i in range(nl):
+        pos = oracle.fold_positions(pos, dom, 8)
+        vals = np.ascontiguousarray(layers[i].transposed[pos]).tobytes()
+        paths = oracle.serialize_nodes(oracle.prove_batch(layers[i].leaves, layers[i].nodes, pos))
+        exp += struct.pack("<I", len(vals)) + vals + struct.pack("<I", len(paths)) + paths
+        dom //= 8
+    rem = np.ascontiguousarray(layers[-1].transposed.T).reshape(-1).tobytes()
+    exp += struct.pack("<H", len(rem)) + rem + b"\0"
+    assert got == bytes(exp)
+
+
+def test_fri_state_errors(ctx, oracle):
+    """FriProver panics when misused (fri/src/prover/mod.rs:167-170,232-235) -> AERO_ERR_STATE."""
+    fri = ctx.fri_from_evaluations(oracle.synthetic_trace(1, 1024, 1)[0])
+    with pytest.raises(AeroError) as e:
+        fri.fold(5)
+    assert e.value.status == aero_b200.AERO_ERR_STATE
+    with pytest.raises(AeroError) as e:
+        fri.open([1, 2])
+    assert e.value.status == aero_b200.AERO_ERR_STATE
+    fri.commit_layer()
+    with pytest.raises(AeroError) as e:
+        fri.commit_layer()
+    assert e.value.status == aero_b200.AERO_ERR_STATE
+
+
+# ------------------------------------------------------------------------------------------------
+# grinding (K10)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits", [0, 1, 8, 16, 20])
+def test_pow_min_nonce(ctx, oracle, bits):
+    seed = oracle.blake2s(b"grind %d" % bits)
+    assert ctx.pow_min_nonce(seed, bits) == oracle.grind_min_nonce(seed, bits)
+
+
+def test_pow_reproduces_golden_nonce(ctx, oracle):
+    """The grinding nonce of the reference's golden proof (45692) is the minimum one."""
+    inp, proof = oracle.read_proof_file(os.path.join(os.path.dirname(__file__), "golden", "fib.bin"))
+    pr = oracle.StarkProof.from_bytes(proof)
+    coin = oracle.RandomCoin(oracle.miden_pub_inputs_seed(inp))
+    roots = [pr.commitments[i:i + 32] for i in range(0, len(pr.commitments), 32)]
+    coin.reseed(roots[0]); coin.reseed(roots[1]); coin.reseed(roots[2])
+    ood = oracle._felts(pr.ood_trace_states)
+    coin.reseed(oracle.hash_elements(ood[:81])); coin.reseed(oracle.hash_elements(ood[81:]))
+    coin.reseed(oracle.hash_elements(oracle._felts(pr.ood_evaluations)))
+    for r in roots[3:]:
+        coin.reseed(r)
+    assert ctx.pow_min_nonce(coin.seed, 16) == pr.pow_nonce == 45692
+
+
+# ------------------------------------------------------------------------------------------------
+# whole proof through the host driver: byte-identical to the restated reference prover
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("logn,wm,wa", [(10, 72, 9), (7, 4, 0), (12, 6, 2), (13, 72, 9)])
+def test_prove_byte_identical(ctx, ctx_mont, oracle, logn, wm, wa):
+    n = 1 << logn
+    main = oracle.synthetic_trace(wm, n)
+    aux = oracle.synthetic_trace(wa, n, 0xAE210000) if wa else None
+    ce, divs = oracle.synthetic_constraint_evaluations(n, 8) if logn <= 10 else (oracle.synthetic_trace(2, 8 * n, 0xCE), [
+        oracle.Divisor(n, 1, [pow(oracle.root_of_unity(logn), n - 1, P)]), oracle.Divisor(1, 1, [])])
+    pub = b"aero-b200 synthetic public inputs"
+    ref = oracle.prove(main, aux, ce, divs, pub, num_constraint_coeff_draws=10)
+    gdivs = [make_divisor(d.a, d.b, d.exemptions) for d in divs]
+    got = ctx.prove(main, aux, ce, gdivs, pub, n_constraint_coeffs=10)
+    assert got == ref.proof_bytes
+    oracle.verify(got, pub, 8)  # and the fib.bin-validated verifier model accepts it
+    if logn <= 10:
+        c2m = oracle.canon_to_mont
+        mdivs = [make_divisor(d.a, int(c2m(np.array([d.b], np.uint64))[0]),
+                              [int(v) for v in c2m(np.array(d.exemptions, np.uint64))]) for d in divs]
+        got_m = ctx_mont.prove(c2m(main), c2m(aux) if wa else None, c2m(ce), mdivs, pub, n_constraint_coeffs=10)
+        assert got_m == ref.proof_bytes
