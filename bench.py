@@ -231,7 +231,7 @@ def run_aero(args) -> None:
         barrier()
         return ms, out
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(1 if args.quick else max(args.warmup, 3)):
         step_device()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -246,6 +246,10 @@ def run_aero(args) -> None:
     ms_step = ms / args.steps
     value = world * n / (ms_step * 1e-3)
 
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms_step, "phase_ms": {k: v[1] / args.steps for k, v in prof.items()}}))
+        return
     step_host()  # warm the pinned path
     ms_e2e, proof_h = timed(step_host, max(1, args.steps // 2))
     ms_e2e /= max(1, args.steps // 2)
@@ -292,6 +296,8 @@ def main() -> None:
     ap.add_argument("--log-rows", type=int, default=20)
     ap.add_argument("--ref-log-rows", type=int, default=18, help="trace size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="profiling aid (ncu): 1 warm-up, no e2e / cpu legs; numbers printed are NOT bench values")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
