@@ -102,6 +102,7 @@ PROTOTYPES = {
     "aero_pow_min_nonce": (c_int, [c_void_p, p_u8, c_uint32, p_u64]),
     # standalone
     "aero_commit_rows_device": (c_int, [c_void_p, c_void_p, c_size_t, c_uint32, c_uint64, p_u8]),
+    "aero_test_field_ops": (c_int, [c_void_p, p_u64, p_u64, c_size_t, p_u64]),
     "aero_device_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "aero_device_free": (c_int, [c_void_p, c_void_p]),
     "aero_device_upload": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),

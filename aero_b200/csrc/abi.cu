@@ -627,6 +627,23 @@ aero_status aero_device_sync(aero_ctx *ctx) {
     return AERO_OK;
 }
 
+aero_status aero_test_field_ops(aero_ctx *ctx, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) {
+    if (!ctx || !a || !b || !out || !n) return AERO_ERR_INVALID;
+    uint64_t *da = nullptr, *db = nullptr, *dout = nullptr;
+    TRY(dev_alloc(ctx, (void **)&da, n * 8));
+    TRY(dev_alloc(ctx, (void **)&db, n * 8));
+    TRY(dev_alloc(ctx, (void **)&dout, 4 * n * 8));
+    CUDA_TRY(ctx, cudaMemcpyAsync(da, a, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(db, b, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    field_ops(da, db, n, dout, ctx->stream);
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, dout, 4 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, da);
+    dev_free(ctx, db);
+    dev_free(ctx, dout);
+    return AERO_OK;
+}
+
 // ---- segments -------------------------------------------------------------------------------
 aero_status aero_segment_commit_device(aero_ctx *ctx, const uint64_t *d_cols, size_t col_stride, uint32_t n_cols,
                                        uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,

@@ -25,14 +25,111 @@ constexpr uint64_t TWO_ADIC_ROOT = 1753635133440165772ULL;  // f64/mod.rs:43, or
 constexpr uint64_t MONT_R_INV = 18446744065119617025ULL;    // 2^-64 mod p
 // (2^-64 = 2^128 since 2^192 = 1;  2^128 = (2^96)*(2^32) = -2^32 = p - 2^32)
 
+// ---- device fast paths (32-bit carry chains in PTX) -------------------------------------------
+// "any" = a u64 congruent to the value mod p but not necessarily < p; "canonical" = in [0, p).
+// The compiler's 64-bit compare/select sequences cost ~2x the INT-pipe work of these chains, and
+// the NTT kernels are INT-pipe bound (profiles/r01_*): ptxas turns the mad.cc chain into
+// IMAD.WIDE.U32 with predicate carry-out, the rest into IADD3/IADD3.X.
+#if defined(__CUDACC__)
+// any x any -> any.  {hh:hl:lo} = a*b ;  lo - hh (borrow: -EPS) + hl*EPS (carry: +EPS)
+__device__ __forceinline__ uint64_t mul_any(uint64_t a, uint64_t b) {
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    uint32_t x0, x1;
+    asm("{\n\t"
+        ".reg .u32 r0, r1, r2, r3, m, c, t0, t1;\n\t"
+        "mul.lo.u32 r0, %2, %4;\n\t"
+        "mul.hi.u32 r1, %2, %4;\n\t"
+        "mad.lo.cc.u32 r1, %2, %5, r1;\n\t"
+        "madc.hi.u32 r2, %2, %5, 0;\n\t"
+        "mad.lo.cc.u32 r1, %3, %4, r1;\n\t"
+        "madc.hi.cc.u32 r2, %3, %4, r2;\n\t"
+        "addc.u32 r3, 0, 0;\n\t"
+        "mad.lo.cc.u32 r2, %3, %5, r2;\n\t"
+        "madc.hi.u32 r3, %3, %5, r3;\n\t"
+        "sub.cc.u32 %0, r0, r3;\n\t"
+        "subc.cc.u32 %1, r1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"          // borrow ? 0xffffffff (= EPS) : 0
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t"
+        "mul.lo.u32 t0, r2, 0xffffffff;\n\t"
+        "mul.hi.u32 t1, r2, 0xffffffff;\n\t"
+        "add.cc.u32 %0, %0, t0;\n\t"
+        "addc.cc.u32 %1, %1, t1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "neg.s32 c, c;\n\t"              // carry ? EPS : 0
+        "add.cc.u32 %0, %0, c;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(x0), "=&r"(x1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return ((uint64_t)x1 << 32) | x0;
+}
+// any -> canonical:  x >= p  <=>  x + EPS carries out of 64 bits (p + EPS = 2^64)
+__device__ __forceinline__ uint64_t canon_any(uint64_t x) {
+    uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), y0, y1;
+    asm("{\n\t"
+        ".reg .u32 t0, t1, c;\n\t"
+        ".reg .pred q;\n\t"
+        "add.cc.u32 t0, %2, 0xffffffff;\n\t"
+        "addc.cc.u32 t1, %3, 0;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "setp.ne.u32 q, c, 0;\n\t"
+        "selp.u32 %0, t0, %2, q;\n\t"
+        "selp.u32 %1, t1, %3, q;\n\t"
+        "}"
+        : "=r"(y0), "=r"(y1)
+        : "r"(x0), "r"(x1));
+    return ((uint64_t)y1 << 32) | y0;
+}
+// u any, v canonical -> any.  u + v < 2^64 + p, so one +EPS fix-up cannot carry again.
+__device__ __forceinline__ uint64_t add_ac(uint64_t u, uint64_t v) {
+    uint32_t u0 = (uint32_t)u, u1 = (uint32_t)(u >> 32), v0 = (uint32_t)v, v1 = (uint32_t)(v >> 32), y0, y1;
+    asm("{\n\t"
+        ".reg .u32 c;\n\t"
+        "add.cc.u32 %0, %2, %4;\n\t"
+        "addc.cc.u32 %1, %3, %5;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "neg.s32 c, c;\n\t"
+        "add.cc.u32 %0, %0, c;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(y0), "=&r"(y1)
+        : "r"(u0), "r"(u1), "r"(v0), "r"(v1));
+    return ((uint64_t)y1 << 32) | y0;
+}
+// u any, v canonical -> any (canonical when u is).  u - v > -p, so one -EPS fix-up cannot borrow again.
+__device__ __forceinline__ uint64_t sub_ac(uint64_t u, uint64_t v) {
+    uint32_t u0 = (uint32_t)u, u1 = (uint32_t)(u >> 32), v0 = (uint32_t)v, v1 = (uint32_t)(v >> 32), y0, y1;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(y0), "=&r"(y1)
+        : "r"(u0), "r"(u1), "r"(v0), "r"(v1));
+    return ((uint64_t)y1 << 32) | y0;
+}
+#endif
+
 GL_HD uint64_t add(uint64_t a, uint64_t b) {  // a, b canonical -> canonical  (f64/mod.rs:273)
+#if defined(__CUDA_ARCH__)
+    return canon_any(add_ac(a, b));
+#else
     uint64_t s = a + b;
     bool wrap = (s < a) | (s >= P);
     return s + (wrap ? EPS : 0ULL);  // s - p == s + EPS (mod 2^64)
+#endif
 }
 GL_HD uint64_t sub(uint64_t a, uint64_t b) {  // f64/mod.rs:293
+#if defined(__CUDA_ARCH__)
+    return sub_ac(a, b);
+#else
     uint64_t d = a - b;
     return d - ((a < b) ? EPS : 0ULL);  // d + p == d - EPS (mod 2^64)
+#endif
 }
 GL_HD uint64_t neg(uint64_t a) { return a ? P - a : 0ULL; }
 
@@ -64,9 +161,13 @@ GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t &lo, uint64_t &hi) {
 }
 
 GL_HD uint64_t mul(uint64_t a, uint64_t b) {  // f64/mod.rs:311
+#if defined(__CUDA_ARCH__)
+    return canon_any(mul_any(a, b));
+#else
     uint64_t lo, hi;
     mul_wide(a, b, lo, hi);
     return reduce128(lo, hi);
+#endif
 }
 GL_HD uint64_t sqr(uint64_t a) { return mul(a, a); }
 

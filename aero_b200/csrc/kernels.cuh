@@ -56,6 +56,7 @@ void pow_search(const uint32_t *seed, uint64_t base, uint32_t count, uint32_t bi
                 cudaStream_t s);
 
 // poly.cu
+void field_ops(const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out, cudaStream_t s);
 void convert_form(const uint64_t *src, uint64_t *dst, size_t count, int to_montgomery, cudaStream_t s);
 void lde_to_natural(const uint64_t *lde_cm, uint64_t *out, int logn, int log_blowup, int to_montgomery,
                     cudaStream_t s);

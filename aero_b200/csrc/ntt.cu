@@ -28,10 +28,11 @@ __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s
                 if (e & (1 << q)) continue;
                 const int k = low + ((e & ((1 << q) - 1)) << s0);
                 const uint64_t w = tw[(1 << (s0 + q)) + k];
+                // values in the tile stay "any" (congruent mod p, < 2^64); only v is canonicalised
                 const uint64_t u = x[e];
-                const uint64_t v = gl::mul(x[e | (1 << q)], w);
-                x[e] = gl::add(u, v);
-                x[e | (1 << q)] = gl::sub(u, v);
+                const uint64_t v = gl::canon_any(gl::mul_any(x[e | (1 << q)], w));
+                x[e] = gl::add_ac(u, v);
+                x[e | (1 << q)] = gl::sub_ac(u, v);
             }
         }
 #pragma unroll
@@ -108,9 +109,9 @@ __global__ void __launch_bounds__(512) dft_pass1_kernel(const uint64_t *__restri
     const uint64_t d = root_pow(wlo, whi, lo_bits, step_i1 * j2);
     const int nchunks = n1 / T;
     for (; c < nchunks; c += cstep, i1 += step_i1) {
-        const uint64_t v = gl::mul(a[i1 * RS + t], f);
+        const uint64_t v = gl::canon_any(gl::mul_any(a[i1 * RS + t], f));
         o[((size_t)c << log2) * T + (size_t)j2 * T + ii] = v;
-        f = gl::mul(f, d);
+        f = gl::mul_any(f, d);
     }
 }
 
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(512) dft_pass2_kernel(const uint64_t *__restri
         uint64_t v = a[i2 * RS + t];
         const uint32_t i1 = i1_0 + t;
         if (post_u) v = gl::mul(v, gl::mul(__ldg(post_u + i1), __ldg(post_v + i2)));
+        else v = gl::canon_any(v);
         const uint32_t i = i1 + ((uint32_t)i2 << log1);
         o[out_index(i, logn, deint)] = v;
     }
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(256) dft_single_kernel(const uint64_t *__restr
         uint64_t v = a[i];
         if (post_u) v = gl::mul(v, __ldg(post_u + i));
         else if (scale != 1) v = gl::mul(v, scale);
+        else v = gl::canon_any(v);
         o[out_index(i, logn, deint)] = v;
     }
 }

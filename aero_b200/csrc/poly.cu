@@ -20,6 +20,23 @@ void convert_form(const uint64_t *src, uint64_t *dst, size_t count, int to_montg
     convert_form_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dst, count, to_montgomery);
 }
 
+// Field-arithmetic self test: arbitrary u64 operands (reduced first where the operation requires
+// canonical inputs).  out: [mul, add, sub, mul of the raw (possibly non-canonical) operands]
+__global__ void field_ops_kernel(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, size_t n,
+                                 uint64_t *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t x = gl::canon(a[i]), y = gl::canon(b[i]);
+    out[i] = gl::mul(x, y);
+    out[n + i] = gl::add(x, y);
+    out[2 * n + i] = gl::sub(x, y);
+    out[3 * n + i] = gl::canon_any(gl::mul_any(a[i], b[i]));
+}
+void field_ops(const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out, cudaStream_t s) {
+    AERO_COUNT_LAUNCH(1);
+    field_ops_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a, b, n, out);
+}
+
 // coset-major LDE column (B cosets of n) -> natural order out[B*i + r] = lde[r*n + i]
 // (the order Matrix::evaluate_columns_over returns, matrix.rs:189-201)
 __global__ void lde_to_natural_kernel(const uint64_t *__restrict__ lde, uint64_t *__restrict__ out, int logn,

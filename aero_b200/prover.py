@@ -172,6 +172,14 @@ class Context:
         self._check(self.lib.aero_fri_from_evaluations(self.h, ev.ctypes.data_as(p_u64), ev.size, ctypes.byref(fri)))
         return FriProver(self, fri)
 
+    def test_field_ops(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, np.uint64)
+        b = np.ascontiguousarray(b, np.uint64)
+        out = np.empty((4, a.size), np.uint64)
+        self._check(self.lib.aero_test_field_ops(self.h, a.ctypes.data_as(p_u64), b.ctypes.data_as(p_u64), a.size,
+                                                 out.ctypes.data_as(p_u64)))
+        return out
+
     def pow_min_nonce(self, seed: bytes, grinding_bits: int) -> int:
         s = (c_uint8 * 32).from_buffer_copy(seed)
         nonce = c_uint64()

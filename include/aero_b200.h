@@ -155,6 +155,10 @@ aero_status aero_pow_min_nonce(aero_ctx *ctx, const uint8_t seed[32], uint32_t g
 /* Matrix::commit_to_rows on a natural-order device matrix (column c at d_m + c*col_stride). */
 aero_status aero_commit_rows_device(aero_ctx *ctx, const uint64_t *d_m, size_t col_stride, uint32_t n_cols,
                                     uint64_t n_rows, uint8_t root[32]);
+/* Self-test of the device Goldilocks arithmetic (math/src/field/f64/mod.rs:273-330): for n operand
+ * pairs (any u64; reduced mod p first) writes out[0..n) = a*b, out[n..2n) = a+b, out[2n..3n) = a-b
+ * (canonical) and out[3n..4n) = a*b computed from the unreduced operands. */
+aero_status aero_test_field_ops(aero_ctx *ctx, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
 /* Device scratch helpers so callers without a CUDA runtime binding can stage data. */
 aero_status aero_device_alloc(aero_ctx *ctx, size_t bytes, void **d_ptr);
 aero_status aero_device_free(aero_ctx *ctx, void *d_ptr);

@@ -299,3 +299,26 @@ def test_prove_byte_identical(ctx, ctx_mont, oracle, logn, wm, wa):
                               [int(v) for v in c2m(np.array(d.exemptions, np.uint64))]) for d in divs]
         got_m = ctx_mont.prove(c2m(main), c2m(aux) if wa else None, c2m(ce), mdivs, pub, n_constraint_coeffs=10)
         assert got_m == ref.proof_bytes
+
+
+# ------------------------------------------------------------------------------------------------
+# field arithmetic edge cases (winterfell/math/src/field/f64/tests.rs:17-143): overflow / borrow /
+# non-canonical operands that random data hits with probability ~2^-32
+# ------------------------------------------------------------------------------------------------
+def test_field_ops_edge_cases(ctx, oracle):
+    E = 0xFFFFFFFF
+    special = [0, 1, 2, 7, E - 1, E, E + 1, E + 2, 1 << 32, (1 << 32) + 1, 1 << 48, (1 << 48) + 12345, 1 << 63, (1 << 63) + 1,
+               P - 1, P - 2, P - E, P - E - 1, (P + 1) // 2, (P - 1) // 2, P, P + 1, P + E - 1, (1 << 64) - 1, (1 << 64) - 2,
+               (1 << 64) - E, 0xFFFFFFFE00000001, 0xFFFFFFFF00000000, 0x00000000FFFFFFFF, 0xFFFFFFFEFFFFFFFF,
+               0x0000000100000000, 0x8000000000000000, 0x7FFFFFFFFFFFFFFF, 1753635133440165772]
+    rnd = [int(v) for v in oracle.splitmix64_column(0xF1E1D, 64)]
+    vals = special + rnd
+    a = np.array([x for x in vals for _ in vals], np.uint64)
+    b = np.array([y for _ in vals for y in vals], np.uint64)
+    out = ctx.test_field_ops(a, b)
+    ai = [int(x) % P for x in a]
+    bi = [int(y) % P for y in b]
+    assert [int(v) for v in out[0]] == [x * y % P for x, y in zip(ai, bi)], "mul"
+    assert [int(v) for v in out[1]] == [(x + y) % P for x, y in zip(ai, bi)], "add"
+    assert [int(v) for v in out[2]] == [(x - y) % P for x, y in zip(ai, bi)], "sub"
+    assert [int(v) for v in out[3]] == [int(x) * int(y) % P for x, y in zip(a, b)], "mul of unreduced operands"
