@@ -1,0 +1,104 @@
+"""CPU tests of the product's host side: the shared library loads, exports every symbol the headers
+declare, refuses to run without a GPU (no CPU fallback), and its host Fiat-Shamir code agrees with
+the oracle / golden vectors.  No compute kernels are launched here."""
+import hashlib
+import os
+import re
+
+import pytest
+
+import aero_b200
+from oracle import stark_oracle as so
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for h in ("aero_b200.h", "aero_prover.h"):
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(aero_[a-z0-9_]+)\s*\(", text))
+    return names - {"aero_aux_builder", "aero_constraint_evaluator", "aero_status"}  # function-pointer typedefs
+
+
+def test_library_exports_every_declared_symbol():
+    lib = aero_b200.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 45
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libaero_b200.so does not export %s" % name
+    # ...and the ctypes table covers exactly the declared ABI
+    assert set(aero_b200._lib.PROTOTYPES) == declared
+
+
+def test_library_is_built_for_sm_100a():
+    so_path = aero_b200.build.LIB
+    assert os.path.exists(so_path)
+    blob = open(so_path, "rb").read()
+    assert b"sm_100a" in blob, "no sm_100a cubin embedded"
+
+
+def test_context_fails_loudly_without_gpu():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(aero_b200.AeroError) as e:
+        aero_b200.Context()
+    assert e.value.status == aero_b200.AERO_ERR_CUDA
+
+
+def test_product_does_not_import_the_oracle():
+    """The product path must never route through oracle/ (it is test infrastructure)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "aero_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower().replace("starkoracles", ""), "%s mentions the oracle" % f
+
+
+def test_host_blake2s_and_hash_elements():
+    data = bytes(range(256)) * 2
+    for ln in (0, 1, 32, 40, 63, 64, 65, 128, 129, 500):
+        assert aero_b200.host_blake2s(data[:ln]) == hashlib.blake2s(data[:ln]).digest()
+    for elems in ([3], [1, 2], list(range(81)), [so.P - 1] * 8):
+        assert aero_b200.host_hash_elements(elems) == so.hash_elements(elems)
+
+
+def test_host_coin_known_answers_and_oracle_agreement():
+    inp, _ = so.read_proof_file(os.path.join(ROOT, "tests", "golden", "fib.bin"))
+    seed = so.miden_pub_inputs_seed(inp)
+    c = aero_b200.RandomCoin(seed)
+    assert c.draw() == 15636605459427237624  # tests/integration/test_verifier.cairo:104
+    assert c.draw_integers(20, 64) == [55, 46, 17, 44, 61, 8, 43, 39, 19, 3, 26, 31, 30, 4, 37, 40, 49, 7, 56, 29]
+    a, b = aero_b200.RandomCoin(b"x"), so.RandomCoin(b"x")
+    for step in range(20):
+        if step % 3 == 0:
+            d = so.blake2s(b"%d" % step)
+            a.reseed(d)
+            b.reseed(d)
+        elif step % 7 == 0:
+            a.reseed_with_int(step)
+            b.reseed_with_int(step)
+        assert a.draw() == b.draw()
+        assert a.seed == b.seed
+        assert a.leading_zeros() == b.leading_zeros()
+        assert a.check_leading_zeros(step) == b.check_leading_zeros(step)
+    assert a.draw_integers(27, 8192) == b.draw_integers(27, 8192)
+    with pytest.raises(RuntimeError):
+        a.draw_integers(64, 64)  # num_values must be smaller than the domain (random/mod.rs:262-265)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """bench.py --impl reference: JSON line with the contract keys, from the oracle port."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--ref-log-rows", "10"], capture_output=True, text=True, check=True)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "trace_rows_per_s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
