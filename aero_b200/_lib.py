@@ -47,13 +47,18 @@ AUX_BUILDER = ctypes.CFUNCTYPE(c_int, c_void_p, p_u64, c_uint32, pp_u64)
 CONSTRAINT_EVALUATOR = ctypes.CFUNCTYPE(c_int, c_void_p, pp_u64, c_uint32, c_uint64, p_u64, c_uint32, pp_u64)
 
 
+ALL_GATHER_COSETS = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_int, c_uint32, c_uint32)
+SUM_ROWS = ctypes.CFUNCTYPE(c_int, c_void_p, p_u64, c_uint64)
+
+
 class ProveInputs(ctypes.Structure):
     _fields_ = [("options", ProofOptions), ("trace_len", c_uint64), ("main_width", c_uint32), ("aux_width", c_uint32),
                 ("aux_rands", c_uint32), ("inputs_on_device", c_int), ("main_cols", pp_u64), ("aux_cols", pp_u64),
                 ("ce_cols", pp_u64), ("divisors", POINTER(Divisor)), ("n_div", c_uint32),
                 ("n_constraint_coeffs", c_uint32), ("aux_builder", AUX_BUILDER),
                 ("constraint_evaluator", CONSTRAINT_EVALUATOR), ("user", c_void_p), ("pub_inputs_bytes", p_u8),
-                ("pub_inputs_len", c_size_t), ("trace_meta", p_u8), ("trace_meta_len", c_uint16)]
+                ("pub_inputs_len", c_size_t), ("trace_meta", p_u8), ("trace_meta_len", c_uint16),
+                ("all_gather_cosets", ALL_GATHER_COSETS), ("sum_rows", SUM_ROWS)]
 
 
 # name -> (restype, argtypes).  Every symbol include/*.h declares is listed here; tests assert that
@@ -75,6 +80,13 @@ PROTOTYPES = {
     "aero_segment_commit": (c_int, [c_void_p, pp_u64, c_uint32, c_uint64, c_uint32, c_int, POINTER(c_void_p), p_u8]),
     "aero_segment_commit_device": (c_int, [c_void_p, c_void_p, c_size_t, c_uint32, c_uint64, c_uint32, c_int,
                                            POINTER(c_void_p), p_u8]),
+    "aero_ctx_set_shard": (c_int, [c_void_p, c_int, c_int]),
+    "aero_segment_leaves_device": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_uint32),
+                                           POINTER(c_uint32)]),
+    "aero_segment_finish_tree": (c_int, [c_void_p, p_u8]),
+    "aero_fri_evaluations_device": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_uint32),
+                                            POINTER(c_uint32)]),
+    "aero_fri_mark_complete": (c_int, [c_void_p]),
     "aero_segment_destroy": (None, [c_void_p]),
     "aero_segment_info": (c_int, [c_void_p, POINTER(c_uint32), POINTER(c_uint64), POINTER(c_uint32)]),
     "aero_segment_download_lde": (c_int, [c_void_p, pp_u64]),

@@ -48,6 +48,7 @@ struct aero_ctx {
     std::map<std::string, PowTableOwned> pow_tables;
     std::vector<void *> owned;  // device allocations freed with the context
     size_t lde_batch_bytes = (size_t)1 << 30;  // NTT scratch budget per column batch
+    int shard_rank = 0, shard_world = 1;       // LDE coset shard of this context (multi-GPU)
 };
 
 #define CTX_FAIL(ctx, code, ...)                         \
@@ -303,9 +304,29 @@ struct aero_segment {
     uint64_t *polys = nullptr;                 // ncols x n, canonical coefficients
     uint64_t *lde = nullptr;                   // ncols x N, coset-major (coset r, i) -> natural B*i + r
     uint32_t *full = nullptr;                  // 2N digests, heap layout, leaf k at N + k
+    // coset shard (multi-GPU): this rank stores cosets [coset_begin, coset_begin + coset_count) only,
+    // compactly: lde[c][q][i] with q = r - coset_begin, column stride coset_count * n.
+    int coset_begin = 0, coset_count = 0;
+    bool tree_pending = false;                 // leaves of other ranks still missing
     uint64_t n() const { return 1ULL << logn; }
     uint64_t N() const { return 1ULL << (logn + log_blowup); }
+    uint64_t lde_stride() const { return (uint64_t)coset_count << logn; }
 };
+
+static aero_status segment_finish_tree(aero_segment *seg, uint8_t root[32]) {
+    aero_ctx *ctx = seg->ctx;
+    {
+        PhaseTimer t(ctx, "merkle");
+        merkle_build(seg->full, seg->N(), ctx->stream);
+    }
+    seg->tree_pending = false;
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (root) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(root, seg->full + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return AERO_OK;
+}
 
 static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint8_t root[32]) {
     aero_ctx *ctx = seg->ctx;
@@ -315,7 +336,11 @@ static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint
     seg->log_blowup = log_blowup;
     const uint64_t n = seg->n(), N = seg->N();
     const int B = 1 << log_blowup;
-    TRY(dev_alloc(ctx, (void **)&seg->lde, (size_t)seg->ncols * N * 8));
+    if (B % ctx->shard_world) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "shard world size %d must divide the blowup factor %d", ctx->shard_world, B);
+    seg->coset_count = B / ctx->shard_world;
+    seg->coset_begin = ctx->shard_rank * seg->coset_count;
+    const uint64_t Nl = seg->lde_stride();  // rows stored on this rank
+    TRY(dev_alloc(ctx, (void **)&seg->lde, (size_t)seg->ncols * Nl * 8));
     TRY(dev_alloc(ctx, (void **)&seg->full, (size_t)2 * N * 32));
     const DftTables *plan;
     TRY(plan_lde(ctx, seg->logn, log_blowup, false, &plan));
@@ -326,19 +351,21 @@ static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint
         int batch = seg->ncols;
         uint64_t *tmp = nullptr;
         if (plan->log1 != 0) {
-            batch = (int)std::max<size_t>(1, ctx->lde_batch_bytes / ((size_t)B * n * 8));
+            batch = (int)std::max<size_t>(1, ctx->lde_batch_bytes / ((size_t)Nl * 8));
             batch = std::min(batch, seg->ncols);
-            TRY(dev_alloc(ctx, (void **)&tmp, (size_t)batch * B * n * 8));
+            TRY(dev_alloc(ctx, (void **)&tmp, (size_t)batch * Nl * 8));
         }
         for (int c0 = 0; c0 < seg->ncols; c0 += batch) {
             DftLaunch l;
             l.src = seg->polys + (size_t)c0 * n;
-            l.dst = seg->lde + (size_t)c0 * N;
+            l.dst = seg->lde + (size_t)c0 * Nl;
             l.tmp = tmp;
             l.src_col_stride = n;
-            l.dst_col_stride = N;
+            l.dst_col_stride = Nl;
             l.ncols = std::min(batch, seg->ncols - c0);
             l.deinterleave_log = 0;
+            l.coset_begin = seg->coset_begin;
+            l.coset_count = seg->coset_count;
             dft_run(*plan, l, ctx->stream);
         }
         dev_free(ctx, tmp);
@@ -347,20 +374,19 @@ static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint
         char nm[32];
         snprintf(nm, sizeof nm, "hash_rows_w%d", seg->ncols);
         PhaseTimer t(ctx, nm);
-        hash_rows_lde(seg->lde, N, seg->ncols, seg->logn, log_blowup, 0, (uint32_t)N, seg->full + (size_t)N * 8,
-                      ctx->stream);
+        hash_rows_lde(seg->lde, Nl, seg->ncols, seg->logn, log_blowup, seg->coset_begin, (uint32_t)Nl,
+                      seg->full + (size_t)N * 8, ctx->stream);
     }
-    {
-        PhaseTimer t(ctx, "merkle");
-        CUDA_TRY(ctx, cudaMemsetAsync(seg->full, 0, 64, ctx->stream));
-        merkle_build(seg->full, N, ctx->stream);
+    CUDA_TRY(ctx, cudaMemsetAsync(seg->full, 0, 64, ctx->stream));
+    if (ctx->shard_world > 1) {
+        // leaves of the other ranks' cosets arrive through the caller's exchange; see
+        // aero_segment_leaves_device / aero_segment_finish_tree
+        seg->tree_pending = true;
+        if (root) memset(root, 0, 32);
+        CUDA_TRY(ctx, cudaGetLastError());
+        return AERO_OK;
     }
-    CUDA_TRY(ctx, cudaGetLastError());
-    if (root) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(root, seg->full + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    return AERO_OK;
+    return segment_finish_tree(seg, root);
 }
 
 // d_src: ncols columns (stride src_stride) of n values in ABI form, on the device
@@ -514,6 +540,8 @@ struct aero_fri {
     uint32_t curM = 0;
     int cur_log_cosets = 0;
     bool cur_committed = false;
+    bool cur_pending = false;  // coset-sharded DEEP evaluations not exchanged yet
+    int coset_begin = 0, coset_count = 0;
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -677,6 +705,31 @@ aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint
     return st;
 }
 
+aero_status aero_ctx_set_shard(aero_ctx *ctx, int rank, int world) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (world < 1 || rank < 0 || rank >= world || (world & (world - 1))) CTX_FAIL(ctx, AERO_ERR_INVALID, "bad shard %d of %d (world must be a power of two)", rank, world);
+    ctx->shard_rank = rank;
+    ctx->shard_world = world;
+    return AERO_OK;
+}
+aero_status aero_segment_leaves_device(aero_segment *seg, void **d_leaves, uint64_t *n_leaves, uint32_t *coset_begin,
+                                       uint32_t *coset_count) {
+    if (!seg || !d_leaves) return AERO_ERR_INVALID;
+    aero_ctx *ctx = seg->ctx;
+    if (!seg->full) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no commitment");
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the caller's exchange may run on another stream
+    *d_leaves = seg->full + (size_t)seg->N() * 8;
+    if (n_leaves) *n_leaves = seg->N();
+    if (coset_begin) *coset_begin = (uint32_t)seg->coset_begin;
+    if (coset_count) *coset_count = (uint32_t)seg->coset_count;
+    return AERO_OK;
+}
+aero_status aero_segment_finish_tree(aero_segment *seg, uint8_t root[32]) {
+    if (!seg) return AERO_ERR_INVALID;
+    if (!seg->full) CTX_FAIL(seg->ctx, AERO_ERR_STATE, "segment has no commitment");
+    return segment_finish_tree(seg, root);
+}
+
 void aero_segment_destroy(aero_segment *seg) {
     if (!seg) return;
     dev_free(seg->ctx, seg->polys);
@@ -701,6 +754,7 @@ aero_status aero_segment_download_lde(aero_segment *seg, uint64_t *const *cols_o
     if (!seg || !cols_out) return AERO_ERR_INVALID;
     aero_ctx *ctx = seg->ctx;
     if (!seg->lde) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no LDE");
+    if (seg->coset_count != (1 << seg->log_blowup)) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "download_lde on a coset-sharded segment");
     const uint64_t N = seg->N();
     PhaseTimer t(ctx, "download_lde");
     uint64_t *tmp = nullptr;
@@ -747,6 +801,7 @@ aero_status aero_segment_open(aero_segment *seg, const uint64_t *positions, uint
     if (!seg || !positions || !len) return AERO_ERR_INVALID;
     aero_ctx *ctx = seg->ctx;
     if (!seg->full) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no commitment");
+    if (seg->tree_pending) CTX_FAIL(ctx, AERO_ERR_STATE, "sharded segment: exchange leaves and call aero_segment_finish_tree first");
     const uint64_t N = seg->N();
     std::vector<std::vector<uint32_t>> idx;
     TRY(batch_proof_indices(ctx, positions, n_pos, N, idx));
@@ -766,7 +821,8 @@ aero_status aero_segment_open(aero_segment *seg, const uint64_t *positions, uint
         TRY(dev_alloc(ctx, (void **)&d_pos, n_pos * 4));
         TRY(dev_alloc(ctx, (void **)&d_rows, (size_t)n_pos * seg->ncols * 8));
         CUDA_TRY(ctx, cudaMemcpyAsync(d_pos, pos.data(), n_pos * 4, cudaMemcpyHostToDevice, ctx->stream));
-        gather_rows(seg->lde, N, seg->ncols, seg->logn, seg->log_blowup, d_pos, (int)n_pos, d_rows, ctx->stream);
+        gather_rows(seg->lde, seg->lde_stride(), seg->ncols, seg->logn, seg->log_blowup, seg->coset_begin,
+                    seg->coset_count, d_pos, (int)n_pos, d_rows, ctx->stream);
         CUDA_TRY(ctx, cudaMemcpyAsync(rows_out, d_rows, (size_t)n_pos * seg->ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         dev_free(ctx, d_pos);
@@ -1067,8 +1123,17 @@ aero_status aero_deep_compose(aero_ctx *ctx, aero_segment *const *trace_segs, ui
                 l.dst_col_stride = N;
                 l.ncols = 1;
                 l.deinterleave_log = 0;
+                // coset shard: own cosets only, written at their global slots so that an in-place
+                // all-gather completes the buffer
+                const int B = 1 << log_blowup;
+                fri->coset_count = B / ctx->shard_world;
+                fri->coset_begin = ctx->shard_rank * fri->coset_count;
+                l.coset_begin = fri->coset_begin;
+                l.coset_count = fri->coset_count;
+                l.dst = fri->cur + (size_t)fri->coset_begin * n;
                 dft_run(*plan, l, ctx->stream);
                 dev_free(ctx, tmp);
+                fri->cur_pending = ctx->shard_world > 1;
             }
         }
     }
@@ -1130,11 +1195,29 @@ aero_status aero_fri_download_evaluations(aero_fri *fri, uint64_t *out, uint64_t
     return AERO_OK;
 }
 
+aero_status aero_fri_evaluations_device(aero_fri *fri, void **d_evals, uint64_t *count, uint32_t *coset_begin,
+                                        uint32_t *coset_count) {
+    if (!fri || !d_evals) return AERO_ERR_INVALID;
+    aero_ctx *ctx = fri->ctx;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *d_evals = fri->cur;
+    if (count) *count = fri->curM;
+    if (coset_begin) *coset_begin = (uint32_t)fri->coset_begin;
+    if (coset_count) *coset_count = (uint32_t)fri->coset_count;
+    return AERO_OK;
+}
+aero_status aero_fri_mark_complete(aero_fri *fri) {
+    if (!fri) return AERO_ERR_INVALID;
+    fri->cur_pending = false;
+    return AERO_OK;
+}
+
 aero_status aero_fri_commit_layer(aero_fri *fri, uint8_t root[32]) {
     if (!fri || !root) return AERO_ERR_INVALID;
     aero_ctx *ctx = fri->ctx;
     if (!fri->cur) CTX_FAIL(ctx, AERO_ERR_STATE, "no evaluations to commit");
     if (fri->cur_committed) CTX_FAIL(ctx, AERO_ERR_STATE, "layer already committed; fold first");
+    if (fri->cur_pending) CTX_FAIL(ctx, AERO_ERR_STATE, "sharded DEEP evaluations: exchange them and call aero_fri_mark_complete first");
     const uint32_t rows = fri->curM / 8;
     if (rows < 2) CTX_FAIL(ctx, AERO_ERR_INVALID, "FRI layer of %u evaluations is too small to commit", fri->curM);
     if (fri->cur_log_cosets && (rows >> fri->cur_log_cosets) == 0) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "layer too small for coset-major layout");

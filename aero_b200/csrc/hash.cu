@@ -26,8 +26,8 @@ __device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t h[8]) 
 // coalesced 8-byte-per-lane stream.  The digest goes to the natural slot leaves[k].
 __global__ void __launch_bounds__(256) hash_rows_kernel(const uint64_t *__restrict__ lde, size_t col_stride, int ncols,
                                                         uint32_t nrows, int logn, int log_blowup,
-                                                        uint32_t row_begin, uint32_t *__restrict__ leaves) {
-    const uint32_t rho = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+                                                        uint32_t coset_begin, uint32_t *__restrict__ leaves) {
+    const uint32_t rho = blockIdx.x * blockDim.x + threadIdx.x;  // local storage row (coset q = rho >> logn)
     if (rho >= nrows) return;
     uint32_t h[8];
     b2s::init(h);
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) hash_rows_kernel(const uint64_t *__restri
         e1 = n1;
     }
     const uint32_t n_mask = (1u << logn) - 1;
-    const uint32_t k = ((rho & n_mask) << log_blowup) | (rho >> logn);
+    const uint32_t k = ((rho & n_mask) << log_blowup) | ((rho >> logn) + coset_begin);
     store_digest(leaves + (size_t)k * 8, h);
 }
 
@@ -130,12 +130,12 @@ void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s) {
     }
 }
 
-void hash_rows_lde(const uint64_t *lde, size_t col_stride, int ncols, int logn, int log_blowup, uint32_t row_begin,
-                   uint32_t row_end, uint32_t *leaves, cudaStream_t s) {
-    const uint32_t count = row_end - row_begin;
-    if (count == 0) return;
+// nrows = (number of locally stored cosets) * n ; local coset q holds natural rows B*i + coset_begin + q
+void hash_rows_lde(const uint64_t *lde, size_t col_stride, int ncols, int logn, int log_blowup, uint32_t coset_begin,
+                   uint32_t nrows, uint32_t *leaves, cudaStream_t s) {
+    if (nrows == 0) return;
     AERO_COUNT_LAUNCH(1);
-    hash_rows_kernel<<<(count + 255) / 256, 256, 0, s>>>(lde, col_stride, ncols, row_end, logn, log_blowup, row_begin,
+    hash_rows_kernel<<<(nrows + 255) / 256, 256, 0, s>>>(lde, col_stride, ncols, nrows, logn, log_blowup, coset_begin,
                                                          leaves);
 }
 void hash_rows_natural(const uint64_t *m, size_t col_stride, int ncols, uint32_t nrows, uint32_t *leaves,

@@ -46,8 +46,8 @@ __device__ __forceinline__ void fri_gather8(const uint64_t *__restrict__ f, uint
 #endif
 
 // hash.cu
-void hash_rows_lde(const uint64_t *lde, size_t col_stride, int ncols, int logn, int log_blowup, uint32_t row_begin,
-                   uint32_t row_end, uint32_t *leaves, cudaStream_t s);
+void hash_rows_lde(const uint64_t *lde, size_t col_stride, int ncols, int logn, int log_blowup, uint32_t coset_begin,
+                   uint32_t nrows, uint32_t *leaves, cudaStream_t s);
 void hash_rows_natural(const uint64_t *m, size_t col_stride, int ncols, uint32_t nrows, uint32_t *leaves,
                        cudaStream_t s);
 void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s);
@@ -77,8 +77,8 @@ void syn_div3(uint64_t *t1, uint64_t *t2, uint64_t *h, int logn, const uint64_t 
               cudaStream_t s);
 void deep_finish(const uint64_t *t1, const uint64_t *t2, const uint64_t *h, int logn, uint64_t d0, uint64_t d1,
                  uint64_t *out, cudaStream_t s);
-void gather_rows(const uint64_t *lde_cm, size_t col_stride, int ncols, int logn, int log_blowup,
-                 const uint32_t *d_positions, int npos, uint64_t *d_out, cudaStream_t s);
+void gather_rows(const uint64_t *lde_cm, size_t col_stride, int ncols, int logn, int log_blowup, int coset_begin,
+                 int coset_count, const uint32_t *d_positions, int npos, uint64_t *d_out, cudaStream_t s);
 void gather_fri_rows(const uint64_t *f, uint32_t rows, int log_cosets, const uint32_t *d_positions, int npos,
                      uint64_t *d_out, cudaStream_t s);
 void gather_digests(const uint32_t *full, const uint32_t *d_idx, int count, uint32_t *d_out, cudaStream_t s);

@@ -183,6 +183,9 @@ __global__ void __launch_bounds__(256) dft_single_kernel(const uint64_t *__restr
 template <int T>
 static void launch_two_pass(const DftTables &t, const DftLaunch &l, cudaStream_t s) {
     const int n1 = 1 << t.log1, n2 = 1 << t.log2;
+    const int nc = l.coset_count ? l.coset_count : t.ncosets;
+    const uint64_t *stage1 = t.stage1 + (size_t)l.coset_begin * n1;
+    const uint64_t *inter_b = t.inter_b + (size_t)l.coset_begin * n2;
     const size_t smem1 = (size_t)n1 * (T + 1) * 8 + (size_t)n1 * 8;
     const size_t smem2 = (size_t)n2 * (T + 1) * 8 + (size_t)n2 * 8;
     static bool attr_set = false;
@@ -197,21 +200,22 @@ static void launch_two_pass(const DftTables &t, const DftLaunch &l, cudaStream_t
         th = (th / (T * T)) * (T * T);
         return th < T * T ? T * T : th;
     };
-    dim3 g1(n2 / T, t.ncosets, l.ncols), g2(n1 / T, t.ncosets, l.ncols);
+    dim3 g1(n2 / T, nc, l.ncols), g2(n1 / T, nc, l.ncols);
     AERO_COUNT_LAUNCH(2);
-    dft_pass1_kernel<T><<<g1, threads_for(n1), smem1, s>>>(l.src, l.tmp, t.stage1, t.inter_b, t.wlo, t.whi, t.lo_bits,
-                                                           t.log1, t.log2, l.src_col_stride, t.ncosets);
+    dft_pass1_kernel<T><<<g1, threads_for(n1), smem1, s>>>(l.src, l.tmp, stage1, inter_b, t.wlo, t.whi, t.lo_bits,
+                                                           t.log1, t.log2, l.src_col_stride, nc);
     dft_pass2_kernel<T><<<g2, threads_for(n2), smem2, s>>>(l.tmp, l.dst, t.stage2, t.post_u, t.post_v, t.log1, t.log2,
-                                                           l.dst_col_stride, t.ncosets, l.deinterleave_log);
+                                                           l.dst_col_stride, nc, l.deinterleave_log);
 }
 
 void dft_run(const DftTables &t, const DftLaunch &l, cudaStream_t s) {
     if (t.log1 == 0) {
         const int n = 1 << t.logn;
         int th = n / 8 < 32 ? 32 : (n / 8 > 256 ? 256 : n / 8);
-        dim3 g(1, t.ncosets, l.ncols);
+        const int nc = l.coset_count ? l.coset_count : t.ncosets;
+        dim3 g(1, nc, l.ncols);
         AERO_COUNT_LAUNCH(1);
-        dft_single_kernel<<<g, th, (size_t)n * 16, s>>>(l.src, l.dst, t.stage2, t.post_u, t.single_scale, t.logn,
+        dft_single_kernel<<<g, th, (size_t)n * 16, s>>>(l.src, l.dst, t.stage2 + (size_t)l.coset_begin * n, t.post_u, t.single_scale, t.logn,
                                                        l.src_col_stride, l.dst_col_stride, l.deinterleave_log);
         return;
     }

@@ -39,6 +39,8 @@ struct DftLaunch {
     size_t src_col_stride, dst_col_stride;
     int ncols;
     int deinterleave_log;  // >0: natural index i is stored at (i & (2^d-1))*(n>>d) + (i>>d)
+    int coset_begin = 0;   // transform only cosets [coset_begin, coset_begin + coset_count) of the plan;
+    int coset_count = 0;   //   0 = all.  Coset (coset_begin + q) is stored at local slot q of dst/tmp.
 };
 
 void dft_run(const DftTables &t, const DftLaunch &l, cudaStream_t s);

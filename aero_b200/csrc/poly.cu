@@ -317,22 +317,29 @@ void deep_finish(const uint64_t *t1, const uint64_t *t2, const uint64_t *h, int 
 // K9: query gathers (prover/src/trace/commitment.rs:115-140, constraints/commitment.rs:54-70,
 // fri/src/prover/mod.rs:282-302, crypto/src/merkle/mod.rs:188-250 for the node list)
 // ---------------------------------------------------------------------------------------------
+// Rows whose coset is not stored on this rank come back as zeros (the ranks' results are disjoint
+// and are summed by the caller's exchange).
 __global__ void gather_rows_kernel(const uint64_t *__restrict__ lde, size_t col_stride, int ncols, int logn,
-                                   int log_blowup, const uint32_t *__restrict__ pos, int npos,
-                                   uint64_t *__restrict__ out) {
+                                   int log_blowup, int coset_begin, int coset_count,
+                                   const uint32_t *__restrict__ pos, int npos, uint64_t *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npos * ncols) return;
     const int p = i / ncols, c = i - p * ncols;
     const uint32_t k = pos[p];
-    const size_t rho = ((size_t)(k & ((1u << log_blowup) - 1)) << logn) + (k >> log_blowup);
+    const int q = (int)(k & ((1u << log_blowup) - 1)) - coset_begin;
+    if (q < 0 || q >= coset_count) {
+        out[i] = 0;
+        return;
+    }
+    const size_t rho = ((size_t)q << logn) + (k >> log_blowup);
     out[i] = lde[(size_t)c * col_stride + rho];
 }
-void gather_rows(const uint64_t *lde_cm, size_t col_stride, int ncols, int logn, int log_blowup,
-                 const uint32_t *d_positions, int npos, uint64_t *d_out, cudaStream_t s) {
+void gather_rows(const uint64_t *lde_cm, size_t col_stride, int ncols, int logn, int log_blowup, int coset_begin,
+                 int coset_count, const uint32_t *d_positions, int npos, uint64_t *d_out, cudaStream_t s) {
     const int total = npos * ncols;
     AERO_COUNT_LAUNCH(1);
-    gather_rows_kernel<<<(total + 127) / 128, 128, 0, s>>>(lde_cm, col_stride, ncols, logn, log_blowup, d_positions,
-                                                           npos, d_out);
+    gather_rows_kernel<<<(total + 127) / 128, 128, 0, s>>>(lde_cm, col_stride, ncols, logn, log_blowup, coset_begin,
+                                                           coset_count, d_positions, npos, d_out);
 }
 __global__ void gather_fri_rows_kernel(const uint64_t *__restrict__ f, uint32_t rows, int log_cosets,
                                        const uint32_t *__restrict__ pos, int npos, uint64_t *__restrict__ out) {

@@ -255,13 +255,31 @@ struct Handles {  // RAII for the device handles of one proof
 
 extern "C" int aero_ctx_get_form(aero_ctx *ctx);
 
+// Multi-GPU: complete a coset-sharded commitment (exchange leaf digests, then build the tree).
+static aero_status finish_commit(aero_ctx *ctx, const aero_prove_inputs &in, aero_segment *seg, uint32_t blowup,
+                                 uint8_t root[32], std::string *err) {
+    if (!in.all_gather_cosets) return AERO_OK;
+    void *d = nullptr;
+    uint64_t nl = 0;
+    uint32_t cb = 0, cc = 0;
+    P_TRY(aero_segment_leaves_device(seg, &d, &nl, &cb, &cc));
+    aero_status st = in.all_gather_cosets(in.user, d, nl / blowup, blowup, 32, 1, cb, cc);
+    if (st != AERO_OK) P_FAIL(st, "all_gather_cosets callback failed");
+    P_TRY(aero_segment_finish_tree(seg, root));
+    return AERO_OK;
+}
+
 // build_segment_queries (prover/src/trace/commitment.rs:115-140)
-static aero_status query_segment(aero_ctx *ctx, aero_segment *seg, const std::vector<uint64_t> &positions,
-                                 uint32_t width, Queries *q, std::string *err) {
+static aero_status query_segment(aero_ctx *ctx, const aero_prove_inputs &in, aero_segment *seg,
+                                 const std::vector<uint64_t> &positions, uint32_t width, Queries *q, std::string *err) {
     std::vector<uint64_t> rows(positions.size() * width);
     std::vector<uint8_t> paths(1 + positions.size() * (1 + 32 * 40));
     size_t len = paths.size();
     P_TRY(aero_segment_open(seg, positions.data(), (uint32_t)positions.size(), rows.data(), paths.data(), &len));
+    if (in.sum_rows) {
+        aero_status st = in.sum_rows(in.user, rows.data(), rows.size());
+        if (st != AERO_OK) P_FAIL(st, "sum_rows callback failed");
+    }
     paths.resize(len);
     q->values.assign((uint8_t *)rows.data(), (uint8_t *)rows.data() + rows.size() * 8);
     q->paths = std::move(paths);
@@ -277,6 +295,7 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     if (in.aux_width && !in.aux_builder && !in.aux_cols) P_FAIL(AERO_ERR_INVALID, "auxiliary segment columns are required");
     if (!in.constraint_evaluator && !in.ce_cols) P_FAIL(AERO_ERR_INVALID, "constraint evaluations are required");
     if (in.inputs_on_device && (in.aux_builder || in.constraint_evaluator)) P_FAIL(AERO_ERR_INVALID, "callbacks need host inputs");
+    if (in.all_gather_cosets && in.constraint_evaluator) P_FAIL(AERO_ERR_UNSUPPORTED, "sharded proofs take precomputed constraint evaluations");
     const bool mont = aero_ctx_get_form(ctx) == AERO_FORM_MONTGOMERY;
     auto to_abi = [&](uint64_t x) { return mont ? gl::canon_to_mont(x) : x; };
     auto from_abi = [&](uint64_t x) { return mont ? gl::mont_to_canon(x) : gl::canon(x); };
@@ -294,6 +313,7 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     else
         P_TRY(aero_segment_commit(ctx, in.main_cols, in.main_width, n, o.blowup_factor, 0, &main_seg, root));
     H.segs.push_back(main_seg);
+    P_TRY(finish_commit(ctx, in, main_seg, o.blowup_factor, root, err));
     channel.commit_trace(Digest(root, root + 32));
 
     aero_segment *aux_seg = nullptr;
@@ -314,6 +334,7 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
         else
             P_TRY(aero_segment_commit(ctx, aux_cols, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root));
         H.segs.push_back(aux_seg);
+        P_TRY(finish_commit(ctx, in, aux_seg, o.blowup_factor, root, err));
         channel.commit_trace(Digest(root, root + 32));
     }
 
@@ -350,6 +371,7 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     H.segs.push_back(comp_seg);
     lde_host.clear();
     P_TRY(aero_segment_commit_polys(comp_seg, o.blowup_factor, root));
+    P_TRY(finish_commit(ctx, in, comp_seg, o.blowup_factor, root, err));
     channel.commit_constraints(Digest(root, root + 32));
 
     // 4 ----- OOD frame + DEEP composition polynomial (lib.rs:421-467)
@@ -379,6 +401,16 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     P_TRY(aero_deep_compose(ctx, trace_segs.data(), (uint32_t)trace_segs.size(), comp_seg, to_abi(z), ood_trace.data(),
                             ood_comp.data(), cc.data(), &H.fri));
 
+    if (in.all_gather_cosets) {
+        void *d = nullptr;
+        uint64_t cnt = 0;
+        uint32_t cb = 0, ccnt = 0;
+        P_TRY(aero_fri_evaluations_device(H.fri, &d, &cnt, &cb, &ccnt));
+        aero_status st = in.all_gather_cosets(in.user, d, n, o.blowup_factor, 8, 0, cb, ccnt);
+        if (st != AERO_OK) P_FAIL(st, "all_gather_cosets callback failed");
+        P_TRY(aero_fri_mark_complete(H.fri));
+    }
+
     // 6 ----- FRI layers (fri/src/prover/mod.rs:166-191)
     const size_t num_layers = ProofOptions{o}.num_fri_layers(N);
     for (size_t l = 0; l < num_layers + 1; l++) {
@@ -401,10 +433,10 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     P_TRY(aero_fri_open(H.fri, positions.data(), (uint32_t)positions.size(), fri_bytes.data(), &flen));
     fri_bytes.resize(flen);
     std::vector<Queries> tq(trace_segs.size());
-    P_TRY(query_segment(ctx, main_seg, positions, in.main_width, &tq[0], err));
-    if (aux_seg) P_TRY(query_segment(ctx, aux_seg, positions, in.aux_width, &tq[1], err));
+    P_TRY(query_segment(ctx, in, main_seg, positions, in.main_width, &tq[0], err));
+    if (aux_seg) P_TRY(query_segment(ctx, in, aux_seg, positions, in.aux_width, &tq[1], err));
     Queries cq;
-    P_TRY(query_segment(ctx, comp_seg, positions, m, &cq, err));
+    P_TRY(query_segment(ctx, in, comp_seg, positions, m, &cq, err));
     *proof_bytes = channel.build_proof(std::move(tq), std::move(cq), std::move(fri_bytes)).to_bytes();
     return AERO_OK;
 }

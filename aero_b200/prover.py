@@ -189,7 +189,7 @@ class Context:
     # ---- whole proof ---------------------------------------------------------------------------
     def prove(self, main_trace, aux_trace, ce_cols, divisors: Sequence[Divisor], pub_inputs_bytes: bytes,
               options: Optional[ProofOptions] = None, aux_rands: int = 16, n_constraint_coeffs: int = 0,
-              on_device: Optional[dict] = None) -> bytes:
+              on_device: Optional[dict] = None, shard=None) -> bytes:
         """Prover::prove.  Host mode: numpy matrices.  Device mode (``on_device`` = dict with
         main/aux/ce device pointers and shapes): inputs already resident in HBM."""
         inp = ProveInputs()
@@ -215,6 +215,12 @@ class Context:
                 setattr(inp, name + "_cols", arr)
                 keep.append(arr)
         inp.aux_rands = aux_rands if inp.aux_width else 0
+        if shard is not None:  # aero_b200.sharded.ShardExchange: coset-sharded proof across ranks
+            self._check(self.lib.aero_ctx_set_shard(self.h, shard.rank, shard.world))
+            inp.all_gather_cosets = shard._gather_cb
+            inp.sum_rows = shard._sum_cb
+        else:
+            self._check(self.lib.aero_ctx_set_shard(self.h, 0, 1))
         divs = (Divisor * len(divisors))(*divisors)
         inp.divisors = divs
         inp.n_div = len(divisors)

@@ -154,8 +154,10 @@ def workload_config(args, log_rows: int) -> dict:
                         "LDE + blake2s Merkle commit (main, aux, constraint) + OOD + DEEP + FRI + grinding + openings"
                         % log_rows,
             "log_rows": log_rows, "main_width": MAIN_W, "aux_width": AUX_W, "constraint_columns": CE_COLS,
-            "blowup": BLOWUP, "parallelism": "one independent proof per GPU (no data-path collective)" if args.gpus > 1
-            else "single GPU", "l2": "inputs (0.7 GB) and LDE (5.4 GB) exceed the 126 MB L2"}
+            "blowup": BLOWUP, "parallelism": ("single GPU" if args.gpus == 1 else
+                                             "one proof sharded by LDE coset across %d GPUs (NCCL all-gather of leaf digests "
+                                             "and DEEP evaluations)" % args.gpus if getattr(args, "shard_proof", False) else
+                                             "one independent proof per GPU (no data-path collective)"), "l2": "inputs (0.7 GB) and LDE (5.4 GB) exceed the 126 MB L2"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -184,7 +186,7 @@ def run_aero(args) -> None:
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
-    seed = 0x1000 * rank
+    seed = 0 if args.shard_proof else 0x1000 * rank  # a sharded proof needs the same trace on every rank
     main = splitmix_matrix(MAIN_W, n, 0xAE200000 + seed)
     aux = splitmix_matrix(AUX_W, n, 0xAE210000 + seed)
     ce = splitmix_matrix(CE_COLS, N, 0xCE000000 + seed)
@@ -203,11 +205,16 @@ def run_aero(args) -> None:
     keep = [pin(main), pin(aux), pin(ce)]
     h_main, h_aux, h_ce = keep[0][1], keep[1][1], keep[2][1]
 
+    shard = None
+    if args.shard_proof and world > 1:
+        from aero_b200.sharded import ShardExchange
+        shard = ShardExchange()
+
     def step_device():
-        return ctx.prove(None, None, None, divs, PUB, on_device=on_device)
+        return ctx.prove(None, None, None, divs, PUB, on_device=on_device, shard=shard)
 
     def step_host():
-        return ctx.prove(h_main, h_aux, h_ce, divs, PUB)
+        return ctx.prove(h_main, h_aux, h_ce, divs, PUB, shard=shard)
 
     def barrier():
         if world > 1:
@@ -244,7 +251,11 @@ def run_aero(args) -> None:
     launches = ctx.lib.aero_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms / args.steps
-    value = world * n / (ms_step * 1e-3)
+    nproofs = 1 if shard is not None else world
+    value = nproofs * n / (ms_step * 1e-3)
+    if shard is not None:  # the sharded proof must equal the single-GPU proof byte for byte
+        single = ctx.prove(None, None, None, divs, PUB, on_device=on_device)
+        assert single == proof, "sharded proof differs from the single-GPU proof"
 
     if args.quick:
         if rank == 0:
@@ -254,7 +265,7 @@ def run_aero(args) -> None:
     ms_e2e, proof_h = timed(step_host, max(1, args.steps // 2))
     ms_e2e /= max(1, args.steps // 2)
     assert proof_h == proof, "host-buffer and device-buffer proofs differ"
-    e2e_val = world * n / (ms_e2e * 1e-3)
+    e2e_val = nproofs * n / (ms_e2e * 1e-3)
     h2d = (MAIN_W + AUX_W) * n * 8 + CE_COLS * N * 8
     d2h = len(proof) + 32 * 9
 
@@ -276,7 +287,8 @@ def run_aero(args) -> None:
                    "sample": "oracle port on a 2^%d-row trace of the same widths/options (%.1f s)" % (args.ref_log_rows, dt)}
         phases = {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items())}
         line = {"metric": "trace_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if shard is not None else "weak",
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args, log_rows),
                 "e2e": {"value": e2e_val, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
@@ -296,6 +308,9 @@ def main() -> None:
     ap.add_argument("--log-rows", type=int, default=20)
     ap.add_argument("--ref-log-rows", type=int, default=18, help="trace size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-proof", action="store_true",
+                    help="N>1: shard ONE proof across the ranks by LDE coset (strong scaling) instead of one "
+                         "independent proof per rank")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu): 1 warm-up, no e2e / cpu legs; numbers printed are NOT bench values")
     args = ap.parse_args()

@@ -86,6 +86,23 @@ aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint
 aero_status aero_segment_commit_device(aero_ctx *ctx, const uint64_t *d_cols, size_t col_stride, uint32_t n_cols,
                                        uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
                                        uint8_t root[32]);
+/* ---- multi-GPU: LDE-coset sharding (one context = one rank) -----------------
+ * After aero_ctx_set_shard(rank, world) (world a power of two dividing the blowup), every segment
+ * commit interpolates all columns but extends and row-hashes only LDE cosets
+ * [rank*B/world, (rank+1)*B/world) -- complete rows k with k mod B in that range -- and leaves the
+ * tree unfinished (root = zeros).  The caller exchanges the 32-byte leaf digests (natural order,
+ * viewed as [N/B][B][32]: a rank owns [:, coset_begin:coset_begin+coset_count, :]) between ranks,
+ * e.g. with an NCCL all-gather, and calls aero_segment_finish_tree on every rank.  aero_deep_compose
+ * likewise fills only the own cosets of the coset-major DEEP evaluations ([B][n] u64: a rank owns
+ * [coset_begin:coset_begin+coset_count, :]); exchange, then aero_fri_mark_complete.
+ * aero_segment_open returns zeros for rows owned by other ranks (sum the ranks' results). */
+aero_status aero_ctx_set_shard(aero_ctx *ctx, int rank, int world);
+aero_status aero_segment_leaves_device(aero_segment *seg, void **d_leaves, uint64_t *n_leaves, uint32_t *coset_begin,
+                                       uint32_t *coset_count);
+aero_status aero_segment_finish_tree(aero_segment *seg, uint8_t root[32]);
+aero_status aero_fri_evaluations_device(aero_fri *fri, void **d_evals, uint64_t *count, uint32_t *coset_begin,
+                                        uint32_t *coset_count);
+aero_status aero_fri_mark_complete(aero_fri *fri);
 void aero_segment_destroy(aero_segment *seg);
 aero_status aero_segment_info(aero_segment *seg, uint32_t *n_cols, uint64_t *n_rows, uint32_t *blowup);
 /* Natural-order LDE columns (lde[c][k] = poly_c(7 * g_N^k), matrix.rs:189-201) for the host-side

@@ -43,6 +43,15 @@ typedef aero_status (*aero_constraint_evaluator)(void *user, const uint64_t *con
                                                  uint64_t lde_size, const uint64_t *coeffs, uint32_t n_coeffs,
                                                  const uint64_t **eval_cols_out);
 
+/* Multi-GPU exchange hooks (NULL on a single GPU).  all_gather_cosets completes a device buffer that
+ * every rank filled for its own LDE cosets: interleaved != 0 -> layout [outer][B][inner_bytes]
+ * (leaf digests), else [B][outer][inner_bytes] (DEEP evaluations).  sum_rows adds the ranks'
+ * disjoint host row matrices (aero_segment_open fills foreign rows with zeros). */
+typedef aero_status (*aero_all_gather_cosets)(void *user, void *d_buf, uint64_t outer, uint32_t n_cosets,
+                                              uint32_t inner_bytes, int interleaved, uint32_t coset_begin,
+                                              uint32_t coset_count);
+typedef aero_status (*aero_sum_rows)(void *user, uint64_t *host_rows, uint64_t count);
+
 typedef struct aero_prove_inputs {
     aero_proof_options options;
     uint64_t trace_len;
@@ -63,6 +72,8 @@ typedef struct aero_prove_inputs {
     size_t pub_inputs_len;
     const uint8_t *trace_meta;         /* TraceInfo meta bytes for the proof context (may be NULL) */
     uint16_t trace_meta_len;
+    aero_all_gather_cosets all_gather_cosets;
+    aero_sum_rows sum_rows;
 } aero_prove_inputs;
 
 /* Prover::prove: writes StarkProof::to_bytes (air/src/proof/mod.rs:122-132) into proof_out.
