@@ -49,6 +49,9 @@ struct aero_ctx {
     std::vector<void *> owned;  // device allocations freed with the context
     size_t lde_batch_bytes = (size_t)1 << 30;  // NTT scratch budget per column batch
     int shard_rank = 0, shard_world = 1;       // LDE coset shard of this context (multi-GPU)
+    std::multimap<size_t, void *> free_blocks;  // exact-size cache of released device blocks
+    std::map<void *, size_t> live_blocks;
+    size_t cached_bytes = 0, cache_limit_bytes = (size_t)96 << 30;
 };
 
 #define CTX_FAIL(ctx, code, ...)                         \
@@ -109,13 +112,50 @@ static void profile_flush(aero_ctx *ctx) {
     ctx->pending.clear();
 }
 
+// Device memory for segments / scratch comes from a per-context exact-size cache: every proof of a
+// given shape requests the same sizes in the same order, so after the first proof no driver call is
+// made at all.  (cudaMallocAsync's pool showed 50-1400 ms stalls when two processes re-shaped their
+// pools at once.)  All work of a context is on one stream, so handing a block freed "now" to a later
+// launch on that stream is ordered correctly without synchronisation.
+static void cache_release_all(aero_ctx *ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->free_blocks) cudaFree(kv.second);
+    ctx->free_blocks.clear();
+    ctx->cached_bytes = 0;
+}
 static aero_status dev_alloc(aero_ctx *ctx, void **p, size_t bytes) {
     if (bytes == 0) bytes = 8;
-    CUDA_TRY(ctx, cudaMallocAsync(p, bytes, ctx->stream));
+    bytes = (bytes + 511) & ~(size_t)511;
+    auto it = ctx->free_blocks.find(bytes);
+    if (it != ctx->free_blocks.end()) {
+        *p = it->second;
+        ctx->free_blocks.erase(it);
+        ctx->cached_bytes -= bytes;
+        ctx->live_blocks[*p] = bytes;
+        return AERO_OK;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {  // give the cached blocks back and retry once
+        cudaGetLastError();
+        cache_release_all(ctx);
+        e = cudaMalloc(p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        CTX_FAIL(ctx, AERO_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+    ctx->live_blocks[*p] = bytes;
     return AERO_OK;
 }
 static void dev_free(aero_ctx *ctx, void *p) {
-    if (p) cudaFreeAsync(p, ctx->stream);
+    if (!p) return;
+    auto it = ctx->live_blocks.find(p);
+    if (it == ctx->live_blocks.end()) return;
+    const size_t bytes = it->second;
+    ctx->live_blocks.erase(it);
+    ctx->free_blocks.emplace(bytes, p);
+    ctx->cached_bytes += bytes;
+    if (ctx->cached_bytes > ctx->cache_limit_bytes) cache_release_all(ctx);
 }
 template <typename T>
 static aero_status upload_vec(aero_ctx *ctx, T **d, const std::vector<T> &h, bool own = true) {
@@ -568,11 +608,8 @@ aero_status aero_ctx_create(const int *device_ids, int n_devices, aero_ctx **out
     if (prop.major < 10) return AERO_ERR_UNSUPPORTED;  // kernels are built for sm_100a only
     aero_ctx *ctx = new aero_ctx();
     ctx->device = dev;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t thr = ~0ULL;  // keep freed blocks cached: segments are re-created every proof
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->cache_limit_bytes = total_b / 2;
     *out = ctx;
     return AERO_OK;
 }
@@ -580,6 +617,8 @@ void aero_ctx_destroy(aero_ctx *ctx) {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
     profile_flush(ctx);
+    cache_release_all(ctx);
+    for (auto &kv : ctx->live_blocks) cudaFree(kv.first);  // handles the caller forgot to destroy
     for (void *p : ctx->owned) cudaFree(p);
     delete ctx;
 }

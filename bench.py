@@ -59,42 +59,55 @@ def bench_divisors(n: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML from a thread while the timed region runs
+    (no fork: spawning nvidia-smi from a process with GBs of pinned memory stalls the step)."""
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mx, self.reasons, self._stop, self.thread, self.err = index, [], None, set(), False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
+                return
+            time.sleep(0.02)
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = set()
-        for r in self.rows:
-            for i, nm in enumerate(names):
-                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        sm = sorted(self.sm)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+               "samples": len(sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def measured_peaks():
@@ -226,9 +239,14 @@ def run_aero(args) -> None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         out = None
+        walls = []
         for _ in range(steps):
+            t0 = time.perf_counter()
             out = fn()
+            walls.append(round((time.perf_counter() - t0) * 1e3, 1))
         e1.record(stream)
+        if os.environ.get("AERO_BENCH_DEBUG"):
+            print("rank %d %s per-step wall ms %s" % (rank, fn.__name__, walls), file=sys.stderr, flush=True)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         if world > 1:
@@ -261,9 +279,10 @@ def run_aero(args) -> None:
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms_step, "phase_ms": {k: v[1] / args.steps for k, v in prof.items()}}))
         return
-    step_host()  # warm the pinned path
-    ms_e2e, proof_h = timed(step_host, max(1, args.steps // 2))
-    ms_e2e /= max(1, args.steps // 2)
+    for _ in range(3):  # warm the pinned path (and let the stream-ordered pool settle on the new sizes)
+        step_host()
+    ms_e2e, proof_h = timed(step_host, args.steps)
+    ms_e2e /= args.steps
     assert proof_h == proof, "host-buffer and device-buffer proofs differ"
     e2e_val = nproofs * n / (ms_e2e * 1e-3)
     h2d = (MAIN_W + AUX_W) * n * 8 + CE_COLS * N * 8
