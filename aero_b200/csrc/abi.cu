@@ -223,6 +223,8 @@ static aero_status get_plan(aero_ctx *ctx, const std::string &key, int logn, boo
     DftTables t;
     t.logn = logn;
     t.ncosets = (int)shifts.size();
+    t.plain = true;
+    for (uint64_t sh : shifts) t.plain = t.plain && sh == 1;
     const uint64_t n = 1ULL << logn;
     uint64_t w = gl::root_of_unity(logn);
     if (inverse) w = gl::inv(w);

@@ -64,6 +64,46 @@ __device__ __forceinline__ uint64_t mul_any(uint64_t a, uint64_t b) {
         : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
     return ((uint64_t)x1 << 32) | x0;
 }
+// any x any -> canonical.  Same product and first fix-up as mul_any; the last fix-up and the
+// canonicalisation merge: with r = x + hl*EPS (carry c) and s = r + EPS (carry c2), the result is s
+// when c | c2 (c: r wrapped, and r + EPS < p; c2: r >= p), else r.  Three instructions fewer than
+// canon_any(mul_any()).
+__device__ __forceinline__ uint64_t mul_canon(uint64_t a, uint64_t b) {
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    uint32_t x0, x1;
+    asm("{\n\t"
+        ".reg .u32 r0, r1, r2, r3, m, c, t0, t1, s0, s1;\n\t"
+        ".reg .pred q;\n\t"
+        "mul.lo.u32 r0, %2, %4;\n\t"
+        "mul.hi.u32 r1, %2, %4;\n\t"
+        "mad.lo.cc.u32 r1, %2, %5, r1;\n\t"
+        "madc.hi.u32 r2, %2, %5, 0;\n\t"
+        "mad.lo.cc.u32 r1, %3, %4, r1;\n\t"
+        "madc.hi.cc.u32 r2, %3, %4, r2;\n\t"
+        "addc.u32 r3, 0, 0;\n\t"
+        "mad.lo.cc.u32 r2, %3, %5, r2;\n\t"
+        "madc.hi.u32 r3, %3, %5, r3;\n\t"
+        "sub.cc.u32 %0, r0, r3;\n\t"
+        "subc.cc.u32 %1, r1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t"
+        "mul.lo.u32 t0, r2, 0xffffffff;\n\t"
+        "mul.hi.u32 t1, r2, 0xffffffff;\n\t"
+        "add.cc.u32 %0, %0, t0;\n\t"
+        "addc.cc.u32 %1, %1, t1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "add.cc.u32 s0, %0, 0xffffffff;\n\t"
+        "addc.cc.u32 s1, %1, 0;\n\t"
+        "addc.u32 c, c, 0;\n\t"
+        "setp.ne.u32 q, c, 0;\n\t"
+        "selp.u32 %0, s0, %0, q;\n\t"
+        "selp.u32 %1, s1, %1, q;\n\t"
+        "}"
+        : "=&r"(x0), "=&r"(x1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return ((uint64_t)x1 << 32) | x0;
+}
 // any -> canonical:  x >= p  <=>  x + EPS carries out of 64 bits (p + EPS = 2^64)
 __device__ __forceinline__ uint64_t canon_any(uint64_t x) {
     uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), y0, y1;
@@ -162,7 +202,7 @@ GL_HD void mul_wide(uint64_t a, uint64_t b, uint64_t &lo, uint64_t &hi) {
 
 GL_HD uint64_t mul(uint64_t a, uint64_t b) {  // f64/mod.rs:311
 #if defined(__CUDA_ARCH__)
-    return canon_any(mul_any(a, b));
+    return mul_canon(a, b);
 #else
     uint64_t lo, hi;
     mul_wide(a, b, lo, hi);

@@ -10,8 +10,12 @@ __device__ __forceinline__ uint32_t bitrev(uint32_t x, int bits) { return __brev
 
 // One register-blocked round of R DIT stages (s0 .. s0+R-1) over an M x T tile in shared memory.
 // a[idx*RS + t]; tw[2^s + k] is the stage-s twiddle for pair offset k (k < 2^s).
-template <int R, int T, int RS>
+// PLAIN0: this is the first round (s0 == 0) of a transform without coset shift, where the
+// twiddle of pair offset k == 0 is 1 -- known at compile time, so 7 of the 12 multiplications of a
+// radix-8 round disappear.
+template <int R, int T, int RS, bool PLAIN0>
 __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s0, int logM) {
+    if (PLAIN0) s0 = 0;
     const int ngroups = (1 << logM) >> R;
     const int items = ngroups * T;
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
@@ -27,10 +31,14 @@ __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s
             for (int e = 0; e < (1 << R); e++) {
                 if (e & (1 << q)) continue;
                 const int k = low + ((e & ((1 << q) - 1)) << s0);
-                const uint64_t w = tw[(1 << (s0 + q)) + k];
                 // values in the tile stay "any" (congruent mod p, < 2^64); only v is canonicalised
                 const uint64_t u = x[e];
-                const uint64_t v = gl::canon_any(gl::mul_any(x[e | (1 << q)], w));
+                uint64_t v;
+                if (PLAIN0 && (e & ((1 << q) - 1)) == 0) {
+                    v = gl::canon_any(x[e | (1 << q)]);
+                } else {
+                    v = gl::mul_canon(x[e | (1 << q)], tw[(1 << (s0 + q)) + k]);
+                }
                 x[e] = gl::add_ac(u, v);
                 x[e | (1 << q)] = gl::sub_ac(u, v);
             }
@@ -41,20 +49,32 @@ __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s
 }
 
 // Full M-point DIT over the tile: input in bit-reversed row order, output in natural row order.
-template <int T, int RS>
+template <int T, int RS, bool PLAIN>
 __device__ __forceinline__ void dit_tile(uint64_t *a, const uint64_t *tw, int logM) {
     int s0 = 0;
+    // first round: s0 == 0 is a compile-time fact, which lets PLAIN transforms drop unit twiddles
+    if (logM >= 3 && logM != 4) {
+        dit_round<3, T, RS, PLAIN>(a, tw, 0, logM);
+        s0 = 3;
+    } else if (logM >= 2) {
+        dit_round<2, T, RS, PLAIN>(a, tw, 0, logM);
+        s0 = 2;
+    } else {
+        dit_round<1, T, RS, PLAIN>(a, tw, 0, logM);
+        s0 = 1;
+    }
+    __syncthreads();
     while (s0 < logM) {
         const int left = logM - s0;
         // prefer 3-stage rounds; avoid a trailing 1-stage round when 4 stages remain (2+2)
         if (left >= 3 && left != 4) {
-            dit_round<3, T, RS>(a, tw, s0, logM);
+            dit_round<3, T, RS, false>(a, tw, s0, logM);
             s0 += 3;
         } else if (left >= 2) {
-            dit_round<2, T, RS>(a, tw, s0, logM);
+            dit_round<2, T, RS, false>(a, tw, s0, logM);
             s0 += 2;
         } else {
-            dit_round<1, T, RS>(a, tw, s0, logM);
+            dit_round<1, T, RS, false>(a, tw, s0, logM);
             s0 += 1;
         }
         __syncthreads();
@@ -73,7 +93,7 @@ __device__ __forceinline__ size_t out_index(uint32_t i, int logn, int deint) {
 
 // ---- pass 1 -------------------------------------------------------------------------------
 // grid: (n2/T, ncosets, ncols).  tmp layout per (col, coset): [i1/T][j2][i1%T].
-template <int T>
+template <int T, bool PLAIN>
 __global__ void __launch_bounds__(512) dft_pass1_kernel(const uint64_t *__restrict__ src, uint64_t *__restrict__ tmp,
                                                         const uint64_t *__restrict__ stage1,
                                                         const uint64_t *__restrict__ inter_b,
@@ -95,7 +115,7 @@ __global__ void __launch_bounds__(512) dft_pass1_kernel(const uint64_t *__restri
         a[bitrev(j1, log1) * RS + t] = s[((size_t)j1 << log2) + j2_0 + t];
     }
     __syncthreads();
-    dit_tile<T, RS>(a, tw, log1);
+    dit_tile<T, RS, PLAIN>(a, tw, log1);
     // inter-pass factor F(i1, j2) = b[j2] * w_n^(i1*j2), advanced by a running product per thread
     uint64_t *o = tmp + ((size_t)col * ncosets + coset) * n;
     const int it0 = threadIdx.x;
@@ -109,7 +129,7 @@ __global__ void __launch_bounds__(512) dft_pass1_kernel(const uint64_t *__restri
     const uint64_t d = root_pow(wlo, whi, lo_bits, step_i1 * j2);
     const int nchunks = n1 / T;
     for (; c < nchunks; c += cstep, i1 += step_i1) {
-        const uint64_t v = gl::canon_any(gl::mul_any(a[i1 * RS + t], f));
+        const uint64_t v = gl::mul_canon(a[i1 * RS + t], f);
         o[((size_t)c << log2) * T + (size_t)j2 * T + ii] = v;
         f = gl::mul_any(f, d);
     }
@@ -139,7 +159,7 @@ __global__ void __launch_bounds__(512) dft_pass2_kernel(const uint64_t *__restri
         a[bitrev(j2, log2) * RS + t] = s[it];
     }
     __syncthreads();
-    dit_tile<T, RS>(a, tw, log2);
+    dit_tile<T, RS, true>(a, tw, log2);
     uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n;
     for (int it = threadIdx.x; it < n2 * T; it += blockDim.x) {
         const int t = it % T, i2 = it / T;
@@ -154,6 +174,7 @@ __global__ void __launch_bounds__(512) dft_pass2_kernel(const uint64_t *__restri
 
 // ---- single pass (n <= 2^11) --------------------------------------------------------------
 // grid: (1, ncosets, ncols)
+template <bool PLAIN>
 __global__ void __launch_bounds__(256) dft_single_kernel(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst,
                                                          const uint64_t *__restrict__ stage,
                                                          const uint64_t *__restrict__ post_u, uint64_t scale, int logn,
@@ -169,7 +190,7 @@ __global__ void __launch_bounds__(256) dft_single_kernel(const uint64_t *__restr
         a[bitrev(i, logn)] = s[i];
     }
     __syncthreads();
-    dit_tile<1, 1>(a, tw, logn);
+    dit_tile<1, 1, PLAIN>(a, tw, logn);
     uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         uint64_t v = a[i];
@@ -190,7 +211,8 @@ static void launch_two_pass(const DftTables &t, const DftLaunch &l, cudaStream_t
     const size_t smem2 = (size_t)n2 * (T + 1) * 8 + (size_t)n2 * 8;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(dft_pass1_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dft_pass1_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dft_pass1_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(dft_pass2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
@@ -202,8 +224,12 @@ static void launch_two_pass(const DftTables &t, const DftLaunch &l, cudaStream_t
     };
     dim3 g1(n2 / T, nc, l.ncols), g2(n1 / T, nc, l.ncols);
     AERO_COUNT_LAUNCH(2);
-    dft_pass1_kernel<T><<<g1, threads_for(n1), smem1, s>>>(l.src, l.tmp, stage1, inter_b, t.wlo, t.whi, t.lo_bits,
-                                                           t.log1, t.log2, l.src_col_stride, nc);
+    if (t.plain)
+        dft_pass1_kernel<T, true><<<g1, threads_for(n1), smem1, s>>>(l.src, l.tmp, stage1, inter_b, t.wlo, t.whi,
+                                                                     t.lo_bits, t.log1, t.log2, l.src_col_stride, nc);
+    else
+        dft_pass1_kernel<T, false><<<g1, threads_for(n1), smem1, s>>>(l.src, l.tmp, stage1, inter_b, t.wlo, t.whi,
+                                                                      t.lo_bits, t.log1, t.log2, l.src_col_stride, nc);
     dft_pass2_kernel<T><<<g2, threads_for(n2), smem2, s>>>(l.tmp, l.dst, t.stage2, t.post_u, t.post_v, t.log1, t.log2,
                                                            l.dst_col_stride, nc, l.deinterleave_log);
 }
@@ -215,8 +241,14 @@ void dft_run(const DftTables &t, const DftLaunch &l, cudaStream_t s) {
         const int nc = l.coset_count ? l.coset_count : t.ncosets;
         dim3 g(1, nc, l.ncols);
         AERO_COUNT_LAUNCH(1);
-        dft_single_kernel<<<g, th, (size_t)n * 16, s>>>(l.src, l.dst, t.stage2 + (size_t)l.coset_begin * n, t.post_u, t.single_scale, t.logn,
-                                                       l.src_col_stride, l.dst_col_stride, l.deinterleave_log);
+        if (t.plain)
+            dft_single_kernel<true><<<g, th, (size_t)n * 16, s>>>(l.src, l.dst, t.stage2 + (size_t)l.coset_begin * n,
+                                                                 t.post_u, t.single_scale, t.logn, l.src_col_stride,
+                                                                 l.dst_col_stride, l.deinterleave_log);
+        else
+            dft_single_kernel<false><<<g, th, (size_t)n * 16, s>>>(l.src, l.dst, t.stage2 + (size_t)l.coset_begin * n,
+                                                                  t.post_u, t.single_scale, t.logn, l.src_col_stride,
+                                                                  l.dst_col_stride, l.deinterleave_log);
         return;
     }
     const int big = t.log1 > t.log2 ? t.log1 : t.log2;

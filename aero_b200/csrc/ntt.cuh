@@ -22,6 +22,7 @@ constexpr int NTT_MAX_LOG = 24;         // two passes of <= 2^12 points
 struct DftTables {
     int logn = 0, log1 = 0, log2 = 0;  // n = n1 * n2 ; log1 == 0 means single pass (n2 = n)
     int ncosets = 1;
+    bool plain = false;               // no coset shift (all shifts == 1): unit twiddles are skipped
     int lo_bits = 0;                  // two-level w_n^e table split
     uint64_t *stage1 = nullptr;       // [ncosets][n1]  pass-1 stage twiddles tw[m/2+k] = sigma^(n1/m) w_m^k
     uint64_t *stage2 = nullptr;       // [n2]           pass-2 stage twiddles (plain); single pass: [ncosets][n]
