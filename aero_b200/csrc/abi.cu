@@ -39,6 +39,7 @@ struct PowTableOwned {
 struct aero_ctx {
     int device = 0;
     cudaStream_t stream = 0;
+    cudaStream_t copy_stream = nullptr;  // host->device uploads overlapped with compute
     int form = AERO_FORM_MONTGOMERY;
     std::string err;
     bool profile = false;
@@ -370,53 +371,53 @@ static aero_status segment_finish_tree(aero_segment *seg, uint8_t root[32]) {
     return AERO_OK;
 }
 
-static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint8_t root[32]) {
+// ---- building blocks of a segment commitment ----------------------------------------------------
+static aero_status segment_alloc_lde(aero_segment *seg, int log_blowup, const DftTables **plan) {
     aero_ctx *ctx = seg->ctx;
     if (seg->lde) CTX_FAIL(ctx, AERO_ERR_STATE, "segment already committed");
     if (log_blowup < 1 || log_blowup > 6) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "blowup must be 2..64");
     if (seg->logn + log_blowup > 31) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "LDE domain too large");
     seg->log_blowup = log_blowup;
-    const uint64_t n = seg->n(), N = seg->N();
     const int B = 1 << log_blowup;
     if (B % ctx->shard_world) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "shard world size %d must divide the blowup factor %d", ctx->shard_world, B);
     seg->coset_count = B / ctx->shard_world;
     seg->coset_begin = ctx->shard_rank * seg->coset_count;
-    const uint64_t Nl = seg->lde_stride();  // rows stored on this rank
-    TRY(dev_alloc(ctx, (void **)&seg->lde, (size_t)seg->ncols * Nl * 8));
-    TRY(dev_alloc(ctx, (void **)&seg->full, (size_t)2 * N * 32));
-    const DftTables *plan;
-    TRY(plan_lde(ctx, seg->logn, log_blowup, false, &plan));
-    {
-        char nm[32];
-        snprintf(nm, sizeof nm, "lde_w%d", seg->ncols);
-        PhaseTimer t(ctx, nm);
-        int batch = seg->ncols;
-        uint64_t *tmp = nullptr;
-        if (plan->log1 != 0) {
-            batch = (int)std::max<size_t>(1, ctx->lde_batch_bytes / ((size_t)Nl * 8));
-            batch = std::min(batch, seg->ncols);
-            TRY(dev_alloc(ctx, (void **)&tmp, (size_t)batch * Nl * 8));
-        }
-        for (int c0 = 0; c0 < seg->ncols; c0 += batch) {
-            DftLaunch l;
-            l.src = seg->polys + (size_t)c0 * n;
-            l.dst = seg->lde + (size_t)c0 * Nl;
-            l.tmp = tmp;
-            l.src_col_stride = n;
-            l.dst_col_stride = Nl;
-            l.ncols = std::min(batch, seg->ncols - c0);
-            l.deinterleave_log = 0;
-            l.coset_begin = seg->coset_begin;
-            l.coset_count = seg->coset_count;
-            dft_run(*plan, l, ctx->stream);
-        }
-        dev_free(ctx, tmp);
-    }
+    TRY(dev_alloc(ctx, (void **)&seg->lde, (size_t)seg->ncols * seg->lde_stride() * 8));
+    TRY(dev_alloc(ctx, (void **)&seg->full, (size_t)2 * seg->N() * 32));
+    return plan_lde(ctx, seg->logn, log_blowup, false, plan);
+}
+static int segment_lde_batch_cols(aero_segment *seg) {
+    const size_t per_col = (size_t)seg->lde_stride() * 8;
+    int batch = (int)std::max<size_t>(1, seg->ctx->lde_batch_bytes / per_col);
+    return std::min(batch, seg->ncols);
+}
+// coset LDE of columns [c0, c0 + ncols) (tmp: >= ncols * lde_stride entries when two-pass)
+static void segment_lde_batch(aero_segment *seg, const DftTables *plan, int c0, int ncols, uint64_t *tmp) {
+    aero_ctx *ctx = seg->ctx;
+    const uint64_t n = seg->n(), Nl = seg->lde_stride();
+    char nm[32];
+    snprintf(nm, sizeof nm, "lde_w%d", seg->ncols);
+    PhaseTimer t(ctx, nm);
+    DftLaunch l;
+    l.src = seg->polys + (size_t)c0 * n;
+    l.dst = seg->lde + (size_t)c0 * Nl;
+    l.tmp = tmp;
+    l.src_col_stride = n;
+    l.dst_col_stride = Nl;
+    l.ncols = ncols;
+    l.deinterleave_log = 0;
+    l.coset_begin = seg->coset_begin;
+    l.coset_count = seg->coset_count;
+    dft_run(*plan, l, ctx->stream);
+}
+static aero_status segment_hash_and_tree(aero_segment *seg, uint8_t root[32]) {
+    aero_ctx *ctx = seg->ctx;
+    const uint64_t N = seg->N(), Nl = seg->lde_stride();
     {
         char nm[32];
         snprintf(nm, sizeof nm, "hash_rows_w%d", seg->ncols);
         PhaseTimer t(ctx, nm);
-        hash_rows_lde(seg->lde, Nl, seg->ncols, seg->logn, log_blowup, seg->coset_begin, (uint32_t)Nl,
+        hash_rows_lde(seg->lde, Nl, seg->ncols, seg->logn, seg->log_blowup, seg->coset_begin, (uint32_t)Nl,
                       seg->full + (size_t)N * 8, ctx->stream);
     }
     CUDA_TRY(ctx, cudaMemsetAsync(seg->full, 0, 64, ctx->stream));
@@ -431,10 +432,25 @@ static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint
     return segment_finish_tree(seg, root);
 }
 
-// d_src: ncols columns (stride src_stride) of n values in ABI form, on the device
+// coefficients already on the device -> LDE + commitment (CompositionPoly::evaluate + commit_to_rows)
+static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint8_t root[32]) {
+    aero_ctx *ctx = seg->ctx;
+    const DftTables *plan;
+    TRY(segment_alloc_lde(seg, log_blowup, &plan));
+    const int batch = segment_lde_batch_cols(seg);
+    uint64_t *tmp = nullptr;
+    if (plan->log1 != 0) TRY(dev_alloc(ctx, (void **)&tmp, (size_t)batch * seg->lde_stride() * 8));
+    for (int c0 = 0; c0 < seg->ncols; c0 += batch) segment_lde_batch(seg, plan, c0, std::min(batch, seg->ncols - c0), tmp);
+    dev_free(ctx, tmp);
+    return segment_hash_and_tree(seg, root);
+}
+
+// d_src: ncols columns (stride src_stride) of n values in ABI form, on the device.  Columns are
+// processed in batches (interpolate, then extend); when `ready` is given, batch b first waits for
+// ready[b] -- the event that says its host->device copy has landed -- so uploads overlap compute.
 static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, size_t src_stride, uint32_t n_cols,
                                        uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
-                                       uint8_t root[32]) {
+                                       uint8_t root[32], int batch_cols = 0, const cudaEvent_t *ready = nullptr) {
     if (!out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null output handle");
     if (n_cols == 0 || n_cols > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of columns must be 1..255, got %u", n_cols);
     // Matrix::new (prover/src/matrix.rs:41-64): at least two rows, power of two
@@ -447,44 +463,49 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
     seg->ncols = (int)n_cols;
     seg->logn = logn;
     const bool mont = ctx->form == AERO_FORM_MONTGOMERY;
+    const DftTables *iplan = nullptr, *lplan = nullptr;
+    uint64_t *tmp_i = nullptr, *tmp_l = nullptr;
     aero_status st = dev_alloc(ctx, (void **)&seg->polys, (size_t)n_cols * n_rows * 8);
+    if (st == AERO_OK && !input_is_coeffs) st = plan_intt(ctx, logn, mont, &iplan);
+    if (st == AERO_OK) st = segment_alloc_lde(seg, ilog2(blowup), &lplan);
+    int batch = 0;
     if (st == AERO_OK) {
-        if (input_is_coeffs) {
-            PhaseTimer t(ctx, "convert");
-            if (src_stride == n_rows) {
-                if (mont) convert_form(d_src, seg->polys, (size_t)n_cols * n_rows, 0, ctx->stream);
-                else st = cudaMemcpyAsync(seg->polys, d_src, (size_t)n_cols * n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream) == cudaSuccess ? AERO_OK : AERO_ERR_CUDA;
-            } else {
-                for (uint32_t c = 0; c < n_cols; c++) {
-                    if (mont) convert_form(d_src + c * src_stride, seg->polys + (size_t)c * n_rows, n_rows, 0, ctx->stream);
-                    else cudaMemcpyAsync(seg->polys + (size_t)c * n_rows, d_src + c * src_stride, n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream);
-                }
-            }
-        } else {
-            const DftTables *plan;
-            st = plan_intt(ctx, logn, mont, &plan);
-            if (st == AERO_OK) {
-                char nm[32];
-                snprintf(nm, sizeof nm, "interpolate_w%d", (int)n_cols);
-                PhaseTimer t(ctx, nm);
-                uint64_t *tmp = nullptr;
-                if (plan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp, (size_t)n_cols * n_rows * 8);
-                if (st == AERO_OK) {
-                    DftLaunch l;
-                    l.src = d_src;
-                    l.dst = seg->polys;
-                    l.tmp = tmp;
-                    l.src_col_stride = src_stride;
-                    l.dst_col_stride = n_rows;
-                    l.ncols = (int)n_cols;
-                    l.deinterleave_log = 0;
-                    dft_run(*plan, l, ctx->stream);
-                    dev_free(ctx, tmp);
-                }
-            }
-        }
+        batch = batch_cols > 0 ? std::min<int>(batch_cols, (int)n_cols) : segment_lde_batch_cols(seg);
+        if (iplan && iplan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp_i, (size_t)batch * n_rows * 8);
     }
-    if (st == AERO_OK && blowup) st = segment_extend_commit(seg, ilog2(blowup), root);
+    if (st == AERO_OK && lplan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp_l, (size_t)batch * seg->lde_stride() * 8);
+    if (st == AERO_OK) {
+        char nm[32];
+        snprintf(nm, sizeof nm, "interpolate_w%d", (int)n_cols);
+        for (int c0 = 0, b = 0; c0 < (int)n_cols; c0 += batch, b++) {
+            const int nc = std::min(batch, (int)n_cols - c0);
+            if (ready) cudaStreamWaitEvent(ctx->stream, ready[b], 0);
+            const uint64_t *src = d_src + (size_t)c0 * src_stride;
+            uint64_t *dst = seg->polys + (size_t)c0 * n_rows;
+            if (input_is_coeffs) {
+                PhaseTimer t(ctx, "convert");
+                for (int c = 0; c < nc; c++) {
+                    if (mont) convert_form(src + (size_t)c * src_stride, dst + (size_t)c * n_rows, n_rows, 0, ctx->stream);
+                    else cudaMemcpyAsync(dst + (size_t)c * n_rows, src + (size_t)c * src_stride, n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+                }
+            } else {
+                PhaseTimer t(ctx, nm);
+                DftLaunch l;
+                l.src = src;
+                l.dst = dst;
+                l.tmp = tmp_i;
+                l.src_col_stride = src_stride;
+                l.dst_col_stride = n_rows;
+                l.ncols = nc;
+                l.deinterleave_log = 0;
+                dft_run(*iplan, l, ctx->stream);
+            }
+            segment_lde_batch(seg, lplan, c0, nc, tmp_l);
+        }
+        st = segment_hash_and_tree(seg, root);
+    }
+    dev_free(ctx, tmp_i);
+    dev_free(ctx, tmp_l);
     if (st != AERO_OK) {
         aero_segment_destroy(seg);
         return st;
@@ -619,6 +640,10 @@ void aero_ctx_destroy(aero_ctx *ctx) {
     if (!ctx) return;
     cudaStreamSynchronize(ctx->stream);
     profile_flush(ctx);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     cache_release_all(ctx);
     for (auto &kv : ctx->live_blocks) cudaFree(kv.first);  // handles the caller forgot to destroy
     for (void *p : ctx->owned) cudaFree(p);
@@ -729,19 +754,28 @@ aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint
     if (!cols) CTX_FAIL(ctx, AERO_ERR_INVALID, "null matrix");
     if (n_cols == 0 || n_cols > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of columns must be 1..255, got %u", n_cols);
     if (n_rows < 2 || !is_pow2(n_rows)) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of rows must be a power of two >= 2, got %llu", (unsigned long long)n_rows);
+    for (uint32_t c = 0; c < n_cols; c++)
+        if (!cols[c]) CTX_FAIL(ctx, AERO_ERR_INVALID, "null column %u", c);
     uint64_t *stage = nullptr;
     TRY(dev_alloc(ctx, (void **)&stage, (size_t)n_cols * n_rows * 8));
-    {
-        PhaseTimer t(ctx, "h2d");
-        for (uint32_t c = 0; c < n_cols; c++) {
-            if (!cols[c]) {
-                dev_free(ctx, stage);
-                CTX_FAIL(ctx, AERO_ERR_INVALID, "null column %u", c);
-            }
-            CUDA_TRY(ctx, cudaMemcpyAsync(stage + (size_t)c * n_rows, cols[c], n_rows * 8, cudaMemcpyHostToDevice, ctx->stream));
-        }
+    // Uploads run on a second stream in column batches; batch b's transforms wait only for batch b,
+    // so the PCIe copy of later columns hides behind the NTTs of earlier ones.
+    if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    const int batch = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (n_cols + 2) / 3));
+    const int nb = ((int)n_cols + batch - 1) / batch;
+    std::vector<cudaEvent_t> ev(nb + 1);
+    for (auto &e : ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // the staging block may still be read by kernels already queued on the compute stream
+    CUDA_TRY(ctx, cudaEventRecord(ev[nb], ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev[nb], 0));
+    for (int b = 0; b < nb; b++) {
+        for (uint32_t c = b * batch; c < std::min<uint32_t>(n_cols, (b + 1) * batch); c++)
+            CUDA_TRY(ctx, cudaMemcpyAsync(stage + (size_t)c * n_rows, cols[c], n_rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_TRY(ctx, cudaEventRecord(ev[b], ctx->copy_stream));
     }
-    aero_status st = segment_from_device(ctx, stage, n_rows, n_cols, n_rows, blowup, input_is_coeffs, out, root);
+    aero_status st = segment_from_device(ctx, stage, n_rows, n_cols, n_rows, blowup, input_is_coeffs, out, root, batch, ev.data());
+    cudaStreamSynchronize(ctx->copy_stream);  // the caller's host buffers are free again on return
+    for (auto &e : ev) cudaEventDestroy(e);
     dev_free(ctx, stage);
     return st;
 }
