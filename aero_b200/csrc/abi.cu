@@ -40,6 +40,11 @@ struct aero_ctx {
     int device = 0;
     cudaStream_t stream = 0;
     cudaStream_t copy_stream = nullptr;  // host->device uploads overlapped with compute
+    cudaStream_t hash_stream = nullptr;  // row hashing of batch k overlapped with the LDE of batch k+1
+    cudaEvent_t ev_lde = nullptr, ev_hash = nullptr;
+    bool overlap_hash = false;           // aero_ctx_set_option("overlap_hash"); measured slower on B200, see DESIGN.md
+    int hash_blocks_per_sm = 2;          // grid cap of an overlapped row-hash launch ("hash_blocks_per_sm")
+    int num_sms = 148;
     int form = AERO_FORM_MONTGOMERY;
     std::string err;
     bool profile = false;
@@ -86,16 +91,18 @@ struct PhaseTimer {
     aero_ctx *ctx;
     PendingEvent ev;
     bool on;
-    PhaseTimer(aero_ctx *c, const char *name) : ctx(c), on(c->profile) {
+    cudaStream_t s;
+    PhaseTimer(aero_ctx *c, const char *name, cudaStream_t stream = nullptr, bool use_given = false)
+        : ctx(c), on(c->profile), s(use_given ? stream : c->stream) {
         if (!on) return;
         ev.name = name;
         cudaEventCreate(&ev.a);
         cudaEventCreate(&ev.b);
-        cudaEventRecord(ev.a, ctx->stream);
+        cudaEventRecord(ev.a, s);
     }
     ~PhaseTimer() {
         if (!on) return;
-        cudaEventRecord(ev.b, ctx->stream);
+        cudaEventRecord(ev.b, s);
         ctx->pending.push_back(ev);
     }
 };
@@ -389,6 +396,7 @@ static aero_status segment_alloc_lde(aero_segment *seg, int log_blowup, const Df
 static int segment_lde_batch_cols(aero_segment *seg) {
     const size_t per_col = (size_t)seg->lde_stride() * 8;
     int batch = (int)std::max<size_t>(1, seg->ctx->lde_batch_bytes / per_col);
+    if (batch > 1) batch &= ~1;  // column ranges handed to the row hash start on a 64-byte block boundary
     return std::min(batch, seg->ncols);
 }
 // coset LDE of columns [c0, c0 + ncols) (tmp: >= ncols * lde_stride entries when two-pass)
@@ -410,15 +418,42 @@ static void segment_lde_batch(aero_segment *seg, const DftTables *plan, int c0, 
     l.coset_count = seg->coset_count;
     dft_run(*plan, l, ctx->stream);
 }
-static aero_status segment_hash_and_tree(aero_segment *seg, uint8_t root[32]) {
+// Row hashing of columns [c0, c0 + nc) (chaining value kept in the leaf slot, see hash_rows_kernel).
+// With ctx->overlap_hash the launch goes to a second stream, ordered after the LDE batch that
+// produced those columns, so it shares the SMs with the next batch's NTT.  Off by default: on B200
+// the mix is 1-8 % SLOWER than running the two back to back (40.3 ms serial vs 41.6-49.2 ms with
+// 4..1 hash blocks per SM) -- IMAD.WIDE blocks the ALU issue port too (tools/int_peak.cu), so the
+// NTT passes leave no usable ALU slack for the hash to fill.
+static bool segment_hash_overlapped(const aero_segment *seg) { return seg->ctx->overlap_hash && seg->ncols > 2; }
+static aero_status segment_hash_batch(aero_segment *seg, int c0, int nc) {
     aero_ctx *ctx = seg->ctx;
     const uint64_t N = seg->N(), Nl = seg->lde_stride();
-    {
-        char nm[32];
-        snprintf(nm, sizeof nm, "hash_rows_w%d", seg->ncols);
-        PhaseTimer t(ctx, nm);
-        hash_rows_lde(seg->lde, Nl, seg->ncols, seg->logn, seg->log_blowup, seg->coset_begin, (uint32_t)Nl,
-                      seg->full + (size_t)N * 8, ctx->stream);
+    cudaStream_t hs = ctx->stream;
+    if (segment_hash_overlapped(seg)) {
+        if (!ctx->hash_stream) {
+            CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->hash_stream, cudaStreamNonBlocking));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_lde, cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_hash, cudaEventDisableTiming));
+        }
+        hs = ctx->hash_stream;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_lde, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(hs, ctx->ev_lde, 0));
+    }
+    char nm[32];
+    snprintf(nm, sizeof nm, "hash_rows_w%d", seg->ncols);
+    PhaseTimer t(ctx, nm, hs, true);
+    // the last column range has no NTT beside it: give it the whole GPU
+    const bool alone = hs == ctx->stream || c0 + nc == seg->ncols;
+    hash_rows_lde(seg->lde, Nl, c0, nc, seg->ncols, seg->logn, seg->log_blowup, seg->coset_begin, (uint32_t)Nl,
+                  seg->full + (size_t)N * 8, alone ? 0 : ctx->hash_blocks_per_sm * ctx->num_sms, hs);
+    return AERO_OK;
+}
+// all column ranges hashed -> join the hash stream, then the tree
+static aero_status segment_tree_after_hash(aero_segment *seg, uint8_t root[32]) {
+    aero_ctx *ctx = seg->ctx;
+    if (segment_hash_overlapped(seg)) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_hash, ctx->hash_stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_hash, 0));
     }
     CUDA_TRY(ctx, cudaMemsetAsync(seg->full, 0, 64, ctx->stream));
     if (ctx->shard_world > 1) {
@@ -440,9 +475,20 @@ static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint
     const int batch = segment_lde_batch_cols(seg);
     uint64_t *tmp = nullptr;
     if (plan->log1 != 0) TRY(dev_alloc(ctx, (void **)&tmp, (size_t)batch * seg->lde_stride() * 8));
-    for (int c0 = 0; c0 < seg->ncols; c0 += batch) segment_lde_batch(seg, plan, c0, std::min(batch, seg->ncols - c0), tmp);
+    aero_status st = AERO_OK;
+    if ((batch & 1) || !segment_hash_overlapped(seg)) {  // extend everything, then one hash launch
+        for (int c0 = 0; c0 < seg->ncols; c0 += batch) segment_lde_batch(seg, plan, c0, std::min(batch, seg->ncols - c0), tmp);
+        st = segment_hash_batch(seg, 0, seg->ncols);
+    } else {
+        for (int c0 = 0; c0 < seg->ncols && st == AERO_OK; c0 += batch) {
+            const int nc = std::min(batch, seg->ncols - c0);
+            segment_lde_batch(seg, plan, c0, nc, tmp);
+            st = segment_hash_batch(seg, c0, nc);
+        }
+    }
     dev_free(ctx, tmp);
-    return segment_hash_and_tree(seg, root);
+    if (st != AERO_OK) return st;
+    return segment_tree_after_hash(seg, root);
 }
 
 // d_src: ncols columns (stride src_stride) of n values in ABI form, on the device.  Columns are
@@ -475,6 +521,7 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
     }
     if (st == AERO_OK && lplan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp_l, (size_t)batch * seg->lde_stride() * 8);
     if (st == AERO_OK) {
+        const bool per_batch_hash = !(batch & 1) && segment_hash_overlapped(seg);
         char nm[32];
         snprintf(nm, sizeof nm, "interpolate_w%d", (int)n_cols);
         for (int c0 = 0, b = 0; c0 < (int)n_cols; c0 += batch, b++) {
@@ -501,8 +548,10 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
                 dft_run(*iplan, l, ctx->stream);
             }
             segment_lde_batch(seg, lplan, c0, nc, tmp_l);
+            if (per_batch_hash && st == AERO_OK) st = segment_hash_batch(seg, c0, nc);
         }
-        st = segment_hash_and_tree(seg, root);
+        if (!per_batch_hash && st == AERO_OK) st = segment_hash_batch(seg, 0, (int)n_cols);
+        if (st == AERO_OK) st = segment_tree_after_hash(seg, root);
     }
     dev_free(ctx, tmp_i);
     dev_free(ctx, tmp_l);
@@ -631,6 +680,7 @@ aero_status aero_ctx_create(const int *device_ids, int n_devices, aero_ctx **out
     if (prop.major < 10) return AERO_ERR_UNSUPPORTED;  // kernels are built for sm_100a only
     aero_ctx *ctx = new aero_ctx();
     ctx->device = dev;
+    ctx->num_sms = prop.multiProcessorCount;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ctx->cache_limit_bytes = total_b / 2;
     *out = ctx;
@@ -643,6 +693,12 @@ void aero_ctx_destroy(aero_ctx *ctx) {
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
+    }
+    if (ctx->hash_stream) {
+        cudaStreamSynchronize(ctx->hash_stream);
+        cudaStreamDestroy(ctx->hash_stream);
+        cudaEventDestroy(ctx->ev_lde);
+        cudaEventDestroy(ctx->ev_hash);
     }
     cache_release_all(ctx);
     for (auto &kv : ctx->live_blocks) cudaFree(kv.first);  // handles the caller forgot to destroy
@@ -662,6 +718,15 @@ aero_status aero_ctx_set_form(aero_ctx *ctx, int form) {
     return AERO_OK;
 }
 int aero_ctx_get_form(aero_ctx *ctx) { return ctx ? ctx->form : -1; }
+aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value) {
+    if (!ctx || !key) return AERO_ERR_INVALID;
+    const std::string k(key);
+    if (k == "overlap_hash") ctx->overlap_hash = value != 0;
+    else if (k == "hash_blocks_per_sm" && value > 0) ctx->hash_blocks_per_sm = (int)value;
+    else if (k == "lde_batch_bytes" && value > 0) ctx->lde_batch_bytes = (size_t)value;
+    else CTX_FAIL(ctx, AERO_ERR_INVALID, "unknown option '%s'", key);
+    return AERO_OK;
+}
 void aero_ctx_set_error(aero_ctx *ctx, const char *msg) {
     if (ctx) ctx->err = msg ? msg : "";
 }
@@ -761,7 +826,8 @@ aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint
     // Uploads run on a second stream in column batches; batch b's transforms wait only for batch b,
     // so the PCIe copy of later columns hides behind the NTTs of earlier ones.
     if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    const int batch = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (n_cols + 2) / 3));
+    int batch = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (n_cols + 2) / 3));
+    if (batch > 1 && (batch & 1)) batch++;  // even batches: each one's row hash can start as soon as it is extended
     const int nb = ((int)n_cols + batch - 1) / batch;
     std::vector<cudaEvent_t> ev(nb + 1);
     for (auto &e : ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

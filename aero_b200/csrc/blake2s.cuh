@@ -48,30 +48,51 @@ B2S_HD uint32_t rotr7(uint32_t x) {
 #endif
 }
 
-#define B2S_G(a, b, c, d, x, y) \
-    do {                        \
-        a = a + b + (x);        \
-        d = rotr16(d ^ a);      \
-        c = c + d;              \
-        b = rotr12(b ^ c);      \
-        a = a + b + (y);        \
-        d = rotr8(d ^ a);       \
-        c = c + d;              \
-        b = rotr7(b ^ c);       \
-    } while (0)
+// Message-word additions go to the FMA pipe: the kernels built on this are bound by the ALU pipe
+// (LOP3/SHF/PRMT: 8 per G), and ptxas otherwise folds `a + b + m` into one three-input IADD3 -- an
+// ALU-pipe instruction -- while the FMA pipe idles.  `m * one + a` with `one` read from constant
+// memory (opaque to ptxas) is a plain IMAD; a compile-time-zero word still costs nothing.
+#if defined(__CUDACC__)
+static __constant__ uint32_t k_one = 1u;
+#endif
+#if defined(__CUDA_ARCH__)
+template <bool HAS>
+__device__ __forceinline__ uint32_t add_msg(uint32_t a, uint32_t m) {
+    if (HAS) asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a) : "r"(m), "r"(k_one));
+    return a;
+}
+#else
+template <bool HAS>
+inline uint32_t add_msg(uint32_t a, uint32_t m) { return HAS ? a + m : a; }
+#endif
 
-// One round with a compile-time message schedule row (s0..s15).
+// HX / HY: whether message words x / y can be non-zero (false: known-zero padding words)
+template <bool HX, bool HY>
+B2S_HD void G(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d, uint32_t x, uint32_t y) {
+    a = add_msg<HX>(a + b, x);
+    d = rotr16(d ^ a);
+    c = c + d;
+    b = rotr12(b ^ c);
+    a = add_msg<HY>(a + b, y);
+    d = rotr8(d ^ a);
+    c = c + d;
+    b = rotr7(b ^ c);
+}
+
+// One round with a compile-time message schedule row (s0..s15).  MASK bit i set = word i may be non-zero.
+#define B2S_NZ(s) (((MASK) >> (s)) & 1u)
 #define B2S_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
-    B2S_G(v0, v4, v8, v12, m[s0], m[s1]);                                               \
-    B2S_G(v1, v5, v9, v13, m[s2], m[s3]);                                               \
-    B2S_G(v2, v6, v10, v14, m[s4], m[s5]);                                              \
-    B2S_G(v3, v7, v11, v15, m[s6], m[s7]);                                              \
-    B2S_G(v0, v5, v10, v15, m[s8], m[s9]);                                              \
-    B2S_G(v1, v6, v11, v12, m[s10], m[s11]);                                            \
-    B2S_G(v2, v7, v8, v13, m[s12], m[s13]);                                             \
-    B2S_G(v3, v4, v9, v14, m[s14], m[s15]);
+    G<B2S_NZ(s0), B2S_NZ(s1)>(v0, v4, v8, v12, m[s0], m[s1]);                           \
+    G<B2S_NZ(s2), B2S_NZ(s3)>(v1, v5, v9, v13, m[s2], m[s3]);                           \
+    G<B2S_NZ(s4), B2S_NZ(s5)>(v2, v6, v10, v14, m[s4], m[s5]);                          \
+    G<B2S_NZ(s6), B2S_NZ(s7)>(v3, v7, v11, v15, m[s6], m[s7]);                          \
+    G<B2S_NZ(s8), B2S_NZ(s9)>(v0, v5, v10, v15, m[s8], m[s9]);                          \
+    G<B2S_NZ(s10), B2S_NZ(s11)>(v1, v6, v11, v12, m[s10], m[s11]);                      \
+    G<B2S_NZ(s12), B2S_NZ(s13)>(v2, v7, v8, v13, m[s12], m[s13]);                       \
+    G<B2S_NZ(s14), B2S_NZ(s15)>(v3, v4, v9, v14, m[s14], m[s15]);
 
-// Compression F(h, m, t, last).  `m` entries that are compile-time zeros cost nothing.
+// Compression F(h, m, t, last).  Words outside MASK must be zero (they are not even read).
+template <uint32_t MASK = 0xFFFFu>
 B2S_HD void compress(uint32_t h[8], const uint32_t m[16], uint32_t t0, bool last) {
     uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
     uint32_t v8 = IV0, v9 = IV1, v10 = IV2, v11 = IV3;
@@ -96,10 +117,11 @@ B2S_HD void compress(uint32_t h[8], const uint32_t m[16], uint32_t t0, bool last
     h[7] ^= v7 ^ v15;
 }
 
-// Note (measured, round 1): the row-hash kernel runs at 96-97 % of the ALU pipe (LOP3/SHF/PRMT,
-// 689 ALU-pipe instructions per compression; the 320 additions already issue as IMAD on the FMA
-// pipe).  Moving rotations to the FMA pipe as IMAD.WIDE (x * 2^(32-n), lo + hi) balanced the static
-// instruction mix (569 ALU / 538 FMA) but ran 1.5 % SLOWER on B200, so the plain form is kept.
+// Note (measured, round 1): the row-hash kernel runs at 96-97 % of the ALU pipe (LOP3/SHF/PRMT:
+// 640 per compression is the floor).  Moving rotations to the FMA pipe as IMAD.WIDE (x * 2^(32-n),
+// lo + hi) balanced the static instruction mix (569 ALU / 538 FMA) but ran 1.5 % SLOWER on B200:
+// tools/int_peak.cu shows IMAD.WIDE / IMAD.HI issue at ~0.4x the IMAD rate AND block the ALU issue
+// port meanwhile, so only plain IMAD (the additions) is worth moving.
 
 B2S_HD void init(uint32_t h[8]) {
     h[0] = H0_INIT; h[1] = IV1; h[2] = IV2; h[3] = IV3;
@@ -110,7 +132,7 @@ B2S_HD void init(uint32_t h[8]) {
 B2S_HD void compress_pair(uint32_t h[8], uint64_t e0, uint64_t e1, uint32_t t0, bool last) {
     const uint32_t m[16] = {(uint32_t)e0, (uint32_t)(e0 >> 32), 0, 0, 0, 0, 0, 0,
                             (uint32_t)e1, (uint32_t)(e1 >> 32), 0, 0, 0, 0, 0, 0};
-    compress(h, m, t0, last);
+    compress<0x0303u>(h, m, t0, last);
 }
 
 // merge(a, b) = BLAKE2s(a || b): one final 64-byte block (blake2s/mod.rs:37-39).
@@ -127,7 +149,7 @@ B2S_HD void merge_with_int(const uint32_t seed[8], uint64_t v, uint32_t out[8]) 
     uint32_t m[16] = {seed[0], seed[1], seed[2], seed[3], seed[4], seed[5], seed[6], seed[7],
                       (uint32_t)v, (uint32_t)(v >> 32), 0, 0, 0, 0, 0, 0};
     init(out);
-    compress(out, m, 40u, true);
+    compress<0x03FFu>(out, m, 40u, true);
 }
 
 }  // namespace b2s

@@ -24,31 +24,43 @@ __device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t h[8]) 
 // One thread per LDE row.  The LDE is stored coset-major: storage row rho = r*n + i holds natural
 // row k = B*i + r (B = blowup), so thread rho reads column c at lde[c*col_stride + rho]: a fully
 // coalesced 8-byte-per-lane stream.  The digest goes to the natural slot leaves[k].
-__global__ void __launch_bounds__(256) hash_rows_kernel(const uint64_t *__restrict__ lde, size_t col_stride, int ncols,
-                                                        uint32_t nrows, int logn, int log_blowup,
-                                                        uint32_t coset_begin, uint32_t *__restrict__ leaves) {
-    const uint32_t rho = blockIdx.x * blockDim.x + threadIdx.x;  // local storage row (coset q = rho >> logn)
-    if (rho >= nrows) return;
-    uint32_t h[8];
-    b2s::init(h);
-    const uint64_t *p = lde + rho;
-    const int nblocks = (ncols + 1) >> 1;
-    uint64_t e0 = __ldg(p), e1 = ncols > 1 ? __ldg(p + col_stride) : 0ULL;
-    for (int b = 0; b < nblocks; b++) {
-        uint64_t n0 = 0, n1 = 0;
-        if (b + 1 < nblocks) {  // prefetch the next pair while this block is compressed
-            n0 = __ldg(p + (size_t)(2 * b + 2) * col_stride);
-            if (2 * b + 3 < ncols) n1 = __ldg(p + (size_t)(2 * b + 3) * col_stride);
-        }
-        const bool last = (b + 1 == nblocks);
-        const uint32_t t = last ? 32u * (uint32_t)ncols : 64u * (uint32_t)(b + 1);
-        b2s::compress_pair(h, e0, e1, t, last);
-        e0 = n0;
-        e1 = n1;
-    }
+//
+// BLAKE2s absorbs the row left to right, so the chaining value after the first 2b columns depends
+// on those columns only: the kernel hashes the column range [c0, c0 + ncols) of a `total_cols`-wide
+// row (c0 even), reading the chaining value left by the previous range from leaves[k] (c0 > 0) and
+// leaving its own there.  A whole row in one launch is the case c0 = 0, ncols = total_cols.  This
+// lets the row hash of one column batch run on a second stream while the next batch is extended.
+__global__ void __launch_bounds__(256) hash_rows_kernel(const uint64_t *__restrict__ lde, size_t col_stride, int c0,
+                                                        int ncols, int total_cols, uint32_t nrows, int logn,
+                                                        int log_blowup, uint32_t coset_begin,
+                                                        uint32_t *__restrict__ leaves) {
     const uint32_t n_mask = (1u << logn) - 1;
-    const uint32_t k = ((rho & n_mask) << log_blowup) | ((rho >> logn) + coset_begin);
-    store_digest(leaves + (size_t)k * 8, h);
+    const int nblocks = (ncols + 1) >> 1;
+    const uint32_t blocks_before = (uint32_t)c0 >> 1;
+    const bool tail = (c0 + ncols == total_cols);
+    // grid-stride over local storage rows rho (coset q = rho >> logn): the launcher bounds the grid so
+    // that an overlapped launch leaves room on every SM for the NTT blocks of the next column batch
+    for (uint32_t rho = blockIdx.x * blockDim.x + threadIdx.x; rho < nrows; rho += gridDim.x * blockDim.x) {
+        const uint32_t k = ((rho & n_mask) << log_blowup) | ((rho >> logn) + coset_begin);
+        uint32_t h[8];
+        if (c0 == 0) b2s::init(h);
+        else load_digest(leaves + (size_t)k * 8, h);
+        const uint64_t *p = lde + (size_t)c0 * col_stride + rho;
+        uint64_t e0 = __ldg(p), e1 = ncols > 1 ? __ldg(p + col_stride) : 0ULL;
+        for (int b = 0; b < nblocks; b++) {
+            uint64_t n0 = 0, n1 = 0;
+            if (b + 1 < nblocks) {  // prefetch the next pair while this block is compressed
+                n0 = __ldg(p + (size_t)(2 * b + 2) * col_stride);
+                if (2 * b + 3 < ncols) n1 = __ldg(p + (size_t)(2 * b + 3) * col_stride);
+            }
+            const bool last = tail && (b + 1 == nblocks);
+            const uint32_t t = last ? 32u * (uint32_t)total_cols : 64u * (blocks_before + (uint32_t)b + 1);
+            b2s::compress_pair(h, e0, e1, t, last);
+            e0 = n0;
+            e1 = n1;
+        }
+        store_digest(leaves + (size_t)k * 8, h);
+    }
 }
 
 // Generic variant: rows of a plain column-major matrix in natural order (used for small inputs /
@@ -130,13 +142,22 @@ void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s) {
     }
 }
 
-// nrows = (number of locally stored cosets) * n ; local coset q holds natural rows B*i + coset_begin + q
-void hash_rows_lde(const uint64_t *lde, size_t col_stride, int ncols, int logn, int log_blowup, uint32_t coset_begin,
-                   uint32_t nrows, uint32_t *leaves, cudaStream_t s) {
-    if (nrows == 0) return;
+// nrows = (number of locally stored cosets) * n ; local coset q holds natural rows B*i + coset_begin + q.
+// Columns [c0, c0 + ncols) of a total_cols-wide row (see hash_rows_kernel); c0 must be even.
+// max_blocks > 0 caps the grid (the kernel strides over the rows).
+void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, int total_cols, int logn, int log_blowup,
+                   uint32_t coset_begin, uint32_t nrows, uint32_t *leaves, int max_blocks, cudaStream_t s) {
+    if (nrows == 0 || ncols == 0) return;
+    uint32_t grid = (nrows + 255) / 256;
+    if (max_blocks > 0 && grid > (uint32_t)max_blocks) grid = (uint32_t)max_blocks;
+    static bool attr_set = false;
+    if (!attr_set) {  // same shared-memory carve-out as the NTT passes, so both can be resident on one SM
+        cudaFuncSetAttribute(hash_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set = true;
+    }
     AERO_COUNT_LAUNCH(1);
-    hash_rows_kernel<<<(nrows + 255) / 256, 256, 0, s>>>(lde, col_stride, ncols, nrows, logn, log_blowup, coset_begin,
-                                                         leaves);
+    hash_rows_kernel<<<grid, 256, 0, s>>>(lde, col_stride, c0, ncols, total_cols, nrows, logn, log_blowup, coset_begin,
+                                          leaves);
 }
 void hash_rows_natural(const uint64_t *m, size_t col_stride, int ncols, uint32_t nrows, uint32_t *leaves,
                        cudaStream_t s) {

@@ -46,8 +46,8 @@ __device__ __forceinline__ void fri_gather8(const uint64_t *__restrict__ f, uint
 #endif
 
 // hash.cu
-void hash_rows_lde(const uint64_t *lde, size_t col_stride, int ncols, int logn, int log_blowup, uint32_t coset_begin,
-                   uint32_t nrows, uint32_t *leaves, cudaStream_t s);
+void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, int total_cols, int logn, int log_blowup,
+                   uint32_t coset_begin, uint32_t nrows, uint32_t *leaves, int max_blocks, cudaStream_t s);
 void hash_rows_natural(const uint64_t *m, size_t col_stride, int ncols, uint32_t nrows, uint32_t *leaves,
                        cudaStream_t s);
 void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s);

@@ -90,6 +90,10 @@ class Context:
     def set_stream(self, cuda_stream: int) -> None:
         self._check(self.lib.aero_ctx_set_stream(self.h, c_void_p(cuda_stream)))
 
+    def set_option(self, key: str, value: int) -> None:
+        """Scheduling knobs of include/aero_b200.h (aero_ctx_set_option); results never change."""
+        self._check(self.lib.aero_ctx_set_option(self.h, key.encode(), int(value)))
+
     def profile_enable(self, on: bool = True) -> None:
         self._check(self.lib.aero_ctx_profile_enable(self.h, int(on)))
 

@@ -198,6 +198,11 @@ def run_aero(args) -> None:
     ctx = aero_b200.Context(local_rank, form=aero_b200.AERO_FORM_MONTGOMERY)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    ctx.set_option("overlap_hash", args.overlap_hash)
+    if args.hash_blocks_per_sm:
+        ctx.set_option("hash_blocks_per_sm", args.hash_blocks_per_sm)
+    if args.lde_batch_mb:
+        ctx.set_option("lde_batch_bytes", args.lde_batch_mb << 20)
 
     seed = 0 if args.shard_proof else 0x1000 * rank  # a sharded proof needs the same trace on every rank
     main = splitmix_matrix(MAIN_W, n, 0xAE200000 + seed)
@@ -330,6 +335,10 @@ def main() -> None:
     ap.add_argument("--shard-proof", action="store_true",
                     help="N>1: shard ONE proof across the ranks by LDE coset (strong scaling) instead of one "
                          "independent proof per rank")
+    ap.add_argument("--overlap-hash", type=int, default=0,
+                    help="1: row hashing of column batch k runs on a second stream beside the LDE of batch k+1")
+    ap.add_argument("--hash-blocks-per-sm", type=int, default=0)
+    ap.add_argument("--lde-batch-mb", type=int, default=0, help="NTT scratch budget per column batch (MiB); 0 = default")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu): 1 warm-up, no e2e / cpu legs; numbers printed are NOT bench values")
     args = ap.parse_args()

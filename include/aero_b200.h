@@ -65,6 +65,14 @@ const char *aero_last_error(aero_ctx *ctx);
 aero_status aero_ctx_set_stream(aero_ctx *ctx, void *cuda_stream);
 aero_status aero_ctx_set_form(aero_ctx *ctx, int form);
 int aero_ctx_get_form(aero_ctx *ctx);
+/* Execution knobs (results never change, only scheduling):
+ *   "overlap_hash"    0 (default) / 1: hash the rows of column batch k on a second stream while batch
+ *                     k+1 is extended (commit_to_rows, matrix.rs:222, interleaved with
+ *                     evaluate_columns_over, :189) -- 0 serialises everything on the context's stream
+ *                     (faster on B200);
+ *   "hash_blocks_per_sm" grid cap (blocks per SM) of an overlapped row-hash launch (default 2);
+ *   "lde_batch_bytes" NTT scratch budget per column batch (default 1 GiB). */
+aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value);
 /* Used by the host driver layered above this ABI to report its own failures through aero_last_error. */
 void aero_ctx_set_error(aero_ctx *ctx, const char *msg);
 /* Per-phase CUDA-event timing (mirrors the reference's debug! timers, prover/src/lib.rs:228-630).
