@@ -43,6 +43,8 @@ struct aero_ctx {
     cudaStream_t hash_stream = nullptr;  // row hashing of batch k overlapped with the LDE of batch k+1
     cudaEvent_t ev_lde = nullptr, ev_hash = nullptr;
     bool overlap_hash = false;           // aero_ctx_set_option("overlap_hash"); measured slower on B200, see DESIGN.md
+    bool force_split_intt = false;       // test hook: take the B x size-n route of constraints_into_poly at any size
+    std::map<std::string, uint64_t *> const_tables;
     int hash_blocks_per_sm = 2;          // grid cap of an overlapped row-hash launch ("hash_blocks_per_sm")
     int num_sms = 148;
     int form = AERO_FORM_MONTGOMERY;
@@ -722,6 +724,7 @@ aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value)
     if (!ctx || !key) return AERO_ERR_INVALID;
     const std::string k(key);
     if (k == "overlap_hash") ctx->overlap_hash = value != 0;
+    else if (k == "force_split_intt") ctx->force_split_intt = value != 0;
     else if (k == "hash_blocks_per_sm" && value > 0) ctx->hash_blocks_per_sm = (int)value;
     else if (k == "lde_batch_bytes" && value > 0) ctx->lde_batch_bytes = (size_t)value;
     else CTX_FAIL(ctx, AERO_ERR_INVALID, "unknown option '%s'", key);
@@ -1056,7 +1059,68 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
         seg->logn = logn;
         st = dev_alloc(ctx, (void **)&seg->polys, N * 8);
     }
-    if (st == AERO_OK) {
+    const int logB = logN - logn;
+    if (st == AERO_OK && (logN > NTT_MAX_LOG || ctx->force_split_intt)) {
+        // N = B*n beyond the two-pass NTT: B plain size-n interpolations (one per LDE coset) and a
+        // B-point inverse DFT across them (coset_interp_combine in poly.cu)
+        if (logB > 4 || logn > NTT_MAX_LOG) {
+            ctx->err = "constraint evaluation domain too large (trace <= 2^24 rows, constraint blowup <= 16 at this size)";
+            st = AERO_ERR_UNSUPPORTED;
+        }
+        const DftTables *plan = nullptr;
+        PowTable ginv, oinv;
+        uint64_t *M = nullptr, *cm = nullptr, *a = nullptr, *tmp = nullptr;
+        char key[48];
+        if (st == AERO_OK) st = plan_intt(ctx, logn, mont, &plan);
+        snprintf(key, sizeof key, "ginv/%d/%d", logN, logn);
+        if (st == AERO_OK) st = get_pow_table(ctx, key, gl::inv(gl::root_of_unity(logN)), logn, 1, &ginv);
+        snprintf(key, sizeof key, "oinv/%d", logn);
+        if (st == AERO_OK) st = get_pow_table(ctx, key, gl::inv(gl::GENERATOR), logn, 1, &oinv);
+        snprintf(key, sizeof key, "cinterp/%d/%d", logn, logB);
+        if (st == AERO_OK) {
+            auto it = ctx->const_tables.find(key);
+            if (it == ctx->const_tables.end()) {
+                const int B = 1 << logB;
+                std::vector<uint64_t> m((size_t)B * B);
+                const uint64_t wBinv = gl::inv(gl::root_of_unity(logB));
+                const uint64_t on_inv = gl::inv(gl::pow(gl::GENERATOR, trace_len));  // offset^-n
+                uint64_t ck = gl::inv((uint64_t)B);
+                for (int k = 0; k < B; k++) {
+                    const uint64_t wk = gl::pow(wBinv, (uint64_t)k);
+                    uint64_t x = ck;
+                    for (int r = 0; r < B; r++) {
+                        m[(size_t)k * B + r] = x;
+                        x = gl::mul(x, wk);
+                    }
+                    ck = gl::mul(ck, on_inv);
+                }
+                st = upload_vec(ctx, &M, m);
+                if (st == AERO_OK) ctx->const_tables[key] = M;
+            } else {
+                M = it->second;
+            }
+        }
+        if (st == AERO_OK) st = dev_alloc(ctx, (void **)&cm, N * 8);
+        if (st == AERO_OK) st = dev_alloc(ctx, (void **)&a, N * 8);
+        if (st == AERO_OK && plan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp, N * 8);
+        if (st == AERO_OK) {
+            PhaseTimer t(ctx, "composition_poly");
+            natural_to_coset_major(combined, cm, logn, logB, ctx->stream);
+            DftLaunch l;
+            l.src = cm;
+            l.dst = a;
+            l.tmp = tmp;
+            l.src_col_stride = trace_len;
+            l.dst_col_stride = trace_len;
+            l.ncols = ncols;
+            l.deinterleave_log = 0;
+            dft_run(*plan, l, ctx->stream);
+            coset_interp_combine(a, ginv, oinv, M, logn, logB, seg->polys, ctx->stream);
+        }
+        dev_free(ctx, tmp);
+        dev_free(ctx, a);
+        dev_free(ctx, cm);
+    } else if (st == AERO_OK) {
         const DftTables *plan;
         st = plan_coset_intt(ctx, logN, mont, &plan);
         if (st == AERO_OK) {

@@ -60,6 +60,9 @@ void field_ops(const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out, cu
 void convert_form(const uint64_t *src, uint64_t *dst, size_t count, int to_montgomery, cudaStream_t s);
 void lde_to_natural(const uint64_t *lde_cm, uint64_t *out, int logn, int log_blowup, int to_montgomery,
                     cudaStream_t s);
+void natural_to_coset_major(const uint64_t *in, uint64_t *out, int logn, int log_blowup, cudaStream_t s);
+bool coset_interp_combine(const uint64_t *a, PowTable ginv, PowTable oinv, const uint64_t *M, int logn, int log_b,
+                          uint64_t *polys, cudaStream_t s);
 // out[p*2 + 0/1] partial sums; see poly.cu
 void ood_eval(const uint64_t *polys, size_t col_stride, int ncols, int logn, const uint64_t *d_points, int npoints,
               uint64_t *d_out /* ncols*npoints */, uint64_t *d_scratch, cudaStream_t s);

@@ -57,6 +57,70 @@ void lde_to_natural(const uint64_t *lde_cm, uint64_t *out, int logn, int log_blo
     lde_to_natural_kernel<<<(unsigned)blocks, 256, 0, s>>>(lde_cm, out, logn, log_blowup, to_montgomery);
 }
 
+// natural order -> coset-major: out[r*n + i] = in[B*i + r]
+__global__ void natural_to_coset_major_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, int logn,
+                                              int log_blowup) {
+    const size_t N = (size_t)1 << (logn + log_blowup);
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = k & (((size_t)1 << log_blowup) - 1), i = k >> log_blowup;
+        out[(r << logn) + i] = in[k];
+    }
+}
+void natural_to_coset_major(const uint64_t *in, uint64_t *out, int logn, int log_blowup, cudaStream_t s) {
+    const size_t N = (size_t)1 << (logn + log_blowup);
+    size_t blocks = (N + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    AERO_COUNT_LAUNCH(1);
+    natural_to_coset_major_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, logn, log_blowup);
+}
+
+// Last step of a size-N = B*n coset interpolation done as B size-n interpolations (the route taken
+// when N exceeds the two-pass NTT, i.e. for traces above 2^21 rows).  With a_r = plain inverse DFT
+// (scale 1/n) of the evaluations on coset r (x = s_r w_n^i, s_r = offset g_N^r), the residue of f
+// modulo x^n - s_r^n has coefficients s_r^-j a_r[j]; writing f = sum_k F_k x^(kn) gives
+//   s_r^-j a_r[j] = sum_k F_k[j] (offset^n)^k w_B^(rk)
+// so F_k[j] = offset^(-nk)/B * sum_r w_B^(-rk) s_r^-j a_r[j]: a B-point inverse DFT across cosets.
+// M[k*B + r] = offset^(-nk)/B * w_B^(-rk).  Coefficient c = k*n + j goes to composition column
+// c mod B, row c div B (CompositionPoly::transpose, composition_poly.rs:111-128).
+template <int LOGB>
+__global__ void __launch_bounds__(256) coset_interp_combine_kernel(const uint64_t *__restrict__ a, PowTable ginv,
+                                                                   PowTable oinv, const uint64_t *__restrict__ M,
+                                                                   int logn, uint64_t *__restrict__ polys) {
+    constexpr int B = 1 << LOGB;
+    const size_t n = (size_t)1 << logn;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t step = pow_lookup(ginv, (uint32_t)j);  // g_N^-j
+    uint64_t t = pow_lookup(oinv, (uint32_t)j);           // offset^-j
+    uint64_t y[B];
+#pragma unroll
+    for (int r = 0; r < B; r++) {
+        y[r] = gl::mul(a[((size_t)r << logn) + j], t);
+        t = gl::mul(t, step);
+    }
+#pragma unroll
+    for (int k = 0; k < B; k++) {
+        uint64_t acc = 0;
+#pragma unroll
+        for (int r = 0; r < B; r++) acc = gl::add(acc, gl::mul(y[r], __ldg(M + k * B + r)));
+        const size_t c = ((size_t)k << logn) + j;
+        polys[((c & (B - 1)) << logn) + (c >> LOGB)] = acc;
+    }
+}
+bool coset_interp_combine(const uint64_t *a, PowTable ginv, PowTable oinv, const uint64_t *M, int logn, int log_b,
+                          uint64_t *polys, cudaStream_t s) {
+    const size_t n = (size_t)1 << logn;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    AERO_COUNT_LAUNCH(1);
+    switch (log_b) {
+        case 1: coset_interp_combine_kernel<1><<<blocks, 256, 0, s>>>(a, ginv, oinv, M, logn, polys); return true;
+        case 2: coset_interp_combine_kernel<2><<<blocks, 256, 0, s>>>(a, ginv, oinv, M, logn, polys); return true;
+        case 3: coset_interp_combine_kernel<3><<<blocks, 256, 0, s>>>(a, ginv, oinv, M, logn, polys); return true;
+        case 4: coset_interp_combine_kernel<4><<<blocks, 256, 0, s>>>(a, ginv, oinv, M, logn, polys); return true;
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Block-wide helpers
 // ---------------------------------------------------------------------------------------------

@@ -32,6 +32,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MAIN_W, AUX_W, CE_COLS, BLOWUP = 72, 9, 2, 8
+# INT roofline of the row hash: static ALU-pipe instruction count of one
+# compress_pair in hash_rows_kernel (cuobjdump: 330 LOP3 + 160 SHF + 160 PRMT + 11 VIADD; floor 648),
+# and the ALU-pipe issue rate measured by tools/int_peak.cu on this pool's B200s.
+ALU_OPS_PER_COMPRESSION = 661
+ALU_PEAK_LANE_OPS = 18.4e12
+# dram__bytes_read.sum + dram__bytes_write.sum of one hash_rows_kernel launch (w=72, N=2^23) from the
+# ncu --set full capture in profiles/ (4.83 GB + 0.27 GB): equals the algorithmic bytes, no re-reads.
+HASH_W72_NCU_DRAM_BYTES = 5.1035e9
 PUB = b"aero-b200 bench public inputs"
 
 
@@ -220,8 +228,10 @@ def run_aero(args) -> None:
     def pin(a):
         t = torch.from_numpy(a.view(np.int64)).pin_memory()
         return t, t.numpy().view(np.uint64)
-    keep = [pin(main), pin(aux), pin(ce)]
-    h_main, h_aux, h_ce = keep[0][1], keep[1][1], keep[2][1]
+    if not args.quick:  # (the profiling aid never runs the e2e leg)
+        keep = [pin(main), pin(aux), pin(ce)]
+        h_main, h_aux, h_ce = keep[0][1], keep[1][1], keep[2][1]
+    del main, aux, ce
 
     shard = None
     if args.shard_proof and world > 1:
@@ -296,14 +306,22 @@ def run_aero(args) -> None:
     if rank == 0:
         peak, peak_kind = measured_peaks()
         calls, tot_ms = prof.get("hash_rows_w%d" % MAIN_W, (0, 0.0))
+        if shard is not None:
+            N = N // world  # a coset shard hashes N/world rows per launch
         alg_bytes = 8 * MAIN_W * N + 32 * N  # read 8wN + write 32N per launch
         avg_ms = tot_ms / calls if calls else None
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms else None
+        comp_per_s = (36 * N) / (avg_ms * 1e-3) if avg_ms else None
         roofline = {"bound": "hbm", "kernel": "hash_rows_kernel (blake2s leaf hash, w=72; INT32-ALU bound: "
-                    "36 compressions x ~980 int ops per row vs 608 B per row)",
+                    "36 compressions x 661 ALU-pipe ops per row vs 608 B per row)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                    "traffic": None, "peak_kind": peak_kind, "avg_launch_ms": avg_ms,
-                    "compressions_per_s": (36 * N) / (avg_ms * 1e-3) if avg_ms else None}
+                    "traffic": HASH_W72_NCU_DRAM_BYTES if (log_rows == 20 and shard is None) else None, "peak_kind": peak_kind,
+                    "avg_launch_ms": avg_ms, "compressions_per_s": comp_per_s,
+                    # the roofline that actually binds this kernel: ALU-pipe instruction issue
+                    "int": {"unit": "ALU-pipe lane-ops/s", "ops_per_compression": ALU_OPS_PER_COMPRESSION,
+                            "achieved": comp_per_s * ALU_OPS_PER_COMPRESSION if comp_per_s else None,
+                            "peak": ALU_PEAK_LANE_OPS, "peak_kind": "measured (tools/int_peak.cu, profiles/r01_int_peak.txt)",
+                            "frac": comp_per_s * ALU_OPS_PER_COMPRESSION / ALU_PEAK_LANE_OPS if comp_per_s else None}}
         cpu = None
         if not args.no_cpu_baseline:
             rps, dt, cores = cpu_port_rows_per_s(args.ref_log_rows, 1)

@@ -164,6 +164,38 @@ def test_constraints_into_poly(ctx, oracle, logn):
     assert root == oracle.commit_polys(ref, 8).root
 
 
+@pytest.mark.parametrize("form", ["canonical", "montgomery"])
+@pytest.mark.parametrize("logn,ce_blowup", [(1, 8), (3, 2), (4, 8), (6, 4), (8, 16), (10, 8), (12, 8), (13, 8)])
+def test_constraints_into_poly_split_route(ctx, ctx_mont, oracle, logn, ce_blowup, form):
+    """Traces above 2^21 rows interpolate the constraint evaluations as B size-n interpolations plus a
+    B-point inverse DFT across the LDE cosets (N = B*n exceeds the two-pass NTT).  The route is forced
+    here at sizes the oracle covers; it must give the same coefficients as the direct one."""
+    c = ctx if form == "canonical" else ctx_mont
+    n = 1 << logn
+    N = ce_blowup * n
+    g = oracle.root_of_unity(logn)
+    cols = oracle.synthetic_trace(2, N, 0xCE00 + logn)
+    divs = [oracle.Divisor(n, 1, [pow(g, n - 1, P)]), oracle.Divisor(1, 1, [])]
+    ref = oracle.constraints_into_poly(cols, divs, n)
+    dv = [make_divisor(d.a, d.b, d.exemptions) for d in divs]
+    if form == "montgomery":
+        cols_in = oracle.canon_to_mont(cols)
+        dv = [make_divisor(d.a, int(oracle.canon_to_mont(np.array([d.b], np.uint64))[0]),
+                           [int(v) for v in oracle.canon_to_mont(np.array(d.exemptions, np.uint64))]) for d in divs]
+    else:
+        cols_in = cols
+    c.set_option("force_split_intt", 1)
+    try:
+        seg = c.constraints_into_poly(cols_in, dv, n)
+        got = seg.download_polys()
+    finally:
+        c.set_option("force_split_intt", 0)
+    if form == "montgomery":
+        got = oracle.mont_to_canon(got)
+    assert np.array_equal(got, ref)
+    seg.destroy()
+
+
 # ------------------------------------------------------------------------------------------------
 # OOD + DEEP (K7, K6)
 # ------------------------------------------------------------------------------------------------
