@@ -36,6 +36,15 @@ struct PowTableOwned {
     PowTable view() const { return PowTable{lo, hi, lo_bits}; }
 };
 
+struct aero_upload {
+    aero_ctx *ctx = nullptr;
+    uint64_t *d = nullptr;          // n_cols x n_rows, contiguous columns
+    cudaEvent_t done = nullptr;
+    std::vector<const uint64_t *> cols;
+    uint64_t n_rows = 0;
+    bool queued = false;
+};
+
 struct aero_ctx {
     int device = 0;
     cudaStream_t stream = 0;
@@ -45,6 +54,7 @@ struct aero_ctx {
     bool overlap_hash = false;           // aero_ctx_set_option("overlap_hash"); measured slower on B200, see DESIGN.md
     bool force_split_intt = false;       // test hook: take the B x size-n route of constraints_into_poly at any size
     std::map<std::string, uint64_t *> const_tables;
+    std::vector<aero_upload *> deferred_uploads;  // queued behind the next segment commit's own copies
     int hash_blocks_per_sm = 2;          // grid cap of an overlapped row-hash launch ("hash_blocks_per_sm")
     int num_sms = 148;
     int form = AERO_FORM_MONTGOMERY;
@@ -806,6 +816,74 @@ aero_status aero_test_field_ops(aero_ctx *ctx, const uint64_t *a, const uint64_t
     return AERO_OK;
 }
 
+// ---- prefetched uploads ------------------------------------------------------------------------
+static aero_status upload_enqueue(aero_upload *u) {
+    aero_ctx *ctx = u->ctx;
+    if (u->queued) return AERO_OK;
+    if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (size_t c = 0; c < u->cols.size(); c++)
+        CUDA_TRY(ctx, cudaMemcpyAsync(u->d + c * u->n_rows, u->cols[c], u->n_rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(ctx, cudaEventRecord(u->done, ctx->copy_stream));
+    u->queued = true;
+    return AERO_OK;
+}
+static aero_status flush_deferred_uploads(aero_ctx *ctx) {
+    std::vector<aero_upload *> list;
+    list.swap(ctx->deferred_uploads);
+    for (aero_upload *u : list) TRY(upload_enqueue(u));
+    return AERO_OK;
+}
+aero_status aero_upload_start(aero_ctx *ctx, const uint64_t *const *cols, uint32_t n_cols, uint64_t n_rows, int defer,
+                              aero_upload **out) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (!cols || !out || n_cols == 0 || n_rows == 0) CTX_FAIL(ctx, AERO_ERR_INVALID, "null or empty matrix");
+    for (uint32_t c = 0; c < n_cols; c++)
+        if (!cols[c]) CTX_FAIL(ctx, AERO_ERR_INVALID, "null column %u", c);
+    aero_upload *u = new aero_upload();
+    u->ctx = ctx;
+    u->n_rows = n_rows;
+    u->cols.assign(cols, cols + n_cols);
+    aero_status st = dev_alloc(ctx, (void **)&u->d, (size_t)n_cols * n_rows * 8);
+    if (st == AERO_OK && cudaEventCreateWithFlags(&u->done, cudaEventDisableTiming) != cudaSuccess) {
+        ctx->err = "cudaEventCreate failed";
+        st = AERO_ERR_CUDA;
+    }
+    if (st == AERO_OK) {
+        if (defer) ctx->deferred_uploads.push_back(u);
+        else st = upload_enqueue(u);
+    }
+    if (st != AERO_OK) {
+        dev_free(ctx, u->d);
+        if (u->done) cudaEventDestroy(u->done);
+        delete u;
+        return st;
+    }
+    *out = u;
+    return AERO_OK;
+}
+aero_status aero_upload_wait(aero_upload *u, const uint64_t **d_cols) {
+    if (!u || !d_cols) return AERO_ERR_INVALID;
+    aero_ctx *ctx = u->ctx;
+    if (!u->queued) {  // still deferred: no commit came in between
+        auto &v = ctx->deferred_uploads;
+        v.erase(std::remove(v.begin(), v.end(), u), v.end());
+        TRY(upload_enqueue(u));
+    }
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, u->done, 0));
+    *d_cols = u->d;
+    return AERO_OK;
+}
+void aero_upload_free(aero_upload *u) {
+    if (!u) return;
+    aero_ctx *ctx = u->ctx;
+    auto &v = ctx->deferred_uploads;
+    v.erase(std::remove(v.begin(), v.end(), u), v.end());
+    if (u->queued) cudaEventSynchronize(u->done);  // the host columns are free again, and so is the block
+    cudaEventDestroy(u->done);
+    dev_free(ctx, u->d);  // later users of the block are ordered on ctx->stream, which waited for `done`
+    delete u;
+}
+
 // ---- segments -------------------------------------------------------------------------------
 aero_status aero_segment_commit_device(aero_ctx *ctx, const uint64_t *d_cols, size_t col_stride, uint32_t n_cols,
                                        uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
@@ -842,8 +920,9 @@ aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint
             CUDA_TRY(ctx, cudaMemcpyAsync(stage + (size_t)c * n_rows, cols[c], n_rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
         CUDA_TRY(ctx, cudaEventRecord(ev[b], ctx->copy_stream));
     }
+    TRY(flush_deferred_uploads(ctx));  // prefetches ride behind this segment's copies, under its NTTs
     aero_status st = segment_from_device(ctx, stage, n_rows, n_cols, n_rows, blowup, input_is_coeffs, out, root, batch, ev.data());
-    cudaStreamSynchronize(ctx->copy_stream);  // the caller's host buffers are free again on return
+    cudaEventSynchronize(ev[nb - 1]);  // the caller's host buffers are free again on return
     for (auto &e : ev) cudaEventDestroy(e);
     dev_free(ctx, stage);
     return st;

@@ -233,7 +233,10 @@ namespace {
 struct Handles {  // RAII for the device handles of one proof
     std::vector<aero_segment *> segs;
     aero_fri *fri = nullptr;
+    aero_upload *up_aux = nullptr, *up_ce = nullptr;
     ~Handles() {
+        aero_upload_free(up_aux);
+        aero_upload_free(up_ce);
         aero_fri_destroy(fri);
         for (auto s : segs) aero_segment_destroy(s);
     }
@@ -306,6 +309,13 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     ProverChannel channel(ctx, in);
     uint8_t root[32];
 
+    // Host inputs that are already known (no callback produces them) start travelling now: their copies
+    // queue behind the main segment's own and land while its columns are being extended and hashed.
+    if (!in.inputs_on_device) {
+        if (in.aux_width && !in.aux_builder) P_TRY(aero_upload_start(ctx, in.aux_cols, in.aux_width, n, 1, &H.up_aux));
+        if (!in.constraint_evaluator) P_TRY(aero_upload_start(ctx, in.ce_cols, in.n_div, N, 1, &H.up_ce));
+    }
+
     // 1 ----- commit to the execution trace (lib.rs:239-248, 269-348)
     aero_segment *main_seg = nullptr;
     if (in.inputs_on_device)
@@ -329,7 +339,11 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
             if (st != AERO_OK) P_FAIL(st, "aux_builder callback failed");
             aux_cols = aux_ptrs.data();
         }
-        if (in.inputs_on_device)
+        if (H.up_aux) {
+            const uint64_t *d_aux = nullptr;
+            P_TRY(aero_upload_wait(H.up_aux, &d_aux));
+            P_TRY(aero_segment_commit_device(ctx, d_aux, n, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root));
+        } else if (in.inputs_on_device)
             P_TRY(aero_segment_commit_device(ctx, aux_cols[0], n, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root));
         else
             P_TRY(aero_segment_commit(ctx, aux_cols, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root));
@@ -364,7 +378,11 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
 
     // 3 ----- commit to constraint evaluations (lib.rs:396-419)
     aero_segment *comp_seg = nullptr;
-    if (in.inputs_on_device)
+    if (H.up_ce) {
+        const uint64_t *d_ce = nullptr;
+        P_TRY(aero_upload_wait(H.up_ce, &d_ce));
+        P_TRY(aero_constraints_into_poly_device(ctx, d_ce, N, in.divisors, in.n_div, N, n, &comp_seg));
+    } else if (in.inputs_on_device)
         P_TRY(aero_constraints_into_poly_device(ctx, ce_cols[0], N, in.divisors, in.n_div, N, n, &comp_seg));
     else
         P_TRY(aero_constraints_into_poly(ctx, ce_cols, in.divisors, in.n_div, N, n, &comp_seg));

@@ -46,6 +46,7 @@ enum { AERO_FORM_MONTGOMERY = 0, AERO_FORM_CANONICAL = 1 };
 typedef struct aero_ctx aero_ctx;
 typedef struct aero_segment aero_segment;
 typedef struct aero_fri aero_fri;
+typedef struct aero_upload aero_upload;
 
 /* (x^a - b) / prod_k (x - exemptions[k]) : air::ConstraintDivisor (air/src/air/divisor.rs:14-17) */
 typedef struct aero_divisor {
@@ -190,6 +191,17 @@ aero_status aero_device_free(aero_ctx *ctx, void *d_ptr);
 aero_status aero_device_upload(aero_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 aero_status aero_device_download(aero_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 aero_status aero_device_sync(aero_ctx *ctx);
+/* Prefetched host->device upload of a column-major matrix (n_cols host pointers, ABI form) on the
+ * context's copy stream, so that it lands while earlier phases compute: e.g. the auxiliary segment and
+ * the constraint evaluations of Prover::prove travel under the main segment's NTTs.  defer != 0 queues
+ * the copies behind the uploads of the next aero_segment_commit instead of ahead of them.
+ * aero_upload_wait orders the context's stream after the copy and returns the device matrix (column c
+ * at d_cols + c*n_rows) for the *_device entry points.  The host columns must stay valid until
+ * aero_upload_free, which also releases the device block. */
+aero_status aero_upload_start(aero_ctx *ctx, const uint64_t *const *cols, uint32_t n_cols, uint64_t n_rows, int defer,
+                              aero_upload **out);
+aero_status aero_upload_wait(aero_upload *up, const uint64_t **d_cols);
+void aero_upload_free(aero_upload *up);
 
 #ifdef __cplusplus
 }
