@@ -77,6 +77,11 @@ PROTOTYPES = {
     "aero_ctx_profile_read": (c_int, [c_void_p, c_char_p, POINTER(c_size_t)]),
     "aero_launch_count": (c_uint64, []),
     "aero_version": (c_char_p, []),
+    "aero_ctx_window_create": (c_int, [c_void_p, c_size_t, p_u8]),
+    "aero_ctx_window_attach": (c_int, [c_void_p, c_int, p_u8]),
+    "aero_ctx_window_ranks": (c_int, [c_void_p]),
+    "aero_window_barrier": (c_int, [c_void_p]),
+    "aero_fri_push_evaluations": (c_int, [c_void_p]),
     "aero_upload_start": (c_int, [c_void_p, pp_u64, c_uint32, c_uint64, c_int, POINTER(c_void_p)]),
     "aero_upload_wait": (c_int, [c_void_p, POINTER(c_void_p)]),
     "aero_upload_free": (None, [c_void_p]),

@@ -3,6 +3,7 @@
 // byte packing); every field/hash operation over trace-sized data runs in a CUDA kernel.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -55,6 +56,18 @@ struct aero_ctx {
     bool force_split_intt = false;       // test hook: take the B x size-n route of constraints_into_poly at any size
     std::map<std::string, uint64_t *> const_tables;
     std::vector<aero_upload *> deferred_uploads;  // queued behind the next segment commit's own copies
+    // Exchange window (multi-GPU): one allocation per rank, the same size everywhere, opened by every
+    // peer through CUDA IPC.  [0, 4096): barrier flags and the time-out word; the rest is a bump heap
+    // that all ranks of a sharded proof allocate from in the same order, so a buffer sits at the same
+    // offset in every window and a kernel can store to its peer copies directly over NVLink.
+    uint8_t *win = nullptr;
+    size_t win_bytes = 0, win_off = 4096;
+    int win_live = 0;
+    int win_ranks = 0;                       // > 1 once the peers are attached and "use_window" is on
+    int win_attached = 0;
+    uint8_t *win_peer[AERO_MAX_PEERS] = {};  // peer windows, in increasing rank order, own rank skipped
+    int win_peer_rank[AERO_MAX_PEERS] = {};
+    unsigned long long win_epoch = 0;
     int hash_blocks_per_sm = 2;          // grid cap of an overlapped row-hash launch ("hash_blocks_per_sm")
     int num_sms = 148;
     int form = AERO_FORM_MONTGOMERY;
@@ -167,8 +180,15 @@ static aero_status dev_alloc(aero_ctx *ctx, void **p, size_t bytes) {
     ctx->live_blocks[*p] = bytes;
     return AERO_OK;
 }
+static bool win_owns(const aero_ctx *ctx, const void *p) {
+    return ctx->win && (const uint8_t *)p >= ctx->win && (const uint8_t *)p < ctx->win + ctx->win_bytes;
+}
 static void dev_free(aero_ctx *ctx, void *p) {
     if (!p) return;
+    if (win_owns(ctx, p)) {  // bump heap: space comes back when the last buffer of the proof goes
+        if (--ctx->win_live == 0) ctx->win_off = 4096;
+        return;
+    }
     auto it = ctx->live_blocks.find(p);
     if (it == ctx->live_blocks.end()) return;
     const size_t bytes = it->second;
@@ -176,6 +196,49 @@ static void dev_free(aero_ctx *ctx, void *p) {
     ctx->free_blocks.emplace(bytes, p);
     ctx->cached_bytes += bytes;
     if (ctx->cached_bytes > ctx->cache_limit_bytes) cache_release_all(ctx);
+}
+// Buffers that other ranks write into (leaf digests, DEEP evaluations) live in the exchange window
+// when one is attached; otherwise this is dev_alloc.
+static aero_status dev_alloc_shared(aero_ctx *ctx, void **p, size_t bytes) {
+    if (ctx->win_ranks > 1 && ctx->shard_world > 1) {
+        bytes = (bytes + 511) & ~(size_t)511;
+        if (ctx->win_off + bytes > ctx->win_bytes)
+            CTX_FAIL(ctx, AERO_ERR_NOMEM, "exchange window too small: %zu bytes needed, %zu of %zu in use", bytes, ctx->win_off, ctx->win_bytes);
+        *p = ctx->win + ctx->win_off;
+        ctx->win_off += bytes;
+        ctx->win_live++;
+        return AERO_OK;
+    }
+    return dev_alloc(ctx, p, bytes);
+}
+// the copies of a window buffer in the peer windows (empty when `p` is not in the window)
+static PeerPtrs peers_of(const aero_ctx *ctx, const void *p) {
+    PeerPtrs q;
+    if (ctx->win_ranks > 1 && win_owns(ctx, p)) {
+        const size_t off = (const uint8_t *)p - ctx->win;
+        q.n = ctx->win_ranks - 1;
+        for (int i = 0; i < q.n; i++) q.p[i] = ctx->win_peer[i] + off;
+    }
+    return q;
+}
+static aero_status window_barrier(aero_ctx *ctx) {
+    if (ctx->win_ranks <= 1 || ctx->shard_world <= 1) return AERO_OK;
+    PeerPtrs f;
+    f.n = ctx->win_ranks - 1;
+    for (int i = 0; i < f.n; i++) f.p[i] = ctx->win_peer[i];
+    peer_barrier((unsigned long long *)ctx->win, f, ctx->shard_rank, ctx->win_peer_rank, ++ctx->win_epoch,
+                 (unsigned int *)(ctx->win + 2048), ctx->stream);
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (getenv("AERO_WINDOW_DEBUG")) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        unsigned long long fl[8];
+        unsigned int to = 0;
+        cudaMemcpy(fl, ctx->win, 64, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&to, ctx->win + 2048, 4, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[window] rank %d epoch %llu sync=%s flags=[%llu %llu %llu %llu] timeouts=%u\n", ctx->shard_rank,
+                ctx->win_epoch, cudaGetErrorString(e), fl[0], fl[1], fl[2], fl[3], to);
+    }
+    return AERO_OK;
 }
 template <typename T>
 static aero_status upload_vec(aero_ctx *ctx, T **d, const std::vector<T> &h, bool own = true) {
@@ -402,7 +465,7 @@ static aero_status segment_alloc_lde(aero_segment *seg, int log_blowup, const Df
     seg->coset_count = B / ctx->shard_world;
     seg->coset_begin = ctx->shard_rank * seg->coset_count;
     TRY(dev_alloc(ctx, (void **)&seg->lde, (size_t)seg->ncols * seg->lde_stride() * 8));
-    TRY(dev_alloc(ctx, (void **)&seg->full, (size_t)2 * seg->N() * 32));
+    TRY(dev_alloc_shared(ctx, (void **)&seg->full, (size_t)2 * seg->N() * 32));
     return plan_lde(ctx, seg->logn, log_blowup, false, plan);
 }
 static int segment_lde_batch_cols(aero_segment *seg) {
@@ -436,7 +499,9 @@ static void segment_lde_batch(aero_segment *seg, const DftTables *plan, int c0, 
 // the mix is 1-8 % SLOWER than running the two back to back (40.3 ms serial vs 41.6-49.2 ms with
 // 4..1 hash blocks per SM) -- IMAD.WIDE blocks the ALU issue port too (tools/int_peak.cu), so the
 // NTT passes leave no usable ALU slack for the hash to fill.
-static bool segment_hash_overlapped(const aero_segment *seg) { return seg->ctx->overlap_hash && seg->ncols > 2; }
+static bool segment_hash_overlapped(const aero_segment *seg) {
+    return seg->ctx->overlap_hash && seg->ncols > 2 && seg->ctx->win_ranks <= 1;
+}
 static aero_status segment_hash_batch(aero_segment *seg, int c0, int nc) {
     aero_ctx *ctx = seg->ctx;
     const uint64_t N = seg->N(), Nl = seg->lde_stride();
@@ -451,13 +516,17 @@ static aero_status segment_hash_batch(aero_segment *seg, int c0, int nc) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_lde, ctx->stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(hs, ctx->ev_lde, 0));
     }
+    uint32_t *leaves = seg->full + (size_t)N * 8;
+    const PeerPtrs peers = peers_of(ctx, leaves);
+    // the peers' copies of this leaf array may still be in use by their previous proof
+    if (peers.n && c0 == 0) TRY(window_barrier(ctx));
     char nm[32];
     snprintf(nm, sizeof nm, "hash_rows_w%d", seg->ncols);
     PhaseTimer t(ctx, nm, hs, true);
     // the last column range has no NTT beside it: give it the whole GPU
     const bool alone = hs == ctx->stream || c0 + nc == seg->ncols;
-    hash_rows_lde(seg->lde, Nl, c0, nc, seg->ncols, seg->logn, seg->log_blowup, seg->coset_begin, (uint32_t)Nl,
-                  seg->full + (size_t)N * 8, alone ? 0 : ctx->hash_blocks_per_sm * ctx->num_sms, hs);
+    hash_rows_lde(seg->lde, Nl, c0, nc, seg->ncols, seg->logn, seg->log_blowup, seg->coset_begin, (uint32_t)Nl, leaves,
+                  peers, alone ? 0 : ctx->hash_blocks_per_sm * ctx->num_sms, hs);
     return AERO_OK;
 }
 // all column ranges hashed -> join the hash stream, then the tree
@@ -712,6 +781,9 @@ void aero_ctx_destroy(aero_ctx *ctx) {
         cudaEventDestroy(ctx->ev_lde);
         cudaEventDestroy(ctx->ev_hash);
     }
+    for (int i = 0; i < AERO_MAX_PEERS; i++)
+        if (ctx->win_peer[i]) cudaIpcCloseMemHandle(ctx->win_peer[i]);
+    if (ctx->win) cudaFree(ctx->win);
     cache_release_all(ctx);
     for (auto &kv : ctx->live_blocks) cudaFree(kv.first);  // handles the caller forgot to destroy
     for (void *p : ctx->owned) cudaFree(p);
@@ -734,6 +806,10 @@ aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value)
     if (!ctx || !key) return AERO_ERR_INVALID;
     const std::string k(key);
     if (k == "overlap_hash") ctx->overlap_hash = value != 0;
+    else if (k == "use_window") {
+        if (ctx->win_live) CTX_FAIL(ctx, AERO_ERR_STATE, "window buffers are live");
+        ctx->win_ranks = value ? ctx->win_attached : 0;
+    }
     else if (k == "force_split_intt") ctx->force_split_intt = value != 0;
     else if (k == "hash_blocks_per_sm" && value > 0) ctx->hash_blocks_per_sm = (int)value;
     else if (k == "lde_batch_bytes" && value > 0) ctx->lde_batch_bytes = (size_t)value;
@@ -935,6 +1011,81 @@ aero_status aero_ctx_set_shard(aero_ctx *ctx, int rank, int world) {
     ctx->shard_world = world;
     return AERO_OK;
 }
+aero_status aero_ctx_window_create(aero_ctx *ctx, size_t bytes, uint8_t handle_out[64]) {
+    if (!ctx || !handle_out) return AERO_ERR_INVALID;
+    if (ctx->win) CTX_FAIL(ctx, AERO_ERR_STATE, "exchange window already created");
+    if (bytes < 8192) CTX_FAIL(ctx, AERO_ERR_INVALID, "exchange window must be at least 8 KiB");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, 4096);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        CTX_FAIL(ctx, AERO_ERR_CUDA, "exchange window: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, 64);
+    ctx->win = (uint8_t *)p;
+    ctx->win_bytes = bytes;
+    ctx->win_off = 4096;
+    ctx->win_live = 0;
+    return AERO_OK;
+}
+aero_status aero_ctx_window_attach(aero_ctx *ctx, int n_ranks, const uint8_t *handles) {
+    if (!ctx || !handles) return AERO_ERR_INVALID;
+    if (!ctx->win) CTX_FAIL(ctx, AERO_ERR_STATE, "create the exchange window first");
+    if (ctx->win_ranks) CTX_FAIL(ctx, AERO_ERR_STATE, "exchange window already attached");
+    if (n_ranks != ctx->shard_world || n_ranks < 2 || n_ranks > AERO_MAX_PEERS + 1)
+        CTX_FAIL(ctx, AERO_ERR_INVALID, "window ranks (%d) must equal the shard world size (%d), 2..%d", n_ranks, ctx->shard_world, AERO_MAX_PEERS + 1);
+    int k = 0;
+    for (int r = 0; r < n_ranks; r++) {
+        if (r == ctx->shard_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int i = 0; i < k; i++) cudaIpcCloseMemHandle(ctx->win_peer[i]), ctx->win_peer[i] = nullptr;
+            CTX_FAIL(ctx, AERO_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        }
+        ctx->win_peer[k] = (uint8_t *)p;
+        ctx->win_peer_rank[k] = r;
+        k++;
+    }
+    ctx->win_ranks = ctx->win_attached = n_ranks;
+    return AERO_OK;
+}
+int aero_ctx_window_ranks(aero_ctx *ctx) { return (ctx && ctx->shard_world > 1) ? ctx->win_ranks : 0; }
+aero_status aero_window_barrier(aero_ctx *ctx) {
+    if (!ctx) return AERO_ERR_INVALID;
+    return window_barrier(ctx);
+}
+// a peer that never reached a barrier (it failed) is reported here instead of hanging the GPU
+static aero_status window_check(aero_ctx *ctx) {
+    if (ctx->win_ranks <= 1 || ctx->shard_world <= 1) return AERO_OK;
+    unsigned int t = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&t, ctx->win + 2048, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (t) CTX_FAIL(ctx, AERO_ERR_STATE, "exchange barrier timed out %u time(s): a peer rank did not arrive", t);
+    return AERO_OK;
+}
+aero_status aero_fri_push_evaluations(aero_fri *fri) {
+    if (!fri) return AERO_ERR_INVALID;
+    aero_ctx *ctx = fri->ctx;
+    if (!fri->cur_pending) return AERO_OK;
+    const PeerPtrs peers = peers_of(ctx, fri->cur);
+    if (peers.n == 0) CTX_FAIL(ctx, AERO_ERR_STATE, "no exchange window attached");
+    const size_t per = (size_t)fri->curM >> fri->cur_log_cosets;  // entries per coset
+    // (the peers' copies were released by the barrier that preceded the first row hash of this proof)
+    peer_push(fri->cur, peers, (size_t)fri->coset_begin * per * 8, (size_t)fri->coset_count * per * 8, ctx->stream);
+    TRY(window_barrier(ctx));
+    TRY(window_check(ctx));
+    fri->cur_pending = false;
+    return AERO_OK;
+}
+
 aero_status aero_segment_leaves_device(aero_segment *seg, void **d_leaves, uint64_t *n_leaves, uint32_t *coset_begin,
                                        uint32_t *coset_count) {
     if (!seg || !d_leaves) return AERO_ERR_INVALID;
@@ -950,7 +1101,8 @@ aero_status aero_segment_leaves_device(aero_segment *seg, void **d_leaves, uint6
 aero_status aero_segment_finish_tree(aero_segment *seg, uint8_t root[32]) {
     if (!seg) return AERO_ERR_INVALID;
     if (!seg->full) CTX_FAIL(seg->ctx, AERO_ERR_STATE, "segment has no commitment");
-    return segment_finish_tree(seg, root);
+    TRY(segment_finish_tree(seg, root));
+    return window_check(seg->ctx);
 }
 
 void aero_segment_destroy(aero_segment *seg) {
@@ -1390,7 +1542,7 @@ aero_status aero_deep_compose(aero_ctx *ctx, aero_segment *const *trace_segs, ui
     aero_fri *fri = new aero_fri();
     fri->ctx = ctx;
     const uint64_t N = n << log_blowup;
-    aero_status st = dev_alloc(ctx, (void **)&fri->cur, N * 8);
+    aero_status st = dev_alloc_shared(ctx, (void **)&fri->cur, N * 8);
     if (st == AERO_OK) {
         const DftTables *plan;
         st = plan_lde(ctx, logn, log_blowup, false, &plan);

@@ -33,7 +33,7 @@ __device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t h[8]) 
 __global__ void __launch_bounds__(256) hash_rows_kernel(const uint64_t *__restrict__ lde, size_t col_stride, int c0,
                                                         int ncols, int total_cols, uint32_t nrows, int logn,
                                                         int log_blowup, uint32_t coset_begin,
-                                                        uint32_t *__restrict__ leaves) {
+                                                        uint32_t *__restrict__ leaves, PeerPtrs peers) {
     const uint32_t n_mask = (1u << logn) - 1;
     const int nblocks = (ncols + 1) >> 1;
     const uint32_t blocks_before = (uint32_t)c0 >> 1;
@@ -60,7 +60,57 @@ __global__ void __launch_bounds__(256) hash_rows_kernel(const uint64_t *__restri
             e1 = n1;
         }
         store_digest(leaves + (size_t)k * 8, h);
+        // fused all-gather: the finished digest also goes to the leaf array of every peer rank (the
+        // intermediate chaining value of a column range stays local)
+        if (tail)
+            for (int q = 0; q < peers.n; q++) store_digest(reinterpret_cast<uint32_t *>(peers.p[q]) + (size_t)k * 8, h);
     }
+}
+
+// ---- peer exchange helpers (multi-GPU) ----------------------------------------------------------
+__global__ void __launch_bounds__(256) peer_push_kernel(const uint4 *__restrict__ local, PeerPtrs peers, size_t first,
+                                                        size_t count) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = local[first + i];
+        for (int q = 0; q < peers.n; q++) reinterpret_cast<uint4 *>(peers.p[q])[first + i] = v;
+    }
+}
+void peer_push(const void *local, const PeerPtrs &peers, size_t off, size_t bytes, cudaStream_t s) {
+    if (peers.n == 0 || bytes == 0) return;
+    const size_t count = bytes / 16;
+    size_t blocks = (count + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    AERO_COUNT_LAUNCH(1);
+    peer_push_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const uint4 *>(local), peers, off / 16, count);
+}
+// Stream-ordered barrier between the ranks of a proof: thread q publishes `epoch` in peer q's flag
+// slot for this rank (after a system-scope fence, so every peer store of earlier kernels on this
+// stream is visible first), then waits for peer q's flag in the local window.  A peer that never
+// arrives (it failed) is given ~4 s; the time-out is reported through *d_timeout instead of hanging.
+__global__ void peer_barrier_kernel(volatile unsigned long long *my_flags, PeerPtrs peer_flags, int my_rank,
+                                    int r0, int r1, int r2, int r3, int r4, int r5, int r6, unsigned long long epoch,
+                                    unsigned int *d_timeout) {
+    const int q = threadIdx.x;
+    if (q >= peer_flags.n) return;
+    const int ranks[AERO_MAX_PEERS] = {r0, r1, r2, r3, r4, r5, r6};
+    __threadfence_system();
+    reinterpret_cast<volatile unsigned long long *>(peer_flags.p[q])[my_rank] = epoch;
+    __threadfence_system();
+    const long long t0 = clock64();
+    while (my_flags[ranks[q]] < epoch) {
+        if (clock64() - t0 > 8000000000LL) {
+            atomicAdd(d_timeout, 1u);
+            break;
+        }
+    }
+    __threadfence_system();
+}
+void peer_barrier(unsigned long long *my_flags, const PeerPtrs &peer_flags, int my_rank, int peer_ranks[AERO_MAX_PEERS],
+                  unsigned long long epoch, unsigned int *d_timeout, cudaStream_t s) {
+    if (peer_flags.n == 0) return;
+    AERO_COUNT_LAUNCH(1);
+    peer_barrier_kernel<<<1, 32, 0, s>>>(my_flags, peer_flags, my_rank, peer_ranks[0], peer_ranks[1], peer_ranks[2],
+                                         peer_ranks[3], peer_ranks[4], peer_ranks[5], peer_ranks[6], epoch, d_timeout);
 }
 
 // Generic variant: rows of a plain column-major matrix in natural order (used for small inputs /
@@ -146,7 +196,8 @@ void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s) {
 // Columns [c0, c0 + ncols) of a total_cols-wide row (see hash_rows_kernel); c0 must be even.
 // max_blocks > 0 caps the grid (the kernel strides over the rows).
 void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, int total_cols, int logn, int log_blowup,
-                   uint32_t coset_begin, uint32_t nrows, uint32_t *leaves, int max_blocks, cudaStream_t s) {
+                   uint32_t coset_begin, uint32_t nrows, uint32_t *leaves, const PeerPtrs &peers, int max_blocks,
+                   cudaStream_t s) {
     if (nrows == 0 || ncols == 0) return;
     uint32_t grid = (nrows + 255) / 256;
     if (max_blocks > 0 && grid > (uint32_t)max_blocks) grid = (uint32_t)max_blocks;
@@ -157,7 +208,7 @@ void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, in
     }
     AERO_COUNT_LAUNCH(1);
     hash_rows_kernel<<<grid, 256, 0, s>>>(lde, col_stride, c0, ncols, total_cols, nrows, logn, log_blowup, coset_begin,
-                                          leaves);
+                                          leaves, peers);
 }
 void hash_rows_natural(const uint64_t *m, size_t col_stride, int ncols, uint32_t nrows, uint32_t *leaves,
                        cudaStream_t s) {

@@ -45,9 +45,24 @@ __device__ __forceinline__ void fri_gather8(const uint64_t *__restrict__ f, uint
 }
 #endif
 
+// Peer copies of one buffer (multi-GPU): the same offset inside every other
+// rank's exchange window, mapped into this process with CUDA IPC.  Kernels store their results to
+// the local buffer and to each p[i] (NVLink peer stores), so the all-gather rides inside the kernel.
+constexpr int AERO_MAX_PEERS = 7;
+struct PeerPtrs {
+    void *p[AERO_MAX_PEERS];
+    int n = 0;
+};
+
 // hash.cu
 void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, int total_cols, int logn, int log_blowup,
-                   uint32_t coset_begin, uint32_t nrows, uint32_t *leaves, int max_blocks, cudaStream_t s);
+                   uint32_t coset_begin, uint32_t nrows, uint32_t *leaves, const PeerPtrs &peers, int max_blocks,
+                   cudaStream_t s);
+// copies [off, off + bytes) of the local buffer to the same range of every peer copy (16-byte units)
+void peer_push(const void *local, const PeerPtrs &peers, size_t off, size_t bytes, cudaStream_t s);
+// all ranks arrive (epoch) before any leaves: flags[r] of rank q's window is written by rank r
+void peer_barrier(unsigned long long *my_flags, const PeerPtrs &peer_flags, int my_rank, int peer_ranks[AERO_MAX_PEERS],
+                  unsigned long long epoch, unsigned int *d_timeout, cudaStream_t s);
 void hash_rows_natural(const uint64_t *m, size_t col_stride, int ncols, uint32_t nrows, uint32_t *leaves,
                        cudaStream_t s);
 void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s);

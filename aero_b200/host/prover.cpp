@@ -261,6 +261,11 @@ extern "C" int aero_ctx_get_form(aero_ctx *ctx);
 // Multi-GPU: complete a coset-sharded commitment (exchange leaf digests, then build the tree).
 static aero_status finish_commit(aero_ctx *ctx, const aero_prove_inputs &in, aero_segment *seg, uint32_t blowup,
                                  uint8_t root[32], std::string *err) {
+    if (aero_ctx_window_ranks(ctx) > 1) {  // digests went to the peers from inside the row-hash kernel
+        P_TRY(aero_window_barrier(ctx));
+        P_TRY(aero_segment_finish_tree(seg, root));
+        return AERO_OK;
+    }
     if (!in.all_gather_cosets) return AERO_OK;
     void *d = nullptr;
     uint64_t nl = 0;
@@ -298,7 +303,7 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     if (in.aux_width && !in.aux_builder && !in.aux_cols) P_FAIL(AERO_ERR_INVALID, "auxiliary segment columns are required");
     if (!in.constraint_evaluator && !in.ce_cols) P_FAIL(AERO_ERR_INVALID, "constraint evaluations are required");
     if (in.inputs_on_device && (in.aux_builder || in.constraint_evaluator)) P_FAIL(AERO_ERR_INVALID, "callbacks need host inputs");
-    if (in.all_gather_cosets && in.constraint_evaluator) P_FAIL(AERO_ERR_UNSUPPORTED, "sharded proofs take precomputed constraint evaluations");
+    if ((in.all_gather_cosets || aero_ctx_window_ranks(ctx) > 1) && in.constraint_evaluator) P_FAIL(AERO_ERR_UNSUPPORTED, "sharded proofs take precomputed constraint evaluations");
     const bool mont = aero_ctx_get_form(ctx) == AERO_FORM_MONTGOMERY;
     auto to_abi = [&](uint64_t x) { return mont ? gl::canon_to_mont(x) : x; };
     auto from_abi = [&](uint64_t x) { return mont ? gl::mont_to_canon(x) : gl::canon(x); };
@@ -419,7 +424,9 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     P_TRY(aero_deep_compose(ctx, trace_segs.data(), (uint32_t)trace_segs.size(), comp_seg, to_abi(z), ood_trace.data(),
                             ood_comp.data(), cc.data(), &H.fri));
 
-    if (in.all_gather_cosets) {
+    if (aero_ctx_window_ranks(ctx) > 1) {
+        P_TRY(aero_fri_push_evaluations(H.fri));
+    } else if (in.all_gather_cosets) {
         void *d = nullptr;
         uint64_t cnt = 0;
         uint32_t cb = 0, ccnt = 0;

@@ -221,7 +221,18 @@ class Context:
         inp.aux_rands = aux_rands if inp.aux_width else 0
         if shard is not None:  # aero_b200.sharded.ShardExchange: coset-sharded proof across ranks
             self._check(self.lib.aero_ctx_set_shard(self.h, shard.rank, shard.world))
-            inp.all_gather_cosets = shard._gather_cb
+            if getattr(shard, "window", False):
+                shard.attach_window(self)  # NVLink peer stores inside the kernels replace the all-gather
+                # the first proof of a shape allocates (cudaMalloc may block on a peer that is already
+                # waiting in the window's flag barrier): it takes the host-synchronised NCCL route
+                key = (inp.trace_len, inp.main_width, inp.aux_width, len(divisors), bool(on_device))
+                warm = key in shard.warm_shapes
+                shard.warm_shapes.add(key)
+                self.set_option("use_window", int(warm))
+                if not warm:
+                    inp.all_gather_cosets = shard._gather_cb
+            else:
+                inp.all_gather_cosets = shard._gather_cb
             inp.sum_rows = shard._sum_cb
         else:
             self._check(self.lib.aero_ctx_set_shard(self.h, 0, 1))

@@ -52,15 +52,40 @@ class _DevBuf:
 class ShardExchange:
     """Builds the C callbacks (aero_all_gather_cosets / aero_sum_rows) for Context.prove."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, window_bytes: int = 0):
+        """window_bytes > 0: exchange over an IPC-mapped peer window (digests and DEEP evaluations are
+        stored into the peers' memory by the producing kernels, a flag barrier replaces the NCCL
+        all-gather); torch.distributed then only carries the 64-byte IPC handles once and the 27 opened
+        rows per segment.  0: NCCL all-gather through the aero_all_gather_cosets hook."""
         import torch
         import torch.distributed as dist
 
         self.torch, self.dist, self.group = torch, dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.bytes_exchanged = 0
+        self.window, self.window_bytes, self._attached = window_bytes > 0, int(window_bytes), None
+        self.warm_shapes = set()
         self._gather_cb = _lib.ALL_GATHER_COSETS(self._gather)
         self._sum_cb = _lib.SUM_ROWS(self._sum_rows)
+
+    def attach_window(self, ctx) -> None:
+        """Creates this rank's window on ``ctx``, all-gathers the IPC handles and maps the peers."""
+        if self._attached is ctx:
+            return
+        if self._attached is not None:
+            raise RuntimeError("a ShardExchange window serves one context")
+        torch, dist = self.torch, self.dist
+        ctx._check(ctx.lib.aero_ctx_set_shard(ctx.h, self.rank, self.world))
+        handle = (ctypes.c_uint8 * 64)()
+        ctx._check(ctx.lib.aero_ctx_window_create(ctx.h, self.window_bytes, handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda" if dist.get_backend(self.group) == "nccl" else "cpu")
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        flat = bytes(torch.cat(parts).cpu().tolist())
+        buf = (ctypes.c_uint8 * len(flat)).from_buffer_copy(flat)
+        ctx._check(ctx.lib.aero_ctx_window_attach(ctx.h, self.world, buf))
+        dist.barrier(group=self.group)
+        self._attached = ctx
 
     def _gather(self, user, d_buf, outer, n_cosets, inner_bytes, interleaved, coset_begin, coset_count):
         try:

@@ -176,8 +176,7 @@ def workload_config(args, log_rows: int) -> dict:
                         % log_rows,
             "log_rows": log_rows, "main_width": MAIN_W, "aux_width": AUX_W, "constraint_columns": CE_COLS,
             "blowup": BLOWUP, "parallelism": ("single GPU" if args.gpus == 1 else
-                                             "one proof sharded by LDE coset across %d GPUs (NCCL all-gather of leaf digests "
-                                             "and DEEP evaluations)" % args.gpus if getattr(args, "shard_proof", False) else
+                                             ("one proof sharded by LDE coset across %d GPUs (%s)" % (args.gpus, "NCCL all-gather of leaf digests and DEEP evaluations" if getattr(args, "nccl_exchange", False) else "leaf digests and DEEP evaluations stored into the peers' memory over NVLink by the producing kernels, flag barrier")) if getattr(args, "shard_proof", False) else
                                              "one independent proof per GPU (no data-path collective)"), "l2": "inputs (0.7 GB) and LDE (5.4 GB) exceed the 126 MB L2"}
 
 
@@ -236,7 +235,8 @@ def run_aero(args) -> None:
     shard = None
     if args.shard_proof and world > 1:
         from aero_b200.sharded import ShardExchange
-        shard = ShardExchange()
+        # window: three 64*N-byte trees + the 8*N-byte DEEP evaluations (+ slack)
+        shard = ShardExchange(window_bytes=0 if args.nccl_exchange else (3 * 64 + 8) * N + (1 << 20))
 
     def step_device():
         return ctx.prove(None, None, None, divs, PUB, on_device=on_device, shard=shard)
@@ -353,6 +353,9 @@ def main() -> None:
     ap.add_argument("--shard-proof", action="store_true",
                     help="N>1: shard ONE proof across the ranks by LDE coset (strong scaling) instead of one "
                          "independent proof per rank")
+    ap.add_argument("--nccl-exchange", action="store_true",
+                    help="--shard-proof: exchange leaf digests / DEEP evaluations with NCCL all-gathers instead of "
+                         "NVLink peer stores from inside the kernels")
     ap.add_argument("--overlap-hash", type=int, default=0,
                     help="1: row hashing of column batch k runs on a second stream beside the LDE of batch k+1")
     ap.add_argument("--hash-blocks-per-sm", type=int, default=0)

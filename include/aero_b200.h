@@ -72,7 +72,12 @@ int aero_ctx_get_form(aero_ctx *ctx);
  *                     evaluate_columns_over, :189) -- 0 serialises everything on the context's stream
  *                     (faster on B200);
  *   "hash_blocks_per_sm" grid cap (blocks per SM) of an overlapped row-hash launch (default 2);
- *   "lde_batch_bytes" NTT scratch budget per column batch (default 1 GiB). */
+ *   "lde_batch_bytes" NTT scratch budget per column batch (default 1 GiB);
+ *   "use_window"      1 (default once attached) / 0: route the multi-GPU exchanges through the peer
+ *                     window or through the aero_all_gather_cosets hook.  The first proof of a shape
+ *                     on a context must take the hook: it still calls cudaMalloc, which can block on
+ *                     a peer GPU whose stream sits in the window's flag barrier (the caveat NCCL
+ *                     documents for its own kernels); later proofs reuse the cached blocks. */
 aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value);
 /* Used by the host driver layered above this ABI to report its own failures through aero_last_error. */
 void aero_ctx_set_error(aero_ctx *ctx, const char *msg);
@@ -106,6 +111,20 @@ aero_status aero_segment_commit_device(aero_ctx *ctx, const uint64_t *d_cols, si
  * [coset_begin:coset_begin+coset_count, :]); exchange, then aero_fri_mark_complete.
  * aero_segment_open returns zeros for rows owned by other ranks (sum the ranks' results). */
 aero_status aero_ctx_set_shard(aero_ctx *ctx, int rank, int world);
+/* Exchange window: the NVLink path of the two exchanges.  Every rank creates a
+ * window of the same size (device memory, exported as a 64-byte CUDA IPC handle), the caller
+ * all-gathers the handles (any transport) and attaches them in rank order.  From then on the leaf
+ * array of a sharded segment and the DEEP evaluations are allocated inside the window at the same
+ * offset on every rank; the row-hash kernel stores each digest into all peer windows as it is
+ * produced (aero_fri_push_evaluations does the same for the DEEP evaluations), and
+ * aero_window_barrier -- a stream-ordered flag barrier over the same peer mapping -- replaces the
+ * all-gather: call it before aero_segment_finish_tree.  Size: 64*N bytes per committed segment of the
+ * proof + 8*N for the DEEP evaluations + 4 KiB (N = LDE domain size). */
+aero_status aero_ctx_window_create(aero_ctx *ctx, size_t bytes, uint8_t ipc_handle_out[64]);
+aero_status aero_ctx_window_attach(aero_ctx *ctx, int n_ranks, const uint8_t *ipc_handles /* n_ranks x 64 */);
+int aero_ctx_window_ranks(aero_ctx *ctx);
+aero_status aero_window_barrier(aero_ctx *ctx);
+aero_status aero_fri_push_evaluations(aero_fri *fri);
 aero_status aero_segment_leaves_device(aero_segment *seg, void **d_leaves, uint64_t *n_leaves, uint32_t *coset_begin,
                                        uint32_t *coset_count);
 aero_status aero_segment_finish_tree(aero_segment *seg, uint8_t root[32]);
