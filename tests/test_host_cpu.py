@@ -102,3 +102,17 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "trace_rows_per_s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_rust_shim_bindings_match_the_headers():
+    """rust/aero-gpu-prover/src/ffi.rs is generated from include/*.h; it must be current and bind every
+    symbol the shared object exports through those headers (the crate itself cannot be compiled here)."""
+    import subprocess
+    import sys
+    from aero_b200 import _lib
+
+    gen = os.path.join(ROOT, "tools", "gen_rust_ffi.py")
+    assert subprocess.run([sys.executable, gen, "--check"]).returncode == 0, "run tools/gen_rust_ffi.py"
+    ffi = open(os.path.join(ROOT, "rust", "aero-gpu-prover", "src", "ffi.rs")).read()
+    for name in _lib.PROTOTYPES:
+        assert "pub fn %s(" % name in ffi, "%s is not bound in ffi.rs" % name
