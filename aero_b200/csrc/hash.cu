@@ -135,17 +135,18 @@ __global__ void __launch_bounds__(256) hash_rows_natural_kernel(const uint64_t *
 
 // Merkle tree over `full` = 2*N digests: full[N + k] = leaf k, full[i] = merge(full[2i], full[2i+1])
 // for 1 <= i < N (heap layout of merkle/mod.rs:316-340; full[1] is the root, full[0] unused/zero).
-// Block b builds the height-`levels` subtree whose top node is (top_lo + b): 2^(levels-1) nodes
-// from global children, then up through shared memory; every level is also written to `full`.
-constexpr int MERKLE_MAX_LEVELS = 9;
-__global__ void __launch_bounds__(256) merkle_subtree_kernel(uint32_t *__restrict__ full, uint32_t top_lo, int levels) {
+// A block takes `width` consecutive nodes of the node level that starts at heap index `level_size`
+// (children from global memory) and climbs `levels` levels through shared memory; every level is
+// written to `full`.  Wide levels climb only MERKLE_LEVELS_PER_LAUNCH levels per launch so that
+// every warp stays full (256, 128, 64, 32 nodes); the last launch (<= 256 nodes) runs to the root.
+constexpr int MERKLE_LEVELS_PER_LAUNCH = 4;
+__global__ void __launch_bounds__(256) merkle_subtree_kernel(uint32_t *__restrict__ full, uint32_t level_size, int width,
+                                                             int levels) {
     __shared__ uint32_t sbuf[2][256 * 8];
-    const uint32_t top = top_lo + blockIdx.x;
-    int width = 1 << (levels - 1);  // nodes at the current level inside this subtree
     int cur = 0;
     // bottom level: children from global memory
     {
-        const uint32_t first = top << (levels - 1);
+        const uint32_t first = level_size + blockIdx.x * width;
         for (int t = threadIdx.x; t < width; t += blockDim.x) {
             const uint32_t node = first + t;
             uint32_t a[8], b[8], o[8];
@@ -157,10 +158,10 @@ __global__ void __launch_bounds__(256) merkle_subtree_kernel(uint32_t *__restric
             for (int i = 0; i < 8; i++) sbuf[cur][t * 8 + i] = o[i];
         }
     }
-    for (int l = levels - 2; l >= 0; l--) {
+    for (int l = 1; l < levels; l++) {
         __syncthreads();
         width >>= 1;
-        const uint32_t first = top << l;
+        const uint32_t first = (level_size >> l) + blockIdx.x * width;
         for (int t = threadIdx.x; t < width; t += blockDim.x) {
             uint32_t a[8], b[8], o[8];
 #pragma unroll
@@ -178,17 +179,20 @@ __global__ void __launch_bounds__(256) merkle_subtree_kernel(uint32_t *__restric
 }
 
 void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s) {
-    // node levels have sizes num_leaves/2, ..., 1 ; level of size L occupies indices [L, 2L)
+    // node levels have sizes num_leaves/2, ..., 1 ; the level of size L occupies heap indices [L, 2L)
     uint64_t level = num_leaves / 2;  // size of the lowest node level still to compute
     while (level >= 1) {
-        int remaining = 0;
-        for (uint64_t l = level; l >= 1; l >>= 1) remaining++;
-        const int levels = remaining < MERKLE_MAX_LEVELS ? remaining : MERKLE_MAX_LEVELS;
-        const uint32_t top_lo = (uint32_t)(level >> (levels - 1));
         AERO_COUNT_LAUNCH(1);
-        merkle_subtree_kernel<<<top_lo, 256, 0, s>>>(full, top_lo, levels);
-        if (top_lo == 1) break;
-        level = top_lo >> 1;
+        if (level > 256) {
+            merkle_subtree_kernel<<<(unsigned)(level / 256), 256, 0, s>>>(full, (uint32_t)level, 256,
+                                                                        MERKLE_LEVELS_PER_LAUNCH);
+            level >>= MERKLE_LEVELS_PER_LAUNCH;
+        } else {
+            int levels = 0;
+            for (uint64_t l = level; l >= 1; l >>= 1) levels++;
+            merkle_subtree_kernel<<<1, 256, 0, s>>>(full, (uint32_t)level, (int)level, levels);
+            break;
+        }
     }
 }
 
