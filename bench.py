@@ -38,8 +38,10 @@ MAIN_W, AUX_W, CE_COLS, BLOWUP = 72, 9, 2, 8
 ALU_OPS_PER_COMPRESSION = 661
 ALU_PEAK_LANE_OPS = 18.4e12
 # dram__bytes_read.sum + dram__bytes_write.sum of one hash_rows_kernel launch (w=72, N=2^23) from the
-# ncu --set full capture in profiles/ (4.83 GB + 0.27 GB): equals the algorithmic bytes, no re-reads.
-HASH_W72_NCU_DRAM_BYTES = 5.1035e9
+# ncu --set full capture profiles/r01_ncu_v4_hash_merkle.txt: 4.834 GB read (= the algorithmic 8wN, no
+# re-reads) + 0.795 GB written (0.268 GB of digests; a thread's 32-byte digest lands at a 256-byte
+# stride because rows of one LDE coset are 8 apart, so half-empty 64-byte DRAM atoms are written).
+HASH_W72_NCU_DRAM_BYTES = 5.6295e9
 PUB = b"aero-b200 bench public inputs"
 
 
