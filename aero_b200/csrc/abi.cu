@@ -79,6 +79,7 @@ struct aero_ctx {
     std::map<std::string, PowTableOwned> pow_tables;
     std::vector<void *> owned;  // device allocations freed with the context
     size_t lde_batch_bytes = (size_t)1 << 30;  // NTT scratch budget per column batch
+    size_t ntt_table_max_bytes = (size_t)1 << 30;  // largest full inter-pass twiddle table a plan may hold
     int shard_rank = 0, shard_world = 1;       // LDE coset shard of this context (multi-GPU)
     std::multimap<size_t, void *> free_blocks;  // exact-size cache of released device blocks
     std::map<void *, size_t> live_blocks;
@@ -260,19 +261,31 @@ static inline uint64_t from_canon(const aero_ctx *ctx, uint64_t x) {
 // -------------------------------------------------------------------------------------------------
 // transform plans
 // -------------------------------------------------------------------------------------------------
-// stage table for an M-point DIT evaluating on the coset sigma*<w_M>: tw[m/2 + k] = sigma^(M/m) w_m^k
+// stage table for an M-point mixed-radix DIT evaluating on the coset sigma*<w_M> (layout: ntt.cuh).
+// For the round that merges 2^R sub-transforms of size 2^s0 into size m = 2^(s0+R), sub-transform e
+// (a bit-reversed residue rho = bitrev_R(e)) at offset low is multiplied by (sigma^(M/m) w_m^low)^rho.
 static void fill_stage_table(uint64_t *tw, int logM, uint64_t sigma, uint64_t wM) {
     const uint64_t M = 1ULL << logM;
     tw[0] = 0;
-    for (int s = 0; s < logM; s++) {
-        const uint64_t m = 2ULL << s;              // sub-transform size
+    const NttRounds rounds(logM);
+    int s0 = 0;
+    for (int i = 0; i < rounds.count; i++) {
+        const int R = rounds.log(i);
+        const uint64_t m = 1ULL << (s0 + R);
         const uint64_t sg = gl::pow(sigma, M / m);  // sigma^(M/m)
         const uint64_t wm = gl::pow(wM, M / m);     // primitive m-th root
-        uint64_t x = sg;
-        for (uint64_t k = 0; k < m / 2; k++) {
-            tw[m / 2 + k] = x;
+        uint64_t x = sg;                            // sigma_m * w_m^low
+        for (uint64_t low = 0; low < (1ULL << s0); low++) {
+            uint64_t pw = x;                        // x^rho
+            for (uint32_t rho = 1; rho < (1u << R); rho++) {
+                uint32_t e = 0;
+                for (int b = 0; b < R; b++) e |= ((rho >> b) & 1u) << (R - 1 - b);
+                tw[((uint64_t)e << s0) + low] = pw;
+                pw = gl::mul(pw, x);
+            }
             x = gl::mul(x, wm);
         }
+        s0 += R;
     }
 }
 static void fill_pow_table(std::vector<uint64_t> &lo, std::vector<uint64_t> &hi, uint64_t base, int total_bits,
@@ -307,6 +320,7 @@ static aero_status get_plan(aero_ctx *ctx, const std::string &key, int logn, boo
     t.logn = logn;
     t.ncosets = (int)shifts.size();
     t.plain = true;
+    t.inverse = inverse;
     for (uint64_t sh : shifts) t.plain = t.plain && sh == 1;
     const uint64_t n = 1ULL << logn;
     uint64_t w = gl::root_of_unity(logn);
@@ -350,6 +364,16 @@ static aero_status get_plan(aero_ctx *ctx, const std::string &key, int logn, boo
         fill_pow_table(lo, hi, w, logn, t.lo_bits, 1);
         TRY(upload_vec(ctx, &t.wlo, lo));
         TRY(upload_vec(ctx, &t.whi, hi));
+        // full inter-pass table (one multiplication per element instead of two) while it stays small
+        // against the transform's own data: [ncosets][n] entries
+        if ((size_t)t.ncosets * n * 8 <= ctx->ntt_table_max_bytes) {
+            void *p = nullptr;
+            CUDA_TRY(ctx, cudaMalloc(&p, (size_t)t.ncosets * n * 8));
+            ctx->owned.push_back(p);
+            dft_fill_inter_table(t, (uint64_t *)p, ctx->stream);
+            CUDA_TRY(ctx, cudaGetLastError());
+            t.inter_full = (uint64_t *)p;
+        }
         if (post_base) {
             std::vector<uint64_t> pu(n1), pv(n2);
             uint64_t x = 1;
@@ -813,6 +837,7 @@ aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value)
     else if (k == "force_split_intt") ctx->force_split_intt = value != 0;
     else if (k == "hash_blocks_per_sm" && value > 0) ctx->hash_blocks_per_sm = (int)value;
     else if (k == "lde_batch_bytes" && value > 0) ctx->lde_batch_bytes = (size_t)value;
+    else if (k == "ntt_table_max_bytes" && value >= 0) ctx->ntt_table_max_bytes = (size_t)value;
     else CTX_FAIL(ctx, AERO_ERR_INVALID, "unknown option '%s'", key);
     return AERO_OK;
 }
@@ -880,11 +905,11 @@ aero_status aero_test_field_ops(aero_ctx *ctx, const uint64_t *a, const uint64_t
     uint64_t *da = nullptr, *db = nullptr, *dout = nullptr;
     TRY(dev_alloc(ctx, (void **)&da, n * 8));
     TRY(dev_alloc(ctx, (void **)&db, n * 8));
-    TRY(dev_alloc(ctx, (void **)&dout, 4 * n * 8));
+    TRY(dev_alloc(ctx, (void **)&dout, 12 * n * 8));
     CUDA_TRY(ctx, cudaMemcpyAsync(da, a, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(db, b, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     field_ops(da, db, n, dout, ctx->stream);
-    CUDA_TRY(ctx, cudaMemcpyAsync(out, dout, 4 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, dout, 12 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     dev_free(ctx, da);
     dev_free(ctx, db);

@@ -152,6 +152,97 @@ __device__ __forceinline__ uint64_t sub_ac(uint64_t u, uint64_t v) {
         : "r"(u0), "r"(u1), "r"(v0), "r"(v1));
     return ((uint64_t)y1 << 32) | y0;
 }
+// u any, v canonical -> canonical.  Like add_ac, but the +EPS fix-up and the final reduction merge
+// (the same select as in mul_canon): r = u + v (carry c), s = r + EPS (carry c2); c | c2 ? s : r.
+__device__ __forceinline__ uint64_t add_cc(uint64_t u, uint64_t v) {
+    uint32_t u0 = (uint32_t)u, u1 = (uint32_t)(u >> 32), v0 = (uint32_t)v, v1 = (uint32_t)(v >> 32), y0, y1;
+    asm("{\n\t"
+        ".reg .u32 c, s0, s1;\n\t"
+        ".reg .pred q;\n\t"
+        "add.cc.u32 %0, %2, %4;\n\t"
+        "addc.cc.u32 %1, %3, %5;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "add.cc.u32 s0, %0, 0xffffffff;\n\t"
+        "addc.cc.u32 s1, %1, 0;\n\t"
+        "addc.u32 c, c, 0;\n\t"
+        "setp.ne.u32 q, c, 0;\n\t"
+        "selp.u32 %0, s0, %0, q;\n\t"
+        "selp.u32 %1, s1, %1, q;\n\t"
+        "}"
+        : "=&r"(y0), "=&r"(y1)
+        : "r"(u0), "r"(u1), "r"(v0), "r"(v1));
+    return ((uint64_t)y1 << 32) | y0;
+}
+
+// x any -> x * 2^S canonical, for a compile-time 0 < S < 96 that is not a multiple of 32.
+// 2 generates the 192 = 3*64 element subgroup of the field (2^96 = -1), so every 64th root of unity
+// is a power of two (w_64 = 2^39 for the reference's TWO_ADIC_ROOT): the twiddles INSIDE a radix-4 /
+// 8 / 16 butterfly are shifts, which cost three funnel shifts and a short carry chain instead of the
+// four IMAD.WIDE of a general product.  With t = 2^32 (t^2 = t - 1, t^3 = -1 mod p), S = 32a + b and
+// {y2:y1:y0} = x << b (y2 < 2^b):
+//   a = 0:  {y1:y0} + y2*EPS                       (the tail of mul_canon)
+//   a = 1:  y0*t + y1*(t-1) - y2 = ({y0:0} - y2) - (p - y1*EPS)     (two canonical subtractions)
+//   a = 2:  y0*(t-1) - y1 - y2*t = y0*EPS - {y2:y1}                 (one canonical subtraction)
+template <int S>
+__device__ __forceinline__ uint64_t mul_pow2(uint64_t x) {
+    static_assert(S > 0 && S < 96 && S % 32 != 0, "shift must be in (0,96) and not a multiple of 32");
+    constexpr int a = S / 32, b = S % 32;
+    const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32);
+    const uint32_t y0 = x0 << b, y1 = __funnelshift_l(x0, x1, b), y2 = x1 >> (32 - b);
+    uint32_t r0, r1;
+    if (a == 0) {
+        asm("{\n\t"
+            ".reg .u32 c, t0, t1, s0, s1;\n\t"
+            ".reg .pred q;\n\t"
+            "mul.lo.u32 t0, %4, 0xffffffff;\n\t"
+            "mul.hi.u32 t1, %4, 0xffffffff;\n\t"
+            "add.cc.u32 %0, %2, t0;\n\t"
+            "addc.cc.u32 %1, %3, t1;\n\t"
+            "addc.u32 c, 0, 0;\n\t"
+            "add.cc.u32 s0, %0, 0xffffffff;\n\t"
+            "addc.cc.u32 s1, %1, 0;\n\t"
+            "addc.u32 c, c, 0;\n\t"
+            "setp.ne.u32 q, c, 0;\n\t"
+            "selp.u32 %0, s0, %0, q;\n\t"
+            "selp.u32 %1, s1, %1, q;\n\t"
+            "}"
+            : "=&r"(r0), "=&r"(r1)
+            : "r"(y0), "r"(y1), "r"(y2));
+    } else if (a == 1) {
+        asm("{\n\t"
+            ".reg .u32 m, w0, w1, n0, n1, ny;\n\t"
+            "sub.cc.u32 w0, 0, %4;\n\t"       // W = {y0:0} - y2  (+p on borrow)
+            "subc.cc.u32 w1, %2, 0;\n\t"
+            "subc.u32 m, 0, 0;\n\t"
+            "sub.cc.u32 w0, w0, m;\n\t"
+            "subc.u32 w1, w1, 0;\n\t"
+            "not.b32 ny, %3;\n\t"             // N = p - y1*EPS = {~y1 : y1 + 1}  (<= p)
+            "add.cc.u32 n0, %3, 1;\n\t"
+            "addc.u32 n1, ny, 0;\n\t"
+            "sub.cc.u32 %0, w0, n0;\n\t"      // W - N  (+p on borrow)
+            "subc.cc.u32 %1, w1, n1;\n\t"
+            "subc.u32 m, 0, 0;\n\t"
+            "sub.cc.u32 %0, %0, m;\n\t"
+            "subc.u32 %1, %1, 0;\n\t"
+            "}"
+            : "=&r"(r0), "=&r"(r1)
+            : "r"(y0), "r"(y1), "r"(y2));
+    } else {
+        asm("{\n\t"
+            ".reg .u32 m, t0, t1;\n\t"
+            "mul.lo.u32 t0, %2, 0xffffffff;\n\t"  // y0*EPS <= (2^32-1)^2 < p
+            "mul.hi.u32 t1, %2, 0xffffffff;\n\t"
+            "sub.cc.u32 %0, t0, %3;\n\t"
+            "subc.cc.u32 %1, t1, %4;\n\t"
+            "subc.u32 m, 0, 0;\n\t"
+            "sub.cc.u32 %0, %0, m;\n\t"
+            "subc.u32 %1, %1, 0;\n\t"
+            "}"
+            : "=&r"(r0), "=&r"(r1)
+            : "r"(y0), "r"(y1), "r"(y2));
+    }
+    return ((uint64_t)r1 << 32) | r0;
+}
 #endif
 
 GL_HD uint64_t add(uint64_t a, uint64_t b) {  // a, b canonical -> canonical  (f64/mod.rs:273)

@@ -1,5 +1,7 @@
 // Goldilocks NTT kernels for sm_100a: shared-memory DIT transforms with register radix-8 rounds,
 // four-step two-pass decomposition for n > 2^11.  See ntt.cuh for the mapping to the reference.
+#include <type_traits>
+
 #include "gl.cuh"
 #include "ntt.cuh"
 #include "kernels.cuh"
@@ -8,12 +10,38 @@ namespace aero {
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t x, int bits) { return __brev(x) >> (32 - bits); }
 
-// One register-blocked round of R DIT stages (s0 .. s0+R-1) over an M x T tile in shared memory.
-// a[idx*RS + t]; tw[2^s + k] is the stage-s twiddle for pair offset k (k < 2^s).
-// PLAIN0: this is the first round (s0 == 0) of a transform without coset shift, where the
-// twiddle of pair offset k == 0 is 1 -- known at compile time, so 7 of the 12 multiplications of a
-// radix-8 round disappear.
-template <int R, int T, int RS, bool PLAIN0>
+// ---- compile-time structure of a 2^R-point round ------------------------------------------------
+template <int N, class F, int I = 0>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<N, F, I + 1>(static_cast<F &&>(f));
+    }
+}
+// w_{2^j} = 2^dft_unit_exp(j): TWO_ADIC_ROOT^(2^(32-j)) is 2^(39 * 2^(6-j)) for j <= 6 (2^192 = 1)
+__host__ __device__ constexpr int dft_unit_exp(int j, bool inv) {
+    const int u = (39 << (6 - j)) % 192;
+    return inv ? (192 - u) % 192 : u;
+}
+// twiddle w_{2^(q+1)}^k of inner stage q as an exponent of two in [0, 192)
+__host__ __device__ constexpr int dft_tw_exp(int q, int k, bool inv) { return (dft_unit_exp(q + 1, inv) * k) % 192; }
+// Must x[e] be canonical when it enters inner stage q?  Yes where a unit twiddle hands it to a
+// butterfly as v unchanged, and for the u of a butterfly one of whose outputs must be canonical
+// (add_cc / sub_ac give canonical sums only from canonical u).
+__host__ __device__ constexpr bool dft_need_canon(int R, int q, int e) {
+    if (q >= R) return false;
+    const int bit = 1 << q;
+    if (e & bit) return (e & (bit - 1)) == 0;
+    return dft_need_canon(R, q + 1, e) || dft_need_canon(R, q + 1, e | bit);
+}
+
+// One register-resident round of a mixed-radix DIT over an M x T tile in shared memory
+// (a[idx*RS + t]): the 2^R sub-transforms of size 2^s0 that merge into one of size m = 2^(s0+R).
+// Input e (a bit-reversed residue) is first multiplied by the general twiddle
+// tw[(e << s0) + low] = (sigma_m w_m^low)^bitrev(e); what remains is a plain 2^R-point DFT whose
+// twiddles are powers of two (gl::mul_pow2), negated where the exponent is >= 96.
+// PLAIN0: first round (s0 == 0) of a transform without coset shift: all general twiddles are 1.
+template <int R, int T, int RS, bool PLAIN0, bool INV>
 __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s0, int logM) {
     if (PLAIN0) s0 = 0;
     const int ngroups = (1 << logM) >> R;
@@ -23,61 +51,69 @@ __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s
         const int low = g & ((1 << s0) - 1);
         const int base = ((g >> s0) << (s0 + R)) | low;
         uint64_t x[1 << R];
-#pragma unroll
-        for (int e = 0; e < (1 << R); e++) x[e] = a[(base + (e << s0)) * RS + t];
-#pragma unroll
-        for (int q = 0; q < R; q++) {
-#pragma unroll
-            for (int e = 0; e < (1 << R); e++) {
-                if (e & (1 << q)) continue;
-                const int k = low + ((e & ((1 << q) - 1)) << s0);
-                // values in the tile stay "any" (congruent mod p, < 2^64); only v is canonicalised
-                const uint64_t u = x[e];
-                uint64_t v;
-                if (PLAIN0 && (e & ((1 << q) - 1)) == 0) {
-                    v = gl::canon_any(x[e | (1 << q)]);
-                } else {
-                    v = gl::mul_canon(x[e | (1 << q)], tw[(1 << (s0 + q)) + k]);
+        // tile values are "any" (congruent mod p, < 2^64); products are canonical
+        static_for<(1 << R)>([&](auto E) {
+            constexpr int e = decltype(E)::value;
+            uint64_t v = a[(base + (e << s0)) * RS + t];
+            if constexpr (e > 0 && !PLAIN0) v = gl::mul_canon(v, tw[(e << s0) + low]);
+            else if constexpr (dft_need_canon(R, 0, e)) v = gl::canon_any(v);
+            x[e] = v;
+        });
+        static_for<R>([&](auto Q) {
+            constexpr int q = decltype(Q)::value;
+            static_for<(1 << R)>([&](auto E) {
+                constexpr int e = decltype(E)::value;
+                if constexpr ((e & (1 << q)) == 0) {
+                    constexpr int f = e | (1 << q);
+                    constexpr int ex = dft_tw_exp(q, e & ((1 << q) - 1), INV);
+                    constexpr bool canon_sum = dft_need_canon(R, q + 1, e);
+                    const uint64_t u = x[e];
+                    if constexpr (ex == 0) {
+                        const uint64_t v = x[f];
+                        x[e] = canon_sum ? gl::add_cc(u, v) : gl::add_ac(u, v);
+                        x[f] = gl::sub_ac(u, v);
+                    } else if constexpr (ex < 96) {
+                        const uint64_t v = gl::mul_pow2<ex>(x[f]);
+                        x[e] = canon_sum ? gl::add_cc(u, v) : gl::add_ac(u, v);
+                        x[f] = gl::sub_ac(u, v);
+                    } else {
+                        const uint64_t v = gl::mul_pow2<ex - 96>(x[f]);  // twiddle = -2^(ex-96)
+                        static_assert(!canon_sum, "only unit-twiddle butterflies feed canonical sums");
+                        x[e] = gl::sub_ac(u, v);
+                        x[f] = gl::add_ac(u, v);
+                    }
                 }
-                x[e] = gl::add_ac(u, v);
-                x[e | (1 << q)] = gl::sub_ac(u, v);
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < (1 << R); e++) a[(base + (e << s0)) * RS + t] = x[e];
+            });
+        });
+        static_for<(1 << R)>([&](auto E) {
+            constexpr int e = decltype(E)::value;
+            a[(base + (e << s0)) * RS + t] = x[e];
+        });
+    }
+}
+
+template <int T, int RS, bool PLAIN0, bool INV>
+__device__ __forceinline__ void dit_round_dispatch(int R, uint64_t *a, const uint64_t *tw, int s0, int logM) {
+    switch (R) {
+    case 4: dit_round<4, T, RS, PLAIN0, INV>(a, tw, s0, logM); break;
+    case 3: dit_round<3, T, RS, PLAIN0, INV>(a, tw, s0, logM); break;
+    case 2: dit_round<2, T, RS, PLAIN0, INV>(a, tw, s0, logM); break;
+    default: dit_round<1, T, RS, PLAIN0, INV>(a, tw, s0, logM); break;
     }
 }
 
 // Full M-point DIT over the tile: input in bit-reversed row order, output in natural row order.
-template <int T, int RS, bool PLAIN>
+template <int T, int RS, bool PLAIN, bool INV>
 __device__ __forceinline__ void dit_tile(uint64_t *a, const uint64_t *tw, int logM) {
-    int s0 = 0;
-    // first round: s0 == 0 is a compile-time fact, which lets PLAIN transforms drop unit twiddles
-    if (logM >= 3 && logM != 4) {
-        dit_round<3, T, RS, PLAIN>(a, tw, 0, logM);
-        s0 = 3;
-    } else if (logM >= 2) {
-        dit_round<2, T, RS, PLAIN>(a, tw, 0, logM);
-        s0 = 2;
-    } else {
-        dit_round<1, T, RS, PLAIN>(a, tw, 0, logM);
-        s0 = 1;
-    }
+    const NttRounds rounds(logM);
+    // first round: s0 == 0 is a compile-time fact, which lets PLAIN transforms skip the unit twiddles
+    dit_round_dispatch<T, RS, PLAIN, INV>(rounds.log(0), a, tw, 0, logM);
     __syncthreads();
-    while (s0 < logM) {
-        const int left = logM - s0;
-        // prefer 3-stage rounds; avoid a trailing 1-stage round when 4 stages remain (2+2).  A 16-point
-        // register round for 4 remaining stages was measured slower (64 registers, LDE 14.1 -> 14.3 ms)
-        if (left >= 3 && left != 4) {
-            dit_round<3, T, RS, false>(a, tw, s0, logM);
-            s0 += 3;
-        } else if (left >= 2) {
-            dit_round<2, T, RS, false>(a, tw, s0, logM);
-            s0 += 2;
-        } else {
-            dit_round<1, T, RS, false>(a, tw, s0, logM);
-            s0 += 1;
-        }
+    int s0 = rounds.log(0);
+    for (int i = 1; i < rounds.count; i++) {
+        const int R = rounds.log(i);
+        dit_round_dispatch<T, RS, false, INV>(R, a, tw, s0, logM);
+        s0 += R;
         __syncthreads();
     }
 }
@@ -94,10 +130,14 @@ __device__ __forceinline__ size_t out_index(uint32_t i, int logn, int deint) {
 
 // ---- pass 1 -------------------------------------------------------------------------------
 // grid: (n2/T, ncosets, ncols).  tmp layout per (col, coset): [i1/T][j2][i1%T].
-template <int T, bool PLAIN>
+// TAB: the inter-pass factor F(i1, j2) = c s^j2 w_n^(i1 j2) comes from a full table in that same tile
+// order (read through L2); otherwise it is advanced by a running product per thread, which costs a
+// second multiplication per element.
+template <int T, bool PLAIN, bool INV, bool TAB>
 __global__ void __launch_bounds__(1024) dft_pass1_kernel(const uint64_t *__restrict__ src, uint64_t *__restrict__ tmp,
                                                         const uint64_t *__restrict__ stage1,
                                                         const uint64_t *__restrict__ inter_b,
+                                                        const uint64_t *__restrict__ inter_full,
                                                         const uint64_t *__restrict__ wlo,
                                                         const uint64_t *__restrict__ whi, int lo_bits, int log1,
                                                         int log2, size_t src_col_stride, int ncosets) {
@@ -110,14 +150,25 @@ __global__ void __launch_bounds__(1024) dft_pass1_kernel(const uint64_t *__restr
     const int coset = blockIdx.y, col = blockIdx.z;
     const uint32_t j2_0 = blockIdx.x * T;
     const uint64_t *s = src + (size_t)col * src_col_stride;
+    const int nchunks = n1 / T;
+    const uint64_t *ftab = nullptr;
+    if (TAB) {
+        // this block's slice of the table: T*T consecutive entries in each of the nchunks tiles
+        ftab = inter_full + (size_t)coset * n + (size_t)j2_0 * T;
+        constexpr int LINE = 16;  // 128-byte lines, in entries
+        constexpr int per_chunk = (T * T + LINE - 1) / LINE;
+        for (int i = threadIdx.x; i < nchunks * per_chunk; i += blockDim.x) {
+            const uint64_t *q = ftab + (((size_t)(i / per_chunk) << log2) * T) + (size_t)(i % per_chunk) * LINE;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        }
+    }
     for (int i = threadIdx.x; i < n1; i += blockDim.x) tw[i] = stage1[(size_t)coset * n1 + i];
     for (int it = threadIdx.x; it < n1 * T; it += blockDim.x) {
         const int t = it % T, j1 = it / T;
         a[bitrev(j1, log1) * RS + t] = s[((size_t)j1 << log2) + j2_0 + t];
     }
     __syncthreads();
-    dit_tile<T, RS, PLAIN>(a, tw, log1);
-    // inter-pass factor F(i1, j2) = b[j2] * w_n^(i1*j2), advanced by a running product per thread
+    dit_tile<T, RS, PLAIN, INV>(a, tw, log1);
     uint64_t *o = tmp + ((size_t)col * ncosets + coset) * n;
     const int it0 = threadIdx.x;
     const int ii = it0 % T, t = (it0 / T) % T;
@@ -126,19 +177,42 @@ __global__ void __launch_bounds__(1024) dft_pass1_kernel(const uint64_t *__restr
     const uint32_t step_i1 = cstep * T;
     int c = it0 / (T * T);
     uint32_t i1 = c * T + ii;
-    uint64_t f = gl::mul(__ldg(inter_b + (size_t)coset * ((size_t)1 << log2) + j2), root_pow(wlo, whi, lo_bits, i1 * j2));
-    const uint64_t d = root_pow(wlo, whi, lo_bits, step_i1 * j2);
-    const int nchunks = n1 / T;
-    for (; c < nchunks; c += cstep, i1 += step_i1) {
-        const uint64_t v = gl::mul_canon(a[i1 * RS + t], f);
-        o[((size_t)c << log2) * T + (size_t)j2 * T + ii] = v;
-        f = gl::mul_any(f, d);
+    if (TAB) {
+        for (; c < nchunks; c += cstep, i1 += step_i1) {
+            const size_t idx = ((size_t)c << log2) * T + (size_t)j2 * T + ii;
+            o[idx] = gl::mul_canon(a[i1 * RS + t], __ldg(ftab + ((size_t)c << log2) * T + t * T + ii));
+        }
+    } else {
+        // F(i1, j2) = b[j2] * w_n^(i1*j2), advanced by a running product per thread
+        uint64_t f = gl::mul(__ldg(inter_b + (size_t)coset * ((size_t)1 << log2) + j2), root_pow(wlo, whi, lo_bits, i1 * j2));
+        const uint64_t d = root_pow(wlo, whi, lo_bits, step_i1 * j2);
+        for (; c < nchunks; c += cstep, i1 += step_i1) {
+            const uint64_t v = gl::mul_canon(a[i1 * RS + t], f);
+            o[((size_t)c << log2) * T + (size_t)j2 * T + ii] = v;
+            f = gl::mul_any(f, d);
+        }
+    }
+}
+
+// Fills the full inter-pass table of one plan: F[coset][(c << log2)*T + j2*T + ii] for i1 = c*T + ii.
+__global__ void inter_table_kernel(uint64_t *__restrict__ out, const uint64_t *__restrict__ inter_b,
+                                   const uint64_t *__restrict__ wlo, const uint64_t *__restrict__ whi, int lo_bits,
+                                   int log1, int log2, int logT) {
+    const size_t n = (size_t)1 << (log1 + log2);
+    const int coset = blockIdx.y;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t ii = idx & ((1u << logT) - 1);
+        const uint32_t j2 = (idx >> logT) & ((1u << log2) - 1);
+        const uint32_t c = idx >> (logT + log2);
+        const uint32_t i1 = (c << logT) | ii;
+        out[(size_t)coset * n + idx] =
+            gl::mul(__ldg(inter_b + ((size_t)coset << log2) + j2), root_pow(wlo, whi, lo_bits, i1 * j2));
     }
 }
 
 // ---- pass 2 -------------------------------------------------------------------------------
 // grid: (n1/T, ncosets, ncols)
-template <int T>
+template <int T, bool INV>
 __global__ void __launch_bounds__(1024) dft_pass2_kernel(const uint64_t *__restrict__ tmp, uint64_t *__restrict__ dst,
                                                         const uint64_t *__restrict__ stage2,
                                                         const uint64_t *__restrict__ post_u,
@@ -160,7 +234,7 @@ __global__ void __launch_bounds__(1024) dft_pass2_kernel(const uint64_t *__restr
         a[bitrev(j2, log2) * RS + t] = s[it];
     }
     __syncthreads();
-    dit_tile<T, RS, true>(a, tw, log2);
+    dit_tile<T, RS, true, INV>(a, tw, log2);
     uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n;
     for (int it = threadIdx.x; it < n2 * T; it += blockDim.x) {
         const int t = it % T, i2 = it / T;
@@ -175,7 +249,7 @@ __global__ void __launch_bounds__(1024) dft_pass2_kernel(const uint64_t *__restr
 
 // ---- single pass (n <= 2^11) --------------------------------------------------------------
 // grid: (1, ncosets, ncols)
-template <bool PLAIN>
+template <bool PLAIN, bool INV>
 __global__ void __launch_bounds__(256) dft_single_kernel(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst,
                                                          const uint64_t *__restrict__ stage,
                                                          const uint64_t *__restrict__ post_u, uint64_t scale, int logn,
@@ -191,7 +265,7 @@ __global__ void __launch_bounds__(256) dft_single_kernel(const uint64_t *__restr
         a[bitrev(i, logn)] = s[i];
     }
     __syncthreads();
-    dit_tile<1, 1, PLAIN>(a, tw, logn);
+    dit_tile<1, 1, PLAIN, INV>(a, tw, logn);
     uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         uint64_t v = a[i];
@@ -202,67 +276,109 @@ __global__ void __launch_bounds__(256) dft_single_kernel(const uint64_t *__restr
     }
 }
 
+int dft_tile_width(int log1, int log2) {
+    // tile width T: 2^10-point passes with T = 8 and 2^11-point passes with T = 4 both leave room for
+    // two blocks per SM (82 / 96 KB each); measured 4.2e11 butterflies/s either way, against 3.0e11
+    // with one 512-thread block per SM
+    return (log1 > log2 ? log1 : log2) <= 10 ? 8 : 4;
+}
+
+void dft_fill_inter_table(const DftTables &t, uint64_t *out, cudaStream_t s) {
+    const int T = dft_tile_width(t.log1, t.log2);
+    const size_t n = (size_t)1 << t.logn;
+    unsigned bx = (unsigned)((n + 255) / 256);
+    if (bx > 148 * 16) bx = 148 * 16;
+    AERO_COUNT_LAUNCH(1);
+    inter_table_kernel<<<dim3(bx, t.ncosets), 256, 0, s>>>(out, t.inter_b, t.wlo, t.whi, t.lo_bits, t.log1, t.log2,
+                                                          T == 8 ? 3 : 2);
+}
+
+template <int T, bool PLAIN, bool INV, bool TAB>
+static void launch_pass1(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        attr_set = true;
+    }
+    const int n1 = 1 << t.log1, n2 = 1 << t.log2;
+    const size_t n = (size_t)1 << t.logn;
+    dim3 g1(n2 / T, nc, l.ncols);
+    dft_pass1_kernel<T, PLAIN, INV, TAB><<<g1, threads, smem, s>>>(
+        l.src, l.tmp, t.stage1 + (size_t)l.coset_begin * n1, t.inter_b + (size_t)l.coset_begin * n2,
+        TAB ? t.inter_full + (size_t)l.coset_begin * n : nullptr, t.wlo, t.whi, t.lo_bits, t.log1, t.log2,
+        l.src_col_stride, nc);
+}
+template <int T, bool INV>
+static void launch_pass2(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(dft_pass2_kernel<T, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dft_pass2_kernel<T, INV>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        attr_set = true;
+    }
+    const int n1 = 1 << t.log1;
+    dim3 g2(n1 / T, nc, l.ncols);
+    dft_pass2_kernel<T, INV><<<g2, threads, smem, s>>>(l.tmp, l.dst, t.stage2, t.post_u, t.post_v, t.log1, t.log2,
+                                                       l.dst_col_stride, nc, l.deinterleave_log);
+}
+
 template <int T>
 static void launch_two_pass(const DftTables &t, const DftLaunch &l, cudaStream_t s) {
     const int n1 = 1 << t.log1, n2 = 1 << t.log2;
     const int nc = l.coset_count ? l.coset_count : t.ncosets;
-    const uint64_t *stage1 = t.stage1 + (size_t)l.coset_begin * n1;
-    const uint64_t *inter_b = t.inter_b + (size_t)l.coset_begin * n2;
     const size_t smem1 = (size_t)n1 * (T + 1) * 8 + (size_t)n1 * 8;
     const size_t smem2 = (size_t)n2 * (T + 1) * 8 + (size_t)n2 * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(dft_pass1_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(dft_pass1_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(dft_pass2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(dft_pass1_kernel<T, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(dft_pass1_kernel<T, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(dft_pass2_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
-    }
     // 512 threads while two blocks fit the 227 KB of shared memory of an SM; a 2^12-point pass
     // (192 KB, one block per SM) runs 1024 threads instead so the SM still holds 32 warps
-    auto threads_for = [](int m, size_t smem) {
+    auto threads_for = [](int logm, size_t smem) {
         const int cap = smem > 113 * 1024 ? 1024 : 512;
-        int items = (m / 8) * T;  // radix-8 work items per round
+        int items = ((1 << logm) >> NttRounds(logm).log(0)) * T;  // work items of the widest round
         int th = items < 64 ? 64 : (items > cap ? cap : items);
         th = (th / (T * T)) * (T * T);
         return th < T * T ? T * T : th;
     };
-    dim3 g1(n2 / T, nc, l.ncols), g2(n1 / T, nc, l.ncols);
+    const int th1 = threads_for(t.log1, smem1), th2 = threads_for(t.log2, smem2);
     AERO_COUNT_LAUNCH(2);
-    if (t.plain)
-        dft_pass1_kernel<T, true><<<g1, threads_for(n1, smem1), smem1, s>>>(l.src, l.tmp, stage1, inter_b, t.wlo, t.whi,
-                                                                     t.lo_bits, t.log1, t.log2, l.src_col_stride, nc);
-    else
-        dft_pass1_kernel<T, false><<<g1, threads_for(n1, smem1), smem1, s>>>(l.src, l.tmp, stage1, inter_b, t.wlo, t.whi,
-                                                                      t.lo_bits, t.log1, t.log2, l.src_col_stride, nc);
-    dft_pass2_kernel<T><<<g2, threads_for(n2, smem2), smem2, s>>>(l.tmp, l.dst, t.stage2, t.post_u, t.post_v, t.log1, t.log2,
-                                                           l.dst_col_stride, nc, l.deinterleave_log);
+    const bool tab = t.inter_full != nullptr;
+#define AERO_P1(PLAIN, INV)                                                          \
+    (tab ? launch_pass1<T, PLAIN, INV, true>(t, l, nc, th1, smem1, s)                \
+         : launch_pass1<T, PLAIN, INV, false>(t, l, nc, th1, smem1, s))
+    if (t.plain) {
+        if (t.inverse) AERO_P1(true, true); else AERO_P1(true, false);
+    } else {
+        if (t.inverse) AERO_P1(false, true); else AERO_P1(false, false);
+    }
+#undef AERO_P1
+    if (t.inverse) launch_pass2<T, true>(t, l, nc, th2, smem2, s);
+    else launch_pass2<T, false>(t, l, nc, th2, smem2, s);
+}
+
+template <bool PLAIN, bool INV>
+static void launch_single(const DftTables &t, const DftLaunch &l, cudaStream_t s) {
+    const int n = 1 << t.logn;
+    const int items = n >> NttRounds(t.logn).log(0);
+    const int th = items < 32 ? 32 : (items > 256 ? 256 : items);
+    const int nc = l.coset_count ? l.coset_count : t.ncosets;
+    dim3 g(1, nc, l.ncols);
+    dft_single_kernel<PLAIN, INV><<<g, th, (size_t)n * 16, s>>>(l.src, l.dst, t.stage2 + (size_t)l.coset_begin * n, t.post_u,
+                                                               t.single_scale, t.logn, l.src_col_stride,
+                                                               l.dst_col_stride, l.deinterleave_log);
 }
 
 void dft_run(const DftTables &t, const DftLaunch &l, cudaStream_t s) {
     if (t.log1 == 0) {
-        const int n = 1 << t.logn;
-        int th = n / 8 < 32 ? 32 : (n / 8 > 256 ? 256 : n / 8);
-        const int nc = l.coset_count ? l.coset_count : t.ncosets;
-        dim3 g(1, nc, l.ncols);
         AERO_COUNT_LAUNCH(1);
-        if (t.plain)
-            dft_single_kernel<true><<<g, th, (size_t)n * 16, s>>>(l.src, l.dst, t.stage2 + (size_t)l.coset_begin * n,
-                                                                 t.post_u, t.single_scale, t.logn, l.src_col_stride,
-                                                                 l.dst_col_stride, l.deinterleave_log);
-        else
-            dft_single_kernel<false><<<g, th, (size_t)n * 16, s>>>(l.src, l.dst, t.stage2 + (size_t)l.coset_begin * n,
-                                                                  t.post_u, t.single_scale, t.logn, l.src_col_stride,
-                                                                  l.dst_col_stride, l.deinterleave_log);
+        if (t.plain) {
+            if (t.inverse) launch_single<true, true>(t, l, s); else launch_single<true, false>(t, l, s);
+        } else {
+            if (t.inverse) launch_single<false, true>(t, l, s); else launch_single<false, false>(t, l, s);
+        }
         return;
     }
-    const int big = t.log1 > t.log2 ? t.log1 : t.log2;
-    // tile width T: 2^10-point passes with T = 8 and 2^11-point passes with T = 4 both leave room for
-    // two blocks per SM (82 / 96 KB each); measured 4.2e11 butterflies/s either way, against 3.0e11
-    // with one 512-thread block per SM
-    if (big <= 10) launch_two_pass<8>(t, l, s);
+    if (dft_tile_width(t.log1, t.log2) == 8) launch_two_pass<8>(t, l, s);
     else launch_two_pass<4>(t, l, s);
 }
 

@@ -9,6 +9,11 @@
 //           times the inter-pass factor s^j2 * w_n^(i1*j2), stored in T x T tiles;
 //   pass 2: n2-point DFTs over j2, natural-order store.
 // Sizes up to 2^11 run in a single shared-memory pass.
+//
+// Each shared-memory transform is a mixed-radix DIT of register-resident rounds of 2^R points
+// (R <= NTT_MAX_ROUND_LOG).  Only the inputs of a round are multiplied by general twiddles; the
+// twiddles inside a round are 2^R-th roots of unity, which are powers of two in this field
+// (w_64 = 2^39), i.e. shifts (gl::mul_pow2).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -17,16 +22,36 @@ namespace aero {
 
 constexpr int NTT_SINGLE_MAX_LOG = 11;  // largest single-pass transform
 constexpr int NTT_MAX_LOG = 24;         // two passes of <= 2^12 points
+constexpr int NTT_MAX_ROUND_LOG = 4;    // largest register-resident round: 16 points
+
+// Round schedule of a 2^logM-point shared-memory transform, shared by the host (stage tables) and the
+// device (dit_tile): the fewest rounds of at most 2^NTT_MAX_ROUND_LOG points, sizes as even as
+// possible, larger rounds first.  Round i covers DIT stages [start, start + log).
+struct NttRounds {
+    int count, base, extra;
+    __host__ __device__ explicit NttRounds(int logM)
+        : count((logM + NTT_MAX_ROUND_LOG - 1) / NTT_MAX_ROUND_LOG), base(0), extra(0) {
+        if (count < 1) count = 1;
+        base = logM / count;
+        extra = logM % count;
+    }
+    __host__ __device__ int log(int i) const { return base + (i < extra ? 1 : 0); }
+};
 
 // Device-resident tables of one transform "plan" (built on the host once per shape, cached).
 struct DftTables {
     int logn = 0, log1 = 0, log2 = 0;  // n = n1 * n2 ; log1 == 0 means single pass (n2 = n)
     int ncosets = 1;
     bool plain = false;               // no coset shift (all shifts == 1): unit twiddles are skipped
+    bool inverse = false;             // transform root is w_n^-1 (selects the shifts inside a round)
     int lo_bits = 0;                  // two-level w_n^e table split
-    uint64_t *stage1 = nullptr;       // [ncosets][n1]  pass-1 stage twiddles tw[m/2+k] = sigma^(n1/m) w_m^k
-    uint64_t *stage2 = nullptr;       // [n2]           pass-2 stage twiddles (plain); single pass: [ncosets][n]
+    // stage tables: for the round covering stages [s0, s0+R), sub-transform e (1 <= e < 2^R) and
+    // offset low < 2^s0:  tw[(e << s0) + low] = (sigma^(M/m) w_m^low)^bitrev_R(e),  m = 2^(s0+R)
+    uint64_t *stage1 = nullptr;       // [ncosets][n1]  pass 1 (coset shift sigma = s_r^n2 absorbed)
+    uint64_t *stage2 = nullptr;       // [n2]           pass 2 (plain); single pass: [ncosets][n]
     uint64_t *inter_b = nullptr;      // [ncosets][n2]  c * s_r^j2
+    uint64_t *inter_full = nullptr;   // optional [ncosets][n]: the whole inter-pass factor c s_r^j2 w_n^(i1 j2) in
+                                      //   the tile order pass 1 stores in (one multiplication instead of two)
     uint64_t *wlo = nullptr, *whi = nullptr;
     uint64_t *post_u = nullptr;       // optional output scale: out[i] *= post_u[i1] * post_v[i2]
     uint64_t *post_v = nullptr;       //   (single pass: post_u[i], post_v unused)
@@ -45,5 +70,9 @@ struct DftLaunch {
 };
 
 void dft_run(const DftTables &t, const DftLaunch &l, cudaStream_t s);
+// two-pass plans: writes the [ncosets][n] table DftTables::inter_full points at (t.inter_full itself
+// is ignored; the other tables of t must be resident)
+void dft_fill_inter_table(const DftTables &t, uint64_t *out, cudaStream_t s);
+int dft_tile_width(int log1, int log2);
 
 }  // namespace aero

@@ -21,7 +21,8 @@ void convert_form(const uint64_t *src, uint64_t *dst, size_t count, int to_montg
 }
 
 // Field-arithmetic self test: arbitrary u64 operands (reduced first where the operation requires
-// canonical inputs).  out: [mul, add, sub, mul of the raw (possibly non-canonical) operands]
+// canonical inputs).  out: [mul, add, sub, mul of the raw (possibly non-canonical) operands,
+// raw a * 2^S for S = 12, 24, ..., 84 (the shifts inside the NTT rounds), canonical-sum add]
 __global__ void field_ops_kernel(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, size_t n,
                                  uint64_t *__restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -31,6 +32,14 @@ __global__ void field_ops_kernel(const uint64_t *__restrict__ a, const uint64_t 
     out[n + i] = gl::add(x, y);
     out[2 * n + i] = gl::sub(x, y);
     out[3 * n + i] = gl::canon_any(gl::mul_any(a[i], b[i]));
+    out[4 * n + i] = gl::mul_pow2<12>(a[i]);
+    out[5 * n + i] = gl::mul_pow2<24>(a[i]);
+    out[6 * n + i] = gl::mul_pow2<36>(a[i]);
+    out[7 * n + i] = gl::mul_pow2<48>(a[i]);
+    out[8 * n + i] = gl::mul_pow2<60>(a[i]);
+    out[9 * n + i] = gl::mul_pow2<72>(a[i]);
+    out[10 * n + i] = gl::mul_pow2<84>(a[i]);
+    out[11 * n + i] = gl::add_cc(x, y);
 }
 void field_ops(const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out, cudaStream_t s) {
     AERO_COUNT_LAUNCH(1);

@@ -179,7 +179,7 @@ class Context:
     def test_field_ops(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a, np.uint64)
         b = np.ascontiguousarray(b, np.uint64)
-        out = np.empty((4, a.size), np.uint64)
+        out = np.empty((12, a.size), np.uint64)
         self._check(self.lib.aero_test_field_ops(self.h, a.ctypes.data_as(p_u64), b.ctypes.data_as(p_u64), a.size,
                                                  out.ctypes.data_as(p_u64)))
         return out

@@ -73,6 +73,9 @@ int aero_ctx_get_form(aero_ctx *ctx);
  *                     (faster on B200);
  *   "hash_blocks_per_sm" grid cap (blocks per SM) of an overlapped row-hash launch (default 2);
  *   "lde_batch_bytes" NTT scratch budget per column batch (default 1 GiB);
+ *   "ntt_table_max_bytes" largest full inter-pass twiddle table (8 bytes per output element of one
+ *                     column) a two-pass transform plan may keep (default 1 GiB; 0 = never, the factor
+ *                     is then advanced by a running product); read when a plan is first built;
  *   "use_window"      1 (default once attached) / 0: route the multi-GPU exchanges through the peer
  *                     window or through the aero_all_gather_cosets hook.  The first proof of a shape
  *                     on a context must take the hook: it still calls cudaMalloc, which can block on
@@ -202,7 +205,9 @@ aero_status aero_commit_rows_device(aero_ctx *ctx, const uint64_t *d_m, size_t c
                                     uint64_t n_rows, uint8_t root[32]);
 /* Self-test of the device Goldilocks arithmetic (math/src/field/f64/mod.rs:273-330): for n operand
  * pairs (any u64; reduced mod p first) writes out[0..n) = a*b, out[n..2n) = a+b, out[2n..3n) = a-b
- * (canonical) and out[3n..4n) = a*b computed from the unreduced operands. */
+ * (canonical), out[3n..4n) = a*b computed from the unreduced operands, out[(4+k)n..(5+k)n) =
+ * a * 2^(12(k+1)) for k = 0..6 from the unreduced a (the power-of-two twiddles inside the NTT
+ * rounds), and out[11n..12n) = a+b through the canonical-sum adder; out holds 12n words. */
 aero_status aero_test_field_ops(aero_ctx *ctx, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
 /* Device scratch helpers so callers without a CUDA runtime binding can stage data. */
 aero_status aero_device_alloc(aero_ctx *ctx, size_t bytes, void **d_ptr);

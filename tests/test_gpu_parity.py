@@ -343,6 +343,13 @@ def test_field_ops_edge_cases(ctx, oracle):
                P - 1, P - 2, P - E, P - E - 1, (P + 1) // 2, (P - 1) // 2, P, P + 1, P + E - 1, (1 << 64) - 1, (1 << 64) - 2,
                (1 << 64) - E, 0xFFFFFFFE00000001, 0xFFFFFFFF00000000, 0x00000000FFFFFFFF, 0xFFFFFFFEFFFFFFFF,
                0x0000000100000000, 0x8000000000000000, 0x7FFFFFFFFFFFFFFF, 1753635133440165772]
+    # limb patterns at the carry / borrow boundaries of the shift-multiplications (b = S mod 32)
+    for b in (4, 8, 12, 16, 20, 24, 28):
+        k = 32 - b
+        for hi in ((1 << k) - 1, 1 << k, E >> b, (E << k) & E, 0):
+            for lo in (0, E, (1 << k) - 1, (E << k) & E):
+                special.append((hi << 32) | lo)
+    special = sorted(set(special))
     rnd = [int(v) for v in oracle.splitmix64_column(0xF1E1D, 64)]
     vals = special + rnd
     a = np.array([x for x in vals for _ in vals], np.uint64)
@@ -354,3 +361,7 @@ def test_field_ops_edge_cases(ctx, oracle):
     assert [int(v) for v in out[1]] == [(x + y) % P for x, y in zip(ai, bi)], "add"
     assert [int(v) for v in out[2]] == [(x - y) % P for x, y in zip(ai, bi)], "sub"
     assert [int(v) for v in out[3]] == [int(x) * int(y) % P for x, y in zip(a, b)], "mul of unreduced operands"
+    for k in range(7):  # power-of-two twiddles of the NTT rounds (gl::mul_pow2), unreduced operand
+        s = 12 * (k + 1)
+        assert [int(v) for v in out[4 + k]] == [(int(x) << s) % P for x in a], "mul_pow2<%d>" % s
+    assert [int(v) for v in out[11]] == [(x + y) % P for x, y in zip(ai, bi)], "add_cc"

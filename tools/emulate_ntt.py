@@ -14,21 +14,53 @@ def bitrev(x, bits):
     return int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
 
 
+MAX_ROUND_LOG = 4  # ntt.cuh NTT_MAX_ROUND_LOG
+
+
+def rounds_of(logM):
+    """NttRounds: fewest rounds of <= 2^MAX_ROUND_LOG points, as even as possible, larger first."""
+    count = max(1, (logM + MAX_ROUND_LOG - 1) // MAX_ROUND_LOG)
+    base, extra = logM // count, logM % count
+    return [base + (1 if i < extra else 0) for i in range(count)]
+
+
 def fill_stage_table(logM, sigma, wM):
     M = 1 << logM
     tw = [0] * M
-    for s in range(logM):
-        m = 2 << s
+    s0 = 0
+    for R in rounds_of(logM):
+        m = 1 << (s0 + R)
         sg = pow(sigma, M // m, P)
         wm = pow(wM, M // m, P)
         x = sg
-        for k in range(m // 2):
-            tw[m // 2 + k] = x
+        for low in range(1 << s0):
+            pw = x
+            for rho in range(1, 1 << R):
+                e = bitrev(rho, R)
+                tw[(e << s0) + low] = pw
+                pw = mul(pw, x)
             x = mul(x, wm)
+        s0 += R
     return tw
 
 
-def dit_round(a, tw, s0, logM, R, T, RS, nthreads):
+def unit_exp(j, inv):
+    u = (39 << (6 - j)) % 192
+    return (192 - u) % 192 if inv else u
+
+
+def need_canon(R, q, e):
+    if q >= R:
+        return False
+    bit = 1 << q
+    if e & bit:
+        return (e & (bit - 1)) == 0
+    return need_canon(R, q + 1, e) or need_canon(R, q + 1, e | bit)
+
+
+def dit_round(a, tw, s0, logM, R, T, RS, nthreads, plain0, inv):
+    """Values are tracked with a known-canonical flag to check the kernel's canonical-form
+    bookkeeping: add_cc / unit-twiddle v operands must be canonical."""
     ngroups = (1 << logM) >> R
     items = ngroups * T
     for tid in range(nthreads):
@@ -37,33 +69,49 @@ def dit_round(a, tw, s0, logM, R, T, RS, nthreads):
             t, g = it % T, it // T
             low = g & ((1 << s0) - 1)
             base = ((g >> s0) << (s0 + R)) | low
-            x = [a[(base + (e << s0)) * RS + t] for e in range(1 << R)]
+            x, canon = [], []
+            for e in range(1 << R):
+                v = a[(base + (e << s0)) * RS + t]
+                if e > 0 and not plain0:
+                    v = mul(v, tw[(e << s0) + low])
+                    canon.append(True)
+                elif need_canon(R, 0, e):
+                    canon.append(True)   # canon_any
+                else:
+                    canon.append(False)
+                x.append(v)
             for q in range(R):
                 for e in range(1 << R):
                     if e & (1 << q):
                         continue
-                    k = low + ((e & ((1 << q) - 1)) << s0)
-                    w = tw[(1 << (s0 + q)) + k]
+                    f = e | (1 << q)
+                    ex = (unit_exp(q + 1, inv) * (e & ((1 << q) - 1))) % 192
+                    canon_sum = need_canon(R, q + 1, e)
                     u = x[e]
-                    v = mul(x[e | (1 << q)], w)
-                    x[e] = (u + v) % P
-                    x[e | (1 << q)] = (u - v) % P
+                    if ex == 0:
+                        assert canon[f], "unit twiddle needs a canonical v"
+                        v = x[f]
+                    else:
+                        assert (ex % 96) % 32 != 0
+                        v = mul(x[f], pow(2, ex % 96, P))
+                    if canon_sum:
+                        assert canon[e], "canonical sum needs a canonical u"
+                    if ex < 96:
+                        x[e], x[f] = (u + v) % P, (u - v) % P
+                        canon[e], canon[f] = canon_sum, canon[e]
+                    else:
+                        assert not canon_sum
+                        x[e], x[f] = (u - v) % P, (u + v) % P
+                        canon[e], canon[f] = canon[e], False
             for e in range(1 << R):
                 a[(base + (e << s0)) * RS + t] = x[e]
             it += nthreads
 
 
-def dit_tile(a, tw, logM, T, RS, nthreads):
+def dit_tile(a, tw, logM, T, RS, nthreads, plain=False, inv=False):
     s0 = 0
-    while s0 < logM:
-        left = logM - s0
-        if left >= 3 and left != 4:
-            R = 3
-        elif left >= 2:
-            R = 2
-        else:
-            R = 1
-        dit_round(a, tw, s0, logM, R, T, RS, nthreads)
+    for i, R in enumerate(rounds_of(logM)):
+        dit_round(a, tw, s0, logM, R, T, RS, nthreads, plain and i == 0, inv)
         s0 += R
 
 
@@ -91,13 +139,14 @@ def dft(src, logn, inverse, shifts, scale_c, post_base, deint=0, single_max=11, 
     if inverse:
         w = so.inv(w)
     outs = []
+    plain = all(sh == 1 for sh in shifts)
     if logn <= single_max:
         for r, sh in enumerate(shifts):
             tw = fill_stage_table(logn, sh, w)
             a = [0] * n
             for i in range(n):
                 a[bitrev(i, logn)] = int(src[i])
-            dit_tile(a, tw, logn, 1, 1, nthreads)
+            dit_tile(a, tw, logn, 1, 1, nthreads, plain, inverse)
             o = [0] * n
             for i in range(n):
                 v = a[i]
@@ -126,7 +175,7 @@ def dft(src, logn, inverse, shifts, scale_c, post_base, deint=0, single_max=11, 
             for it in range(n1 * T):
                 t, j1 = it % T, it // T
                 a[bitrev(j1, log1) * RS + t] = int(src[(j1 << log2_) + j2_0 + t])
-            dit_tile(a, st1, log1, T, RS, nthreads)
+            dit_tile(a, st1, log1, T, RS, nthreads, plain, inverse)
             bd = max(T * T, (nthreads // (T * T)) * (T * T))
             for tid in range(bd):
                 ii, t = tid % T, (tid // T) % T
@@ -152,7 +201,7 @@ def dft(src, logn, inverse, shifts, scale_c, post_base, deint=0, single_max=11, 
             for it in range(n2 * T):
                 t, j2 = it % T, it // T
                 a[bitrev(j2, log2_) * RS + t] = tmp[base + it]
-            dit_tile(a, st2, log2_, T, RS, nthreads)
+            dit_tile(a, st2, log2_, T, RS, nthreads, True, inverse)
             for it in range(n2 * T):
                 t, i2 = it % T, it // T
                 v = a[i2 * RS + t]
@@ -179,6 +228,9 @@ def check(logn, single_max):
     outs = dft(polys[0], logn, False, shifts, 1, 0, single_max=single_max)
     for r in range(8):
         assert outs[r] == [int(lde[8 * i + r]) for i in range(n)], ("lde", logn, r)
+    if logn < 3:
+        print('ok logn=%d (no deinterleave case)' % logn)
+        return
     # coset iNTT with deinterleave 3
     ev = so.synthetic_trace(1, n, 0x777)[0]
     itw = np.empty(n // 2, np.uint64)
@@ -194,7 +246,7 @@ def check(logn, single_max):
 
 
 if __name__ == "__main__":
-    for logn in (3, 4, 5, 7, 10):
+    for logn in (1, 2, 3, 4, 5, 6, 7, 8, 10, 11):
         check(logn, 11)
-    for logn in (6, 7, 9):  # force the two-pass path at small sizes (T=8 needs n1,n2 >= 8)
+    for logn in (6, 7, 9, 12):  # force the two-pass path at small sizes (T=8 needs n1,n2 >= 8)
         check(logn, 2)
