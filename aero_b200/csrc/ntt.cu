@@ -10,6 +10,15 @@ namespace aero {
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t x, int bits) { return __brev(x) >> (32 - bits); }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): a tile is fetched with every load of a thread in
+// flight at once and no register staging; a plain load/store loop exposes one DRAM latency per
+// iteration (ncu: 40 % of the stall samples of the first version sat on that loop's STS).
+__device__ __forceinline__ void cp_async8(uint64_t *smem_dst, const uint64_t *gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- compile-time structure of a 2^R-point round ------------------------------------------------
 template <int N, class F, int I = 0>
 __device__ __forceinline__ void static_for(F &&f) {
@@ -162,11 +171,12 @@ __global__ void __launch_bounds__(1024) dft_pass1_kernel(const uint64_t *__restr
             asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
         }
     }
-    for (int i = threadIdx.x; i < n1; i += blockDim.x) tw[i] = stage1[(size_t)coset * n1 + i];
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) cp_async8(tw + i, stage1 + (size_t)coset * n1 + i);
     for (int it = threadIdx.x; it < n1 * T; it += blockDim.x) {
         const int t = it % T, j1 = it / T;
-        a[bitrev(j1, log1) * RS + t] = s[((size_t)j1 << log2) + j2_0 + t];
+        cp_async8(a + bitrev(j1, log1) * RS + t, s + ((size_t)j1 << log2) + j2_0 + t);
     }
+    cp_async_wait_all();
     __syncthreads();
     dit_tile<T, RS, PLAIN, INV>(a, tw, log1);
     uint64_t *o = tmp + ((size_t)col * ncosets + coset) * n;
@@ -178,9 +188,28 @@ __global__ void __launch_bounds__(1024) dft_pass1_kernel(const uint64_t *__restr
     int c = it0 / (T * T);
     uint32_t i1 = c * T + ii;
     if (TAB) {
-        for (; c < nchunks; c += cstep, i1 += step_i1) {
-            const size_t idx = ((size_t)c << log2) * T + (size_t)j2 * T + ii;
-            o[idx] = gl::mul_canon(a[i1 * RS + t], __ldg(ftab + ((size_t)c << log2) * T + t * T + ii));
+        // table loads of U chunks in flight before the first product needs one
+        constexpr int U = 4;
+        const size_t cstride = ((size_t)cstep << log2) * T;       // entries between this thread's chunks
+        const uint64_t *fp = ftab + ((size_t)c << log2) * T + t * T + ii;
+        uint64_t *op = o + ((size_t)c << log2) * T + (size_t)j2 * T + ii;
+        const uint64_t *ap = a + i1 * RS + t;
+        const int astride = step_i1 * RS;
+        for (; c + (U - 1) * cstep < nchunks; c += U * cstep) {
+            uint64_t f[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) f[u] = __ldg(fp + u * cstride);
+#pragma unroll
+            for (int u = 0; u < U; u++) op[u * cstride] = gl::mul_canon(ap[u * astride], f[u]);
+            fp += U * cstride;
+            op += U * cstride;
+            ap += U * astride;
+        }
+        for (; c < nchunks; c += cstep) {
+            *op = gl::mul_canon(*ap, __ldg(fp));
+            fp += cstride;
+            op += cstride;
+            ap += astride;
         }
     } else {
         // F(i1, j2) = b[j2] * w_n^(i1*j2), advanced by a running product per thread
@@ -228,11 +257,12 @@ __global__ void __launch_bounds__(1024) dft_pass2_kernel(const uint64_t *__restr
     const int coset = blockIdx.y, col = blockIdx.z;
     const uint32_t i1_0 = blockIdx.x * T;
     const uint64_t *s = tmp + ((size_t)col * ncosets + coset) * n + ((size_t)blockIdx.x << log2) * T;
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) tw[i] = stage2[i];
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) cp_async8(tw + i, stage2 + i);
     for (int it = threadIdx.x; it < n2 * T; it += blockDim.x) {
         const int t = it % T, j2 = it / T;
-        a[bitrev(j2, log2) * RS + t] = s[it];
+        cp_async8(a + bitrev(j2, log2) * RS + t, s + it);
     }
+    cp_async_wait_all();
     __syncthreads();
     dit_tile<T, RS, true, INV>(a, tw, log2);
     uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n;
@@ -261,9 +291,10 @@ __global__ void __launch_bounds__(256) dft_single_kernel(const uint64_t *__restr
     const int coset = blockIdx.y, col = blockIdx.z;
     const uint64_t *s = src + (size_t)col * src_col_stride;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        tw[i] = stage[(size_t)coset * n + i];
-        a[bitrev(i, logn)] = s[i];
+        cp_async8(tw + i, stage + (size_t)coset * n + i);
+        cp_async8(a + bitrev(i, logn), s + i);
     }
+    cp_async_wait_all();
     __syncthreads();
     dit_tile<1, 1, PLAIN, INV>(a, tw, logn);
     uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n;
