@@ -277,6 +277,14 @@ def run_aero(args) -> None:
 
     for _ in range(1 if args.quick else max(args.warmup, 3)):
         step_device()
+    if args.trace:  # profiling aid: CUPTI timeline (kernels, copies, runtime calls) of one step
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as tp:
+            step_device()
+            torch.cuda.synchronize()
+        tp.export_chrome_trace(args.trace)
+        return
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -366,6 +374,7 @@ def main() -> None:
     ap.add_argument("--lde-batch-mb", type=int, default=0, help="NTT scratch budget per column batch (MiB); 0 = default")
     ap.add_argument("--ntt-table-mb", type=int, default=-1,
                     help="largest full inter-pass NTT twiddle table per plan (MiB); 0 = running products; -1 = default")
+    ap.add_argument("--trace", default="", help="profiling aid: write a chrome trace of one device-input step and exit")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu): 1 warm-up, no e2e / cpu legs; numbers printed are NOT bench values")
     args = ap.parse_args()
