@@ -17,7 +17,35 @@ __device__ __forceinline__ void cp_async8(uint64_t *smem_dst, const uint64_t *gm
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async8_saddr(unsigned sa, const uint64_t *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Fetches an M x T tile (M = 2^logM rows of T consecutive words, row j at g + (j << gsh_row)) into
+// shared memory with row j stored at row bitrev_logM(j).  blockDim.x = J*T threads, J a power of two
+// <= M: thread (j0 = tid / T, t = tid % T) owns rows j0 + k*J, whose bit-reversed positions are the
+// 2^m consecutive rows starting at bitrev_logJ(j0) << m  (m = logM - logJ).  Walking those in order
+// leaves one BREV and one 64-bit add per element; the plain loop over `it` spent ~20 instructions per
+// element on index arithmetic (ncu: a fifth of all instructions of a pass).
+template <int T, int RS>
+__device__ __forceinline__ void load_tile_bitrev(uint64_t *a, const uint64_t *g, int logM, int gsh_row) {
+    const int logJ = 31 - __clz((int)blockDim.x / T);
+    const int m = logM - logJ;
+    const int t = threadIdx.x % T, j0 = threadIdx.x / T;
+    const uint32_t row0 = (logJ ? (__brev((uint32_t)j0) >> (32 - logJ)) : 0u) << m;
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(a + row0 * RS + t);
+    const uint64_t *gp = g + ((size_t)j0 << gsh_row) + t;
+    const int gsh = logJ + gsh_row;
+    if (m == 0) {
+        cp_async8_saddr(sa, gp);
+        return;
+    }
+    const int rsh = 32 - m;
+#pragma unroll 8
+    for (int r = 0; r < (1 << m); r++)
+        cp_async8_saddr(sa + r * (RS * 8), gp + ((size_t)(__brev((uint32_t)r) >> rsh) << gsh));
+}
 
 // ---- compile-time structure of a 2^R-point round ------------------------------------------------
 template <int N, class F, int I = 0>
@@ -101,8 +129,14 @@ __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s
     }
 }
 
-template <int T, int RS, bool PLAIN0, bool INV>
+template <int T, int RS, bool PLAIN0, bool INV, int RMAX>
 __device__ __forceinline__ void dit_round_dispatch(int R, uint64_t *a, const uint64_t *tw, int s0, int logM) {
+    if constexpr (RMAX >= 5) {
+        if (R == 5) {
+            dit_round<5, T, RS, PLAIN0, INV>(a, tw, s0, logM);
+            return;
+        }
+    }
     switch (R) {
     case 4: dit_round<4, T, RS, PLAIN0, INV>(a, tw, s0, logM); break;
     case 3: dit_round<3, T, RS, PLAIN0, INV>(a, tw, s0, logM); break;
@@ -112,16 +146,16 @@ __device__ __forceinline__ void dit_round_dispatch(int R, uint64_t *a, const uin
 }
 
 // Full M-point DIT over the tile: input in bit-reversed row order, output in natural row order.
-template <int T, int RS, bool PLAIN, bool INV>
+template <int T, int RS, bool PLAIN, bool INV, int RMAX>
 __device__ __forceinline__ void dit_tile(uint64_t *a, const uint64_t *tw, int logM) {
     const NttRounds rounds(logM);
     // first round: s0 == 0 is a compile-time fact, which lets PLAIN transforms skip the unit twiddles
-    dit_round_dispatch<T, RS, PLAIN, INV>(rounds.log(0), a, tw, 0, logM);
+    dit_round_dispatch<T, RS, PLAIN, INV, RMAX>(rounds.log(0), a, tw, 0, logM);
     __syncthreads();
     int s0 = rounds.log(0);
     for (int i = 1; i < rounds.count; i++) {
         const int R = rounds.log(i);
-        dit_round_dispatch<T, RS, false, INV>(R, a, tw, s0, logM);
+        dit_round_dispatch<T, RS, false, INV, RMAX>(R, a, tw, s0, logM);
         s0 += R;
         __syncthreads();
     }
@@ -142,8 +176,10 @@ __device__ __forceinline__ size_t out_index(uint32_t i, int logn, int deint) {
 // TAB: the inter-pass factor F(i1, j2) = c s^j2 w_n^(i1 j2) comes from a full table in that same tile
 // order (read through L2); otherwise it is advanced by a running product per thread, which costs a
 // second multiplication per element.
-template <int T, bool PLAIN, bool INV, bool TAB>
-__global__ void __launch_bounds__(1024) dft_pass1_kernel(const uint64_t *__restrict__ src, uint64_t *__restrict__ tmp,
+// MAXT: largest block the instantiation is launched with.  The 256-thread variants have 128+ registers
+// per thread and are the only ones that contain 32-point rounds (64 data registers).
+template <int T, bool PLAIN, bool INV, bool TAB, int MAXT>
+__global__ void __launch_bounds__(MAXT) dft_pass1_kernel(const uint64_t *__restrict__ src, uint64_t *__restrict__ tmp,
                                                         const uint64_t *__restrict__ stage1,
                                                         const uint64_t *__restrict__ inter_b,
                                                         const uint64_t *__restrict__ inter_full,
@@ -172,13 +208,10 @@ __global__ void __launch_bounds__(1024) dft_pass1_kernel(const uint64_t *__restr
         }
     }
     for (int i = threadIdx.x; i < n1; i += blockDim.x) cp_async8(tw + i, stage1 + (size_t)coset * n1 + i);
-    for (int it = threadIdx.x; it < n1 * T; it += blockDim.x) {
-        const int t = it % T, j1 = it / T;
-        cp_async8(a + bitrev(j1, log1) * RS + t, s + ((size_t)j1 << log2) + j2_0 + t);
-    }
+    load_tile_bitrev<T, RS>(a, s + j2_0, log1, log2);   // row j1 at s[(j1 << log2) + j2_0 + t]
     cp_async_wait_all();
     __syncthreads();
-    dit_tile<T, RS, PLAIN, INV>(a, tw, log1);
+    dit_tile<T, RS, PLAIN, INV, (MAXT <= 256 ? 5 : 4)>(a, tw, log1);
     uint64_t *o = tmp + ((size_t)col * ncosets + coset) * n;
     const int it0 = threadIdx.x;
     const int ii = it0 % T, t = (it0 / T) % T;
@@ -241,8 +274,8 @@ __global__ void inter_table_kernel(uint64_t *__restrict__ out, const uint64_t *_
 
 // ---- pass 2 -------------------------------------------------------------------------------
 // grid: (n1/T, ncosets, ncols)
-template <int T, bool INV>
-__global__ void __launch_bounds__(1024) dft_pass2_kernel(const uint64_t *__restrict__ tmp, uint64_t *__restrict__ dst,
+template <int T, bool INV, int MAXT>
+__global__ void __launch_bounds__(MAXT) dft_pass2_kernel(const uint64_t *__restrict__ tmp, uint64_t *__restrict__ dst,
                                                         const uint64_t *__restrict__ stage2,
                                                         const uint64_t *__restrict__ post_u,
                                                         const uint64_t *__restrict__ post_v, int log1, int log2,
@@ -258,22 +291,40 @@ __global__ void __launch_bounds__(1024) dft_pass2_kernel(const uint64_t *__restr
     const uint32_t i1_0 = blockIdx.x * T;
     const uint64_t *s = tmp + ((size_t)col * ncosets + coset) * n + ((size_t)blockIdx.x << log2) * T;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) cp_async8(tw + i, stage2 + i);
-    for (int it = threadIdx.x; it < n2 * T; it += blockDim.x) {
-        const int t = it % T, j2 = it / T;
-        cp_async8(a + bitrev(j2, log2) * RS + t, s + it);
-    }
+    load_tile_bitrev<T, RS>(a, s, log2, T == 8 ? 3 : 2);   // row j2 at s[j2*T + t]
     cp_async_wait_all();
     __syncthreads();
-    dit_tile<T, RS, true, INV>(a, tw, log2);
+    dit_tile<T, RS, true, INV, (MAXT <= 256 ? 5 : 4)>(a, tw, log2);
     uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n;
-    for (int it = threadIdx.x; it < n2 * T; it += blockDim.x) {
-        const int t = it % T, i2 = it / T;
-        uint64_t v = a[i2 * RS + t];
-        const uint32_t i1 = i1_0 + t;
-        if (post_u) v = gl::mul(v, gl::mul(__ldg(post_u + i1), __ldg(post_v + i2)));
-        else v = gl::canon_any(v);
-        const uint32_t i = i1 + ((uint32_t)i2 << log1);
-        o[out_index(i, logn, deint)] = v;
+    // thread (j0 = tid / T, t = tid % T) stores rows i2 = j0 + k*J of its tile column i1 = i1_0 + t
+    const int J = blockDim.x / T;
+    const int t = threadIdx.x % T, j0 = threadIdx.x / T;
+    const uint32_t i1 = i1_0 + t;
+    const uint64_t *ap = a + j0 * RS + t;
+    const int astep = J * RS;
+    const int K = n2 / J;
+    if (deint == 0) {
+        uint64_t *op = o + i1 + ((size_t)j0 << log1);
+        const size_t ostep = (size_t)J << log1;
+        if (post_u) {
+            const uint64_t pu = __ldg(post_u + i1);
+            const uint64_t *pv = post_v + j0;
+#pragma unroll 4
+            for (int k = 0; k < K; k++)
+                op[k * ostep] = gl::mul(ap[k * astep], gl::mul(pu, __ldg(pv + k * J)));
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < K; k++) op[k * ostep] = gl::canon_any(ap[k * astep]);
+        }
+    } else {
+        for (int k = 0; k < K; k++) {
+            const int i2 = j0 + k * J;
+            uint64_t v = ap[k * astep];
+            if (post_u) v = gl::mul(v, gl::mul(__ldg(post_u + i1), __ldg(post_v + i2)));
+            else v = gl::canon_any(v);
+            const uint32_t i = i1 + ((uint32_t)i2 << log1);
+            o[out_index(i, logn, deint)] = v;
+        }
     }
 }
 
@@ -296,7 +347,7 @@ __global__ void __launch_bounds__(256) dft_single_kernel(const uint64_t *__restr
     }
     cp_async_wait_all();
     __syncthreads();
-    dit_tile<1, 1, PLAIN, INV>(a, tw, logn);
+    dit_tile<1, 1, PLAIN, INV, 5>(a, tw, logn);
     uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         uint64_t v = a[i];
@@ -324,35 +375,35 @@ void dft_fill_inter_table(const DftTables &t, uint64_t *out, cudaStream_t s) {
                                                           T == 8 ? 3 : 2);
 }
 
-template <int T, bool PLAIN, bool INV, bool TAB>
+template <int T, bool PLAIN, bool INV, bool TAB, int MAXT>
 static void launch_pass1(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     const int n1 = 1 << t.log1, n2 = 1 << t.log2;
     const size_t n = (size_t)1 << t.logn;
     dim3 g1(n2 / T, nc, l.ncols);
-    dft_pass1_kernel<T, PLAIN, INV, TAB><<<g1, threads, smem, s>>>(
+    dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT><<<g1, threads, smem, s>>>(
         l.src, l.tmp, t.stage1 + (size_t)l.coset_begin * n1, t.inter_b + (size_t)l.coset_begin * n2,
         TAB ? t.inter_full + (size_t)l.coset_begin * n : nullptr, t.wlo, t.whi, t.lo_bits, t.log1, t.log2,
         l.src_col_stride, nc);
 }
-template <int T, bool INV>
+template <int T, bool INV, int MAXT>
 static void launch_pass2(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(dft_pass2_kernel<T, INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(dft_pass2_kernel<T, INV>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
     const int n1 = 1 << t.log1;
     dim3 g2(n1 / T, nc, l.ncols);
-    dft_pass2_kernel<T, INV><<<g2, threads, smem, s>>>(l.tmp, l.dst, t.stage2, t.post_u, t.post_v, t.log1, t.log2,
+    dft_pass2_kernel<T, INV, MAXT><<<g2, threads, smem, s>>>(l.tmp, l.dst, t.stage2, t.post_u, t.post_v, t.log1, t.log2,
                                                        l.dst_col_stride, nc, l.deinterleave_log);
 }
 
@@ -364,27 +415,37 @@ static void launch_two_pass(const DftTables &t, const DftLaunch &l, cudaStream_t
     const size_t smem2 = (size_t)n2 * (T + 1) * 8 + (size_t)n2 * 8;
     // 512 threads while two blocks fit the 227 KB of shared memory of an SM; a 2^12-point pass
     // (192 KB, one block per SM) runs 1024 threads instead so the SM still holds 32 warps
-    auto threads_for = [](int logm, size_t smem) {
-        const int cap = smem > 113 * 1024 ? 1024 : 512;
+    // a schedule with a 32-point round needs the 256-thread (128-register) instantiation
+    auto wide = [](int logm) { return NttRounds(logm).log(0) >= 5; };
+    auto threads_for = [&](int logm, size_t smem) {
+        const int cap = wide(logm) ? 256 : (smem > 113 * 1024 ? 1024 : 512);
         int items = ((1 << logm) >> NttRounds(logm).log(0)) * T;  // work items of the widest round
         int th = items < 64 ? 64 : (items > cap ? cap : items);
         th = (th / (T * T)) * (T * T);
         return th < T * T ? T * T : th;
     };
-    const int th1 = threads_for(t.log1, smem1), th2 = threads_for(t.log2, smem2);
+    int th1 = threads_for(t.log1, smem1), th2 = threads_for(t.log2, smem2);
+    // the tile copies give every thread whole rows: at most one thread row per tile row
+    while (th1 / T > n1 && th1 > T * T) th1 /= 2;
+    while (th2 / T > n2 && th2 > T * T) th2 /= 2;
     AERO_COUNT_LAUNCH(2);
     const bool tab = t.inter_full != nullptr;
-#define AERO_P1(PLAIN, INV)                                                          \
-    (tab ? launch_pass1<T, PLAIN, INV, true>(t, l, nc, th1, smem1, s)                \
-         : launch_pass1<T, PLAIN, INV, false>(t, l, nc, th1, smem1, s))
+    const bool w1 = wide(t.log1), w2 = wide(t.log2);
+#define AERO_P1M(PLAIN, INV, TAB)                                                    \
+    (w1 ? launch_pass1<T, PLAIN, INV, TAB, 256>(t, l, nc, th1, smem1, s)             \
+        : launch_pass1<T, PLAIN, INV, TAB, 1024>(t, l, nc, th1, smem1, s))
+#define AERO_P1(PLAIN, INV) (tab ? AERO_P1M(PLAIN, INV, true) : AERO_P1M(PLAIN, INV, false))
     if (t.plain) {
         if (t.inverse) AERO_P1(true, true); else AERO_P1(true, false);
     } else {
         if (t.inverse) AERO_P1(false, true); else AERO_P1(false, false);
     }
 #undef AERO_P1
-    if (t.inverse) launch_pass2<T, true>(t, l, nc, th2, smem2, s);
-    else launch_pass2<T, false>(t, l, nc, th2, smem2, s);
+#undef AERO_P1M
+#define AERO_P2(INV)                                                                 \
+    (w2 ? launch_pass2<T, INV, 256>(t, l, nc, th2, smem2, s) : launch_pass2<T, INV, 1024>(t, l, nc, th2, smem2, s))
+    if (t.inverse) AERO_P2(true); else AERO_P2(false);
+#undef AERO_P2
 }
 
 template <bool PLAIN, bool INV>
