@@ -79,11 +79,15 @@ struct aero_ctx {
     std::map<std::string, PowTableOwned> pow_tables;
     std::vector<void *> owned;  // device allocations freed with the context
     size_t lde_batch_bytes = (size_t)1 << 30;  // NTT scratch budget per column batch
+    int upload_batch_cols = 8;                 // columns per host->device copy batch of aero_segment_commit
     size_t ntt_table_max_bytes = (size_t)1 << 30;  // largest full inter-pass twiddle table a plan may hold
     int shard_rank = 0, shard_world = 1;       // LDE coset shard of this context (multi-GPU)
     std::multimap<size_t, void *> free_blocks;  // exact-size cache of released device blocks
     std::map<void *, size_t> live_blocks;
     size_t cached_bytes = 0, cache_limit_bytes = (size_t)96 << 30;
+    // staging pair of the opening phase (GatherBatch): pinned host + device, grown on demand
+    uint8_t *h_stage = nullptr, *d_stage = nullptr;
+    size_t stage_bytes = 0;
 };
 
 #define CTX_FAIL(ctx, code, ...)                         \
@@ -197,6 +201,22 @@ static void dev_free(aero_ctx *ctx, void *p) {
     ctx->free_blocks.emplace(bytes, p);
     ctx->cached_bytes += bytes;
     if (ctx->cached_bytes > ctx->cache_limit_bytes) cache_release_all(ctx);
+}
+// Pinned host / device staging pair for small result downloads (OOD frame, openings): results land
+// in pinned memory so that several downloads can be queued before the single synchronisation.
+static aero_status stage_reserve(aero_ctx *ctx, size_t total) {
+    if (total <= ctx->stage_bytes) return AERO_OK;
+    size_t cap = ctx->stage_bytes ? ctx->stage_bytes : ((size_t)1 << 20);
+    while (cap < total) cap *= 2;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    ctx->h_stage = ctx->d_stage = nullptr;
+    ctx->stage_bytes = 0;
+    CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_stage, cap));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_stage, cap));
+    ctx->stage_bytes = cap;
+    return AERO_OK;
 }
 // Buffers that other ranks write into (leaf digests, DEEP evaluations) live in the exchange window
 // when one is attached; otherwise this is dev_alloc.
@@ -712,30 +732,17 @@ static aero_status batch_proof_indices(aero_ctx *ctx, const uint64_t *positions,
 // index list (merkle/mod.rs:226-240), including after `i += 1` skipped a sibling; the loop above
 // mirrors that: when a sibling pair is merged, `i` has already advanced, exactly as in the Rust.
 
-static aero_status fetch_batch_proof(aero_ctx *ctx, const uint32_t *full, const std::vector<std::vector<uint32_t>> &idx,
-                                     std::vector<uint8_t> &bytes) {
-    std::vector<uint32_t> flat;
-    for (auto &v : idx) flat.insert(flat.end(), v.begin(), v.end());
-    std::vector<uint8_t> dig(flat.size() * 32);
-    if (!flat.empty()) {
-        uint32_t *d_idx = nullptr, *d_out = nullptr;
-        TRY(dev_alloc(ctx, (void **)&d_idx, flat.size() * 4));
-        TRY(dev_alloc(ctx, (void **)&d_out, flat.size() * 32));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_idx, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-        gather_digests(full, d_idx, (int)flat.size(), d_out, ctx->stream);
-        CUDA_TRY(ctx, cudaMemcpyAsync(dig.data(), d_out, dig.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        dev_free(ctx, d_idx);
-        dev_free(ctx, d_out);
-    }
-    // BatchMerkleProof::serialize_nodes (merkle/proofs.rs:421-439)
+// BatchMerkleProof::serialize_nodes (merkle/proofs.rs:421-439) over the gathered digests `dig`
+// (32 bytes per entry of idx, in order)
+static aero_status serialize_batch_proof(aero_ctx *ctx, const std::vector<std::vector<uint32_t>> &idx, const uint8_t *dig,
+                                         std::vector<uint8_t> &bytes) {
     bytes.clear();
     bytes.push_back((uint8_t)idx.size());
     size_t off = 0;
     for (auto &v : idx) {
         if (v.size() > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "too many nodes in a batch proof vector");
         bytes.push_back((uint8_t)v.size());
-        bytes.insert(bytes.end(), dig.begin() + off * 32, dig.begin() + (off + v.size()) * 32);
+        bytes.insert(bytes.end(), dig + off * 32, dig + (off + v.size()) * 32);
         off += v.size();
     }
     return AERO_OK;
@@ -760,6 +767,206 @@ struct aero_fri {
     bool cur_pending = false;  // coset-sharded DEEP evaluations not exchanged yet
     int coset_begin = 0, coset_count = 0;
 };
+
+
+// -------------------------------------------------------------------------------------------------
+// Openings.  The query phase gathers a few hundred digests and rows out of trees and matrices that
+// stay on the device.  A GatherBatch collects every index list first, uploads them in one copy, runs
+// the gather kernels back to back and downloads all results with one copy and ONE stream
+// synchronisation (a proof used to pay 17 host round trips of 20-100 us here; profiles/r01_trace_gaps_v5.txt).
+// -------------------------------------------------------------------------------------------------
+struct GatherBatch {
+    enum Kind { DIGESTS, SEG_ROWS, FRI_ROWS, COPY };
+    struct Job {
+        Kind kind;
+        const void *src;
+        const aero_segment *seg;
+        uint32_t rows;
+        int log_cosets;
+        size_t idx_off;   // first index (u32 units)
+        int count;
+        size_t out_off, out_bytes;
+    };
+    aero_ctx *ctx;
+    std::vector<uint32_t> idx;
+    std::vector<Job> jobs;
+    size_t out_bytes = 0;
+    const uint8_t *host = nullptr;  // results, valid until the next batch of this context runs
+    explicit GatherBatch(aero_ctx *c) : ctx(c) {}
+    size_t push(Kind k, const void *src, const aero_segment *seg, uint32_t rows, int log_cosets, const uint32_t *ix,
+                size_t n, size_t bytes) {
+        Job j{k, src, seg, rows, log_cosets, idx.size(), (int)n, out_bytes, bytes};
+        if (ix) idx.insert(idx.end(), ix, ix + n);
+        out_bytes += (bytes + 15) & ~(size_t)15;
+        jobs.push_back(j);
+        return j.out_off;
+    }
+    // each returns the offset of its result inside `host`
+    size_t digests(const uint32_t *full, const std::vector<std::vector<uint32_t>> &lists) {
+        std::vector<uint32_t> flat;
+        for (auto &v : lists) flat.insert(flat.end(), v.begin(), v.end());
+        return push(DIGESTS, full, nullptr, 0, 0, flat.data(), flat.size(), flat.size() * 32);
+    }
+    size_t segment_rows(const aero_segment *seg, const std::vector<uint32_t> &pos);
+    size_t fri_rows(const FriLayerDev &L, const std::vector<uint32_t> &pos) {
+        return push(FRI_ROWS, L.evals, nullptr, L.M / 8, L.log_cosets, pos.data(), pos.size(), pos.size() * 64);
+    }
+    size_t copy(const void *d_src, size_t bytes) { return push(COPY, d_src, nullptr, 0, 0, nullptr, 0, bytes); }
+    aero_status run();
+};
+
+size_t GatherBatch::segment_rows(const aero_segment *seg, const std::vector<uint32_t> &pos) {
+    return push(SEG_ROWS, seg->lde, seg, 0, 0, pos.data(), pos.size(), pos.size() * (size_t)seg->ncols * 8);
+}
+aero_status GatherBatch::run() {
+    const size_t idx_bytes = (idx.size() * 4 + 15) & ~(size_t)15;
+    const size_t total = idx_bytes + out_bytes;
+    TRY(stage_reserve(ctx, total));
+    uint8_t *d = ctx->d_stage;
+    if (!idx.empty()) {
+        memcpy(ctx->h_stage, idx.data(), idx.size() * 4);
+        CUDA_TRY(ctx, cudaMemcpyAsync(d, ctx->h_stage, idx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for (const Job &j : jobs) {
+        if (j.out_bytes == 0) continue;
+        const uint32_t *d_idx = (const uint32_t *)d + j.idx_off;
+        uint8_t *d_out = d + idx_bytes + j.out_off;
+        switch (j.kind) {
+        case DIGESTS: gather_digests((const uint32_t *)j.src, d_idx, j.count, (uint32_t *)d_out, ctx->stream); break;
+        case SEG_ROWS:
+            gather_rows(j.seg->lde, j.seg->lde_stride(), j.seg->ncols, j.seg->logn, j.seg->log_blowup, j.seg->coset_begin,
+                        j.seg->coset_count, d_idx, j.count, (uint64_t *)d_out, ctx->stream);
+            break;
+        case FRI_ROWS:
+            gather_fri_rows((const uint64_t *)j.src, j.rows, j.log_cosets, d_idx, j.count, (uint64_t *)d_out, ctx->stream);
+            break;
+        case COPY: CUDA_TRY(ctx, cudaMemcpyAsync(d_out, j.src, j.out_bytes, cudaMemcpyDeviceToDevice, ctx->stream)); break;
+        }
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (out_bytes)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage + idx_bytes, d + idx_bytes, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    host = ctx->h_stage + idx_bytes;
+    return AERO_OK;
+}
+
+// One segment's query: index lists now, bytes after the batch ran.
+struct SegmentOpening {
+    aero_segment *seg = nullptr;
+    std::vector<std::vector<uint32_t>> idx;
+    uint32_t n_pos = 0;
+    size_t dig_off = 0, rows_off = 0;
+    bool want_rows = false;
+};
+static aero_status segment_open_plan(aero_segment *seg, const uint64_t *positions, uint32_t n_pos, bool want_rows,
+                                     GatherBatch &gb, SegmentOpening &o) {
+    aero_ctx *ctx = seg->ctx;
+    if (!seg->full) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no commitment");
+    if (seg->tree_pending) CTX_FAIL(ctx, AERO_ERR_STATE, "sharded segment: exchange leaves and call aero_segment_finish_tree first");
+    o.seg = seg;
+    o.n_pos = n_pos;
+    o.want_rows = want_rows;
+    TRY(batch_proof_indices(ctx, positions, n_pos, seg->N(), o.idx));
+    o.dig_off = gb.digests(seg->full, o.idx);
+    if (want_rows) {
+        std::vector<uint32_t> pos(n_pos);
+        for (uint32_t i = 0; i < n_pos; i++) pos[i] = (uint32_t)positions[i];
+        o.rows_off = gb.segment_rows(seg, pos);
+    }
+    return AERO_OK;
+}
+static aero_status segment_open_finish(const SegmentOpening &o, const GatherBatch &gb, uint64_t *rows_out,
+                                       uint8_t *batch_nodes_out, size_t *len) {
+    aero_ctx *ctx = o.seg->ctx;
+    std::vector<uint8_t> bytes;
+    TRY(serialize_batch_proof(ctx, o.idx, gb.host + o.dig_off, bytes));
+    if (!batch_nodes_out || *len < bytes.size()) {
+        *len = bytes.size();
+        CTX_FAIL(ctx, AERO_ERR_BUFFER, "batch proof needs %zu bytes", bytes.size());
+    }
+    memcpy(batch_nodes_out, bytes.data(), bytes.size());
+    *len = bytes.size();
+    if (o.want_rows) memcpy(rows_out, gb.host + o.rows_off, (size_t)o.n_pos * o.seg->ncols * 8);
+    return AERO_OK;
+}
+
+// fold_positions (fri/src/folding/mod.rs:159-176)
+static std::vector<uint64_t> fold_positions(const std::vector<uint64_t> &pos, uint64_t source, uint64_t ff) {
+    const uint64_t target = source / ff;
+    std::vector<uint64_t> r;
+    for (uint64_t p : pos) {
+        p %= target;
+        if (std::find(r.begin(), r.end(), p) == r.end()) r.push_back(p);
+    }
+    return r;
+}
+// FriProver::build_proof (fri/src/prover/mod.rs:231-275), same split
+struct FriOpening {
+    aero_fri *fri = nullptr;
+    struct Layer {
+        std::vector<std::vector<uint32_t>> idx;
+        size_t n_pos = 0, vals_off = 0, dig_off = 0;
+    };
+    std::vector<Layer> layers;
+    size_t rem_off = 0;
+};
+static aero_status fri_open_plan(aero_fri *fri, const uint64_t *positions, uint32_t n_pos, GatherBatch &gb, FriOpening &o) {
+    aero_ctx *ctx = fri->ctx;
+    if (fri->layers.empty()) CTX_FAIL(ctx, AERO_ERR_STATE, "FRI layers have not been built yet");  // prover/mod.rs:232-235
+    if (n_pos == 0 || n_pos > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of positions must be 1..255");
+    std::vector<uint64_t> pos(positions, positions + n_pos);
+    for (uint64_t p : pos)
+        if (p >= fri->layers[0].M) CTX_FAIL(ctx, AERO_ERR_INVALID, "query position out of range");
+    const FriLayerDev &R = fri->layers.back();
+    if (R.log_cosets) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "remainder layer cannot be the DEEP layer");
+    if ((size_t)R.M * 8 > 0xFFFF) CTX_FAIL(ctx, AERO_ERR_INVALID, "remainder too large for the wire format");
+    o.fri = fri;
+    const size_t nl = fri->layers.size() - 1;
+    o.layers.resize(nl);
+    uint64_t domain = fri->layers[0].M;
+    for (size_t i = 0; i < nl; i++) {
+        const FriLayerDev &L = fri->layers[i];
+        pos = fold_positions(pos, domain, 8);
+        // queried values: [E; 8] rows at the folded positions, canonical bytes
+        std::vector<uint32_t> p32(pos.begin(), pos.end());
+        o.layers[i].n_pos = p32.size();
+        o.layers[i].vals_off = gb.fri_rows(L, p32);
+        TRY(batch_proof_indices(ctx, pos.data(), (uint32_t)pos.size(), L.M / 8, o.layers[i].idx));
+        o.layers[i].dig_off = gb.digests(L.full, o.layers[i].idx);
+        domain /= 8;
+    }
+    // remainder = last committed layer in natural order (prover/mod.rs:258-268 un-transposes the
+    // stored transposed copy; ours is stored natural already)
+    o.rem_off = gb.copy(R.evals, (size_t)R.M * 8);
+    return AERO_OK;
+}
+static aero_status fri_open_finish(const FriOpening &o, const GatherBatch &gb, uint8_t *out_bytes, size_t *len) {
+    aero_ctx *ctx = o.fri->ctx;
+    std::vector<uint8_t> bytes;
+    bytes.push_back((uint8_t)o.layers.size());
+    for (const FriOpening::Layer &l : o.layers) {
+        std::vector<uint8_t> paths;
+        TRY(serialize_batch_proof(ctx, l.idx, gb.host + l.dig_off, paths));
+        // FriProofLayer::write_into (fri/src/proof.rs:351-359)
+        const uint32_t vlen = (uint32_t)(l.n_pos * 64), plen = (uint32_t)paths.size();
+        bytes.insert(bytes.end(), (uint8_t *)&vlen, (uint8_t *)&vlen + 4);
+        bytes.insert(bytes.end(), gb.host + l.vals_off, gb.host + l.vals_off + vlen);
+        bytes.insert(bytes.end(), (uint8_t *)&plen, (uint8_t *)&plen + 4);
+        bytes.insert(bytes.end(), paths.begin(), paths.end());
+    }
+    const uint16_t rl = (uint16_t)(o.fri->layers.back().M * 8);
+    bytes.insert(bytes.end(), (uint8_t *)&rl, (uint8_t *)&rl + 2);
+    bytes.insert(bytes.end(), gb.host + o.rem_off, gb.host + o.rem_off + rl);
+    bytes.push_back(0);  // log2(num_partitions = 1), fri/src/proof.rs:50-52
+    if (!out_bytes || *len < bytes.size()) {
+        *len = bytes.size();
+        CTX_FAIL(ctx, AERO_ERR_BUFFER, "FRI proof needs %zu bytes", bytes.size());
+    }
+    memcpy(out_bytes, bytes.data(), bytes.size());
+    *len = bytes.size();
+    return AERO_OK;
+}
 
 // -------------------------------------------------------------------------------------------------
 // extern "C"
@@ -811,6 +1018,8 @@ void aero_ctx_destroy(aero_ctx *ctx) {
     cache_release_all(ctx);
     for (auto &kv : ctx->live_blocks) cudaFree(kv.first);  // handles the caller forgot to destroy
     for (void *p : ctx->owned) cudaFree(p);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
     delete ctx;
 }
 const char *aero_last_error(aero_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -838,6 +1047,7 @@ aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value)
     else if (k == "hash_blocks_per_sm" && value > 0) ctx->hash_blocks_per_sm = (int)value;
     else if (k == "lde_batch_bytes" && value > 0) ctx->lde_batch_bytes = (size_t)value;
     else if (k == "ntt_table_max_bytes" && value >= 0) ctx->ntt_table_max_bytes = (size_t)value;
+    else if (k == "upload_batch_cols" && value >= 1 && value <= 255) ctx->upload_batch_cols = (int)value;
     else CTX_FAIL(ctx, AERO_ERR_INVALID, "unknown option '%s'", key);
     return AERO_OK;
 }
@@ -1008,7 +1218,7 @@ aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint
     // Uploads run on a second stream in column batches; batch b's transforms wait only for batch b,
     // so the PCIe copy of later columns hides behind the NTTs of earlier ones.
     if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    int batch = (int)std::max<uint32_t>(1, std::min<uint32_t>(8, (n_cols + 2) / 3));
+    int batch = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->upload_batch_cols, (n_cols + 2) / 3));
     if (batch > 1 && (batch & 1)) batch++;  // even batches: each one's row hash can start as soon as it is extended
     const int nb = ((int)n_cols + batch - 1) / batch;
     std::vector<cudaEvent_t> ev(nb + 1);
@@ -1199,36 +1409,43 @@ aero_status aero_segment_download_leaves(aero_segment *seg, uint8_t *leaves_out)
 aero_status aero_segment_open(aero_segment *seg, const uint64_t *positions, uint32_t n_pos, uint64_t *rows_out,
                               uint8_t *batch_nodes_out, size_t *len) {
     if (!seg || !positions || !len) return AERO_ERR_INVALID;
-    aero_ctx *ctx = seg->ctx;
-    if (!seg->full) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no commitment");
-    if (seg->tree_pending) CTX_FAIL(ctx, AERO_ERR_STATE, "sharded segment: exchange leaves and call aero_segment_finish_tree first");
-    const uint64_t N = seg->N();
-    std::vector<std::vector<uint32_t>> idx;
-    TRY(batch_proof_indices(ctx, positions, n_pos, N, idx));
-    std::vector<uint8_t> bytes;
-    TRY(fetch_batch_proof(ctx, seg->full, idx, bytes));
-    if (!batch_nodes_out || *len < bytes.size()) {
-        *len = bytes.size();
-        CTX_FAIL(ctx, AERO_ERR_BUFFER, "batch proof needs %zu bytes", bytes.size());
+    GatherBatch gb(seg->ctx);
+    SegmentOpening o;
+    TRY(segment_open_plan(seg, positions, n_pos, rows_out != nullptr, gb, o));
+    TRY(gb.run());
+    return segment_open_finish(o, gb, rows_out, batch_nodes_out, len);
+}
+
+aero_status aero_open_queries(aero_ctx *ctx, aero_fri *fri, aero_segment *const *segs, uint32_t n_segs,
+                              const uint64_t *positions, uint32_t n_pos, uint8_t *fri_proof_bytes, size_t *fri_len,
+                              uint64_t *const *rows_out, uint8_t *const *batch_nodes_out, size_t *batch_len) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (!positions || (fri && !fri_len) || (n_segs && (!segs || !rows_out || !batch_nodes_out || !batch_len)))
+        CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    GatherBatch gb(ctx);
+    FriOpening fo;
+    std::vector<SegmentOpening> so(n_segs);
+    if (fri) {
+        if (fri->ctx != ctx) CTX_FAIL(ctx, AERO_ERR_INVALID, "FRI handle belongs to another context");
+        TRY(fri_open_plan(fri, positions, n_pos, gb, fo));
     }
-    memcpy(batch_nodes_out, bytes.data(), bytes.size());
-    *len = bytes.size();
-    if (rows_out) {
-        std::vector<uint32_t> pos(n_pos);
-        for (uint32_t i = 0; i < n_pos; i++) pos[i] = (uint32_t)positions[i];
-        uint32_t *d_pos = nullptr;
-        uint64_t *d_rows = nullptr;
-        TRY(dev_alloc(ctx, (void **)&d_pos, n_pos * 4));
-        TRY(dev_alloc(ctx, (void **)&d_rows, (size_t)n_pos * seg->ncols * 8));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_pos, pos.data(), n_pos * 4, cudaMemcpyHostToDevice, ctx->stream));
-        gather_rows(seg->lde, seg->lde_stride(), seg->ncols, seg->logn, seg->log_blowup, seg->coset_begin,
-                    seg->coset_count, d_pos, (int)n_pos, d_rows, ctx->stream);
-        CUDA_TRY(ctx, cudaMemcpyAsync(rows_out, d_rows, (size_t)n_pos * seg->ncols * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        dev_free(ctx, d_pos);
-        dev_free(ctx, d_rows);
+    for (uint32_t i = 0; i < n_segs; i++) {
+        if (!segs[i] || segs[i]->ctx != ctx) CTX_FAIL(ctx, AERO_ERR_INVALID, "segment %u is null or belongs to another context", i);
+        TRY(segment_open_plan(segs[i], positions, n_pos, true, gb, so[i]));
     }
-    return AERO_OK;
+    TRY(gb.run());
+    aero_status worst = AERO_OK;  // report every required size before failing with AERO_ERR_BUFFER
+    if (fri) {
+        aero_status st = fri_open_finish(fo, gb, fri_proof_bytes, fri_len);
+        if (st != AERO_OK && st != AERO_ERR_BUFFER) return st;
+        if (st != AERO_OK) worst = st;
+    }
+    for (uint32_t i = 0; i < n_segs; i++) {
+        aero_status st = segment_open_finish(so[i], gb, rows_out[i], batch_nodes_out[i], &batch_len[i]);
+        if (st != AERO_OK && st != AERO_ERR_BUFFER) return st;
+        if (st != AERO_OK) worst = st;
+    }
+    return worst;
 }
 
 aero_status aero_commit_rows_device(aero_ctx *ctx, const uint64_t *d_m, size_t col_stride, uint32_t n_cols,
@@ -1429,13 +1646,22 @@ aero_status aero_constraints_into_poly(aero_ctx *ctx, const uint64_t *const *eva
 }
 
 // ---- OOD + DEEP -----------------------------------------------------------------------------
-static aero_status ood_one(aero_ctx *ctx, aero_segment *seg, const std::vector<uint64_t> &points, uint64_t *host_out /* npoints x ncols */) {
+// Queues the evaluation of every column of `seg` at `points`; the results (ncols x npoints, column
+// major) are copied to h_stage + host_off.  Nothing is synchronised here.
+struct OodJob {
+    aero_segment *seg = nullptr;
+    int np = 0;
+    uint64_t *d_tab = nullptr, *d_out = nullptr, *d_scr = nullptr;
+    size_t host_off = 0;
+};
+static aero_status ood_enqueue(aero_ctx *ctx, aero_segment *seg, const std::vector<uint64_t> &points, size_t host_off,
+                               OodJob &job) {
     const int logn = seg->logn;
     const int np = (int)points.size();
     const uint64_t n = seg->n();
     const int chunk_len = n < 4096 ? (int)n : 4096;
     const int nchunks = (int)(n / chunk_len);
-    const int stride = 257 + nchunks;
+    const int stride = 257 + nchunks + 16;  // layout: see ood_partial_kernel
     std::vector<uint64_t> tab((size_t)np * stride);
     for (int p = 0; p < np; p++) {
         uint64_t *t = tab.data() + (size_t)p * stride;
@@ -1450,55 +1676,80 @@ static aero_status ood_one(aero_ctx *ctx, aero_segment *seg, const std::vector<u
             t[257 + c] = x;
             x = gl::mul(x, xc);
         }
+        x = 1;
+        for (int l = 0; l < 16; l++) {
+            t[257 + nchunks + l] = x;
+            x = gl::mul(x, t[256]);
+        }
     }
-    uint64_t *d_tab = nullptr, *d_out = nullptr, *d_scr = nullptr;
-    TRY(dev_alloc(ctx, (void **)&d_tab, tab.size() * 8));
-    TRY(dev_alloc(ctx, (void **)&d_out, (size_t)seg->ncols * np * 8));
-    TRY(dev_alloc(ctx, (void **)&d_scr, ood_scratch_elems(seg->ncols, logn, np) * 8));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    ood_eval(seg->polys, n, seg->ncols, logn, d_tab, np, d_out, d_scr, ctx->stream);
-    std::vector<uint64_t> res((size_t)seg->ncols * np);
-    CUDA_TRY(ctx, cudaMemcpyAsync(res.data(), d_out, res.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int c = 0; c < seg->ncols; c++)
-        for (int p = 0; p < np; p++) host_out[(size_t)p * seg->ncols + c] = res[(size_t)c * np + p];
-    dev_free(ctx, d_tab);
-    dev_free(ctx, d_out);
-    dev_free(ctx, d_scr);
+    job.seg = seg;
+    job.np = np;
+    job.host_off = host_off;
+    TRY(dev_alloc(ctx, (void **)&job.d_tab, tab.size() * 8));
+    TRY(dev_alloc(ctx, (void **)&job.d_out, (size_t)seg->ncols * np * 8));
+    TRY(dev_alloc(ctx, (void **)&job.d_scr, ood_scratch_elems(seg->ncols, logn, np) * 8));
+    // pageable source: the runtime stages it before returning, so `tab` may go out of scope
+    CUDA_TRY(ctx, cudaMemcpyAsync(job.d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ood_eval(seg->polys, n, seg->ncols, logn, job.d_tab, np, job.d_out, job.d_scr, ctx->stream);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage + host_off, job.d_out, (size_t)seg->ncols * np * 8, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
     return AERO_OK;
+}
+static void ood_release(aero_ctx *ctx, OodJob &job) {
+    dev_free(ctx, job.d_tab);
+    dev_free(ctx, job.d_out);
+    dev_free(ctx, job.d_scr);
+    job.d_tab = job.d_out = job.d_scr = nullptr;
 }
 
 aero_status aero_ood_eval(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs, aero_segment *comp,
                           uint64_t z, uint64_t *out_trace, uint64_t *out_comp) {
     if (!ctx) return AERO_ERR_INVALID;
     if (n_trace_segs && (!trace_segs || !out_trace)) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (comp && !out_comp) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     PhaseTimer t(ctx, "ood_eval");
     const uint64_t zc = to_canon(ctx, z);
+    int W = 0;
+    for (uint32_t s = 0; s < n_trace_segs; s++) {
+        if (!trace_segs[s] || trace_segs[s]->logn != trace_segs[0]->logn) CTX_FAIL(ctx, AERO_ERR_INVALID, "trace segments must have equal length");
+        W += trace_segs[s]->ncols;
+    }
+    // all segments are queued before the one synchronisation
+    TRY(stage_reserve(ctx, ((size_t)2 * W + (comp ? comp->ncols : 0)) * 8));
+    std::vector<OodJob> jobs(n_trace_segs + (comp ? 1 : 0));
+    size_t off = 0;
+    aero_status st = AERO_OK;
     if (n_trace_segs) {
-        int W = 0;
-        for (uint32_t s = 0; s < n_trace_segs; s++) {
-            if (!trace_segs[s] || trace_segs[s]->logn != trace_segs[0]->logn) CTX_FAIL(ctx, AERO_ERR_INVALID, "trace segments must have equal length");
-            W += trace_segs[s]->ncols;
-        }
         const uint64_t g = gl::root_of_unity(trace_segs[0]->logn);
-        std::vector<uint64_t> pts = {zc, gl::mul(zc, g)};
-        int off = 0;
-        for (uint32_t s = 0; s < n_trace_segs; s++) {
-            std::vector<uint64_t> tmp((size_t)2 * trace_segs[s]->ncols);
-            TRY(ood_one(ctx, trace_segs[s], pts, tmp.data()));
-            for (int c = 0; c < trace_segs[s]->ncols; c++) {
-                out_trace[off + c] = from_canon(ctx, tmp[c]);
-                out_trace[W + off + c] = from_canon(ctx, tmp[trace_segs[s]->ncols + c]);
-            }
-            off += trace_segs[s]->ncols;
+        const std::vector<uint64_t> pts = {zc, gl::mul(zc, g)};
+        for (uint32_t s = 0; s < n_trace_segs && st == AERO_OK; s++) {
+            st = ood_enqueue(ctx, trace_segs[s], pts, off, jobs[s]);
+            off += (size_t)2 * trace_segs[s]->ncols * 8;
         }
     }
+    if (comp && st == AERO_OK) {
+        const std::vector<uint64_t> pts = {gl::pow(zc, (uint64_t)comp->ncols)};
+        st = ood_enqueue(ctx, comp, pts, off, jobs[n_trace_segs]);
+    }
+    if (st == AERO_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        ctx->err = "aero_ood_eval: stream synchronisation failed";
+        st = AERO_ERR_CUDA;
+    }
+    for (auto &j : jobs) ood_release(ctx, j);
+    if (st != AERO_OK) return st;
+    int c0 = 0;
+    for (uint32_t s = 0; s < n_trace_segs; s++) {
+        const uint64_t *res = (const uint64_t *)(ctx->h_stage + jobs[s].host_off);  // [col][point]
+        const int nc = trace_segs[s]->ncols;
+        for (int c = 0; c < nc; c++) {
+            out_trace[c0 + c] = from_canon(ctx, res[(size_t)c * 2]);
+            out_trace[W + c0 + c] = from_canon(ctx, res[(size_t)c * 2 + 1]);
+        }
+        c0 += nc;
+    }
     if (comp) {
-        if (!out_comp) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
-        std::vector<uint64_t> pts = {gl::pow(zc, (uint64_t)comp->ncols)};
-        std::vector<uint64_t> tmp(comp->ncols);
-        TRY(ood_one(ctx, comp, pts, tmp.data()));
-        for (int c = 0; c < comp->ncols; c++) out_comp[c] = from_canon(ctx, tmp[c]);
+        const uint64_t *res = (const uint64_t *)(ctx->h_stage + jobs[n_trace_segs].host_off);
+        for (int c = 0; c < comp->ncols; c++) out_comp[c] = from_canon(ctx, res[c]);
     }
     return AERO_OK;
 }
@@ -1730,79 +1981,13 @@ aero_status aero_fri_fold(aero_fri *fri, uint64_t alpha) {
     return AERO_OK;
 }
 
-// fold_positions (fri/src/folding/mod.rs:159-176)
-static std::vector<uint64_t> fold_positions(const std::vector<uint64_t> &pos, uint64_t source, uint64_t ff) {
-    const uint64_t target = source / ff;
-    std::vector<uint64_t> r;
-    for (uint64_t p : pos) {
-        p %= target;
-        if (std::find(r.begin(), r.end(), p) == r.end()) r.push_back(p);
-    }
-    return r;
-}
-
 aero_status aero_fri_open(aero_fri *fri, const uint64_t *positions, uint32_t n_pos, uint8_t *out_bytes, size_t *len) {
     if (!fri || !positions || !len) return AERO_ERR_INVALID;
-    aero_ctx *ctx = fri->ctx;
-    if (fri->layers.empty()) CTX_FAIL(ctx, AERO_ERR_STATE, "FRI layers have not been built yet");  // prover/mod.rs:232-235
-    if (n_pos == 0 || n_pos > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of positions must be 1..255");
-    std::vector<uint64_t> pos(positions, positions + n_pos);
-    for (uint64_t p : pos)
-        if (p >= fri->layers[0].M) CTX_FAIL(ctx, AERO_ERR_INVALID, "query position out of range");
-    std::vector<uint8_t> bytes;
-    const size_t nl = fri->layers.size() - 1;
-    bytes.push_back((uint8_t)nl);
-    uint64_t domain = fri->layers[0].M;
-    for (size_t i = 0; i < nl; i++) {
-        const FriLayerDev &L = fri->layers[i];
-        pos = fold_positions(pos, domain, 8);
-        const uint32_t rows = L.M / 8;
-        // queried values: [E; 8] rows at the folded positions, canonical bytes
-        std::vector<uint32_t> p32(pos.begin(), pos.end());
-        uint32_t *d_pos = nullptr;
-        uint64_t *d_vals = nullptr;
-        TRY(dev_alloc(ctx, (void **)&d_pos, p32.size() * 4));
-        TRY(dev_alloc(ctx, (void **)&d_vals, p32.size() * 64));
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_pos, p32.data(), p32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-        gather_fri_rows(L.evals, rows, L.log_cosets, d_pos, (int)p32.size(), d_vals, ctx->stream);
-        std::vector<uint64_t> vals(p32.size() * 8);
-        CUDA_TRY(ctx, cudaMemcpyAsync(vals.data(), d_vals, vals.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        dev_free(ctx, d_pos);
-        dev_free(ctx, d_vals);
-        std::vector<std::vector<uint32_t>> idx;
-        TRY(batch_proof_indices(ctx, pos.data(), (uint32_t)pos.size(), rows, idx));
-        std::vector<uint8_t> paths;
-        TRY(fetch_batch_proof(ctx, L.full, idx, paths));
-        // FriProofLayer::write_into (fri/src/proof.rs:351-359)
-        const uint32_t vlen = (uint32_t)(vals.size() * 8), plen = (uint32_t)paths.size();
-        bytes.insert(bytes.end(), (uint8_t *)&vlen, (uint8_t *)&vlen + 4);
-        bytes.insert(bytes.end(), (uint8_t *)vals.data(), (uint8_t *)vals.data() + vlen);
-        bytes.insert(bytes.end(), (uint8_t *)&plen, (uint8_t *)&plen + 4);
-        bytes.insert(bytes.end(), paths.begin(), paths.end());
-        domain /= 8;
-    }
-    {
-        // remainder = last committed layer in natural order (prover/mod.rs:258-268 un-transposes
-        // the stored transposed copy; ours is stored natural already)
-        const FriLayerDev &L = fri->layers.back();
-        if (L.log_cosets) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "remainder layer cannot be the DEEP layer");
-        if ((size_t)L.M * 8 > 0xFFFF) CTX_FAIL(ctx, AERO_ERR_INVALID, "remainder too large for the wire format");
-        std::vector<uint64_t> rem(L.M);
-        CUDA_TRY(ctx, cudaMemcpyAsync(rem.data(), L.evals, (size_t)L.M * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        const uint16_t rl = (uint16_t)(L.M * 8);
-        bytes.insert(bytes.end(), (uint8_t *)&rl, (uint8_t *)&rl + 2);
-        bytes.insert(bytes.end(), (uint8_t *)rem.data(), (uint8_t *)rem.data() + rl);
-        bytes.push_back(0);  // log2(num_partitions = 1), fri/src/proof.rs:50-52
-    }
-    if (!out_bytes || *len < bytes.size()) {
-        *len = bytes.size();
-        CTX_FAIL(ctx, AERO_ERR_BUFFER, "FRI proof needs %zu bytes", bytes.size());
-    }
-    memcpy(out_bytes, bytes.data(), bytes.size());
-    *len = bytes.size();
-    return AERO_OK;
+    GatherBatch gb(fri->ctx);
+    FriOpening o;
+    TRY(fri_open_plan(fri, positions, n_pos, gb, o));
+    TRY(gb.run());
+    return fri_open_finish(o, gb, out_bytes, len);
 }
 
 void aero_fri_destroy(aero_fri *fri) {

@@ -1,5 +1,6 @@
 // Goldilocks NTT kernels for sm_100a: shared-memory DIT transforms with register radix-8 rounds,
 // four-step two-pass decomposition for n > 2^11.  See ntt.cuh for the mapping to the reference.
+#include <cstdlib>
 #include <type_traits>
 
 #include "gl.cuh"
@@ -362,7 +363,13 @@ int dft_tile_width(int log1, int log2) {
     // tile width T: 2^10-point passes with T = 8 and 2^11-point passes with T = 4 both leave room for
     // two blocks per SM (82 / 96 KB each); measured 4.2e11 butterflies/s either way, against 3.0e11
     // with one 512-thread block per SM
-    return (log1 > log2 ? log1 : log2) <= 10 ? 8 : 4;
+    static const int forced = [] {  // experiment hook: AERO_NTT_TILE=4|8 forces the width for passes <= 2^10 points
+        const char *e = getenv("AERO_NTT_TILE");
+        return e ? atoi(e) : 0;
+    }();
+    const int big = log1 > log2 ? log1 : log2;
+    if (big <= 10 && (forced == 4 || forced == 8)) return forced;
+    return big <= 10 ? 8 : 4;
 }
 
 void dft_fill_inter_table(const DftTables &t, uint64_t *out, cudaStream_t s) {

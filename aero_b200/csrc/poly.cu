@@ -155,7 +155,8 @@ __device__ __forceinline__ uint64_t block_sum(uint64_t v, uint64_t *sm /* >= 32 
 // (math/src/polynom/mod.rs:53-62); here sum_j p[j] x^j is split into chunks of CH coefficients:
 // thread t takes j = j0 + t + 256*l (coalesced), Horner in x^256, times x^t, block-reduced, times
 // x^j0; a second tiny kernel adds the chunk partials.
-// d_tab layout per point p (stride tab_stride): [0..255] x^t ; [256] x^256 ; [257 + chunk] x^(chunk*CH)
+// d_tab layout per point p (stride tab_stride): [0..255] x^t ; [256] x^256 ; [257 + chunk] x^(chunk*CH) ;
+// [257 + nchunks + l] x^(256 l), l < 16
 // ---------------------------------------------------------------------------------------------
 constexpr int OOD_THREADS = 256;
 constexpr int OOD_L = 16;
@@ -173,11 +174,11 @@ __global__ void __launch_bounds__(OOD_THREADS) ood_partial_kernel(const uint64_t
     for (int l = 0; l < OOD_L; l++) c[l] = (l < L && t + OOD_THREADS * l < chunk_len) ? __ldg(p + t + OOD_THREADS * l) : 0ULL;
     for (int pt = 0; pt < npoints; pt++) {
         const uint64_t *tab = d_tab + (size_t)pt * tab_stride;
-        const uint64_t x256 = tab[256];
-        uint64_t acc = 0;
+        const uint64_t *xp = tab + 257 + nchunks;  // x^(256 l), l < OOD_L
+        gl::Acc160 dot;                            // sum_l c[l] x^(256 l), reduced once
 #pragma unroll
-        for (int l = OOD_L - 1; l >= 0; l--) acc = gl::add(gl::mul(acc, x256), c[l]);
-        acc = gl::mul(acc, tab[t]);
+        for (int l = 0; l < OOD_L; l++) dot.mac(c[l], __ldg(xp + l));
+        uint64_t acc = gl::mul(dot.reduce(), tab[t]);
         acc = block_sum(acc, sm);
         if (t == 0) partial[((size_t)col * npoints + pt) * nchunks + chunk] = gl::mul(acc, tab[257 + chunk]);
     }
@@ -203,7 +204,7 @@ void ood_eval(const uint64_t *polys, size_t col_stride, int ncols, int logn, con
               uint64_t *d_out, uint64_t *d_scratch, cudaStream_t s) {
     const int chunk_len = ood_chunk_len(logn);
     const int nchunks = (1 << logn) / chunk_len;
-    const int tab_stride = 257 + nchunks;
+    const int tab_stride = 257 + nchunks + OOD_L;
     dim3 g(nchunks, ncols);
     AERO_COUNT_LAUNCH(2);
     ood_partial_kernel<<<g, OOD_THREADS, 0, s>>>(polys, col_stride, logn, d_tab, tab_stride, npoints, chunk_len,
@@ -228,17 +229,20 @@ __global__ void __launch_bounds__(256) deep_accumulate_kernel(DeepSegs segs, con
                                                               uint64_t *__restrict__ h) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    uint64_t a1 = 0, a2 = 0, ah = 0;
+    // three dot products over the columns, reduced once each (gl::Acc160)
+    gl::Acc160 s1, s2, sh;
     int i = 0;  // running trace-column index across segments (composer/mod.rs:96-99)
     for (int s = 0; s < segs.nseg; s++) {
         const uint64_t *tp = segs.p[s] + j;
+#pragma unroll 4
         for (int c = 0; c < segs.ncols[s]; c++, i++) {
             const uint64_t v = __ldg(tp + (size_t)c * n);
-            a1 = gl::add(a1, gl::mul(v, __ldg(cc + 2 * i)));
-            a2 = gl::add(a2, gl::mul(v, __ldg(cc + 2 * i + 1)));
+            s1.mac(v, __ldg(cc + 2 * i));
+            s2.mac(v, __ldg(cc + 2 * i + 1));
         }
     }
-    for (int c = 0; c < m; c++) ah = gl::add(ah, gl::mul(__ldg(cp + (size_t)c * n + j), __ldg(cc + 2 * i + c)));
+    for (int c = 0; c < m; c++) sh.mac(__ldg(cp + (size_t)c * n + j), __ldg(cc + 2 * i + c));
+    uint64_t a1 = s1.reduce(), a2 = s2.reduce(), ah = sh.reduce();
     if (j == 0) {
         a1 = gl::sub(a1, consts[0]);
         a2 = gl::sub(a2, consts[1]);

@@ -277,23 +277,6 @@ static aero_status finish_commit(aero_ctx *ctx, const aero_prove_inputs &in, aer
     return AERO_OK;
 }
 
-// build_segment_queries (prover/src/trace/commitment.rs:115-140)
-static aero_status query_segment(aero_ctx *ctx, const aero_prove_inputs &in, aero_segment *seg,
-                                 const std::vector<uint64_t> &positions, uint32_t width, Queries *q, std::string *err) {
-    std::vector<uint64_t> rows(positions.size() * width);
-    std::vector<uint8_t> paths(1 + positions.size() * (1 + 32 * 40));
-    size_t len = paths.size();
-    P_TRY(aero_segment_open(seg, positions.data(), (uint32_t)positions.size(), rows.data(), paths.data(), &len));
-    if (in.sum_rows) {
-        aero_status st = in.sum_rows(in.user, rows.data(), rows.size());
-        if (st != AERO_OK) P_FAIL(st, "sum_rows callback failed");
-    }
-    paths.resize(len);
-    q->values.assign((uint8_t *)rows.data(), (uint8_t *)rows.data() + rows.size() * 8);
-    q->paths = std::move(paths);
-    return AERO_OK;
-}
-
 aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_t> *proof_bytes, std::string *err) {
     const aero_proof_options &o = in.options;
     if (o.hash_fn != 4) P_FAIL(AERO_ERR_UNSUPPORTED, "only Blake2s_256 (hash_fn = 4) is supported");
@@ -453,15 +436,54 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     if (!channel.get_query_positions(&positions)) P_FAIL(AERO_ERR_STATE, "failed to draw query positions");
 
     // 8 ----- proof object (lib.rs:518-539)
-    std::vector<uint8_t> fri_bytes(1 << 20);
+    // FriProver::build_proof + build_segment_queries (prover/src/trace/commitment.rs:115-140) for every
+    // segment: one batched gather, one host round trip
+    std::vector<aero_segment *> open_segs = trace_segs;
+    open_segs.push_back(comp_seg);
+    std::vector<uint32_t> widths = {in.main_width};
+    if (aux_seg) widths.push_back(in.aux_width);
+    widths.push_back(m);
+    const size_t ns = open_segs.size(), np = positions.size();
+    std::vector<std::vector<uint64_t>> rows(ns);
+    std::vector<std::vector<uint8_t>> paths(ns);
+    std::vector<uint64_t *> rows_ptr(ns);
+    std::vector<uint8_t *> paths_ptr(ns);
+    std::vector<size_t> paths_len(ns);
+    for (size_t i = 0; i < ns; i++) {
+        rows[i].resize(np * widths[i]);
+        paths[i].resize(1 + np * (1 + 32 * 40));
+        rows_ptr[i] = rows[i].data();
+        paths_ptr[i] = paths[i].data();
+        paths_len[i] = paths[i].size();
+    }
+    std::vector<uint8_t> fri_bytes(256 << 10);
     size_t flen = fri_bytes.size();
-    P_TRY(aero_fri_open(H.fri, positions.data(), (uint32_t)positions.size(), fri_bytes.data(), &flen));
+    aero_status ost = aero_open_queries(ctx, H.fri, open_segs.data(), (uint32_t)ns, positions.data(), (uint32_t)np,
+                                        fri_bytes.data(), &flen, rows_ptr.data(), paths_ptr.data(), paths_len.data());
+    if (ost == AERO_ERR_BUFFER) {  // sizes were reported: grow and repeat
+        fri_bytes.resize(flen);
+        for (size_t i = 0; i < ns; i++) {
+            paths[i].resize(paths_len[i]);
+            paths_ptr[i] = paths[i].data();
+        }
+        ost = aero_open_queries(ctx, H.fri, open_segs.data(), (uint32_t)ns, positions.data(), (uint32_t)np, fri_bytes.data(),
+                                &flen, rows_ptr.data(), paths_ptr.data(), paths_len.data());
+    }
+    P_TRY(ost);
     fri_bytes.resize(flen);
-    std::vector<Queries> tq(trace_segs.size());
-    P_TRY(query_segment(ctx, in, main_seg, positions, in.main_width, &tq[0], err));
-    if (aux_seg) P_TRY(query_segment(ctx, in, aux_seg, positions, in.aux_width, &tq[1], err));
-    Queries cq;
-    P_TRY(query_segment(ctx, in, comp_seg, positions, m, &cq, err));
+    std::vector<Queries> all_q(ns);
+    for (size_t i = 0; i < ns; i++) {
+        if (in.sum_rows) {  // coset-sharded proof: rows of other ranks come back as zeros
+            aero_status st = in.sum_rows(in.user, rows[i].data(), rows[i].size());
+            if (st != AERO_OK) P_FAIL(st, "sum_rows callback failed");
+        }
+        paths[i].resize(paths_len[i]);
+        all_q[i].values.assign((uint8_t *)rows[i].data(), (uint8_t *)rows[i].data() + rows[i].size() * 8);
+        all_q[i].paths = std::move(paths[i]);
+    }
+    Queries cq = std::move(all_q.back());
+    all_q.pop_back();
+    std::vector<Queries> tq = std::move(all_q);
     *proof_bytes = channel.build_proof(std::move(tq), std::move(cq), std::move(fri_bytes)).to_bytes();
     return AERO_OK;
 }

@@ -70,6 +70,7 @@ class Context:
             raise AeroError(st, "aero_ctx_create failed (no usable sm_100 CUDA device; there is no CPU fallback)")
         self.h = h
         self.form = form
+        self._proof_buf = (c_uint8 * (1 << 20))()
         self._check(self.lib.aero_ctx_set_form(self.h, form))
 
     def close(self) -> None:
@@ -191,6 +192,27 @@ class Context:
         return nonce.value
 
     # ---- whole proof ---------------------------------------------------------------------------
+    def open_queries(self, fri, segments, positions: Sequence[int]):
+        """The query phase in one host round trip (aero_open_queries): FriProver::build_proof bytes (None
+        when ``fri`` is None) and, per segment, (rows canonical, serialize_nodes bytes)."""
+        pos = np.array(list(positions), np.uint64)
+        ns = len(segments)
+        segs = (c_void_p * max(ns, 1))(*[s.h for s in segments])
+        rows = [np.empty((len(pos), s.n_cols), np.uint64) for s in segments]
+        caps = [2 + len(pos) * (1 + 32 * 64) for _ in segments]
+        bufs = [(c_uint8 * c)() for c in caps]
+        rows_p = (p_u64 * max(ns, 1))(*[r.ctypes.data_as(p_u64) for r in rows])
+        bufs_p = (p_u8 * max(ns, 1))(*[ctypes.cast(b, p_u8) for b in bufs])
+        lens = (c_size_t * max(ns, 1))(*caps)
+        fcap = 1 << 20
+        fbuf = (c_uint8 * fcap)()
+        flen = c_size_t(fcap)
+        self._check(self.lib.aero_open_queries(self.h, fri.h if fri is not None else None, segs, ns,
+                                               pos.ctypes.data_as(p_u64), len(pos), fbuf, ctypes.byref(flen),
+                                               rows_p, bufs_p, lens))
+        fri_bytes = ctypes.string_at(fbuf, flen.value) if fri is not None else None
+        return fri_bytes, [(rows[i], ctypes.string_at(bufs[i], lens[i])) for i in range(ns)]
+
     def prove(self, main_trace, aux_trace, ce_cols, divisors: Sequence[Divisor], pub_inputs_bytes: bytes,
               options: Optional[ProofOptions] = None, aux_rands: int = 16, n_constraint_coeffs: int = 0,
               on_device: Optional[dict] = None, shard=None) -> bytes:
@@ -243,16 +265,16 @@ class Context:
         pub = (c_uint8 * len(pub_inputs_bytes)).from_buffer_copy(pub_inputs_bytes)
         inp.pub_inputs_bytes = pub
         inp.pub_inputs_len = len(pub_inputs_bytes)
-        cap = 1 << 20
         while True:
-            buf = (c_uint8 * cap)()
+            buf = self._proof_buf  # reused across proofs (a c_uint8 slice would build a list of ints)
+            cap = len(buf)
             ln = c_size_t(cap)
             st = self.lib.aero_prove(self.h, ctypes.byref(inp), buf, ctypes.byref(ln))
             if st == AERO_ERR_BUFFER and ln.value > cap:
-                cap = ln.value
+                self._proof_buf = (c_uint8 * ln.value)()
                 continue
             self._check(st)
-            return bytes(buf[: ln.value])
+            return ctypes.string_at(buf, ln.value)
 
 
 class Segment:
@@ -296,7 +318,7 @@ class Segment:
         ln = c_size_t(cap)
         self.ctx._check(self.ctx.lib.aero_segment_open(self.h, pos.ctypes.data_as(p_u64), len(pos),
                                                        rows.ctypes.data_as(p_u64), buf, ctypes.byref(ln)))
-        return rows, bytes(buf[: ln.value])
+        return rows, ctypes.string_at(buf, ln.value)
 
     def destroy(self) -> None:
         if self.h:
@@ -338,7 +360,7 @@ class FriProver:
         buf = (c_uint8 * cap)()
         ln = c_size_t(cap)
         self.ctx._check(self.ctx.lib.aero_fri_open(self.h, pos.ctypes.data_as(p_u64), len(pos), buf, ctypes.byref(ln)))
-        return bytes(buf[: ln.value])
+        return ctypes.string_at(buf, ln.value)
 
     def destroy(self) -> None:
         if self.h:

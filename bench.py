@@ -212,6 +212,8 @@ def run_aero(args) -> None:
         ctx.set_option("hash_blocks_per_sm", args.hash_blocks_per_sm)
     if args.lde_batch_mb:
         ctx.set_option("lde_batch_bytes", args.lde_batch_mb << 20)
+    if args.upload_batch_cols:
+        ctx.set_option("upload_batch_cols", args.upload_batch_cols)
     if args.ntt_table_mb >= 0:
         ctx.set_option("ntt_table_max_bytes", args.ntt_table_mb << 20)
 
@@ -372,6 +374,7 @@ def main() -> None:
                     help="1: row hashing of column batch k runs on a second stream beside the LDE of batch k+1")
     ap.add_argument("--hash-blocks-per-sm", type=int, default=0)
     ap.add_argument("--lde-batch-mb", type=int, default=0, help="NTT scratch budget per column batch (MiB); 0 = default")
+    ap.add_argument("--upload-batch-cols", type=int, default=0, help="columns per host->device copy batch (0 = default 8)")
     ap.add_argument("--ntt-table-mb", type=int, default=-1,
                     help="largest full inter-pass NTT twiddle table per plan (MiB); 0 = running products; -1 = default")
     ap.add_argument("--trace", default="", help="profiling aid: write a chrome trace of one device-input step and exit")

@@ -193,6 +193,14 @@ aero_status aero_fri_fold(aero_fri *fri, uint64_t alpha);
 aero_status aero_fri_open(aero_fri *fri, const uint64_t *positions, uint32_t n_pos, uint8_t *fri_proof_bytes,
                           size_t *len);
 void aero_fri_destroy(aero_fri *fri);
+/* The whole query phase of Prover::prove_after_constraint_eval (prover/src/lib.rs:518-539:
+ * fri_prover.build_proof, trace_commitment.query, constraint_commitment.query) in one call and ONE
+ * host round trip: aero_fri_open (fri may be NULL) plus aero_segment_open for each of `segs`, all at
+ * the same `positions`.  rows_out[i] / batch_nodes_out[i] / batch_len[i] are segment i's
+ * aero_segment_open arguments; on AERO_ERR_BUFFER every *len holds the size its buffer needs. */
+aero_status aero_open_queries(aero_ctx *ctx, aero_fri *fri, aero_segment *const *segs, uint32_t n_segs,
+                              const uint64_t *positions, uint32_t n_pos, uint8_t *fri_proof_bytes, size_t *fri_len,
+                              uint64_t *const *rows_out, uint8_t *const *batch_nodes_out, size_t *batch_len);
 
 /* ---- grinding ---------------------------------------------------------------------------------- */
 /* ProverChannel::grind_query_seed, serial build (prover/src/channel.rs:151-167): smallest nonce >= 1

@@ -270,6 +270,36 @@ def test_fri_layers_and_proof(ctx, oracle, logM):
     assert got == bytes(exp)
 
 
+def test_open_queries_equals_separate_openings(ctx, oracle):
+    """aero_open_queries = aero_fri_open + aero_segment_open per segment, batched into one host round
+    trip (prover/src/lib.rs:518-539); bytes must be identical to the separately checked entry points."""
+    n, M = 256, 2048
+    segs = [ctx.build_trace_commitment(oracle.synthetic_trace(w, n, 0x51 + w), 8) for w in (5, 2, 8)]
+    fri = ctx.fri_from_evaluations(oracle.synthetic_trace(1, M, 0xF2)[0])
+    coin = aero_b200.RandomCoin(b"oq")
+    nl = oracle.ProofOptions().num_fri_layers(M)
+    for l in range(nl + 1):
+        coin.reseed(fri.commit_layer())
+        alpha = coin.draw()
+        if l < nl:
+            fri.fold(alpha)
+    for positions in ([9], oracle.RandomCoin(b"q2").draw_integers(27, M), [2047, 0, 1024, 1, 1023]):
+        fri_bytes, opened = ctx.open_queries(fri, segs, positions)
+        assert fri_bytes == fri.open(positions)
+        for seg, (rows, paths) in zip(segs, opened):
+            r2, p2 = seg.open(positions)
+            assert np.array_equal(rows, r2) and paths == p2
+    # segments only / FRI only
+    _, opened = ctx.open_queries(None, segs[:1], [3, 4])
+    r2, p2 = segs[0].open([3, 4])
+    assert np.array_equal(opened[0][0], r2) and opened[0][1] == p2
+    fb, none = ctx.open_queries(fri, [], [3, 4])
+    assert fb == fri.open([3, 4]) and none == []
+    with pytest.raises(AeroError) as e:  # duplicate position: prove_batch's error, not a crash
+        ctx.open_queries(fri, segs, [5, 5])
+    assert e.value.status == aero_b200.AERO_ERR_INVALID
+
+
 def test_fri_state_errors(ctx, oracle):
     """FriProver panics when misused (fri/src/prover/mod.rs:167-170,232-235) -> AERO_ERR_STATE."""
     fri = ctx.fri_from_evaluations(oracle.synthetic_trace(1, 1024, 1)[0])
