@@ -75,6 +75,26 @@ def test_prove_split_route_byte_identical(ctx, oracle, logn, wm, wa):
     assert got == ref.proof_bytes
 
 
+def test_prove_2_16_rows_full_width_byte_identical(ctx, oracle):
+    """BASELINE.json configs[1]: a 2^16-row trace at the full Miden widths (72 main + 9 aux columns,
+    Miden 96-bit options): the proof bytes equal the restated reference prover's -- roots, OOD frame,
+    FRI layers, openings and grinding nonce included -- and the fib.bin-pinned verifier model accepts it."""
+    from aero_b200 import make_divisor
+
+    logn = 16
+    n = 1 << logn
+    main = oracle.synthetic_trace(72, n, 0xAE160000)
+    aux = oracle.synthetic_trace(9, n, 0xAE170000)
+    ce = oracle.synthetic_trace(2, 8 * n, 0xCE16)
+    divs = [oracle.Divisor(n, 1, [pow(oracle.root_of_unity(logn), n - 1, P)]), oracle.Divisor(1, 1, [])]
+    pub = b"2^16 rows, full width"
+    ref = oracle.prove(main, aux, ce, divs, pub)
+    got = ctx.prove(main, aux, ce, [make_divisor(d.a, d.b, d.exemptions) for d in divs], pub)
+    assert got == ref.proof_bytes
+    rep = oracle.verify(got, pub, 8)
+    assert len(rep.positions) == 27
+
+
 def test_prove_2_22_rows_accepted_by_verifier_model(ctx, oracle):
     """A 2^22-row proof (LDE domain 2^25, past the direct constraint interpolation): the verifier
     model pinned on the reference's fib.bin re-derives every coin, checks the three batch openings
