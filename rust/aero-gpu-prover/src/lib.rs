@@ -241,15 +241,32 @@ impl Prover for GpuExecutionProver {
         let positions = channel.get_query_positions();
         let pos64: Vec<u64> = positions.iter().map(|&p| p as u64).collect();
 
-        // FRI query phase (fri/src/prover/mod.rs:231-302): FriProof::write_into bytes from the GPU
-        let mut buf = vec![0u8; 1 << 22];
-        let mut len = buf.len();
-        check(ctx, unsafe { ffi::aero_fri_open(fri, pos64.as_ptr(), pos64.len() as u32, buf.as_mut_ptr(), &mut len) });
-        let fri_proof = FriProof::read_from(&mut SliceReader::new(&buf[..len])).expect("FRI proof bytes");
+        // query phase (prover/src/lib.rs:518-539): FriProver::build_proof bytes and the rows + batch
+        // Merkle proof of every segment in ONE host round trip (aero_open_queries)
+        let ns = segs.len();
+        let mut fri_buf = vec![0u8; 1 << 22];
+        let mut fri_len = fri_buf.len();
+        let mut rows: Vec<Vec<u64>> = segs.iter().map(|s| vec![0u64; pos64.len() * s.width]).collect();
+        let mut paths: Vec<Vec<u8>> = (0..ns).map(|_| vec![0u8; 2 + pos64.len() * (1 + 32 * 64)]).collect();
+        let mut path_len: Vec<usize> = paths.iter().map(|p| p.len()).collect();
+        let seg_h: Vec<*mut ffi::aero_segment> = segs.iter().map(|s| s.h).collect();
+        let rows_p: Vec<*mut u64> = rows.iter_mut().map(|r| r.as_mut_ptr()).collect();
+        let paths_p: Vec<*mut u8> = paths.iter_mut().map(|p| p.as_mut_ptr()).collect();
+        check(ctx, unsafe {
+            ffi::aero_open_queries(ctx, fri, seg_h.as_ptr(), ns as u32, pos64.as_ptr(), pos64.len() as u32, fri_buf.as_mut_ptr(),
+                                   &mut fri_len, rows_p.as_ptr(), paths_p.as_ptr(), path_len.as_mut_ptr())
+        });
+        let fri_proof = FriProof::read_from(&mut SliceReader::new(&fri_buf[..fri_len])).expect("FRI proof bytes");
         unsafe { ffi::aero_fri_destroy(fri) };
-
-        let trace_queries: Vec<Queries> = segs[..segs.len() - 1].iter().map(|s| s.query(&positions)).collect();
-        let constraint_queries = segs.last().unwrap().query(&positions);
+        let mut queries: Vec<Queries> = (0..ns)
+            .map(|i| {
+                paths[i].truncate(path_len[i]);
+                let values = rows[i].iter().flat_map(|v| v.to_le_bytes()).collect();
+                Queries::from_raw_parts(values, std::mem::take(&mut paths[i]))
+            })
+            .collect();
+        let constraint_queries = queries.pop().unwrap();
+        let trace_queries = queries;
         segs.clear();
         Ok(channel.build_proof(trace_queries, constraint_queries, fri_proof))
     }
