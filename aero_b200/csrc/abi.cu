@@ -639,10 +639,18 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
     aero_status st = dev_alloc(ctx, (void **)&seg->polys, (size_t)n_cols * n_rows * 8);
     if (st == AERO_OK && !input_is_coeffs) st = plan_intt(ctx, logn, mont, &iplan);
     if (st == AERO_OK) st = segment_alloc_lde(seg, ilog2(blowup), &lplan);
-    int batch = 0;
+    int batch = 0, ibatch = 0;
     if (st == AERO_OK) {
         batch = batch_cols > 0 ? std::min<int>(batch_cols, (int)n_cols) : segment_lde_batch_cols(seg);
-        if (iplan && iplan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp_i, (size_t)batch * n_rows * 8);
+        // Inputs already on the device: the inverse transforms of many LDE batches share one launch
+        // pair (a 16-column interpolation is only ~7 waves of blocks); uploads in flight keep the
+        // per-batch order so that batch b waits for ready[b] only.
+        ibatch = batch;
+        if (!ready && !input_is_coeffs) {
+            const size_t fit = ctx->lde_batch_bytes / ((size_t)n_rows * 8);
+            ibatch = (int)std::min<size_t>(n_cols, std::max<size_t>(batch, fit / batch * batch));
+        }
+        if (iplan && iplan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp_i, (size_t)ibatch * n_rows * 8);
     }
     if (st == AERO_OK && lplan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp_l, (size_t)batch * seg->lde_stride() * 8);
     if (st == AERO_OK) {
@@ -652,23 +660,23 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
         for (int c0 = 0, b = 0; c0 < (int)n_cols; c0 += batch, b++) {
             const int nc = std::min(batch, (int)n_cols - c0);
             if (ready) cudaStreamWaitEvent(ctx->stream, ready[b], 0);
-            const uint64_t *src = d_src + (size_t)c0 * src_stride;
-            uint64_t *dst = seg->polys + (size_t)c0 * n_rows;
             if (input_is_coeffs) {
+                const uint64_t *src = d_src + (size_t)c0 * src_stride;
+                uint64_t *dst = seg->polys + (size_t)c0 * n_rows;
                 PhaseTimer t(ctx, "convert");
                 for (int c = 0; c < nc; c++) {
                     if (mont) convert_form(src + (size_t)c * src_stride, dst + (size_t)c * n_rows, n_rows, 0, ctx->stream);
                     else cudaMemcpyAsync(dst + (size_t)c * n_rows, src + (size_t)c * src_stride, n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream);
                 }
-            } else {
+            } else if (c0 % ibatch == 0) {
                 PhaseTimer t(ctx, nm);
                 DftLaunch l;
-                l.src = src;
-                l.dst = dst;
+                l.src = d_src + (size_t)c0 * src_stride;
+                l.dst = seg->polys + (size_t)c0 * n_rows;
                 l.tmp = tmp_i;
                 l.src_col_stride = src_stride;
                 l.dst_col_stride = n_rows;
-                l.ncols = nc;
+                l.ncols = std::min(ibatch, (int)n_cols - c0);
                 l.deinterleave_log = 0;
                 dft_run(*iplan, l, ctx->stream);
             }
@@ -1924,8 +1932,8 @@ aero_status aero_fri_mark_complete(aero_fri *fri) {
     return AERO_OK;
 }
 
-aero_status aero_fri_commit_layer(aero_fri *fri, uint8_t root[32]) {
-    if (!fri || !root) return AERO_ERR_INVALID;
+// transpose_slice + hash_values + MerkleTree::new of the current evaluations, queued on the stream
+static aero_status fri_commit_enqueue(aero_fri *fri) {
     aero_ctx *ctx = fri->ctx;
     if (!fri->cur) CTX_FAIL(ctx, AERO_ERR_STATE, "no evaluations to commit");
     if (fri->cur_committed) CTX_FAIL(ctx, AERO_ERR_STATE, "layer already committed; fold first");
@@ -1946,14 +1954,10 @@ aero_status aero_fri_commit_layer(aero_fri *fri, uint8_t root[32]) {
     }
     fri->layers.push_back(L);
     fri->cur_committed = true;
-    CUDA_TRY(ctx, cudaMemcpyAsync(root, L.full + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    CUDA_TRY(ctx, cudaGetLastError());
     return AERO_OK;
 }
-
-aero_status aero_fri_fold(aero_fri *fri, uint64_t alpha) {
-    if (!fri) return AERO_ERR_INVALID;
+// apply_drp of the committed layer; the challenge comes by value or from device memory (alpha_dev)
+static aero_status fri_fold_enqueue(aero_fri *fri, uint64_t alpha_canon, const uint64_t *alpha_dev) {
     aero_ctx *ctx = fri->ctx;
     if (!fri->cur_committed) CTX_FAIL(ctx, AERO_ERR_STATE, "commit the layer before folding it");
     const uint32_t M = fri->curM, rows = M / 8;
@@ -1971,13 +1975,61 @@ aero_status aero_fri_fold(aero_fri *fri, uint64_t alpha) {
     TRY(dev_alloc(ctx, (void **)&next, (size_t)rows * 8));
     {
         PhaseTimer t(ctx, "fri_fold");
-        fri_fold(fri->cur, rows, fri->cur_log_cosets, to_canon(ctx, alpha), xinv, w, gl::inv(8), next, ctx->stream);
+        fri_fold(fri->cur, rows, fri->cur_log_cosets, alpha_canon, alpha_dev, xinv, w, gl::inv(8), next, ctx->stream);
     }
     fri->cur = next;  // the committed layer keeps ownership of the old buffer
     fri->curM = rows;
     fri->cur_log_cosets = 0;
     fri->cur_committed = false;
     CUDA_TRY(ctx, cudaGetLastError());
+    return AERO_OK;
+}
+
+aero_status aero_fri_commit_layer(aero_fri *fri, uint8_t root[32]) {
+    if (!fri || !root) return AERO_ERR_INVALID;
+    aero_ctx *ctx = fri->ctx;
+    TRY(fri_commit_enqueue(fri));
+    CUDA_TRY(ctx, cudaMemcpyAsync(root, fri->layers.back().full + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return AERO_OK;
+}
+
+aero_status aero_fri_fold(aero_fri *fri, uint64_t alpha) {
+    if (!fri) return AERO_ERR_INVALID;
+    return fri_fold_enqueue(fri, to_canon(fri->ctx, alpha), nullptr);
+}
+
+aero_status aero_fri_build_layers(aero_fri *fri, const uint8_t coin_seed[32], uint32_t num_layers, uint8_t *roots_out,
+                                  uint64_t *alphas_out) {
+    if (!fri) return AERO_ERR_INVALID;
+    aero_ctx *ctx = fri->ctx;
+    if (!coin_seed || !roots_out || !alphas_out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (!fri->layers.empty() || fri->cur_committed) CTX_FAIL(ctx, AERO_ERR_STATE, "FRI layers have already been built");
+    if (num_layers > 32) CTX_FAIL(ctx, AERO_ERR_INVALID, "too many FRI layers");
+    const uint32_t nl = num_layers + 1;  // + the remainder commitment
+    // staging layout (host mirror at the same offsets): seed[32] | roots[nl][32] | alphas[nl]
+    const size_t off_roots = 32, off_alpha = 32 + (size_t)nl * 32, total = off_alpha + (size_t)nl * 8;
+    TRY(stage_reserve(ctx, total));
+    memcpy(ctx->h_stage, coin_seed, 32);
+    uint8_t *d = ctx->d_stage;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d, ctx->h_stage, 32, cudaMemcpyHostToDevice, ctx->stream));
+    for (uint32_t l = 0; l < nl; l++) {
+        TRY(fri_commit_enqueue(fri));
+        uint64_t *d_alpha = (uint64_t *)(d + off_alpha) + l;
+        fri_coin((uint32_t *)d, fri->layers.back().full + 8, d_alpha, (uint32_t *)(d + off_roots + (size_t)l * 32), ctx->stream);
+        // the reference also draws a challenge for the remainder layer and discards the fold (prover/mod.rs:174-183)
+        if (l < num_layers) TRY(fri_fold_enqueue(fri, 0, d_alpha));
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage + off_roots, d + off_roots, total - off_roots, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    memcpy(roots_out, ctx->h_stage + off_roots, (size_t)nl * 32);
+    const uint64_t *al = (const uint64_t *)(ctx->h_stage + off_alpha);
+    for (uint32_t l = 0; l < nl; l++) {
+        if (al[l] == ~0ULL) CTX_FAIL(ctx, AERO_ERR_STATE, "failed to draw a FRI challenge for layer %u", l);
+        alphas_out[l] = from_canon(ctx, al[l]);
+    }
     return AERO_OK;
 }
 

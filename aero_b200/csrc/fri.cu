@@ -17,10 +17,11 @@ struct FoldConsts {
 };
 
 __global__ void __launch_bounds__(256) fri_fold_kernel(const uint64_t *__restrict__ f, uint32_t rows, int log_cosets,
-                                                       uint64_t alpha, PowTable xinv, FoldConsts fc,
-                                                       uint64_t *__restrict__ out) {
+                                                       uint64_t alpha, const uint64_t *__restrict__ alpha_dev,
+                                                       PowTable xinv, FoldConsts fc, uint64_t *__restrict__ out) {
     const uint32_t tau = blockIdx.x * blockDim.x + threadIdx.x;
     if (tau >= rows) return;
+    if (alpha_dev) alpha = *alpha_dev;  // drawn by the device coin earlier on this stream (fri_coin)
     uint64_t v[8];
     uint32_t j;
     fri_gather8(f, rows, log_cosets, tau, j, v);
@@ -54,13 +55,13 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const uint64_t *__restric
     out[j] = gl::mul(acc, fc.inv8);
 }
 
-void fri_fold(const uint64_t *f, uint32_t rows, int log_cosets, uint64_t alpha, PowTable xinv, const uint64_t w8inv[4],
-              uint64_t inv8, uint64_t *out, cudaStream_t s) {
+void fri_fold(const uint64_t *f, uint32_t rows, int log_cosets, uint64_t alpha, const uint64_t *alpha_dev, PowTable xinv,
+              const uint64_t w8inv[4], uint64_t inv8, uint64_t *out, cudaStream_t s) {
     FoldConsts fc;
     for (int i = 0; i < 4; i++) fc.w[i] = w8inv[i];
     fc.inv8 = inv8;
     AERO_COUNT_LAUNCH(1);
-    fri_fold_kernel<<<(rows + 255) / 256, 256, 0, s>>>(f, rows, log_cosets, alpha, xinv, fc, out);
+    fri_fold_kernel<<<(rows + 255) / 256, 256, 0, s>>>(f, rows, log_cosets, alpha, alpha_dev, xinv, fc, out);
 }
 
 }  // namespace aero

@@ -243,6 +243,37 @@ void fri_leaf_hash(const uint64_t *f, uint32_t rows, int log_cosets, uint32_t *l
     fri_leaf_hash_kernel<<<(rows + 255) / 256, 256, 0, s>>>(f, rows, log_cosets, leaves);
 }
 
+__global__ void fri_coin_kernel(uint32_t *__restrict__ seed, const uint32_t *__restrict__ root,
+                                uint64_t *__restrict__ alpha_out, uint32_t *__restrict__ root_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t s[8], r[8], t[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        s[i] = seed[i];
+        r[i] = root[i];
+    }
+    b2s::merge(s, r, t);
+    uint64_t alpha = ~0ULL;
+    for (uint64_t counter = 1; counter <= 1000; counter++) {
+        b2s::merge_with_int(t, counter, o);
+        const uint64_t v = ((uint64_t)o[1] << 32) | o[0];
+        if (v < gl::P) {  // from_random_bytes rejects non-canonical values (f64/mod.rs:438-454)
+            alpha = v;
+            break;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        seed[i] = t[i];
+        root_out[i] = r[i];
+    }
+    *alpha_out = alpha;
+}
+void fri_coin(uint32_t *seed, const uint32_t *root, uint64_t *alpha_out, uint32_t *root_out, cudaStream_t s) {
+    AERO_COUNT_LAUNCH(1);
+    fri_coin_kernel<<<1, 32, 0, s>>>(seed, root, alpha_out, root_out);
+}
+
 // Grinding: smallest nonce >= 1 whose digest head has >= `bits` trailing zero bits.  Batches are
 // scanned in ascending order; inside a batch atomicMin keeps the smallest hit, so the result is
 // the global minimum, matching the reference's serial `find` (channel.rs:154-157).

@@ -67,6 +67,10 @@ void hash_rows_natural(const uint64_t *m, size_t col_stride, int ncols, uint32_t
                        cudaStream_t s);
 void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s);
 void fri_leaf_hash(const uint64_t *f, uint32_t rows, int log_cosets, uint32_t *leaves, cudaStream_t s);
+// Fiat-Shamir for one FRI layer on the device: seed <- H(seed || root) (RandomCoin::reseed,
+// crypto/src/random/mod.rs:105-108), alpha <- first canonical draw (:179-196); the root is also
+// copied to root_out so that all layer roots leave in one download.  alpha = 2^64-1 if 1000 draws fail.
+void fri_coin(uint32_t *seed, const uint32_t *root, uint64_t *alpha_out, uint32_t *root_out, cudaStream_t s);
 void pow_search(const uint32_t *seed, uint64_t base, uint32_t count, uint32_t bits, unsigned long long *best,
                 cudaStream_t s);
 
@@ -115,7 +119,8 @@ void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDe
                         uint64_t offset, PowTable gN, uint64_t *combined, cudaStream_t s);
 
 // fri.cu
-void fri_fold(const uint64_t *f, uint32_t rows, int log_cosets, uint64_t alpha, PowTable xinv /* (7 g_M^j)^-1 */,
-              const uint64_t w8inv[4], uint64_t inv8, uint64_t *out, cudaStream_t s);
+// alpha_dev != nullptr: the folding challenge is read from device memory (written by fri_coin)
+void fri_fold(const uint64_t *f, uint32_t rows, int log_cosets, uint64_t alpha, const uint64_t *alpha_dev,
+              PowTable xinv /* (7 g_M^j)^-1 */, const uint64_t w8inv[4], uint64_t inv8, uint64_t *out, cudaStream_t s);
 
 }  // namespace aero

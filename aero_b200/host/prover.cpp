@@ -421,13 +421,18 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
 
     // 6 ----- FRI layers (fri/src/prover/mod.rs:166-191)
     const size_t num_layers = ProofOptions{o}.num_fri_layers(N);
-    for (size_t l = 0; l < num_layers + 1; l++) {
-        P_TRY(aero_fri_commit_layer(H.fri, root));
-        channel.commit_fri_layer(Digest(root, root + 32));
-        uint64_t alpha;
-        if (!channel.coin().draw(&alpha)) P_FAIL(AERO_ERR_STATE, "failed to draw FRI alpha");
-        // the reference also folds the remainder layer and discards the result (prover/mod.rs:174-183)
-        if (l < num_layers) P_TRY(aero_fri_fold(H.fri, to_abi(alpha)));
+    {
+        // all layers in one host round trip: the coin's reseed/draw per layer runs on the device
+        // between the kernels; the channel is replayed from the returned roots and must agree
+        std::vector<uint8_t> roots((num_layers + 1) * 32);
+        std::vector<uint64_t> alphas(num_layers + 1);
+        P_TRY(aero_fri_build_layers(H.fri, channel.coin().seed().data(), (uint32_t)num_layers, roots.data(), alphas.data()));
+        for (size_t l = 0; l < num_layers + 1; l++) {
+            channel.commit_fri_layer(Digest(roots.begin() + l * 32, roots.begin() + (l + 1) * 32));
+            uint64_t alpha;
+            if (!channel.coin().draw(&alpha)) P_FAIL(AERO_ERR_STATE, "failed to draw FRI alpha");
+            if (to_abi(alpha) != alphas[l]) P_FAIL(AERO_ERR_STATE, "device coin diverged from the channel's coin");
+        }
     }
 
     // 7 ----- query positions (lib.rs:502-516)

@@ -354,6 +354,17 @@ class FriProver:
     def fold(self, alpha: int) -> None:
         self.ctx._check(self.ctx.lib.aero_fri_fold(self.h, alpha))
 
+    def build_layers(self, coin_seed: bytes, num_layers: int):
+        """FriProver::build_layers with the coin on the device (aero_fri_build_layers): the
+        num_layers + 1 roots and the challenges drawn after each (ABI form)."""
+        nl = num_layers + 1
+        seed = (c_uint8 * 32).from_buffer_copy(coin_seed)
+        roots = (c_uint8 * (32 * nl))()
+        alphas = (c_uint64 * nl)()
+        self.ctx._check(self.ctx.lib.aero_fri_build_layers(self.h, seed, num_layers, roots, alphas))
+        raw = ctypes.string_at(roots, 32 * nl)
+        return [raw[32 * i: 32 * i + 32] for i in range(nl)], [int(a) for a in alphas]
+
     def open(self, positions: Sequence[int]) -> bytes:
         pos = np.array(list(positions), np.uint64)
         cap = 1 << 20

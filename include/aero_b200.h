@@ -188,6 +188,15 @@ aero_status aero_fri_download_evaluations(aero_fri *fri, uint64_t *out, uint64_t
 aero_status aero_fri_from_evaluations(aero_ctx *ctx, const uint64_t *evaluations, uint64_t count, aero_fri **out);
 aero_status aero_fri_commit_layer(aero_fri *fri, uint8_t root[32]);
 aero_status aero_fri_fold(aero_fri *fri, uint64_t alpha);
+/* FriProver::build_layers (fri/src/prover/mod.rs:166-191) in one call and ONE host round trip: all
+ * num_layers + 1 commitments (the last one is the remainder) and num_layers folds, with the channel's
+ * part -- commit_fri_layer = coin.reseed(root), draw_fri_alpha = coin.draw()
+ * (prover/src/channel.rs:172-184, crypto/src/random/mod.rs:105-108,179-196) -- evaluated on the device
+ * between the kernels.  coin_seed: the public coin's seed when FRI starts.  roots_out:
+ * (num_layers + 1) x 32 bytes; alphas_out: the num_layers + 1 challenges drawn (ABI form), so that
+ * the caller replays its own channel (reseed + draw per layer) and checks it agrees. */
+aero_status aero_fri_build_layers(aero_fri *fri, const uint8_t coin_seed[32], uint32_t num_layers, uint8_t *roots_out,
+                                  uint64_t *alphas_out);
 /* FriProver::build_proof (fri/src/prover/mod.rs:231-275) in FriProof::write_into format
  * (fri/src/proof.rs:201-214,351-359); the last committed layer is the remainder. */
 aero_status aero_fri_open(aero_fri *fri, const uint64_t *positions, uint32_t n_pos, uint8_t *fri_proof_bytes,

@@ -300,6 +300,48 @@ def test_open_queries_equals_separate_openings(ctx, oracle):
     assert e.value.status == aero_b200.AERO_ERR_INVALID
 
 
+@pytest.mark.parametrize("logM", [7, 11, 14, 17])
+def test_fri_build_layers_device_coin(ctx, ctx_mont, oracle, logM):
+    """aero_fri_build_layers (coin reseed/draw on the device between the kernels) == the stepwise
+    route with the host coin: same roots, same challenges, same FriProof bytes -- and both equal the
+    oracle's FriProver (fri/src/prover/mod.rs:166-191)."""
+    M = 1 << logM
+    evals = oracle.synthetic_trace(1, M, 0xF7)[0]
+    nl = oracle.ProofOptions().num_fri_layers(M)
+    coin_o = oracle.RandomCoin(b"fri-dev")
+    seed0 = coin_o.seed
+    exp_roots, exp_alphas, cur = [], [], evals
+    for l in range(nl + 1):
+        def alpha_fn(r):
+            coin_o.reseed(r)
+            return coin_o.draw()
+        layer, nxt = oracle.fri_build_layer(cur, 8, alpha_fn)
+        exp_roots.append(layer.nodes[1].tobytes())
+        cur = nxt
+    coin_r = oracle.RandomCoin(b"fri-dev")
+    for r in exp_roots:
+        coin_r.reseed(r)
+        exp_alphas.append(coin_r.draw())
+    fri = ctx.fri_from_evaluations(evals)
+    roots, alphas = fri.build_layers(seed0, nl)
+    assert roots == exp_roots and alphas == exp_alphas
+    fri2 = ctx.fri_from_evaluations(evals)
+    for l in range(nl + 1):
+        assert fri2.commit_layer() == exp_roots[l]
+        if l < nl:
+            fri2.fold(exp_alphas[l])
+    positions = oracle.RandomCoin(b"q3").draw_integers(min(27, M // 8 - 1), M)
+    assert fri.open(positions) == fri2.open(positions)
+    with pytest.raises(AeroError) as e:  # FriProver::build_layers panics when called twice (prover/mod.rs:167-170)
+        fri.build_layers(seed0, nl)
+    assert e.value.status == aero_b200.AERO_ERR_STATE
+    # Montgomery-form context: challenges come back in ABI form
+    c2m = oracle.canon_to_mont
+    fri3 = ctx_mont.fri_from_evaluations(c2m(evals))
+    roots3, alphas3 = fri3.build_layers(seed0, nl)
+    assert roots3 == exp_roots and alphas3 == [int(v) for v in c2m(np.array(exp_alphas, np.uint64))]
+
+
 def test_fri_state_errors(ctx, oracle):
     """FriProver panics when misused (fri/src/prover/mod.rs:167-170,232-235) -> AERO_ERR_STATE."""
     fri = ctx.fri_from_evaluations(oracle.synthetic_trace(1, 1024, 1)[0])

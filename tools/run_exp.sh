@@ -9,3 +9,11 @@ python -c "
 import json
 d=json.load(open('gpurun_out/bench_$TAG.json')); print(d['ms_per_step'], d['e2e']['ms_per_step']); print(d['phase_ms_per_step'])"
 tail -n 3 gpurun_out/bench_$TAG.err
+for L in ${SIZES:-}; do
+  python bench.py --log-rows $L --quick --steps 5 --warmup 1 --no-cpu-baseline 2>/dev/null | cut -c1-60
+done
+if [ -n "${TRACE:-}" ]; then
+  python bench.py --trace gpurun_out/trace_$TAG.json --no-cpu-baseline > gpurun_out/trace.log 2>&1
+  python tools/trace_gaps.py gpurun_out/trace_$TAG.json 14 > gpurun_out/trace_gaps_$TAG.txt 2>&1
+  head -18 gpurun_out/trace_gaps_$TAG.txt; gzip -f gpurun_out/trace_$TAG.json
+fi
