@@ -477,6 +477,10 @@ struct aero_segment {
     // compactly: lde[c][q][i] with q = r - coset_begin, column stride coset_count * n.
     int coset_begin = 0, coset_count = 0;
     bool tree_pending = false;                 // leaves of other ranks still missing
+    // sharded proof over the exchange window: the digests of the OTHER ranks' rows arrive here,
+    // coset-major ([B][n] x 32 bytes, so a rank's contribution is one contiguous block that its
+    // row-hash kernel streams over NVLink); interleaved into `full` before the tree is built
+    uint32_t *leaf_stage = nullptr;
     uint64_t n() const { return 1ULL << logn; }
     uint64_t N() const { return 1ULL << (logn + log_blowup); }
     uint64_t lde_stride() const { return (uint64_t)coset_count << logn; }
@@ -486,6 +490,9 @@ static aero_status segment_finish_tree(aero_segment *seg, uint8_t root[32]) {
     aero_ctx *ctx = seg->ctx;
     {
         PhaseTimer t(ctx, "merkle");
+        if (seg->leaf_stage)  // digests the peers stored into the window -> natural leaf slots
+            leaves_from_stage(seg->leaf_stage, seg->full + (size_t)seg->N() * 8, seg->logn, seg->log_blowup, seg->coset_begin,
+                              seg->coset_count, ctx->stream);
         merkle_build(seg->full, seg->N(), ctx->stream);
     }
     seg->tree_pending = false;
@@ -509,7 +516,12 @@ static aero_status segment_alloc_lde(aero_segment *seg, int log_blowup, const Df
     seg->coset_count = B / ctx->shard_world;
     seg->coset_begin = ctx->shard_rank * seg->coset_count;
     TRY(dev_alloc(ctx, (void **)&seg->lde, (size_t)seg->ncols * seg->lde_stride() * 8));
-    TRY(dev_alloc_shared(ctx, (void **)&seg->full, (size_t)2 * seg->N() * 32));
+    if (ctx->win_ranks > 1 && ctx->shard_world > 1) {
+        TRY(dev_alloc_shared(ctx, (void **)&seg->leaf_stage, (size_t)seg->N() * 32));
+        TRY(dev_alloc(ctx, (void **)&seg->full, (size_t)2 * seg->N() * 32));
+    } else {
+        TRY(dev_alloc(ctx, (void **)&seg->full, (size_t)2 * seg->N() * 32));
+    }
     return plan_lde(ctx, seg->logn, log_blowup, false, plan);
 }
 static int segment_lde_batch_cols(aero_segment *seg) {
@@ -561,8 +573,8 @@ static aero_status segment_hash_batch(aero_segment *seg, int c0, int nc) {
         CUDA_TRY(ctx, cudaStreamWaitEvent(hs, ctx->ev_lde, 0));
     }
     uint32_t *leaves = seg->full + (size_t)N * 8;
-    const PeerPtrs peers = peers_of(ctx, leaves);
-    // the peers' copies of this leaf array may still be in use by their previous proof
+    const PeerPtrs peers = seg->leaf_stage ? peers_of(ctx, seg->leaf_stage) : PeerPtrs{};
+    // the peers' staging arrays may still be in use by their previous proof
     if (peers.n && c0 == 0) TRY(window_barrier(ctx));
     char nm[32];
     snprintf(nm, sizeof nm, "hash_rows_w%d", seg->ncols);
@@ -1359,6 +1371,7 @@ void aero_segment_destroy(aero_segment *seg) {
     dev_free(seg->ctx, seg->polys);
     dev_free(seg->ctx, seg->lde);
     dev_free(seg->ctx, seg->full);
+    dev_free(seg->ctx, seg->leaf_stage);
     delete seg;
 }
 aero_status aero_segment_info(aero_segment *seg, uint32_t *n_cols, uint64_t *n_rows, uint32_t *blowup) {

@@ -62,12 +62,41 @@ __global__ void __launch_bounds__(256) hash_rows_kernel(const uint64_t *__restri
         store_digest(leaves + (size_t)k * 8, h);
         // fused all-gather: the finished digest also goes to the leaf array of every peer rank (the
         // intermediate chaining value of a column range stays local)
-        if (tail)
-            for (int q = 0; q < peers.n; q++) store_digest(reinterpret_cast<uint32_t *>(peers.p[q]) + (size_t)k * 8, h);
+        // (coset-major slot in the peer's staging array: consecutive threads write consecutive 32-byte
+        // digests, so the NVLink stores coalesce; natural slots are 32 bytes every 32*B bytes and
+        // ran at ~150 GB/s)
+        if (tail) {
+            const size_t slot = (size_t)rho + ((size_t)coset_begin << logn);
+            for (int q = 0; q < peers.n; q++) store_digest(reinterpret_cast<uint32_t *>(peers.p[q]) + slot * 8, h);
+        }
     }
 }
 
 // ---- peer exchange helpers (multi-GPU) ----------------------------------------------------------
+// 16 bytes per thread: stage[(r*n + i)*2 + half] -> leaves[((i << log_blowup) | r)*2 + half] for the
+// cosets r outside [coset_begin, coset_begin + coset_count)
+__global__ void __launch_bounds__(256) leaves_from_stage_kernel(const uint4 *__restrict__ stage, uint4 *__restrict__ leaves,
+                                                                int logn, int log_blowup, int coset_begin,
+                                                                int coset_count) {
+    const size_t total = (size_t)2 << (logn + log_blowup);
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t d = t >> 1;
+        const uint32_t r = (uint32_t)(d >> logn), i = (uint32_t)(d & (((size_t)1 << logn) - 1));
+        if ((int)r >= coset_begin && (int)r < coset_begin + coset_count) continue;
+        leaves[((((size_t)i << log_blowup) | r) << 1) | (t & 1)] = stage[t];
+    }
+}
+void leaves_from_stage(const uint32_t *stage, uint32_t *leaves, int logn, int log_blowup, int coset_begin,
+                       int coset_count, cudaStream_t s) {
+    const size_t total = (size_t)2 << (logn + log_blowup);
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    AERO_COUNT_LAUNCH(1);
+    leaves_from_stage_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const uint4 *>(stage),
+                                                             reinterpret_cast<uint4 *>(leaves), logn, log_blowup,
+                                                             coset_begin, coset_count);
+}
+
 __global__ void __launch_bounds__(256) peer_push_kernel(const uint4 *__restrict__ local, PeerPtrs peers, size_t first,
                                                         size_t count) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {

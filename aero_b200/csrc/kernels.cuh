@@ -58,6 +58,13 @@ struct PeerPtrs {
 void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, int total_cols, int logn, int log_blowup,
                    uint32_t coset_begin, uint32_t nrows, uint32_t *leaves, const PeerPtrs &peers, int max_blocks,
                    cudaStream_t s);
+// Sharded proofs: `leaves` of hash_rows_lde stays the LOCAL natural-order leaf array; the peer copies
+// (`peers`) are the other ranks' coset-major staging arrays, where this rank's digests form one
+// contiguous block (coset r at [r*n, (r+1)*n) digests).  leaves_from_stage moves the digests of the
+// cosets NOT in [coset_begin, coset_begin + coset_count) from the local staging array to their
+// natural slots leaves[B*i + r].
+void leaves_from_stage(const uint32_t *stage, uint32_t *leaves, int logn, int log_blowup, int coset_begin,
+                       int coset_count, cudaStream_t s);
 // copies [off, off + bytes) of the local buffer to the same range of every peer copy (16-byte units)
 void peer_push(const void *local, const PeerPtrs &peers, size_t off, size_t bytes, cudaStream_t s);
 // all ranks arrive (epoch) before any leaves: flags[r] of rank q's window is written by rank r
