@@ -79,7 +79,9 @@ __host__ __device__ constexpr bool dft_need_canon(int R, int q, int e) {
 // tw[(e << s0) + low] = (sigma_m w_m^low)^bitrev(e); what remains is a plain 2^R-point DFT whose
 // twiddles are powers of two (gl::mul_pow2), negated where the exponent is >= 96.
 // PLAIN0: first round (s0 == 0) of a transform without coset shift: all general twiddles are 1.
-template <int R, int T, int RS, bool PLAIN0, bool INV>
+// IN_CANON: the tile holds canonical values already (pass 2 reads what pass 1 stored with
+// mul_canon), so a PLAIN0 round has nothing to canonicalise on the way in.
+template <int R, int T, int RS, bool PLAIN0, bool INV, bool IN_CANON = false>
 __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s0, int logM) {
     if (PLAIN0) s0 = 0;
     const int ngroups = (1 << logM) >> R;
@@ -94,7 +96,7 @@ __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s
             constexpr int e = decltype(E)::value;
             uint64_t v = a[(base + (e << s0)) * RS + t];
             if constexpr (e > 0 && !PLAIN0) v = gl::mul_canon(v, tw[(e << s0) + low]);
-            else if constexpr (dft_need_canon(R, 0, e)) v = gl::canon_any(v);
+            else if constexpr (!IN_CANON && dft_need_canon(R, 0, e)) v = gl::canon_any(v);
             x[e] = v;
         });
         static_for<R>([&](auto Q) {
@@ -130,28 +132,28 @@ __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s
     }
 }
 
-template <int T, int RS, bool PLAIN0, bool INV, int RMAX>
+template <int T, int RS, bool PLAIN0, bool INV, int RMAX, bool IN_CANON = false>
 __device__ __forceinline__ void dit_round_dispatch(int R, uint64_t *a, const uint64_t *tw, int s0, int logM) {
     if constexpr (RMAX >= 5) {
         if (R == 5) {
-            dit_round<5, T, RS, PLAIN0, INV>(a, tw, s0, logM);
+            dit_round<5, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM);
             return;
         }
     }
     switch (R) {
-    case 4: dit_round<4, T, RS, PLAIN0, INV>(a, tw, s0, logM); break;
-    case 3: dit_round<3, T, RS, PLAIN0, INV>(a, tw, s0, logM); break;
-    case 2: dit_round<2, T, RS, PLAIN0, INV>(a, tw, s0, logM); break;
-    default: dit_round<1, T, RS, PLAIN0, INV>(a, tw, s0, logM); break;
+    case 4: dit_round<4, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM); break;
+    case 3: dit_round<3, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM); break;
+    case 2: dit_round<2, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM); break;
+    default: dit_round<1, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM); break;
     }
 }
 
 // Full M-point DIT over the tile: input in bit-reversed row order, output in natural row order.
-template <int T, int RS, bool PLAIN, bool INV, int RMAX>
+template <int T, int RS, bool PLAIN, bool INV, int RMAX, bool IN_CANON = false>
 __device__ __forceinline__ void dit_tile(uint64_t *a, const uint64_t *tw, int logM) {
     const NttRounds rounds(logM);
     // first round: s0 == 0 is a compile-time fact, which lets PLAIN transforms skip the unit twiddles
-    dit_round_dispatch<T, RS, PLAIN, INV, RMAX>(rounds.log(0), a, tw, 0, logM);
+    dit_round_dispatch<T, RS, PLAIN, INV, RMAX, IN_CANON>(rounds.log(0), a, tw, 0, logM);
     __syncthreads();
     int s0 = rounds.log(0);
     for (int i = 1; i < rounds.count; i++) {
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(MAXT) dft_pass2_kernel(const uint64_t *__restr
     load_tile_bitrev<T, RS>(a, s, log2, T == 8 ? 3 : 2);   // row j2 at s[j2*T + t]
     cp_async_wait_all();
     __syncthreads();
-    dit_tile<T, RS, true, INV, (MAXT <= 256 ? 5 : 4)>(a, tw, log2);
+    dit_tile<T, RS, true, INV, (MAXT <= 256 ? 5 : 4), true>(a, tw, log2);  // tmp is canonical (pass 1's mul_canon)
     uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n;
     // thread (j0 = tid / T, t = tid % T) stores rows i2 = j0 + k*J of its tile column i1 = i1_0 + t
     const int J = blockDim.x / T;

@@ -336,6 +336,13 @@ def run_aero(args) -> None:
                             "achieved": comp_per_s * ALU_OPS_PER_COMPRESSION if comp_per_s else None,
                             "peak": ALU_PEAK_LANE_OPS, "peak_kind": "measured (tools/int_peak.cu, profiles/r01_int_peak.txt)",
                             "frac": comp_per_s * ALU_OPS_PER_COMPRESSION / ALU_PEAK_LANE_OPS if comp_per_s else None}}
+        # second-largest share of the step: the NTT passes (interpolation + coset LDE of the trace segments)
+        ntt_ms = sum(prof.get(k, (0, 0.0))[1] for k in ("interpolate_w%d" % MAIN_W, "interpolate_w%d" % AUX_W,
+                                                        "lde_w%d" % MAIN_W, "lde_w%d" % AUX_W)) / args.steps
+        if ntt_ms > 0 and shard is None:
+            bfly = (1 + BLOWUP) * (MAIN_W + AUX_W) * (n // 2) * log_rows
+            roofline["ntt"] = {"unit": "butterflies/s", "achieved": bfly / (ntt_ms * 1e-3), "ms_per_step": ntt_ms,
+                               "note": "INT bound: ALU pipe 73-79 % busy in ncu (profiles/r01_ncu_v5_ntt.txt), DRAM 17-26 %"}
         cpu = None
         if not args.no_cpu_baseline:
             rps, dt, cores = cpu_port_rows_per_s(args.ref_log_rows, 1)
