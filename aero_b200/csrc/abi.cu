@@ -628,12 +628,24 @@ static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint
     return segment_tree_after_hash(seg, root);
 }
 
+// Column batches of an upload-overlapped commit: [edge, batch, batch, ..., batch, edge] when edge > 0
+// (batch - 2*edge... the middle batches are full; the last one takes whatever is left, at most edge
+// when the column count allows), else uniform batches.
+static int upload_batch_size(int c0, int n_cols, int batch, int edge) {
+    if (edge <= 0 || edge >= batch) return batch;
+    if (c0 == 0) return edge;
+    const int left = n_cols - c0;
+    // keep the final batch short: stop the full batches `edge` columns before the end
+    if (left > batch + edge) return batch;
+    if (left > edge) return left - edge;
+    return left;
+}
 // d_src: ncols columns (stride src_stride) of n values in ABI form, on the device.  Columns are
 // processed in batches (interpolate, then extend); when `ready` is given, batch b first waits for
 // ready[b] -- the event that says its host->device copy has landed -- so uploads overlap compute.
 static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, size_t src_stride, uint32_t n_cols,
                                        uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
-                                       uint8_t root[32], int batch_cols = 0, const cudaEvent_t *ready = nullptr) {
+                                       uint8_t root[32], int batch_cols = 0, const cudaEvent_t *ready = nullptr, int edge_cols = 0) {
     if (!out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null output handle");
     if (n_cols == 0 || n_cols > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of columns must be 1..255, got %u", n_cols);
     // Matrix::new (prover/src/matrix.rs:41-64): at least two rows, power of two
@@ -669,8 +681,10 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
         const bool per_batch_hash = !(batch & 1) && segment_hash_overlapped(seg);
         char nm[32];
         snprintf(nm, sizeof nm, "interpolate_w%d", (int)n_cols);
-        for (int c0 = 0, b = 0; c0 < (int)n_cols; c0 += batch, b++) {
-            const int nc = std::min(batch, (int)n_cols - c0);
+        // edge_cols > 0 (uploads in flight): the first and the last batch are short -- the first so that
+        // compute starts early, the last so that little work is left once the final copy has landed
+        for (int c0 = 0, b = 0, nc = 0; c0 < (int)n_cols; c0 += nc, b++) {
+            nc = std::min(upload_batch_size(c0, (int)n_cols, batch, edge_cols), (int)n_cols - c0);
             if (ready) cudaStreamWaitEvent(ctx->stream, ready[b], 0);
             if (input_is_coeffs) {
                 const uint64_t *src = d_src + (size_t)c0 * src_stride;
@@ -680,7 +694,7 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
                     if (mont) convert_form(src + (size_t)c * src_stride, dst + (size_t)c * n_rows, n_rows, 0, ctx->stream);
                     else cudaMemcpyAsync(dst + (size_t)c * n_rows, src + (size_t)c * src_stride, n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream);
                 }
-            } else if (c0 % ibatch == 0) {
+            } else if (edge_cols > 0 || c0 % ibatch == 0) {
                 PhaseTimer t(ctx, nm);
                 DftLaunch l;
                 l.src = d_src + (size_t)c0 * src_stride;
@@ -688,7 +702,7 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
                 l.tmp = tmp_i;
                 l.src_col_stride = src_stride;
                 l.dst_col_stride = n_rows;
-                l.ncols = std::min(ibatch, (int)n_cols - c0);
+                l.ncols = edge_cols > 0 ? nc : std::min(ibatch, (int)n_cols - c0);
                 l.deinterleave_log = 0;
                 dft_run(*iplan, l, ctx->stream);
             }
@@ -1246,19 +1260,27 @@ aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint
     if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     int batch = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->upload_batch_cols, (n_cols + 2) / 3));
     if (batch > 1 && (batch & 1)) batch++;  // even batches: each one's row hash can start as soon as it is extended
-    const int nb = ((int)n_cols + batch - 1) / batch;
+    // short first / last batches once there are enough columns for it to matter (see upload_batch_size)
+    const int edge = ((int)n_cols >= 4 * batch && batch >= 4) ? ((batch / 2) & ~1) : 0;
+    std::vector<int> sizes;
+    for (int c0 = 0; c0 < (int)n_cols;) {
+        const int nc = std::min(upload_batch_size(c0, (int)n_cols, batch, edge), (int)n_cols - c0);
+        sizes.push_back(nc);
+        c0 += nc;
+    }
+    const int nb = (int)sizes.size();
     std::vector<cudaEvent_t> ev(nb + 1);
     for (auto &e : ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     // the staging block may still be read by kernels already queued on the compute stream
     CUDA_TRY(ctx, cudaEventRecord(ev[nb], ctx->stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev[nb], 0));
-    for (int b = 0; b < nb; b++) {
-        for (uint32_t c = b * batch; c < std::min<uint32_t>(n_cols, (b + 1) * batch); c++)
+    for (int b = 0, c = 0; b < nb; b++) {
+        for (int k = 0; k < sizes[b]; k++, c++)
             CUDA_TRY(ctx, cudaMemcpyAsync(stage + (size_t)c * n_rows, cols[c], n_rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
         CUDA_TRY(ctx, cudaEventRecord(ev[b], ctx->copy_stream));
     }
     TRY(flush_deferred_uploads(ctx));  // prefetches ride behind this segment's copies, under its NTTs
-    aero_status st = segment_from_device(ctx, stage, n_rows, n_cols, n_rows, blowup, input_is_coeffs, out, root, batch, ev.data());
+    aero_status st = segment_from_device(ctx, stage, n_rows, n_cols, n_rows, blowup, input_is_coeffs, out, root, batch, ev.data(), edge);
     cudaEventSynchronize(ev[nb - 1]);  // the caller's host buffers are free again on return
     for (auto &e : ev) cudaEventDestroy(e);
     dev_free(ctx, stage);

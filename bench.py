@@ -35,6 +35,7 @@ MAIN_W, AUX_W, CE_COLS, BLOWUP = 72, 9, 2, 8
 # INT roofline of the row hash: static ALU-pipe instruction count of one
 # compress_pair in hash_rows_kernel (cuobjdump: 330 LOP3 + 160 SHF + 160 PRMT + 11 VIADD; floor 648),
 # and the ALU-pipe issue rate measured by tools/int_peak.cu on this pool's B200s.
+NTT_ALU_OPS_PER_BUTTERFLY = 21.8
 ALU_OPS_PER_COMPRESSION = 661
 ALU_PEAK_LANE_OPS = 18.4e12
 # dram__bytes_read.sum + dram__bytes_write.sum of one hash_rows_kernel launch (w=72, N=2^23) from the
@@ -341,8 +342,13 @@ def run_aero(args) -> None:
                                                         "lde_w%d" % MAIN_W, "lde_w%d" % AUX_W)) / args.steps
         if ntt_ms > 0 and shard is None:
             bfly = (1 + BLOWUP) * (MAIN_W + AUX_W) * (n // 2) * log_rows
-            roofline["ntt"] = {"unit": "butterflies/s", "achieved": bfly / (ntt_ms * 1e-3), "ms_per_step": ntt_ms,
-                               "note": "INT bound: ALU pipe 73-79 % busy in ncu (profiles/r01_ncu_v5_ntt.txt), DRAM 17-26 %"}
+            bps = bfly / (ntt_ms * 1e-3)
+            roofline["ntt"] = {"unit": "butterflies/s", "achieved": bps, "ms_per_step": ntt_ms,
+                               # ncu: 34.2 executed thread instructions per butterfly of a 2^10-point pass, 63.8 % of
+                               # them on the ALU pipe (profiles/r01_ncu_v5_ntt.txt, r01_ncu_v10_ntt.txt)
+                               "alu_ops_per_butterfly": NTT_ALU_OPS_PER_BUTTERFLY,
+                               "int_frac": bps * NTT_ALU_OPS_PER_BUTTERFLY / ALU_PEAK_LANE_OPS,
+                               "note": "INT bound: ALU pipe 71-80 % busy in ncu, DRAM 17-26 %"}
         cpu = None
         if not args.no_cpu_baseline:
             rps, dt, cores = cpu_port_rows_per_s(args.ref_log_rows, 1)

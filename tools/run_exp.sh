@@ -17,3 +17,4 @@ if [ -n "${TRACE:-}" ]; then
   python tools/trace_gaps.py gpurun_out/trace_$TAG.json 14 > gpurun_out/trace_gaps_$TAG.txt 2>&1
   head -18 gpurun_out/trace_gaps_$TAG.txt; gzip -f gpurun_out/trace_$TAG.json
 fi
+if [ -n "${SMOKE:-}" ]; then python -c "import __graft_entry__ as g; g.smoke()"; fi
