@@ -74,6 +74,7 @@ PROTOTYPES = {
     "aero_ctx_set_option": (c_int, [c_void_p, c_char_p, ctypes.c_longlong]),
     "aero_ctx_set_error": (None, [c_void_p, c_char_p]),
     "aero_ctx_profile_enable": (c_int, [c_void_p, c_int]),
+    "aero_ctx_profile_filter": (c_int, [c_void_p, c_char_p]),
     "aero_ctx_profile_read": (c_int, [c_void_p, c_char_p, POINTER(c_size_t)]),
     "aero_launch_count": (c_uint64, []),
     "aero_version": (c_char_p, []),

@@ -73,13 +73,16 @@ struct aero_ctx {
     int form = AERO_FORM_MONTGOMERY;
     std::string err;
     bool profile = false;
+    std::string profile_prefix;  // non-empty: only phases whose name starts with it are timed
     std::map<std::string, PhaseStat> stats;
     std::vector<PendingEvent> pending;
+    std::vector<cudaEvent_t> event_pool;  // timing events of finished phases, reused (no driver call per phase)
     std::map<std::string, DftTables> plans;
     std::map<std::string, PowTableOwned> pow_tables;
     std::vector<void *> owned;  // device allocations freed with the context
     size_t lde_batch_bytes = (size_t)1 << 30;  // NTT scratch budget per column batch
     int upload_batch_cols = 8;                 // columns per host->device copy batch of aero_segment_commit
+    int upload_edge_cols = -1;                 // size of its first / last batch (-1: half a batch, 0: uniform batches)
     size_t ntt_table_max_bytes = (size_t)1 << 30;  // largest full inter-pass twiddle table a plan may hold
     int shard_rank = 0, shard_world = 1;       // LDE coset shard of this context (multi-GPU)
     std::multimap<size_t, void *> free_blocks;  // exact-size cache of released device blocks
@@ -124,16 +127,27 @@ struct PhaseTimer {
     cudaStream_t s;
     PhaseTimer(aero_ctx *c, const char *name, cudaStream_t stream = nullptr, bool use_given = false)
         : ctx(c), on(c->profile), s(use_given ? stream : c->stream) {
+        if (on && !c->profile_prefix.empty() && strncmp(name, c->profile_prefix.c_str(), c->profile_prefix.size()) != 0) on = false;
         if (!on) return;
         ev.name = name;
-        cudaEventCreate(&ev.a);
-        cudaEventCreate(&ev.b);
+        ev.a = take(c);
+        ev.b = take(c);
         cudaEventRecord(ev.a, s);
     }
     ~PhaseTimer() {
         if (!on) return;
         cudaEventRecord(ev.b, s);
         ctx->pending.push_back(ev);
+    }
+    static cudaEvent_t take(aero_ctx *c) {
+        cudaEvent_t e = nullptr;
+        if (!c->event_pool.empty()) {
+            e = c->event_pool.back();
+            c->event_pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
     }
 };
 static void profile_flush(aero_ctx *ctx) {
@@ -144,8 +158,8 @@ static void profile_flush(aero_ctx *ctx) {
         auto &s = ctx->stats[p.name];
         s.calls++;
         s.ms += ms;
-        cudaEventDestroy(p.a);
-        cudaEventDestroy(p.b);
+        ctx->event_pool.push_back(p.a);
+        ctx->event_pool.push_back(p.b);
     }
     ctx->pending.clear();
 }
@@ -1056,6 +1070,7 @@ void aero_ctx_destroy(aero_ctx *ctx) {
     for (void *p : ctx->owned) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     delete ctx;
 }
 const char *aero_last_error(aero_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -1084,6 +1099,7 @@ aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value)
     else if (k == "lde_batch_bytes" && value > 0) ctx->lde_batch_bytes = (size_t)value;
     else if (k == "ntt_table_max_bytes" && value >= 0) ctx->ntt_table_max_bytes = (size_t)value;
     else if (k == "upload_batch_cols" && value >= 1 && value <= 255) ctx->upload_batch_cols = (int)value;
+    else if (k == "upload_edge_cols" && value >= -1 && value <= 255) ctx->upload_edge_cols = (int)value;
     else if (k == "cache_limit_bytes" && value >= 0) {
         ctx->cache_limit_bytes = (size_t)value;
         if (ctx->cached_bytes > ctx->cache_limit_bytes) cache_release_all(ctx);
@@ -1097,6 +1113,11 @@ void aero_ctx_set_error(aero_ctx *ctx, const char *msg) {
 aero_status aero_ctx_profile_enable(aero_ctx *ctx, int enable) {
     if (!ctx) return AERO_ERR_INVALID;
     ctx->profile = enable != 0;
+    return AERO_OK;
+}
+aero_status aero_ctx_profile_filter(aero_ctx *ctx, const char *prefix) {
+    if (!ctx) return AERO_ERR_INVALID;
+    ctx->profile_prefix = prefix ? prefix : "";
     return AERO_OK;
 }
 aero_status aero_ctx_profile_read(aero_ctx *ctx, char *json_out, size_t *len) {
@@ -1261,7 +1282,8 @@ aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint
     int batch = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->upload_batch_cols, (n_cols + 2) / 3));
     if (batch > 1 && (batch & 1)) batch++;  // even batches: each one's row hash can start as soon as it is extended
     // short first / last batches once there are enough columns for it to matter (see upload_batch_size)
-    const int edge = ((int)n_cols >= 4 * batch && batch >= 4) ? ((batch / 2) & ~1) : 0;
+    int edge = ((int)n_cols >= 4 * batch && batch >= 4) ? ((batch / 2) & ~1) : 0;
+    if (edge && ctx->upload_edge_cols >= 0) edge = std::min(ctx->upload_edge_cols & ~1, batch);
     std::vector<int> sizes;
     for (int c0 = 0; c0 < (int)n_cols;) {
         const int nc = std::min(upload_batch_size(c0, (int)n_cols, batch, edge), (int)n_cols - c0);

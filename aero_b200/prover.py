@@ -95,7 +95,9 @@ class Context:
         """Scheduling knobs of include/aero_b200.h (aero_ctx_set_option); results never change."""
         self._check(self.lib.aero_ctx_set_option(self.h, key.encode(), int(value)))
 
-    def profile_enable(self, on: bool = True) -> None:
+    def profile_enable(self, on: bool = True, only: str = "") -> None:
+        """Per-phase CUDA-event timing; ``only`` restricts it to phases whose name starts with that prefix."""
+        self._check(self.lib.aero_ctx_profile_filter(self.h, only.encode()))
         self._check(self.lib.aero_ctx_profile_enable(self.h, int(on)))
 
     def profile_read(self) -> Dict[str, Tuple[int, float]]:

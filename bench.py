@@ -215,6 +215,8 @@ def run_aero(args) -> None:
         ctx.set_option("lde_batch_bytes", args.lde_batch_mb << 20)
     if args.upload_batch_cols:
         ctx.set_option("upload_batch_cols", args.upload_batch_cols)
+    if args.upload_edge_cols >= -1:
+        ctx.set_option("upload_edge_cols", args.upload_edge_cols)
     if args.ntt_table_mb >= 0:
         ctx.set_option("ntt_table_max_bytes", args.ntt_table_mb << 20)
 
@@ -292,7 +294,11 @@ def run_aero(args) -> None:
     if rank == 0:
         sampler.start()
     launches0 = ctx.lib.aero_launch_count()
-    ctx.profile_enable(True)
+    # Inside the timed region only the dominant kernel is bracketed by CUDA events (roofline.avg_launch_ms):
+    # every timed phase costs two event records on the stream, ~0.2 ms per step when all ~25 phases are on.
+    # The other phases are read in a second, untimed pass of the same steps.
+    hash_phase = "hash_rows_w%d" % MAIN_W
+    ctx.profile_enable(True, only="" if args.quick else hash_phase)
     ms, proof = timed(step_device, args.steps)
     prof = ctx.profile_read()
     ctx.profile_enable(False)
@@ -305,6 +311,13 @@ def run_aero(args) -> None:
         single = ctx.prove(None, None, None, divs, PUB, on_device=on_device)
         assert single == proof, "sharded proof differs from the single-GPU proof"
 
+    if not args.quick:
+        ctx.profile_enable(True)
+        timed(step_device, args.steps)
+        prof_all = ctx.profile_read()
+        ctx.profile_enable(False)
+        prof_all[hash_phase] = prof.get(hash_phase, prof_all.get(hash_phase))  # the timed region's own measurement
+        prof = prof_all
     if args.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms_step, "phase_ms": {k: v[1] / args.steps for k, v in prof.items()}}))
@@ -313,6 +326,13 @@ def run_aero(args) -> None:
         step_host()
     ms_e2e, proof_h = timed(step_host, args.steps)
     ms_e2e /= args.steps
+    prof_e2e = {}
+    if args.e2e_phases:  # diagnostic, outside the timed region: per-phase events perturb the host-buffer step
+        ctx.profile_enable(True)
+        ctx.profile_read()
+        timed(step_host, args.steps)
+        prof_e2e = ctx.profile_read()
+        ctx.profile_enable(False)
     assert proof_h == proof, "host-buffer and device-buffer proofs differ"
     e2e_val = nproofs * n / (ms_e2e * 1e-3)
     h2d = (MAIN_W + AUX_W) * n * 8 + CE_COLS * N * 8
@@ -362,7 +382,10 @@ def run_aero(args) -> None:
                 "e2e": {"value": e2e_val, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-                "phase_ms_per_step": phases, "proof_bytes": len(proof)}
+                "phase_ms_per_step": phases,
+                "proof_bytes": len(proof)}
+        if prof_e2e:  # --e2e-phases: the same phases inside a host-buffer step (separate, untimed pass)
+            line["e2e_phase_ms_per_step"] = {k: round(v[1] / args.steps, 4) for k, v in sorted(prof_e2e.items())}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -388,6 +411,8 @@ def main() -> None:
     ap.add_argument("--hash-blocks-per-sm", type=int, default=0)
     ap.add_argument("--lde-batch-mb", type=int, default=0, help="NTT scratch budget per column batch (MiB); 0 = default")
     ap.add_argument("--upload-batch-cols", type=int, default=0, help="columns per host->device copy batch (0 = default 8)")
+    ap.add_argument("--upload-edge-cols", type=int, default=-2, help="first/last upload batch size (-1 = half a batch, 0 = uniform)")
+    ap.add_argument("--e2e-phases", action="store_true", help="also report per-phase times of the host-buffer step")
     ap.add_argument("--ntt-table-mb", type=int, default=-1,
                     help="largest full inter-pass NTT twiddle table per plan (MiB); 0 = running products; -1 = default")
     ap.add_argument("--trace", default="", help="profiling aid: write a chrome trace of one device-input step and exit")

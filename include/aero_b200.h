@@ -87,6 +87,11 @@ void aero_ctx_set_error(aero_ctx *ctx, const char *msg);
 /* Per-phase CUDA-event timing (mirrors the reference's debug! timers, prover/src/lib.rs:228-630).
  * aero_ctx_profile_read writes a JSON object {"phase": [calls, total_ms], ...} and resets. */
 aero_status aero_ctx_profile_enable(aero_ctx *ctx, int enable);
+/* Restricts the timing to phases whose name starts with `prefix` (NULL or "" = all phases).  Every
+ * timed phase costs two event records on the stream (~4 us of device time): a benchmark that needs
+ * one kernel's duration inside its timed region filters on that phase and reads the rest in a
+ * separate pass. */
+aero_status aero_ctx_profile_filter(aero_ctx *ctx, const char *prefix);
 aero_status aero_ctx_profile_read(aero_ctx *ctx, char *json_out, size_t *len);
 /* Number of CUDA kernels this library has launched in this process. */
 uint64_t aero_launch_count(void);
