@@ -1,6 +1,6 @@
-# diagnostics: run-to-run spread of the bench line (device-resident step and host-buffer step)
+# diagnostics: row hash of column batch k on a second stream beside the LDE of batch k+1
 mkdir -p gpurun_out
-for i in 1 2 3; do
-python bench.py --no-cpu-baseline > gpurun_out/bench_rep$i.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/bench_rep$i.json')); print(d['ms_per_step'], d['e2e']['ms_per_step'], d['clocks'])"
+python bench.py --quick --steps 5 --no-cpu-baseline 2>/dev/null | cut -c1-58
+for v in "--overlap-hash 1 --hash-blocks-per-sm 1" "--overlap-hash 1 --hash-blocks-per-sm 2" "--overlap-hash 1 --hash-blocks-per-sm 4" "--overlap-hash 1 --hash-blocks-per-sm 2 --lde-batch-mb 512"; do
+  echo "$v"; python bench.py --quick --steps 5 --no-cpu-baseline $v 2>/dev/null | cut -c1-58
 done
