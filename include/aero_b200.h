@@ -121,13 +121,15 @@ aero_status aero_segment_commit_device(aero_ctx *ctx, const uint64_t *d_cols, si
 aero_status aero_ctx_set_shard(aero_ctx *ctx, int rank, int world);
 /* Exchange window: the NVLink path of the two exchanges.  Every rank creates a
  * window of the same size (device memory, exported as a 64-byte CUDA IPC handle), the caller
- * all-gathers the handles (any transport) and attaches them in rank order.  From then on the leaf
- * array of a sharded segment and the DEEP evaluations are allocated inside the window at the same
- * offset on every rank; the row-hash kernel stores each digest into all peer windows as it is
- * produced (aero_fri_push_evaluations does the same for the DEEP evaluations), and
- * aero_window_barrier -- a stream-ordered flag barrier over the same peer mapping -- replaces the
- * all-gather: call it before aero_segment_finish_tree.  Size: 64*N bytes per committed segment of the
- * proof + 8*N for the DEEP evaluations + 4 KiB (N = LDE domain size). */
+ * all-gathers the handles (any transport) and attaches them in rank order.  From then on every
+ * sharded segment gets a coset-major staging array of leaf digests ([B][n] x 32 bytes) inside the
+ * window, at the same offset on every rank, and so do the DEEP evaluations; the row-hash kernel stores
+ * each digest into its own leaf slot and into the staging arrays of all peers as it is produced
+ * (aero_fri_push_evaluations does the same for the DEEP evaluations), and aero_window_barrier -- a
+ * stream-ordered flag barrier over the same peer mapping -- replaces the all-gather: call it before
+ * aero_segment_finish_tree, which moves the received digests to their natural leaf slots and builds
+ * the tree.  Size: 32*N bytes per committed segment of the proof + 8*N for the DEEP evaluations +
+ * 4 KiB (N = LDE domain size); larger windows are fine. */
 aero_status aero_ctx_window_create(aero_ctx *ctx, size_t bytes, uint8_t ipc_handle_out[64]);
 aero_status aero_ctx_window_attach(aero_ctx *ctx, int n_ranks, const uint8_t *ipc_handles /* n_ranks x 64 */);
 int aero_ctx_window_ranks(aero_ctx *ctx);
