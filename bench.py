@@ -166,7 +166,10 @@ def run_reference(args) -> None:
     line = {"impl": "reference", "metric": "trace_rows_per_s", "value": rps, "unit": "rows/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": workload_config(args, log_rows),
+            # same metric / unit / config as the aero arm; every step is a bounded sample of that workload (the
+            # metric is per trace row, the sample keeps all widths and options and shortens the trace)
+            "config": dict(workload_config(args, args.log_rows), reference_sample_log_rows=log_rows,
+                           parallelism="reference CPU path: %d host threads" % cores),
             "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}

@@ -102,6 +102,9 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "trace_rows_per_s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    # the arm reports on the aero arm's workload (2^20 rows), timed on a bounded sample of it
+    assert line["config"]["log_rows"] == 20 and line["config"]["reference_sample_log_rows"] == 10
+    assert line["e2e"]["value"] == line["value"] == line["cpu_baseline"]["value"]
 
 
 def test_rust_shim_bindings_match_the_headers():
