@@ -17,7 +17,7 @@
 using namespace aero;
 
 namespace aero {
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -651,7 +651,8 @@ static int upload_batch_size(int c0, int n_cols, int batch, int edge) {
     const int left = n_cols - c0;
     // keep the final batch short: stop the full batches `edge` columns before the end
     if (left > batch + edge) return batch;
-    if (left > edge) return left - edge;
+    // (even, so that the next batch still starts on a 64-byte block boundary of the row hash)
+    if (left > edge) return std::max(2, (left - edge) & ~1);
     return left;
 }
 // d_src: ncols columns (stride src_stride) of n values in ABI form, on the device.  Columns are
@@ -1022,7 +1023,7 @@ static aero_status fri_open_finish(const FriOpening &o, const GatherBatch &gb, u
 extern "C" {
 
 const char *aero_version(void) { return "aero_b200 0.1 (sm_100a)"; }
-uint64_t aero_launch_count(void) { return aero::g_launch_count; }
+uint64_t aero_launch_count(void) { return aero::g_launch_count.load(); }
 
 aero_status aero_ctx_create(const int *device_ids, int n_devices, aero_ctx **out) {
     if (!out) return AERO_ERR_INVALID;

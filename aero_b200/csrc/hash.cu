@@ -234,11 +234,9 @@ void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, in
     if (nrows == 0 || ncols == 0) return;
     uint32_t grid = (nrows + 255) / 256;
     if (max_blocks > 0 && grid > (uint32_t)max_blocks) grid = (uint32_t)max_blocks;
-    static bool attr_set = false;
-    if (!attr_set) {  // same shared-memory carve-out as the NTT passes, so both can be resident on one SM
-        cudaFuncSetAttribute(hash_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
-    }
+    static DeviceOnce once;
+    // same shared-memory carve-out as the NTT passes, so both can be resident on one SM
+    once.run([] { cudaFuncSetAttribute(hash_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); });
     AERO_COUNT_LAUNCH(1);
     hash_rows_kernel<<<grid, 256, 0, s>>>(lde, col_stride, c0, ncols, total_cols, nrows, logn, log_blowup, coset_begin,
                                           leaves, peers);

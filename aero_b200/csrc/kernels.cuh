@@ -1,5 +1,7 @@
 // Shared declarations for the aero_b200 CUDA kernels (host-callable launchers + device helpers).
 #pragma once
+#include <atomic>
+#include <mutex>
 #include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -8,8 +10,25 @@
 
 namespace aero {
 
-extern unsigned long long g_launch_count;  // kernels launched by this library (aero_launch_count)
+extern std::atomic<unsigned long long> g_launch_count;  // kernels launched by this library (aero_launch_count)
 #define AERO_COUNT_LAUNCH(n) (aero::g_launch_count += (n))
+
+// cudaFuncSetAttribute is per device: run(f) calls f once per device the calling thread has current
+// (a process may hold contexts on several GPUs, one host thread each).
+struct DeviceOnce {
+    std::mutex mu;
+    unsigned long long mask = 0;
+    template <class F>
+    void run(F &&f) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ULL << (dev & 63);
+        std::lock_guard<std::mutex> lock(mu);
+        if (mask & bit) return;
+        f();
+        mask |= bit;
+    }
+};
 
 // Two-level table for powers of a fixed base: base^e = lo[e & (2^lo_bits-1)] * hi[e >> lo_bits].
 // `hi` may carry an extra constant factor (folded scale).

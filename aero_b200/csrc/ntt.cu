@@ -386,13 +386,12 @@ void dft_fill_inter_table(const DftTables &t, uint64_t *out, cudaStream_t s) {
 
 template <int T, bool PLAIN, bool INV, bool TAB, int MAXT>
 static void launch_pass1(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce once;  // function attributes are per device
+    once.run([] {
         cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
-    }
+    });
     const int n1 = 1 << t.log1, n2 = 1 << t.log2;
     const size_t n = (size_t)1 << t.logn;
     dim3 g1(n2 / T, nc, l.ncols);
@@ -403,13 +402,12 @@ static void launch_pass1(const DftTables &t, const DftLaunch &l, int nc, int thr
 }
 template <int T, bool INV, int MAXT>
 static void launch_pass2(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce once;
+    once.run([] {
         cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
-    }
+    });
     const int n1 = 1 << t.log1;
     dim3 g2(n1 / T, nc, l.ncols);
     dft_pass2_kernel<T, INV, MAXT><<<g2, threads, smem, s>>>(l.tmp, l.dst, t.stage2, t.post_u, t.post_v, t.log1, t.log2,

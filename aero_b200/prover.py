@@ -217,12 +217,20 @@ class Context:
 
     def prove(self, main_trace, aux_trace, ce_cols, divisors: Sequence[Divisor], pub_inputs_bytes: bytes,
               options: Optional[ProofOptions] = None, aux_rands: int = 16, n_constraint_coeffs: int = 0,
-              on_device: Optional[dict] = None, shard=None) -> bytes:
+              on_device: Optional[dict] = None, shard=None, aux_builder=None, aux_width: int = 0,
+              constraint_evaluator=None) -> bytes:
         """Prover::prove.  Host mode: numpy matrices.  Device mode (``on_device`` = dict with
-        main/aux/ce device pointers and shapes): inputs already resident in HBM."""
+        main/aux/ce device pointers and shapes): inputs already resident in HBM.
+
+        ``aux_builder(rand_elements: np.ndarray) -> (aux_width, n) matrix`` and
+        ``constraint_evaluator(trace_lde: list of N-element columns, coeffs: np.ndarray) -> (n_div, N)
+        matrix`` are the two callbacks of include/aero_prover.h (the steps the north star keeps on the
+        reference's Rust path); with them ``aux_trace`` / ``ce_cols`` may be None."""
         inp = ProveInputs()
         inp.options = options or miden_options()
         keep = []
+        cb_err = []
+        n_div = len(divisors)
         if on_device is None:
             inp.trace_len = main_trace.shape[1]
             inp.main_width = main_trace.shape[0]
@@ -230,8 +238,38 @@ class Context:
             if aux_trace is not None:
                 inp.aux_width = aux_trace.shape[0]
                 inp.aux_cols = _cols(aux_trace)
-            inp.ce_cols = _cols(ce_cols)
+            if ce_cols is not None:
+                inp.ce_cols = _cols(ce_cols)
             keep += [main_trace, aux_trace, ce_cols]
+            if aux_builder is not None:
+                inp.aux_width = aux_width
+
+                def _aux(user, rands, n_rand, cols_out):
+                    try:
+                        m = np.ascontiguousarray(aux_builder(np.ctypeslib.as_array(rands, shape=(n_rand,)).copy()), np.uint64)
+                        assert m.shape == (aux_width, inp.trace_len)
+                        keep.append(m)
+                        for c in range(aux_width):
+                            cols_out[c] = ctypes.cast(m.ctypes.data + c * m.shape[1] * 8, p_u64)
+                        return AERO_OK
+                    except Exception as e:  # never let an exception cross the C boundary
+                        cb_err.append(e)
+                        return _lib.AERO_ERR_STATE
+                inp.aux_builder = _lib.AUX_BUILDER(_aux)
+            if constraint_evaluator is not None:
+                def _ce(user, lde, width, lde_size, coeffs, n_coeffs, cols_out):
+                    try:
+                        cols = [np.ctypeslib.as_array(lde[c], shape=(lde_size,)) for c in range(width)]
+                        m = np.ascontiguousarray(constraint_evaluator(cols, np.ctypeslib.as_array(coeffs, shape=(n_coeffs,)).copy() if n_coeffs else np.zeros(0, np.uint64)), np.uint64)
+                        assert m.shape == (n_div, lde_size)
+                        keep.append(m)
+                        for c in range(n_div):
+                            cols_out[c] = ctypes.cast(m.ctypes.data + c * m.shape[1] * 8, p_u64)
+                        return AERO_OK
+                    except Exception as e:
+                        cb_err.append(e)
+                        return _lib.AERO_ERR_STATE
+                inp.constraint_evaluator = _lib.CONSTRAINT_EVALUATOR(_ce)
         else:
             inp.inputs_on_device = 1
             inp.trace_len = on_device["trace_len"]
@@ -275,6 +313,8 @@ class Context:
             if st == AERO_ERR_BUFFER and ln.value > cap:
                 self._proof_buf = (c_uint8 * ln.value)()
                 continue
+            if st != AERO_OK and cb_err:
+                raise cb_err[0]
             self._check(st)
             return ctypes.string_at(buf, ln.value)
 

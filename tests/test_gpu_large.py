@@ -111,3 +111,36 @@ def test_prove_2_22_rows_accepted_by_verifier_model(ctx, oracle):
     proof = ctx.prove(main, aux, ce, divs, pub)
     rep = oracle.verify(proof, pub, 8)
     assert len(rep.positions) == 27 and len(rep.roots) >= 3
+
+
+def test_prove_2_20_rows_full_width_byte_identical(ctx_mont, oracle):
+    """BASELINE.json's headline configuration (configs[2], the bench.py workload): a 2^20-row trace at the
+    full Miden widths, 72 main + 9 aux columns, Miden 96-bit options.  The proof bytes equal the restated
+    reference prover's (about 20 s of CPU), through the Montgomery ABI form and both input routes."""
+    from aero_b200 import make_divisor
+
+    logn = 20
+    n = 1 << logn
+    main = oracle.synthetic_trace(72, n, 0xAE200000)
+    aux = oracle.synthetic_trace(9, n, 0xAE210000)
+    ce = oracle.synthetic_trace(2, 8 * n, 0xCE000000)
+    divs = [oracle.Divisor(n, 1, [pow(oracle.root_of_unity(logn), n - 1, P)]), oracle.Divisor(1, 1, [])]
+    pub = b"2^20 rows, full width"
+    ref = oracle.prove(main, aux, ce, divs, pub)
+    c2m = oracle.canon_to_mont
+    mdivs = [make_divisor(d.a, int(c2m(np.array([d.b], np.uint64))[0]),
+                          [int(v) for v in c2m(np.array(d.exemptions, np.uint64))]) for d in divs]
+    main_m, aux_m, ce_m = c2m(main), c2m(aux), c2m(ce)
+    got = ctx_mont.prove(main_m, aux_m, ce_m, mdivs, pub)
+    assert got == ref.proof_bytes
+    rep = oracle.verify(got, pub, 8)
+    assert len(rep.positions) == 27 and rep.roots[0] == ref.main.root
+    # device-resident inputs (the route bench.py's `value` times)
+    d = [ctx_mont.device_alloc(a.nbytes) for a in (main_m, aux_m, ce_m)]
+    for p, a in zip(d, (main_m, aux_m, ce_m)):
+        ctx_mont.device_upload(p, a)
+    got_d = ctx_mont.prove(None, None, None, mdivs, pub, on_device={"trace_len": n, "main_width": 72, "aux_width": 9,
+                                                                   "main": d[0], "aux": d[1], "ce": d[2]})
+    for p in d:
+        ctx_mont.device_free(p)
+    assert got_d == ref.proof_bytes

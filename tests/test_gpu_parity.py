@@ -437,3 +437,71 @@ def test_field_ops_edge_cases(ctx, oracle):
         s = 12 * (k + 1)
         assert [int(v) for v in out[4 + k]] == [(int(x) << s) % P for x in a], "mul_pow2<%d>" % s
     assert [int(v) for v in out[11]] == [(x + y) % P for x, y in zip(ai, bi)], "add_cc"
+
+
+# ------------------------------------------------------------------------------------------------
+# the callback route of aero_prove (aux_builder / constraint_evaluator, include/aero_prover.h): the
+# only route the Rust integration uses (rust/aero-gpu-prover).  Same bytes as the precomputed route.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("form", ["canonical", "montgomery"])
+@pytest.mark.parametrize("logn,wm,wa", [(8, 5, 2), (12, 72, 9)])
+def test_prove_callback_route_byte_identical(ctx, ctx_mont, oracle, logn, wm, wa, form):
+    n = 1 << logn
+    N = 8 * n
+    main = oracle.synthetic_trace(wm, n, 0xCB000000)
+    aux = oracle.synthetic_trace(wa, n, 0xCB100000)
+    ce = oracle.synthetic_trace(2, N, 0xCB200000)
+    divs = [oracle.Divisor(n, 1, [pow(oracle.root_of_unity(logn), n - 1, P)]), oracle.Divisor(1, 1, [])]
+    pub = b"callback route"
+    ref = oracle.prove(main, aux, ce, divs, pub, num_constraint_coeff_draws=6)
+    mont = form == "montgomery"
+    c = ctx_mont if mont else ctx
+    to_abi = oracle.canon_to_mont if mont else (lambda a: a)
+    from_abi = oracle.mont_to_canon if mont else (lambda a: a)
+    gdivs = [make_divisor(d.a, int(to_abi(np.array([d.b], np.uint64))[0]),
+                          [int(v) for v in to_abi(np.array(d.exemptions, np.uint64))]) for d in divs]
+    seen = {}
+
+    def aux_builder(rands):
+        # Trace::build_aux_segment receives the elements drawn after the main commitment (lib.rs:313-318)
+        seen["rands"] = [int(v) for v in from_abi(rands)]
+        return to_abi(aux)
+
+    def evaluator(lde_cols, coeffs):
+        # ConstraintEvaluator::evaluate sees the natural-order LDE of every trace column (lib.rs:350-382)
+        seen["coeffs"] = len(coeffs)
+        lde = np.stack([from_abi(col.copy()) for col in lde_cols])
+        seen["lde_ok"] = bool(np.array_equal(lde[:wm], ref.main.lde) and np.array_equal(lde[wm:], ref.aux.lde))
+        return to_abi(ce)
+
+    got = c.prove(to_abi(main), None, None, gdivs, pub, n_constraint_coeffs=6, aux_builder=aux_builder, aux_width=wa,
+                  constraint_evaluator=evaluator)
+    assert seen["rands"] == ref.aux_rand_elements and seen["coeffs"] == 6 and seen["lde_ok"]
+    assert got == ref.proof_bytes
+    # mixed: precomputed aux, evaluated constraints
+    got2 = c.prove(to_abi(main), to_abi(aux), None, gdivs, pub, n_constraint_coeffs=6, constraint_evaluator=evaluator)
+    assert got2 == ref.proof_bytes
+
+
+@pytest.mark.parametrize("logn,width", [(10, 9), (11, 72), (10, 81), (10, 33), (12, 20)])
+def test_segment_commit_overlapped_hash_chain(oracle, logn, width):
+    """overlap_hash = 1: the row hash runs per column batch on a second stream and keeps the BLAKE2s
+    chaining value between batches (hash_rows_kernel with c0 > 0).  Odd and even widths, with the short
+    first / last upload batches of the host-buffer path; digests and root equal the oracle's."""
+    c = aero_b200.Context(0, form=aero_b200.AERO_FORM_CANONICAL)
+    try:
+        c.set_option("overlap_hash", 1)
+        n = 1 << logn
+        trace = oracle.synthetic_trace(width, n, 0x0E000000 + width)
+        ref = oracle.build_trace_commitment(trace, 8)
+        seg = c.build_trace_commitment(trace, 8)
+        assert np.array_equal(seg.download_leaves(), ref.leaves), "row hashes mismatch"
+        assert seg.root == ref.root
+        d = c.device_alloc(trace.nbytes)
+        c.device_upload(d, trace)
+        c.set_option("lde_batch_bytes", 6 * 8 * n * 8)  # several column batches on the device-input path too
+        seg2 = c.build_trace_commitment_device(d, width, n, 8)
+        assert seg2.root == ref.root
+        c.device_free(d)
+    finally:
+        c.close()
