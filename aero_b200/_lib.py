@@ -47,18 +47,16 @@ AUX_BUILDER = ctypes.CFUNCTYPE(c_int, c_void_p, p_u64, c_uint32, pp_u64)
 CONSTRAINT_EVALUATOR = ctypes.CFUNCTYPE(c_int, c_void_p, pp_u64, c_uint32, c_uint64, p_u64, c_uint32, pp_u64)
 
 
-ALL_GATHER_COSETS = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_uint64, c_uint32, c_uint32, c_int, c_uint32, c_uint32)
-SUM_ROWS = ctypes.CFUNCTYPE(c_int, c_void_p, p_u64, c_uint64)
+HOST_BARRIER = ctypes.CFUNCTYPE(c_int, c_void_p)
 
 
 class ProveInputs(ctypes.Structure):
     _fields_ = [("options", ProofOptions), ("trace_len", c_uint64), ("main_width", c_uint32), ("aux_width", c_uint32),
                 ("aux_rands", c_uint32), ("inputs_on_device", c_int), ("main_cols", pp_u64), ("aux_cols", pp_u64),
                 ("ce_cols", pp_u64), ("divisors", POINTER(Divisor)), ("n_div", c_uint32),
-                ("n_constraint_coeffs", c_uint32), ("aux_builder", AUX_BUILDER),
+                ("n_constraint_coeffs", c_uint32), ("ce_blowup", c_uint32), ("aux_builder", AUX_BUILDER),
                 ("constraint_evaluator", CONSTRAINT_EVALUATOR), ("user", c_void_p), ("pub_inputs_bytes", p_u8),
-                ("pub_inputs_len", c_size_t), ("trace_meta", p_u8), ("trace_meta_len", c_uint16),
-                ("all_gather_cosets", ALL_GATHER_COSETS), ("sum_rows", SUM_ROWS)]
+                ("pub_inputs_len", c_size_t), ("trace_meta", p_u8), ("trace_meta_len", c_uint16)]
 
 
 # name -> (restype, argtypes).  Every symbol include/*.h declares is listed here; tests assert that
@@ -80,10 +78,13 @@ PROTOTYPES = {
     "aero_version": (c_char_p, []),
     "aero_ctx_window_create": (c_int, [c_void_p, c_size_t, p_u8]),
     "aero_ctx_window_attach": (c_int, [c_void_p, c_int, p_u8]),
+    "aero_ctx_window_attach_local": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),
     "aero_ctx_window_ranks": (c_int, [c_void_p]),
+    "aero_ctx_set_host_barrier": (c_int, [c_void_p, HOST_BARRIER, c_void_p]),
+    "aero_ctx_shard_begin": (c_int, [c_void_p, c_char_p]),
+    "aero_ctx_shard_end": (c_int, [c_void_p, c_int]),
     "aero_window_barrier": (c_int, [c_void_p]),
-    "aero_fri_push_evaluations": (c_int, [c_void_p]),
-    "aero_upload_start": (c_int, [c_void_p, pp_u64, c_uint32, c_uint64, c_int, POINTER(c_void_p)]),
+    "aero_upload_start": (c_int, [c_void_p, pp_u64, c_uint32, c_uint64, c_int, c_int, POINTER(c_void_p)]),
     "aero_upload_wait": (c_int, [c_void_p, POINTER(c_void_p)]),
     "aero_upload_free": (None, [c_void_p]),
     # segments
@@ -91,12 +92,6 @@ PROTOTYPES = {
     "aero_segment_commit_device": (c_int, [c_void_p, c_void_p, c_size_t, c_uint32, c_uint64, c_uint32, c_int,
                                            POINTER(c_void_p), p_u8]),
     "aero_ctx_set_shard": (c_int, [c_void_p, c_int, c_int]),
-    "aero_segment_leaves_device": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_uint32),
-                                           POINTER(c_uint32)]),
-    "aero_segment_finish_tree": (c_int, [c_void_p, p_u8]),
-    "aero_fri_evaluations_device": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint64), POINTER(c_uint32),
-                                            POINTER(c_uint32)]),
-    "aero_fri_mark_complete": (c_int, [c_void_p]),
     "aero_segment_destroy": (None, [c_void_p]),
     "aero_segment_info": (c_int, [c_void_p, POINTER(c_uint32), POINTER(c_uint64), POINTER(c_uint32)]),
     "aero_segment_download_lde": (c_int, [c_void_p, pp_u64]),
@@ -128,6 +123,7 @@ PROTOTYPES = {
     # standalone
     "aero_commit_rows_device": (c_int, [c_void_p, c_void_p, c_size_t, c_uint32, c_uint64, p_u8]),
     "aero_test_field_ops": (c_int, [c_void_p, p_u64, p_u64, c_size_t, p_u64]),
+    "aero_measure_alu_peak": (c_int, [c_void_p, POINTER(ctypes.c_double)]),
     "aero_device_alloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "aero_device_free": (c_int, [c_void_p, c_void_p]),
     "aero_device_upload": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
@@ -135,6 +131,12 @@ PROTOTYPES = {
     "aero_device_sync": (c_int, [c_void_p]),
     # host driver (aero_prover.h)
     "aero_prove": (c_int, [c_void_p, POINTER(ProveInputs), p_u8, POINTER(c_size_t)]),
+    "aero_group_create": (c_int, [POINTER(c_int), c_int, c_size_t, POINTER(c_void_p)]),
+    "aero_group_destroy": (None, [c_void_p]),
+    "aero_group_size": (c_int, [c_void_p]),
+    "aero_group_ctx": (c_void_p, [c_void_p, c_int]),
+    "aero_group_last_error": (c_char_p, [c_void_p]),
+    "aero_group_prove": (c_int, [c_void_p, POINTER(ProveInputs), c_int, p_u8, POINTER(c_size_t)]),
     "aero_host_blake2s": (None, [p_u8, c_size_t, p_u8]),
     "aero_host_hash_elements": (None, [p_u64, c_size_t, p_u8]),
     "aero_coin_new": (c_void_p, [p_u8, c_size_t]),

@@ -6,7 +6,7 @@ import shutil
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["csrc/abi.cu", "csrc/ntt.cu", "csrc/hash.cu", "csrc/poly.cu", "csrc/fri.cu", "host/prover.cpp"]
+SOURCES = ["csrc/abi.cu", "csrc/ntt.cu", "csrc/hash.cu", "csrc/poly.cu", "csrc/fri.cu", "csrc/peak.cu", "host/prover.cpp"]
 HEADERS = ["csrc/gl.cuh", "csrc/blake2s.cuh", "csrc/kernels.cuh", "csrc/ntt.cuh", "host/prover.hpp",
            "../include/aero_b200.h", "../include/aero_prover.h"]
 LIB = os.path.join(_HERE, "libaero_b200.so")

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <set>
 #include <string>
 #include <vector>
@@ -42,6 +43,7 @@ struct aero_upload {
     uint64_t *d = nullptr;          // n_cols x n_rows, contiguous columns
     cudaEvent_t done = nullptr;
     std::vector<const uint64_t *> cols;
+    int col_begin = 0, col_end = 0;  // columns actually copied (a sharded context may take its own only)
     uint64_t n_rows = 0;
     bool queued = false;
 };
@@ -51,23 +53,33 @@ struct aero_ctx {
     cudaStream_t stream = 0;
     cudaStream_t copy_stream = nullptr;  // host->device uploads overlapped with compute
     cudaStream_t hash_stream = nullptr;  // row hashing of batch k overlapped with the LDE of batch k+1
-    cudaEvent_t ev_lde = nullptr, ev_hash = nullptr;
+    cudaEvent_t ev_lde = nullptr, ev_hash = nullptr, ev_copy_order = nullptr;
     bool overlap_hash = false;           // aero_ctx_set_option("overlap_hash"); measured slower on B200, see DESIGN.md
     bool force_split_intt = false;       // test hook: take the B x size-n route of constraints_into_poly at any size
     std::map<std::string, uint64_t *> const_tables;
     std::vector<aero_upload *> deferred_uploads;  // queued behind the next segment commit's own copies
-    // Exchange window (multi-GPU): one allocation per rank, the same size everywhere, opened by every
-    // peer through CUDA IPC.  [0, 4096): barrier flags and the time-out word; the rest is a bump heap
+    // Exchange window (multi-GPU): one allocation per rank, the same size everywhere, mapped by every
+    // peer (CUDA IPC across processes, plain peer access inside one).  [0, 4096): barrier flags and the time-out word; the rest is a bump heap
     // that all ranks of a sharded proof allocate from in the same order, so a buffer sits at the same
     // offset in every window and a kernel can store to its peer copies directly over NVLink.
     uint8_t *win = nullptr;
     size_t win_bytes = 0, win_off = 4096;
     int win_live = 0;
-    int win_ranks = 0;                       // > 1 once the peers are attached and "use_window" is on
-    int win_attached = 0;
-    uint8_t *win_peer[AERO_MAX_PEERS] = {};  // peer windows, in increasing rank order, own rank skipped
-    int win_peer_rank[AERO_MAX_PEERS] = {};
+    int win_ranks = 0;                       // > 1 once the peers are attached
+    uint8_t *win_base[AERO_MAX_RANKS] = {};  // every rank's window as mapped here (win_base[shard_rank] == win)
+    bool win_ipc[AERO_MAX_RANKS] = {};       // mapped with cudaIpcOpenMemHandle (closed with the context)
     unsigned long long win_epoch = 0;
+    // Barriers between the ranks are device-side flag barriers (no host involvement) once a proof shape is
+    // warm.  While a context may still call cudaMalloc -- the first proof of a shape -- a rank spinning on
+    // the device could block a peer's allocation, so those proofs synchronise on the host instead:
+    // stream sync + the caller's rendezvous (aero_ctx_set_host_barrier).
+    bool win_host_sync = true;
+    aero_host_barrier_fn host_barrier = nullptr;
+    void *host_barrier_user = nullptr;
+    std::set<std::string> warm_shapes;
+    std::string cur_shape;
+    bool force_host_sync = false;            // test hook: never switch to device-side barriers
+    bool own_stream = false;                 // `stream` was created by aero_ctx_create_stream
     int hash_blocks_per_sm = 2;          // grid cap of an overlapped row-hash launch ("hash_blocks_per_sm")
     int num_sms = 148;
     int form = AERO_FORM_MONTGOMERY;
@@ -216,6 +228,31 @@ static void dev_free(aero_ctx *ctx, void *p) {
     ctx->cached_bytes += bytes;
     if (ctx->cached_bytes > ctx->cache_limit_bytes) cache_release_all(ctx);
 }
+// temporary device blocks of one call: returned to the cache when the call ends, also on error paths
+struct DevBlocks {
+    aero_ctx *ctx;
+    std::vector<void *> v;
+    explicit DevBlocks(aero_ctx *c) : ctx(c) {}
+    DevBlocks(const DevBlocks &) = delete;
+    aero_status alloc(void **p, size_t bytes) {
+        aero_status st = dev_alloc(ctx, p, bytes);
+        if (st == AERO_OK) v.push_back(*p);
+        return st;
+    }
+    aero_status alloc_shared(void **p, size_t bytes);
+    ~DevBlocks() {
+        for (void *p : v) dev_free(ctx, p);
+    }
+};
+struct SegmentDeleter {
+    void operator()(aero_segment *s) const { aero_segment_destroy(s); }
+};
+using SegmentGuard = std::unique_ptr<aero_segment, SegmentDeleter>;
+struct FriDeleter {
+    void operator()(aero_fri *f) const { aero_fri_destroy(f); }
+};
+using FriGuard = std::unique_ptr<aero_fri, FriDeleter>;
+
 // Pinned host / device staging pair for small result downloads (OOD frame, openings): results land
 // in pinned memory so that several downloads can be queued before the single synchronisation.
 static aero_status stage_reserve(aero_ctx *ctx, size_t total) {
@@ -232,10 +269,17 @@ static aero_status stage_reserve(aero_ctx *ctx, size_t total) {
     ctx->stage_bytes = cap;
     return AERO_OK;
 }
-// Buffers that other ranks write into (leaf digests, DEEP evaluations) live in the exchange window
-// when one is attached; otherwise this is dev_alloc.
+static bool ctx_sharded(const aero_ctx *ctx) { return ctx->shard_world > 1; }
+static aero_status window_barrier(aero_ctx *ctx);
+// Buffers that other ranks write into (coefficients, leaf digests, sub-roots, DEEP evaluations, opening
+// results) live in the exchange window of a sharded context; otherwise this is dev_alloc.
 static aero_status dev_alloc_shared(aero_ctx *ctx, void **p, size_t bytes) {
-    if (ctx->win_ranks > 1 && ctx->shard_world > 1) {
+    if (ctx_sharded(ctx)) {
+        if (ctx->win_ranks != ctx->shard_world)
+            CTX_FAIL(ctx, AERO_ERR_STATE, "sharded context (%d ranks) has no exchange window attached", ctx->shard_world);
+        // first allocation after the heap was reset: every rank must be done with the previous contents
+        // before anyone stores into them again (the ranks allocate in the same order, so all arrive here)
+        if (ctx->win_live == 0) TRY(window_barrier(ctx));
         bytes = (bytes + 511) & ~(size_t)511;
         if (ctx->win_off + bytes > ctx->win_bytes)
             CTX_FAIL(ctx, AERO_ERR_NOMEM, "exchange window too small: %zu bytes needed, %zu of %zu in use", bytes, ctx->win_off, ctx->win_bytes);
@@ -246,32 +290,46 @@ static aero_status dev_alloc_shared(aero_ctx *ctx, void **p, size_t bytes) {
     }
     return dev_alloc(ctx, p, bytes);
 }
-// the copies of a window buffer in the peer windows (empty when `p` is not in the window)
-static PeerPtrs peers_of(const aero_ctx *ctx, const void *p) {
-    PeerPtrs q;
-    if (ctx->win_ranks > 1 && win_owns(ctx, p)) {
+// the copies of a buffer on every rank (only the own rank's for a buffer outside the window)
+static RankPtrs rank_ptrs(const aero_ctx *ctx, const void *p) {
+    RankPtrs q;
+    for (int r = 0; r < AERO_MAX_RANKS; r++) q.p[r] = nullptr;
+    q.p[ctx_sharded(ctx) ? ctx->shard_rank : 0] = const_cast<void *>(p);
+    if (ctx_sharded(ctx) && win_owns(ctx, p)) {
         const size_t off = (const uint8_t *)p - ctx->win;
-        q.n = ctx->win_ranks - 1;
-        for (int i = 0; i < q.n; i++) q.p[i] = ctx->win_peer[i] + off;
+        for (int r = 0; r < ctx->win_ranks; r++) q.p[r] = ctx->win_base[r] + off;
     }
     return q;
 }
 static aero_status window_barrier(aero_ctx *ctx) {
-    if (ctx->win_ranks <= 1 || ctx->shard_world <= 1) return AERO_OK;
-    PeerPtrs f;
-    f.n = ctx->win_ranks - 1;
-    for (int i = 0; i < f.n; i++) f.p[i] = ctx->win_peer[i];
-    peer_barrier((unsigned long long *)ctx->win, f, ctx->shard_rank, ctx->win_peer_rank, ++ctx->win_epoch,
-                 (unsigned int *)(ctx->win + 2048), ctx->stream);
+    if (!ctx_sharded(ctx)) return AERO_OK;
+    if (ctx->win_host_sync) {
+        if (!ctx->host_barrier) CTX_FAIL(ctx, AERO_ERR_STATE, "sharded context needs a host barrier (aero_ctx_set_host_barrier) until a proof shape is warm");
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->host_barrier(ctx->host_barrier_user) != AERO_OK) CTX_FAIL(ctx, AERO_ERR_STATE, "host barrier failed: a peer rank did not arrive");
+        return AERO_OK;
+    }
+    peer_barrier(rank_ptrs(ctx, ctx->win), ctx->shard_world, ctx->shard_rank, ++ctx->win_epoch, (unsigned int *)(ctx->win + 2048),
+                 ctx->stream);
     CUDA_TRY(ctx, cudaGetLastError());
-    if (getenv("AERO_WINDOW_DEBUG")) {
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        unsigned long long fl[8];
-        unsigned int to = 0;
-        cudaMemcpy(fl, ctx->win, 64, cudaMemcpyDeviceToHost);
-        cudaMemcpy(&to, ctx->win + 2048, 4, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[window] rank %d epoch %llu sync=%s flags=[%llu %llu %llu %llu] timeouts=%u\n", ctx->shard_rank,
-                ctx->win_epoch, cudaGetErrorString(e), fl[0], fl[1], fl[2], fl[3], to);
+    return AERO_OK;
+}
+aero_status DevBlocks::alloc_shared(void **p, size_t bytes) {
+    aero_status st = dev_alloc_shared(ctx, p, bytes);
+    if (st == AERO_OK) v.push_back(*p);
+    return st;
+}
+// A peer that never reached a device-side barrier (it failed) is reported here instead of hanging the
+// GPU.  The time-out count is cleared once reported, so the context stays usable after the ranks are
+// back in lock-step.
+static aero_status window_check(aero_ctx *ctx) {
+    if (!ctx_sharded(ctx) || ctx->win_host_sync) return AERO_OK;
+    unsigned int t = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&t, ctx->win + 2048, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (t) {
+        cudaMemsetAsync(ctx->win + 2048, 0, 4, ctx->stream);
+        CTX_FAIL(ctx, AERO_ERR_STATE, "exchange barrier timed out %u time(s): a peer rank did not arrive", t);
     }
     return AERO_OK;
 }
@@ -484,38 +542,50 @@ static aero_status get_pow_table(aero_ctx *ctx, const std::string &key, uint64_t
 struct aero_segment {
     aero_ctx *ctx = nullptr;
     int ncols = 0, logn = 0, log_blowup = -1;  // log_blowup < 0: polys only, not yet extended
-    uint64_t *polys = nullptr;                 // ncols x n, canonical coefficients
-    uint64_t *lde = nullptr;                   // ncols x N, coset-major (coset r, i) -> natural B*i + r
-    uint32_t *full = nullptr;                  // 2N digests, heap layout, leaf k at N + k
+    uint64_t *polys = nullptr;                 // ncols x n, canonical coefficients (all columns, on every rank)
+    uint64_t *lde = nullptr;                   // ncols x (coset_count * n), coset-major: (local coset q, i) -> natural B*i + coset_begin + q
+    // Commitment.  With G ranks, rank r owns the leaf block [r*N/G, (r+1)*N/G) = LDE rows of
+    // i in [r*nb, (r+1)*nb), nb = n/G, and the subtree above it (merkle/concurrent.rs:21-70 splits the
+    // tree the same way); G = 1 is the whole tree.
+    uint32_t *leaf_stage = nullptr;            // [B][nb] digests of the block, coset-major: leaf B*il + c at c*nb + il
+    uint32_t *heap = nullptr;                  // B*nb digests: the block's subtree in heap layout, heap[1] = sub-root
+    uint32_t *top = nullptr;                   // 2G digests: nodes 1 .. 2G-1 of the whole tree, top[1] = root
     // coset shard (multi-GPU): this rank stores cosets [coset_begin, coset_begin + coset_count) only,
     // compactly: lde[c][q][i] with q = r - coset_begin, column stride coset_count * n.
     int coset_begin = 0, coset_count = 0;
-    bool tree_pending = false;                 // leaves of other ranks still missing
-    // sharded proof over the exchange window: the digests of the OTHER ranks' rows arrive here,
-    // coset-major ([B][n] x 32 bytes, so a rank's contribution is one contiguous block that its
-    // row-hash kernel streams over NVLink); interleaved into `full` before the tree is built
-    uint32_t *leaf_stage = nullptr;
+    int logG = 0;
     uint64_t n() const { return 1ULL << logn; }
     uint64_t N() const { return 1ULL << (logn + log_blowup); }
     uint64_t lde_stride() const { return (uint64_t)coset_count << logn; }
+    uint32_t nb() const { return 1u << (logn - logG); }
+    SegTreeView tree_view() const { return SegTreeView{leaf_stage, heap, top, logn, log_blowup, logG, ctx->shard_rank}; }
 };
 
+// this rank's share of the columns of a matrix (interpolation is sharded by column, extension by coset)
+static void own_columns(const aero_ctx *ctx, int ncols, int *cb, int *ce) {
+    *cb = (int)((long long)ctx->shard_rank * ncols / ctx->shard_world);
+    *ce = (int)((long long)(ctx->shard_rank + 1) * ncols / ctx->shard_world);
+}
+
+// All digests of this rank's leaf block are in `leaf_stage` (after a barrier when other ranks wrote
+// some of them): build the block's subtree, exchange the G sub-roots, finish the top levels.
 static aero_status segment_finish_tree(aero_segment *seg, uint8_t root[32]) {
     aero_ctx *ctx = seg->ctx;
+    const int G = ctx->shard_world;
+    TRY(window_barrier(ctx));
     {
         PhaseTimer t(ctx, "merkle");
-        if (seg->leaf_stage)  // digests the peers stored into the window -> natural leaf slots
-            leaves_from_stage(seg->leaf_stage, seg->full + (size_t)seg->N() * 8, seg->logn, seg->log_blowup, seg->coset_begin,
-                              seg->coset_count, ctx->stream);
-        merkle_build(seg->full, seg->N(), ctx->stream);
+        merkle_build_block(seg->leaf_stage, seg->heap, seg->nb(), seg->log_blowup, ctx->stream);
+        merkle_push_subroot(seg->heap, rank_ptrs(ctx, seg->top), G, ctx->shard_rank, ctx->stream);
     }
-    seg->tree_pending = false;
+    TRY(window_barrier(ctx));
+    merkle_top(seg->top, G, ctx->stream);
     CUDA_TRY(ctx, cudaGetLastError());
     if (root) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(root, seg->full + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(root, seg->top + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    return AERO_OK;
+    return window_check(ctx);
 }
 
 // ---- building blocks of a segment commitment ----------------------------------------------------
@@ -525,17 +595,17 @@ static aero_status segment_alloc_lde(aero_segment *seg, int log_blowup, const Df
     if (log_blowup < 1 || log_blowup > 6) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "blowup must be 2..64");
     if (seg->logn + log_blowup > 31) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "LDE domain too large");
     seg->log_blowup = log_blowup;
-    const int B = 1 << log_blowup;
-    if (B % ctx->shard_world) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "shard world size %d must divide the blowup factor %d", ctx->shard_world, B);
-    seg->coset_count = B / ctx->shard_world;
+    const int B = 1 << log_blowup, G = ctx->shard_world;
+    if (B % G) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "shard world size %d must divide the blowup factor %d", G, B);
+    seg->logG = ilog2((uint64_t)G);
+    if (seg->logn < seg->logG) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "trace of %llu rows is too short for %d ranks", (unsigned long long)seg->n(), G);
+    seg->coset_count = B / G;
     seg->coset_begin = ctx->shard_rank * seg->coset_count;
+    const size_t block = (size_t)seg->N() >> seg->logG;  // leaves of this rank's block
     TRY(dev_alloc(ctx, (void **)&seg->lde, (size_t)seg->ncols * seg->lde_stride() * 8));
-    if (ctx->win_ranks > 1 && ctx->shard_world > 1) {
-        TRY(dev_alloc_shared(ctx, (void **)&seg->leaf_stage, (size_t)seg->N() * 32));
-        TRY(dev_alloc(ctx, (void **)&seg->full, (size_t)2 * seg->N() * 32));
-    } else {
-        TRY(dev_alloc(ctx, (void **)&seg->full, (size_t)2 * seg->N() * 32));
-    }
+    TRY(dev_alloc_shared(ctx, (void **)&seg->leaf_stage, block * 32));
+    TRY(dev_alloc_shared(ctx, (void **)&seg->top, (size_t)2 * G * 32));
+    TRY(dev_alloc(ctx, (void **)&seg->heap, block * 32));
     return plan_lde(ctx, seg->logn, log_blowup, false, plan);
 }
 static int segment_lde_batch_cols(aero_segment *seg) {
@@ -570,11 +640,11 @@ static void segment_lde_batch(aero_segment *seg, const DftTables *plan, int c0, 
 // 4..1 hash blocks per SM) -- IMAD.WIDE blocks the ALU issue port too (tools/int_peak.cu), so the
 // NTT passes leave no usable ALU slack for the hash to fill.
 static bool segment_hash_overlapped(const aero_segment *seg) {
-    return seg->ctx->overlap_hash && seg->ncols > 2 && seg->ctx->win_ranks <= 1;
+    return seg->ctx->overlap_hash && seg->ncols > 2 && !ctx_sharded(seg->ctx);
 }
 static aero_status segment_hash_batch(aero_segment *seg, int c0, int nc) {
     aero_ctx *ctx = seg->ctx;
-    const uint64_t N = seg->N(), Nl = seg->lde_stride();
+    const uint64_t Nl = seg->lde_stride();
     cudaStream_t hs = ctx->stream;
     if (segment_hash_overlapped(seg)) {
         if (!ctx->hash_stream) {
@@ -586,17 +656,13 @@ static aero_status segment_hash_batch(aero_segment *seg, int c0, int nc) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_lde, ctx->stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(hs, ctx->ev_lde, 0));
     }
-    uint32_t *leaves = seg->full + (size_t)N * 8;
-    const PeerPtrs peers = seg->leaf_stage ? peers_of(ctx, seg->leaf_stage) : PeerPtrs{};
-    // the peers' staging arrays may still be in use by their previous proof
-    if (peers.n && c0 == 0) TRY(window_barrier(ctx));
     char nm[32];
     snprintf(nm, sizeof nm, "hash_rows_w%d", seg->ncols);
     PhaseTimer t(ctx, nm, hs, true);
     // the last column range has no NTT beside it: give it the whole GPU
     const bool alone = hs == ctx->stream || c0 + nc == seg->ncols;
-    hash_rows_lde(seg->lde, Nl, c0, nc, seg->ncols, seg->logn, seg->log_blowup, seg->coset_begin, (uint32_t)Nl, leaves,
-                  peers, alone ? 0 : ctx->hash_blocks_per_sm * ctx->num_sms, hs);
+    hash_rows_lde(seg->lde, Nl, c0, nc, seg->ncols, seg->logn, (uint32_t)seg->coset_begin, (uint32_t)Nl, seg->logn - seg->logG,
+                  rank_ptrs(ctx, seg->leaf_stage), alone ? 0 : ctx->hash_blocks_per_sm * ctx->num_sms, hs);
     return AERO_OK;
 }
 // all column ranges hashed -> join the hash stream, then the tree
@@ -606,39 +672,30 @@ static aero_status segment_tree_after_hash(aero_segment *seg, uint8_t root[32]) 
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_hash, ctx->hash_stream));
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_hash, 0));
     }
-    CUDA_TRY(ctx, cudaMemsetAsync(seg->full, 0, 64, ctx->stream));
-    if (ctx->shard_world > 1) {
-        // leaves of the other ranks' cosets arrive through the caller's exchange; see
-        // aero_segment_leaves_device / aero_segment_finish_tree
-        seg->tree_pending = true;
-        if (root) memset(root, 0, 32);
-        CUDA_TRY(ctx, cudaGetLastError());
-        return AERO_OK;
-    }
+    CUDA_TRY(ctx, cudaMemsetAsync(seg->heap, 0, 32, ctx->stream));
     return segment_finish_tree(seg, root);
 }
 
-// coefficients already on the device -> LDE + commitment (CompositionPoly::evaluate + commit_to_rows)
+// coefficients already on the device (all columns, on every rank) -> LDE + commitment
+// (CompositionPoly::evaluate + commit_to_rows)
 static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint8_t root[32]) {
     aero_ctx *ctx = seg->ctx;
     const DftTables *plan;
     TRY(segment_alloc_lde(seg, log_blowup, &plan));
     const int batch = segment_lde_batch_cols(seg);
-    uint64_t *tmp = nullptr;
-    if (plan->log1 != 0) TRY(dev_alloc(ctx, (void **)&tmp, (size_t)batch * seg->lde_stride() * 8));
-    aero_status st = AERO_OK;
+    DevBlocks tmp(ctx);
+    uint64_t *tmp_l = nullptr;
+    if (plan->log1 != 0) TRY(tmp.alloc((void **)&tmp_l, (size_t)batch * seg->lde_stride() * 8));
     if ((batch & 1) || !segment_hash_overlapped(seg)) {  // extend everything, then one hash launch
-        for (int c0 = 0; c0 < seg->ncols; c0 += batch) segment_lde_batch(seg, plan, c0, std::min(batch, seg->ncols - c0), tmp);
-        st = segment_hash_batch(seg, 0, seg->ncols);
+        for (int c0 = 0; c0 < seg->ncols; c0 += batch) segment_lde_batch(seg, plan, c0, std::min(batch, seg->ncols - c0), tmp_l);
+        TRY(segment_hash_batch(seg, 0, seg->ncols));
     } else {
-        for (int c0 = 0; c0 < seg->ncols && st == AERO_OK; c0 += batch) {
+        for (int c0 = 0; c0 < seg->ncols; c0 += batch) {
             const int nc = std::min(batch, seg->ncols - c0);
-            segment_lde_batch(seg, plan, c0, nc, tmp);
-            st = segment_hash_batch(seg, c0, nc);
+            segment_lde_batch(seg, plan, c0, nc, tmp_l);
+            TRY(segment_hash_batch(seg, c0, nc));
         }
     }
-    dev_free(ctx, tmp);
-    if (st != AERO_OK) return st;
     return segment_tree_after_hash(seg, root);
 }
 
@@ -655,10 +712,14 @@ static int upload_batch_size(int c0, int n_cols, int batch, int edge) {
     if (left > edge) return std::max(2, (left - edge) & ~1);
     return left;
 }
-// d_src: ncols columns (stride src_stride) of n values in ABI form, on the device.  Columns are
-// processed in batches (interpolate, then extend); when `ready` is given, batch b first waits for
-// ready[b] -- the event that says its host->device copy has landed -- so uploads overlap compute.
-static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, size_t src_stride, uint32_t n_cols,
+// d_src: columns [src_col0, ...) of the matrix (column c at d_src + (c - src_col0) * src_stride), n values
+// each in ABI form, on the device; this rank reads its own columns only (own_columns).  They are
+// processed in batches (interpolate, extend); when `ready` is given, batch b first waits for ready[b] --
+// the event that says its host->device copy has landed -- so uploads overlap compute.  In a sharded
+// proof every batch of coefficients is also pushed into the peers' copies of `polys` as soon as it
+// exists (NVLink stores under the next batch's upload and transform); after the barrier the columns
+// the other ranks interpolated are extended too.
+static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, size_t src_stride, int src_col0, uint32_t n_cols,
                                        uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
                                        uint8_t root[32], int batch_cols = 0, const cudaEvent_t *ready = nullptr, int edge_cols = 0) {
     if (!out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null output handle");
@@ -668,72 +729,81 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
     if (!is_pow2(blowup) || blowup < 2) CTX_FAIL(ctx, AERO_ERR_INVALID, "blowup factor must be a power of two >= 2, got %u", blowup);
     const int logn = ilog2(n_rows);
     if (logn > NTT_MAX_LOG) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "trace length 2^%d unsupported (max 2^%d)", logn, NTT_MAX_LOG);
-    aero_segment *seg = new aero_segment();
+    SegmentGuard seg(new aero_segment());
     seg->ctx = ctx;
     seg->ncols = (int)n_cols;
     seg->logn = logn;
     const bool mont = ctx->form == AERO_FORM_MONTGOMERY;
+    const bool sharded = ctx_sharded(ctx);
     const DftTables *iplan = nullptr, *lplan = nullptr;
+    DevBlocks tmp(ctx);
     uint64_t *tmp_i = nullptr, *tmp_l = nullptr;
-    aero_status st = dev_alloc(ctx, (void **)&seg->polys, (size_t)n_cols * n_rows * 8);
-    if (st == AERO_OK && !input_is_coeffs) st = plan_intt(ctx, logn, mont, &iplan);
-    if (st == AERO_OK) st = segment_alloc_lde(seg, ilog2(blowup), &lplan);
-    int batch = 0, ibatch = 0;
-    if (st == AERO_OK) {
-        batch = batch_cols > 0 ? std::min<int>(batch_cols, (int)n_cols) : segment_lde_batch_cols(seg);
-        // Inputs already on the device: the inverse transforms of many LDE batches share one launch
-        // pair (a 16-column interpolation is only ~7 waves of blocks); uploads in flight keep the
-        // per-batch order so that batch b waits for ready[b] only.
-        ibatch = batch;
-        if (!ready && !input_is_coeffs) {
-            const size_t fit = ctx->lde_batch_bytes / ((size_t)n_rows * 8);
-            ibatch = (int)std::min<size_t>(n_cols, std::max<size_t>(batch, fit / batch * batch));
-        }
-        if (iplan && iplan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp_i, (size_t)ibatch * n_rows * 8);
+    TRY(dev_alloc_shared(ctx, (void **)&seg->polys, (size_t)n_cols * n_rows * 8));
+    if (!input_is_coeffs) TRY(plan_intt(ctx, logn, mont, &iplan));
+    TRY(segment_alloc_lde(seg.get(), ilog2(blowup), &lplan));
+    int cb = 0, ce = (int)n_cols;
+    own_columns(ctx, (int)n_cols, &cb, &ce);
+    const int lde_batch = segment_lde_batch_cols(seg.get());
+    const int batch = batch_cols > 0 ? std::min<int>(batch_cols, std::max(1, ce - cb)) : lde_batch;
+    // Inputs already on the device: the inverse transforms of many LDE batches share one launch
+    // pair (a 16-column interpolation is only ~7 waves of blocks); uploads in flight keep the
+    // per-batch order so that batch b waits for ready[b] only.
+    int ibatch = batch;
+    if (!ready && !input_is_coeffs) {
+        const size_t fit = ctx->lde_batch_bytes / ((size_t)n_rows * 8);
+        ibatch = (int)std::min<size_t>(n_cols, std::max<size_t>(batch, fit / batch * batch));
     }
-    if (st == AERO_OK && lplan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp_l, (size_t)batch * seg->lde_stride() * 8);
-    if (st == AERO_OK) {
-        const bool per_batch_hash = !(batch & 1) && segment_hash_overlapped(seg);
-        char nm[32];
-        snprintf(nm, sizeof nm, "interpolate_w%d", (int)n_cols);
-        // edge_cols > 0 (uploads in flight): the first and the last batch are short -- the first so that
-        // compute starts early, the last so that little work is left once the final copy has landed
-        for (int c0 = 0, b = 0, nc = 0; c0 < (int)n_cols; c0 += nc, b++) {
-            nc = std::min(upload_batch_size(c0, (int)n_cols, batch, edge_cols), (int)n_cols - c0);
-            if (ready) cudaStreamWaitEvent(ctx->stream, ready[b], 0);
-            if (input_is_coeffs) {
-                const uint64_t *src = d_src + (size_t)c0 * src_stride;
-                uint64_t *dst = seg->polys + (size_t)c0 * n_rows;
-                PhaseTimer t(ctx, "convert");
-                for (int c = 0; c < nc; c++) {
-                    if (mont) convert_form(src + (size_t)c * src_stride, dst + (size_t)c * n_rows, n_rows, 0, ctx->stream);
-                    else cudaMemcpyAsync(dst + (size_t)c * n_rows, src + (size_t)c * src_stride, n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream);
-                }
-            } else if (edge_cols > 0 || c0 % ibatch == 0) {
-                PhaseTimer t(ctx, nm);
-                DftLaunch l;
-                l.src = d_src + (size_t)c0 * src_stride;
-                l.dst = seg->polys + (size_t)c0 * n_rows;
-                l.tmp = tmp_i;
-                l.src_col_stride = src_stride;
-                l.dst_col_stride = n_rows;
-                l.ncols = edge_cols > 0 ? nc : std::min(ibatch, (int)n_cols - c0);
-                l.deinterleave_log = 0;
-                dft_run(*iplan, l, ctx->stream);
+    if (iplan && iplan->log1 != 0) TRY(tmp.alloc((void **)&tmp_i, (size_t)ibatch * n_rows * 8));
+    if (lplan->log1 != 0) TRY(tmp.alloc((void **)&tmp_l, (size_t)std::max(batch, lde_batch) * seg->lde_stride() * 8));
+    const bool per_batch_hash = !(batch & 1) && segment_hash_overlapped(seg.get());
+    char nm[32];
+    snprintf(nm, sizeof nm, "interpolate_w%d", (int)n_cols);
+    const RankPtrs polys_all = rank_ptrs(ctx, seg->polys);
+    // edge_cols > 0 (uploads in flight): the first and the last batch are short -- the first so that
+    // compute starts early, the last so that little work is left once the final copy has landed
+    for (int c0 = cb, b = 0, nc = 0; c0 < ce; c0 += nc, b++) {
+        nc = std::min(upload_batch_size(c0 - cb, ce - cb, batch, edge_cols), ce - c0);
+        if (ready) cudaStreamWaitEvent(ctx->stream, ready[b], 0);
+        const uint64_t *src = d_src + (size_t)(c0 - src_col0) * src_stride;
+        int done = nc;  // columns whose coefficients exist after this step, starting at c0
+        if (input_is_coeffs) {
+            uint64_t *dst = seg->polys + (size_t)c0 * n_rows;
+            PhaseTimer t(ctx, "convert");
+            for (int c = 0; c < nc; c++) {
+                if (mont) convert_form(src + (size_t)c * src_stride, dst + (size_t)c * n_rows, n_rows, 0, ctx->stream);
+                else CUDA_TRY(ctx, cudaMemcpyAsync(dst + (size_t)c * n_rows, src + (size_t)c * src_stride, n_rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
             }
-            segment_lde_batch(seg, lplan, c0, nc, tmp_l);
-            if (per_batch_hash && st == AERO_OK) st = segment_hash_batch(seg, c0, nc);
+        } else if (edge_cols > 0 || (c0 - cb) % ibatch == 0) {
+            PhaseTimer t(ctx, nm);
+            DftLaunch l;
+            l.src = src;
+            l.dst = seg->polys + (size_t)c0 * n_rows;
+            l.tmp = tmp_i;
+            l.src_col_stride = src_stride;
+            l.dst_col_stride = n_rows;
+            l.ncols = done = edge_cols > 0 ? nc : std::min(ibatch, ce - c0);
+            l.deinterleave_log = 0;
+            dft_run(*iplan, l, ctx->stream);
+        } else {
+            done = 0;  // part of an earlier, wider interpolation launch
         }
-        if (!per_batch_hash && st == AERO_OK) st = segment_hash_batch(seg, 0, (int)n_cols);
-        if (st == AERO_OK) st = segment_tree_after_hash(seg, root);
+        if (sharded && done) {
+            PhaseTimer t(ctx, "push_polys");
+            peer_push(polys_all, ctx->shard_world, ctx->shard_rank, (size_t)c0 * n_rows * 8, (size_t)done * n_rows * 8, ctx->stream);
+        }
+        segment_lde_batch(seg.get(), lplan, c0, nc, tmp_l);
+        if (per_batch_hash) TRY(segment_hash_batch(seg.get(), c0, nc));
     }
-    dev_free(ctx, tmp_i);
-    dev_free(ctx, tmp_l);
-    if (st != AERO_OK) {
-        aero_segment_destroy(seg);
-        return st;
+    if (sharded) {  // the other ranks' coefficients have arrived: extend those columns too
+        TRY(window_barrier(ctx));
+        for (int part = 0; part < 2; part++) {
+            const int lo = part ? ce : 0, hi = part ? (int)n_cols : cb;
+            for (int c0 = lo; c0 < hi; c0 += lde_batch) segment_lde_batch(seg.get(), lplan, c0, std::min(lde_batch, hi - c0), tmp_l);
+        }
     }
-    *out = seg;
+    if (!per_batch_hash) TRY(segment_hash_batch(seg.get(), 0, (int)n_cols));
+    TRY(segment_tree_after_hash(seg.get(), root));
+    *out = seg.release();
     return AERO_OK;
 }
 
@@ -813,8 +883,6 @@ struct aero_fri {
     uint32_t curM = 0;
     int cur_log_cosets = 0;
     bool cur_committed = false;
-    bool cur_pending = false;  // coset-sharded DEEP evaluations not exchanged yet
-    int coset_begin = 0, coset_count = 0;
 };
 
 
@@ -825,7 +893,7 @@ struct aero_fri {
 // synchronisation (a proof used to pay 17 host round trips of 20-100 us here; profiles/r01_trace_gaps_v5.txt).
 // -------------------------------------------------------------------------------------------------
 struct GatherBatch {
-    enum Kind { DIGESTS, SEG_ROWS, FRI_ROWS, COPY };
+    enum Kind { DIGESTS, TREE_DIGESTS, SEG_ROWS, FRI_ROWS, COPY };
     struct Job {
         Kind kind;
         const void *src;
@@ -856,6 +924,11 @@ struct GatherBatch {
         for (auto &v : lists) flat.insert(flat.end(), v.begin(), v.end());
         return push(DIGESTS, full, nullptr, 0, 0, flat.data(), flat.size(), flat.size() * 32);
     }
+    size_t tree_digests(const aero_segment *seg, const std::vector<std::vector<uint32_t>> &lists) {
+        std::vector<uint32_t> flat;
+        for (auto &v : lists) flat.insert(flat.end(), v.begin(), v.end());
+        return push(TREE_DIGESTS, nullptr, seg, 0, 0, flat.data(), flat.size(), flat.size() * 32);
+    }
     size_t segment_rows(const aero_segment *seg, const std::vector<uint32_t> &pos);
     size_t fri_rows(const FriLayerDev &L, const std::vector<uint32_t> &pos) {
         return push(FRI_ROWS, L.evals, nullptr, L.M / 8, L.log_cosets, pos.data(), pos.size(), pos.size() * 64);
@@ -867,11 +940,18 @@ struct GatherBatch {
 size_t GatherBatch::segment_rows(const aero_segment *seg, const std::vector<uint32_t> &pos) {
     return push(SEG_ROWS, seg->lde, seg, 0, 0, pos.data(), pos.size(), pos.size() * (size_t)seg->ncols * 8);
 }
+// Results of a sharded proof are assembled in the exchange window: each entry is written by the rank
+// that owns it into every rank's result buffer (gather_rows / gather_tree_digests), one barrier later
+// all ranks hold everything; replicated sources (FRI layers) are gathered locally.
 aero_status GatherBatch::run() {
     const size_t idx_bytes = (idx.size() * 4 + 15) & ~(size_t)15;
     const size_t total = idx_bytes + out_bytes;
     TRY(stage_reserve(ctx, total));
     uint8_t *d = ctx->d_stage;
+    DevBlocks win(ctx);
+    uint8_t *d_res = d + idx_bytes;
+    if (ctx_sharded(ctx) && out_bytes) TRY(win.alloc_shared((void **)&d_res, out_bytes));
+    const RankPtrs res_all = rank_ptrs(ctx, d_res);
     if (!idx.empty()) {
         memcpy(ctx->h_stage, idx.data(), idx.size() * 4);
         CUDA_TRY(ctx, cudaMemcpyAsync(d, ctx->h_stage, idx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -879,12 +959,16 @@ aero_status GatherBatch::run() {
     for (const Job &j : jobs) {
         if (j.out_bytes == 0) continue;
         const uint32_t *d_idx = (const uint32_t *)d + j.idx_off;
-        uint8_t *d_out = d + idx_bytes + j.out_off;
+        uint8_t *d_out = d_res + j.out_off;
+        RankPtrs out_all = res_all;
+        for (int r = 0; r < AERO_MAX_RANKS; r++)
+            if (out_all.p[r]) out_all.p[r] = (uint8_t *)out_all.p[r] + j.out_off;
         switch (j.kind) {
         case DIGESTS: gather_digests((const uint32_t *)j.src, d_idx, j.count, (uint32_t *)d_out, ctx->stream); break;
+        case TREE_DIGESTS: gather_tree_digests(j.seg->tree_view(), d_idx, j.count, out_all, ctx->stream); break;
         case SEG_ROWS:
             gather_rows(j.seg->lde, j.seg->lde_stride(), j.seg->ncols, j.seg->logn, j.seg->log_blowup, j.seg->coset_begin,
-                        j.seg->coset_count, d_idx, j.count, (uint64_t *)d_out, ctx->stream);
+                        j.seg->coset_count, ctx->shard_world, d_idx, j.count, out_all, ctx->stream);
             break;
         case FRI_ROWS:
             gather_fri_rows((const uint64_t *)j.src, j.rows, j.log_cosets, d_idx, j.count, (uint64_t *)d_out, ctx->stream);
@@ -893,9 +977,11 @@ aero_status GatherBatch::run() {
         }
     }
     CUDA_TRY(ctx, cudaGetLastError());
+    TRY(window_barrier(ctx));
     if (out_bytes)
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage + idx_bytes, d + idx_bytes, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage + idx_bytes, d_res, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    TRY(window_check(ctx));
     host = ctx->h_stage + idx_bytes;
     return AERO_OK;
 }
@@ -911,13 +997,12 @@ struct SegmentOpening {
 static aero_status segment_open_plan(aero_segment *seg, const uint64_t *positions, uint32_t n_pos, bool want_rows,
                                      GatherBatch &gb, SegmentOpening &o) {
     aero_ctx *ctx = seg->ctx;
-    if (!seg->full) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no commitment");
-    if (seg->tree_pending) CTX_FAIL(ctx, AERO_ERR_STATE, "sharded segment: exchange leaves and call aero_segment_finish_tree first");
+    if (!seg->heap) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no commitment");
     o.seg = seg;
     o.n_pos = n_pos;
     o.want_rows = want_rows;
     TRY(batch_proof_indices(ctx, positions, n_pos, seg->N(), o.idx));
-    o.dig_off = gb.digests(seg->full, o.idx);
+    o.dig_off = gb.tree_digests(seg, o.idx);
     if (want_rows) {
         std::vector<uint32_t> pos(n_pos);
         for (uint32_t i = 0; i < n_pos; i++) pos[i] = (uint32_t)positions[i];
@@ -1020,6 +1105,9 @@ static aero_status fri_open_finish(const FriOpening &o, const GatherBatch &gb, u
 // -------------------------------------------------------------------------------------------------
 // extern "C"
 // -------------------------------------------------------------------------------------------------
+// every entry point runs on the context's device, whatever the calling thread had current
+static inline void enter(const aero_ctx *ctx) { cudaSetDevice(ctx->device); }
+
 extern "C" {
 
 const char *aero_version(void) { return "aero_b200 0.1 (sm_100a)"; }
@@ -1051,11 +1139,13 @@ aero_status aero_ctx_create(const int *device_ids, int n_devices, aero_ctx **out
 }
 void aero_ctx_destroy(aero_ctx *ctx) {
     if (!ctx) return;
+    enter(ctx);
     cudaStreamSynchronize(ctx->stream);
     profile_flush(ctx);
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
+        cudaEventDestroy(ctx->ev_copy_order);
     }
     if (ctx->hash_stream) {
         cudaStreamSynchronize(ctx->hash_stream);
@@ -1063,8 +1153,8 @@ void aero_ctx_destroy(aero_ctx *ctx) {
         cudaEventDestroy(ctx->ev_lde);
         cudaEventDestroy(ctx->ev_hash);
     }
-    for (int i = 0; i < AERO_MAX_PEERS; i++)
-        if (ctx->win_peer[i]) cudaIpcCloseMemHandle(ctx->win_peer[i]);
+    for (int r = 0; r < AERO_MAX_RANKS; r++)
+        if (ctx->win_ipc[r]) cudaIpcCloseMemHandle(ctx->win_base[r]);
     if (ctx->win) cudaFree(ctx->win);
     cache_release_all(ctx);
     for (auto &kv : ctx->live_blocks) cudaFree(kv.first);  // handles the caller forgot to destroy
@@ -1072,16 +1162,23 @@ void aero_ctx_destroy(aero_ctx *ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 const char *aero_last_error(aero_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 aero_status aero_ctx_set_stream(aero_ctx *ctx, void *s) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
+    // cached blocks are handed out on the assumption that all work is ordered on one stream
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->own_stream = false;
     ctx->stream = (cudaStream_t)s;
     return AERO_OK;
 }
 aero_status aero_ctx_set_form(aero_ctx *ctx, int form) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (form != AERO_FORM_MONTGOMERY && form != AERO_FORM_CANONICAL) CTX_FAIL(ctx, AERO_ERR_INVALID, "unknown element form %d", form);
     ctx->form = form;
     return AERO_OK;
@@ -1091,10 +1188,16 @@ aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value)
     if (!ctx || !key) return AERO_ERR_INVALID;
     const std::string k(key);
     if (k == "overlap_hash") ctx->overlap_hash = value != 0;
-    else if (k == "use_window") {
-        if (ctx->win_live) CTX_FAIL(ctx, AERO_ERR_STATE, "window buffers are live");
-        ctx->win_ranks = value ? ctx->win_attached : 0;
+    else if (k == "own_stream") {
+        if (value && !ctx->own_stream) {
+            cudaStream_t st = nullptr;
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            ctx->stream = st;
+            ctx->own_stream = true;
+        }
     }
+    else if (k == "force_host_sync") ctx->force_host_sync = value != 0;
     else if (k == "force_split_intt") ctx->force_split_intt = value != 0;
     else if (k == "hash_blocks_per_sm" && value > 0) ctx->hash_blocks_per_sm = (int)value;
     else if (k == "lde_batch_bytes" && value > 0) ctx->lde_batch_bytes = (size_t)value;
@@ -1113,11 +1216,13 @@ void aero_ctx_set_error(aero_ctx *ctx, const char *msg) {
 }
 aero_status aero_ctx_profile_enable(aero_ctx *ctx, int enable) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     ctx->profile = enable != 0;
     return AERO_OK;
 }
 aero_status aero_ctx_profile_filter(aero_ctx *ctx, const char *prefix) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     ctx->profile_prefix = prefix ? prefix : "";
     return AERO_OK;
 }
@@ -1150,23 +1255,39 @@ aero_status aero_device_alloc(aero_ctx *ctx, size_t bytes, void **d_ptr) {
 }
 aero_status aero_device_free(aero_ctx *ctx, void *d_ptr) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     CUDA_TRY(ctx, cudaFree(d_ptr));
     return AERO_OK;
 }
 aero_status aero_device_upload(aero_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     CUDA_TRY(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return AERO_OK;
 }
 aero_status aero_device_download(aero_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     CUDA_TRY(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return AERO_OK;
 }
 aero_status aero_device_sync(aero_ctx *ctx) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return AERO_OK;
+}
+
+aero_status aero_measure_alu_peak(aero_ctx *ctx, double *lane_ops_per_s) {
+    if (!ctx || !lane_ops_per_s) return AERO_ERR_INVALID;
+    enter(ctx);
+    DevBlocks blk(ctx);
+    uint32_t *scratch = nullptr;
+    TRY(blk.alloc((void **)&scratch, (size_t)ctx->num_sms * 4 * 256 * 4));
+    *lane_ops_per_s = measure_alu_peak(ctx->num_sms, scratch, ctx->stream);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaGetLastError());
     return AERO_OK;
@@ -1174,28 +1295,41 @@ aero_status aero_device_sync(aero_ctx *ctx) {
 
 aero_status aero_test_field_ops(aero_ctx *ctx, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) {
     if (!ctx || !a || !b || !out || !n) return AERO_ERR_INVALID;
+    DevBlocks blk(ctx);
     uint64_t *da = nullptr, *db = nullptr, *dout = nullptr;
-    TRY(dev_alloc(ctx, (void **)&da, n * 8));
-    TRY(dev_alloc(ctx, (void **)&db, n * 8));
-    TRY(dev_alloc(ctx, (void **)&dout, 12 * n * 8));
+    TRY(blk.alloc((void **)&da, n * 8));
+    TRY(blk.alloc((void **)&db, n * 8));
+    TRY(blk.alloc((void **)&dout, 12 * n * 8));
     CUDA_TRY(ctx, cudaMemcpyAsync(da, a, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(db, b, n * 8, cudaMemcpyHostToDevice, ctx->stream));
     field_ops(da, db, n, dout, ctx->stream);
     CUDA_TRY(ctx, cudaMemcpyAsync(out, dout, 12 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, da);
-    dev_free(ctx, db);
-    dev_free(ctx, dout);
     return AERO_OK;
 }
 
 // ---- prefetched uploads ------------------------------------------------------------------------
+static aero_status ensure_copy_stream(aero_ctx *ctx) {
+    if (!ctx->copy_stream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_order, cudaEventDisableTiming));
+    }
+    return AERO_OK;
+}
+// The destination of a copy on the copy stream is a cached block that kernels already queued on the
+// compute stream may still read or write: order the copy stream after the compute stream's tail.
+static aero_status copy_stream_after_compute(aero_ctx *ctx) {
+    TRY(ensure_copy_stream(ctx));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy_order, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_order, 0));
+    return AERO_OK;
+}
 static aero_status upload_enqueue(aero_upload *u) {
     aero_ctx *ctx = u->ctx;
     if (u->queued) return AERO_OK;
-    if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (size_t c = 0; c < u->cols.size(); c++)
-        CUDA_TRY(ctx, cudaMemcpyAsync(u->d + c * u->n_rows, u->cols[c], u->n_rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+    TRY(copy_stream_after_compute(ctx));
+    for (int c = u->col_begin; c < u->col_end; c++)
+        CUDA_TRY(ctx, cudaMemcpyAsync(u->d + (size_t)c * u->n_rows, u->cols[c], u->n_rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
     CUDA_TRY(ctx, cudaEventRecord(u->done, ctx->copy_stream));
     u->queued = true;
     return AERO_OK;
@@ -1207,8 +1341,9 @@ static aero_status flush_deferred_uploads(aero_ctx *ctx) {
     return AERO_OK;
 }
 aero_status aero_upload_start(aero_ctx *ctx, const uint64_t *const *cols, uint32_t n_cols, uint64_t n_rows, int defer,
-                              aero_upload **out) {
+                              int own_columns_only, aero_upload **out) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (!cols || !out || n_cols == 0 || n_rows == 0) CTX_FAIL(ctx, AERO_ERR_INVALID, "null or empty matrix");
     for (uint32_t c = 0; c < n_cols; c++)
         if (!cols[c]) CTX_FAIL(ctx, AERO_ERR_INVALID, "null column %u", c);
@@ -1216,6 +1351,9 @@ aero_status aero_upload_start(aero_ctx *ctx, const uint64_t *const *cols, uint32
     u->ctx = ctx;
     u->n_rows = n_rows;
     u->cols.assign(cols, cols + n_cols);
+    u->col_begin = 0;
+    u->col_end = (int)n_cols;
+    if (own_columns_only) own_columns(ctx, (int)n_cols, &u->col_begin, &u->col_end);
     aero_status st = dev_alloc(ctx, (void **)&u->d, (size_t)n_cols * n_rows * 8);
     if (st == AERO_OK && cudaEventCreateWithFlags(&u->done, cudaEventDisableTiming) != cudaSuccess) {
         ctx->err = "cudaEventCreate failed";
@@ -1237,6 +1375,7 @@ aero_status aero_upload_start(aero_ctx *ctx, const uint64_t *const *cols, uint32
 aero_status aero_upload_wait(aero_upload *u, const uint64_t **d_cols) {
     if (!u || !d_cols) return AERO_ERR_INVALID;
     aero_ctx *ctx = u->ctx;
+    enter(ctx);
     if (!u->queued) {  // still deferred: no commit came in between
         auto &v = ctx->deferred_uploads;
         v.erase(std::remove(v.begin(), v.end(), u), v.end());
@@ -1249,6 +1388,7 @@ aero_status aero_upload_wait(aero_upload *u, const uint64_t **d_cols) {
 void aero_upload_free(aero_upload *u) {
     if (!u) return;
     aero_ctx *ctx = u->ctx;
+    enter(ctx);
     auto &v = ctx->deferred_uploads;
     v.erase(std::remove(v.begin(), v.end(), u), v.end());
     if (u->queued) cudaEventSynchronize(u->done);  // the host columns are free again, and so is the block
@@ -1262,63 +1402,80 @@ aero_status aero_segment_commit_device(aero_ctx *ctx, const uint64_t *d_cols, si
                                        uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
                                        uint8_t root[32]) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (!d_cols) CTX_FAIL(ctx, AERO_ERR_INVALID, "null matrix");
     if (col_stride < n_rows) CTX_FAIL(ctx, AERO_ERR_INVALID, "column stride smaller than the number of rows");
-    return segment_from_device(ctx, d_cols, col_stride, n_cols, n_rows, blowup, input_is_coeffs, out, root);
+    return segment_from_device(ctx, d_cols, col_stride, 0, n_cols, n_rows, blowup, input_is_coeffs, out, root);
 }
 
 aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint32_t n_cols, uint64_t n_rows,
                                 uint32_t blowup, int input_is_coeffs, aero_segment **out, uint8_t root[32]) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (!cols) CTX_FAIL(ctx, AERO_ERR_INVALID, "null matrix");
     if (n_cols == 0 || n_cols > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of columns must be 1..255, got %u", n_cols);
     if (n_rows < 2 || !is_pow2(n_rows)) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of rows must be a power of two >= 2, got %llu", (unsigned long long)n_rows);
     for (uint32_t c = 0; c < n_cols; c++)
         if (!cols[c]) CTX_FAIL(ctx, AERO_ERR_INVALID, "null column %u", c);
+    // a sharded context uploads (and interpolates) its own columns only; the coefficients of the others
+    // arrive over NVLink
+    int cb = 0, ce = (int)n_cols;
+    own_columns(ctx, (int)n_cols, &cb, &ce);
+    const int own = ce - cb;
+    DevBlocks blocks(ctx);
     uint64_t *stage = nullptr;
-    TRY(dev_alloc(ctx, (void **)&stage, (size_t)n_cols * n_rows * 8));
+    TRY(blocks.alloc((void **)&stage, (size_t)std::max(own, 1) * n_rows * 8));
     // Uploads run on a second stream in column batches; batch b's transforms wait only for batch b,
     // so the PCIe copy of later columns hides behind the NTTs of earlier ones.
-    if (!ctx->copy_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    int batch = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->upload_batch_cols, (n_cols + 2) / 3));
+    int batch = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->upload_batch_cols, ((uint32_t)own + 2) / 3));
     if (batch > 1 && (batch & 1)) batch++;  // even batches: each one's row hash can start as soon as it is extended
     // short first / last batches once there are enough columns for it to matter (see upload_batch_size)
-    int edge = ((int)n_cols >= 4 * batch && batch >= 4) ? ((batch / 2) & ~1) : 0;
+    int edge = (own >= 4 * batch && batch >= 4) ? ((batch / 2) & ~1) : 0;
     if (edge && ctx->upload_edge_cols >= 0) edge = std::min(ctx->upload_edge_cols & ~1, batch);
     std::vector<int> sizes;
-    for (int c0 = 0; c0 < (int)n_cols;) {
-        const int nc = std::min(upload_batch_size(c0, (int)n_cols, batch, edge), (int)n_cols - c0);
+    for (int c0 = 0; c0 < own;) {
+        const int nc = std::min(upload_batch_size(c0, own, batch, edge), own - c0);
         sizes.push_back(nc);
         c0 += nc;
     }
     const int nb = (int)sizes.size();
-    std::vector<cudaEvent_t> ev(nb + 1);
-    for (auto &e : ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    struct Events {
+        std::vector<cudaEvent_t> ev;
+        ~Events() {
+            for (auto e : ev)
+                if (e) cudaEventDestroy(e);
+        }
+    } evs;
+    evs.ev.assign((size_t)nb, nullptr);
+    for (auto &e : evs.ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     // the staging block may still be read by kernels already queued on the compute stream
-    CUDA_TRY(ctx, cudaEventRecord(ev[nb], ctx->stream));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev[nb], 0));
+    TRY(copy_stream_after_compute(ctx));
     for (int b = 0, c = 0; b < nb; b++) {
         for (int k = 0; k < sizes[b]; k++, c++)
-            CUDA_TRY(ctx, cudaMemcpyAsync(stage + (size_t)c * n_rows, cols[c], n_rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CUDA_TRY(ctx, cudaEventRecord(ev[b], ctx->copy_stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(stage + (size_t)c * n_rows, cols[cb + c], n_rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_TRY(ctx, cudaEventRecord(evs.ev[b], ctx->copy_stream));
     }
     TRY(flush_deferred_uploads(ctx));  // prefetches ride behind this segment's copies, under its NTTs
-    aero_status st = segment_from_device(ctx, stage, n_rows, n_cols, n_rows, blowup, input_is_coeffs, out, root, batch, ev.data(), edge);
-    cudaEventSynchronize(ev[nb - 1]);  // the caller's host buffers are free again on return
-    for (auto &e : ev) cudaEventDestroy(e);
-    dev_free(ctx, stage);
+    aero_status st = segment_from_device(ctx, stage, n_rows, cb, n_cols, n_rows, blowup, input_is_coeffs, out, root, batch,
+                                         nb ? evs.ev.data() : nullptr, edge);
+    if (nb) cudaEventSynchronize(evs.ev[nb - 1]);  // the caller's host buffers are free again on return
     return st;
 }
 
 aero_status aero_ctx_set_shard(aero_ctx *ctx, int rank, int world) {
     if (!ctx) return AERO_ERR_INVALID;
-    if (world < 1 || rank < 0 || rank >= world || (world & (world - 1))) CTX_FAIL(ctx, AERO_ERR_INVALID, "bad shard %d of %d (world must be a power of two)", rank, world);
+    if (world < 1 || world > AERO_MAX_RANKS || rank < 0 || rank >= world || (world & (world - 1)))
+        CTX_FAIL(ctx, AERO_ERR_INVALID, "bad shard %d of %d (world must be a power of two <= %d)", rank, world, AERO_MAX_RANKS);
+    if (ctx->win_live) CTX_FAIL(ctx, AERO_ERR_STATE, "window buffers of a sharded proof are live");
+    if (ctx->win_ranks && world > 1 && (world != ctx->win_ranks || ctx->win_base[rank] != ctx->win))
+        CTX_FAIL(ctx, AERO_ERR_STATE, "the attached exchange window serves rank layout %d, not %d of %d", ctx->win_ranks, rank, world);
     ctx->shard_rank = rank;
     ctx->shard_world = world;
     return AERO_OK;
 }
 aero_status aero_ctx_window_create(aero_ctx *ctx, size_t bytes, uint8_t handle_out[64]) {
-    if (!ctx || !handle_out) return AERO_ERR_INVALID;
+    if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (ctx->win) CTX_FAIL(ctx, AERO_ERR_STATE, "exchange window already created");
     if (bytes < 8192) CTX_FAIL(ctx, AERO_ERR_INVALID, "exchange window must be at least 8 KiB");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1326,97 +1483,113 @@ aero_status aero_ctx_window_create(aero_ctx *ctx, size_t bytes, uint8_t handle_o
     CUDA_TRY(ctx, cudaMalloc(&p, bytes));
     cudaError_t e = cudaMemset(p, 0, 4096);
     cudaIpcMemHandle_t h;
-    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e == cudaSuccess && handle_out) e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) {
         cudaFree(p);
         CTX_FAIL(ctx, AERO_ERR_CUDA, "exchange window: %s", cudaGetErrorString(e));
     }
-    memcpy(handle_out, &h, 64);
+    if (handle_out) memcpy(handle_out, &h, 64);
     ctx->win = (uint8_t *)p;
     ctx->win_bytes = bytes;
     ctx->win_off = 4096;
     ctx->win_live = 0;
     return AERO_OK;
 }
-aero_status aero_ctx_window_attach(aero_ctx *ctx, int n_ranks, const uint8_t *handles) {
-    if (!ctx || !handles) return AERO_ERR_INVALID;
+static aero_status window_attach_check(aero_ctx *ctx, int n_ranks) {
     if (!ctx->win) CTX_FAIL(ctx, AERO_ERR_STATE, "create the exchange window first");
     if (ctx->win_ranks) CTX_FAIL(ctx, AERO_ERR_STATE, "exchange window already attached");
-    if (n_ranks != ctx->shard_world || n_ranks < 2 || n_ranks > AERO_MAX_PEERS + 1)
-        CTX_FAIL(ctx, AERO_ERR_INVALID, "window ranks (%d) must equal the shard world size (%d), 2..%d", n_ranks, ctx->shard_world, AERO_MAX_PEERS + 1);
-    int k = 0;
+    if (n_ranks != ctx->shard_world || n_ranks < 2 || n_ranks > AERO_MAX_RANKS)
+        CTX_FAIL(ctx, AERO_ERR_INVALID, "window ranks (%d) must equal the shard world size (%d), 2..%d", n_ranks, ctx->shard_world, AERO_MAX_RANKS);
+    return AERO_OK;
+}
+aero_status aero_ctx_window_attach(aero_ctx *ctx, int n_ranks, const uint8_t *handles) {
+    if (!ctx || !handles) return AERO_ERR_INVALID;
+    enter(ctx);
+    TRY(window_attach_check(ctx, n_ranks));
     for (int r = 0; r < n_ranks; r++) {
-        if (r == ctx->shard_rank) continue;
+        if (r == ctx->shard_rank) {
+            ctx->win_base[r] = ctx->win;
+            continue;
+        }
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + (size_t)r * 64, 64);
         void *p = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            for (int i = 0; i < k; i++) cudaIpcCloseMemHandle(ctx->win_peer[i]), ctx->win_peer[i] = nullptr;
+            for (int i = 0; i < r; i++)
+                if (ctx->win_ipc[i]) cudaIpcCloseMemHandle(ctx->win_base[i]), ctx->win_ipc[i] = false;
             CTX_FAIL(ctx, AERO_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
         }
-        ctx->win_peer[k] = (uint8_t *)p;
-        ctx->win_peer_rank[k] = r;
-        k++;
+        ctx->win_base[r] = (uint8_t *)p;
+        ctx->win_ipc[r] = true;
     }
-    ctx->win_ranks = ctx->win_attached = n_ranks;
+    ctx->win_ranks = n_ranks;
+    return AERO_OK;
+}
+aero_status aero_ctx_window_attach_local(aero_ctx *ctx, int n_ranks, aero_ctx *const *ranks) {
+    if (!ctx || !ranks) return AERO_ERR_INVALID;
+    enter(ctx);
+    TRY(window_attach_check(ctx, n_ranks));
+    for (int r = 0; r < n_ranks; r++) {
+        aero_ctx *o = ranks[r];
+        if (!o || !o->win || o->win_bytes != ctx->win_bytes) CTX_FAIL(ctx, AERO_ERR_INVALID, "rank %d has no exchange window of the same size", r);
+        if ((r == ctx->shard_rank) != (o == ctx)) CTX_FAIL(ctx, AERO_ERR_INVALID, "ranks[%d] does not match this context's shard rank %d", r, ctx->shard_rank);
+        if (o->device != ctx->device) {
+            int can = 0;
+            CUDA_TRY(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, o->device));
+            if (!can) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "device %d cannot access device %d", ctx->device, o->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CTX_FAIL(ctx, AERO_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", o->device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        ctx->win_base[r] = o->win;
+    }
+    ctx->win_ranks = n_ranks;
     return AERO_OK;
 }
 int aero_ctx_window_ranks(aero_ctx *ctx) { return (ctx && ctx->shard_world > 1) ? ctx->win_ranks : 0; }
+aero_status aero_ctx_set_host_barrier(aero_ctx *ctx, aero_host_barrier_fn fn, void *user) {
+    if (!ctx) return AERO_ERR_INVALID;
+    ctx->host_barrier = fn;
+    ctx->host_barrier_user = user;
+    return AERO_OK;
+}
 aero_status aero_window_barrier(aero_ctx *ctx) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     return window_barrier(ctx);
 }
-// a peer that never reached a barrier (it failed) is reported here instead of hanging the GPU
-static aero_status window_check(aero_ctx *ctx) {
-    if (ctx->win_ranks <= 1 || ctx->shard_world <= 1) return AERO_OK;
-    unsigned int t = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&t, ctx->win + 2048, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (t) CTX_FAIL(ctx, AERO_ERR_STATE, "exchange barrier timed out %u time(s): a peer rank did not arrive", t);
+// A sharded proof of a shape this context has proved before makes no driver allocation (every block
+// comes from the cache), so its barriers can be device-side; the first proof of a shape synchronises
+// on the host (see aero_ctx::win_host_sync).
+aero_status aero_ctx_shard_begin(aero_ctx *ctx, const char *shape_key) {
+    if (!ctx || !shape_key) return AERO_ERR_INVALID;
+    enter(ctx);
+    if (!ctx_sharded(ctx)) return AERO_OK;
+    if (ctx->win_ranks != ctx->shard_world) CTX_FAIL(ctx, AERO_ERR_STATE, "sharded context (%d ranks) has no exchange window attached", ctx->shard_world);
+    const bool warm = ctx->warm_shapes.count(shape_key) != 0;
+    ctx->win_host_sync = !warm || ctx->force_host_sync;
+    ctx->cur_shape = shape_key;
     return AERO_OK;
 }
-aero_status aero_fri_push_evaluations(aero_fri *fri) {
-    if (!fri) return AERO_ERR_INVALID;
-    aero_ctx *ctx = fri->ctx;
-    if (!fri->cur_pending) return AERO_OK;
-    const PeerPtrs peers = peers_of(ctx, fri->cur);
-    if (peers.n == 0) CTX_FAIL(ctx, AERO_ERR_STATE, "no exchange window attached");
-    const size_t per = (size_t)fri->curM >> fri->cur_log_cosets;  // entries per coset
-    // (the peers' copies were released by the barrier that preceded the first row hash of this proof)
-    peer_push(fri->cur, peers, (size_t)fri->coset_begin * per * 8, (size_t)fri->coset_count * per * 8, ctx->stream);
-    TRY(window_barrier(ctx));
-    TRY(window_check(ctx));
-    fri->cur_pending = false;
+aero_status aero_ctx_shard_end(aero_ctx *ctx, int ok) {
+    if (!ctx) return AERO_ERR_INVALID;
+    if (!ctx_sharded(ctx)) return AERO_OK;
+    if (ok) ctx->warm_shapes.insert(ctx->cur_shape);
+    else ctx->warm_shapes.erase(ctx->cur_shape);
+    ctx->win_host_sync = true;
     return AERO_OK;
-}
-
-aero_status aero_segment_leaves_device(aero_segment *seg, void **d_leaves, uint64_t *n_leaves, uint32_t *coset_begin,
-                                       uint32_t *coset_count) {
-    if (!seg || !d_leaves) return AERO_ERR_INVALID;
-    aero_ctx *ctx = seg->ctx;
-    if (!seg->full) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no commitment");
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the caller's exchange may run on another stream
-    *d_leaves = seg->full + (size_t)seg->N() * 8;
-    if (n_leaves) *n_leaves = seg->N();
-    if (coset_begin) *coset_begin = (uint32_t)seg->coset_begin;
-    if (coset_count) *coset_count = (uint32_t)seg->coset_count;
-    return AERO_OK;
-}
-aero_status aero_segment_finish_tree(aero_segment *seg, uint8_t root[32]) {
-    if (!seg) return AERO_ERR_INVALID;
-    if (!seg->full) CTX_FAIL(seg->ctx, AERO_ERR_STATE, "segment has no commitment");
-    TRY(segment_finish_tree(seg, root));
-    return window_check(seg->ctx);
 }
 
 void aero_segment_destroy(aero_segment *seg) {
     if (!seg) return;
+    enter(seg->ctx);
     dev_free(seg->ctx, seg->polys);
     dev_free(seg->ctx, seg->lde);
-    dev_free(seg->ctx, seg->full);
+    dev_free(seg->ctx, seg->heap);
     dev_free(seg->ctx, seg->leaf_stage);
+    dev_free(seg->ctx, seg->top);
     delete seg;
 }
 aero_status aero_segment_info(aero_segment *seg, uint32_t *n_cols, uint64_t *n_rows, uint32_t *blowup) {
@@ -1428,6 +1601,7 @@ aero_status aero_segment_info(aero_segment *seg, uint32_t *n_cols, uint64_t *n_r
 }
 aero_status aero_segment_commit_polys(aero_segment *seg, uint32_t blowup, uint8_t root[32]) {
     if (!seg) return AERO_ERR_INVALID;
+    enter(seg->ctx);
     if (!is_pow2(blowup) || blowup < 2) CTX_FAIL(seg->ctx, AERO_ERR_INVALID, "blowup factor must be a power of two >= 2, got %u", blowup);
     return segment_extend_commit(seg, ilog2(blowup), root);
 }
@@ -1435,27 +1609,30 @@ aero_status aero_segment_commit_polys(aero_segment *seg, uint32_t blowup, uint8_
 aero_status aero_segment_download_lde(aero_segment *seg, uint64_t *const *cols_out) {
     if (!seg || !cols_out) return AERO_ERR_INVALID;
     aero_ctx *ctx = seg->ctx;
+    enter(ctx);
     if (!seg->lde) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no LDE");
     if (seg->coset_count != (1 << seg->log_blowup)) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "download_lde on a coset-sharded segment");
     const uint64_t N = seg->N();
     PhaseTimer t(ctx, "download_lde");
+    DevBlocks blk(ctx);
     uint64_t *tmp = nullptr;
-    TRY(dev_alloc(ctx, (void **)&tmp, N * 8));
+    TRY(blk.alloc((void **)&tmp, N * 8));
     for (int c = 0; c < seg->ncols; c++) {
         lde_to_natural(seg->lde + (size_t)c * N, tmp, seg->logn, seg->log_blowup, ctx->form == AERO_FORM_MONTGOMERY, ctx->stream);
         CUDA_TRY(ctx, cudaMemcpyAsync(cols_out[c], tmp, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, tmp);
     return AERO_OK;
 }
 aero_status aero_segment_download_polys(aero_segment *seg, uint64_t *const *cols_out) {
     if (!seg || !cols_out) return AERO_ERR_INVALID;
     aero_ctx *ctx = seg->ctx;
+    enter(ctx);
     const uint64_t n = seg->n();
+    DevBlocks blk(ctx);
     uint64_t *tmp = nullptr;
     const bool mont = ctx->form == AERO_FORM_MONTGOMERY;
-    if (mont) TRY(dev_alloc(ctx, (void **)&tmp, n * 8));
+    if (mont) TRY(blk.alloc((void **)&tmp, n * 8));
     for (int c = 0; c < seg->ncols; c++) {
         const uint64_t *src = seg->polys + (size_t)c * n;
         if (mont) {
@@ -1465,15 +1642,20 @@ aero_status aero_segment_download_polys(aero_segment *seg, uint64_t *const *cols
         CUDA_TRY(ctx, cudaMemcpyAsync(cols_out[c], src, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, tmp);
     return AERO_OK;
 }
 aero_status aero_segment_download_leaves(aero_segment *seg, uint8_t *leaves_out) {
     if (!seg || !leaves_out) return AERO_ERR_INVALID;
     aero_ctx *ctx = seg->ctx;
-    if (!seg->full) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no commitment");
+    enter(ctx);
+    if (!seg->heap) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no commitment");
+    if (seg->logG) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "download_leaves on a sharded segment");
     const uint64_t N = seg->N();
-    CUDA_TRY(ctx, cudaMemcpyAsync(leaves_out, seg->full + (size_t)N * 8, N * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    DevBlocks tmp(ctx);
+    uint32_t *nat = nullptr;
+    TRY(tmp.alloc((void **)&nat, N * 32));
+    leaves_to_natural(seg->leaf_stage, nat, seg->logn, seg->log_blowup, ctx->stream);
+    CUDA_TRY(ctx, cudaMemcpyAsync(leaves_out, nat, N * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return AERO_OK;
 }
@@ -1481,6 +1663,7 @@ aero_status aero_segment_download_leaves(aero_segment *seg, uint8_t *leaves_out)
 aero_status aero_segment_open(aero_segment *seg, const uint64_t *positions, uint32_t n_pos, uint64_t *rows_out,
                               uint8_t *batch_nodes_out, size_t *len) {
     if (!seg || !positions || !len) return AERO_ERR_INVALID;
+    enter(seg->ctx);
     GatherBatch gb(seg->ctx);
     SegmentOpening o;
     TRY(segment_open_plan(seg, positions, n_pos, rows_out != nullptr, gb, o));
@@ -1492,6 +1675,7 @@ aero_status aero_open_queries(aero_ctx *ctx, aero_fri *fri, aero_segment *const 
                               const uint64_t *positions, uint32_t n_pos, uint8_t *fri_proof_bytes, size_t *fri_len,
                               uint64_t *const *rows_out, uint8_t *const *batch_nodes_out, size_t *batch_len) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (!positions || (fri && !fri_len) || (n_segs && (!segs || !rows_out || !batch_nodes_out || !batch_len)))
         CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     GatherBatch gb(ctx);
@@ -1523,6 +1707,7 @@ aero_status aero_open_queries(aero_ctx *ctx, aero_fri *fri, aero_segment *const 
 aero_status aero_commit_rows_device(aero_ctx *ctx, const uint64_t *d_m, size_t col_stride, uint32_t n_cols,
                                     uint64_t n_rows, uint8_t root[32]) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (!d_m || !root) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     if (n_cols == 0) CTX_FAIL(ctx, AERO_ERR_INVALID, "matrix must have at least one column");
     // MerkleTree::new (crypto/src/merkle/mod.rs:108-114): >= 2 leaves, power of two
@@ -1551,6 +1736,7 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
                                               const aero_divisor *divs, uint32_t n_div, uint64_t ce_domain_size,
                                               uint64_t trace_len, aero_segment **out) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (!d_eval_cols || !divs || !out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     if (col_stride < ce_domain_size) CTX_FAIL(ctx, AERO_ERR_INVALID, "column stride smaller than the domain");
     if (n_div == 0 || n_div > 8) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of divisors must be 1..8, got %u", n_div);
@@ -1701,20 +1887,22 @@ aero_status aero_constraints_into_poly(aero_ctx *ctx, const uint64_t *const *eva
                                        uint32_t n_div, uint64_t ce_domain_size, uint64_t trace_len,
                                        aero_segment **out) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (!eval_cols || !divs || !out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     if (n_div == 0 || n_div > 8) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of divisors must be 1..8, got %u", n_div);
     if (!is_pow2(ce_domain_size)) CTX_FAIL(ctx, AERO_ERR_INVALID, "domain sizes must be powers of two");
     const uint64_t N = ce_domain_size;
+    DevBlocks blk(ctx);
     uint64_t *cols = nullptr;
-    TRY(dev_alloc(ctx, (void **)&cols, (size_t)n_div * N * 8));
+    TRY(blk.alloc((void **)&cols, (size_t)n_div * N * 8));
     {
         PhaseTimer t(ctx, "h2d");
-        for (uint32_t d = 0; d < n_div; d++)
+        for (uint32_t d = 0; d < n_div; d++) {
+            if (!eval_cols[d]) CTX_FAIL(ctx, AERO_ERR_INVALID, "null evaluation column %u", d);
             CUDA_TRY(ctx, cudaMemcpyAsync(cols + (size_t)d * N, eval_cols[d], N * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
     }
-    aero_status st = aero_constraints_into_poly_device(ctx, cols, N, divs, n_div, ce_domain_size, trace_len, out);
-    dev_free(ctx, cols);
-    return st;
+    return aero_constraints_into_poly_device(ctx, cols, N, divs, n_div, ce_domain_size, trace_len, out);
 }
 
 // ---- OOD + DEEP -----------------------------------------------------------------------------
@@ -1777,6 +1965,7 @@ static void ood_release(aero_ctx *ctx, OodJob &job) {
 aero_status aero_ood_eval(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs, aero_segment *comp,
                           uint64_t z, uint64_t *out_trace, uint64_t *out_comp) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (n_trace_segs && (!trace_segs || !out_trace)) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     if (comp && !out_comp) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     PhaseTimer t(ctx, "ood_eval");
@@ -1830,6 +2019,7 @@ aero_status aero_deep_compose(aero_ctx *ctx, aero_segment *const *trace_segs, ui
                               aero_segment *comp, uint64_t z, const uint64_t *ood_trace, const uint64_t *ood_comp,
                               const uint64_t *cc, aero_fri **out) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (!trace_segs || !n_trace_segs || !comp || !ood_trace || !ood_comp || !cc || !out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     if (n_trace_segs > 4) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "at most 4 trace segments");
     const int logn = trace_segs[0]->logn;
@@ -1864,14 +2054,15 @@ aero_status aero_deep_compose(aero_ctx *ctx, aero_segment *const *trace_segs, ui
     const uint64_t d0 = to_canon(ctx, cc[3 * W + m]), d1 = to_canon(ctx, cc[3 * W + m + 1]);
     const uint64_t h_consts[3] = {k1, k2, kh};
 
+    DevBlocks tmp(ctx);
     uint64_t *d_cc = nullptr, *d_consts = nullptr, *t1 = nullptr, *t2 = nullptr, *hh = nullptr, *carry = nullptr, *coeffs = nullptr;
-    TRY(dev_alloc(ctx, (void **)&d_cc, h_cc.size() * 8));
-    TRY(dev_alloc(ctx, (void **)&d_consts, 3 * 8));
-    TRY(dev_alloc(ctx, (void **)&t1, n * 8));
-    TRY(dev_alloc(ctx, (void **)&t2, n * 8));
-    TRY(dev_alloc(ctx, (void **)&hh, n * 8));
-    TRY(dev_alloc(ctx, (void **)&coeffs, n * 8));
-    TRY(dev_alloc(ctx, (void **)&carry, (6 * (n / 256 + 1)) * 8));
+    TRY(tmp.alloc((void **)&d_cc, h_cc.size() * 8));
+    TRY(tmp.alloc((void **)&d_consts, 3 * 8));
+    TRY(tmp.alloc((void **)&t1, n * 8));
+    TRY(tmp.alloc((void **)&t2, n * 8));
+    TRY(tmp.alloc((void **)&hh, n * 8));
+    TRY(tmp.alloc((void **)&coeffs, n * 8));
+    TRY(tmp.alloc((void **)&carry, (6 * (n / 256 + 1)) * 8));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_cc, h_cc.data(), h_cc.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_consts, h_consts, 24, cudaMemcpyHostToDevice, ctx->stream));
     {
@@ -1887,84 +2078,74 @@ aero_status aero_deep_compose(aero_ctx *ctx, aero_segment *const *trace_segs, ui
         syn_div3(t1, t2, hh, logn, bs, carry, ctx->stream);
         deep_finish(t1, t2, hh, logn, d0, d1, coeffs, ctx->stream);
     }
-    aero_fri *fri = new aero_fri();
+    FriGuard fri(new aero_fri());
     fri->ctx = ctx;
     const uint64_t N = n << log_blowup;
-    aero_status st = dev_alloc_shared(ctx, (void **)&fri->cur, N * 8);
-    if (st == AERO_OK) {
-        const DftTables *plan;
-        st = plan_lde(ctx, logn, log_blowup, false, &plan);
-        if (st == AERO_OK) {
-            PhaseTimer t(ctx, "deep_lde");
-            uint64_t *tmp = nullptr;
-            if (plan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp, N * 8);
-            if (st == AERO_OK) {
-                DftLaunch l;
-                l.src = coeffs;
-                l.dst = fri->cur;
-                l.tmp = tmp;
-                l.src_col_stride = n;
-                l.dst_col_stride = N;
-                l.ncols = 1;
-                l.deinterleave_log = 0;
-                // coset shard: own cosets only, written at their global slots so that an in-place
-                // all-gather completes the buffer
-                const int B = 1 << log_blowup;
-                fri->coset_count = B / ctx->shard_world;
-                fri->coset_begin = ctx->shard_rank * fri->coset_count;
-                l.coset_begin = fri->coset_begin;
-                l.coset_count = fri->coset_count;
-                l.dst = fri->cur + (size_t)fri->coset_begin * n;
-                dft_run(*plan, l, ctx->stream);
-                dev_free(ctx, tmp);
-                fri->cur_pending = ctx->shard_world > 1;
-            }
-        }
-    }
+    const int B = 1 << log_blowup;
+    if (B % ctx->shard_world) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "shard world size %d must divide the blowup factor %d", ctx->shard_world, B);
+    TRY(dev_alloc_shared(ctx, (void **)&fri->cur, N * 8));
     fri->curM = (uint32_t)N;
     fri->cur_log_cosets = log_blowup;
-    dev_free(ctx, d_cc);
-    dev_free(ctx, d_consts);
-    dev_free(ctx, t1);
-    dev_free(ctx, t2);
-    dev_free(ctx, hh);
-    dev_free(ctx, carry);
-    dev_free(ctx, coeffs);
-    if (st == AERO_OK && cudaGetLastError() != cudaSuccess) { ctx->err = "kernel launch failed in deep_compose"; st = AERO_ERR_CUDA; }
-    if (st != AERO_OK) {
-        aero_fri_destroy(fri);
-        return st;
+    const DftTables *plan;
+    TRY(plan_lde(ctx, logn, log_blowup, false, &plan));
+    uint64_t *tmp_l = nullptr;
+    // coset shard: own cosets only, written at their global slots and into the peers' copies
+    const int coset_count = B / ctx->shard_world, coset_begin = ctx->shard_rank * coset_count;
+    if (plan->log1 != 0) TRY(tmp.alloc((void **)&tmp_l, (size_t)coset_count * n * 8));
+    {
+        PhaseTimer t(ctx, "deep_lde");
+        DftLaunch l;
+        l.src = coeffs;
+        l.tmp = tmp_l;
+        l.src_col_stride = n;
+        l.dst_col_stride = N;
+        l.ncols = 1;
+        l.deinterleave_log = 0;
+        l.coset_begin = coset_begin;
+        l.coset_count = coset_count;
+        l.dst = fri->cur + (size_t)coset_begin * n;
+        dft_run(*plan, l, ctx->stream);
     }
-    *out = fri;
+    if (ctx_sharded(ctx)) {
+        {
+            PhaseTimer t(ctx, "push_deep");
+            peer_push(rank_ptrs(ctx, fri->cur), ctx->shard_world, ctx->shard_rank, (size_t)coset_begin * n * 8, (size_t)coset_count * n * 8, ctx->stream);
+        }
+        TRY(window_barrier(ctx));
+    }
+    if (cudaGetLastError() != cudaSuccess) CTX_FAIL(ctx, AERO_ERR_CUDA, "kernel launch failed in deep_compose");
+    *out = fri.release();
     return AERO_OK;
 }
 
 // ---- FRI ------------------------------------------------------------------------------------
 aero_status aero_fri_from_evaluations(aero_ctx *ctx, const uint64_t *evaluations, uint64_t count, aero_fri **out) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (!evaluations || !out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     if (!is_pow2(count) || count < 16 || count > (1ULL << 31)) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of evaluations must be a power of two >= 16");
-    aero_fri *fri = new aero_fri();
+    FriGuard fri(new aero_fri());
     fri->ctx = ctx;
-    aero_status st = dev_alloc(ctx, (void **)&fri->cur, count * 8);
-    if (st != AERO_OK) { delete fri; return st; }
+    TRY(dev_alloc(ctx, (void **)&fri->cur, count * 8));
     CUDA_TRY(ctx, cudaMemcpyAsync(fri->cur, evaluations, count * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->form == AERO_FORM_MONTGOMERY) convert_form(fri->cur, fri->cur, count, 0, ctx->stream);
     fri->curM = (uint32_t)count;
     fri->cur_log_cosets = 0;
-    *out = fri;
+    *out = fri.release();
     return AERO_OK;
 }
 aero_status aero_fri_download_evaluations(aero_fri *fri, uint64_t *out, uint64_t *count) {
     if (!fri || !count) return AERO_ERR_INVALID;
     aero_ctx *ctx = fri->ctx;
+    enter(ctx);
     if (!out || *count < fri->curM) {
         *count = fri->curM;
         CTX_FAIL(ctx, AERO_ERR_BUFFER, "need room for %u evaluations", fri->curM);
     }
     *count = fri->curM;
+    DevBlocks blk(ctx);
     uint64_t *tmp = nullptr;
-    TRY(dev_alloc(ctx, (void **)&tmp, (size_t)fri->curM * 8));
+    TRY(blk.alloc((void **)&tmp, (size_t)fri->curM * 8));
     const bool mont = ctx->form == AERO_FORM_MONTGOMERY;
     if (fri->cur_log_cosets) {
         lde_to_natural(fri->cur, tmp, ilog2(fri->curM) - fri->cur_log_cosets, fri->cur_log_cosets, mont, ctx->stream);
@@ -1975,33 +2156,15 @@ aero_status aero_fri_download_evaluations(aero_fri *fri, uint64_t *out, uint64_t
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(out, tmp, (size_t)fri->curM * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, tmp);
-    return AERO_OK;
-}
-
-aero_status aero_fri_evaluations_device(aero_fri *fri, void **d_evals, uint64_t *count, uint32_t *coset_begin,
-                                        uint32_t *coset_count) {
-    if (!fri || !d_evals) return AERO_ERR_INVALID;
-    aero_ctx *ctx = fri->ctx;
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    *d_evals = fri->cur;
-    if (count) *count = fri->curM;
-    if (coset_begin) *coset_begin = (uint32_t)fri->coset_begin;
-    if (coset_count) *coset_count = (uint32_t)fri->coset_count;
-    return AERO_OK;
-}
-aero_status aero_fri_mark_complete(aero_fri *fri) {
-    if (!fri) return AERO_ERR_INVALID;
-    fri->cur_pending = false;
     return AERO_OK;
 }
 
 // transpose_slice + hash_values + MerkleTree::new of the current evaluations, queued on the stream
 static aero_status fri_commit_enqueue(aero_fri *fri) {
     aero_ctx *ctx = fri->ctx;
+    enter(ctx);
     if (!fri->cur) CTX_FAIL(ctx, AERO_ERR_STATE, "no evaluations to commit");
     if (fri->cur_committed) CTX_FAIL(ctx, AERO_ERR_STATE, "layer already committed; fold first");
-    if (fri->cur_pending) CTX_FAIL(ctx, AERO_ERR_STATE, "sharded DEEP evaluations: exchange them and call aero_fri_mark_complete first");
     const uint32_t rows = fri->curM / 8;
     if (rows < 2) CTX_FAIL(ctx, AERO_ERR_INVALID, "FRI layer of %u evaluations is too small to commit", fri->curM);
     if (fri->cur_log_cosets && (rows >> fri->cur_log_cosets) == 0) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "layer too small for coset-major layout");
@@ -2023,6 +2186,7 @@ static aero_status fri_commit_enqueue(aero_fri *fri) {
 // apply_drp of the committed layer; the challenge comes by value or from device memory (alpha_dev)
 static aero_status fri_fold_enqueue(aero_fri *fri, uint64_t alpha_canon, const uint64_t *alpha_dev) {
     aero_ctx *ctx = fri->ctx;
+    enter(ctx);
     if (!fri->cur_committed) CTX_FAIL(ctx, AERO_ERR_STATE, "commit the layer before folding it");
     const uint32_t M = fri->curM, rows = M / 8;
     const int logM = ilog2(M);
@@ -2052,6 +2216,7 @@ static aero_status fri_fold_enqueue(aero_fri *fri, uint64_t alpha_canon, const u
 aero_status aero_fri_commit_layer(aero_fri *fri, uint8_t root[32]) {
     if (!fri || !root) return AERO_ERR_INVALID;
     aero_ctx *ctx = fri->ctx;
+    enter(ctx);
     TRY(fri_commit_enqueue(fri));
     CUDA_TRY(ctx, cudaMemcpyAsync(root, fri->layers.back().full + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -2068,6 +2233,7 @@ aero_status aero_fri_build_layers(aero_fri *fri, const uint8_t coin_seed[32], ui
                                   uint64_t *alphas_out) {
     if (!fri) return AERO_ERR_INVALID;
     aero_ctx *ctx = fri->ctx;
+    enter(ctx);
     if (!coin_seed || !roots_out || !alphas_out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     if (!fri->layers.empty() || fri->cur_committed) CTX_FAIL(ctx, AERO_ERR_STATE, "FRI layers have already been built");
     if (num_layers > 32) CTX_FAIL(ctx, AERO_ERR_INVALID, "too many FRI layers");
@@ -2099,6 +2265,7 @@ aero_status aero_fri_build_layers(aero_fri *fri, const uint8_t coin_seed[32], ui
 
 aero_status aero_fri_open(aero_fri *fri, const uint64_t *positions, uint32_t n_pos, uint8_t *out_bytes, size_t *len) {
     if (!fri || !positions || !len) return AERO_ERR_INVALID;
+    enter(fri->ctx);
     GatherBatch gb(fri->ctx);
     FriOpening o;
     TRY(fri_open_plan(fri, positions, n_pos, gb, o));
@@ -2121,13 +2288,15 @@ void aero_fri_destroy(aero_fri *fri) {
 // ---- grinding -------------------------------------------------------------------------------
 aero_status aero_pow_min_nonce(aero_ctx *ctx, const uint8_t seed[32], uint32_t grinding_bits, uint64_t *nonce) {
     if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
     if (!seed || !nonce) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     if (grinding_bits > 40) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "grinding factor above 40 bits");
     PhaseTimer t(ctx, "grind");
+    DevBlocks blk(ctx);
     uint32_t *d_seed = nullptr;
     unsigned long long *d_best = nullptr;
-    TRY(dev_alloc(ctx, (void **)&d_seed, 32));
-    TRY(dev_alloc(ctx, (void **)&d_best, 8));
+    TRY(blk.alloc((void **)&d_seed, 32));
+    TRY(blk.alloc((void **)&d_best, 8));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_seed, seed, 32, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(d_best, 0xFF, 8, ctx->stream));
     const uint32_t batch = 1u << 18;
@@ -2140,8 +2309,6 @@ aero_status aero_pow_min_nonce(aero_ctx *ctx, const uint8_t seed[32], uint32_t g
         if (best != ~0ULL) break;
         base += batch;
     }
-    dev_free(ctx, d_seed);
-    dev_free(ctx, d_best);
     *nonce = best;
     return AERO_OK;
 }

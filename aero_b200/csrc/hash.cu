@@ -21,30 +21,34 @@ __device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t h[8]) 
     h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
 }
 
-// One thread per LDE row.  The LDE is stored coset-major: storage row rho = r*n + i holds natural
-// row k = B*i + r (B = blowup), so thread rho reads column c at lde[c*col_stride + rho]: a fully
-// coalesced 8-byte-per-lane stream.  The digest goes to the natural slot leaves[k].
+// One thread per LDE row.  The LDE is stored coset-major: storage row rho = q*n + i (local coset q)
+// holds natural row k = B*i + coset_begin + q, so thread rho reads column c at lde[c*col_stride + rho]:
+// a fully coalesced 8-byte-per-lane stream.  The digest goes to the leaf stage of the rank that owns
+// the leaf block of i (kernels.cuh): coset-major inside the block, so consecutive threads store
+// consecutive 32-byte digests -- into local memory or, for foreign blocks, over NVLink.  A sharded proof
+// thereby sends each digest to exactly ONE peer (an all-to-all of N*32*(G-1)/G^2 bytes per rank)
+// instead of all-gathering the leaves.
 //
 // BLAKE2s absorbs the row left to right, so the chaining value after the first 2b columns depends
 // on those columns only: the kernel hashes the column range [c0, c0 + ncols) of a `total_cols`-wide
-// row (c0 even), reading the chaining value left by the previous range from leaves[k] (c0 > 0) and
+// row (c0 even), reading the chaining value left by the previous range from the leaf slot (c0 > 0) and
 // leaving its own there.  A whole row in one launch is the case c0 = 0, ncols = total_cols.  This
 // lets the row hash of one column batch run on a second stream while the next batch is extended.
 __global__ void __launch_bounds__(256) hash_rows_kernel(const uint64_t *__restrict__ lde, size_t col_stride, int c0,
                                                         int ncols, int total_cols, uint32_t nrows, int logn,
-                                                        int log_blowup, uint32_t coset_begin,
-                                                        uint32_t *__restrict__ leaves, PeerPtrs peers) {
-    const uint32_t n_mask = (1u << logn) - 1;
+                                                        uint32_t coset_begin, int log_nb, RankPtrs stage) {
+    const uint32_t n_mask = (1u << logn) - 1, nb_mask = (1u << log_nb) - 1;
     const int nblocks = (ncols + 1) >> 1;
     const uint32_t blocks_before = (uint32_t)c0 >> 1;
     const bool tail = (c0 + ncols == total_cols);
     // grid-stride over local storage rows rho (coset q = rho >> logn): the launcher bounds the grid so
     // that an overlapped launch leaves room on every SM for the NTT blocks of the next column batch
     for (uint32_t rho = blockIdx.x * blockDim.x + threadIdx.x; rho < nrows; rho += gridDim.x * blockDim.x) {
-        const uint32_t k = ((rho & n_mask) << log_blowup) | ((rho >> logn) + coset_begin);
+        const uint32_t i = rho & n_mask, coset = (rho >> logn) + coset_begin;
+        uint32_t *slot = reinterpret_cast<uint32_t *>(stage.p[i >> log_nb]) + ((((size_t)coset << log_nb) + (i & nb_mask)) << 3);
         uint32_t h[8];
         if (c0 == 0) b2s::init(h);
-        else load_digest(leaves + (size_t)k * 8, h);
+        else load_digest(slot, h);
         const uint64_t *p = lde + (size_t)c0 * col_stride + rho;
         uint64_t e0 = __ldg(p), e1 = ncols > 1 ? __ldg(p + col_stride) : 0ULL;
         for (int b = 0; b < nblocks; b++) {
@@ -59,74 +63,40 @@ __global__ void __launch_bounds__(256) hash_rows_kernel(const uint64_t *__restri
             e0 = n0;
             e1 = n1;
         }
-        store_digest(leaves + (size_t)k * 8, h);
-        // fused all-gather: the finished digest also goes to the leaf array of every peer rank (the
-        // intermediate chaining value of a column range stays local)
-        // (coset-major slot in the peer's staging array: consecutive threads write consecutive 32-byte
-        // digests, so the NVLink stores coalesce; natural slots are 32 bytes every 32*B bytes and
-        // ran at ~150 GB/s)
-        if (tail) {
-            const size_t slot = (size_t)rho + ((size_t)coset_begin << logn);
-            for (int q = 0; q < peers.n; q++) store_digest(reinterpret_cast<uint32_t *>(peers.p[q]) + slot * 8, h);
-        }
+        store_digest(slot, h);
     }
 }
 
 // ---- peer exchange helpers (multi-GPU) ----------------------------------------------------------
-// 16 bytes per thread: stage[(r*n + i)*2 + half] -> leaves[((i << log_blowup) | r)*2 + half] for the
-// cosets r outside [coset_begin, coset_begin + coset_count)
-__global__ void __launch_bounds__(256) leaves_from_stage_kernel(const uint4 *__restrict__ stage, uint4 *__restrict__ leaves,
-                                                                int logn, int log_blowup, int coset_begin,
-                                                                int coset_count) {
-    const size_t total = (size_t)2 << (logn + log_blowup);
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t d = t >> 1;
-        const uint32_t r = (uint32_t)(d >> logn), i = (uint32_t)(d & (((size_t)1 << logn) - 1));
-        if ((int)r >= coset_begin && (int)r < coset_begin + coset_count) continue;
-        leaves[((((size_t)i << log_blowup) | r) << 1) | (t & 1)] = stage[t];
-    }
-}
-void leaves_from_stage(const uint32_t *stage, uint32_t *leaves, int logn, int log_blowup, int coset_begin,
-                       int coset_count, cudaStream_t s) {
-    const size_t total = (size_t)2 << (logn + log_blowup);
-    size_t blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    AERO_COUNT_LAUNCH(1);
-    leaves_from_stage_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const uint4 *>(stage),
-                                                             reinterpret_cast<uint4 *>(leaves), logn, log_blowup,
-                                                             coset_begin, coset_count);
-}
-
-__global__ void __launch_bounds__(256) peer_push_kernel(const uint4 *__restrict__ local, PeerPtrs peers, size_t first,
-                                                        size_t count) {
+__global__ void __launch_bounds__(256) peer_push_kernel(RankPtrs buf, int G, int rank, size_t first, size_t count) {
+    const uint4 *local = reinterpret_cast<const uint4 *>(buf.p[rank]);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
         const uint4 v = local[first + i];
-        for (int q = 0; q < peers.n; q++) reinterpret_cast<uint4 *>(peers.p[q])[first + i] = v;
+        for (int q = 0; q < G; q++)
+            if (q != rank) reinterpret_cast<uint4 *>(buf.p[q])[first + i] = v;
     }
 }
-void peer_push(const void *local, const PeerPtrs &peers, size_t off, size_t bytes, cudaStream_t s) {
-    if (peers.n == 0 || bytes == 0) return;
+void peer_push(const RankPtrs &buf, int G, int rank, size_t off, size_t bytes, cudaStream_t s) {
+    if (G <= 1 || bytes == 0) return;
     const size_t count = bytes / 16;
     size_t blocks = (count + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     AERO_COUNT_LAUNCH(1);
-    peer_push_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const uint4 *>(local), peers, off / 16, count);
+    peer_push_kernel<<<(unsigned)blocks, 256, 0, s>>>(buf, G, rank, off / 16, count);
 }
-// Stream-ordered barrier between the ranks of a proof: thread q publishes `epoch` in peer q's flag
+// Stream-ordered barrier between the ranks of a proof: thread q publishes `epoch` in rank q's flag
 // slot for this rank (after a system-scope fence, so every peer store of earlier kernels on this
-// stream is visible first), then waits for peer q's flag in the local window.  A peer that never
+// stream is visible first), then waits for rank q's flag in the local window.  A peer that never
 // arrives (it failed) is given ~4 s; the time-out is reported through *d_timeout instead of hanging.
-__global__ void peer_barrier_kernel(volatile unsigned long long *my_flags, PeerPtrs peer_flags, int my_rank,
-                                    int r0, int r1, int r2, int r3, int r4, int r5, int r6, unsigned long long epoch,
-                                    unsigned int *d_timeout) {
+__global__ void peer_barrier_kernel(RankPtrs flags, int G, int rank, unsigned long long epoch, unsigned int *d_timeout) {
     const int q = threadIdx.x;
-    if (q >= peer_flags.n) return;
-    const int ranks[AERO_MAX_PEERS] = {r0, r1, r2, r3, r4, r5, r6};
+    if (q >= G || q == rank) return;
+    volatile unsigned long long *mine = reinterpret_cast<volatile unsigned long long *>(flags.p[rank]);
     __threadfence_system();
-    reinterpret_cast<volatile unsigned long long *>(peer_flags.p[q])[my_rank] = epoch;
+    reinterpret_cast<volatile unsigned long long *>(flags.p[q])[rank] = epoch;
     __threadfence_system();
     const long long t0 = clock64();
-    while (my_flags[ranks[q]] < epoch) {
+    while (mine[q] < epoch) {
         if (clock64() - t0 > 8000000000LL) {
             atomicAdd(d_timeout, 1u);
             break;
@@ -134,12 +104,29 @@ __global__ void peer_barrier_kernel(volatile unsigned long long *my_flags, PeerP
     }
     __threadfence_system();
 }
-void peer_barrier(unsigned long long *my_flags, const PeerPtrs &peer_flags, int my_rank, int peer_ranks[AERO_MAX_PEERS],
-                  unsigned long long epoch, unsigned int *d_timeout, cudaStream_t s) {
-    if (peer_flags.n == 0) return;
+void peer_barrier(const RankPtrs &flags, int G, int rank, unsigned long long epoch, unsigned int *d_timeout,
+                  cudaStream_t s) {
+    if (G <= 1) return;
     AERO_COUNT_LAUNCH(1);
-    peer_barrier_kernel<<<1, 32, 0, s>>>(my_flags, peer_flags, my_rank, peer_ranks[0], peer_ranks[1], peer_ranks[2],
-                                         peer_ranks[3], peer_ranks[4], peer_ranks[5], peer_ranks[6], epoch, d_timeout);
+    peer_barrier_kernel<<<1, 32, 0, s>>>(flags, G, rank, epoch, d_timeout);
+}
+
+// stage[c*n + i] -> out[B*i + c] (32 bytes each; single-rank segments only)
+__global__ void leaves_to_natural_kernel(const uint4 *__restrict__ stage, uint4 *__restrict__ out, int logn, int log_blowup) {
+    const size_t total = (size_t)2 << (logn + log_blowup);
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t k = t >> 1;
+        const size_t c = k & (((size_t)1 << log_blowup) - 1), i = k >> log_blowup;
+        out[t] = stage[(((c << logn) + i) << 1) | (t & 1)];
+    }
+}
+void leaves_to_natural(const uint32_t *stage, uint32_t *out, int logn, int log_blowup, cudaStream_t s) {
+    const size_t total = (size_t)2 << (logn + log_blowup);
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    AERO_COUNT_LAUNCH(1);
+    leaves_to_natural_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const uint4 *>(stage),
+                                                             reinterpret_cast<uint4 *>(out), logn, log_blowup);
 }
 
 // Generic variant: rows of a plain column-major matrix in natural order (used for small inputs /
@@ -169,9 +156,15 @@ __global__ void __launch_bounds__(256) hash_rows_natural_kernel(const uint64_t *
 // written to `full`.  Wide levels climb only MERKLE_LEVELS_PER_LAUNCH levels per launch so that
 // every warp stays full (256, 128, 64, 32 nodes); the last launch (<= 256 nodes) runs to the root.
 constexpr int MERKLE_LEVELS_PER_LAUNCH = 4;
+// stage != nullptr: the children of the bottom level are the leaf digests of a segment's coset-major
+// leaf stage ([B][nb]: leaf B*il + c at stage[c*nb + il], kernels.cuh) instead of heap nodes.
+// Digests travel between levels through shared memory WORD-MAJOR (sbuf[word][node]): a warp's stores
+// of one word are 32 consecutive banks and its loads of the (2t, 2t+1) child pair one 8-byte access per
+// lane, both conflict-free (the node-major layout of round 1 had 8-way conflicts on every access).
 __global__ void __launch_bounds__(256) merkle_subtree_kernel(uint32_t *__restrict__ full, uint32_t level_size, int width,
-                                                             int levels) {
-    __shared__ uint32_t sbuf[2][256 * 8];
+                                                             int levels, const uint32_t *__restrict__ stage, uint32_t nb,
+                                                             int log_blowup) {
+    __shared__ __align__(16) uint32_t sbuf[2][8][256];
     int cur = 0;
     // bottom level: children from global memory
     {
@@ -179,12 +172,19 @@ __global__ void __launch_bounds__(256) merkle_subtree_kernel(uint32_t *__restric
         for (int t = threadIdx.x; t < width; t += blockDim.x) {
             const uint32_t node = first + t;
             uint32_t a[8], b[8], o[8];
-            load_digest(full + (size_t)(2 * node) * 8, a);
-            load_digest(full + (size_t)(2 * node + 1) * 8, b);
+            if (stage) {
+                const uint32_t j = node - level_size;                   // pair index: leaves 2j, 2j + 1
+                const uint32_t il = j >> (log_blowup - 1), c = (j & ((1u << (log_blowup - 1)) - 1)) << 1;
+                load_digest(stage + ((size_t)c * nb + il) * 8, a);
+                load_digest(stage + ((size_t)(c + 1) * nb + il) * 8, b);
+            } else {
+                load_digest(full + (size_t)(2 * node) * 8, a);
+                load_digest(full + (size_t)(2 * node + 1) * 8, b);
+            }
             b2s::merge(a, b, o);
             store_digest(full + (size_t)node * 8, o);
 #pragma unroll
-            for (int i = 0; i < 8; i++) sbuf[cur][t * 8 + i] = o[i];
+            for (int i = 0; i < 8; i++) sbuf[cur][i][t] = o[i];
         }
     }
     for (int l = 1; l < levels; l++) {
@@ -195,41 +195,69 @@ __global__ void __launch_bounds__(256) merkle_subtree_kernel(uint32_t *__restric
             uint32_t a[8], b[8], o[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                a[i] = sbuf[cur][(2 * t) * 8 + i];
-                b[i] = sbuf[cur][(2 * t + 1) * 8 + i];
+                const uint2 ab = *reinterpret_cast<const uint2 *>(&sbuf[cur][i][2 * t]);
+                a[i] = ab.x;
+                b[i] = ab.y;
             }
             b2s::merge(a, b, o);
             store_digest(full + (size_t)(first + t) * 8, o);
 #pragma unroll
-            for (int i = 0; i < 8; i++) sbuf[cur ^ 1][t * 8 + i] = o[i];
+            for (int i = 0; i < 8; i++) sbuf[cur ^ 1][i][t] = o[i];
         }
         cur ^= 1;
     }
 }
 
-void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s) {
-    // node levels have sizes num_leaves/2, ..., 1 ; the level of size L occupies heap indices [L, 2L)
-    uint64_t level = num_leaves / 2;  // size of the lowest node level still to compute
+// levels from the node level of size `level` (children: heap nodes, or the leaf stage) up to the root
+static void merkle_levels(uint32_t *full, uint64_t level, const uint32_t *stage, uint32_t nb, int log_blowup, cudaStream_t s) {
     while (level >= 1) {
         AERO_COUNT_LAUNCH(1);
         if (level > 256) {
-            merkle_subtree_kernel<<<(unsigned)(level / 256), 256, 0, s>>>(full, (uint32_t)level, 256,
-                                                                        MERKLE_LEVELS_PER_LAUNCH);
+            merkle_subtree_kernel<<<(unsigned)(level / 256), 256, 0, s>>>(full, (uint32_t)level, 256, MERKLE_LEVELS_PER_LAUNCH,
+                                                                        stage, nb, log_blowup);
             level >>= MERKLE_LEVELS_PER_LAUNCH;
         } else {
             int levels = 0;
             for (uint64_t l = level; l >= 1; l >>= 1) levels++;
-            merkle_subtree_kernel<<<1, 256, 0, s>>>(full, (uint32_t)level, (int)level, levels);
+            merkle_subtree_kernel<<<1, 256, 0, s>>>(full, (uint32_t)level, (int)level, levels, stage, nb, log_blowup);
             break;
         }
+        stage = nullptr;
     }
 }
+void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s) {
+    // node levels have sizes num_leaves/2, ..., 1 ; the level of size L occupies heap indices [L, 2L)
+    merkle_levels(full, num_leaves / 2, nullptr, 0, 0, s);
+}
+void merkle_build_block(const uint32_t *stage, uint32_t *heap, uint32_t nb, int log_blowup, cudaStream_t s) {
+    merkle_levels(heap, ((uint64_t)nb << log_blowup) / 2, stage, nb, log_blowup, s);
+}
+__global__ void merkle_push_subroot_kernel(const uint32_t *__restrict__ heap, RankPtrs top, int G, int rank) {
+    const int r = threadIdx.x >> 3, w = threadIdx.x & 7;
+    if (r < G) reinterpret_cast<uint32_t *>(top.p[r])[(size_t)(G + rank) * 8 + w] = heap[8 + w];
+}
+void merkle_push_subroot(const uint32_t *heap, const RankPtrs &top, int G, int rank, cudaStream_t s) {
+    AERO_COUNT_LAUNCH(1);
+    merkle_push_subroot_kernel<<<1, 8 * AERO_MAX_RANKS, 0, s>>>(heap, top, G, rank);
+}
+__global__ void merkle_top_kernel(uint32_t *__restrict__ top, int G) {
+    if (threadIdx.x != 0) return;
+    for (int j = G - 1; j >= 1; j--) {
+        uint32_t a[8], b[8], o[8];
+        load_digest(top + (size_t)(2 * j) * 8, a);
+        load_digest(top + (size_t)(2 * j + 1) * 8, b);
+        b2s::merge(a, b, o);
+        store_digest(top + (size_t)j * 8, o);
+    }
+}
+void merkle_top(uint32_t *top, int G, cudaStream_t s) {
+    if (G <= 1) return;
+    AERO_COUNT_LAUNCH(1);
+    merkle_top_kernel<<<1, 32, 0, s>>>(top, G);
+}
 
-// nrows = (number of locally stored cosets) * n ; local coset q holds natural rows B*i + coset_begin + q.
-// Columns [c0, c0 + ncols) of a total_cols-wide row (see hash_rows_kernel); c0 must be even.
-// max_blocks > 0 caps the grid (the kernel strides over the rows).
-void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, int total_cols, int logn, int log_blowup,
-                   uint32_t coset_begin, uint32_t nrows, uint32_t *leaves, const PeerPtrs &peers, int max_blocks,
+void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, int total_cols, int logn,
+                   uint32_t coset_begin, uint32_t nrows, int log_nb, const RankPtrs &stage, int max_blocks,
                    cudaStream_t s) {
     if (nrows == 0 || ncols == 0) return;
     uint32_t grid = (nrows + 255) / 256;
@@ -238,8 +266,7 @@ void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, in
     // same shared-memory carve-out as the NTT passes, so both can be resident on one SM
     once.run([] { cudaFuncSetAttribute(hash_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); });
     AERO_COUNT_LAUNCH(1);
-    hash_rows_kernel<<<grid, 256, 0, s>>>(lde, col_stride, c0, ncols, total_cols, nrows, logn, log_blowup, coset_begin,
-                                          leaves, peers);
+    hash_rows_kernel<<<grid, 256, 0, s>>>(lde, col_stride, c0, ncols, total_cols, nrows, logn, coset_begin, log_nb, stage);
 }
 void hash_rows_natural(const uint64_t *m, size_t col_stride, int ncols, uint32_t nrows, uint32_t *leaves,
                        cudaStream_t s) {

@@ -64,31 +64,41 @@ __device__ __forceinline__ void fri_gather8(const uint64_t *__restrict__ f, uint
 }
 #endif
 
-// Peer copies of one buffer (multi-GPU): the same offset inside every other
-// rank's exchange window, mapped into this process with CUDA IPC.  Kernels store their results to
-// the local buffer and to each p[i] (NVLink peer stores), so the all-gather rides inside the kernel.
-constexpr int AERO_MAX_PEERS = 7;
-struct PeerPtrs {
-    void *p[AERO_MAX_PEERS];
-    int n = 0;
+// Multi-GPU: every rank of a sharded proof owns an exchange window; a buffer
+// bump-allocated inside it sits at the same offset on every rank, so a kernel can address all G copies:
+// p[r] = the copy on rank r (p[own rank] = the local buffer).  Kernels store results straight into the
+// copy of the rank that consumes them (NVLink peer stores), so the exchange rides inside the producer.
+constexpr int AERO_MAX_RANKS = 8;
+struct RankPtrs {
+    void *p[AERO_MAX_RANKS];
 };
 
 // hash.cu
-void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, int total_cols, int logn, int log_blowup,
-                   uint32_t coset_begin, uint32_t nrows, uint32_t *leaves, const PeerPtrs &peers, int max_blocks,
+// Row hashing of the LDE (K3).  nrows = (locally stored cosets) * n; local coset q holds natural rows
+// B*i + coset_begin + q.  The digest of (coset c, row i) goes to the LEAF STAGE of the rank that owns
+// the leaf block of i: rank i >> log_nb, slot (c << log_nb) + (i & (nb - 1)) -- coset-major inside the
+// block, so consecutive threads store consecutive 32-byte digests, locally or over NVLink.  With one
+// rank log_nb = logn and the stage is simply [B][n].  Columns [c0, c0 + ncols) of a total_cols-wide
+// row (see hash_rows_kernel); c0 must be even and, when > 0, all destinations local.
+// max_blocks > 0 caps the grid (the kernel strides over the rows).
+void hash_rows_lde(const uint64_t *lde, size_t col_stride, int c0, int ncols, int total_cols, int logn,
+                   uint32_t coset_begin, uint32_t nrows, int log_nb, const RankPtrs &stage, int max_blocks,
                    cudaStream_t s);
-// Sharded proofs: `leaves` of hash_rows_lde stays the LOCAL natural-order leaf array; the peer copies
-// (`peers`) are the other ranks' coset-major staging arrays, where this rank's digests form one
-// contiguous block (coset r at [r*n, (r+1)*n) digests).  leaves_from_stage moves the digests of the
-// cosets NOT in [coset_begin, coset_begin + coset_count) from the local staging array to their
-// natural slots leaves[B*i + r].
-void leaves_from_stage(const uint32_t *stage, uint32_t *leaves, int logn, int log_blowup, int coset_begin,
-                       int coset_count, cudaStream_t s);
-// copies [off, off + bytes) of the local buffer to the same range of every peer copy (16-byte units)
-void peer_push(const void *local, const PeerPtrs &peers, size_t off, size_t bytes, cudaStream_t s);
+// Tree over one rank's leaf block (K4, bottom part): stage = [B][nb] digests, heap = B*nb digests in
+// heap layout for the block's subtree (heap[1] = sub-root; the level of L nodes at [L, 2L)).  Leaf
+// B*il + c of the block is stage[c*nb + il].  Builds every level up to heap[1].
+void merkle_build_block(const uint32_t *stage, uint32_t *heap, uint32_t nb, int log_blowup, cudaStream_t s);
+// heap[1] of every rank -> top[G + rank] on all ranks (top = nodes 1 .. 2G-1 of the whole tree)
+void merkle_push_subroot(const uint32_t *heap, const RankPtrs &top, int G, int rank, cudaStream_t s);
+// top[j] = merge(top[2j], top[2j+1]) for j = G-1 .. 1
+void merkle_top(uint32_t *top, int G, cudaStream_t s);
+// copies [off, off + bytes) of the local buffer to the same range of every other rank's copy (16-byte units)
+void peer_push(const RankPtrs &buf, int G, int rank, size_t off, size_t bytes, cudaStream_t s);
 // all ranks arrive (epoch) before any leaves: flags[r] of rank q's window is written by rank r
-void peer_barrier(unsigned long long *my_flags, const PeerPtrs &peer_flags, int my_rank, int peer_ranks[AERO_MAX_PEERS],
-                  unsigned long long epoch, unsigned int *d_timeout, cudaStream_t s);
+void peer_barrier(const RankPtrs &flags, int G, int rank, unsigned long long epoch, unsigned int *d_timeout,
+                  cudaStream_t s);
+// natural-order leaf digests of a single-rank segment (tests / aero_segment_download_leaves)
+void leaves_to_natural(const uint32_t *stage, uint32_t *out, int logn, int log_blowup, cudaStream_t s);
 void hash_rows_natural(const uint64_t *m, size_t col_stride, int ncols, uint32_t nrows, uint32_t *leaves,
                        cudaStream_t s);
 void merkle_build(uint32_t *full, uint64_t num_leaves, cudaStream_t s);
@@ -125,8 +135,17 @@ void syn_div3(uint64_t *t1, uint64_t *t2, uint64_t *h, int logn, const uint64_t 
               cudaStream_t s);
 void deep_finish(const uint64_t *t1, const uint64_t *t2, const uint64_t *h, int logn, uint64_t d0, uint64_t d1,
                  uint64_t *out, cudaStream_t s);
+// Openings of a (possibly sharded) segment: every entry has ONE owning rank, which writes it into the
+// result buffer of every rank (out.p[r] + same offset); after a barrier all ranks hold all results.
+// Rows belong to the rank that stores their LDE coset; tree nodes to the rank whose leaf block they
+// cover; the top log2(G) levels exist on every rank and are written locally only.
+struct SegTreeView {
+    const uint32_t *stage, *heap, *top;
+    int logn, log_blowup, logG, rank;
+};
 void gather_rows(const uint64_t *lde_cm, size_t col_stride, int ncols, int logn, int log_blowup, int coset_begin,
-                 int coset_count, const uint32_t *d_positions, int npos, uint64_t *d_out, cudaStream_t s);
+                 int coset_count, int G, const uint32_t *d_positions, int npos, const RankPtrs &out, cudaStream_t s);
+void gather_tree_digests(const SegTreeView &t, const uint32_t *d_idx, int count, const RankPtrs &out, cudaStream_t s);
 void gather_fri_rows(const uint64_t *f, uint32_t rows, int log_cosets, const uint32_t *d_positions, int npos,
                      uint64_t *d_out, cudaStream_t s);
 void gather_digests(const uint32_t *full, const uint32_t *d_idx, int count, uint32_t *d_out, cudaStream_t s);
@@ -143,6 +162,9 @@ struct DivisorDev {
 void divisor_inverses(const DivisorDev &d, uint64_t *zinv_out, int logN, PowTable gN, cudaStream_t s);
 void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDev *divs, int ndiv, int logN,
                         uint64_t offset, PowTable gN, uint64_t *combined, cudaStream_t s);
+
+// peak.cu
+double measure_alu_peak(int num_sms, uint32_t *scratch, cudaStream_t s);
 
 // fri.cu
 // alpha_dev != nullptr: the folding challenge is read from device memory (written by fri_coin)

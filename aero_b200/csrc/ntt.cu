@@ -23,6 +23,23 @@ __device__ __forceinline__ void cp_async8_saddr(unsigned sa, const uint64_t *gme
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Shared-memory layout of an M x T tile: row `row` starts at word row*RS + T*(row >> r1), RS = T + 1 for
+// T > 1 (so that the transposed accesses of the store stages spread over the banks), plus T words of
+// padding after every 2^r1 rows, r1 = log2 of the first round's size.  Without the group padding the
+// 32/T row groups a warp touches in the first round (rows 2^r1 apart: 2^r1 * RS words, a multiple of the
+// 32 banks) all fell on the same banks -- 4-way conflicts for 8-wide tiles, 8-way for 4-wide ones (ncu:
+// 46-51 % of the shared wavefronts of a pass were conflicts); with it they tile the banks exactly.  In
+// every round the rows of one butterfly group stay an arithmetic progression, so the padding costs no
+// instruction there.
+template <int T, int RS>
+__host__ __device__ __forceinline__ int tile_off(int row, int r1) {
+    return row * RS + T * (row >> r1);
+}
+template <int T, int RS>
+__host__ __device__ __forceinline__ int tile_words(int logM, int r1) {
+    return (RS << logM) + T * ((1 << logM) >> r1);
+}
+
 // Fetches an M x T tile (M = 2^logM rows of T consecutive words, row j at g + (j << gsh_row)) into
 // shared memory with row j stored at row bitrev_logM(j).  blockDim.x = J*T threads, J a power of two
 // <= M: thread (j0 = tid / T, t = tid % T) owns rows j0 + k*J, whose bit-reversed positions are the
@@ -30,22 +47,27 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // leaves one BREV and one 64-bit add per element; the plain loop over `it` spent ~20 instructions per
 // element on index arithmetic (ncu: a fifth of all instructions of a pass).
 template <int T, int RS>
-__device__ __forceinline__ void load_tile_bitrev(uint64_t *a, const uint64_t *g, int logM, int gsh_row) {
+__device__ __forceinline__ void load_tile_bitrev(uint64_t *a, const uint64_t *g, int logM, int gsh_row, int r1) {
     const int logJ = 31 - __clz((int)blockDim.x / T);
     const int m = logM - logJ;
     const int t = threadIdx.x % T, j0 = threadIdx.x / T;
     const uint32_t row0 = (logJ ? (__brev((uint32_t)j0) >> (32 - logJ)) : 0u) << m;
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(a + row0 * RS + t);
     const uint64_t *gp = g + ((size_t)j0 << gsh_row) + t;
     const int gsh = logJ + gsh_row;
     if (m == 0) {
-        cp_async8_saddr(sa, gp);
+        cp_async8(a + tile_off<T, RS>((int)row0, r1) + t, gp);
         return;
     }
     const int rsh = 32 - m;
+    if (m <= r1) {  // the 2^m rows share one padding group
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(a + tile_off<T, RS>((int)row0, r1) + t);
 #pragma unroll 8
-    for (int r = 0; r < (1 << m); r++)
-        cp_async8_saddr(sa + r * (RS * 8), gp + ((size_t)(__brev((uint32_t)r) >> rsh) << gsh));
+        for (int r = 0; r < (1 << m); r++)
+            cp_async8_saddr(sa + r * (RS * 8), gp + ((size_t)(__brev((uint32_t)r) >> rsh) << gsh));
+    } else {
+        for (int r = 0; r < (1 << m); r++)
+            cp_async8(a + tile_off<T, RS>((int)row0 + r, r1) + t, gp + ((size_t)(__brev((uint32_t)r) >> rsh) << gsh));
+    }
 }
 
 // ---- compile-time structure of a 2^R-point round ------------------------------------------------
@@ -82,19 +104,22 @@ __host__ __device__ constexpr bool dft_need_canon(int R, int q, int e) {
 // IN_CANON: the tile holds canonical values already (pass 2 reads what pass 1 stored with
 // mul_canon), so a PLAIN0 round has nothing to canonicalise on the way in.
 template <int R, int T, int RS, bool PLAIN0, bool INV, bool IN_CANON = false>
-__device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s0, int logM) {
+__device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s0, int logM, int r1) {
     if (PLAIN0) s0 = 0;
     const int ngroups = (1 << logM) >> R;
     const int items = ngroups * T;
+    // rows base + (e << s0) of a group: words astep apart (s0 is 0 or >= r1, see tile_off)
+    const int astep = (RS << s0) + (s0 >= r1 ? (T << (s0 - r1)) : 0);
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
         const int t = it % T, g = it / T;
         const int low = g & ((1 << s0) - 1);
         const int base = ((g >> s0) << (s0 + R)) | low;
+        uint64_t *ag = a + tile_off<T, RS>(base, r1) + t;
         uint64_t x[1 << R];
         // tile values are "any" (congruent mod p, < 2^64); products are canonical
         static_for<(1 << R)>([&](auto E) {
             constexpr int e = decltype(E)::value;
-            uint64_t v = a[(base + (e << s0)) * RS + t];
+            uint64_t v = ag[e * astep];
             if constexpr (e > 0 && !PLAIN0) v = gl::mul_canon(v, tw[(e << s0) + low]);
             else if constexpr (!IN_CANON && dft_need_canon(R, 0, e)) v = gl::canon_any(v);
             x[e] = v;
@@ -127,24 +152,24 @@ __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s
         });
         static_for<(1 << R)>([&](auto E) {
             constexpr int e = decltype(E)::value;
-            a[(base + (e << s0)) * RS + t] = x[e];
+            ag[e * astep] = x[e];
         });
     }
 }
 
 template <int T, int RS, bool PLAIN0, bool INV, int RMAX, bool IN_CANON = false>
-__device__ __forceinline__ void dit_round_dispatch(int R, uint64_t *a, const uint64_t *tw, int s0, int logM) {
+__device__ __forceinline__ void dit_round_dispatch(int R, uint64_t *a, const uint64_t *tw, int s0, int logM, int r1) {
     if constexpr (RMAX >= 5) {
         if (R == 5) {
-            dit_round<5, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM);
+            dit_round<5, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM, r1);
             return;
         }
     }
     switch (R) {
-    case 4: dit_round<4, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM); break;
-    case 3: dit_round<3, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM); break;
-    case 2: dit_round<2, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM); break;
-    default: dit_round<1, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM); break;
+    case 4: dit_round<4, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM, r1); break;
+    case 3: dit_round<3, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM, r1); break;
+    case 2: dit_round<2, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM, r1); break;
+    default: dit_round<1, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM, r1); break;
     }
 }
 
@@ -152,13 +177,14 @@ __device__ __forceinline__ void dit_round_dispatch(int R, uint64_t *a, const uin
 template <int T, int RS, bool PLAIN, bool INV, int RMAX, bool IN_CANON = false>
 __device__ __forceinline__ void dit_tile(uint64_t *a, const uint64_t *tw, int logM) {
     const NttRounds rounds(logM);
+    const int r1 = rounds.log(0);
     // first round: s0 == 0 is a compile-time fact, which lets PLAIN transforms skip the unit twiddles
-    dit_round_dispatch<T, RS, PLAIN, INV, RMAX, IN_CANON>(rounds.log(0), a, tw, 0, logM);
+    dit_round_dispatch<T, RS, PLAIN, INV, RMAX, IN_CANON>(r1, a, tw, 0, logM, r1);
     __syncthreads();
-    int s0 = rounds.log(0);
+    int s0 = r1;
     for (int i = 1; i < rounds.count; i++) {
         const int R = rounds.log(i);
-        dit_round_dispatch<T, RS, false, INV, RMAX>(R, a, tw, s0, logM);
+        dit_round_dispatch<T, RS, false, INV, RMAX>(R, a, tw, s0, logM, r1);
         s0 += R;
         __syncthreads();
     }
@@ -193,8 +219,9 @@ __global__ void __launch_bounds__(MAXT) dft_pass1_kernel(const uint64_t *__restr
     extern __shared__ uint64_t smem[];
     const int n1 = 1 << log1;
     const size_t n = (size_t)1 << (log1 + log2);
-    uint64_t *a = smem;            // n1 * RS
-    uint64_t *tw = smem + n1 * RS; // n1
+    const int r1 = NttRounds(log1).log(0);
+    uint64_t *a = smem;                                  // the tile (tile_words)
+    uint64_t *tw = smem + tile_words<T, RS>(log1, r1);   // n1
     const int coset = blockIdx.y, col = blockIdx.z;
     const uint32_t j2_0 = blockIdx.x * T;
     const uint64_t *s = src + (size_t)col * src_col_stride;
@@ -211,7 +238,7 @@ __global__ void __launch_bounds__(MAXT) dft_pass1_kernel(const uint64_t *__restr
         }
     }
     for (int i = threadIdx.x; i < n1; i += blockDim.x) cp_async8(tw + i, stage1 + (size_t)coset * n1 + i);
-    load_tile_bitrev<T, RS>(a, s + j2_0, log1, log2);   // row j1 at s[(j1 << log2) + j2_0 + t]
+    load_tile_bitrev<T, RS>(a, s + j2_0, log1, log2, r1);   // row j1 at s[(j1 << log2) + j2_0 + t]
     cp_async_wait_all();
     __syncthreads();
     dit_tile<T, RS, PLAIN, INV, (MAXT <= 256 ? 5 : 4)>(a, tw, log1);
@@ -229,30 +256,38 @@ __global__ void __launch_bounds__(MAXT) dft_pass1_kernel(const uint64_t *__restr
         const size_t cstride = ((size_t)cstep << log2) * T;       // entries between this thread's chunks
         const uint64_t *fp = ftab + ((size_t)c << log2) * T + t * T + ii;
         uint64_t *op = o + ((size_t)c << log2) * T + (size_t)j2 * T + ii;
-        const uint64_t *ap = a + i1 * RS + t;
-        const int astride = step_i1 * RS;
-        for (; c + (U - 1) * cstep < nchunks; c += U * cstep) {
-            uint64_t f[U];
+        if ((step_i1 & ((1u << r1) - 1)) == 0) {  // this thread's rows are whole padding groups apart
+            const uint64_t *ap = a + tile_off<T, RS>((int)i1, r1) + t;
+            const int astride = step_i1 * RS + T * (step_i1 >> r1);
+            for (; c + (U - 1) * cstep < nchunks; c += U * cstep) {
+                uint64_t f[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) f[u] = __ldg(fp + u * cstride);
+                for (int u = 0; u < U; u++) f[u] = __ldg(fp + u * cstride);
 #pragma unroll
-            for (int u = 0; u < U; u++) op[u * cstride] = gl::mul_canon(ap[u * astride], f[u]);
-            fp += U * cstride;
-            op += U * cstride;
-            ap += U * astride;
-        }
-        for (; c < nchunks; c += cstep) {
-            *op = gl::mul_canon(*ap, __ldg(fp));
-            fp += cstride;
-            op += cstride;
-            ap += astride;
+                for (int u = 0; u < U; u++) op[u * cstride] = gl::mul_canon(ap[u * astride], f[u]);
+                fp += U * cstride;
+                op += U * cstride;
+                ap += U * astride;
+            }
+            for (; c < nchunks; c += cstep) {
+                *op = gl::mul_canon(*ap, __ldg(fp));
+                fp += cstride;
+                op += cstride;
+                ap += astride;
+            }
+        } else {  // small transforms
+            for (; c < nchunks; c += cstep, i1 += step_i1) {
+                *op = gl::mul_canon(a[tile_off<T, RS>((int)i1, r1) + t], __ldg(fp));
+                fp += cstride;
+                op += cstride;
+            }
         }
     } else {
         // F(i1, j2) = b[j2] * w_n^(i1*j2), advanced by a running product per thread
         uint64_t f = gl::mul(__ldg(inter_b + (size_t)coset * ((size_t)1 << log2) + j2), root_pow(wlo, whi, lo_bits, i1 * j2));
         const uint64_t d = root_pow(wlo, whi, lo_bits, step_i1 * j2);
         for (; c < nchunks; c += cstep, i1 += step_i1) {
-            const uint64_t v = gl::mul_canon(a[i1 * RS + t], f);
+            const uint64_t v = gl::mul_canon(a[tile_off<T, RS>((int)i1, r1) + t], f);
             o[((size_t)c << log2) * T + (size_t)j2 * T + ii] = v;
             f = gl::mul_any(f, d);
         }
@@ -288,13 +323,14 @@ __global__ void __launch_bounds__(MAXT) dft_pass2_kernel(const uint64_t *__restr
     const int n2 = 1 << log2;
     const int logn = log1 + log2;
     const size_t n = (size_t)1 << logn;
+    const int r1 = NttRounds(log2).log(0);
     uint64_t *a = smem;
-    uint64_t *tw = smem + n2 * RS;
+    uint64_t *tw = smem + tile_words<T, RS>(log2, r1);
     const int coset = blockIdx.y, col = blockIdx.z;
     const uint32_t i1_0 = blockIdx.x * T;
     const uint64_t *s = tmp + ((size_t)col * ncosets + coset) * n + ((size_t)blockIdx.x << log2) * T;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) cp_async8(tw + i, stage2 + i);
-    load_tile_bitrev<T, RS>(a, s, log2, T == 8 ? 3 : 2);   // row j2 at s[j2*T + t]
+    load_tile_bitrev<T, RS>(a, s, log2, T == 8 ? 3 : 2, r1);   // row j2 at s[j2*T + t]
     cp_async_wait_all();
     __syncthreads();
     dit_tile<T, RS, true, INV, (MAXT <= 256 ? 5 : 4), true>(a, tw, log2);  // tmp is canonical (pass 1's mul_canon)
@@ -303,9 +339,19 @@ __global__ void __launch_bounds__(MAXT) dft_pass2_kernel(const uint64_t *__restr
     const int J = blockDim.x / T;
     const int t = threadIdx.x % T, j0 = threadIdx.x / T;
     const uint32_t i1 = i1_0 + t;
-    const uint64_t *ap = a + j0 * RS + t;
-    const int astep = J * RS;
     const int K = n2 / J;
+    if ((J & ((1 << r1) - 1)) != 0) {  // small transforms: rows of a thread inside one padding group
+        for (int k = 0; k < K; k++) {
+            const int i2 = j0 + k * J;
+            uint64_t v = a[tile_off<T, RS>(i2, r1) + t];
+            if (post_u) v = gl::mul(v, gl::mul(__ldg(post_u + i1), __ldg(post_v + i2)));
+            else v = gl::canon_any(v);
+            o[out_index(i1 + ((uint32_t)i2 << log1), logn, deint)] = v;
+        }
+        return;
+    }
+    const uint64_t *ap = a + tile_off<T, RS>(j0, r1) + t;
+    const int astep = J * RS + T * (J >> r1);
     if (deint == 0) {
         uint64_t *op = o + i1 + ((size_t)j0 << log1);
         const size_t ostep = (size_t)J << log1;
@@ -340,20 +386,21 @@ __global__ void __launch_bounds__(256) dft_single_kernel(const uint64_t *__restr
                                                          size_t src_col_stride, size_t dst_col_stride, int deint) {
     extern __shared__ uint64_t smem[];
     const int n = 1 << logn;
+    const int r1 = NttRounds(logn).log(0);
     uint64_t *a = smem;
-    uint64_t *tw = smem + n;
+    uint64_t *tw = smem + tile_words<1, 1>(logn, r1);
     const int coset = blockIdx.y, col = blockIdx.z;
     const uint64_t *s = src + (size_t)col * src_col_stride;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         cp_async8(tw + i, stage + (size_t)coset * n + i);
-        cp_async8(a + bitrev(i, logn), s + i);
+        cp_async8(a + tile_off<1, 1>((int)bitrev(i, logn), r1), s + i);
     }
     cp_async_wait_all();
     __syncthreads();
     dit_tile<1, 1, PLAIN, INV, 5>(a, tw, logn);
     uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        uint64_t v = a[i];
+        uint64_t v = a[tile_off<1, 1>(i, r1)];
         if (post_u) v = gl::mul(v, __ldg(post_u + i));
         else if (scale != 1) v = gl::mul(v, scale);
         else v = gl::canon_any(v);
@@ -388,7 +435,7 @@ template <int T, bool PLAIN, bool INV, bool TAB, int MAXT>
 static void launch_pass1(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
     static DeviceOnce once;  // function attributes are per device
     once.run([] {
-        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     });
@@ -404,7 +451,7 @@ template <int T, bool INV, int MAXT>
 static void launch_pass2(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
     static DeviceOnce once;
     once.run([] {
-        cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     });
@@ -418,8 +465,8 @@ template <int T>
 static void launch_two_pass(const DftTables &t, const DftLaunch &l, cudaStream_t s) {
     const int n1 = 1 << t.log1, n2 = 1 << t.log2;
     const int nc = l.coset_count ? l.coset_count : t.ncosets;
-    const size_t smem1 = (size_t)n1 * (T + 1) * 8 + (size_t)n1 * 8;
-    const size_t smem2 = (size_t)n2 * (T + 1) * 8 + (size_t)n2 * 8;
+    const size_t smem1 = (size_t)(tile_words<T, T + 1>(t.log1, NttRounds(t.log1).log(0)) + n1) * 8;
+    const size_t smem2 = (size_t)(tile_words<T, T + 1>(t.log2, NttRounds(t.log2).log(0)) + n2) * 8;
     // 512 threads while two blocks fit the 227 KB of shared memory of an SM; a 2^12-point pass
     // (192 KB, one block per SM) runs 1024 threads instead so the SM still holds 32 warps
     // a schedule with a 32-point round needs the 256-thread (128-register) instantiation
@@ -462,7 +509,8 @@ static void launch_single(const DftTables &t, const DftLaunch &l, cudaStream_t s
     const int th = items < 32 ? 32 : (items > 256 ? 256 : items);
     const int nc = l.coset_count ? l.coset_count : t.ncosets;
     dim3 g(1, nc, l.ncols);
-    dft_single_kernel<PLAIN, INV><<<g, th, (size_t)n * 16, s>>>(l.src, l.dst, t.stage2 + (size_t)l.coset_begin * n, t.post_u,
+    const size_t smem = (size_t)(tile_words<1, 1>(t.logn, NttRounds(t.logn).log(0)) + n) * 8;
+    dft_single_kernel<PLAIN, INV><<<g, th, smem, s>>>(l.src, l.dst, t.stage2 + (size_t)l.coset_begin * n, t.post_u,
                                                                t.single_scale, t.logn, l.src_col_stride,
                                                                l.dst_col_stride, l.deinterleave_log);
 }

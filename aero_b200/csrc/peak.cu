@@ -1,0 +1,51 @@
+// In-run measurement of the roofline denominator that binds this path: the issue rate of the ALU pipe
+// (LOP3 / SHF / PRMT / IADD3), which is what the BLAKE2s row hash and the carry chains of the NTT
+// butterflies saturate (the full instruction table is tools/int_peak.cu).
+#include "kernels.cuh"
+
+namespace aero {
+
+constexpr int PEAK_ILP = 8;
+__global__ void __launch_bounds__(256) alu_peak_kernel(uint32_t *out, uint32_t seed, int iters) {
+    uint32_t x[PEAK_ILP], y[PEAK_ILP];
+#pragma unroll
+    for (int i = 0; i < PEAK_ILP; i++) {
+        x[i] = seed + threadIdx.x * 77 + i;
+        y[i] = seed * 3 + i + blockIdx.x + threadIdx.x * 0x9e3779b1u;
+    }
+    const uint32_t c = seed | 1;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < PEAK_ILP; i++) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y[i]), "r"(c));
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < PEAK_ILP; i++) acc ^= x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+// lane-operations per second of dependent-chain-free LOP3 streams, 8 warps per scheduler, ~1 ms
+double measure_alu_peak(int num_sms, uint32_t *scratch /* num_sms * 4 * 256 words */, cudaStream_t s) {
+    const int blocks = num_sms * 4, iters = 4096;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    AERO_COUNT_LAUNCH(3);
+    alu_peak_kernel<<<blocks, 256, 0, s>>>(scratch, 12345u, iters);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 2; rep++) {
+        cudaEventRecord(e0, s);
+        alu_peak_kernel<<<blocks, 256, 0, s>>>(scratch, 12345u + rep, iters);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double rate = (double)blocks * 256 * iters * PEAK_ILP / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return best;
+}
+
+}  // namespace aero

@@ -394,29 +394,59 @@ void deep_finish(const uint64_t *t1, const uint64_t *t2, const uint64_t *h, int 
 // K9: query gathers (prover/src/trace/commitment.rs:115-140, constraints/commitment.rs:54-70,
 // fri/src/prover/mod.rs:282-302, crypto/src/merkle/mod.rs:188-250 for the node list)
 // ---------------------------------------------------------------------------------------------
-// Rows whose coset is not stored on this rank come back as zeros (the ranks' results are disjoint
-// and are summed by the caller's exchange).
+// Every opened row / node has one owning rank, which writes it into the result buffer of every rank.
 __global__ void gather_rows_kernel(const uint64_t *__restrict__ lde, size_t col_stride, int ncols, int logn,
-                                   int log_blowup, int coset_begin, int coset_count,
-                                   const uint32_t *__restrict__ pos, int npos, uint64_t *__restrict__ out) {
+                                   int log_blowup, int coset_begin, int coset_count, int G,
+                                   const uint32_t *__restrict__ pos, int npos, RankPtrs out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npos * ncols) return;
     const int p = i / ncols, c = i - p * ncols;
     const uint32_t k = pos[p];
     const int q = (int)(k & ((1u << log_blowup) - 1)) - coset_begin;
-    if (q < 0 || q >= coset_count) {
-        out[i] = 0;
-        return;
-    }
+    if (q < 0 || q >= coset_count) return;  // another rank stores this coset
     const size_t rho = ((size_t)q << logn) + (k >> log_blowup);
-    out[i] = lde[(size_t)c * col_stride + rho];
+    const uint64_t v = lde[(size_t)c * col_stride + rho];
+    for (int r = 0; r < G; r++) reinterpret_cast<uint64_t *>(out.p[r])[i] = v;
 }
 void gather_rows(const uint64_t *lde_cm, size_t col_stride, int ncols, int logn, int log_blowup, int coset_begin,
-                 int coset_count, const uint32_t *d_positions, int npos, uint64_t *d_out, cudaStream_t s) {
+                 int coset_count, int G, const uint32_t *d_positions, int npos, const RankPtrs &out, cudaStream_t s) {
     const int total = npos * ncols;
     AERO_COUNT_LAUNCH(1);
     gather_rows_kernel<<<(total + 127) / 128, 128, 0, s>>>(lde_cm, col_stride, ncols, logn, log_blowup, coset_begin,
-                                                           coset_count, d_positions, npos, d_out);
+                                                           coset_count, G, d_positions, npos, out);
+}
+// idx: heap indices of the WHOLE tree (leaf k = N + k, internal node j, root 1)
+__global__ void gather_tree_digests_kernel(SegTreeView t, const uint32_t *__restrict__ idx, int count, RankPtrs out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count * 8) return;
+    const uint32_t g = idx[i >> 3], w = i & 7;
+    const int logN = t.logn + t.log_blowup, log_nb = t.logn - t.logG;
+    const int G = 1 << t.logG;
+    const uint32_t *src;
+    int owner;
+    if (g >> logN) {  // leaf
+        const uint32_t k = g - (1u << logN);
+        const uint32_t r = k >> t.log_blowup, c = k & ((1u << t.log_blowup) - 1);
+        owner = (int)(r >> log_nb);
+        src = t.stage + ((((size_t)c << log_nb) + (r & ((1u << log_nb) - 1))) << 3);
+    } else if (g >= (uint32_t)G) {  // node inside a rank's subtree
+        const int lv = 31 - __clz(g);          // level of 2^lv nodes
+        const uint32_t j = g - (1u << lv);
+        const int ll = lv - t.logG;            // 2^ll of them per rank
+        owner = (int)(j >> ll);
+        src = t.heap + ((((size_t)1 << ll) + (j & ((1u << ll) - 1))) << 3);
+    } else {  // top levels: on every rank
+        reinterpret_cast<uint32_t *>(out.p[t.rank])[i] = t.top[(size_t)g * 8 + w];
+        return;
+    }
+    if (owner != t.rank) return;
+    const uint32_t v = src[w];
+    for (int r = 0; r < G; r++) reinterpret_cast<uint32_t *>(out.p[r])[i] = v;
+}
+void gather_tree_digests(const SegTreeView &t, const uint32_t *d_idx, int count, const RankPtrs &out, cudaStream_t s) {
+    if (!count) return;
+    AERO_COUNT_LAUNCH(1);
+    gather_tree_digests_kernel<<<(count * 8 + 127) / 128, 128, 0, s>>>(t, d_idx, count, out);
 }
 __global__ void gather_fri_rows_kernel(const uint64_t *__restrict__ f, uint32_t rows, int log_cosets,
                                        const uint32_t *__restrict__ pos, int npos, uint64_t *__restrict__ out) {

@@ -2,7 +2,12 @@
 #include "prover.hpp"
 
 #include <algorithm>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 #include "../csrc/blake2s.cuh"
 #include "../csrc/gl.cuh"
@@ -34,6 +39,7 @@ Digest blake2s(const uint8_t *data, size_t len) {
     return to_digest(h);
 }
 Digest hash_elements(const std::vector<uint64_t> &e) {
+    if (e.empty()) return blake2s(nullptr, 0);  // BLAKE2s of the empty message, not the bare IV
     uint32_t h[8];
     b2s::init(h);
     const size_t nblocks = (e.size() + 1) / 2;
@@ -258,26 +264,41 @@ struct Handles {  // RAII for the device handles of one proof
 
 extern "C" int aero_ctx_get_form(aero_ctx *ctx);
 
-// Multi-GPU: complete a coset-sharded commitment (exchange leaf digests, then build the tree).
-static aero_status finish_commit(aero_ctx *ctx, const aero_prove_inputs &in, aero_segment *seg, uint32_t blowup,
-                                 uint8_t root[32], std::string *err) {
-    if (aero_ctx_window_ranks(ctx) > 1) {  // digests went to the peers from inside the row-hash kernel
-        P_TRY(aero_window_barrier(ctx));
-        P_TRY(aero_segment_finish_tree(seg, root));
-        return AERO_OK;
-    }
-    if (!in.all_gather_cosets) return AERO_OK;
-    void *d = nullptr;
-    uint64_t nl = 0;
-    uint32_t cb = 0, cc = 0;
-    P_TRY(aero_segment_leaves_device(seg, &d, &nl, &cb, &cc));
-    aero_status st = in.all_gather_cosets(in.user, d, nl / blowup, blowup, 32, 1, cb, cc);
-    if (st != AERO_OK) P_FAIL(st, "all_gather_cosets callback failed");
-    P_TRY(aero_segment_finish_tree(seg, root));
-    return AERO_OK;
+static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_t> *proof_bytes, std::string *err);
+
+// ProofOptions::new (air/src/options.rs:120-160) panics on these; here they are AERO_ERR_INVALID.
+static const char *check_options(const aero_proof_options &o) {
+    auto pow2 = [](uint32_t x) { return x && !(x & (x - 1)); };
+    if (o.num_queries == 0) return "number of queries must be greater than 0";
+    if (o.num_queries > 128) return "number of queries cannot be greater than 128";
+    if (!pow2(o.blowup_factor)) return "blowup factor must be a power of 2";
+    if (o.blowup_factor < 2) return "blowup factor cannot be smaller than 2";
+    if (o.blowup_factor > 128) return "blowup factor cannot be greater than 128";
+    if (o.grinding_factor > 32) return "grinding factor cannot be greater than 32";
+    if (!pow2(o.fri_folding_factor)) return "FRI folding factor must be a power of 2";
+    if (o.fri_folding_factor < 4) return "FRI folding factor cannot be smaller than 4";
+    if (o.fri_folding_factor > 16) return "FRI folding factor cannot be greater than 16";
+    if (!pow2(o.fri_max_remainder_size)) return "FRI max remainder size must be a power of 2";
+    if (o.fri_max_remainder_size < 32) return "FRI max remainder size cannot be smaller than 32";
+    if (o.fri_max_remainder_size > 1024) return "FRI max remainder size cannot be greater than 1024";
+    return nullptr;
 }
 
+// Brackets a (possibly sharded) proof: the first proof of a shape on a sharded context synchronises its
+// rank barriers on the host, later ones on the device (include/aero_b200.h, multi-GPU section).
 aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_t> *proof_bytes, std::string *err) {
+    if (const char *msg = check_options(in.options)) P_FAIL(AERO_ERR_INVALID, msg);
+    char key[160];
+    snprintf(key, sizeof key, "prove/%llu/%u/%u/%u/%d/q%u/b%u/g%u/r%u/c%u", (unsigned long long)in.trace_len, in.main_width, in.aux_width,
+             in.n_div, in.inputs_on_device, in.options.num_queries, in.options.blowup_factor, in.options.grinding_factor,
+             in.options.fri_max_remainder_size, in.ce_blowup);
+    P_TRY(aero_ctx_shard_begin(ctx, key));
+    aero_status st = prove_inner(ctx, in, proof_bytes, err);
+    aero_ctx_shard_end(ctx, st == AERO_OK);
+    return st;
+}
+
+static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_t> *proof_bytes, std::string *err) {
     const aero_proof_options &o = in.options;
     if (o.hash_fn != 4) P_FAIL(AERO_ERR_UNSUPPORTED, "only Blake2s_256 (hash_fn = 4) is supported");
     if (o.field_extension != 1) P_FAIL(AERO_ERR_UNSUPPORTED, "only FieldExtension::None is supported");
@@ -286,12 +307,18 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     if (in.aux_width && !in.aux_builder && !in.aux_cols) P_FAIL(AERO_ERR_INVALID, "auxiliary segment columns are required");
     if (!in.constraint_evaluator && !in.ce_cols) P_FAIL(AERO_ERR_INVALID, "constraint evaluations are required");
     if (in.inputs_on_device && (in.aux_builder || in.constraint_evaluator)) P_FAIL(AERO_ERR_INVALID, "callbacks need host inputs");
-    if ((in.all_gather_cosets || aero_ctx_window_ranks(ctx) > 1) && in.constraint_evaluator) P_FAIL(AERO_ERR_UNSUPPORTED, "sharded proofs take precomputed constraint evaluations");
+    const bool sharded = aero_ctx_window_ranks(ctx) > 1;
+    if (sharded && (in.constraint_evaluator || in.aux_builder)) P_FAIL(AERO_ERR_UNSUPPORTED, "sharded proofs take precomputed auxiliary columns and constraint evaluations");
+    if (in.trace_len < 2 || (in.trace_len & (in.trace_len - 1))) P_FAIL(AERO_ERR_INVALID, "trace length must be a power of two >= 2");
     const bool mont = aero_ctx_get_form(ctx) == AERO_FORM_MONTGOMERY;
     auto to_abi = [&](uint64_t x) { return mont ? gl::canon_to_mont(x) : x; };
     auto from_abi = [&](uint64_t x) { return mont ? gl::mont_to_canon(x) : gl::canon(x); };
     const uint64_t n = in.trace_len, N = n * o.blowup_factor;
     const uint32_t W = in.main_width + in.aux_width;
+    const uint32_t ce_blowup = in.ce_blowup ? in.ce_blowup : o.blowup_factor;
+    if ((ce_blowup & (ce_blowup - 1)) || ce_blowup < 2 || ce_blowup > o.blowup_factor)
+        P_FAIL(AERO_ERR_INVALID, "constraint evaluation blowup must be a power of two in 2..blowup_factor");
+    const uint64_t CE = n * ce_blowup;  // constraint evaluation domain (StarkDomain::ce_domain_size)
 
     Handles H;
     ProverChannel channel(ctx, in);
@@ -300,8 +327,9 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     // Host inputs that are already known (no callback produces them) start travelling now: their copies
     // queue behind the main segment's own and land while its columns are being extended and hashed.
     if (!in.inputs_on_device) {
-        if (in.aux_width && !in.aux_builder) P_TRY(aero_upload_start(ctx, in.aux_cols, in.aux_width, n, 1, &H.up_aux));
-        if (!in.constraint_evaluator) P_TRY(aero_upload_start(ctx, in.ce_cols, in.n_div, N, 1, &H.up_ce));
+        // (a sharded proof uploads only the trace columns this rank interpolates)
+        if (in.aux_width && !in.aux_builder) P_TRY(aero_upload_start(ctx, in.aux_cols, in.aux_width, n, 1, sharded, &H.up_aux));
+        if (!in.constraint_evaluator) P_TRY(aero_upload_start(ctx, in.ce_cols, in.n_div, CE, 1, 0, &H.up_ce));
     }
 
     // 1 ----- commit to the execution trace (lib.rs:239-248, 269-348)
@@ -311,7 +339,6 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     else
         P_TRY(aero_segment_commit(ctx, in.main_cols, in.main_width, n, o.blowup_factor, 0, &main_seg, root));
     H.segs.push_back(main_seg);
-    P_TRY(finish_commit(ctx, in, main_seg, o.blowup_factor, root, err));
     channel.commit_trace(Digest(root, root + 32));
 
     aero_segment *aux_seg = nullptr;
@@ -336,7 +363,6 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
         else
             P_TRY(aero_segment_commit(ctx, aux_cols, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root));
         H.segs.push_back(aux_seg);
-        P_TRY(finish_commit(ctx, in, aux_seg, o.blowup_factor, root, err));
         channel.commit_trace(Digest(root, root + 32));
     }
 
@@ -369,15 +395,14 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     if (H.up_ce) {
         const uint64_t *d_ce = nullptr;
         P_TRY(aero_upload_wait(H.up_ce, &d_ce));
-        P_TRY(aero_constraints_into_poly_device(ctx, d_ce, N, in.divisors, in.n_div, N, n, &comp_seg));
+        P_TRY(aero_constraints_into_poly_device(ctx, d_ce, CE, in.divisors, in.n_div, CE, n, &comp_seg));
     } else if (in.inputs_on_device)
-        P_TRY(aero_constraints_into_poly_device(ctx, ce_cols[0], N, in.divisors, in.n_div, N, n, &comp_seg));
+        P_TRY(aero_constraints_into_poly_device(ctx, ce_cols[0], CE, in.divisors, in.n_div, CE, n, &comp_seg));
     else
-        P_TRY(aero_constraints_into_poly(ctx, ce_cols, in.divisors, in.n_div, N, n, &comp_seg));
+        P_TRY(aero_constraints_into_poly(ctx, ce_cols, in.divisors, in.n_div, CE, n, &comp_seg));
     H.segs.push_back(comp_seg);
     lde_host.clear();
     P_TRY(aero_segment_commit_polys(comp_seg, o.blowup_factor, root));
-    P_TRY(finish_commit(ctx, in, comp_seg, o.blowup_factor, root, err));
     channel.commit_constraints(Digest(root, root + 32));
 
     // 4 ----- OOD frame + DEEP composition polynomial (lib.rs:421-467)
@@ -406,18 +431,6 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     for (auto &v : cc) v = to_abi(v);
     P_TRY(aero_deep_compose(ctx, trace_segs.data(), (uint32_t)trace_segs.size(), comp_seg, to_abi(z), ood_trace.data(),
                             ood_comp.data(), cc.data(), &H.fri));
-
-    if (aero_ctx_window_ranks(ctx) > 1) {
-        P_TRY(aero_fri_push_evaluations(H.fri));
-    } else if (in.all_gather_cosets) {
-        void *d = nullptr;
-        uint64_t cnt = 0;
-        uint32_t cb = 0, ccnt = 0;
-        P_TRY(aero_fri_evaluations_device(H.fri, &d, &cnt, &cb, &ccnt));
-        aero_status st = in.all_gather_cosets(in.user, d, n, o.blowup_factor, 8, 0, cb, ccnt);
-        if (st != AERO_OK) P_FAIL(st, "all_gather_cosets callback failed");
-        P_TRY(aero_fri_mark_complete(H.fri));
-    }
 
     // 6 ----- FRI layers (fri/src/prover/mod.rs:166-191)
     const size_t num_layers = ProofOptions{o}.num_fri_layers(N);
@@ -478,10 +491,6 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     fri_bytes.resize(flen);
     std::vector<Queries> all_q(ns);
     for (size_t i = 0; i < ns; i++) {
-        if (in.sum_rows) {  // coset-sharded proof: rows of other ranks come back as zeros
-            aero_status st = in.sum_rows(in.user, rows[i].data(), rows[i].size());
-            if (st != AERO_OK) P_FAIL(st, "sum_rows callback failed");
-        }
         paths[i].resize(paths_len[i]);
         all_q[i].values.assign((uint8_t *)rows[i].data(), (uint8_t *)rows[i].data() + rows[i].size() * 8);
         all_q[i].paths = std::move(paths[i]);
@@ -500,6 +509,128 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
 // C entry points (include/aero_prover.h)
 // ---------------------------------------------------------------------------------------------
 using namespace aero::host;
+
+// ---------------------------------------------------------------------------------------------
+// aero_group: G contexts of one process working on one proof (include/aero_prover.h)
+// ---------------------------------------------------------------------------------------------
+struct aero_group {
+    std::vector<aero_ctx *> ctxs;
+    // host rendezvous of the ranks' threads (first proof of a shape); abort() releases waiters with an
+    // error when a rank has failed
+    std::mutex mu;
+    std::condition_variable cv;
+    int waiting = 0;
+    unsigned long long generation = 0;
+    bool broken = false;
+    std::string err;
+    aero_status wait() {
+        std::unique_lock<std::mutex> lock(mu);
+        if (broken) return AERO_ERR_STATE;
+        const unsigned long long gen = generation;
+        if (++waiting == (int)ctxs.size()) {
+            waiting = 0;
+            generation++;
+            cv.notify_all();
+            return AERO_OK;
+        }
+        cv.wait(lock, [&] { return generation != gen || broken; });
+        return generation != gen ? AERO_OK : AERO_ERR_STATE;
+    }
+    void abort() {
+        std::lock_guard<std::mutex> lock(mu);
+        broken = true;
+        cv.notify_all();
+    }
+};
+static aero_status group_host_barrier(void *user) { return static_cast<aero_group *>(user)->wait(); }
+
+extern "C" {
+void aero_ctx_set_error(aero_ctx *ctx, const char *msg);
+
+aero_status aero_group_create(const int *device_ids, int n_ranks, size_t window_bytes, aero_group **out) {
+    if (!out || !device_ids) return AERO_ERR_INVALID;
+    *out = nullptr;
+    if (n_ranks < 1 || n_ranks > 8 || (n_ranks & (n_ranks - 1))) return AERO_ERR_INVALID;
+    // Ranks that share a device (tests) must not share a hardware work queue: a copy queued behind
+    // another rank's spinning barrier kernel would never start.  Only effective before CUDA initialises.
+    for (int r = 1; r < n_ranks; r++)
+        if (device_ids[r] == device_ids[0]) setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    aero_group *g = new aero_group();
+    aero_status st = AERO_OK;
+    for (int r = 0; r < n_ranks && st == AERO_OK; r++) {
+        aero_ctx *c = nullptr;
+        st = aero_ctx_create(&device_ids[r], 1, &c);
+        if (st != AERO_OK) break;
+        g->ctxs.push_back(c);
+        st = aero_ctx_set_option(c, "own_stream", 1);
+        if (st == AERO_OK) st = aero_ctx_set_shard(c, r, n_ranks);
+        if (st == AERO_OK && n_ranks > 1) st = aero_ctx_window_create(c, window_bytes, nullptr);
+        if (st == AERO_OK) st = aero_ctx_set_host_barrier(c, group_host_barrier, g);
+    }
+    for (int r = 0; r < n_ranks && st == AERO_OK && n_ranks > 1; r++) st = aero_ctx_window_attach_local(g->ctxs[r], n_ranks, g->ctxs.data());
+    if (st != AERO_OK) {
+        for (aero_ctx *c : g->ctxs) aero_ctx_destroy(c);
+        delete g;
+        return st;
+    }
+    *out = g;
+    return AERO_OK;
+}
+void aero_group_destroy(aero_group *g) {
+    if (!g) return;
+    for (aero_ctx *c : g->ctxs) aero_ctx_destroy(c);
+    delete g;
+}
+int aero_group_size(aero_group *g) { return g ? (int)g->ctxs.size() : 0; }
+aero_ctx *aero_group_ctx(aero_group *g, int rank) { return (g && rank >= 0 && rank < (int)g->ctxs.size()) ? g->ctxs[rank] : nullptr; }
+const char *aero_group_last_error(aero_group *g) { return g ? g->err.c_str() : "null group"; }
+
+aero_status aero_group_prove(aero_group *g, const aero_prove_inputs *in, int n_inputs, uint8_t *proof_out, size_t *len) {
+    if (!g || !in || !len) return AERO_ERR_INVALID;
+    const int G = (int)g->ctxs.size();
+    if (n_inputs != 1 && n_inputs != G) {
+        g->err = "n_inputs must be 1 (shared host inputs) or the number of ranks";
+        return AERO_ERR_INVALID;
+    }
+    {
+        std::lock_guard<std::mutex> lock(g->mu);
+        g->broken = false;
+        g->waiting = 0;
+    }
+    std::vector<std::vector<uint8_t>> bytes(G);
+    std::vector<std::string> errs(G);
+    std::vector<aero_status> sts(G, AERO_OK);
+    std::vector<std::thread> threads;
+    for (int r = 0; r < G; r++)
+        threads.emplace_back([&, r] {
+            sts[r] = prove(g->ctxs[r], in[n_inputs == 1 ? 0 : r], &bytes[r], &errs[r]);
+            if (sts[r] != AERO_OK) g->abort();  // do not leave the other ranks waiting for this one
+        });
+    for (auto &t : threads) t.join();
+    for (int r = 0; r < G; r++)
+        if (sts[r] != AERO_OK) {
+            char b[64];
+            snprintf(b, sizeof b, "rank %d: ", r);
+            g->err = b + errs[r];
+            aero_ctx_set_error(g->ctxs[r], errs[r].c_str());
+            return sts[r];
+        }
+    for (int r = 1; r < G; r++)
+        if (bytes[r] != bytes[0]) {
+            g->err = "the ranks produced different proofs";
+            return AERO_ERR_STATE;
+        }
+    if (!proof_out || *len < bytes[0].size()) {
+        *len = bytes[0].size();
+        g->err = "proof buffer too small";
+        return AERO_ERR_BUFFER;
+    }
+    memcpy(proof_out, bytes[0].data(), bytes[0].size());
+    *len = bytes[0].size();
+    return AERO_OK;
+}
+}
+
 struct aero_coin {
     RandomCoin c;
 };

@@ -187,6 +187,12 @@ class Context:
                                                  out.ctypes.data_as(p_u64)))
         return out
 
+    def measure_alu_peak(self) -> float:
+        """ALU-pipe issue rate of this GPU in lane-operations per second (aero_measure_alu_peak)."""
+        out = ctypes.c_double()
+        self._check(self.lib.aero_measure_alu_peak(self.h, ctypes.byref(out)))
+        return out.value
+
     def pow_min_nonce(self, seed: bytes, grinding_bits: int) -> int:
         s = (c_uint8 * 32).from_buffer_copy(seed)
         nonce = c_uint64()
@@ -218,93 +224,24 @@ class Context:
     def prove(self, main_trace, aux_trace, ce_cols, divisors: Sequence[Divisor], pub_inputs_bytes: bytes,
               options: Optional[ProofOptions] = None, aux_rands: int = 16, n_constraint_coeffs: int = 0,
               on_device: Optional[dict] = None, shard=None, aux_builder=None, aux_width: int = 0,
-              constraint_evaluator=None) -> bytes:
+              constraint_evaluator=None, ce_blowup: int = 0) -> bytes:
         """Prover::prove.  Host mode: numpy matrices.  Device mode (``on_device`` = dict with
         main/aux/ce device pointers and shapes): inputs already resident in HBM.
 
         ``aux_builder(rand_elements: np.ndarray) -> (aux_width, n) matrix`` and
         ``constraint_evaluator(trace_lde: list of N-element columns, coeffs: np.ndarray) -> (n_div, N)
         matrix`` are the two callbacks of include/aero_prover.h (the steps the north star keeps on the
-        reference's Rust path); with them ``aux_trace`` / ``ce_cols`` may be None."""
-        inp = ProveInputs()
-        inp.options = options or miden_options()
-        keep = []
-        cb_err = []
-        n_div = len(divisors)
-        if on_device is None:
-            inp.trace_len = main_trace.shape[1]
-            inp.main_width = main_trace.shape[0]
-            inp.main_cols = _cols(main_trace)
-            if aux_trace is not None:
-                inp.aux_width = aux_trace.shape[0]
-                inp.aux_cols = _cols(aux_trace)
-            if ce_cols is not None:
-                inp.ce_cols = _cols(ce_cols)
-            keep += [main_trace, aux_trace, ce_cols]
-            if aux_builder is not None:
-                inp.aux_width = aux_width
+        reference's Rust path); with them ``aux_trace`` / ``ce_cols`` may be None.
 
-                def _aux(user, rands, n_rand, cols_out):
-                    try:
-                        m = np.ascontiguousarray(aux_builder(np.ctypeslib.as_array(rands, shape=(n_rand,)).copy()), np.uint64)
-                        assert m.shape == (aux_width, inp.trace_len)
-                        keep.append(m)
-                        for c in range(aux_width):
-                            cols_out[c] = ctypes.cast(m.ctypes.data + c * m.shape[1] * 8, p_u64)
-                        return AERO_OK
-                    except Exception as e:  # never let an exception cross the C boundary
-                        cb_err.append(e)
-                        return _lib.AERO_ERR_STATE
-                inp.aux_builder = _lib.AUX_BUILDER(_aux)
-            if constraint_evaluator is not None:
-                def _ce(user, lde, width, lde_size, coeffs, n_coeffs, cols_out):
-                    try:
-                        cols = [np.ctypeslib.as_array(lde[c], shape=(lde_size,)) for c in range(width)]
-                        m = np.ascontiguousarray(constraint_evaluator(cols, np.ctypeslib.as_array(coeffs, shape=(n_coeffs,)).copy() if n_coeffs else np.zeros(0, np.uint64)), np.uint64)
-                        assert m.shape == (n_div, lde_size)
-                        keep.append(m)
-                        for c in range(n_div):
-                            cols_out[c] = ctypes.cast(m.ctypes.data + c * m.shape[1] * 8, p_u64)
-                        return AERO_OK
-                    except Exception as e:
-                        cb_err.append(e)
-                        return _lib.AERO_ERR_STATE
-                inp.constraint_evaluator = _lib.CONSTRAINT_EVALUATOR(_ce)
-        else:
-            inp.inputs_on_device = 1
-            inp.trace_len = on_device["trace_len"]
-            inp.main_width = on_device["main_width"]
-            inp.aux_width = on_device.get("aux_width", 0)
-            for name in ("main", "aux", "ce"):
-                arr = (p_u64 * 1)()
-                arr[0] = ctypes.cast(c_void_p(on_device.get(name, 0) or 0), p_u64)
-                setattr(inp, name + "_cols", arr)
-                keep.append(arr)
-        inp.aux_rands = aux_rands if inp.aux_width else 0
-        if shard is not None:  # aero_b200.sharded.ShardExchange: coset-sharded proof across ranks
-            self._check(self.lib.aero_ctx_set_shard(self.h, shard.rank, shard.world))
-            if getattr(shard, "window", False):
-                shard.attach_window(self)  # NVLink peer stores inside the kernels replace the all-gather
-                # the first proof of a shape allocates (cudaMalloc may block on a peer that is already
-                # waiting in the window's flag barrier): it takes the host-synchronised NCCL route
-                key = (inp.trace_len, inp.main_width, inp.aux_width, len(divisors), bool(on_device))
-                warm = key in shard.warm_shapes
-                shard.warm_shapes.add(key)
-                self.set_option("use_window", int(warm))
-                if not warm:
-                    inp.all_gather_cosets = shard._gather_cb
-            else:
-                inp.all_gather_cosets = shard._gather_cb
-            inp.sum_rows = shard._sum_cb
+        ``shard`` (aero_b200.sharded.ShardExchange): this process is one rank of a proof spread over
+        several GPUs; every rank calls prove with the same inputs and gets the same bytes."""
+        inp, keep, cb_err = build_prove_inputs(main_trace, aux_trace, ce_cols, divisors, pub_inputs_bytes, options,
+                                               aux_rands, n_constraint_coeffs, on_device, aux_builder, aux_width,
+                                               constraint_evaluator, ce_blowup)
+        if shard is not None:
+            shard.attach(self)  # set_shard + exchange window + host rendezvous, once per context
         else:
             self._check(self.lib.aero_ctx_set_shard(self.h, 0, 1))
-        divs = (Divisor * len(divisors))(*divisors)
-        inp.divisors = divs
-        inp.n_div = len(divisors)
-        inp.n_constraint_coeffs = n_constraint_coeffs
-        pub = (c_uint8 * len(pub_inputs_bytes)).from_buffer_copy(pub_inputs_bytes)
-        inp.pub_inputs_bytes = pub
-        inp.pub_inputs_len = len(pub_inputs_bytes)
         while True:
             buf = self._proof_buf  # reused across proofs (a c_uint8 slice would build a list of ints)
             cap = len(buf)
@@ -317,6 +254,126 @@ class Context:
                 raise cb_err[0]
             self._check(st)
             return ctypes.string_at(buf, ln.value)
+
+
+def build_prove_inputs(main_trace, aux_trace, ce_cols, divisors, pub_inputs_bytes, options=None, aux_rands=16,
+                       n_constraint_coeffs=0, on_device=None, aux_builder=None, aux_width=0, constraint_evaluator=None,
+                       ce_blowup=0):
+    """aero_prove_inputs for Context.prove / Group.prove: (struct, objects to keep alive, callback errors)."""
+    inp = ProveInputs()
+    inp.options = options or miden_options()
+    keep = []
+    cb_err = []
+    n_div = len(divisors)
+    if on_device is None:
+        inp.trace_len = main_trace.shape[1]
+        inp.main_width = main_trace.shape[0]
+        inp.main_cols = _cols(main_trace)
+        if aux_trace is not None:
+            inp.aux_width = aux_trace.shape[0]
+            inp.aux_cols = _cols(aux_trace)
+        if ce_cols is not None:
+            inp.ce_cols = _cols(ce_cols)
+        keep += [main_trace, aux_trace, ce_cols]
+        if aux_builder is not None:
+            inp.aux_width = aux_width
+
+            def _aux(user, rands, n_rand, cols_out):
+                try:
+                    m = np.ascontiguousarray(aux_builder(np.ctypeslib.as_array(rands, shape=(n_rand,)).copy()), np.uint64)
+                    assert m.shape == (aux_width, inp.trace_len)
+                    keep.append(m)
+                    for c in range(aux_width):
+                        cols_out[c] = ctypes.cast(m.ctypes.data + c * m.shape[1] * 8, p_u64)
+                    return AERO_OK
+                except Exception as e:  # never let an exception cross the C boundary
+                    cb_err.append(e)
+                    return _lib.AERO_ERR_STATE
+            inp.aux_builder = _lib.AUX_BUILDER(_aux)
+        if constraint_evaluator is not None:
+            def _ce(user, lde, width, lde_size, coeffs, n_coeffs, cols_out):
+                try:
+                    cols = [np.ctypeslib.as_array(lde[c], shape=(lde_size,)) for c in range(width)]
+                    cf = np.ctypeslib.as_array(coeffs, shape=(n_coeffs,)).copy() if n_coeffs else np.zeros(0, np.uint64)
+                    m = np.ascontiguousarray(constraint_evaluator(cols, cf), np.uint64)
+                    assert m.shape == (n_div, inp.trace_len * (ce_blowup or inp.options.blowup_factor))
+                    keep.append(m)
+                    for c in range(n_div):
+                        cols_out[c] = ctypes.cast(m.ctypes.data + c * m.shape[1] * 8, p_u64)
+                    return AERO_OK
+                except Exception as e:
+                    cb_err.append(e)
+                    return _lib.AERO_ERR_STATE
+            inp.constraint_evaluator = _lib.CONSTRAINT_EVALUATOR(_ce)
+    else:
+        inp.inputs_on_device = 1
+        inp.trace_len = on_device["trace_len"]
+        inp.main_width = on_device["main_width"]
+        inp.aux_width = on_device.get("aux_width", 0)
+        for name in ("main", "aux", "ce"):
+            arr = (p_u64 * 1)()
+            arr[0] = ctypes.cast(c_void_p(on_device.get(name, 0) or 0), p_u64)
+            setattr(inp, name + "_cols", arr)
+            keep.append(arr)
+    inp.aux_rands = aux_rands if inp.aux_width else 0
+    divs = (Divisor * len(divisors))(*divisors)
+    inp.divisors = divs
+    inp.n_div = len(divisors)
+    inp.n_constraint_coeffs = n_constraint_coeffs
+    inp.ce_blowup = ce_blowup
+    pub = (c_uint8 * len(pub_inputs_bytes)).from_buffer_copy(pub_inputs_bytes)
+    inp.pub_inputs_bytes = pub
+    inp.pub_inputs_len = len(pub_inputs_bytes)
+    keep += [divs, pub]
+    return inp, keep, cb_err
+
+
+class Group:
+    """aero_group: several GPUs of this process (or several contexts on one GPU, in tests) proving ONE
+    trace, the reference's rayon `concurrent` feature across devices (include/aero_prover.h)."""
+
+    def __init__(self, devices: Sequence[int], window_bytes: int, form: int = AERO_FORM_MONTGOMERY):
+        self.lib = _lib.load()
+        ids = (ctypes.c_int * len(devices))(*devices)
+        h = c_void_p()
+        st = self.lib.aero_group_create(ids, len(devices), window_bytes, ctypes.byref(h))
+        if st != AERO_OK:
+            raise AeroError(st, "aero_group_create failed")
+        self.h, self.size = h, len(devices)
+        for r in range(self.size):
+            st = self.lib.aero_ctx_set_form(self.lib.aero_group_ctx(self.h, r), form)
+            assert st == AERO_OK
+
+    def set_option(self, key: str, value: int) -> None:
+        for r in range(self.size):
+            st = self.lib.aero_ctx_set_option(self.lib.aero_group_ctx(self.h, r), key.encode(), int(value))
+            if st != AERO_OK:
+                raise AeroError(st, "set_option(%s)" % key)
+
+    def prove(self, main_trace, aux_trace, ce_cols, divisors, pub_inputs_bytes, **kw) -> bytes:
+        inp, keep, _ = build_prove_inputs(main_trace, aux_trace, ce_cols, divisors, pub_inputs_bytes, **kw)
+        cap = 1 << 20
+        while True:
+            buf = (c_uint8 * cap)()
+            ln = c_size_t(cap)
+            st = self.lib.aero_group_prove(self.h, ctypes.byref(inp), 1, buf, ctypes.byref(ln))
+            if st == AERO_ERR_BUFFER and ln.value > cap:
+                cap = ln.value
+                continue
+            if st != AERO_OK:
+                raise AeroError(st, (self.lib.aero_group_last_error(self.h) or b"").decode())
+            return ctypes.string_at(buf, ln.value)
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.aero_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Segment:

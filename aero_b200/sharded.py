@@ -1,110 +1,97 @@
-"""Multi-GPU plumbing for coset-sharded proofs: one process per GPU, torch.distributed (NCCL over
-NVLink on the GPU box, gloo in the CPU tests) carries the two exchanges the path needs.
+"""Multi-process plumbing for ONE proof spread over several GPUs: one process per GPU
+(torch.distributed: NCCL on the GPU box, gloo in the CPU tests).
 
-Sharding: rank r of G extends and row-hashes LDE cosets
-[r*B/G, (r+1)*B/G) of every column, i.e. complete LDE rows k with k mod B in that range.  Only
-  * 32-byte leaf digests (3 commitments) and
-  * the 8-byte DEEP evaluations (one column)
-cross the fabric; LDE data never moves.  Every rank then builds the (cheap) trees and runs the
-one-column FRI redundantly, so all Fiat-Shamir coins stay in lock-step without a broadcast.
+The data path never goes through torch.distributed: coefficients, leaf digests, sub-roots, DEEP
+evaluations and opening results are stored by the producing kernels straight into the consuming rank's
+exchange window over NVLink (include/aero_b200.h, multi-GPU section).  What is
+left for the process group is
+  * the all-gather of the 64-byte CUDA IPC handles of the windows, once per context, and
+  * a host rendezvous for the first proof of a shape (while contexts may still call cudaMalloc).
+
+Sharding: rank r of G interpolates (and uploads) trace columns [r*w/G, (r+1)*w/G), extends and
+row-hashes LDE cosets [r*B/G, (r+1)*B/G) of every column, and owns the Merkle subtree over leaves
+[r*N/G, (r+1)*N/G).
 """
 from __future__ import annotations
 
 import ctypes
-from typing import Optional
-
-import numpy as np
+from typing import List, Tuple
 
 from . import _lib
 
 
-def exchange_cosets(buf, outer: int, n_cosets: int, inner_bytes: int, interleaved: bool, coset_begin: int,
-                    coset_count: int, group=None) -> None:
-    """Completes ``buf`` (flat uint8 torch tensor, any device) in place: every rank contributed the
-    slices of its own cosets.  interleaved: [outer][B][inner] else [B][outer][inner]."""
+def own_columns(rank: int, world: int, n_cols: int) -> Tuple[int, int]:
+    """Columns a rank interpolates (own_columns in csrc/abi.cu)."""
+    return rank * n_cols // world, (rank + 1) * n_cols // world
+
+
+def own_cosets(rank: int, world: int, blowup: int) -> Tuple[int, int]:
+    """LDE cosets a rank extends and row-hashes."""
+    assert blowup % world == 0, "the number of ranks must divide the blowup factor"
+    return rank * blowup // world, (rank + 1) * blowup // world
+
+
+def leaf_block_owner(leaf: int, world: int, n_leaves: int) -> int:
+    """Rank whose subtree covers a leaf (and that therefore serves its Merkle path below the top log2(G) levels)."""
+    return leaf // (n_leaves // world)
+
+
+def window_bytes(log_rows: int, trace_cols: int, world: int, blowup: int = 8) -> int:
+    """Exchange-window size for a proof: coefficient matrices of the trace segments, three leaf blocks,
+    the DEEP evaluations, opening results and slack (include/aero_b200.h)."""
+    n = 1 << log_rows
+    N = n * blowup
+    return 8 * n * trace_cols + 3 * 32 * (N // world) + 8 * N + (8 << 20)
+
+
+def all_gather_handles(handle: bytes, group=None, device: str = "cpu") -> List[bytes]:
+    """Every rank's 64-byte IPC handle, in rank order."""
     import torch
     import torch.distributed as dist
 
-    world = dist.get_world_size(group)
-    assert coset_count * world == n_cosets and coset_begin == dist.get_rank(group) * coset_count
-    if interleaved:
-        t = buf.view(outer, n_cosets, inner_bytes)
-        own = t[:, coset_begin:coset_begin + coset_count, :].contiguous()
-    else:
-        t = buf.view(n_cosets, outer, inner_bytes)
-        own = t[coset_begin:coset_begin + coset_count].contiguous()
-    parts = [torch.empty_like(own) for _ in range(world)]
-    dist.all_gather(parts, own, group=group)
-    for p, part in enumerate(parts):
-        if p == dist.get_rank(group):
-            continue
-        if interleaved:
-            t[:, p * coset_count:(p + 1) * coset_count, :] = part
-        else:
-            t[p * coset_count:(p + 1) * coset_count] = part
-
-
-class _DevBuf:
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+    assert len(handle) == 64
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+    parts = [torch.empty_like(mine) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(parts, mine, group=group)
+    return [bytes(p.cpu().tolist()) for p in parts]
 
 
 class ShardExchange:
-    """Builds the C callbacks (aero_all_gather_cosets / aero_sum_rows) for Context.prove."""
+    """Makes a Context one rank of a sharded proof (``Context.prove(..., shard=ex)``)."""
 
-    def __init__(self, group=None, window_bytes: int = 0):
-        """window_bytes > 0: exchange over an IPC-mapped peer window (digests and DEEP evaluations are
-        stored into the peers' memory by the producing kernels, a flag barrier replaces the NCCL
-        all-gather); torch.distributed then only carries the 64-byte IPC handles once and the 27 opened
-        rows per segment.  0: NCCL all-gather through the aero_all_gather_cosets hook."""
-        import torch
+    def __init__(self, window_bytes: int, group=None):
         import torch.distributed as dist
 
-        self.torch, self.dist, self.group = torch, dist, group
+        self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.bytes_exchanged = 0
-        self.window, self.window_bytes, self._attached = window_bytes > 0, int(window_bytes), None
-        self.warm_shapes = set()
-        self._gather_cb = _lib.ALL_GATHER_COSETS(self._gather)
-        self._sum_cb = _lib.SUM_ROWS(self._sum_rows)
+        self.window_bytes = int(window_bytes)
+        self._attached = None
+        self.host_barriers = 0
+        self._barrier_cb = _lib.HOST_BARRIER(self._host_barrier)
 
-    def attach_window(self, ctx) -> None:
+    def _host_barrier(self, user) -> int:
+        try:
+            self.host_barriers += 1
+            self.dist.barrier(group=self.group)
+            return _lib.AERO_OK
+        except Exception as e:  # never let an exception cross the C boundary
+            print("host barrier failed:", repr(e))
+            return _lib.AERO_ERR_STATE
+
+    def attach(self, ctx) -> None:
         """Creates this rank's window on ``ctx``, all-gathers the IPC handles and maps the peers."""
         if self._attached is ctx:
             return
         if self._attached is not None:
-            raise RuntimeError("a ShardExchange window serves one context")
-        torch, dist = self.torch, self.dist
+            raise RuntimeError("a ShardExchange serves one context")
         ctx._check(ctx.lib.aero_ctx_set_shard(ctx.h, self.rank, self.world))
-        handle = (ctypes.c_uint8 * 64)()
-        ctx._check(ctx.lib.aero_ctx_window_create(ctx.h, self.window_bytes, handle))
-        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda" if dist.get_backend(self.group) == "nccl" else "cpu")
-        parts = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(parts, mine, group=self.group)
-        flat = bytes(torch.cat(parts).cpu().tolist())
-        buf = (ctypes.c_uint8 * len(flat)).from_buffer_copy(flat)
-        ctx._check(ctx.lib.aero_ctx_window_attach(ctx.h, self.world, buf))
-        dist.barrier(group=self.group)
+        if self.world > 1:
+            handle = (ctypes.c_uint8 * 64)()
+            ctx._check(ctx.lib.aero_ctx_window_create(ctx.h, self.window_bytes, handle))
+            dev = "cuda" if self.dist.get_backend(self.group) == "nccl" else "cpu"
+            flat = b"".join(all_gather_handles(bytes(handle), self.group, dev))
+            buf = (ctypes.c_uint8 * len(flat)).from_buffer_copy(flat)
+            ctx._check(ctx.lib.aero_ctx_window_attach(ctx.h, self.world, buf))
+            ctx._check(ctx.lib.aero_ctx_set_host_barrier(ctx.h, self._barrier_cb, None))
+            self.dist.barrier(group=self.group)
         self._attached = ctx
-
-    def _gather(self, user, d_buf, outer, n_cosets, inner_bytes, interleaved, coset_begin, coset_count):
-        try:
-            nbytes = outer * n_cosets * inner_bytes
-            buf = self.torch.as_tensor(_DevBuf(d_buf, nbytes), device="cuda")
-            exchange_cosets(buf, outer, n_cosets, inner_bytes, bool(interleaved), coset_begin, coset_count, self.group)
-            self.bytes_exchanged += nbytes // n_cosets * coset_count * (self.world - 1)
-            return _lib.AERO_OK
-        except Exception as e:  # never let an exception cross the C boundary
-            print("all_gather_cosets failed:", repr(e))
-            return _lib.AERO_ERR_STATE
-
-    def _sum_rows(self, user, host_rows, count):
-        try:
-            a = np.ctypeslib.as_array(host_rows, shape=(count,))
-            t = self.torch.from_numpy(a.view(np.int64).copy()).cuda()
-            self.dist.all_reduce(t, group=self.group)
-            a[:] = t.cpu().numpy().view(np.uint64)
-            return _lib.AERO_OK
-        except Exception as e:
-            print("sum_rows failed:", repr(e))
-            return _lib.AERO_ERR_STATE

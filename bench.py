@@ -32,17 +32,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MAIN_W, AUX_W, CE_COLS, BLOWUP = 72, 9, 2, 8
-# INT roofline of the row hash: static ALU-pipe instruction count of one
-# compress_pair in hash_rows_kernel (cuobjdump: 330 LOP3 + 160 SHF + 160 PRMT + 11 VIADD; floor 648),
-# and the ALU-pipe issue rate measured by tools/int_peak.cu on this pool's B200s.
+# INT roofline.  The row hash and the NTT passes are bound by instruction issue on
+# the ALU pipe (LOP3 / SHF / PRMT / IADD3).  Numerators: static ALU-pipe instruction count of one
+# compress_pair in hash_rows_kernel (cuobjdump: 330 LOP3 + 160 SHF + 160 PRMT + 11 VIADD; floor 648) and
+# ncu's executed ALU-pipe instructions per butterfly of the NTT passes.  Denominator: the ALU-pipe issue
+# rate MEASURED IN THIS RUN (aero_measure_alu_peak, a ~1 ms stream of independent LOP3).
 NTT_ALU_OPS_PER_BUTTERFLY = 21.8
 ALU_OPS_PER_COMPRESSION = 661
-ALU_PEAK_LANE_OPS = 18.4e12
-# dram__bytes_read.sum + dram__bytes_write.sum of one hash_rows_kernel launch (w=72, N=2^23) from the
-# ncu --set full capture profiles/r01_ncu_v4_hash_merkle.txt: 4.834 GB read (= the algorithmic 8wN, no
-# re-reads) + 0.795 GB written (0.268 GB of digests; a thread's 32-byte digest lands at a 256-byte
-# stride because rows of one LDE coset are 8 apart, so half-empty 64-byte DRAM atoms are written).
-HASH_W72_NCU_DRAM_BYTES = 5.6295e9
+# DRAM bytes of one hash_rows_kernel launch (w = 72, N = 2^23) in this round's ncu --set full capture
+# (profiles/r02_ncu_hash.txt); reported under roofline.traffic_ncu, never as a measurement of this run
+HASH_W72_NCU = None
 PUB = b"aero-b200 bench public inputs"
 
 
@@ -132,44 +131,59 @@ def measured_peaks():
 # reference arm / cpu_baseline: the oracle port timed on the host cores
 # --------------------------------------------------------------------------------------------------
 def cpu_port_rows_per_s(log_rows: int, steps: int = 1):
-    """Times oracle.prove (C/OpenMP restatement of the reference prover's hot path, all host threads)
-    on a bounded sample: a 2^log_rows-row trace of the same widths and options."""
+    """Times oracle.prove (C/OpenMP restatement of the reference prover's hot path) on a 2^log_rows-row
+    trace of the bench widths and options, on ALL host cores: the thread count is set explicitly
+    (torch.distributed.run exports OMP_NUM_THREADS=1).  Returns (rows/s of the best step, seconds of
+    every step, threads)."""
     from oracle import stark_oracle as so
 
     n = 1 << log_rows
+    lib = so.lib()
+    lib.aero_or_set_num_threads(os.cpu_count() or 1)
     main = splitmix_matrix(MAIN_W, n, 0xAE200000)
     aux = splitmix_matrix(AUX_W, n, 0xAE210000)
     ce = splitmix_matrix(CE_COLS, n * BLOWUP, 0xCE000000)
     g = so.root_of_unity(log_rows)
     divs = [so.Divisor(n, 1, [pow(g, n - 1, so.P)]), so.Divisor(1, 1, [])]
-    so.lib()
-    best = None
+    times = []
     for _ in range(steps):
         t = time.perf_counter()
         so.prove(main, aux, ce, divs, PUB, num_constraint_coeff_draws=0)
-        dt = time.perf_counter() - t
-        best = dt if best is None else min(best, dt)
-    return n / best, best, int(so.lib().aero_or_num_threads())
+        times.append(time.perf_counter() - t)
+    return n / min(times), times, int(lib.aero_or_num_threads())
 
 
 def run_reference(args) -> None:
+    """The reference's CPU implementation of the path (the oracle port: the Rust reference cannot be built
+    in this image) on the aero arm's workload -- the full 2^log_rows-row configuration, all host cores.
+    A 2^20-row proof takes ~20 s here, so the number of timed steps is what fits a ~150 s budget (at least
+    one); `steps` / `warmup` in the line are what actually ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    log_rows = args.ref_log_rows
     t0 = time.perf_counter()
-    for _ in range(args.warmup and 1):
-        cpu_port_rows_per_s(max(10, log_rows - 4), 1)
-    rps, dt, cores = cpu_port_rows_per_s(log_rows, max(1, min(args.steps, 3)))
-    sample = ("oracle port (C/OpenMP restatement of winter-prover's LDE+commit+DEEP+FRI; the Rust reference "
-              "cannot be built in this image) on a 2^%d-row 72+9-column synthetic trace, %d threads" % (log_rows, cores))
+    log_rows = args.ref_log_rows if args.ref_log_rows else args.log_rows
+    warm = 0
+    est = None
+    if args.warmup:
+        wl = max(10, log_rows - 4)
+        _, ts, _ = cpu_port_rows_per_s(wl, 1)  # warms the thread pool / page cache; also the time estimate
+        warm = 1
+        est = ts[0] * (1 << (log_rows - wl)) * 1.1
+    steps = max(1, min(args.steps, int(args.ref_budget_s / est))) if est else max(1, min(args.steps, 3))
+    rps, times, cores = cpu_port_rows_per_s(log_rows, steps)
+    dt = min(times)
+    sample = ("oracle port (C/OpenMP restatement of winter-prover's LDE + commit + DEEP + FRI) proving the "
+              "2^%d-row 72+9-column synthetic trace, %d threads, %d timed step(s) of %s s" %
+              (log_rows, cores, steps, "/".join("%.1f" % t for t in times)))
+    cfg = dict(workload_config(args, log_rows), parallelism="reference CPU path: %d host threads" % cores)
+    cfg["requested_steps"], cfg["requested_warmup"] = args.steps, args.warmup
+    if warm:
+        cfg["warmup_note"] = "warm-up = one proof of a 2^%d-row trace" % max(10, log_rows - 4)
     line = {"impl": "reference", "metric": "trace_rows_per_s", "value": rps, "unit": "rows/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            # same metric / unit / config as the aero arm; every step is a bounded sample of that workload (the
-            # metric is per trace row, the sample keeps all widths and options and shortens the trace)
-            "config": dict(workload_config(args, args.log_rows), reference_sample_log_rows=log_rows,
-                           parallelism="reference CPU path: %d host threads" % cores),
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 and not args.independent else "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
@@ -177,13 +191,19 @@ def run_reference(args) -> None:
 
 
 def workload_config(args, log_rows: int) -> dict:
+    if args.gpus == 1:
+        par = "single GPU"
+    elif args.independent:
+        par = "one independent proof per GPU (no data-path collective)"
+    else:
+        par = ("ONE proof over %d GPUs: interpolation sharded by column (coefficients stored into the peers over "
+               "NVLink), LDE + row hash sharded by coset, leaf digests stored into the rank owning the leaf block, "
+               "per-rank Merkle subtrees + top levels, device-side flag barriers" % args.gpus)
     return {"workload": "synthetic Miden trace 2^%d rows (72 main + 9 aux cols), blowup 8, Miden 96-bit options: "
                         "LDE + blake2s Merkle commit (main, aux, constraint) + OOD + DEEP + FRI + grinding + openings"
                         % log_rows,
             "log_rows": log_rows, "main_width": MAIN_W, "aux_width": AUX_W, "constraint_columns": CE_COLS,
-            "blowup": BLOWUP, "parallelism": ("single GPU" if args.gpus == 1 else
-                                             ("one proof sharded by LDE coset across %d GPUs (%s)" % (args.gpus, "NCCL all-gather of leaf digests and DEEP evaluations" if getattr(args, "nccl_exchange", False) else "leaf digests and DEEP evaluations stored into the peers' memory over NVLink by the producing kernels, flag barrier")) if getattr(args, "shard_proof", False) else
-                                             "one independent proof per GPU (no data-path collective)"), "l2": "inputs (0.7 GB) and LDE (5.4 GB) exceed the 126 MB L2"}
+            "blowup": BLOWUP, "parallelism": par, "l2": "inputs (0.7 GB) and LDE (5.4 GB) exceed the 126 MB L2"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -204,6 +224,7 @@ def run_aero(args) -> None:
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sharded = world > 1 and not args.independent
 
     log_rows = args.log_rows
     n = 1 << log_rows
@@ -223,7 +244,7 @@ def run_aero(args) -> None:
     if args.ntt_table_mb >= 0:
         ctx.set_option("ntt_table_max_bytes", args.ntt_table_mb << 20)
 
-    seed = 0 if args.shard_proof else 0x1000 * rank  # a sharded proof needs the same trace on every rank
+    seed = 0 if sharded else 0x1000 * rank  # one sharded proof: the same trace on every rank
     main = splitmix_matrix(MAIN_W, n, 0xAE200000 + seed)
     aux = splitmix_matrix(AUX_W, n, 0xAE210000 + seed)
     ce = splitmix_matrix(CE_COLS, N, 0xCE000000 + seed)
@@ -242,19 +263,21 @@ def run_aero(args) -> None:
     if not args.quick:  # (the profiling aid never runs the e2e leg)
         keep = [pin(main), pin(aux), pin(ce)]
         h_main, h_aux, h_ce = keep[0][1], keep[1][1], keep[2][1]
-    del main, aux, ce
+    pageable = (main, aux, ce)  # plain numpy buffers: what a caller holding Vec<Vec<u64>> columns passes
 
     shard = None
-    if args.shard_proof and world > 1:
-        from aero_b200.sharded import ShardExchange
-        # window: three 64*N-byte trees + the 8*N-byte DEEP evaluations (+ slack)
-        shard = ShardExchange(window_bytes=0 if args.nccl_exchange else (3 * 64 + 8) * N + (1 << 20))
+    if sharded:
+        from aero_b200.sharded import ShardExchange, window_bytes
+        shard = ShardExchange(window_bytes(log_rows, MAIN_W + AUX_W, world, BLOWUP))
 
     def step_device():
         return ctx.prove(None, None, None, divs, PUB, on_device=on_device, shard=shard)
 
     def step_host():
         return ctx.prove(h_main, h_aux, h_ce, divs, PUB, shard=shard)
+
+    def step_pageable():
+        return ctx.prove(pageable[0], pageable[1], pageable[2], divs, PUB, shard=shard)
 
     def barrier():
         if world > 1:
@@ -308,11 +331,9 @@ def run_aero(args) -> None:
     launches = ctx.lib.aero_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms / args.steps
-    nproofs = 1 if shard is not None else world
+    nproofs = 1 if sharded else world
     value = nproofs * n / (ms_step * 1e-3)
-    if shard is not None:  # the sharded proof must equal the single-GPU proof byte for byte
-        single = ctx.prove(None, None, None, divs, PUB, on_device=on_device)
-        assert single == proof, "sharded proof differs from the single-GPU proof"
+    alu_peak = ctx.measure_alu_peak()  # the INT roofline's denominator, measured on this GPU in this run
 
     if not args.quick:
         ctx.profile_enable(True)
@@ -325,7 +346,7 @@ def run_aero(args) -> None:
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": ms_step, "phase_ms": {k: v[1] / args.steps for k, v in prof.items()}}))
         return
-    for _ in range(3):  # warm the pinned path (and let the stream-ordered pool settle on the new sizes)
+    for _ in range(3):  # warm the pinned path (block cache settles on the new sizes)
         step_host()
     ms_e2e, proof_h = timed(step_host, args.steps)
     ms_e2e /= args.steps
@@ -337,56 +358,99 @@ def run_aero(args) -> None:
         prof_e2e = ctx.profile_read()
         ctx.profile_enable(False)
     assert proof_h == proof, "host-buffer and device-buffer proofs differ"
+    # the same call with pageable host buffers (no pinning by the caller, none by the library)
+    step_pageable()
+    ms_pg, proof_p = timed(step_pageable, max(2, args.steps // 2))
+    ms_pg /= max(2, args.steps // 2)
+    assert proof_p == proof, "pageable-buffer proof differs"
     e2e_val = nproofs * n / (ms_e2e * 1e-3)
-    h2d = (MAIN_W + AUX_W) * n * 8 + CE_COLS * N * 8
+    own_frac = 1.0 / world if sharded else 1.0  # a sharded rank uploads its own trace columns only
+    h2d = int((MAIN_W + AUX_W) * n * 8 * own_frac) + CE_COLS * N * 8
     d2h = len(proof) + 32 * 9
+
+    # Parity inside the bench run (checker only, outside every timed region).  N > 1: the sharded proof must
+    # equal the single-GPU proof of the same inputs byte for byte, and a 2^14-row sharded proof must equal
+    # the CPU restatement's bytes (what the driver's one-GPU test box cannot run).
+    parity = None
+    independent = None
+    if sharded:
+        ctx._check(ctx.lib.aero_ctx_set_shard(ctx.h, 0, 1))
+        single = ctx.prove(None, None, None, divs, PUB, on_device=on_device)
+        assert single == proof, "sharded proof differs from the single-GPU proof"
+        # secondary figure: one independent proof per GPU (throughput use of the box)
+        for _ in range(2):
+            ctx.prove(None, None, None, divs, PUB, on_device=on_device)
+        ms_ind, _ = timed(lambda: ctx.prove(None, None, None, divs, PUB, on_device=on_device), args.steps)
+        independent = {"value": world * n / (ms_ind / args.steps * 1e-3), "unit": "rows/s", "ms_per_step": ms_ind / args.steps,
+                       "note": "one independent proof per GPU, no data-path exchange (weak scaling)"}
+        ln = 14
+        sm, sa, sc = (splitmix_matrix(MAIN_W, 1 << ln, 0xAE200000), splitmix_matrix(AUX_W, 1 << ln, 0xAE210000),
+                      splitmix_matrix(CE_COLS, BLOWUP << ln, 0xCE000000))
+        small = ctx.prove(sm, sa, sc, bench_divisors(1 << ln), PUB, shard=shard)
+        parity = {"sharded_equals_single_gpu": True, "small_sharded_proof_bytes": len(small)}
+        if rank == 0 and not args.no_cpu_baseline:
+            from oracle import stark_oracle as so
+            so.lib().aero_or_set_num_threads(os.cpu_count() or 1)
+            m2c = so.mont_to_canon
+            g = so.root_of_unity(ln)
+            odivs = [so.Divisor(1 << ln, int(m2c(np.array([1], np.uint64))[0]), [int(m2c(np.array([pow(g, (1 << ln) - 1, so.P)], np.uint64))[0])]),
+                     so.Divisor(1, int(m2c(np.array([1], np.uint64))[0]), [])]
+            ref = so.prove(m2c(sm), m2c(sa), m2c(sc), odivs, PUB)
+            assert ref.proof_bytes == small, "2^14-row sharded proof differs from the CPU restatement"
+            parity["small_sharded_equals_cpu_restatement"] = True
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
         calls, tot_ms = prof.get("hash_rows_w%d" % MAIN_W, (0, 0.0))
-        if shard is not None:
-            N = N // world  # a coset shard hashes N/world rows per launch
-        alg_bytes = 8 * MAIN_W * N + 32 * N  # read 8wN + write 32N per launch
+        Nl = N // world if sharded else N  # a coset shard hashes N/world rows per launch
+        alg_bytes = 8 * MAIN_W * Nl + 32 * Nl  # read 8wN + write 32N per launch
         avg_ms = tot_ms / calls if calls else None
-        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms else None
-        comp_per_s = (36 * N) / (avg_ms * 1e-3) if avg_ms else None
-        roofline = {"bound": "hbm", "kernel": "hash_rows_kernel (blake2s leaf hash, w=72; INT32-ALU bound: "
-                    "36 compressions x 661 ALU-pipe ops per row vs 608 B per row)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                    "traffic": HASH_W72_NCU_DRAM_BYTES if (log_rows == 20 and shard is None) else None, "peak_kind": peak_kind,
-                    "avg_launch_ms": avg_ms, "compressions_per_s": comp_per_s,
-                    # the roofline that actually binds this kernel: ALU-pipe instruction issue
-                    "int": {"unit": "ALU-pipe lane-ops/s", "ops_per_compression": ALU_OPS_PER_COMPRESSION,
-                            "achieved": comp_per_s * ALU_OPS_PER_COMPRESSION if comp_per_s else None,
-                            "peak": ALU_PEAK_LANE_OPS, "peak_kind": "measured (tools/int_peak.cu, profiles/r01_int_peak.txt)",
-                            "frac": comp_per_s * ALU_OPS_PER_COMPRESSION / ALU_PEAK_LANE_OPS if comp_per_s else None}}
+        hbm_achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms else None
+        comp_per_s = (36 * Nl) / (avg_ms * 1e-3) if avg_ms else None
+        alu_achieved = comp_per_s * ALU_OPS_PER_COMPRESSION if comp_per_s else None
+        roofline = {"bound": "int", "kernel": "hash_rows_kernel (blake2s leaf hash, w=72): 36 compressions x 661 ALU-pipe "
+                    "instructions per row against 608 algorithmic bytes per row -- ALU-pipe issue is the roofline that binds",
+                    "achieved": alu_achieved / 1e12 if alu_achieved else None, "peak": alu_peak / 1e12, "unit": "Tlane-op/s (ALU pipe)",
+                    "frac": alu_achieved / alu_peak if alu_achieved else None,
+                    "peak_kind": "measured in this run (aero_measure_alu_peak: independent LOP3 streams, ~1 ms)",
+                    "ops_per_compression": ALU_OPS_PER_COMPRESSION, "compressions_per_s": comp_per_s,
+                    "avg_launch_ms": avg_ms, "traffic": None, "traffic_ncu": HASH_W72_NCU,
+                    "hbm": {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak if hbm_achieved else None,
+                            "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_bytes}}
         # second-largest share of the step: the NTT passes (interpolation + coset LDE of the trace segments)
         ntt_ms = sum(prof.get(k, (0, 0.0))[1] for k in ("interpolate_w%d" % MAIN_W, "interpolate_w%d" % AUX_W,
                                                         "lde_w%d" % MAIN_W, "lde_w%d" % AUX_W)) / args.steps
-        if ntt_ms > 0 and shard is None:
-            bfly = (1 + BLOWUP) * (MAIN_W + AUX_W) * (n // 2) * log_rows
+        if ntt_ms > 0:
+            bfly = (1 + BLOWUP) * (MAIN_W + AUX_W) * (n // 2) * log_rows / (world if sharded else 1)
             bps = bfly / (ntt_ms * 1e-3)
             roofline["ntt"] = {"unit": "butterflies/s", "achieved": bps, "ms_per_step": ntt_ms,
-                               # ncu: 34.2 executed thread instructions per butterfly of a 2^10-point pass, 63.8 % of
-                               # them on the ALU pipe (profiles/r01_ncu_v5_ntt.txt, r01_ncu_v10_ntt.txt)
+                               # ncu: executed ALU-pipe thread instructions per butterfly (profiles/)
                                "alu_ops_per_butterfly": NTT_ALU_OPS_PER_BUTTERFLY,
-                               "int_frac": bps * NTT_ALU_OPS_PER_BUTTERFLY / ALU_PEAK_LANE_OPS,
+                               "int_frac": bps * NTT_ALU_OPS_PER_BUTTERFLY / alu_peak,
                                "note": "INT bound: ALU pipe 71-80 % busy in ncu, DRAM 17-26 %"}
         cpu = None
-        if not args.no_cpu_baseline:
-            rps, dt, cores = cpu_port_rows_per_s(args.ref_log_rows, 1)
+        if not args.no_cpu_baseline and world == 1:
+            cl = args.ref_log_rows if args.ref_log_rows else log_rows
+            rps, ts, cores = cpu_port_rows_per_s(cl, 1)
             cpu = {"value": rps, "unit": "rows/s", "cores": cores, "kind": "port",
-                   "sample": "oracle port on a 2^%d-row trace of the same widths/options (%.1f s)" % (args.ref_log_rows, dt)}
+                   "sample": "oracle port proving the same 2^%d-row workload once (%.1f s)" % (cl, ts[0])}
         phases = {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items())}
         line = {"metric": "trace_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong" if shard is not None else "weak",
+                "scaling": "strong" if sharded else "weak",
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(args, log_rows),
                 "e2e": {"value": e2e_val, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e},
+                        "ms_per_step": ms_e2e, "host_buffers": "pinned"},
+                "e2e_pageable": {"value": nproofs * n / (ms_pg * 1e-3), "unit": "rows/s", "ms_per_step": ms_pg,
+                                 "note": "same call with pageable (unpinned) host columns, cudaMemcpyAsync straight from the "
+                                         "caller's pointers: the copies stage through the driver and do not overlap compute"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "phase_ms_per_step": phases,
                 "proof_bytes": len(proof)}
+        if independent:
+            line["independent_proofs"] = independent
+        if parity:
+            line["parity"] = parity
         if prof_e2e:  # --e2e-phases: the same phases inside a host-buffer step (separate, untimed pass)
             line["e2e_phase_ms_per_step"] = {k: round(v[1] / args.steps, 4) for k, v in sorted(prof_e2e.items())}
         print(json.dumps(line), flush=True)
@@ -401,14 +465,12 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="aero", choices=["aero", "reference"])
     ap.add_argument("--log-rows", type=int, default=20)
-    ap.add_argument("--ref-log-rows", type=int, default=18, help="trace size of the bounded CPU sample")
+    ap.add_argument("--ref-log-rows", type=int, default=0, help="trace size of the CPU arm (0 = the workload's own size)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="time budget of the reference arm's timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard-proof", action="store_true",
-                    help="N>1: shard ONE proof across the ranks by LDE coset (strong scaling) instead of one "
-                         "independent proof per rank")
-    ap.add_argument("--nccl-exchange", action="store_true",
-                    help="--shard-proof: exchange leaf digests / DEEP evaluations with NCCL all-gathers instead of "
-                         "NVLink peer stores from inside the kernels")
+    ap.add_argument("--independent", action="store_true",
+                    help="N>1: one independent proof per rank (weak scaling) instead of ONE proof sharded over the ranks")
+    ap.add_argument("--shard-proof", action="store_true", help="(default for N>1; kept for older command lines)")
     ap.add_argument("--overlap-hash", type=int, default=0,
                     help="1: row hashing of column batch k runs on a second stream beside the LDE of batch k+1")
     ap.add_argument("--hash-blocks-per-sm", type=int, default=0)

@@ -57,8 +57,9 @@ typedef struct aero_divisor {
 } aero_divisor;
 
 /* ---- context --------------------------------------------------------------------------------- */
-/* n_devices must be 1 in this release (one process per GPU; multi-GPU is composed above the ABI,
- * see DESIGN.md).  device_ids == NULL selects the current device. */
+/* One context drives one GPU: n_devices must be 1 (device_ids == NULL selects the current device).
+ * Several GPUs work on one proof as one context per GPU joined by an exchange window: see the
+ * multi-GPU section below, and aero_group_create (include/aero_prover.h) for the one-process form. */
 aero_status aero_ctx_create(const int *device_ids, int n_devices, aero_ctx **out);
 void aero_ctx_destroy(aero_ctx *ctx);
 const char *aero_last_error(aero_ctx *ctx);
@@ -76,11 +77,9 @@ int aero_ctx_get_form(aero_ctx *ctx);
  *   "ntt_table_max_bytes" largest full inter-pass twiddle table (8 bytes per output element of one
  *                     column) a two-pass transform plan may keep (default 1 GiB; 0 = never, the factor
  *                     is then advanced by a running product); read when a plan is first built;
- *   "use_window"      1 (default once attached) / 0: route the multi-GPU exchanges through the peer
- *                     window or through the aero_all_gather_cosets hook.  The first proof of a shape
- *                     on a context must take the hook: it still calls cudaMalloc, which can block on
- *                     a peer GPU whose stream sits in the window's flag barrier (the caveat NCCL
- *                     documents for its own kernels); later proofs reuse the cached blocks. */
+ *   "own_stream"      1: create a non-blocking stream for this context and launch on it (contexts that
+ *                     share a device or a process must not meet on the legacy default stream);
+ *   "force_host_sync" 1: sharded proofs keep host-synchronised barriers even for warm shapes (tests). */
 aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value);
 /* Used by the host driver layered above this ABI to report its own failures through aero_last_error. */
 void aero_ctx_set_error(aero_ctx *ctx, const char *msg);
@@ -108,39 +107,48 @@ aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint
 aero_status aero_segment_commit_device(aero_ctx *ctx, const uint64_t *d_cols, size_t col_stride, uint32_t n_cols,
                                        uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
                                        uint8_t root[32]);
-/* ---- multi-GPU: LDE-coset sharding (one context = one rank) -----------------
- * After aero_ctx_set_shard(rank, world) (world a power of two dividing the blowup), every segment
- * commit interpolates all columns but extends and row-hashes only LDE cosets
- * [rank*B/world, (rank+1)*B/world) -- complete rows k with k mod B in that range -- and leaves the
- * tree unfinished (root = zeros).  The caller exchanges the 32-byte leaf digests (natural order,
- * viewed as [N/B][B][32]: a rank owns [:, coset_begin:coset_begin+coset_count, :]) between ranks,
- * e.g. with an NCCL all-gather, and calls aero_segment_finish_tree on every rank.  aero_deep_compose
- * likewise fills only the own cosets of the coset-major DEEP evaluations ([B][n] u64: a rank owns
- * [coset_begin:coset_begin+coset_count, :]); exchange, then aero_fri_mark_complete.
- * aero_segment_open returns zeros for rows owned by other ranks (sum the ranks' results). */
+/* ---- multi-GPU: ONE proof over G GPUs (one context = one rank) -----------------
+ * After aero_ctx_set_shard(rank, G) (G a power of two dividing the blowup, G <= 8) the same call
+ * sequence on every rank produces one proof, byte-identical to the single-GPU one:
+ *   - trace columns are interpolated by the rank that owns them (columns [rank*w/G, (rank+1)*w/G)),
+ *     which is also the only rank that uploads them, and the coefficients are stored into every peer's
+ *     copy of the coefficient matrix as they are produced;
+ *   - every rank extends and row-hashes LDE cosets [rank*B/G, (rank+1)*B/G) of ALL columns -- complete
+ *     rows k with k mod B in that range, so no LDE value ever moves;
+ *   - the row-hash kernel stores each leaf digest straight into the rank that owns the leaf's block
+ *     [r*N/G, (r+1)*N/G); each rank builds the subtree over its block (the reference's concurrent
+ *     build_merkle_nodes splits the tree the same way, crypto/src/merkle/concurrent.rs:21-70), the G
+ *     sub-roots are exchanged and every rank finishes the top log2(G) levels;
+ *   - aero_deep_compose extends the DEEP polynomial over the own cosets and stores them into the peers;
+ *     composition, OOD, DEEP coefficients and the one-column FRI are replicated so every rank's
+ *     Fiat-Shamir coin stays in lock-step without a broadcast;
+ *   - openings: the rank that stores an opened row / tree node writes it into every rank's result buffer.
+ * All of this goes through the EXCHANGE WINDOW: one device allocation per rank, the same size
+ * everywhere, mapped by every peer -- over CUDA IPC between processes (aero_ctx_window_attach; the
+ * caller all-gathers the 64-byte handles with any transport), directly inside one process
+ * (aero_ctx_window_attach_local; include/aero_prover.h wraps this as aero_group_*).  Buffers other ranks
+ * write into are bump-allocated inside the window, at the same offset on every rank.  Size: about
+ * 8*n*(all trace columns) + 3 * 32*N/G + 8*N + 4 MiB for a proof (n rows, N = B*n).
+ * Barriers between the ranks are stream-ordered flag barriers on the device (a rank that never arrives
+ * is reported as AERO_ERR_STATE after ~4 s instead of hanging).  The first proof of a shape on a context
+ * still calls cudaMalloc, which can block on a peer that already spins in such a barrier (the caveat
+ * NCCL documents for its own kernels); it therefore synchronises on the host instead, through the
+ * rendezvous the caller provides with aero_ctx_set_host_barrier.  aero_ctx_shard_begin / _end bracket a
+ * proof: begin(shape_key) selects the barrier kind (device-side once `shape_key` has completed before on
+ * this context), end(ok) records the outcome.  Outside such a bracket barriers are host-synchronised. */
+typedef aero_status (*aero_host_barrier_fn)(void *user);
 aero_status aero_ctx_set_shard(aero_ctx *ctx, int rank, int world);
-/* Exchange window: the NVLink path of the two exchanges.  Every rank creates a
- * window of the same size (device memory, exported as a 64-byte CUDA IPC handle), the caller
- * all-gathers the handles (any transport) and attaches them in rank order.  From then on every
- * sharded segment gets a coset-major staging array of leaf digests ([B][n] x 32 bytes) inside the
- * window, at the same offset on every rank, and so do the DEEP evaluations; the row-hash kernel stores
- * each digest into its own leaf slot and into the staging arrays of all peers as it is produced
- * (aero_fri_push_evaluations does the same for the DEEP evaluations), and aero_window_barrier -- a
- * stream-ordered flag barrier over the same peer mapping -- replaces the all-gather: call it before
- * aero_segment_finish_tree, which moves the received digests to their natural leaf slots and builds
- * the tree.  Size: 32*N bytes per committed segment of the proof + 8*N for the DEEP evaluations +
- * 4 KiB (N = LDE domain size); larger windows are fine. */
+/* ipc_handle_out may be NULL when the window is only attached inside this process. */
 aero_status aero_ctx_window_create(aero_ctx *ctx, size_t bytes, uint8_t ipc_handle_out[64]);
 aero_status aero_ctx_window_attach(aero_ctx *ctx, int n_ranks, const uint8_t *ipc_handles /* n_ranks x 64 */);
+/* Same-process variant: ranks[r] is the context of rank r (ranks[own rank] == ctx); peer access between
+ * the devices is enabled as needed.  Contexts may share a device (used by the single-GPU tests). */
+aero_status aero_ctx_window_attach_local(aero_ctx *ctx, int n_ranks, aero_ctx *const *ranks);
 int aero_ctx_window_ranks(aero_ctx *ctx);
+aero_status aero_ctx_set_host_barrier(aero_ctx *ctx, aero_host_barrier_fn barrier, void *user);
+aero_status aero_ctx_shard_begin(aero_ctx *ctx, const char *shape_key);
+aero_status aero_ctx_shard_end(aero_ctx *ctx, int ok);
 aero_status aero_window_barrier(aero_ctx *ctx);
-aero_status aero_fri_push_evaluations(aero_fri *fri);
-aero_status aero_segment_leaves_device(aero_segment *seg, void **d_leaves, uint64_t *n_leaves, uint32_t *coset_begin,
-                                       uint32_t *coset_count);
-aero_status aero_segment_finish_tree(aero_segment *seg, uint8_t root[32]);
-aero_status aero_fri_evaluations_device(aero_fri *fri, void **d_evals, uint64_t *count, uint32_t *coset_begin,
-                                        uint32_t *coset_count);
-aero_status aero_fri_mark_complete(aero_fri *fri);
 void aero_segment_destroy(aero_segment *seg);
 aero_status aero_segment_info(aero_segment *seg, uint32_t *n_cols, uint64_t *n_rows, uint32_t *blowup);
 /* Natural-order LDE columns (lde[c][k] = poly_c(7 * g_N^k), matrix.rs:189-201) for the host-side
@@ -233,6 +241,10 @@ aero_status aero_commit_rows_device(aero_ctx *ctx, const uint64_t *d_m, size_t c
  * a * 2^(12(k+1)) for k = 0..6 from the unreduced a (the power-of-two twiddles inside the NTT
  * rounds), and out[11n..12n) = a+b through the canonical-sum adder; out holds 12n words. */
 aero_status aero_test_field_ops(aero_ctx *ctx, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
+/* Roofline denominator of this path, measured on the spot: issue rate of the ALU pipe
+ * (LOP3/SHF/PRMT/IADD3, what BLAKE2s and the butterflies' carry chains saturate) in lane-operations
+ * per second, from a ~1 ms stream of independent LOP3 at 8 warps per scheduler. */
+aero_status aero_measure_alu_peak(aero_ctx *ctx, double *lane_ops_per_s);
 /* Device scratch helpers so callers without a CUDA runtime binding can stage data. */
 aero_status aero_device_alloc(aero_ctx *ctx, size_t bytes, void **d_ptr);
 aero_status aero_device_free(aero_ctx *ctx, void *d_ptr);
@@ -243,11 +255,13 @@ aero_status aero_device_sync(aero_ctx *ctx);
  * context's copy stream, so that it lands while earlier phases compute: e.g. the auxiliary segment and
  * the constraint evaluations of Prover::prove travel under the main segment's NTTs.  defer != 0 queues
  * the copies behind the uploads of the next aero_segment_commit instead of ahead of them.
+ * own_columns_only != 0: a sharded context copies only the columns it will interpolate itself (the matrix
+ * must then be consumed by aero_segment_commit_device, which reads exactly those).
  * aero_upload_wait orders the context's stream after the copy and returns the device matrix (column c
  * at d_cols + c*n_rows) for the *_device entry points.  The host columns must stay valid until
  * aero_upload_free, which also releases the device block. */
 aero_status aero_upload_start(aero_ctx *ctx, const uint64_t *const *cols, uint32_t n_cols, uint64_t n_rows, int defer,
-                              aero_upload **out);
+                              int own_columns_only, aero_upload **out);
 aero_status aero_upload_wait(aero_upload *up, const uint64_t **d_cols);
 void aero_upload_free(aero_upload *up);
 

@@ -43,15 +43,6 @@ typedef aero_status (*aero_constraint_evaluator)(void *user, const uint64_t *con
                                                  uint64_t lde_size, const uint64_t *coeffs, uint32_t n_coeffs,
                                                  const uint64_t **eval_cols_out);
 
-/* Multi-GPU exchange hooks (NULL on a single GPU).  all_gather_cosets completes a device buffer that
- * every rank filled for its own LDE cosets: interleaved != 0 -> layout [outer][B][inner_bytes]
- * (leaf digests), else [B][outer][inner_bytes] (DEEP evaluations).  sum_rows adds the ranks'
- * disjoint host row matrices (aero_segment_open fills foreign rows with zeros). */
-typedef aero_status (*aero_all_gather_cosets)(void *user, void *d_buf, uint64_t outer, uint32_t n_cosets,
-                                              uint32_t inner_bytes, int interleaved, uint32_t coset_begin,
-                                              uint32_t coset_count);
-typedef aero_status (*aero_sum_rows)(void *user, uint64_t *host_rows, uint64_t count);
-
 typedef struct aero_prove_inputs {
     aero_proof_options options;
     uint64_t trace_len;
@@ -65,6 +56,11 @@ typedef struct aero_prove_inputs {
     const aero_divisor *divisors;
     uint32_t n_div;
     uint32_t n_constraint_coeffs;      /* field elements drawn for constraint composition */
+    /* Constraint evaluation domain = trace_len * ce_blowup (AirContext::ce_blowup_factor,
+     * air/src/air/context.rs:124-137; a power of two <= options.blowup_factor); 0 = the LDE domain, as
+     * for Miden.  ce_cols / the evaluator's columns hold that many evaluations each (over
+     * offset * <g_ce>), and the composition polynomial gets ce_blowup columns. */
+    uint32_t ce_blowup;
     aero_aux_builder aux_builder;
     aero_constraint_evaluator constraint_evaluator;
     void *user;
@@ -72,13 +68,29 @@ typedef struct aero_prove_inputs {
     size_t pub_inputs_len;
     const uint8_t *trace_meta;         /* TraceInfo meta bytes for the proof context (may be NULL) */
     uint16_t trace_meta_len;
-    aero_all_gather_cosets all_gather_cosets;
-    aero_sum_rows sum_rows;
 } aero_prove_inputs;
 
 /* Prover::prove: writes StarkProof::to_bytes (air/src/proof/mod.rs:122-132) into proof_out.
- * *len: in = capacity, out = bytes written / required (AERO_ERR_BUFFER). */
+ * *len: in = capacity, out = bytes written / required (AERO_ERR_BUFFER).  Options are checked like
+ * ProofOptions::new (air/src/options.rs:120-160) and rejected with AERO_ERR_INVALID.
+ * On a sharded context (aero_ctx_set_shard + exchange window) every rank calls this with the same inputs
+ * and gets the same bytes; the callbacks are not available there. */
 aero_status aero_prove(aero_ctx *ctx, const aero_prove_inputs *in, uint8_t *proof_out, size_t *len);
+
+/* ONE proof on several GPUs of this process: n_ranks contexts (one per entry of device_ids; the same
+ * device may appear more than once, which is how the single-GPU tests run the sharded path) joined by an
+ * exchange window of window_bytes each (size: include/aero_b200.h, multi-GPU section).  aero_group_prove
+ * runs aero_prove on every rank, one host thread per rank, and returns the common proof.  in: one
+ * aero_prove_inputs shared by all ranks (host inputs: every rank uploads only the columns it
+ * interpolates) or n_ranks entries (n_inputs == n_ranks: e.g. device-resident inputs per GPU).
+ * This is the reference's rayon "concurrent" feature across GPUs: Prover::prove stays one call. */
+typedef struct aero_group aero_group;
+aero_status aero_group_create(const int *device_ids, int n_ranks, size_t window_bytes, aero_group **out);
+void aero_group_destroy(aero_group *g);
+int aero_group_size(aero_group *g);
+aero_ctx *aero_group_ctx(aero_group *g, int rank);
+const char *aero_group_last_error(aero_group *g);
+aero_status aero_group_prove(aero_group *g, const aero_prove_inputs *in, int n_inputs, uint8_t *proof_out, size_t *len);
 
 /* Host Fiat-Shamir primitives, exported for tests (crypto/src/random/mod.rs:73-306,
  * crypto/src/hash/blake2s/mod.rs:33-77).  Elements canonical. */

@@ -1,0 +1,232 @@
+"""TEST INFRASTRUCTURE (oracle): a small AIR with REAL constraint evaluations, restated from the
+reference, so that the oracle's verifier can run the reference's out-of-domain consistency check --
+the first reference-derived constraint on ConstraintEvaluationTable::into_poly
+(winterfell/prover/src/constraints/evaluation_table.rs:166-190,330-419: divisor and exemption
+handling) and on CompositionPoly's column transposition (constraints/composition_poly.rs:111-128).
+Synthetic constraint columns (random data) can never fail that check's prover side silently: here a
+wrong divisor convention, a missing exemption or a swapped composition column makes `verify` fail.
+
+Restated, each with the file:line it follows (paths relative to winterfell/):
+  * the Fibonacci AIR of examples/src/fibonacci/fib2 (air.rs:15-71, prover.rs:22-40);
+  * AirContext (air/src/air/context.rs:87-193): ce_blowup_factor, composition degree;
+  * TransitionConstraints / TransitionConstraintGroup (air/src/air/transition/mod.rs:36-290,
+    degree.rs:102-131): grouping by evaluation degree, degree adjustment, merge_evaluations;
+  * BoundaryConstraints / BoundaryConstraintGroup / BoundaryConstraint (air/src/air/boundary/
+    mod.rs:44-190, constraint_group.rs:44-110, constraint.rs:46-113) for single-value assertions;
+  * ConstraintDivisor (air/src/air/divisor.rs:36-108);
+  * the prover's ConstraintEvaluator (prover/src/constraints/evaluator.rs:54-230, boundary.rs:59-100,
+    255-275, domain.rs:99-117): one column per divisor over the constraint evaluation domain;
+  * the verifier's evaluate_constraints (verifier/src/evaluator.rs:14-107) and the comparison in
+    verifier/src/lib.rs:248-290.
+Only what fib2 uses is covered: main segment only, single-value assertions, no periodic columns.
+Pure Python big-int arithmetic: small traces only."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+P = 0xFFFFFFFF00000001
+GENERATOR = 7
+TWO_ADIC_ROOT = 1753635133440165772
+
+
+def root_of_unity(k: int) -> int:
+    return pow(TWO_ADIC_ROOT, 1 << (32 - k), P)
+
+
+def inv(x: int) -> int:
+    return pow(x % P, P - 2, P)
+
+
+def log2(n: int) -> int:
+    assert n > 0 and n & (n - 1) == 0
+    return n.bit_length() - 1
+
+
+@dataclass
+class ConstraintDivisor:  # air/src/air/divisor.rs: (x^a - b) / prod (x - e)
+    a: int
+    b: int
+    exemptions: List[int] = field(default_factory=list)
+
+    def degree(self) -> int:  # divisor.rs:69-76
+        return self.a - len(self.exemptions)
+
+    def evaluate_at(self, x: int) -> int:  # divisor.rs:79-96
+        num = (pow(x, self.a, P) - self.b) % P
+        den = 1
+        for e in self.exemptions:
+            den = den * ((x - e) % P) % P
+        return num * inv(den) % P
+
+
+@dataclass
+class Assertion:  # single-value assertions only (air/src/air/assertions/mod.rs:79-96)
+    column: int
+    step: int
+    value: int
+
+
+class Fib2Air:
+    """examples/src/fibonacci/fib2/air.rs: two registers, two terms of the sequence per row."""
+
+    trace_width = 2
+    transition_degrees = [1, 1]  # TransitionConstraintDegree::new(1) twice (air.rs:27-30)
+    num_transition_exemptions = 1  # context.rs:159
+
+    def __init__(self, trace_length: int, result: int, blowup: int = 8):
+        self.n, self.result, self.blowup = trace_length, result, blowup
+        # context.rs:124-137 with degree.rs:113-131: max over constraints of
+        # max(next_power_of_two(base + cycles - 1), MIN_BLOWUP_FACTOR = 2)
+        self.ce_blowup = max(max(_next_pow2(d - 1), 2) for d in self.transition_degrees)
+        assert blowup >= self.ce_blowup
+        self.g = root_of_unity(log2(trace_length))
+
+    # context.rs:183-193
+    def ce_domain_size(self) -> int:
+        return self.n * self.ce_blowup
+
+    def composition_degree(self) -> int:
+        return self.ce_domain_size() - 1
+
+    def trace_poly_degree(self) -> int:
+        return self.n - 1
+
+    @staticmethod
+    def build_trace(n: int) -> np.ndarray:  # prover.rs:22-40
+        s0, s1 = 1, 1
+        cols = np.empty((2, n), np.uint64)
+        for i in range(n):
+            cols[0, i], cols[1, i] = s0, s1
+            s0 = (s0 + s1) % P
+            s1 = (s1 + s0) % P
+        return cols
+
+    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int]) -> List[int]:  # air.rs:41-58
+        return [(nxt[0] - (cur[0] + cur[1])) % P, (nxt[1] - (cur[1] + nxt[0])) % P]
+
+    def get_assertions(self) -> List[Assertion]:  # air.rs:60-70
+        return [Assertion(0, 0, 1), Assertion(1, 0, 1), Assertion(1, self.n - 1, self.result)]
+
+    def num_constraint_coefficients(self) -> int:
+        """Field elements drawn by get_constraint_composition_coefficients (air/src/air/mod.rs:511-533):
+        a pair per transition constraint, then a pair per assertion."""
+        return 2 * (len(self.transition_degrees) + len(self.get_assertions()))
+
+    # ---- constraint structure shared by prover and verifier ---------------------------------
+    def transition_divisor(self) -> ConstraintDivisor:  # divisor.rs:36-45
+        ex = [pow(self.g, s, P) for s in range(self.n - self.num_transition_exemptions, self.n)]
+        return ConstraintDivisor(self.n, 1, ex)
+
+    def transition_groups(self, coeffs: Sequence[Tuple[int, int]]):
+        """transition/mod.rs:305-343: constraints grouped by evaluation degree (BTreeMap order);
+        each group: (degree_adjustment, [(constraint index, (c0, c1))])."""
+        div_deg = self.transition_divisor().degree()
+        groups: Dict[int, Tuple[int, list]] = {}
+        for i, d in enumerate(self.transition_degrees):
+            ev_deg = d * (self.n - 1)  # degree.rs:102-108 without cycles
+            if ev_deg not in groups:
+                target = self.composition_degree() + div_deg  # transition/mod.rs:224-226
+                groups[ev_deg] = (target - ev_deg, [])
+            groups[ev_deg][1].append((i, coeffs[i]))
+        return [groups[k] for k in sorted(groups)]
+
+    def boundary_groups(self, coeffs: Sequence[Tuple[int, int]]):
+        """boundary/mod.rs:120-190: assertions sorted by (stride, first step, column) -- the BTreeSet
+        order of assertions/mod.rs:310-322 -- zipped with the coefficient pairs, grouped by
+        (stride, first step), groups sorted by degree adjustment (stable).  Each group:
+        (divisor, degree_adjustment, [(column, value, (c0, c1))])."""
+        assertions = sorted(self.get_assertions(), key=lambda a: (0, a.step, a.column))
+        groups: Dict[Tuple[int, int], Tuple[ConstraintDivisor, int, list]] = {}
+        for a, cc in zip(assertions, coeffs):
+            key = (0, a.step)
+            if key not in groups:
+                # divisor.rs:47-61 (num_steps = 1): x - g^step
+                div = ConstraintDivisor(1, pow(self.g, a.step, P) if a.step else 1, [])
+                adj = self.composition_degree() + div.degree() - self.trace_poly_degree()  # constraint_group.rs:28-30
+                groups[key] = (div, adj, [])
+            groups[key][2].append((a.column, a.value, cc))
+        out = [groups[k] for k in sorted(groups)]
+        out.sort(key=lambda gr: gr[1])
+        return out
+
+    def divisors(self) -> List[ConstraintDivisor]:
+        """Columns of the prover's evaluation table (evaluator.rs:66-67): transition first."""
+        pairs = [(0, 0)] * (self.num_constraint_coefficients() // 2)
+        nt = len(self.transition_degrees)
+        return [self.transition_divisor()] + [g[0] for g in self.boundary_groups(pairs[nt:])]
+
+    @staticmethod
+    def split_coefficients(flat: Sequence[int], n_transition: int):
+        pairs = [(int(flat[2 * i]), int(flat[2 * i + 1])) for i in range(len(flat) // 2)]
+        return pairs[:n_transition], pairs[n_transition:]
+
+    # ---- prover side: ConstraintEvaluator::evaluate -----------------------------------------
+    def evaluate_constraints_over_ce_domain(self, trace_lde: Sequence[Sequence[int]], coeffs: Sequence[int]) -> np.ndarray:
+        """trace_lde: natural-order LDE columns (N = blowup * n values each); coeffs: the drawn
+        composition coefficients, flat.  Returns (1 + boundary groups, ce_domain_size) merged
+        evaluations, one column per divisor (evaluator.rs:121-160, 207-224; boundary.rs:59-72)."""
+        t_cc, b_cc = self.split_coefficients(coeffs, len(self.transition_degrees))
+        tg, bg = self.transition_groups(t_cc), self.boundary_groups(b_cc)
+        ce = self.ce_domain_size()
+        N = self.blowup * self.n
+        lde_shift = log2(self.blowup // self.ce_blowup)
+        g_ce = root_of_unity(log2(ce))
+        out = np.zeros((1 + len(bg), ce), np.uint64)
+        x = GENERATOR  # domain.rs:99-101: ce_domain[step] * offset
+        for step in range(ce):
+            row = step << lde_shift
+            cur = [int(c[row]) for c in trace_lde]
+            nxt = [int(c[(row + self.blowup) % N]) for c in trace_lde]  # trace_lde.rs: next = + blowup, wrapping
+            t = self.evaluate_transition(cur, nxt)
+            acc = 0
+            for adj, members in tg:
+                xp = pow(x, adj, P)  # domain.rs:109-117: ce_domain[step*power mod ce] * offset^power = x^power
+                for idx, (c0, c1) in members:
+                    acc = (acc + (c0 + c1 * xp) * t[idx]) % P  # transition/mod.rs:272-283
+            out[0, step] = acc
+            for j, (_, adj, members) in enumerate(bg):
+                xp = pow(x, adj, P)
+                acc = 0
+                for col, value, (c0, c1) in members:
+                    acc = (acc + (c0 + c1 * xp) * ((cur[col] - value) % P)) % P  # boundary.rs:260-263
+                out[1 + j, step] = acc
+            x = x * g_ce % P
+        return out
+
+    # ---- verifier side: evaluate_constraints at the out-of-domain point ---------------------
+    def evaluate_constraints_at(self, coeffs: Sequence[int], ood_cur: Sequence[int], ood_next: Sequence[int], z: int) -> int:
+        """verifier/src/evaluator.rs:14-107."""
+        t_cc, b_cc = self.split_coefficients(coeffs, len(self.transition_degrees))
+        t = self.evaluate_transition(ood_cur, ood_next)
+        result = 0
+        for adj, members in self.transition_groups(t_cc):  # transition/mod.rs:165-185
+            xp = pow(z, adj, P)
+            for idx, (c0, c1) in members:
+                result = (result + (c0 + c1 * xp) * t[idx]) % P
+        result = result * inv(self.transition_divisor().evaluate_at(z)) % P
+        for div, adj, members in self.boundary_groups(b_cc):  # constraint_group.rs:82-108
+            xp = pow(z, adj, P)
+            num = 0
+            for col, value, (c0, c1) in members:
+                num = (num + ((ood_cur[col] - value) % P) * (c0 + c1 * xp)) % P
+            result = (result + num * inv(div.evaluate_at(z))) % P
+        return result
+
+
+def _next_pow2(x: int) -> int:
+    """usize::next_power_of_two: 0 and 1 map to 1."""
+    return 1 if x <= 1 else 1 << (x - 1).bit_length()
+
+
+def ood_consistency_check(air: Fib2Air, coeffs: Sequence[int], ood_cur, ood_next, ood_comp: Sequence[int], z: int) -> None:
+    """verifier/src/lib.rs:248-290: constraints evaluated over the OOD frame must equal
+    sum_i z^i * H_i(z^m) reduced from the composition-column evaluations the prover sent."""
+    lhs = air.evaluate_constraints_at(coeffs, ood_cur, ood_next, z)
+    rhs = 0
+    for i, v in enumerate(ood_comp):
+        rhs = (rhs + pow(z, i, P) * v) % P
+    if lhs != rhs:
+        raise AssertionError("InconsistentOodConstraintEvaluations")

@@ -545,7 +545,10 @@ class VerifyReport:
     roots: List[bytes] = field(default_factory=list)
 
 
-def verify(proof_bytes: bytes, pub_inputs_seed_bytes: bytes, num_comp_columns: Optional[int] = None) -> VerifyReport:
+def verify(proof_bytes: bytes, pub_inputs_seed_bytes: bytes, num_comp_columns: Optional[int] = None, air=None) -> VerifyReport:
+    """verifier/src/lib.rs:189-360.  With `air` (oracle/air.py) the out-of-domain consistency check of
+    lib.rs:248-290 runs too: constraints evaluated over the OOD frame == the reduced composition-column
+    evaluations; without it (synthetic constraint columns) that step is skipped."""
     pr = StarkProof.from_bytes(proof_bytes)
     ctx, opt = pr.context, pr.context.options
     n, N = ctx.trace_length, ctx.lde_domain_size
@@ -564,6 +567,8 @@ def verify(proof_bytes: bytes, pub_inputs_seed_bytes: bytes, num_comp_columns: O
     for c in trace_roots[1:]:
         [coin.draw() for _ in range(ctx.aux_rands)]
         coin.reseed(c)
+    # get_constraint_composition_coefficients (lib.rs:221-226, air/src/air/mod.rs:511-533)
+    constraint_coeffs = [coin.draw() for _ in range(air.num_constraint_coefficients())] if air is not None else []
     coin.reseed(constraint_root)
     z = coin.draw()
     rep.z = z
@@ -579,6 +584,10 @@ def verify(proof_bytes: bytes, pub_inputs_seed_bytes: bytes, num_comp_columns: O
     if num_comp_columns is not None:
         assert m == num_comp_columns
     coin.reseed(hash_elements(ood_comp))
+    if air is not None:
+        from . import air as _air
+        assert air.n == n and m == air.ce_blowup, "proof context does not match the AIR"
+        _air.ood_consistency_check(air, constraint_coeffs, ood_cur, ood_next, ood_comp, z)
 
     # DEEP coefficients: air/src/air/mod.rs:537-561
     cc_trace = [(coin.draw(), coin.draw(), coin.draw()) for _ in range(w)]
@@ -859,9 +868,13 @@ class ProveResult:
 def prove(main_trace: np.ndarray, aux_trace: Optional[np.ndarray], ce_cols: np.ndarray,
           divisors: Sequence[Divisor], pub_inputs_seed_bytes: bytes,
           options: ProofOptions = ProofOptions(), aux_rands: int = 16,
-          num_constraint_coeff_draws: int = 0) -> ProveResult:
+          num_constraint_coeff_draws: int = 0, constraint_evaluator=None) -> ProveResult:
     """Prover::generate_proof (prover/src/lib.rs:203-267) with AIR evaluation and aux-segment
-    construction replaced by caller-supplied data (they stay on the reference Rust path)."""
+    construction replaced by caller-supplied data (they stay on the reference Rust path).
+    constraint_evaluator(trace_lde columns, drawn coefficients) -> (n_div, ce_domain) matrix stands in
+    for ConstraintEvaluator::evaluate (lib.rs:350-382), e.g. oracle/air.py's Fib2Air; ce_cols is then
+    ignored.  The constraint evaluation domain is ce_cols.shape[1] (any multiple of the trace length up
+    to the LDE domain: ce_blowup <= blowup)."""
     w_main, n = main_trace.shape
     blowup = options.blowup_factor
     N = n * blowup
@@ -879,7 +892,10 @@ def prove(main_trace: np.ndarray, aux_trace: Optional[np.ndarray], ce_cols: np.n
         aux = build_trace_commitment(aux_trace, blowup)  # lib.rs:328
         commitments += aux.root
         coin.reseed(aux.root)
-    [coin.draw() for _ in range(num_constraint_coeff_draws)]  # lib.rs:369 (draws never move the seed)
+    cc_draws = [coin.draw() for _ in range(num_constraint_coeff_draws)]  # lib.rs:369 (draws never move the seed)
+    if constraint_evaluator is not None:
+        lde_cols = list(main.lde) + (list(aux.lde) if aux is not None else [])
+        ce_cols = np.ascontiguousarray(constraint_evaluator(lde_cols, cc_draws), np.uint64)
 
     comp_polys = constraints_into_poly(ce_cols, divisors, n)  # lib.rs:400
     assert comp_polys[-1, -1] != 0 or comp_polys.shape[0] == 1 or True

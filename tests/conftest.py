@@ -3,6 +3,12 @@ import sys
 
 import pytest
 
+# The sharded-proof tests run up to 8 ranks as contexts on ONE GPU, each with a compute and a copy
+# stream: with the default 8 hardware work queues two ranks' streams share a queue, and a copy queued
+# behind another rank's spinning barrier kernel never starts (a false dependency that cannot occur with
+# one rank per GPU).  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -1,0 +1,106 @@
+"""A real AIR end to end (the reference's Fibonacci example, winterfell/examples/src/fibonacci/fib2):
+constraint evaluations computed from the trace LDE through the constraint_evaluator callback of
+aero_prove, composition polynomial built by the GPU's into_poly, and the verifier's out-of-domain
+consistency check (winterfell/verifier/src/lib.rs:248-290) run over the proof.  That check is what
+constrains ConstraintEvaluationTable::into_poly's divisor / exemption handling and CompositionPoly's
+column transposition (evaluation_table.rs:166-190,330-419; composition_poly.rs:111-128) from the
+reference's side: synthetic constraint columns cannot.  The CPU half (oracle + AIR restatement) runs
+without a GPU; the GPU half requires byte-identical proofs."""
+import numpy as np
+import pytest
+
+from oracle import stark_oracle as so
+from oracle.air import Fib2Air, P
+
+
+def _setup(logn):
+    n = 1 << logn
+    trace = Fib2Air.build_trace(n)
+    air = Fib2Air(n, int(trace[1, n - 1]))
+    divs = [so.Divisor(d.a, d.b, d.exemptions) for d in air.divisors()]
+    pub = int(trace[1, n - 1]).to_bytes(8, "little")  # BaseElement::to_bytes of the public input
+    return n, trace, air, divs, pub
+
+
+def _oracle_prove(trace, air, divs, pub, **kw):
+    ce0 = np.zeros((len(divs), air.ce_domain_size()), np.uint64)
+    return so.prove(trace, None, ce0, divs, pub, num_constraint_coeff_draws=air.num_constraint_coefficients(),
+                    constraint_evaluator=lambda lde, cc: air.evaluate_constraints_over_ce_domain(lde, cc), **kw)
+
+
+def test_fib2_trace_and_structure():
+    """The trace builder, the constraint groups and degree adjustments of the restated AIR."""
+    n, trace, air, divs, _ = _setup(4)
+    assert [int(v) for v in trace[0, :4]] == [1, 2, 5, 13] and [int(v) for v in trace[1, :4]] == [1, 3, 8, 21]
+    assert air.ce_blowup == 2 and air.composition_degree() == 2 * n - 1
+    assert air.num_constraint_coefficients() == 10
+    (adj_t, members), = air.transition_groups([(1, 2), (3, 4)])
+    assert adj_t == (2 * n - 1) + (n - 1) - (n - 1) and [m[0] for m in members] == [0, 1]
+    groups = air.boundary_groups([(0, 0)] * 3)
+    assert [(g[0].a, g[0].b) for g in groups] == [(1, 1), (1, pow(air.g, n - 1, P))]
+    assert [len(g[2]) for g in groups] == [2, 1] and all(g[1] == n + 1 for g in groups)
+    # every transition constraint vanishes on the trace, every assertion holds
+    for i in range(n - 1):
+        assert air.evaluate_transition([int(trace[0, i]), int(trace[1, i])], [int(trace[0, i + 1]), int(trace[1, i + 1])]) == [0, 0]
+
+
+@pytest.mark.parametrize("logn", [3, 6, 8])
+def test_fib2_oracle_proof_passes_the_ood_consistency_check(logn):
+    n, trace, air, divs, pub = _setup(logn)
+    ref = _oracle_prove(trace, air, divs, pub)
+    rep = so.verify(ref.proof_bytes, pub, air.ce_blowup, air=air)
+    assert len(rep.positions) == 27 and rep.z == ref.z
+    # CompositionPoly::new's degree check (composition_poly.rs:36-41): the top coefficient is non-zero
+    assert ref.comp.polys.shape == (air.ce_blowup, n)
+
+
+def test_fib2_check_rejects_perturbed_into_poly():
+    """The check has teeth: a dropped exemption, a wrong divisor constant, a wrong trace value and
+    swapped composition columns are all rejected (and nothing else in the verifier model would notice
+    the first two or the last)."""
+    n, trace, air, divs, pub = _setup(6)
+
+    def rejected(proof):
+        with pytest.raises(AssertionError, match="InconsistentOodConstraintEvaluations"):
+            so.verify(proof, pub, air.ce_blowup, air=air)
+
+    rejected(_oracle_prove(trace, air, [so.Divisor(divs[0].a, divs[0].b, []), divs[1], divs[2]], pub).proof_bytes)
+    rejected(_oracle_prove(trace, air, [divs[0], divs[1], so.Divisor(1, pow(air.g, n - 2, P), [])], pub).proof_bytes)
+    bad = trace.copy()
+    bad[0, 5] = np.uint64((int(bad[0, 5]) + 1) % P)
+    rejected(_oracle_prove(bad, air, divs, pub).proof_bytes)
+    # composition columns swapped after into_poly (what a wrong transposition would produce)
+    orig = so.constraints_into_poly
+    try:
+        so.constraints_into_poly = lambda *a, **k: np.ascontiguousarray(orig(*a, **k)[::-1])
+        swapped = _oracle_prove(trace, air, divs, pub).proof_bytes
+    finally:
+        so.constraints_into_poly = orig
+    rejected(swapped)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("form", ["canonical", "montgomery"])
+@pytest.mark.parametrize("logn", [3, 6, 10])
+def test_fib2_gpu_proof_is_byte_identical_and_verifies(ctx, ctx_mont, logn, form):
+    """aero_prove with the evaluator callback: same bytes as the oracle prover, accepted by the verifier
+    model including the OOD consistency check."""
+    from aero_b200 import make_divisor
+
+    n, trace, air, divs, pub = _setup(logn)
+    ref = _oracle_prove(trace, air, divs, pub)
+    mont = form == "montgomery"
+    c = ctx_mont if mont else ctx
+    to_abi = so.canon_to_mont if mont else (lambda a: a)
+    from_abi = so.mont_to_canon if mont else (lambda a: a)
+    gdivs = [make_divisor(d.a, int(to_abi(np.array([d.b], np.uint64))[0]),
+                          [int(v) for v in to_abi(np.array(d.exemptions, np.uint64))]) for d in divs]
+
+    def evaluator(lde_cols, coeffs):
+        lde = [from_abi(col.copy()) for col in lde_cols]
+        return to_abi(air.evaluate_constraints_over_ce_domain(lde, [int(v) for v in from_abi(coeffs)]))
+
+    got = c.prove(to_abi(trace), None, None, gdivs, pub, n_constraint_coeffs=air.num_constraint_coefficients(),
+                  constraint_evaluator=evaluator, ce_blowup=air.ce_blowup)
+    assert got == ref.proof_bytes
+    so.verify(got, pub, air.ce_blowup, air=air)

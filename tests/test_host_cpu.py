@@ -93,17 +93,21 @@ def test_host_coin_known_answers_and_oracle_agreement():
 
 
 def test_bench_reference_arm_runs_on_cpu():
-    """bench.py --impl reference: JSON line with the contract keys, from the oracle port."""
+    """bench.py --impl reference: JSON line with the contract keys, from the oracle port, on the workload
+    the line names (here shrunk with --log-rows), with the steps / warm-up that actually ran and all host
+    threads even under torchrun's OMP_NUM_THREADS=1."""
     import json
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--ref-log-rows", "10"], capture_output=True, text=True, check=True)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--log-rows", "11"], capture_output=True, text=True, check=True, env=env)
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "trace_rows_per_s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
-    # the arm reports on the aero arm's workload (2^20 rows), timed on a bounded sample of it
-    assert line["config"]["log_rows"] == 20 and line["config"]["reference_sample_log_rows"] == 10
+    assert line["config"]["log_rows"] == 11 and "2^11 rows" in line["config"]["workload"]
+    assert line["steps"] == 2 and line["warmup"] == 1
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
     assert line["e2e"]["value"] == line["value"] == line["cpu_baseline"]["value"]
 
 

@@ -1,10 +1,10 @@
-"""Debug aid (torchrun, 2+ GPUs): a small coset-sharded proof over the IPC exchange window, compared
-with the single-GPU proof of the same inputs."""
+"""Debug aid / two-GPU test body (torchrun, 2+ GPUs): a small proof sharded over the ranks through the
+IPC exchange window, compared with the single-GPU proof of the same inputs."""
 import os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import numpy as np, torch, torch.distributed as dist
 import aero_b200
-from aero_b200.sharded import ShardExchange
+from aero_b200.sharded import ShardExchange, window_bytes
 from bench import splitmix_matrix, bench_divisors, PUB
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
@@ -14,8 +14,8 @@ n = 1 << logn; N = 8 * n
 ctx = aero_b200.Context(lr); ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 main, aux, ce = splitmix_matrix(12, n, 1), splitmix_matrix(3, n, 2), splitmix_matrix(2, N, 3)
 divs = bench_divisors(n)
-ex = ShardExchange(window_bytes=(3 * 64 + 8) * N + (1 << 20))
 single = ctx.prove(main, aux, ce, divs, PUB)
+ex = ShardExchange(window_bytes(logn, 15, world))
 for it in range(3):
     dist.barrier(); torch.cuda.synchronize()
     t = time.perf_counter()
