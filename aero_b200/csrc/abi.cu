@@ -103,6 +103,12 @@ struct aero_ctx {
     // staging pair of the opening phase (GatherBatch): pinned host + device, grown on demand
     uint8_t *h_stage = nullptr, *d_stage = nullptr;
     size_t stage_bytes = 0;
+    // Pinned ring for the small host<->device transfers of a proof (roots, coefficient vectors, OOD point
+    // tables, flags).  An async copy from or to PAGEABLE memory makes the calling thread wait inside the
+    // driver until the stream gets there -- behind a rank barrier that wait can starve the very peers
+    // the barrier is waiting for when several ranks share a process; pinned copies just queue.
+    uint8_t *h_ring = nullptr;
+    size_t ring_bytes = 0, ring_off = 0;
 };
 
 #define CTX_FAIL(ctx, code, ...)                         \
@@ -253,6 +259,42 @@ struct FriDeleter {
 };
 using FriGuard = std::unique_ptr<aero_fri, FriDeleter>;
 
+// `bytes` of pinned scratch, valid until RING_BYTES more have been taken (every proof synchronises its
+// stream many times per lap)
+constexpr size_t RING_BYTES = (size_t)8 << 20;
+static aero_status ring_take(aero_ctx *ctx, size_t bytes, void **out) {
+    bytes = (bytes + 63) & ~(size_t)63;
+    if (!ctx->h_ring || bytes > ctx->ring_bytes) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+        ctx->h_ring = nullptr;
+        ctx->ring_bytes = std::max(RING_BYTES, 2 * bytes);
+        CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_ring, ctx->ring_bytes));
+        ctx->ring_off = 0;
+    }
+    if (ctx->ring_off + bytes > ctx->ring_bytes) ctx->ring_off = 0;
+    *out = ctx->h_ring + ctx->ring_off;
+    ctx->ring_off += bytes;
+    return AERO_OK;
+}
+// device -> caller memory through the ring: queue, synchronise, copy out
+static aero_status download_small(aero_ctx *ctx, void *dst, const void *d_src, size_t bytes) {
+    void *h = nullptr;
+    TRY(ring_take(ctx, bytes, &h));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(dst, h, bytes);
+    return AERO_OK;
+}
+// caller memory -> device through the ring (the source may be reused as soon as this returns)
+static aero_status upload_small(aero_ctx *ctx, void *d_dst, const void *src, size_t bytes) {
+    void *h = nullptr;
+    TRY(ring_take(ctx, bytes, &h));
+    memcpy(h, src, bytes);
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_dst, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return AERO_OK;
+}
+
 // Pinned host / device staging pair for small result downloads (OOD frame, openings): results land
 // in pinned memory so that several downloads can be queued before the single synchronisation.
 static aero_status stage_reserve(aero_ctx *ctx, size_t total) {
@@ -325,8 +367,7 @@ aero_status DevBlocks::alloc_shared(void **p, size_t bytes) {
 static aero_status window_check(aero_ctx *ctx) {
     if (!ctx_sharded(ctx) || ctx->win_host_sync) return AERO_OK;
     unsigned int t = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&t, ctx->win + 2048, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    TRY(download_small(ctx, &t, ctx->win + 2048, 4));
     if (t) {
         cudaMemsetAsync(ctx->win + 2048, 0, 4, ctx->stream);
         CTX_FAIL(ctx, AERO_ERR_STATE, "exchange barrier timed out %u time(s): a peer rank did not arrive", t);
@@ -581,10 +622,7 @@ static aero_status segment_finish_tree(aero_segment *seg, uint8_t root[32]) {
     TRY(window_barrier(ctx));
     merkle_top(seg->top, G, ctx->stream);
     CUDA_TRY(ctx, cudaGetLastError());
-    if (root) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(root, seg->top + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    if (root) TRY(download_small(ctx, root, seg->top + 8, 32));
     return window_check(ctx);
 }
 
@@ -893,7 +931,7 @@ struct aero_fri {
 // synchronisation (a proof used to pay 17 host round trips of 20-100 us here; profiles/r01_trace_gaps_v5.txt).
 // -------------------------------------------------------------------------------------------------
 struct GatherBatch {
-    enum Kind { DIGESTS, TREE_DIGESTS, SEG_ROWS, FRI_ROWS, COPY };
+    enum Kind { DIGESTS, TREE_DIGESTS, SEG_ROWS, FRI_ROWS, COPY, COPY_NATURAL };
     struct Job {
         Kind kind;
         const void *src;
@@ -934,6 +972,10 @@ struct GatherBatch {
         return push(FRI_ROWS, L.evals, nullptr, L.M / 8, L.log_cosets, pos.data(), pos.size(), pos.size() * 64);
     }
     size_t copy(const void *d_src, size_t bytes) { return push(COPY, d_src, nullptr, 0, 0, nullptr, 0, bytes); }
+    // `count` evaluations stored coset-major (2^log_cosets cosets), delivered in natural order
+    size_t copy_natural(const uint64_t *d_src, uint32_t count, int log_cosets) {
+        return push(COPY_NATURAL, d_src, nullptr, count, log_cosets, nullptr, 0, (size_t)count * 8);
+    }
     aero_status run();
 };
 
@@ -974,6 +1016,9 @@ aero_status GatherBatch::run() {
             gather_fri_rows((const uint64_t *)j.src, j.rows, j.log_cosets, d_idx, j.count, (uint64_t *)d_out, ctx->stream);
             break;
         case COPY: CUDA_TRY(ctx, cudaMemcpyAsync(d_out, j.src, j.out_bytes, cudaMemcpyDeviceToDevice, ctx->stream)); break;
+        case COPY_NATURAL:
+            lde_to_natural((const uint64_t *)j.src, (uint64_t *)d_out, ilog2(j.rows) - j.log_cosets, j.log_cosets, 0, ctx->stream);
+            break;
         }
     }
     CUDA_TRY(ctx, cudaGetLastError());
@@ -1053,7 +1098,6 @@ static aero_status fri_open_plan(aero_fri *fri, const uint64_t *positions, uint3
     for (uint64_t p : pos)
         if (p >= fri->layers[0].M) CTX_FAIL(ctx, AERO_ERR_INVALID, "query position out of range");
     const FriLayerDev &R = fri->layers.back();
-    if (R.log_cosets) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "remainder layer cannot be the DEEP layer");
     if ((size_t)R.M * 8 > 0xFFFF) CTX_FAIL(ctx, AERO_ERR_INVALID, "remainder too large for the wire format");
     o.fri = fri;
     const size_t nl = fri->layers.size() - 1;
@@ -1072,7 +1116,8 @@ static aero_status fri_open_plan(aero_fri *fri, const uint64_t *positions, uint3
     }
     // remainder = last committed layer in natural order (prover/mod.rs:258-268 un-transposes the
     // stored transposed copy; ours is stored natural already)
-    o.rem_off = gb.copy(R.evals, (size_t)R.M * 8);
+    // (with no FRI layer at all -- LDE domain <= max remainder size -- it is the coset-major DEEP layer)
+    o.rem_off = R.log_cosets ? gb.copy_natural(R.evals, R.M, R.log_cosets) : gb.copy(R.evals, (size_t)R.M * 8);
     return AERO_OK;
 }
 static aero_status fri_open_finish(const FriOpening &o, const GatherBatch &gb, uint8_t *out_bytes, size_t *len) {
@@ -1161,6 +1206,7 @@ void aero_ctx_destroy(aero_ctx *ctx) {
     for (void *p : ctx->owned) cudaFree(p);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1724,9 +1770,9 @@ aero_status aero_commit_rows_device(aero_ctx *ctx, const uint64_t *d_m, size_t c
         PhaseTimer t(ctx, "merkle");
         merkle_build(full, n_rows, ctx->stream);
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(root, full + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    aero_status st = download_small(ctx, root, full + 8, 32);
     dev_free(ctx, full);
+    if (st != AERO_OK) return st;
     CUDA_TRY(ctx, cudaGetLastError());
     return AERO_OK;
 }
@@ -1948,8 +1994,7 @@ static aero_status ood_enqueue(aero_ctx *ctx, aero_segment *seg, const std::vect
     TRY(dev_alloc(ctx, (void **)&job.d_tab, tab.size() * 8));
     TRY(dev_alloc(ctx, (void **)&job.d_out, (size_t)seg->ncols * np * 8));
     TRY(dev_alloc(ctx, (void **)&job.d_scr, ood_scratch_elems(seg->ncols, logn, np) * 8));
-    // pageable source: the runtime stages it before returning, so `tab` may go out of scope
-    CUDA_TRY(ctx, cudaMemcpyAsync(job.d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(upload_small(ctx, job.d_tab, tab.data(), tab.size() * 8));
     ood_eval(seg->polys, n, seg->ncols, logn, job.d_tab, np, job.d_out, job.d_scr, ctx->stream);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage + host_off, job.d_out, (size_t)seg->ncols * np * 8, cudaMemcpyDeviceToHost,
                                   ctx->stream));
@@ -2063,8 +2108,8 @@ aero_status aero_deep_compose(aero_ctx *ctx, aero_segment *const *trace_segs, ui
     TRY(tmp.alloc((void **)&hh, n * 8));
     TRY(tmp.alloc((void **)&coeffs, n * 8));
     TRY(tmp.alloc((void **)&carry, (6 * (n / 256 + 1)) * 8));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_cc, h_cc.data(), h_cc.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_consts, h_consts, 24, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(upload_small(ctx, d_cc, h_cc.data(), h_cc.size() * 8));
+    TRY(upload_small(ctx, d_consts, h_consts, 24));
     {
         PhaseTimer t(ctx, "deep_compose");
         DeepSegs segs;
@@ -2218,8 +2263,7 @@ aero_status aero_fri_commit_layer(aero_fri *fri, uint8_t root[32]) {
     aero_ctx *ctx = fri->ctx;
     enter(ctx);
     TRY(fri_commit_enqueue(fri));
-    CUDA_TRY(ctx, cudaMemcpyAsync(root, fri->layers.back().full + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    TRY(download_small(ctx, root, fri->layers.back().full + 8, 32));
     CUDA_TRY(ctx, cudaGetLastError());
     return AERO_OK;
 }
@@ -2297,15 +2341,14 @@ aero_status aero_pow_min_nonce(aero_ctx *ctx, const uint8_t seed[32], uint32_t g
     unsigned long long *d_best = nullptr;
     TRY(blk.alloc((void **)&d_seed, 32));
     TRY(blk.alloc((void **)&d_best, 8));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_seed, seed, 32, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(upload_small(ctx, d_seed, seed, 32));
     CUDA_TRY(ctx, cudaMemsetAsync(d_best, 0xFF, 8, ctx->stream));
     const uint32_t batch = 1u << 18;
     uint64_t base = 1;
     unsigned long long best = ~0ULL;
     for (;;) {
         pow_search(d_seed, base, batch, grinding_bits, d_best, ctx->stream);
-        CUDA_TRY(ctx, cudaMemcpyAsync(&best, d_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        TRY(download_small(ctx, &best, d_best, 8));
         if (best != ~0ULL) break;
         base += batch;
     }

@@ -31,13 +31,19 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // 46-51 % of the shared wavefronts of a pass were conflicts); with it they tile the banks exactly.  In
 // every round the rows of one butterfly group stay an arithmetic progression, so the padding costs no
 // instruction there.
+// Measured: 8-wide tiles (2^10-point passes) do not gain from it (LDE of 72 columns x 2^20: 9.99 ms without,
+// 10.2 ms with -- those passes are bound by ALU issue and two of the four wavefronts were already hidden),
+// so they keep the plain layout; the 4-wide tiles of 2^11 / 2^12-point passes (traces of 2^22 rows and
+// more), where every first-round access was an 8-way conflict, and single-pass transforms use it.
+template <int T>
+__host__ __device__ constexpr int tile_pad() { return T == 8 ? 0 : T; }
 template <int T, int RS>
 __host__ __device__ __forceinline__ int tile_off(int row, int r1) {
-    return row * RS + T * (row >> r1);
+    return row * RS + tile_pad<T>() * (row >> r1);
 }
 template <int T, int RS>
 __host__ __device__ __forceinline__ int tile_words(int logM, int r1) {
-    return (RS << logM) + T * ((1 << logM) >> r1);
+    return (RS << logM) + tile_pad<T>() * ((1 << logM) >> r1);
 }
 
 // Fetches an M x T tile (M = 2^logM rows of T consecutive words, row j at g + (j << gsh_row)) into
@@ -103,13 +109,14 @@ __host__ __device__ constexpr bool dft_need_canon(int R, int q, int e) {
 // PLAIN0: first round (s0 == 0) of a transform without coset shift: all general twiddles are 1.
 // IN_CANON: the tile holds canonical values already (pass 2 reads what pass 1 stored with
 // mul_canon), so a PLAIN0 round has nothing to canonicalise on the way in.
-template <int R, int T, int RS, bool PLAIN0, bool INV, bool IN_CANON = false>
+template <int R, int T, int RS, bool PLAIN0, bool INV, bool IN_CANON = false, bool FIRST = PLAIN0>
 __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s0, int logM, int r1) {
-    if (PLAIN0) s0 = 0;
+    if (FIRST) s0 = 0;
     const int ngroups = (1 << logM) >> R;
     const int items = ngroups * T;
-    // rows base + (e << s0) of a group: words astep apart (s0 is 0 or >= r1, see tile_off)
-    const int astep = (RS << s0) + (s0 >= r1 ? (T << (s0 - r1)) : 0);
+    // rows base + (e << s0) of a group: words astep apart.  First round (s0 = 0, R = r1): the group is
+    // one padding group, RS apart -- compile-time offsets; later rounds have s0 >= r1 (see tile_off).
+    const int astep = FIRST ? RS : (RS << s0) + (tile_pad<T>() << (s0 - r1));
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
         const int t = it % T, g = it / T;
         const int low = g & ((1 << s0) - 1);
@@ -157,19 +164,19 @@ __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s
     }
 }
 
-template <int T, int RS, bool PLAIN0, bool INV, int RMAX, bool IN_CANON = false>
+template <int T, int RS, bool PLAIN0, bool INV, int RMAX, bool IN_CANON = false, bool FIRST = PLAIN0>
 __device__ __forceinline__ void dit_round_dispatch(int R, uint64_t *a, const uint64_t *tw, int s0, int logM, int r1) {
     if constexpr (RMAX >= 5) {
         if (R == 5) {
-            dit_round<5, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM, r1);
+            dit_round<5, T, RS, PLAIN0, INV, IN_CANON, FIRST>(a, tw, s0, logM, r1);
             return;
         }
     }
     switch (R) {
-    case 4: dit_round<4, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM, r1); break;
-    case 3: dit_round<3, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM, r1); break;
-    case 2: dit_round<2, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM, r1); break;
-    default: dit_round<1, T, RS, PLAIN0, INV, IN_CANON>(a, tw, s0, logM, r1); break;
+    case 4: dit_round<4, T, RS, PLAIN0, INV, IN_CANON, FIRST>(a, tw, s0, logM, r1); break;
+    case 3: dit_round<3, T, RS, PLAIN0, INV, IN_CANON, FIRST>(a, tw, s0, logM, r1); break;
+    case 2: dit_round<2, T, RS, PLAIN0, INV, IN_CANON, FIRST>(a, tw, s0, logM, r1); break;
+    default: dit_round<1, T, RS, PLAIN0, INV, IN_CANON, FIRST>(a, tw, s0, logM, r1); break;
     }
 }
 
@@ -179,7 +186,7 @@ __device__ __forceinline__ void dit_tile(uint64_t *a, const uint64_t *tw, int lo
     const NttRounds rounds(logM);
     const int r1 = rounds.log(0);
     // first round: s0 == 0 is a compile-time fact, which lets PLAIN transforms skip the unit twiddles
-    dit_round_dispatch<T, RS, PLAIN, INV, RMAX, IN_CANON>(r1, a, tw, 0, logM, r1);
+    dit_round_dispatch<T, RS, PLAIN, INV, RMAX, IN_CANON, true>(r1, a, tw, 0, logM, r1);
     __syncthreads();
     int s0 = r1;
     for (int i = 1; i < rounds.count; i++) {
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(MAXT) dft_pass1_kernel(const uint64_t *__restr
         uint64_t *op = o + ((size_t)c << log2) * T + (size_t)j2 * T + ii;
         if ((step_i1 & ((1u << r1) - 1)) == 0) {  // this thread's rows are whole padding groups apart
             const uint64_t *ap = a + tile_off<T, RS>((int)i1, r1) + t;
-            const int astride = step_i1 * RS + T * (step_i1 >> r1);
+            const int astride = step_i1 * RS + tile_pad<T>() * (step_i1 >> r1);
             for (; c + (U - 1) * cstep < nchunks; c += U * cstep) {
                 uint64_t f[U];
 #pragma unroll
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(MAXT) dft_pass2_kernel(const uint64_t *__restr
         return;
     }
     const uint64_t *ap = a + tile_off<T, RS>(j0, r1) + t;
-    const int astep = J * RS + T * (J >> r1);
+    const int astep = J * RS + tile_pad<T>() * (J >> r1);
     if (deint == 0) {
         uint64_t *op = o + i1 + ((size_t)j0 << log1);
         const size_t ostep = (size_t)J << log1;

@@ -17,11 +17,26 @@ pytestmark = pytest.mark.gpu
 P = 0xFFFFFFFF00000001
 
 
+_PINNED = []
+
+
+def _pin(a):
+    """Page-locked copy of a matrix.  The ranks of these tests are threads of ONE process on ONE device:
+    a copy from pageable memory makes its thread wait inside the driver until the stream gets there, and
+    behind a rank barrier that wait can hold up the other ranks' launches.  (One rank per process / GPU,
+    the deployment, has no such coupling.)"""
+    import torch
+
+    t = torch.from_numpy(a.view(np.int64)).pin_memory()
+    _PINNED.append(t)
+    return t.numpy().view(np.uint64)
+
+
 def _inputs(oracle, logn, wm, wa, seed=0):
     n = 1 << logn
-    main = oracle.synthetic_trace(wm, n, 0xAE200000 + seed)
-    aux = oracle.synthetic_trace(wa, n, 0xAE210000 + seed) if wa else None
-    ce = oracle.synthetic_trace(2, 8 * n, 0xCE + seed)
+    main = _pin(oracle.synthetic_trace(wm, n, 0xAE200000 + seed))
+    aux = _pin(oracle.synthetic_trace(wa, n, 0xAE210000 + seed)) if wa else None
+    ce = _pin(oracle.synthetic_trace(2, 8 * n, 0xCE + seed))
     divs = [oracle.Divisor(n, 1, [pow(oracle.root_of_unity(logn), n - 1, P)]), oracle.Divisor(1, 1, [])]
     return main, aux, ce, divs
 
@@ -60,10 +75,11 @@ def test_group_prove_montgomery_and_host_sync(oracle):
     g = aero_b200.Group([0, 0], window_bytes(11, 11, 2))
     try:
         g.set_option("force_host_sync", 1)
+        mm, ma, mc = _pin(c2m(main)), _pin(c2m(aux)), _pin(c2m(ce))
         for _ in range(2):
-            assert g.prove(c2m(main), c2m(aux), c2m(ce), mdivs, pub) == ref.proof_bytes
+            assert g.prove(mm, ma, mc, mdivs, pub) == ref.proof_bytes
         g.set_option("force_host_sync", 0)
-        assert g.prove(c2m(main), c2m(aux), c2m(ce), mdivs, pub) == ref.proof_bytes
+        assert g.prove(mm, ma, mc, mdivs, pub) == ref.proof_bytes
     finally:
         g.close()
 
