@@ -44,6 +44,7 @@ struct aero_upload {
     cudaEvent_t done = nullptr;
     std::vector<const uint64_t *> cols;
     int col_begin = 0, col_end = 0;  // columns actually copied (a sharded context may take its own only)
+    uint64_t row_begin = 0, row_end = 0;  // rows actually copied (likewise: its own row block)
     uint64_t n_rows = 0;
     bool queued = false;
 };
@@ -53,6 +54,9 @@ struct aero_ctx {
     cudaStream_t stream = 0;
     cudaStream_t copy_stream = nullptr;  // host->device uploads overlapped with compute
     cudaStream_t hash_stream = nullptr;  // row hashing of batch k overlapped with the LDE of batch k+1
+    cudaStream_t push_stream = nullptr;  // coefficient pushes to the peers, beside the LDE of the columns already here
+    cudaEvent_t ev_push = nullptr;
+    unsigned long long push_epoch = 0;   // arrival flags of the coefficient exchange (window + 1024 + 8 * source rank)
     cudaEvent_t ev_lde = nullptr, ev_hash = nullptr, ev_copy_order = nullptr;
     bool overlap_hash = false;           // aero_ctx_set_option("overlap_hash"); measured slower on B200, see DESIGN.md
     bool force_split_intt = false;       // test hook: take the B x size-n route of constraints_into_poly at any size
@@ -364,15 +368,38 @@ aero_status DevBlocks::alloc_shared(void **p, size_t bytes) {
 // A peer that never reached a device-side barrier (it failed) is reported here instead of hanging the
 // GPU.  The time-out count is cleared once reported, so the context stays usable after the ranks are
 // back in lock-step.
-static aero_status window_check(aero_ctx *ctx) {
+// The check rides on a synchronisation the caller needs anyway: window_check_queue() queues the download
+// of the time-out word, the caller queues its own downloads and synchronises the stream once, then
+// window_check_result() looks at the word.
+static aero_status window_check_queue(aero_ctx *ctx, const unsigned int **word) {
+    *word = nullptr;
     if (!ctx_sharded(ctx) || ctx->win_host_sync) return AERO_OK;
-    unsigned int t = 0;
-    TRY(download_small(ctx, &t, ctx->win + 2048, 4));
-    if (t) {
+    void *h = nullptr;
+    TRY(ring_take(ctx, 4, &h));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, ctx->win + 2048, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    *word = (const unsigned int *)h;
+    return AERO_OK;
+}
+static aero_status window_check_result(aero_ctx *ctx, const unsigned int *word) {
+    if (word && *word) {
+        const unsigned int t = *word;
         cudaMemsetAsync(ctx->win + 2048, 0, 4, ctx->stream);
         CTX_FAIL(ctx, AERO_ERR_STATE, "exchange barrier timed out %u time(s): a peer rank did not arrive", t);
     }
     return AERO_OK;
+}
+static aero_status window_check(aero_ctx *ctx) {
+    const unsigned int *word = nullptr;
+    TRY(window_check_queue(ctx, &word));
+    if (word) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return window_check_result(ctx, word);
+}
+// device -> caller memory and the barrier check with ONE stream synchronisation
+static aero_status download_small_checked(aero_ctx *ctx, void *dst, const void *d_src, size_t bytes) {
+    const unsigned int *word = nullptr;
+    TRY(window_check_queue(ctx, &word));
+    TRY(download_small(ctx, dst, d_src, bytes));
+    return window_check_result(ctx, word);
 }
 template <typename T>
 static aero_status upload_vec(aero_ctx *ctx, T **d, const std::vector<T> &h, bool own = true) {
@@ -602,11 +629,12 @@ struct aero_segment {
     SegTreeView tree_view() const { return SegTreeView{leaf_stage, heap, top, logn, log_blowup, logG, ctx->shard_rank}; }
 };
 
-// this rank's share of the columns of a matrix (interpolation is sharded by column, extension by coset)
-static void own_columns(const aero_ctx *ctx, int ncols, int *cb, int *ce) {
-    *cb = (int)((long long)ctx->shard_rank * ncols / ctx->shard_world);
-    *ce = (int)((long long)(ctx->shard_rank + 1) * ncols / ctx->shard_world);
+// a rank's share of the columns of a matrix (interpolation is sharded by column, extension by coset)
+static void columns_of_rank(const aero_ctx *ctx, int rank, int ncols, int *cb, int *ce) {
+    *cb = (int)((long long)rank * ncols / ctx->shard_world);
+    *ce = (int)((long long)(rank + 1) * ncols / ctx->shard_world);
 }
+static void own_columns(const aero_ctx *ctx, int ncols, int *cb, int *ce) { columns_of_rank(ctx, ctx->shard_rank, ncols, cb, ce); }
 
 // All digests of this rank's leaf block are in `leaf_stage` (after a barrier when other ranks wrote
 // some of them): build the block's subtree, exchange the G sub-roots, finish the top levels.
@@ -622,7 +650,7 @@ static aero_status segment_finish_tree(aero_segment *seg, uint8_t root[32]) {
     TRY(window_barrier(ctx));
     merkle_top(seg->top, G, ctx->stream);
     CUDA_TRY(ctx, cudaGetLastError());
-    if (root) TRY(download_small(ctx, root, seg->top + 8, 32));
+    if (root) return download_small_checked(ctx, root, seg->top + 8, 32);
     return window_check(ctx);
 }
 
@@ -825,19 +853,45 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
         } else {
             done = 0;  // part of an earlier, wider interpolation launch
         }
-        if (sharded && done) {
+        if (sharded && done && ctx->win_host_sync) {
             PhaseTimer t(ctx, "push_polys");
             peer_push(polys_all, ctx->shard_world, ctx->shard_rank, (size_t)c0 * n_rows * 8, (size_t)done * n_rows * 8, ctx->stream);
         }
+        if (sharded && !ctx->win_host_sync && c0 + nc == ce) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_push, ctx->stream));  // all own coefficients exist
         segment_lde_batch(seg.get(), lplan, c0, nc, tmp_l);
         if (per_batch_hash) TRY(segment_hash_batch(seg.get(), c0, nc));
     }
-    if (sharded) {  // the other ranks' coefficients have arrived: extend those columns too
+    if (sharded && ctx->win_host_sync) {  // the other ranks' coefficients have arrived: extend those columns too
         TRY(window_barrier(ctx));
         for (int part = 0; part < 2; part++) {
             const int lo = part ? ce : 0, hi = part ? (int)n_cols : cb;
             for (int c0 = lo; c0 < hi; c0 += lde_batch) segment_lde_batch(seg.get(), lplan, c0, std::min(lde_batch, hi - c0), tmp_l);
         }
+    } else if (sharded) {
+        // Warm shape: the exchange runs on its own stream beside the LDE.  Rank r sends its columns to
+        // r+1, r+2, ... in turn, each transfer at the full NVLink rate of the sender, and raises an arrival
+        // flag at the receiver after each; so rank r receives from r-1 first, then r-2, ... and extends
+        // each rank's columns as soon as they are there, while the later ones are still in flight.
+        const int G = ctx->shard_world, me = ctx->shard_rank;
+        const unsigned long long epoch = ++ctx->push_epoch;
+        if (ce == cb) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_push, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->push_stream, ctx->ev_push, 0));
+        {
+            PhaseTimer t(ctx, "push_polys", ctx->push_stream, true);
+            for (int k = 1; k < G; k++) {
+                const int dest = (me + k) % G;
+                peer_send(polys_all, me, dest, (size_t)cb * n_rows * 8, (size_t)(ce - cb) * n_rows * 8,
+                          (unsigned long long *)(ctx->win_base[dest] + 1024) + me, epoch, ctx->push_stream);
+            }
+        }
+        for (int k = 1; k < G; k++) {
+            const int src = (me - k + G) % G;
+            int lo = 0, hi = 0;
+            columns_of_rank(ctx, src, (int)n_cols, &lo, &hi);
+            peer_wait((unsigned long long *)(ctx->win + 1024) + src, epoch, (unsigned int *)(ctx->win + 2048), ctx->stream);
+            for (int c0 = lo; c0 < hi; c0 += lde_batch) segment_lde_batch(seg.get(), lplan, c0, std::min(lde_batch, hi - c0), tmp_l);
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
     }
     if (!per_batch_hash) TRY(segment_hash_batch(seg.get(), 0, (int)n_cols));
     TRY(segment_tree_after_hash(seg.get(), root));
@@ -1023,10 +1077,12 @@ aero_status GatherBatch::run() {
     }
     CUDA_TRY(ctx, cudaGetLastError());
     TRY(window_barrier(ctx));
+    const unsigned int *word = nullptr;
+    TRY(window_check_queue(ctx, &word));
     if (out_bytes)
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage + idx_bytes, d_res, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    TRY(window_check(ctx));
+    TRY(window_check_result(ctx, word));
     host = ctx->h_stage + idx_bytes;
     return AERO_OK;
 }
@@ -1197,6 +1253,11 @@ void aero_ctx_destroy(aero_ctx *ctx) {
         cudaStreamDestroy(ctx->hash_stream);
         cudaEventDestroy(ctx->ev_lde);
         cudaEventDestroy(ctx->ev_hash);
+    }
+    if (ctx->push_stream) {
+        cudaStreamSynchronize(ctx->push_stream);
+        cudaStreamDestroy(ctx->push_stream);
+        cudaEventDestroy(ctx->ev_push);
     }
     for (int r = 0; r < AERO_MAX_RANKS; r++)
         if (ctx->win_ipc[r]) cudaIpcCloseMemHandle(ctx->win_base[r]);
@@ -1375,7 +1436,8 @@ static aero_status upload_enqueue(aero_upload *u) {
     if (u->queued) return AERO_OK;
     TRY(copy_stream_after_compute(ctx));
     for (int c = u->col_begin; c < u->col_end; c++)
-        CUDA_TRY(ctx, cudaMemcpyAsync(u->d + (size_t)c * u->n_rows, u->cols[c], u->n_rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(u->d + (size_t)c * u->n_rows + u->row_begin, u->cols[c] + u->row_begin,
+                                      (u->row_end - u->row_begin) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
     CUDA_TRY(ctx, cudaEventRecord(u->done, ctx->copy_stream));
     u->queued = true;
     return AERO_OK;
@@ -1387,7 +1449,7 @@ static aero_status flush_deferred_uploads(aero_ctx *ctx) {
     return AERO_OK;
 }
 aero_status aero_upload_start(aero_ctx *ctx, const uint64_t *const *cols, uint32_t n_cols, uint64_t n_rows, int defer,
-                              int own_columns_only, aero_upload **out) {
+                              int shard_mode, aero_upload **out) {
     if (!ctx) return AERO_ERR_INVALID;
     enter(ctx);
     if (!cols || !out || n_cols == 0 || n_rows == 0) CTX_FAIL(ctx, AERO_ERR_INVALID, "null or empty matrix");
@@ -1399,7 +1461,14 @@ aero_status aero_upload_start(aero_ctx *ctx, const uint64_t *const *cols, uint32
     u->cols.assign(cols, cols + n_cols);
     u->col_begin = 0;
     u->col_end = (int)n_cols;
-    if (own_columns_only) own_columns(ctx, (int)n_cols, &u->col_begin, &u->col_end);
+    u->row_begin = 0;
+    u->row_end = n_rows;
+    if (shard_mode == AERO_UPLOAD_OWN_COLUMNS) own_columns(ctx, (int)n_cols, &u->col_begin, &u->col_end);
+    else if (shard_mode == AERO_UPLOAD_OWN_ROWS) {
+        if (n_rows % (uint64_t)ctx->shard_world) CTX_FAIL(ctx, AERO_ERR_INVALID, "rows not divisible by the number of ranks");
+        u->row_begin = n_rows / ctx->shard_world * ctx->shard_rank;
+        u->row_end = u->row_begin + n_rows / ctx->shard_world;
+    } else if (shard_mode != AERO_UPLOAD_ALL) CTX_FAIL(ctx, AERO_ERR_INVALID, "unknown upload shard mode %d", shard_mode);
     aero_status st = dev_alloc(ctx, (void **)&u->d, (size_t)n_cols * n_rows * 8);
     if (st == AERO_OK && cudaEventCreateWithFlags(&u->done, cudaEventDisableTiming) != cudaSuccess) {
         ctx->err = "cudaEventCreate failed";
@@ -1541,6 +1610,14 @@ aero_status aero_ctx_window_create(aero_ctx *ctx, size_t bytes, uint8_t handle_o
     ctx->win_live = 0;
     return AERO_OK;
 }
+static aero_status ensure_push_stream(aero_ctx *ctx) {
+    if (!ctx->push_stream) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->push_stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_push, cudaEventDisableTiming));
+        preload_exchange_kernels();
+    }
+    return AERO_OK;
+}
 static aero_status window_attach_check(aero_ctx *ctx, int n_ranks) {
     if (!ctx->win) CTX_FAIL(ctx, AERO_ERR_STATE, "create the exchange window first");
     if (ctx->win_ranks) CTX_FAIL(ctx, AERO_ERR_STATE, "exchange window already attached");
@@ -1571,7 +1648,7 @@ aero_status aero_ctx_window_attach(aero_ctx *ctx, int n_ranks, const uint8_t *ha
         ctx->win_ipc[r] = true;
     }
     ctx->win_ranks = n_ranks;
-    return AERO_OK;
+    return ensure_push_stream(ctx);
 }
 aero_status aero_ctx_window_attach_local(aero_ctx *ctx, int n_ranks, aero_ctx *const *ranks) {
     if (!ctx || !ranks) return AERO_ERR_INVALID;
@@ -1592,7 +1669,7 @@ aero_status aero_ctx_window_attach_local(aero_ctx *ctx, int n_ranks, aero_ctx *c
         ctx->win_base[r] = o->win;
     }
     ctx->win_ranks = n_ranks;
-    return AERO_OK;
+    return ensure_push_stream(ctx);
 }
 int aero_ctx_window_ranks(aero_ctx *ctx) { return (ctx && ctx->shard_world > 1) ? ctx->win_ranks : 0; }
 aero_status aero_ctx_set_host_barrier(aero_ctx *ctx, aero_host_barrier_fn fn, void *user) {
@@ -1802,7 +1879,12 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
     }
     const uint64_t *cols = d_eval_cols;
     uint64_t *combined = nullptr;
-    TRY(dev_alloc(ctx, (void **)&combined, N * 8));
+    // A sharded context combines its own block of rows [rank*N/G, (rank+1)*N/G) -- the only part of the
+    // evaluation columns it reads, so the only part it has to upload -- and stores it into the peers.
+    const int G = ctx->shard_world;
+    if (N % (uint64_t)G) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "constraint evaluation domain smaller than the number of ranks");
+    const uint64_t rows_per = N / G, row0 = rows_per * ctx->shard_rank;
+    TRY(dev_alloc_shared(ctx, (void **)&combined, N * 8));
     std::vector<DivisorDev> dd(n_div);
     std::vector<uint64_t *> zbufs;
     aero_status st = AERO_OK;
@@ -1826,7 +1908,12 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
             divisor_inverses(o, z, logN, gN, ctx->stream);
             o.zinv = z;
         }
-        if (st == AERO_OK) constraint_combine(cols, col_stride, dd.data(), (int)n_div, logN, gl::GENERATOR, gN, combined, ctx->stream);
+        if (st == AERO_OK) constraint_combine(cols, col_stride, dd.data(), (int)n_div, logN, gl::GENERATOR, gN, (uint32_t)row0,
+                                              (uint32_t)rows_per, combined, ctx->stream);
+    }
+    if (st == AERO_OK && G > 1) {
+        peer_push_words(rank_ptrs(ctx, combined), G, ctx->shard_rank, row0, rows_per, ctx->stream);
+        st = window_barrier(ctx);
     }
     aero_segment *seg = nullptr;
     if (st == AERO_OK) {
@@ -1943,28 +2030,27 @@ aero_status aero_constraints_into_poly(aero_ctx *ctx, const uint64_t *const *eva
     TRY(blk.alloc((void **)&cols, (size_t)n_div * N * 8));
     {
         PhaseTimer t(ctx, "h2d");
+        const uint64_t per = N / ctx->shard_world, r0 = per * ctx->shard_rank;  // own row block (all rows on one GPU)
         for (uint32_t d = 0; d < n_div; d++) {
             if (!eval_cols[d]) CTX_FAIL(ctx, AERO_ERR_INVALID, "null evaluation column %u", d);
-            CUDA_TRY(ctx, cudaMemcpyAsync(cols + (size_t)d * N, eval_cols[d], N * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(cols + (size_t)d * N + r0, eval_cols[d] + r0, per * 8, cudaMemcpyHostToDevice, ctx->stream));
         }
     }
     return aero_constraints_into_poly_device(ctx, cols, N, divs, n_div, ce_domain_size, trace_len, out);
 }
 
 // ---- OOD + DEEP -----------------------------------------------------------------------------
-// Queues the evaluation of every column of `seg` at `points`; the results (ncols x npoints, column
-// major) are copied to h_stage + host_off.  Nothing is synchronised here.
-struct OodJob {
-    aero_segment *seg = nullptr;
-    int np = 0;
-    uint64_t *d_tab = nullptr, *d_out = nullptr, *d_scr = nullptr;
-    size_t host_off = 0;
-};
-static aero_status ood_enqueue(aero_ctx *ctx, aero_segment *seg, const std::vector<uint64_t> &points, size_t host_off,
-                               OodJob &job) {
+// Evaluation of the columns of `seg` at `points`, results [col][point] at res + res_off.  A sharded context
+// evaluates the columns it owns (own_columns; every rank holds all coefficients) and stores them into the
+// result buffer of every rank.  Nothing is synchronised here.
+static aero_status ood_enqueue(aero_ctx *ctx, aero_segment *seg, const std::vector<uint64_t> &points, uint64_t *res,
+                               size_t res_off, DevBlocks &blk) {
     const int logn = seg->logn;
     const int np = (int)points.size();
     const uint64_t n = seg->n();
+    int cb = 0, ce = seg->ncols;
+    own_columns(ctx, seg->ncols, &cb, &ce);
+    if (ce == cb) return AERO_OK;
     const int chunk_len = n < 4096 ? (int)n : 4096;
     const int nchunks = (int)(n / chunk_len);
     const int stride = 257 + nchunks + 16;  // layout: see ood_partial_kernel
@@ -1988,23 +2074,14 @@ static aero_status ood_enqueue(aero_ctx *ctx, aero_segment *seg, const std::vect
             x = gl::mul(x, t[256]);
         }
     }
-    job.seg = seg;
-    job.np = np;
-    job.host_off = host_off;
-    TRY(dev_alloc(ctx, (void **)&job.d_tab, tab.size() * 8));
-    TRY(dev_alloc(ctx, (void **)&job.d_out, (size_t)seg->ncols * np * 8));
-    TRY(dev_alloc(ctx, (void **)&job.d_scr, ood_scratch_elems(seg->ncols, logn, np) * 8));
-    TRY(upload_small(ctx, job.d_tab, tab.data(), tab.size() * 8));
-    ood_eval(seg->polys, n, seg->ncols, logn, job.d_tab, np, job.d_out, job.d_scr, ctx->stream);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage + host_off, job.d_out, (size_t)seg->ncols * np * 8, cudaMemcpyDeviceToHost,
-                                  ctx->stream));
+    uint64_t *d_tab = nullptr, *d_scr = nullptr;
+    TRY(blk.alloc((void **)&d_tab, tab.size() * 8));
+    TRY(blk.alloc((void **)&d_scr, ood_scratch_elems(ce - cb, logn, np) * 8));
+    TRY(upload_small(ctx, d_tab, tab.data(), tab.size() * 8));
+    const size_t first = res_off + (size_t)cb * np, count = (size_t)(ce - cb) * np;
+    ood_eval(seg->polys + (size_t)cb * n, n, ce - cb, logn, d_tab, np, res + first, d_scr, ctx->stream);
+    peer_push_words(rank_ptrs(ctx, res), ctx->shard_world, ctx->shard_rank, first, count, ctx->stream);
     return AERO_OK;
-}
-static void ood_release(aero_ctx *ctx, OodJob &job) {
-    dev_free(ctx, job.d_tab);
-    dev_free(ctx, job.d_out);
-    dev_free(ctx, job.d_scr);
-    job.d_tab = job.d_out = job.d_scr = nullptr;
 }
 
 aero_status aero_ood_eval(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs, aero_segment *comp,
@@ -2013,49 +2090,54 @@ aero_status aero_ood_eval(aero_ctx *ctx, aero_segment *const *trace_segs, uint32
     enter(ctx);
     if (n_trace_segs && (!trace_segs || !out_trace)) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     if (comp && !out_comp) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
-    PhaseTimer t(ctx, "ood_eval");
     const uint64_t zc = to_canon(ctx, z);
     int W = 0;
     for (uint32_t s = 0; s < n_trace_segs; s++) {
         if (!trace_segs[s] || trace_segs[s]->logn != trace_segs[0]->logn) CTX_FAIL(ctx, AERO_ERR_INVALID, "trace segments must have equal length");
         W += trace_segs[s]->ncols;
     }
-    // all segments are queued before the one synchronisation
-    TRY(stage_reserve(ctx, ((size_t)2 * W + (comp ? comp->ncols : 0)) * 8));
-    std::vector<OodJob> jobs(n_trace_segs + (comp ? 1 : 0));
-    size_t off = 0;
-    aero_status st = AERO_OK;
-    if (n_trace_segs) {
-        const uint64_t g = gl::root_of_unity(trace_segs[0]->logn);
-        const std::vector<uint64_t> pts = {zc, gl::mul(zc, g)};
-        for (uint32_t s = 0; s < n_trace_segs && st == AERO_OK; s++) {
-            st = ood_enqueue(ctx, trace_segs[s], pts, off, jobs[s]);
-            off += (size_t)2 * trace_segs[s]->ncols * 8;
+    const size_t total = (size_t)2 * W + (comp ? comp->ncols : 0);
+    if (total == 0) return AERO_OK;
+    // all segments are queued before the one synchronisation; results: [seg][col][point]
+    DevBlocks blk(ctx);
+    uint64_t *res = nullptr;
+    TRY(blk.alloc_shared((void **)&res, total * 8));
+    std::vector<size_t> seg_off(n_trace_segs + 1, 0);
+    {
+        PhaseTimer t(ctx, "ood_eval");
+        size_t off = 0;
+        if (n_trace_segs) {
+            const uint64_t g = gl::root_of_unity(trace_segs[0]->logn);
+            const std::vector<uint64_t> pts = {zc, gl::mul(zc, g)};
+            for (uint32_t s = 0; s < n_trace_segs; s++) {
+                seg_off[s] = off;
+                TRY(ood_enqueue(ctx, trace_segs[s], pts, res, off, blk));
+                off += (size_t)2 * trace_segs[s]->ncols;
+            }
         }
+        seg_off[n_trace_segs] = off;
+        if (comp) {
+            const std::vector<uint64_t> pts = {gl::pow(zc, (uint64_t)comp->ncols)};
+            TRY(ood_enqueue(ctx, comp, pts, res, off, blk));
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
     }
-    if (comp && st == AERO_OK) {
-        const std::vector<uint64_t> pts = {gl::pow(zc, (uint64_t)comp->ncols)};
-        st = ood_enqueue(ctx, comp, pts, off, jobs[n_trace_segs]);
-    }
-    if (st == AERO_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-        ctx->err = "aero_ood_eval: stream synchronisation failed";
-        st = AERO_ERR_CUDA;
-    }
-    for (auto &j : jobs) ood_release(ctx, j);
-    if (st != AERO_OK) return st;
+    TRY(window_barrier(ctx));
+    std::vector<uint64_t> h(total);
+    TRY(download_small_checked(ctx, h.data(), res, total * 8));
     int c0 = 0;
     for (uint32_t s = 0; s < n_trace_segs; s++) {
-        const uint64_t *res = (const uint64_t *)(ctx->h_stage + jobs[s].host_off);  // [col][point]
+        const uint64_t *r = h.data() + seg_off[s];  // [col][point]
         const int nc = trace_segs[s]->ncols;
         for (int c = 0; c < nc; c++) {
-            out_trace[c0 + c] = from_canon(ctx, res[(size_t)c * 2]);
-            out_trace[W + c0 + c] = from_canon(ctx, res[(size_t)c * 2 + 1]);
+            out_trace[c0 + c] = from_canon(ctx, r[(size_t)c * 2]);
+            out_trace[W + c0 + c] = from_canon(ctx, r[(size_t)c * 2 + 1]);
         }
         c0 += nc;
     }
     if (comp) {
-        const uint64_t *res = (const uint64_t *)(ctx->h_stage + jobs[n_trace_segs].host_off);
-        for (int c = 0; c < comp->ncols; c++) out_comp[c] = from_canon(ctx, res[c]);
+        const uint64_t *r = h.data() + seg_off[n_trace_segs];
+        for (int c = 0; c < comp->ncols; c++) out_comp[c] = from_canon(ctx, r[c]);
     }
     return AERO_OK;
 }
@@ -2103,9 +2185,10 @@ aero_status aero_deep_compose(aero_ctx *ctx, aero_segment *const *trace_segs, ui
     uint64_t *d_cc = nullptr, *d_consts = nullptr, *t1 = nullptr, *t2 = nullptr, *hh = nullptr, *carry = nullptr, *coeffs = nullptr;
     TRY(tmp.alloc((void **)&d_cc, h_cc.size() * 8));
     TRY(tmp.alloc((void **)&d_consts, 3 * 8));
-    TRY(tmp.alloc((void **)&t1, n * 8));
-    TRY(tmp.alloc((void **)&t2, n * 8));
-    TRY(tmp.alloc((void **)&hh, n * 8));
+    // (a sharded context accumulates its own range of coefficient indices and stores it into the peers)
+    TRY(tmp.alloc_shared((void **)&t1, n * 8));
+    TRY(tmp.alloc_shared((void **)&t2, n * 8));
+    TRY(tmp.alloc_shared((void **)&hh, n * 8));
     TRY(tmp.alloc((void **)&coeffs, n * 8));
     TRY(tmp.alloc((void **)&carry, (6 * (n / 256 + 1)) * 8));
     TRY(upload_small(ctx, d_cc, h_cc.data(), h_cc.size() * 8));
@@ -2118,7 +2201,13 @@ aero_status aero_deep_compose(aero_ctx *ctx, aero_segment *const *trace_segs, ui
             segs.p[s] = trace_segs[s]->polys;
             segs.ncols[s] = trace_segs[s]->ncols;
         }
-        deep_accumulate(segs, comp->polys, m, logn, d_cc, d_consts, t1, t2, hh, ctx->stream);
+        const int G = ctx->shard_world;
+        const uint32_t per = (uint32_t)(n / G), j0 = per * (uint32_t)ctx->shard_rank;
+        deep_accumulate(segs, comp->polys, m, logn, j0, per, d_cc, d_consts, t1, t2, hh, ctx->stream);
+        if (G > 1) {
+            for (uint64_t *buf : {t1, t2, hh}) peer_push_words(rank_ptrs(ctx, buf), G, ctx->shard_rank, j0, per, ctx->stream);
+            TRY(window_barrier(ctx));
+        }
         const uint64_t bs[3] = {zc, zg, zm};
         syn_div3(t1, t2, hh, logn, bs, carry, ctx->stream);
         deep_finish(t1, t2, hh, logn, d0, d1, coeffs, ctx->stream);

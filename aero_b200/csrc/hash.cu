@@ -84,6 +84,59 @@ void peer_push(const RankPtrs &buf, int G, int rank, size_t off, size_t bytes, c
     AERO_COUNT_LAUNCH(1);
     peer_push_kernel<<<(unsigned)blocks, 256, 0, s>>>(buf, G, rank, off / 16, count);
 }
+__global__ void __launch_bounds__(256) peer_push_words_kernel(RankPtrs buf, int G, int rank, size_t first, size_t count) {
+    const uint64_t *local = reinterpret_cast<const uint64_t *>(buf.p[rank]);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t v = local[first + i];
+        for (int q = 0; q < G; q++)
+            if (q != rank) reinterpret_cast<uint64_t *>(buf.p[q])[first + i] = v;
+    }
+}
+void peer_push_words(const RankPtrs &buf, int G, int rank, size_t first, size_t count, cudaStream_t s) {
+    if (G <= 1 || count == 0) return;
+    size_t blocks = (count + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    AERO_COUNT_LAUNCH(1);
+    peer_push_words_kernel<<<(unsigned)blocks, 256, 0, s>>>(buf, G, rank, first, count);
+}
+__global__ void __launch_bounds__(256) peer_send_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t count) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void peer_flag_kernel(volatile unsigned long long *flag, unsigned long long epoch) {
+    __threadfence_system();
+    *flag = epoch;
+    __threadfence_system();
+}
+void peer_send(const RankPtrs &buf, int rank, int dest, size_t off, size_t bytes, unsigned long long *dest_flag,
+               unsigned long long epoch, cudaStream_t s) {
+    const size_t count = bytes / 16;
+    AERO_COUNT_LAUNCH(2);
+    if (count) {
+        size_t blocks = (count + 255) / 256;
+        if (blocks > 148 * 4) blocks = 148 * 4;  // a few resident blocks per SM keep NVLink busy and leave the SMs to the LDE
+        peer_send_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const uint4 *>((const uint8_t *)buf.p[rank] + off),
+                                                         reinterpret_cast<uint4 *>((uint8_t *)buf.p[dest] + off), count);
+    }
+    peer_flag_kernel<<<1, 1, 0, s>>>(dest_flag, epoch);
+}
+__global__ void peer_wait_kernel(const volatile unsigned long long *flag, unsigned long long epoch, unsigned int *d_timeout) {
+    const long long t0 = clock64();
+    while (*flag < epoch) {
+        if (clock64() - t0 > 8000000000LL) {
+            atomicAdd(d_timeout, 1u);
+            break;
+        }
+    }
+    __threadfence_system();
+}
+void peer_wait(const unsigned long long *flag, unsigned long long epoch, unsigned int *d_timeout, cudaStream_t s) {
+    AERO_COUNT_LAUNCH(1);
+    peer_wait_kernel<<<1, 1, 0, s>>>(flag, epoch, d_timeout);
+}
+// The kernels of the device-side exchange are first LAUNCHED by the second proof of a shape, when the
+// peers may already be spinning in a barrier -- and with lazy module loading (the CUDA 12 default) a first
+// launch loads the kernel, which can synchronise the device.  Load them while nothing spins.
+void preload_exchange_kernels();
 // Stream-ordered barrier between the ranks of a proof: thread q publishes `epoch` in rank q's flag
 // slot for this rank (after a system-scope fence, so every peer store of earlier kernels on this
 // stream is visible first), then waits for rank q's flag in the local window.  A peer that never
@@ -103,6 +156,15 @@ __global__ void peer_barrier_kernel(RankPtrs flags, int G, int rank, unsigned lo
         }
     }
     __threadfence_system();
+}
+void preload_exchange_kernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, peer_barrier_kernel);
+    cudaFuncGetAttributes(&a, peer_send_kernel);
+    cudaFuncGetAttributes(&a, peer_flag_kernel);
+    cudaFuncGetAttributes(&a, peer_wait_kernel);
+    cudaFuncGetAttributes(&a, peer_push_kernel);
+    cudaFuncGetAttributes(&a, peer_push_words_kernel);
 }
 void peer_barrier(const RankPtrs &flags, int G, int rank, unsigned long long epoch, unsigned int *d_timeout,
                   cudaStream_t s) {

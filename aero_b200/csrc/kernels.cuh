@@ -94,6 +94,16 @@ void merkle_push_subroot(const uint32_t *heap, const RankPtrs &top, int G, int r
 void merkle_top(uint32_t *top, int G, cudaStream_t s);
 // copies [off, off + bytes) of the local buffer to the same range of every other rank's copy (16-byte units)
 void peer_push(const RankPtrs &buf, int G, int rank, size_t off, size_t bytes, cudaStream_t s);
+// same for [first, first + count) 8-byte words (small, unaligned ranges)
+void peer_push_words(const RankPtrs &buf, int G, int rank, size_t first, size_t count, cudaStream_t s);
+// [off, off + bytes) of the local buffer -> the copy on rank `dest` only; then (a second, one-thread kernel:
+// all stores of the first have completed) *dest_flag = epoch, the arrival flag the receiver polls
+void peer_send(const RankPtrs &buf, int rank, int dest, size_t off, size_t bytes, unsigned long long *dest_flag,
+               unsigned long long epoch, cudaStream_t s);
+// spins until *flag >= epoch (one thread; ~4 s time-out counted in *d_timeout)
+void peer_wait(const unsigned long long *flag, unsigned long long epoch, unsigned int *d_timeout, cudaStream_t s);
+// loads the exchange kernels (see hash.cu)
+void preload_exchange_kernels();
 // all ranks arrive (epoch) before any leaves: flags[r] of rank q's window is written by rank r
 void peer_barrier(const RankPtrs &flags, int G, int rank, unsigned long long epoch, unsigned int *d_timeout,
                   cudaStream_t s);
@@ -127,8 +137,9 @@ struct DeepSegs {  // trace segments in order (main, aux...): column c of segmen
     int ncols[4];
     int nseg;
 };
-void deep_accumulate(const DeepSegs &segs, const uint64_t *comp_polys, int m, int logn,
-                     const uint64_t *d_cc /* W*2 + m */,
+// coefficient indices [j_begin, j_begin + j_count) only (a rank's share of a sharded proof)
+void deep_accumulate(const DeepSegs &segs, const uint64_t *comp_polys, int m, int logn, uint32_t j_begin,
+                     uint32_t j_count, const uint64_t *d_cc /* W*2 + m */,
                      const uint64_t *d_consts /* 3: subtract from coefficient 0 of t1,t2,h */, uint64_t *t1,
                      uint64_t *t2, uint64_t *h, cudaStream_t s);
 void syn_div3(uint64_t *t1, uint64_t *t2, uint64_t *h, int logn, const uint64_t b[3], uint64_t *d_carry,
@@ -160,8 +171,10 @@ struct DivisorDev {
     uint32_t zn;           // N / a
 };
 void divisor_inverses(const DivisorDev &d, uint64_t *zinv_out, int logN, PowTable gN, cudaStream_t s);
+// rows [i_begin, i_begin + i_count) of the constraint evaluation domain
 void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDev *divs, int ndiv, int logN,
-                        uint64_t offset, PowTable gN, uint64_t *combined, cudaStream_t s);
+                        uint64_t offset, PowTable gN, uint32_t i_begin, uint32_t i_count, uint64_t *combined,
+                        cudaStream_t s);
 
 // peak.cu
 double measure_alu_peak(int num_sms, uint32_t *scratch, cudaStream_t s);

@@ -223,12 +223,14 @@ void ood_eval(const uint64_t *polys, size_t col_stride, int ncols, int logn, con
 // out[j] = d0*c[j] + d1*c[j-1] (adjust_degree, :222-238).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) deep_accumulate_kernel(DeepSegs segs, const uint64_t *__restrict__ cp, int m,
-                                                              uint32_t n, const uint64_t *__restrict__ cc,
+                                                              uint32_t n, uint32_t j_begin, uint32_t j_count,
+                                                              const uint64_t *__restrict__ cc,
                                                               const uint64_t *__restrict__ consts,
                                                               uint64_t *__restrict__ t1, uint64_t *__restrict__ t2,
                                                               uint64_t *__restrict__ h) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+    const uint32_t jl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jl >= j_count) return;
+    const uint32_t j = j_begin + jl;
     // three dot products over the columns, reduced once each (gl::Acc160)
     gl::Acc160 s1, s2, sh;
     int i = 0;  // running trace-column index across segments (composer/mod.rs:96-99)
@@ -252,11 +254,14 @@ __global__ void __launch_bounds__(256) deep_accumulate_kernel(DeepSegs segs, con
     t2[j] = a2;
     h[j] = ah;
 }
-void deep_accumulate(const DeepSegs &segs, const uint64_t *comp_polys, int m, int logn, const uint64_t *d_cc,
-                     const uint64_t *d_consts, uint64_t *t1, uint64_t *t2, uint64_t *h, cudaStream_t s) {
+void deep_accumulate(const DeepSegs &segs, const uint64_t *comp_polys, int m, int logn, uint32_t j_begin, uint32_t j_count,
+                     const uint64_t *d_cc, const uint64_t *d_consts, uint64_t *t1, uint64_t *t2, uint64_t *h,
+                     cudaStream_t s) {
     const uint32_t n = 1u << logn;
+    if (!j_count) return;
     AERO_COUNT_LAUNCH(1);
-    deep_accumulate_kernel<<<(n + 255) / 256, 256, 0, s>>>(segs, comp_polys, m, n, d_cc, d_consts, t1, t2, h);
+    deep_accumulate_kernel<<<(j_count + 255) / 256, 256, 0, s>>>(segs, comp_polys, m, n, j_begin, j_count, d_cc, d_consts,
+                                                               t1, t2, h);
 }
 
 // Synthetic division by (x - b) as a suffix recurrence c <- p[i] + b*c, q[i] = previous c.
@@ -522,10 +527,12 @@ struct DivisorSet {
     int n;
 };
 __global__ void __launch_bounds__(256) constraint_combine_kernel(const uint64_t *__restrict__ cols, size_t col_stride,
-                                                                 DivisorSet ds, uint32_t N, uint64_t offset,
-                                                                 PowTable gN, uint64_t *__restrict__ combined) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
+                                                                 DivisorSet ds, uint32_t i_begin, uint32_t i_count,
+                                                                 uint64_t offset, PowTable gN,
+                                                                 uint64_t *__restrict__ combined) {
+    const uint32_t il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= i_count) return;
+    const uint32_t i = i_begin + il;
     const uint64_t x = gl::mul(pow_lookup(gN, i), offset);  // domain.get_ce_x_at, domain.rs:101-103
     uint64_t acc = 0;
     for (int k = 0; k < ds.n; k++) {
@@ -537,13 +544,15 @@ __global__ void __launch_bounds__(256) constraint_combine_kernel(const uint64_t 
     combined[i] = acc;
 }
 void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDev *divs, int ndiv, int logN,
-                        uint64_t offset, PowTable gN, uint64_t *combined, cudaStream_t s) {
+                        uint64_t offset, PowTable gN, uint32_t i_begin, uint32_t i_count, uint64_t *combined,
+                        cudaStream_t s) {
+    (void)logN;
     DivisorSet ds;
     ds.n = ndiv;
     for (int i = 0; i < ndiv; i++) ds.d[i] = divs[i];
-    const uint32_t N = 1u << logN;
+    if (!i_count) return;
     AERO_COUNT_LAUNCH(1);
-    constraint_combine_kernel<<<(N + 255) / 256, 256, 0, s>>>(cols, col_stride, ds, N, offset, gN, combined);
+    constraint_combine_kernel<<<(i_count + 255) / 256, 256, 0, s>>>(cols, col_stride, ds, i_begin, i_count, offset, gN, combined);
 }
 
 }  // namespace aero

@@ -327,9 +327,9 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
     // Host inputs that are already known (no callback produces them) start travelling now: their copies
     // queue behind the main segment's own and land while its columns are being extended and hashed.
     if (!in.inputs_on_device) {
-        // (a sharded proof uploads only the trace columns this rank interpolates)
-        if (in.aux_width && !in.aux_builder) P_TRY(aero_upload_start(ctx, in.aux_cols, in.aux_width, n, 1, sharded, &H.up_aux));
-        if (!in.constraint_evaluator) P_TRY(aero_upload_start(ctx, in.ce_cols, in.n_div, CE, 1, 0, &H.up_ce));
+        // (a sharded proof uploads only what this rank reads: its trace columns, its rows of the constraint evaluations)
+        if (in.aux_width && !in.aux_builder) P_TRY(aero_upload_start(ctx, in.aux_cols, in.aux_width, n, 1, AERO_UPLOAD_OWN_COLUMNS, &H.up_aux));
+        if (!in.constraint_evaluator) P_TRY(aero_upload_start(ctx, in.ce_cols, in.n_div, CE, 1, AERO_UPLOAD_OWN_ROWS, &H.up_ce));
     }
 
     // 1 ----- commit to the execution trace (lib.rs:239-248, 269-348)

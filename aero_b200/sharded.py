@@ -37,11 +37,13 @@ def leaf_block_owner(leaf: int, world: int, n_leaves: int) -> int:
 
 
 def window_bytes(log_rows: int, trace_cols: int, world: int, blowup: int = 8) -> int:
-    """Exchange-window size for a proof: coefficient matrices of the trace segments, three leaf blocks,
-    the DEEP evaluations, opening results and slack (include/aero_b200.h)."""
+    """Exchange-window size for a proof (include/aero_b200.h): coefficient matrices of the trace segments,
+    three leaf blocks, the combined constraint evaluations, the three DEEP accumulators, the DEEP
+    evaluations, OOD / opening results and slack.  The window is a bump heap that is reset when the last
+    buffer of a proof is released, so everything a proof ever allocates in it counts."""
     n = 1 << log_rows
     N = n * blowup
-    return 8 * n * trace_cols + 3 * 32 * (N // world) + 8 * N + (8 << 20)
+    return 8 * n * trace_cols + 3 * 32 * (N // world) + 8 * N + 3 * 8 * n + 8 * N + (16 << 20)
 
 
 def all_gather_handles(handle: bytes, group=None, device: str = "cpu") -> List[bytes]:

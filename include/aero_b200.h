@@ -127,8 +127,10 @@ aero_status aero_segment_commit_device(aero_ctx *ctx, const uint64_t *d_cols, si
  * everywhere, mapped by every peer -- over CUDA IPC between processes (aero_ctx_window_attach; the
  * caller all-gathers the 64-byte handles with any transport), directly inside one process
  * (aero_ctx_window_attach_local; include/aero_prover.h wraps this as aero_group_*).  Buffers other ranks
- * write into are bump-allocated inside the window, at the same offset on every rank.  Size: about
- * 8*n*(all trace columns) + 3 * 32*N/G + 8*N + 4 MiB for a proof (n rows, N = B*n).
+ * write into are bump-allocated inside the window, at the same offset on every rank.  Size for a proof
+ * of n rows (N = B*n): 8*n*(all trace columns) for the coefficients + 3 * 32*N/G for the leaf blocks +
+ * 8*N combined constraint evaluations + 24*n DEEP accumulators + 8*N DEEP evaluations + 16 MiB
+ * (aero_b200/sharded.py window_bytes).
  * Barriers between the ranks are stream-ordered flag barriers on the device (a rank that never arrives
  * is reported as AERO_ERR_STATE after ~4 s instead of hanging).  The first proof of a shape on a context
  * still calls cudaMalloc, which can block on a peer that already spins in such a barrier (the caveat
@@ -255,13 +257,17 @@ aero_status aero_device_sync(aero_ctx *ctx);
  * context's copy stream, so that it lands while earlier phases compute: e.g. the auxiliary segment and
  * the constraint evaluations of Prover::prove travel under the main segment's NTTs.  defer != 0 queues
  * the copies behind the uploads of the next aero_segment_commit instead of ahead of them.
- * own_columns_only != 0: a sharded context copies only the columns it will interpolate itself (the matrix
- * must then be consumed by aero_segment_commit_device, which reads exactly those).
+ * shard_mode: what a sharded context copies -- AERO_UPLOAD_OWN_COLUMNS: only the columns it interpolates itself
+ * (for a trace matrix consumed by aero_segment_commit_device, which reads exactly those);
+ * AERO_UPLOAD_OWN_ROWS: only its block of rows [rank*n_rows/G, (rank+1)*n_rows/G) of every column (for the
+ * constraint evaluations consumed by aero_constraints_into_poly_device, likewise); the rest of the device
+ * matrix stays unwritten.  AERO_UPLOAD_ALL (and any mode on an unsharded context) copies everything.
  * aero_upload_wait orders the context's stream after the copy and returns the device matrix (column c
  * at d_cols + c*n_rows) for the *_device entry points.  The host columns must stay valid until
  * aero_upload_free, which also releases the device block. */
+enum { AERO_UPLOAD_ALL = 0, AERO_UPLOAD_OWN_COLUMNS = 1, AERO_UPLOAD_OWN_ROWS = 2 };
 aero_status aero_upload_start(aero_ctx *ctx, const uint64_t *const *cols, uint32_t n_cols, uint64_t n_rows, int defer,
-                              int own_columns_only, aero_upload **out);
+                              int shard_mode, aero_upload **out);
 aero_status aero_upload_wait(aero_upload *up, const uint64_t **d_cols);
 void aero_upload_free(aero_upload *up);
 
