@@ -114,6 +114,8 @@ PROTOTYPES = {
     "aero_fri_commit_layer": (c_int, [c_void_p, p_u8]),
     "aero_fri_fold": (c_int, [c_void_p, c_uint64]),
     "aero_fri_build_layers": (c_int, [c_void_p, p_u8, c_uint32, p_u8, p_u64]),
+    "aero_fri_build_layers_grind": (c_int, [c_void_p, p_u8, c_uint32, c_uint32, p_u8, p_u64, p_u64]),
+    "aero_segments_roots": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, p_u8]),
     "aero_fri_open": (c_int, [c_void_p, p_u64, c_uint32, p_u8, POINTER(c_size_t)]),
     "aero_open_queries": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_uint32, p_u64, c_uint32, p_u8,
                                   POINTER(c_size_t), POINTER(p_u64), POINTER(p_u8), POINTER(c_size_t)]),

@@ -650,8 +650,9 @@ static aero_status segment_finish_tree(aero_segment *seg, uint8_t root[32]) {
     TRY(window_barrier(ctx));
     merkle_top(seg->top, G, ctx->stream);
     CUDA_TRY(ctx, cudaGetLastError());
+    // root == NULL: the caller collects the root later (aero_segments_roots), together with the barrier check
     if (root) return download_small_checked(ctx, root, seg->top + 8, 32);
-    return window_check(ctx);
+    return AERO_OK;
 }
 
 // ---- building blocks of a segment commitment ----------------------------------------------------
@@ -1722,6 +1723,23 @@ aero_status aero_segment_info(aero_segment *seg, uint32_t *n_cols, uint64_t *n_r
     if (blowup) *blowup = seg->log_blowup < 0 ? 0 : (1u << seg->log_blowup);
     return AERO_OK;
 }
+aero_status aero_segments_roots(aero_ctx *ctx, aero_segment *const *segs, uint32_t n_segs, uint8_t *roots_out) {
+    if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
+    if (!segs || !roots_out || !n_segs) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    void *h = nullptr;
+    TRY(ring_take(ctx, (size_t)n_segs * 32, &h));
+    for (uint32_t i = 0; i < n_segs; i++) {
+        if (!segs[i] || segs[i]->ctx != ctx || !segs[i]->top) CTX_FAIL(ctx, AERO_ERR_STATE, "segment %u has no commitment on this context", i);
+        CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t *)h + (size_t)i * 32, segs[i]->top + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    const unsigned int *word = nullptr;
+    TRY(window_check_queue(ctx, &word));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    TRY(window_check_result(ctx, word));
+    memcpy(roots_out, h, (size_t)n_segs * 32);
+    return AERO_OK;
+}
 aero_status aero_segment_commit_polys(aero_segment *seg, uint32_t blowup, uint8_t root[32]) {
     if (!seg) return AERO_ERR_INVALID;
     enter(seg->ctx);
@@ -2362,17 +2380,16 @@ aero_status aero_fri_fold(aero_fri *fri, uint64_t alpha) {
     return fri_fold_enqueue(fri, to_canon(fri->ctx, alpha), nullptr);
 }
 
-aero_status aero_fri_build_layers(aero_fri *fri, const uint8_t coin_seed[32], uint32_t num_layers, uint8_t *roots_out,
-                                  uint64_t *alphas_out) {
-    if (!fri) return AERO_ERR_INVALID;
+static aero_status fri_build_layers_impl(aero_fri *fri, const uint8_t coin_seed[32], uint32_t num_layers, int grinding_bits,
+                                        uint8_t *roots_out, uint64_t *alphas_out, uint64_t *nonce_out) {
     aero_ctx *ctx = fri->ctx;
-    enter(ctx);
     if (!coin_seed || !roots_out || !alphas_out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
     if (!fri->layers.empty() || fri->cur_committed) CTX_FAIL(ctx, AERO_ERR_STATE, "FRI layers have already been built");
     if (num_layers > 32) CTX_FAIL(ctx, AERO_ERR_INVALID, "too many FRI layers");
+    if (grinding_bits > 40) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "grinding factor above 40 bits");
     const uint32_t nl = num_layers + 1;  // + the remainder commitment
-    // staging layout (host mirror at the same offsets): seed[32] | roots[nl][32] | alphas[nl]
-    const size_t off_roots = 32, off_alpha = 32 + (size_t)nl * 32, total = off_alpha + (size_t)nl * 8;
+    // staging layout (host mirror at the same offsets): seed[32] | roots[nl][32] | alphas[nl] | nonce
+    const size_t off_roots = 32, off_alpha = 32 + (size_t)nl * 32, off_nonce = off_alpha + (size_t)nl * 8, total = off_nonce + 8;
     TRY(stage_reserve(ctx, total));
     memcpy(ctx->h_stage, coin_seed, 32);
     uint8_t *d = ctx->d_stage;
@@ -2384,6 +2401,16 @@ aero_status aero_fri_build_layers(aero_fri *fri, const uint8_t coin_seed[32], ui
         // the reference also draws a challenge for the remainder layer and discards the fold (prover/mod.rs:174-183)
         if (l < num_layers) TRY(fri_fold_enqueue(fri, 0, d_alpha));
     }
+    // Grinding rides on the same round trip: the coin's seed after the last layer is already on the device
+    // (draws never move it).  One batch of 2^18 nonces finds a 16-bit nonce with probability 98 %; the
+    // ascending batches below keep the result the MINIMUM nonce, like the reference's serial search.
+    const uint32_t batch = 1u << 18;
+    unsigned long long *d_best = (unsigned long long *)(d + off_nonce);
+    if (grinding_bits >= 0) {
+        PhaseTimer t(ctx, "grind");
+        CUDA_TRY(ctx, cudaMemsetAsync(d_best, 0xFF, 8, ctx->stream));
+        pow_search((const uint32_t *)d, 1, batch, (uint32_t)grinding_bits, d_best, ctx->stream);
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_stage + off_roots, d + off_roots, total - off_roots, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaGetLastError());
@@ -2393,7 +2420,28 @@ aero_status aero_fri_build_layers(aero_fri *fri, const uint8_t coin_seed[32], ui
         if (al[l] == ~0ULL) CTX_FAIL(ctx, AERO_ERR_STATE, "failed to draw a FRI challenge for layer %u", l);
         alphas_out[l] = from_canon(ctx, al[l]);
     }
+    if (grinding_bits >= 0) {
+        unsigned long long best = *(const unsigned long long *)(ctx->h_stage + off_nonce);
+        for (uint64_t base = 1 + batch; best == ~0ULL; base += batch) {
+            pow_search((const uint32_t *)d, base, batch, (uint32_t)grinding_bits, d_best, ctx->stream);
+            TRY(download_small(ctx, &best, d_best, 8));
+        }
+        *nonce_out = best;
+    }
     return AERO_OK;
+}
+aero_status aero_fri_build_layers(aero_fri *fri, const uint8_t coin_seed[32], uint32_t num_layers, uint8_t *roots_out,
+                                  uint64_t *alphas_out) {
+    if (!fri) return AERO_ERR_INVALID;
+    enter(fri->ctx);
+    return fri_build_layers_impl(fri, coin_seed, num_layers, -1, roots_out, alphas_out, nullptr);
+}
+aero_status aero_fri_build_layers_grind(aero_fri *fri, const uint8_t coin_seed[32], uint32_t num_layers, uint32_t grinding_bits,
+                                        uint8_t *roots_out, uint64_t *alphas_out, uint64_t *nonce_out) {
+    if (!fri) return AERO_ERR_INVALID;
+    enter(fri->ctx);
+    if (!nonce_out) CTX_FAIL(fri->ctx, AERO_ERR_INVALID, "null argument");
+    return fri_build_layers_impl(fri, coin_seed, num_layers, (int)grinding_bits, roots_out, alphas_out, nonce_out);
 }
 
 aero_status aero_fri_open(aero_fri *fri, const uint64_t *positions, uint32_t n_pos, uint8_t *out_bytes, size_t *len) {

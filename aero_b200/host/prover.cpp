@@ -207,6 +207,13 @@ void ProverChannel::commit_fri_layer(const Digest &root) {
     put_bytes(commitments_, root);
     coin_.reseed(root);
 }
+aero_status ProverChannel::set_pow_nonce(uint64_t nonce) {
+    // the nonce came from the device-side search seeded with the device coin: it must satisfy the host coin too
+    if (coin_.check_leading_zeros(nonce) < options_.o.grinding_factor) return AERO_ERR_STATE;
+    pow_nonce_ = nonce;
+    coin_.reseed_with_int(nonce);
+    return AERO_OK;
+}
 aero_status ProverChannel::grind_query_seed() {
     uint64_t nonce = 0;
     aero_status st = aero_pow_min_nonce(ctx_, coin_.seed().data(), options_.o.grinding_factor, &nonce);
@@ -323,6 +330,11 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
     Handles H;
     ProverChannel channel(ctx, in);
     uint8_t root[32];
+    // Nothing on the device depends on a trace root before the OOD point is drawn unless a callback has to
+    // see the randomness in between: then the three commitments are queued back to back and their roots
+    // collected in ONE host round trip (aero_segments_roots), with the transcript replayed in order.
+    const bool defer_roots = !in.aux_builder && !in.constraint_evaluator;
+    uint8_t *root_now = defer_roots ? nullptr : root;
 
     // Host inputs that are already known (no callback produces them) start travelling now: their copies
     // queue behind the main segment's own and land while its columns are being extended and hashed.
@@ -335,16 +347,16 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
     // 1 ----- commit to the execution trace (lib.rs:239-248, 269-348)
     aero_segment *main_seg = nullptr;
     if (in.inputs_on_device)
-        P_TRY(aero_segment_commit_device(ctx, in.main_cols[0], n, in.main_width, n, o.blowup_factor, 0, &main_seg, root));
+        P_TRY(aero_segment_commit_device(ctx, in.main_cols[0], n, in.main_width, n, o.blowup_factor, 0, &main_seg, root_now));
     else
-        P_TRY(aero_segment_commit(ctx, in.main_cols, in.main_width, n, o.blowup_factor, 0, &main_seg, root));
+        P_TRY(aero_segment_commit(ctx, in.main_cols, in.main_width, n, o.blowup_factor, 0, &main_seg, root_now));
     H.segs.push_back(main_seg);
-    channel.commit_trace(Digest(root, root + 32));
+    if (!defer_roots) channel.commit_trace(Digest(root, root + 32));
 
     aero_segment *aux_seg = nullptr;
     if (in.aux_width) {
         std::vector<uint64_t> rand_elements;
-        if (!channel.draw_elements(in.aux_rands, &rand_elements)) P_FAIL(AERO_ERR_STATE, "failed to draw random elements");
+        if (!defer_roots && !channel.draw_elements(in.aux_rands, &rand_elements)) P_FAIL(AERO_ERR_STATE, "failed to draw random elements");
         std::vector<const uint64_t *> aux_ptrs(in.aux_width);
         const uint64_t *const *aux_cols = in.aux_cols;
         if (in.aux_builder) {
@@ -357,19 +369,19 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
         if (H.up_aux) {
             const uint64_t *d_aux = nullptr;
             P_TRY(aero_upload_wait(H.up_aux, &d_aux));
-            P_TRY(aero_segment_commit_device(ctx, d_aux, n, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root));
+            P_TRY(aero_segment_commit_device(ctx, d_aux, n, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root_now));
         } else if (in.inputs_on_device)
-            P_TRY(aero_segment_commit_device(ctx, aux_cols[0], n, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root));
+            P_TRY(aero_segment_commit_device(ctx, aux_cols[0], n, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root_now));
         else
-            P_TRY(aero_segment_commit(ctx, aux_cols, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root));
+            P_TRY(aero_segment_commit(ctx, aux_cols, in.aux_width, n, o.blowup_factor, 0, &aux_seg, root_now));
         H.segs.push_back(aux_seg);
-        channel.commit_trace(Digest(root, root + 32));
+        if (!defer_roots) channel.commit_trace(Digest(root, root + 32));
     }
 
     // 2 ----- evaluate constraints (lib.rs:350-382): coefficients are drawn here; evaluation itself
     // stays with the caller (reference Rust path) or is supplied precomputed.
     std::vector<uint64_t> coeffs;
-    if (!channel.draw_elements(in.n_constraint_coeffs, &coeffs)) P_FAIL(AERO_ERR_STATE, "failed to draw composition coefficients");
+    if (!defer_roots && !channel.draw_elements(in.n_constraint_coeffs, &coeffs)) P_FAIL(AERO_ERR_STATE, "failed to draw composition coefficients");
     std::vector<const uint64_t *> ce_ptrs(in.n_div);
     const uint64_t *const *ce_cols = in.ce_cols;
     std::vector<std::vector<uint64_t>> lde_host;
@@ -402,7 +414,18 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
         P_TRY(aero_constraints_into_poly(ctx, ce_cols, in.divisors, in.n_div, CE, n, &comp_seg));
     H.segs.push_back(comp_seg);
     lde_host.clear();
-    P_TRY(aero_segment_commit_polys(comp_seg, o.blowup_factor, root));
+    P_TRY(aero_segment_commit_polys(comp_seg, o.blowup_factor, root_now));
+    if (defer_roots) {  // replay: commit_trace, draw aux randomness, commit_trace, draw coefficients (draws never move the seed)
+        std::vector<uint8_t> roots(H.segs.size() * 32);
+        P_TRY(aero_segments_roots(ctx, H.segs.data(), (uint32_t)H.segs.size(), roots.data()));
+        std::vector<uint64_t> unused;
+        for (size_t i = 0; i + 1 < H.segs.size(); i++) {
+            if (i == 1 && !channel.draw_elements(in.aux_rands, &unused)) P_FAIL(AERO_ERR_STATE, "failed to draw random elements");
+            channel.commit_trace(Digest(roots.begin() + i * 32, roots.begin() + (i + 1) * 32));
+        }
+        if (!channel.draw_elements(in.n_constraint_coeffs, &unused)) P_FAIL(AERO_ERR_STATE, "failed to draw composition coefficients");
+        memcpy(root, roots.data() + (H.segs.size() - 1) * 32, 32);
+    }
     channel.commit_constraints(Digest(root, root + 32));
 
     // 4 ----- OOD frame + DEEP composition polynomial (lib.rs:421-467)
@@ -439,17 +462,20 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
         // between the kernels; the channel is replayed from the returned roots and must agree
         std::vector<uint8_t> roots((num_layers + 1) * 32);
         std::vector<uint64_t> alphas(num_layers + 1);
-        P_TRY(aero_fri_build_layers(H.fri, channel.coin().seed().data(), (uint32_t)num_layers, roots.data(), alphas.data()));
+        uint64_t nonce = 0;
+        // ... and the grinding search (channel.rs:151-167) queued right behind them, on the device coin's seed
+        P_TRY(aero_fri_build_layers_grind(H.fri, channel.coin().seed().data(), (uint32_t)num_layers, o.grinding_factor,
+                                          roots.data(), alphas.data(), &nonce));
         for (size_t l = 0; l < num_layers + 1; l++) {
             channel.commit_fri_layer(Digest(roots.begin() + l * 32, roots.begin() + (l + 1) * 32));
             uint64_t alpha;
             if (!channel.coin().draw(&alpha)) P_FAIL(AERO_ERR_STATE, "failed to draw FRI alpha");
             if (to_abi(alpha) != alphas[l]) P_FAIL(AERO_ERR_STATE, "device coin diverged from the channel's coin");
         }
+        // 7 ----- query positions (lib.rs:502-516)
+        if (channel.set_pow_nonce(nonce) != AERO_OK) P_FAIL(AERO_ERR_STATE, "device grinding nonce does not satisfy the channel's coin");
     }
 
-    // 7 ----- query positions (lib.rs:502-516)
-    P_TRY(channel.grind_query_seed());
     std::vector<uint64_t> positions;
     if (!channel.get_query_positions(&positions)) P_FAIL(AERO_ERR_STATE, "failed to draw query positions");
 

@@ -73,6 +73,7 @@ class ProverChannel {
     bool draw_elements(size_t n, std::vector<uint64_t> *out);                    // :104-134
     void commit_fri_layer(const Digest &root);                                   // :200-203
     aero_status grind_query_seed();                                              // :151-167 (GPU search)
+    aero_status set_pow_nonce(uint64_t nonce);                                   // same, nonce found with the FRI layers
     bool get_query_positions(std::vector<uint64_t> *out);                        // :140-146
     StarkProof build_proof(std::vector<Queries> trace_queries, Queries constraint_queries,
                            std::vector<uint8_t> fri_proof);                      // :173-194

@@ -103,7 +103,10 @@ const char *aero_version(void);
  * cols: n_cols host pointers to n_rows elements each.  root receives MerkleTree::root(). */
 aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint32_t n_cols, uint64_t n_rows,
                                 uint32_t blowup, int input_is_coeffs, aero_segment **out, uint8_t root[32]);
-/* Same with the matrix already resident in device memory (column c at d_cols + c*col_stride). */
+/* root may be NULL in every commit call: nothing is synchronised then and the root is collected later with
+ * aero_segments_roots -- one host round trip for several commitments whose roots the caller does not need
+ * in between (trace segments that do not depend on each other's randomness).
+ * Same with the matrix already resident in device memory (column c at d_cols + c*col_stride). */
 aero_status aero_segment_commit_device(aero_ctx *ctx, const uint64_t *d_cols, size_t col_stride, uint32_t n_cols,
                                        uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
                                        uint8_t root[32]);
@@ -151,6 +154,8 @@ aero_status aero_ctx_set_host_barrier(aero_ctx *ctx, aero_host_barrier_fn barrie
 aero_status aero_ctx_shard_begin(aero_ctx *ctx, const char *shape_key);
 aero_status aero_ctx_shard_end(aero_ctx *ctx, int ok);
 aero_status aero_window_barrier(aero_ctx *ctx);
+/* MerkleTree::root() of n_segs committed segments (roots_out: n_segs x 32 bytes), one synchronisation. */
+aero_status aero_segments_roots(aero_ctx *ctx, aero_segment *const *segs, uint32_t n_segs, uint8_t *roots_out);
 void aero_segment_destroy(aero_segment *seg);
 aero_status aero_segment_info(aero_segment *seg, uint32_t *n_cols, uint64_t *n_rows, uint32_t *blowup);
 /* Natural-order LDE columns (lde[c][k] = poly_c(7 * g_N^k), matrix.rs:189-201) for the host-side
@@ -214,6 +219,11 @@ aero_status aero_fri_fold(aero_fri *fri, uint64_t alpha);
  * the caller replays its own channel (reseed + draw per layer) and checks it agrees. */
 aero_status aero_fri_build_layers(aero_fri *fri, const uint8_t coin_seed[32], uint32_t num_layers, uint8_t *roots_out,
                                   uint64_t *alphas_out);
+/* The same plus ProverChannel::grind_query_seed (prover/src/channel.rs:151-167) in that round trip: the
+ * coin's seed after the last layer commitment is already on the device, so the search for the minimum
+ * nonce (aero_pow_min_nonce) is queued right behind the layers. */
+aero_status aero_fri_build_layers_grind(aero_fri *fri, const uint8_t coin_seed[32], uint32_t num_layers, uint32_t grinding_bits,
+                                        uint8_t *roots_out, uint64_t *alphas_out, uint64_t *nonce_out);
 /* FriProver::build_proof (fri/src/prover/mod.rs:231-275) in FriProof::write_into format
  * (fri/src/proof.rs:201-214,351-359); the last committed layer is the remainder. */
 aero_status aero_fri_open(aero_fri *fri, const uint64_t *positions, uint32_t n_pos, uint8_t *fri_proof_bytes,
