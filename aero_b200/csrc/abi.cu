@@ -49,14 +49,18 @@ struct aero_upload {
     bool queued = false;
 };
 
+constexpr int PUSH_PARTS = 4;
 struct aero_ctx {
     int device = 0;
     cudaStream_t stream = 0;
     cudaStream_t copy_stream = nullptr;  // host->device uploads overlapped with compute
     cudaStream_t hash_stream = nullptr;  // row hashing of batch k overlapped with the LDE of batch k+1
-    cudaStream_t push_stream = nullptr;  // coefficient pushes to the peers, beside the LDE of the columns already here
+    // coefficient pushes to the peers, beside the LDE of the columns already here: one copy engine moves
+    // ~280 GB/s over NVLink, so every block goes out as PUSH_PARTS pieces on as many streams
+    cudaStream_t push_stream[PUSH_PARTS] = {};
+    int push_parts = PUSH_PARTS;         // "push_parts": pieces actually used (ranks sharing a device run short of hardware queues)
     cudaEvent_t ev_push = nullptr;
-    unsigned long long push_epoch = 0;   // arrival flags of the coefficient exchange (window + 1024 + 8 * source rank)
+    unsigned long long push_epoch = 0;   // arrival flags: window + 1024 + 8 * (source rank * PUSH_PARTS + piece)
     cudaEvent_t ev_lde = nullptr, ev_hash = nullptr, ev_copy_order = nullptr;
     bool overlap_hash = false;           // aero_ctx_set_option("overlap_hash"); measured slower on B200, see DESIGN.md
     bool force_split_intt = false;       // test hook: take the B x size-n route of constraints_into_poly at any size
@@ -876,20 +880,24 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
         const int G = ctx->shard_world, me = ctx->shard_rank;
         const unsigned long long epoch = ++ctx->push_epoch;
         if (ce == cb) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_push, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->push_stream, ctx->ev_push, 0));
-        {
-            PhaseTimer t(ctx, "push_polys", ctx->push_stream, true);
+        const int parts = ctx->push_parts;
+        const size_t own_bytes = (size_t)(ce - cb) * n_rows * 8, piece = ((own_bytes / parts) + 15) & ~(size_t)15;
+        for (int part = 0; part < parts; part++) {
+            cudaStream_t ps = ctx->push_stream[part];
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ps, ctx->ev_push, 0));
+            PhaseTimer t(ctx, "push_polys", ps, true);
+            const size_t p0 = std::min(own_bytes, piece * part), p1 = part + 1 == parts ? own_bytes : std::min(own_bytes, piece * (part + 1));
             for (int k = 1; k < G; k++) {
                 const int dest = (me + k) % G;
-                peer_send(polys_all, me, dest, (size_t)cb * n_rows * 8, (size_t)(ce - cb) * n_rows * 8,
-                          (unsigned long long *)(ctx->win_base[dest] + 1024) + me, epoch, ctx->push_stream);
+                peer_send(polys_all, me, dest, (size_t)cb * n_rows * 8 + p0, p1 - p0,
+                          (unsigned long long *)(ctx->win_base[dest] + 1024) + me * PUSH_PARTS + part, epoch, ps);
             }
         }
         for (int k = 1; k < G; k++) {
             const int src = (me - k + G) % G;
             int lo = 0, hi = 0;
             columns_of_rank(ctx, src, (int)n_cols, &lo, &hi);
-            peer_wait((unsigned long long *)(ctx->win + 1024) + src, epoch, (unsigned int *)(ctx->win + 2048), ctx->stream);
+            peer_wait((unsigned long long *)(ctx->win + 1024) + src * PUSH_PARTS, parts, epoch, (unsigned int *)(ctx->win + 2048), ctx->stream);
             for (int c0 = lo; c0 < hi; c0 += lde_batch) segment_lde_batch(seg.get(), lplan, c0, std::min(lde_batch, hi - c0), tmp_l);
         }
         CUDA_TRY(ctx, cudaGetLastError());
@@ -1255,9 +1263,11 @@ void aero_ctx_destroy(aero_ctx *ctx) {
         cudaEventDestroy(ctx->ev_lde);
         cudaEventDestroy(ctx->ev_hash);
     }
-    if (ctx->push_stream) {
-        cudaStreamSynchronize(ctx->push_stream);
-        cudaStreamDestroy(ctx->push_stream);
+    if (ctx->push_stream[0]) {
+        for (cudaStream_t ps : ctx->push_stream) {
+            cudaStreamSynchronize(ps);
+            cudaStreamDestroy(ps);
+        }
         cudaEventDestroy(ctx->ev_push);
     }
     for (int r = 0; r < AERO_MAX_RANKS; r++)
@@ -1306,6 +1316,7 @@ aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value)
         }
     }
     else if (k == "force_host_sync") ctx->force_host_sync = value != 0;
+    else if (k == "push_parts" && value >= 1 && value <= PUSH_PARTS) ctx->push_parts = (int)value;
     else if (k == "force_split_intt") ctx->force_split_intt = value != 0;
     else if (k == "hash_blocks_per_sm" && value > 0) ctx->hash_blocks_per_sm = (int)value;
     else if (k == "lde_batch_bytes" && value > 0) ctx->lde_batch_bytes = (size_t)value;
@@ -1612,8 +1623,8 @@ aero_status aero_ctx_window_create(aero_ctx *ctx, size_t bytes, uint8_t handle_o
     return AERO_OK;
 }
 static aero_status ensure_push_stream(aero_ctx *ctx) {
-    if (!ctx->push_stream) {
-        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->push_stream, cudaStreamNonBlocking));
+    if (!ctx->push_stream[0]) {
+        for (cudaStream_t &ps : ctx->push_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_push, cudaEventDisableTiming));
         preload_exchange_kernels();
     }

@@ -106,15 +106,17 @@ __global__ void peer_flag_kernel(volatile unsigned long long *flag, unsigned lon
 }
 void peer_send(const RankPtrs &buf, int rank, int dest, size_t off, size_t bytes, unsigned long long *dest_flag,
                unsigned long long epoch, cudaStream_t s) {
-    // One destination at a time: the copy engines move the block at the NVLink rate (770 GB/s measured for a
-    // peer copy on this pool; a store kernel confined to a few blocks per SM reached 310) and leave every SM
-    // to the LDE running beside it.  The flag kernel starts when the copy has completed.
+    // One destination at a time, through a copy engine: every SM stays with the LDE running beside it.  The
+    // flag kernel starts when the copy has completed.
     AERO_COUNT_LAUNCH(1);
     if (bytes)
         cudaMemcpyAsync((uint8_t *)buf.p[dest] + off, (const uint8_t *)buf.p[rank] + off, bytes, cudaMemcpyDeviceToDevice, s);
     peer_flag_kernel<<<1, 1, 0, s>>>(dest_flag, epoch);
 }
-__global__ void peer_wait_kernel(const volatile unsigned long long *flag, unsigned long long epoch, unsigned int *d_timeout) {
+__global__ void peer_wait_kernel(const volatile unsigned long long *flag, int nflags, unsigned long long epoch,
+                                 unsigned int *d_timeout) {
+    if ((int)threadIdx.x >= nflags) return;
+    flag += threadIdx.x;
     const long long t0 = clock64();
     while (*flag < epoch) {
         if (clock64() - t0 > 8000000000LL) {
@@ -124,9 +126,9 @@ __global__ void peer_wait_kernel(const volatile unsigned long long *flag, unsign
     }
     __threadfence_system();
 }
-void peer_wait(const unsigned long long *flag, unsigned long long epoch, unsigned int *d_timeout, cudaStream_t s) {
+void peer_wait(const unsigned long long *flags, int nflags, unsigned long long epoch, unsigned int *d_timeout, cudaStream_t s) {
     AERO_COUNT_LAUNCH(1);
-    peer_wait_kernel<<<1, 1, 0, s>>>(flag, epoch, d_timeout);
+    peer_wait_kernel<<<1, 32, 0, s>>>(flags, nflags, epoch, d_timeout);
 }
 // The kernels of the device-side exchange are first LAUNCHED by the second proof of a shape, when the
 // peers may already be spinning in a barrier -- and with lazy module loading (the CUDA 12 default) a first

@@ -100,8 +100,8 @@ void peer_push_words(const RankPtrs &buf, int G, int rank, size_t first, size_t 
 // all stores of the first have completed) *dest_flag = epoch, the arrival flag the receiver polls
 void peer_send(const RankPtrs &buf, int rank, int dest, size_t off, size_t bytes, unsigned long long *dest_flag,
                unsigned long long epoch, cudaStream_t s);
-// spins until *flag >= epoch (one thread; ~4 s time-out counted in *d_timeout)
-void peer_wait(const unsigned long long *flag, unsigned long long epoch, unsigned int *d_timeout, cudaStream_t s);
+// spins until flags[0 .. nflags) >= epoch (nflags <= 32; ~4 s time-out counted in *d_timeout)
+void peer_wait(const unsigned long long *flags, int nflags, unsigned long long epoch, unsigned int *d_timeout, cudaStream_t s);
 // loads the exchange kernels (see hash.cu)
 void preload_exchange_kernels();
 // all ranks arrive (epoch) before any leaves: flags[r] of rank q's window is written by rank r

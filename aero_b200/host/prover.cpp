@@ -589,6 +589,9 @@ aero_status aero_group_create(const int *device_ids, int n_ranks, size_t window_
         if (st != AERO_OK) break;
         g->ctxs.push_back(c);
         st = aero_ctx_set_option(c, "own_stream", 1);
+        bool shared_device = false;  // ranks on one device: few streams each, there are only 32 hardware queues
+        for (int q = 0; q < n_ranks; q++) shared_device = shared_device || (q != r && device_ids[q] == device_ids[r]);
+        if (st == AERO_OK && shared_device) st = aero_ctx_set_option(c, "push_parts", 1);
         if (st == AERO_OK) st = aero_ctx_set_shard(c, r, n_ranks);
         if (st == AERO_OK && n_ranks > 1) st = aero_ctx_window_create(c, window_bytes, nullptr);
         if (st == AERO_OK) st = aero_ctx_set_host_barrier(c, group_host_barrier, g);

@@ -82,7 +82,8 @@ class ShardExchange:
 
     def attach(self, ctx) -> None:
         """Creates this rank's window on ``ctx``, all-gathers the IPC handles and maps the peers."""
-        if self._attached is ctx:
+        if self._attached is ctx:  # (the context may have proved unsharded in between)
+            ctx._check(ctx.lib.aero_ctx_set_shard(ctx.h, self.rank, self.world))
             return
         if self._attached is not None:
             raise RuntimeError("a ShardExchange serves one context")

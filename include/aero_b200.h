@@ -79,7 +79,9 @@ int aero_ctx_get_form(aero_ctx *ctx);
  *                     is then advanced by a running product); read when a plan is first built;
  *   "own_stream"      1: create a non-blocking stream for this context and launch on it (contexts that
  *                     share a device or a process must not meet on the legacy default stream);
- *   "force_host_sync" 1: sharded proofs keep host-synchronised barriers even for warm shapes (tests). */
+ *   "force_host_sync" 1: sharded proofs keep host-synchronised barriers even for warm shapes (tests);
+ *   "push_parts"      1..4 (default 4): copy streams a rank's coefficient block is split over when it is sent
+ *                     to a peer (one copy engine does not fill NVLink). */
 aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value);
 /* Used by the host driver layered above this ABI to report its own failures through aero_last_error. */
 void aero_ctx_set_error(aero_ctx *ctx, const char *msg);
