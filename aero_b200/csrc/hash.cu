@@ -36,7 +36,8 @@ __device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t h[8]) 
 // lets the row hash of one column batch run on a second stream while the next batch is extended.
 __global__ void __launch_bounds__(256) hash_rows_kernel(const uint64_t *__restrict__ lde, size_t col_stride, int c0,
                                                         int ncols, int total_cols, uint32_t nrows, int logn,
-                                                        uint32_t coset_begin, int log_nb, RankPtrs stage) {
+                                                        uint32_t coset_begin, int log_nb,
+                                                        const __grid_constant__ RankPtrs stage) {
     const uint32_t n_mask = (1u << logn) - 1, nb_mask = (1u << log_nb) - 1;
     const int nblocks = (ncols + 1) >> 1;
     const uint32_t blocks_before = (uint32_t)c0 >> 1;
