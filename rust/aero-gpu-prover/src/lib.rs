@@ -15,10 +15,21 @@
 //! size; `BaseElement` is a `u64` in Montgomery form (math/src/field/f64/mod.rs:56-61), which is the
 //! ABI's default element form, so `Matrix` columns are handed over without copy or conversion.
 //!
+//! Reference-side changes this crate needs are the five patches under `rust/patches/` (applied with
+//! `patch -p1` at the root of the Aero checkout; `tests/test_host_cpu.py` checks that they still apply
+//! to the reference sources and that every non-public item used below is one they export):
+//!   0001  `pub use trace::{TraceCommitment, TracePolyTable}` in winter-prover (they appear in the
+//!         signatures of the overridable provided methods but were crate-private);
+//!   0002  `MerkleTree::from_root`, 0003 `Queries::from_raw_parts`,
+//!   0004  `ConstraintEvaluationTable::into_raw_parts`,
+//!   0005  the `gpu` / `dump-fixture` features of miden-proof-generator.
+//!
 //! This file has not been compiled in the aero_b200 build image (no Rust toolchain there); the C++
 //! driver `aero_b200/host/prover.cpp` performs the identical call sequence and is what the parity
-//! tests exercise (`tests/test_gpu_parity.py::test_prove_byte_identical`).
+//! tests exercise (`tests/test_gpu_parity.py::test_prove_byte_identical`, and through the callbacks this
+//! crate's route takes, `::test_prove_callback_route_byte_identical`).
 
+pub mod dump;
 pub mod ffi;
 
 use std::ffi::CStr;
@@ -32,11 +43,19 @@ use winter_air::{Air, ProofOptions};
 use winter_crypto::{ElementHasher, MerkleTree};
 use winter_fri::FriProof;
 use winter_math::{FieldElement, StarkField};
+// ProverChannel is re-exported at the crate root (winterfell/prover/src/lib.rs:97-98); TraceCommitment and
+// TracePolyTable are exported by rust/patches/0001.
 use winter_prover::{
-    channel::ProverChannel, ConstraintEvaluationTable, Matrix, Prover, ProverError, StarkDomain,
-    TraceCommitment, TracePolyTable,
+    ConstraintEvaluationTable, Matrix, Prover, ProverChannel, ProverError, StarkDomain, TraceCommitment,
+    TracePolyTable,
 };
 use winter_utils::{Deserializable, SliceReader};
+
+/// A 32-byte GPU digest as the hasher's digest type (`Digest: Deserializable`,
+/// winterfell/crypto/src/hash/mod.rs:67-79; `ByteDigest::read_from` copies the bytes, :152-156).
+fn digest_from_bytes<D: Deserializable>(bytes: &[u8; 32]) -> D {
+    D::read_from(&mut SliceReader::new(bytes)).expect("32-byte digest")
+}
 
 /// Error text of the last failed call on `ctx` (aero_last_error).
 fn last_error(ctx: *mut ffi::aero_ctx) -> String {
@@ -168,7 +187,7 @@ impl Prover for GpuExecutionProver {
         let seg = Segment::commit(&self.ctx, trace, domain.trace_to_lde_blowup(), false);
         let lde = seg.lde(domain.lde_domain_size());
         let polys = seg.polys(trace.num_rows());
-        let tree = MerkleTree::<H>::from_root(seg.root, domain.lde_domain_size());
+        let tree = MerkleTree::<H>::from_root(digest_from_bytes(&seg.root), domain.lde_domain_size());
         self.segs.borrow_mut().push(seg);
         (lde, tree, polys)
     }
@@ -202,7 +221,7 @@ impl Prover for GpuExecutionProver {
         });
         check(ctx, unsafe { ffi::aero_segment_commit_polys(comp, air.options().blowup_factor() as u32, root.as_mut_ptr()) });
         segs.push(Segment { ctx, h: comp, root, width: air.context().num_constraint_composition_columns() });
-        channel.commit_constraints(H::Digest::from_bytes(root));
+        channel.commit_constraints(digest_from_bytes(&root));
 
         // OOD frame (trace/poly_table.rs:59-72, composition_poly.rs:93-96)
         let z: E = channel.get_ood_point();
@@ -230,7 +249,7 @@ impl Prover for GpuExecutionProver {
         let layers = air.options().to_fri_options().num_fri_layers(lde_size);
         for _ in 0..=layers {
             check(ctx, unsafe { ffi::aero_fri_commit_layer(fri, root.as_mut_ptr()) });
-            winter_fri::ProverChannel::commit_fri_layer(&mut channel, H::Digest::from_bytes(root));
+            winter_fri::ProverChannel::commit_fri_layer(&mut channel, digest_from_bytes(&root));
             let alpha: E = winter_fri::ProverChannel::draw_fri_alpha(&mut channel);
             check(ctx, unsafe { ffi::aero_fri_fold(fri, as_u64(alpha)) });
         }

@@ -123,3 +123,50 @@ def test_rust_shim_bindings_match_the_headers():
     ffi = open(os.path.join(ROOT, "rust", "aero-gpu-prover", "src", "ffi.rs")).read()
     for name in _lib.PROTOTYPES:
         assert "pub fn %s(" % name in ffi, "%s is not bound in ffi.rs" % name
+
+
+def test_rust_patches_apply_and_export_what_the_shim_uses(tmp_path):
+    """rust/patches/*.patch are the complete reference-side change set of the shim crate: they apply to the
+    reference sources, and every item the crate imports from winter-prover or calls on a winterfell type is
+    public after them (the crate itself cannot be compiled here: no Rust toolchain)."""
+    import re
+    import shutil
+    import subprocess
+
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "winterfell")):
+        pytest.skip("reference checkout not present on this box")
+    patches = sorted(os.listdir(os.path.join(ROOT, "rust", "patches")))
+    assert [p[:4] for p in patches] == ["0001", "0002", "0003", "0004", "0005"]
+    touched = set()
+    for p in patches:
+        for line in open(os.path.join(ROOT, "rust", "patches", p)):
+            if line.startswith("+++ b/"):
+                touched.add(line[6:].strip())
+    for rel in touched:  # a private copy of exactly the files the patches touch
+        os.makedirs(os.path.dirname(tmp_path / rel), exist_ok=True)
+        shutil.copy(os.path.join(ref, rel), tmp_path / rel)
+    for p in patches:
+        r = subprocess.run(["patch", "-p1", "--forward", "-i", os.path.join(ROOT, "rust", "patches", p)], cwd=tmp_path,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, "%s does not apply: %s" % (p, r.stdout + r.stderr)
+    prover_lib = open(tmp_path / "winterfell/prover/src/lib.rs").read()
+    exported = set()
+    for m in re.finditer(r"pub use [\w:]+::\{([^}]*)\};|pub use [\w:]+::(\w+);", prover_lib):
+        exported |= {x.strip() for x in (m.group(1) or m.group(2)).split(",") if x.strip()}
+    exported |= set(re.findall(r"^pub (?:trait|struct|enum|fn) (\w+)", prover_lib, flags=re.M))  # defined in lib.rs itself
+    shim = "".join(open(os.path.join(ROOT, "rust", "aero-gpu-prover", "src", f)).read() for f in ("lib.rs", "dump.rs"))
+    imported = set()
+    for m in re.finditer(r"use winter_prover::\{([^}]*)\};", shim):
+        imported |= {x.strip() for x in m.group(1).split(",") if x.strip()}
+    assert imported and "channel::ProverChannel" not in imported
+    assert imported <= exported, "not exported by winter-prover: %s" % sorted(imported - exported)
+    # constructors / accessors the shim calls that the reference does not have without the patches
+    for name, rel in (("from_root", "winterfell/crypto/src/merkle/mod.rs"), ("from_raw_parts", "winterfell/air/src/proof/queries.rs"),
+                      ("into_raw_parts", "winterfell/prover/src/constraints/evaluation_table.rs"),
+                      ("divisors", "winterfell/prover/src/constraints/evaluation_table.rs")):
+        assert re.search(r"pub fn %s\b" % name, open(tmp_path / rel).read()), name
+        assert ("%s(" % name) in shim
+        assert not re.search(r"pub fn %s\b" % name, open(os.path.join(ref, rel)).read()), "%s exists upstream: drop the patch" % name
+    main_rs = open(tmp_path / "miden-proof-generator/src/main.rs").read()
+    assert "GpuExecutionProver::new(inner, 0)" in main_rs and "DumpingProver::new(inner" in main_rs
