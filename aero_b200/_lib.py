@@ -120,6 +120,11 @@ PROTOTYPES = {
     "aero_open_queries": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_uint32, p_u64, c_uint32, p_u8,
                                   POINTER(c_size_t), POINTER(p_u64), POINTER(p_u8), POINTER(c_size_t)]),
     "aero_fri_destroy": (None, [c_void_p]),
+    # auxiliary-segment construction
+    "aero_running_product_columns": (c_int, [c_void_p, pp_u64, p_u64, c_uint32, c_uint64, pp_u64]),
+    "aero_running_product_columns_device": (c_int, [c_void_p, c_void_p, c_size_t, p_u64, c_uint32, c_uint64, c_void_p,
+                                                    c_size_t]),
+    "aero_batch_inverse": (c_int, [c_void_p, p_u64, c_uint64, p_u64]),
     # grinding
     "aero_pow_min_nonce": (c_int, [c_void_p, p_u8, c_uint32, p_u64]),
     # standalone

@@ -9,6 +9,7 @@
 #include <memory>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/aero_b200.h"
@@ -117,6 +118,10 @@ struct aero_ctx {
     // the barrier is waiting for when several ranks share a process; pinned copies just queue.
     uint8_t *h_ring = nullptr;
     size_t ring_bytes = 0, ring_off = 0;
+    // two pinned slots for bulk transfers whose host side is pageable (aero_segment_download_lde)
+    uint8_t *h_bulk[2] = {nullptr, nullptr};
+    size_t bulk_bytes = 0;
+    cudaEvent_t ev_bulk[2] = {nullptr, nullptr};
 };
 
 #define CTX_FAIL(ctx, code, ...)                         \
@@ -275,6 +280,10 @@ static aero_status ring_take(aero_ctx *ctx, size_t bytes, void **out) {
     if (!ctx->h_ring || bytes > ctx->ring_bytes) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->h_bulk[i]) cudaFreeHost(ctx->h_bulk[i]);
+        if (ctx->ev_bulk[i]) cudaEventDestroy(ctx->ev_bulk[i]);
+    }
         ctx->h_ring = nullptr;
         ctx->ring_bytes = std::max(RING_BYTES, 2 * bytes);
         CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_ring, ctx->ring_bytes));
@@ -301,6 +310,33 @@ static aero_status upload_small(aero_ctx *ctx, void *d_dst, const void *src, siz
     memcpy(h, src, bytes);
     CUDA_TRY(ctx, cudaMemcpyAsync(d_dst, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return AERO_OK;
+}
+
+// host copy split over a few threads: one thread moves ~10 GB/s, PCIe 5 x16 ~55 GB/s
+static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = bytes < ((size_t)4 << 20) ? 1 : std::min<size_t>(std::min<unsigned>(8, hw), bytes >> 21);
+    if (nt <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++) {
+        const size_t a = std::min(bytes, per * t), b = t + 1 == nt ? bytes : std::min(bytes, per * (t + 1));
+        if (b > a) th.emplace_back([=] { memcpy((uint8_t *)dst + a, (const uint8_t *)src + a, b - a); });
+    }
+    for (auto &t : th) t.join();
+}
+// is this host pointer page-locked (cudaMallocHost / cudaHostRegister)?  Async copies from or to pageable
+// memory are staged by the driver and block the caller.
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
 }
 
 // Pinned host / device staging pair for small result downloads (OOD frame, openings): results land
@@ -1758,6 +1794,24 @@ aero_status aero_segment_commit_polys(aero_segment *seg, uint32_t blowup, uint8_
     return segment_extend_commit(seg, ilog2(blowup), root);
 }
 
+static aero_status bulk_reserve(aero_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->bulk_bytes) return AERO_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 2; i++) {
+        if (ctx->h_bulk[i]) cudaFreeHost(ctx->h_bulk[i]);
+        ctx->h_bulk[i] = nullptr;
+        if (!ctx->ev_bulk[i]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_bulk[i], cudaEventDisableTiming));
+    }
+    ctx->bulk_bytes = 0;
+    for (int i = 0; i < 2; i++) CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_bulk[i], bytes));
+    ctx->bulk_bytes = bytes;
+    return AERO_OK;
+}
+// The extended trace for the host-side AIR evaluator: 8 * N bytes per column, 5.4 GB for a 2^20-row Miden
+// trace -- the transfer that dominates a real proof once the rest of the path is on the GPU.
+// Columns are converted to natural order two at a time into alternating device buffers; page-locked
+// destinations receive them directly; pageable ones (a Rust Vec) through two pinned slots, the host copy of
+// column c (split over threads) running under the PCIe transfer of column c + 1.
 aero_status aero_segment_download_lde(aero_segment *seg, uint64_t *const *cols_out) {
     if (!seg || !cols_out) return AERO_ERR_INVALID;
     aero_ctx *ctx = seg->ctx;
@@ -1765,15 +1819,50 @@ aero_status aero_segment_download_lde(aero_segment *seg, uint64_t *const *cols_o
     if (!seg->lde) CTX_FAIL(ctx, AERO_ERR_STATE, "segment has no LDE");
     if (seg->coset_count != (1 << seg->log_blowup)) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "download_lde on a coset-sharded segment");
     const uint64_t N = seg->N();
+    const size_t col_bytes = N * 8;
+    for (int c = 0; c < seg->ncols; c++)
+        if (!cols_out[c]) CTX_FAIL(ctx, AERO_ERR_INVALID, "null column %d", c);
     PhaseTimer t(ctx, "download_lde");
     DevBlocks blk(ctx);
-    uint64_t *tmp = nullptr;
-    TRY(blk.alloc((void **)&tmp, N * 8));
-    for (int c = 0; c < seg->ncols; c++) {
-        lde_to_natural(seg->lde + (size_t)c * N, tmp, seg->logn, seg->log_blowup, ctx->form == AERO_FORM_MONTGOMERY, ctx->stream);
-        CUDA_TRY(ctx, cudaMemcpyAsync(cols_out[c], tmp, N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    uint64_t *tmp[2] = {nullptr, nullptr};
+    TRY(blk.alloc((void **)&tmp[0], col_bytes));
+    TRY(blk.alloc((void **)&tmp[1], col_bytes));
+    bool all_pinned = true;
+    for (int c = 0; c < seg->ncols; c++) all_pinned = all_pinned && host_is_pinned(cols_out[c]);
+    if (!all_pinned) TRY(bulk_reserve(ctx, col_bytes));
+    TRY(ensure_copy_stream(ctx));
+    // conversion kernels on the compute stream, transfers on the copy stream: ev_conv[s] = slot s converted,
+    // ev_bulk[s] = slot s transferred (device buffer and pinned slot free again)
+    cudaEvent_t ev_conv[2];
+    for (auto &e : ev_conv) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!ctx->ev_bulk[0])
+        for (int i = 0; i < 2; i++) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_bulk[i], cudaEventDisableTiming));
+    aero_status st = AERO_OK;
+    const bool mont = ctx->form == AERO_FORM_MONTGOMERY;
+    for (int c = 0; c <= seg->ncols && st == AERO_OK; c++) {
+        const int s = c & 1;
+        if (c < seg->ncols) {
+            if (c >= 2) {  // slot s last served column c - 2: its transfer must be over, and (pageable) copied out
+                if (cudaStreamWaitEvent(ctx->stream, ctx->ev_bulk[s], 0) != cudaSuccess) st = AERO_ERR_CUDA;
+            }
+            lde_to_natural(seg->lde + (size_t)c * N, tmp[s], seg->logn, seg->log_blowup, mont, ctx->stream);
+            cudaEventRecord(ev_conv[s], ctx->stream);
+            cudaStreamWaitEvent(ctx->copy_stream, ev_conv[s], 0);
+        }
+        if (c < seg->ncols) {  // (pinned slot s is free: column c - 2 was copied out of it in the previous iteration)
+            void *dst = all_pinned ? (void *)cols_out[c] : (void *)ctx->h_bulk[s];
+            if (cudaMemcpyAsync(dst, tmp[s], col_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream) != cudaSuccess) st = AERO_ERR_CUDA;
+            cudaEventRecord(ctx->ev_bulk[s], ctx->copy_stream);
+        }
+        if (!all_pinned && c >= 1) {  // column c - 1 has arrived in the other slot: copy it out under column c's transfer
+            const int p = (c - 1) & 1;
+            if (cudaEventSynchronize(ctx->ev_bulk[p]) != cudaSuccess) st = AERO_ERR_CUDA;
+            parallel_memcpy(cols_out[c - 1], ctx->h_bulk[p], col_bytes);
+        }
     }
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = AERO_ERR_CUDA;
+    for (auto &e : ev_conv) cudaEventDestroy(e);
+    if (st != AERO_OK) CTX_FAIL(ctx, st, "download_lde: %s", cudaGetErrorString(cudaGetLastError()));
     return AERO_OK;
 }
 aero_status aero_segment_download_polys(aero_segment *seg, uint64_t *const *cols_out) {
@@ -2475,6 +2564,63 @@ void aero_fri_destroy(aero_fri *fri) {
     }
     if (!cur_owned_by_layer) dev_free(fri->ctx, fri->cur);
     delete fri;
+}
+
+// ---- auxiliary-segment construction (running-product columns) -------------------------------------
+aero_status aero_running_product_columns_device(aero_ctx *ctx, const uint64_t *d_multiplicands, size_t m_stride,
+                                                const uint64_t *init, uint32_t n_cols, uint64_t n_rows, uint64_t *d_out,
+                                                size_t out_stride) {
+    if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
+    if (!d_multiplicands || !init || !d_out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (n_cols == 0 || n_cols > 255 || n_rows < 2) CTX_FAIL(ctx, AERO_ERR_INVALID, "need 1..255 columns of at least two rows");
+    if (m_stride + 1 < n_rows || out_stride < n_rows) CTX_FAIL(ctx, AERO_ERR_INVALID, "column stride smaller than the number of rows");
+    DevBlocks blk(ctx);
+    uint64_t *scr = nullptr, *d_init = nullptr;
+    TRY(blk.alloc((void **)&scr, running_product_scratch_elems((int)n_cols, n_rows) * 8));
+    TRY(blk.alloc((void **)&d_init, (size_t)n_cols * 8));
+    TRY(upload_small(ctx, d_init, init, (size_t)n_cols * 8));
+    PhaseTimer t(ctx, "aux_running_product");
+    running_product(d_multiplicands, m_stride, d_init, (int)n_cols, n_rows, ctx->form == AERO_FORM_MONTGOMERY, d_out, out_stride,
+                    scr, ctx->stream);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return AERO_OK;
+}
+aero_status aero_running_product_columns(aero_ctx *ctx, const uint64_t *const *multiplicands, const uint64_t *init,
+                                         uint32_t n_cols, uint64_t n_rows, uint64_t *const *cols_out) {
+    if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
+    if (!multiplicands || !init || !cols_out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (n_cols == 0 || n_cols > 255 || n_rows < 2) CTX_FAIL(ctx, AERO_ERR_INVALID, "need 1..255 columns of at least two rows");
+    DevBlocks blk(ctx);
+    uint64_t *d_m = nullptr, *d_o = nullptr;
+    TRY(blk.alloc((void **)&d_m, (size_t)n_cols * n_rows * 8));
+    TRY(blk.alloc((void **)&d_o, (size_t)n_cols * n_rows * 8));
+    for (uint32_t c = 0; c < n_cols; c++) {
+        if (!multiplicands[c] || !cols_out[c]) CTX_FAIL(ctx, AERO_ERR_INVALID, "null column %u", c);
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_m + (size_t)c * n_rows, multiplicands[c], (n_rows - 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    TRY(aero_running_product_columns_device(ctx, d_m, n_rows, init, n_cols, n_rows, d_o, n_rows));
+    for (uint32_t c = 0; c < n_cols; c++)
+        CUDA_TRY(ctx, cudaMemcpyAsync(cols_out[c], d_o + (size_t)c * n_rows, n_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return AERO_OK;
+}
+aero_status aero_batch_inverse(aero_ctx *ctx, const uint64_t *values, uint64_t count, uint64_t *out) {
+    if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
+    if (!values || !out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (!count) return AERO_OK;
+    DevBlocks blk(ctx);
+    uint64_t *d_v = nullptr, *d_o = nullptr;
+    TRY(blk.alloc((void **)&d_v, count * 8));
+    TRY(blk.alloc((void **)&d_o, count * 8));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_v, values, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    batch_inverse(d_v, count, ctx->form == AERO_FORM_MONTGOMERY, d_o, ctx->stream);
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, d_o, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return AERO_OK;
 }
 
 // ---- grinding -------------------------------------------------------------------------------

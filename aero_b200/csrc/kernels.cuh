@@ -161,6 +161,12 @@ void gather_fri_rows(const uint64_t *f, uint32_t rows, int log_cosets, const uin
                      uint64_t *d_out, cudaStream_t s);
 void gather_digests(const uint32_t *full, const uint32_t *d_idx, int count, uint32_t *d_out, cudaStream_t s);
 
+// running-product columns and batch inversion (poly.cu)
+size_t running_product_scratch_elems(int ncols, uint64_t n);
+void running_product(const uint64_t *m, size_t m_stride, const uint64_t *d_init, int ncols, uint64_t n, int montgomery,
+                     uint64_t *out, size_t out_stride, uint64_t *scratch, cudaStream_t s);
+void batch_inverse(const uint64_t *v, uint64_t count, int montgomery, uint64_t *out, cudaStream_t s);
+
 struct DivisorDev {
     uint64_t a;            // numerator degree: (x^a - b)
     uint64_t b;

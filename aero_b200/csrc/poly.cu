@@ -396,6 +396,131 @@ void deep_finish(const uint64_t *t1, const uint64_t *t2, const uint64_t *h, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Running-product auxiliary columns.  Every auxiliary column of the Miden trace is
+//   col[0] = init,  col[i + 1] = col[i] * m[i]
+// with m[i] the multiplicand of the table update at row i, 1 where nothing happens
+// (miden/processor/src/trace/utils.rs:153-199 build_aux_column; decoder / stack / range / hasher / chiplets
+// columns all go through it, processor/src/trace/mod.rs:188-249): an exclusive prefix product, done here as
+// a blocked scan -- chunk products, a carry per chunk, then the prefix inside each chunk.
+// ---------------------------------------------------------------------------------------------
+constexpr int RP_T = 256, RP_L = 16;  // threads per block, rows per thread: chunks of 4096 rows
+// exclusive scan (product) of one value per thread; returns this thread's prefix, *total = block product
+__device__ __forceinline__ uint64_t block_exclusive_product(uint64_t v, uint64_t *sm /* RP_T */, uint64_t *total) {
+    const int t = threadIdx.x;
+    sm[t] = v;
+    __syncthreads();
+    for (int d = 1; d < RP_T; d <<= 1) {
+        const uint64_t x = t >= d ? gl::mul(sm[t], sm[t - d]) : sm[t];
+        __syncthreads();
+        sm[t] = x;
+        __syncthreads();
+    }
+    const uint64_t excl = t ? sm[t - 1] : 1ULL;
+    *total = sm[RP_T - 1];
+    __syncthreads();
+    return excl;
+}
+template <bool APPLY>
+__global__ void __launch_bounds__(RP_T) running_product_kernel(const uint64_t *__restrict__ m, size_t m_stride, uint64_t n,
+                                                               int mont, uint64_t *__restrict__ tot,
+                                                               const uint64_t *__restrict__ carry,
+                                                               uint64_t *__restrict__ out, size_t out_stride) {
+    __shared__ uint64_t sm[RP_T];
+    const int col = blockIdx.y, nchunks = gridDim.x;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * RP_T + threadIdx.x) * RP_L;
+    const uint64_t *mc = m + (size_t)col * m_stride;
+    uint64_t p[RP_L];  // p[l] = product of this thread's multiplicands before row i0 + l
+    uint64_t acc = 1;
+#pragma unroll
+    for (int l = 0; l < RP_L; l++) {
+        p[l] = acc;
+        const uint64_t i = i0 + l;
+        if (i + 1 < n) {  // the multiplicand of the last row is never used
+            uint64_t v = mc[i];
+            v = mont ? gl::mont_to_canon(v) : gl::canon(v);
+            acc = gl::mul(acc, v);
+        }
+    }
+    uint64_t total;
+    const uint64_t excl = block_exclusive_product(acc, sm, &total);
+    if (!APPLY) {
+        if (threadIdx.x == 0) tot[(size_t)col * nchunks + blockIdx.x] = total;
+        return;
+    }
+    const uint64_t base = gl::mul(carry[(size_t)col * nchunks + blockIdx.x], excl);
+    uint64_t *oc = out + (size_t)col * out_stride;
+#pragma unroll
+    for (int l = 0; l < RP_L; l++) {
+        const uint64_t i = i0 + l;
+        if (i < n) {
+            const uint64_t v = gl::mul(base, p[l]);
+            oc[i] = mont ? gl::canon_to_mont(v) : v;
+        }
+    }
+}
+// carry[col][chunk] = init[col] * prod_{ch' < chunk} tot[col][ch']  (one thread per column)
+__global__ void running_product_carry_kernel(const uint64_t *__restrict__ tot, const uint64_t *__restrict__ init, int mont,
+                                             int ncols, int nchunks, uint64_t *__restrict__ carry) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    uint64_t c = mont ? gl::mont_to_canon(init[col]) : gl::canon(init[col]);
+    for (int ch = 0; ch < nchunks; ch++) {
+        carry[(size_t)col * nchunks + ch] = c;
+        c = gl::mul(c, tot[(size_t)col * nchunks + ch]);
+    }
+}
+size_t running_product_scratch_elems(int ncols, uint64_t n) {
+    const uint64_t chunk = (uint64_t)RP_T * RP_L;
+    return (size_t)2 * ncols * ((n + chunk - 1) / chunk);
+}
+void running_product(const uint64_t *m, size_t m_stride, const uint64_t *d_init, int ncols, uint64_t n, int montgomery,
+                     uint64_t *out, size_t out_stride, uint64_t *scratch, cudaStream_t s) {
+    const uint64_t chunk = (uint64_t)RP_T * RP_L;
+    const int nchunks = (int)((n + chunk - 1) / chunk);
+    uint64_t *tot = scratch, *carry = scratch + (size_t)ncols * nchunks;
+    dim3 g(nchunks, ncols);
+    AERO_COUNT_LAUNCH(3);
+    running_product_kernel<false><<<g, RP_T, 0, s>>>(m, m_stride, n, montgomery, tot, carry, out, out_stride);
+    running_product_carry_kernel<<<(ncols + 31) / 32, 32, 0, s>>>(tot, d_init, montgomery, ncols, nchunks, carry);
+    running_product_kernel<true><<<g, RP_T, 0, s>>>(m, m_stride, n, montgomery, tot, carry, out, out_stride);
+}
+// out[i] = 1 / v[i], zero -> zero (math::batch_inversion, winterfell/math/src/utils/mod.rs:218-238; the lookup-table
+// row inverses of processor/src/trace/utils.rs:build_lookup_table_row_values are this over non-zero values)
+__global__ void __launch_bounds__(256) batch_inverse_kernel(const uint64_t *__restrict__ v_in, uint64_t count, int mont,
+                                                            uint64_t *__restrict__ out) {
+    constexpr int NB = 32;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * NB;
+    if (i0 >= count) return;
+    uint64_t v[NB], pre[NB];
+    uint64_t acc = 1;
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+        const uint64_t i = i0 + k;
+        v[k] = 0;
+        if (i < count) v[k] = mont ? gl::mont_to_canon(v_in[i]) : gl::canon(v_in[i]);
+        pre[k] = acc;
+        if (v[k]) acc = gl::mul(acc, v[k]);
+    }
+    acc = gl::inv(acc);
+#pragma unroll
+    for (int k = NB - 1; k >= 0; k--) {
+        const uint64_t i = i0 + k;
+        uint64_t r = 0;
+        if (v[k]) {
+            r = gl::mul(acc, pre[k]);
+            acc = gl::mul(acc, v[k]);
+        }
+        if (i < count) out[i] = mont ? gl::canon_to_mont(r) : r;
+    }
+}
+void batch_inverse(const uint64_t *v, uint64_t count, int montgomery, uint64_t *out, cudaStream_t s) {
+    if (!count) return;
+    const uint64_t threads = (count + 31) / 32;
+    AERO_COUNT_LAUNCH(1);
+    batch_inverse_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(v, count, montgomery, out);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K9: query gathers (prover/src/trace/commitment.rs:115-140, constraints/commitment.rs:54-70,
 // fri/src/prover/mod.rs:282-302, crypto/src/merkle/mod.rs:188-250 for the node list)
 // ---------------------------------------------------------------------------------------------

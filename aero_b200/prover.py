@@ -187,6 +187,22 @@ class Context:
                                                  out.ctypes.data_as(p_u64)))
         return out
 
+    def running_product_columns(self, multiplicands: np.ndarray, init: Sequence[int]) -> np.ndarray:
+        """build_aux_column for every column (processor/src/trace/utils.rs:153-199): (cols, n) multiplicands ->
+        (cols, n) running products starting at ``init``."""
+        m = np.ascontiguousarray(multiplicands, np.uint64)
+        out = np.empty_like(m)
+        ini = np.ascontiguousarray(np.array(list(init), np.uint64))
+        self._check(self.lib.aero_running_product_columns(self.h, _cols(m), ini.ctypes.data_as(p_u64), m.shape[0], m.shape[1],
+                                                          _cols(out)))
+        return out
+
+    def batch_inverse(self, values: np.ndarray) -> np.ndarray:
+        v = np.ascontiguousarray(values, np.uint64)
+        out = np.empty_like(v)
+        self._check(self.lib.aero_batch_inverse(self.h, v.ctypes.data_as(p_u64), v.size, out.ctypes.data_as(p_u64)))
+        return out
+
     def measure_alu_peak(self) -> float:
         """ALU-pipe issue rate of this GPU in lane-operations per second (aero_measure_alu_peak)."""
         out = ctypes.c_double()
@@ -398,8 +414,12 @@ class Segment:
         self.ctx._check(self.ctx.lib.aero_segment_download_polys(self.h, _cols(out)))
         return out
 
-    def download_lde(self) -> np.ndarray:
-        out = np.empty((self.n_cols, self.n_rows * self.blowup), np.uint64)
+    def download_lde(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Natural-order LDE columns (TraceLde for the host-side AIR evaluator).  ``out``: destination matrix
+        (page-locked memory is filled directly by the copy engine, pageable memory through pinned slots)."""
+        if out is None:
+            out = np.empty((self.n_cols, self.n_rows * self.blowup), np.uint64)
+        assert out.shape == (self.n_cols, self.n_rows * self.blowup)
         self.ctx._check(self.ctx.lib.aero_segment_download_lde(self.h, _cols(out)))
         return out
 

@@ -368,6 +368,32 @@ def run_aero(args) -> None:
     h2d = int((MAIN_W + AUX_W) * n * 8 * own_frac) + CE_COLS * N * 8
     d2h = len(proof) + 32 * 9
 
+    # The transfer the north star times separately: the extended trace going back to the host for the Rust AIR
+    # evaluator (aero_segment_download_lde; 8 bytes x 8 x rows x columns).  One GPU, main segment.
+    lde_download = None
+    if world == 1 and not args.no_lde_download:
+        seg = ctx.build_trace_commitment_device(d_main.data_ptr(), MAIN_W, n, BLOWUP)
+        nbytes = MAIN_W * N * 8
+        t_pin = torch.empty((MAIN_W, N), dtype=torch.int64).pin_memory()
+        dst_pin = t_pin.numpy().view(np.uint64)
+        dst_pag = np.empty((MAIN_W, N), np.uint64)
+        dst_pag[:, ::512] = 0  # touch the pages once: first-touch faults are not what is being measured
+        times = {}
+        for name, dst in (("pinned", dst_pin), ("pageable", dst_pag)):
+            seg.download_lde(dst)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            seg.download_lde(dst)
+            times[name] = (time.perf_counter() - t0) * 1e3
+        assert np.array_equal(dst_pin[:, ::4099], dst_pag[:, ::4099])
+        seg.destroy()
+        lde_download = {"bytes": nbytes, "columns": MAIN_W, "ms_pinned": times["pinned"], "ms_pageable": times["pageable"],
+                        "gbs_pinned": nbytes / times["pinned"] / 1e6, "gbs_pageable": nbytes / times["pageable"] / 1e6,
+                        "note": "natural-order main-segment LDE to host memory, wall clock; column conversion on the device "
+                                "double-buffered under the PCIe transfer; pageable destinations go through two pinned "
+                                "slots with the host copy split over threads"}
+        del t_pin, dst_pin, dst_pag
+
     # Parity inside the bench run (checker only, outside every timed region).  N > 1: the sharded proof must
     # equal the single-GPU proof of the same inputs byte for byte, and a 2^14-row sharded proof must equal
     # the CPU restatement's bytes (what the driver's one-GPU test box cannot run).
@@ -447,6 +473,8 @@ def run_aero(args) -> None:
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "phase_ms_per_step": phases,
                 "proof_bytes": len(proof)}
+        if lde_download:
+            line["lde_download"] = lde_download
         if independent:
             line["independent_proofs"] = independent
         if parity:
@@ -468,6 +496,7 @@ def main() -> None:
     ap.add_argument("--ref-log-rows", type=int, default=0, help="trace size of the CPU arm (0 = the workload's own size)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="time budget of the reference arm's timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lde-download", action="store_true", help="skip the separately timed LDE download (5 GB of host memory)")
     ap.add_argument("--independent", action="store_true",
                     help="N>1: one independent proof per rank (weak scaling) instead of ONE proof sharded over the ranks")
     ap.add_argument("--shard-proof", action="store_true", help="(default for N>1; kept for older command lines)")

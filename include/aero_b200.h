@@ -240,6 +240,24 @@ aero_status aero_open_queries(aero_ctx *ctx, aero_fri *fri, aero_segment *const 
                               const uint64_t *positions, uint32_t n_pos, uint8_t *fri_proof_bytes, size_t *fri_len,
                               uint64_t *const *rows_out, uint8_t *const *batch_nodes_out, size_t *batch_len);
 
+/* ---- auxiliary-segment construction: running-product columns ------------------------------------- */
+/* The data-parallel core of Trace::build_aux_segment for Miden (miden/processor/src/trace/mod.rs:188-249):
+ * every auxiliary column is a running product over the table updates of the main trace, built by
+ * build_aux_column (processor/src/trace/utils.rs:153-199):
+ *     col[0] = init[c],   col[i + 1] = col[i] * multiplicands[c][i]     (multiplicand 1 on rows without an update)
+ * -- an exclusive prefix product, a blocked scan here.  multiplicands[c] has n_rows - 1 entries that matter
+ * (ABI form).  Which rows update which table, and the row values mixed from the random elements, are Miden
+ * VM logic and stay with the caller; aero_batch_inverse serves the inversions of those row values
+ * (build_lookup_table_row_values, utils.rs; math::batch_inversion semantics: zero maps to zero).
+ * The *_device form takes and leaves the columns in device memory (column c at base + c*stride), so the
+ * result can go straight into aero_segment_commit_device without crossing PCIe again. */
+aero_status aero_running_product_columns(aero_ctx *ctx, const uint64_t *const *multiplicands, const uint64_t *init,
+                                         uint32_t n_cols, uint64_t n_rows, uint64_t *const *cols_out);
+aero_status aero_running_product_columns_device(aero_ctx *ctx, const uint64_t *d_multiplicands, size_t m_stride,
+                                                const uint64_t *init, uint32_t n_cols, uint64_t n_rows, uint64_t *d_out,
+                                                size_t out_stride);
+aero_status aero_batch_inverse(aero_ctx *ctx, const uint64_t *values, uint64_t count, uint64_t *out);
+
 /* ---- grinding ---------------------------------------------------------------------------------- */
 /* ProverChannel::grind_query_seed, serial build (prover/src/channel.rs:151-167): smallest nonce >= 1
  * with trailing_zeros(LE64(merge_with_int(seed, nonce)[0..8])) >= grinding_bits. */

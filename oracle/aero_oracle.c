@@ -412,6 +412,14 @@ void aero_or_batch_inversion(const u64 *v, u64 n, u64 *out) {
     }
 }
 
+/* Running-product auxiliary column: miden/processor/src/trace/utils.rs:153-199 (build_aux_column) with the
+ * table hints flattened to one multiplicand per row (1 where no update happens): result[0] = init,
+ * result[clk + 1] = result[clk] * multiplicand(clk); rows between updates repeat the last value. */
+void aero_or_build_aux_column(const u64 *multiplicands, u64 n, u64 init, u64 *out) {
+    out[0] = init;
+    for (u64 i = 0; i + 1 < n; i++) out[i + 1] = gl_mul(out[i], multiplicands[i]);
+}
+
 /* OOD frame: prover/src/trace/poly_table.rs:59-72 (evaluate_at / get_ood_frame) and
  * constraints/composition_poly.rs:93-96 (evaluate_at z^m): Horner per column. */
 void aero_or_eval_columns_at(const u64 *polys, u64 w, u64 n, u64 x, u64 *out) {

@@ -790,6 +790,23 @@ def constraints_into_poly(eval_cols: np.ndarray, divisors: Sequence[Divisor], tr
     return out
 
 
+def build_aux_columns(multiplicands: np.ndarray, init: Sequence[int]) -> np.ndarray:
+    """miden/processor/src/trace/utils.rs:153-199 for every column: (cols, n) multiplicands -> running products."""
+    m = np.ascontiguousarray(multiplicands, np.uint64)
+    out = np.empty_like(m)
+    for c in range(m.shape[0]):
+        lib().aero_or_build_aux_column(_a64(m[c]), u64(m.shape[1]), u64(int(init[c])), _a64(out[c]))
+    return out
+
+
+def batch_inversion(values: np.ndarray) -> np.ndarray:
+    """math::batch_inversion (winterfell/math/src/utils/mod.rs:192-238): zero maps to zero."""
+    v = np.ascontiguousarray(values, np.uint64)
+    out = np.empty_like(v)
+    lib().aero_or_batch_inversion(_a64(v), u64(v.size), _a64(out))
+    return out
+
+
 def eval_columns_at(polys: np.ndarray, x: int) -> List[int]:
     w, n = polys.shape
     out = np.empty(w, np.uint64)

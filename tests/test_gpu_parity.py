@@ -505,3 +505,36 @@ def test_segment_commit_overlapped_hash_chain(oracle, logn, width):
         c.device_free(d)
     finally:
         c.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# auxiliary-segment construction: running-product columns and batch inversion
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("form", ["canonical", "montgomery"])
+@pytest.mark.parametrize("n,cols", [(2, 1), (8, 3), (4096, 2), (4097 * 2, 9), (1 << 16, 9), (100003, 4)])
+def test_running_product_columns(ctx, ctx_mont, oracle, n, cols, form):
+    """build_aux_column (miden/processor/src/trace/utils.rs:153-199): col[0] = init, col[i+1] = col[i] * m[i].
+    Sparse updates (most multiplicands are 1), zeros, and lengths that are not multiples of the chunk."""
+    m = oracle.synthetic_trace(cols, n, 0xA0C0 + n % 997)
+    rng = np.random.default_rng(n)
+    m[rng.random((cols, n)) < 0.6] = 1          # rows without a table update
+    if n > 16:
+        m[0, n // 2] = 0                        # a zero multiplicand zeroes the rest of the column
+    init = [int(v) for v in oracle.synthetic_trace(1, cols, 7)[0]]
+    init[0] = 1
+    ref = oracle.build_aux_columns(m, init)
+    if form == "montgomery":
+        got = oracle.mont_to_canon(ctx_mont.running_product_columns(oracle.canon_to_mont(m), [int(v) for v in oracle.canon_to_mont(np.array(init, np.uint64))]))
+    else:
+        got = ctx.running_product_columns(m, init)
+    assert np.array_equal(got, ref)
+    assert [int(v) for v in got[:, 0]] == init
+
+
+def test_batch_inverse(ctx, ctx_mont, oracle):
+    v = oracle.synthetic_trace(1, 5000, 0x1BB)[0]
+    v[[0, 17, 4999]] = 0
+    ref = oracle.batch_inversion(v)
+    assert np.array_equal(ctx.batch_inverse(v), ref)
+    assert all(int(a) * int(b) % P == 1 for a, b in zip(v[1:17], ref[1:17])) and ref[0] == 0
+    assert np.array_equal(oracle.mont_to_canon(ctx_mont.batch_inverse(oracle.canon_to_mont(v))), ref)
