@@ -122,6 +122,7 @@ struct aero_ctx {
     uint8_t *h_bulk[2] = {nullptr, nullptr};
     size_t bulk_bytes = 0;
     cudaEvent_t ev_bulk[2] = {nullptr, nullptr};
+    int bulk_slot = 0;
 };
 
 #define CTX_FAIL(ctx, code, ...)                         \
@@ -280,10 +281,6 @@ static aero_status ring_take(aero_ctx *ctx, size_t bytes, void **out) {
     if (!ctx->h_ring || bytes > ctx->ring_bytes) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
-    for (int i = 0; i < 2; i++) {
-        if (ctx->h_bulk[i]) cudaFreeHost(ctx->h_bulk[i]);
-        if (ctx->ev_bulk[i]) cudaEventDestroy(ctx->ev_bulk[i]);
-    }
         ctx->h_ring = nullptr;
         ctx->ring_bytes = std::max(RING_BYTES, 2 * bytes);
         CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_ring, ctx->ring_bytes));
@@ -337,6 +334,41 @@ static bool host_is_pinned(const void *p) {
         return false;
     }
     return a.type == cudaMemoryTypeHost;
+}
+
+static aero_status bulk_reserve(aero_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->bulk_bytes) return AERO_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    for (int i = 0; i < 2; i++) {
+        if (ctx->h_bulk[i]) cudaFreeHost(ctx->h_bulk[i]);
+        ctx->h_bulk[i] = nullptr;
+        if (!ctx->ev_bulk[i]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_bulk[i], cudaEventDisableTiming));
+    }
+    ctx->bulk_bytes = 0;
+    for (int i = 0; i < 2; i++) CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_bulk[i], bytes));
+    ctx->bulk_bytes = bytes;
+    return AERO_OK;
+}
+// Host -> device copy of `bytes` from possibly PAGEABLE memory on the copy stream: page-locked sources are
+// handed to the copy engine as they are; pageable ones go through the two pinned bulk slots in pieces, the
+// host copy of piece k + 1 (split over threads) running under the PCIe transfer of piece k.  (Left to the
+// driver, a pageable source is staged by one thread at ~8-10 GB/s while the caller is blocked.)
+static aero_status staged_h2d(aero_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, bool pinned, int *slot_counter) {
+    if (pinned) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        return AERO_OK;
+    }
+    const size_t piece = ctx->bulk_bytes;
+    for (size_t off = 0; off < bytes; off += piece) {
+        const size_t len = std::min(piece, bytes - off);
+        const int slot = (*slot_counter)++ & 1;
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_bulk[slot]));  // the slot's previous transfer has left it
+        parallel_memcpy(ctx->h_bulk[slot], (const uint8_t *)h_src + off, len);
+        CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t *)d_dst + off, ctx->h_bulk[slot], len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_bulk[slot], ctx->copy_stream));
+    }
+    return AERO_OK;
 }
 
 // Pinned host / device staging pair for small result downloads (OOD frame, openings): results land
@@ -819,6 +851,16 @@ static int upload_batch_size(int c0, int n_cols, int batch, int edge) {
     if (left > edge) return std::max(2, (left - edge) & ~1);
     return left;
 }
+// Where the column batches of an upload-overlapped commit come from (aero_segment_commit): prepare(b) makes
+// sure the copy of batch b is queued on the copy stream and ev[b] recorded behind it.
+struct BatchSource {
+    std::vector<cudaEvent_t> ev;
+    virtual aero_status prepare(int b) = 0;
+    virtual ~BatchSource() {
+        for (auto e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+};
 // d_src: columns [src_col0, ...) of the matrix (column c at d_src + (c - src_col0) * src_stride), n values
 // each in ABI form, on the device; this rank reads its own columns only (own_columns).  They are
 // processed in batches (interpolate, extend); when `ready` is given, batch b first waits for ready[b] --
@@ -828,7 +870,7 @@ static int upload_batch_size(int c0, int n_cols, int batch, int edge) {
 // the other ranks interpolated are extended too.
 static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, size_t src_stride, int src_col0, uint32_t n_cols,
                                        uint64_t n_rows, uint32_t blowup, int input_is_coeffs, aero_segment **out,
-                                       uint8_t root[32], int batch_cols = 0, const cudaEvent_t *ready = nullptr, int edge_cols = 0) {
+                                       uint8_t root[32], int batch_cols = 0, BatchSource *ready = nullptr, int edge_cols = 0) {
     if (!out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null output handle");
     if (n_cols == 0 || n_cols > 255) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of columns must be 1..255, got %u", n_cols);
     // Matrix::new (prover/src/matrix.rs:41-64): at least two rows, power of two
@@ -870,7 +912,10 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
     // compute starts early, the last so that little work is left once the final copy has landed
     for (int c0 = cb, b = 0, nc = 0; c0 < ce; c0 += nc, b++) {
         nc = std::min(upload_batch_size(c0 - cb, ce - cb, batch, edge_cols), ce - c0);
-        if (ready) cudaStreamWaitEvent(ctx->stream, ready[b], 0);
+        if (ready) {  // batch b's host->device copy: queue it if that has not happened yet, then order after it
+            TRY(ready->prepare(b));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ready->ev[b], 0));
+        }
         const uint64_t *src = d_src + (size_t)(c0 - src_col0) * src_stride;
         int done = nc;  // columns whose coefficients exist after this step, starting at c0
         if (input_is_coeffs) {
@@ -1315,6 +1360,10 @@ void aero_ctx_destroy(aero_ctx *ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->h_bulk[i]) cudaFreeHost(ctx->h_bulk[i]);
+        if (ctx->ev_bulk[i]) cudaEventDestroy(ctx->ev_bulk[i]);
+    }
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1483,9 +1532,12 @@ static aero_status upload_enqueue(aero_upload *u) {
     aero_ctx *ctx = u->ctx;
     if (u->queued) return AERO_OK;
     TRY(copy_stream_after_compute(ctx));
+    bool pinned = true;
+    for (int c = u->col_begin; c < u->col_end; c++) pinned = pinned && host_is_pinned(u->cols[c]);
+    if (!pinned) TRY(bulk_reserve(ctx, (size_t)16 << 20));
     for (int c = u->col_begin; c < u->col_end; c++)
-        CUDA_TRY(ctx, cudaMemcpyAsync(u->d + (size_t)c * u->n_rows + u->row_begin, u->cols[c] + u->row_begin,
-                                      (u->row_end - u->row_begin) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        TRY(staged_h2d(ctx, u->d + (size_t)c * u->n_rows + u->row_begin, u->cols[c] + u->row_begin,
+                       (u->row_end - u->row_begin) * 8, pinned, &ctx->bulk_slot));
     CUDA_TRY(ctx, cudaEventRecord(u->done, ctx->copy_stream));
     u->queued = true;
     return AERO_OK;
@@ -1602,26 +1654,52 @@ aero_status aero_segment_commit(aero_ctx *ctx, const uint64_t *const *cols, uint
         c0 += nc;
     }
     const int nb = (int)sizes.size();
-    struct Events {
-        std::vector<cudaEvent_t> ev;
-        ~Events() {
-            for (auto e : ev)
-                if (e) cudaEventDestroy(e);
+    struct HostColumns : BatchSource {
+        aero_ctx *ctx;
+        const uint64_t *const *cols;
+        uint64_t *stage;
+        uint64_t n_rows;
+        std::vector<int> sizes, first;
+        bool pinned = true;
+        int queued = 0;  // batches whose copies are on the copy stream
+        aero_status queue(int b) {
+            for (int k = 0; k < sizes[b]; k++) {
+                const int c = first[b] + k;
+                TRY(staged_h2d(ctx, stage + (size_t)c * n_rows, cols[c], n_rows * 8, pinned, &ctx->bulk_slot));
+            }
+            CUDA_TRY(ctx, cudaEventRecord(ev[b], ctx->copy_stream));
+            if (b + 1 == (int)sizes.size()) TRY(flush_deferred_uploads(ctx));  // prefetches ride behind this segment's copies, under its NTTs
+            return AERO_OK;
         }
-    } evs;
-    evs.ev.assign((size_t)nb, nullptr);
-    for (auto &e : evs.ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        aero_status prepare(int b) override {
+            for (; queued <= b; queued++) TRY(queue(queued));
+            return AERO_OK;
+        }
+    } src;
+    src.ctx = ctx;
+    src.cols = cols + cb;
+    src.stage = stage;
+    src.n_rows = n_rows;
+    src.sizes = sizes;
+    for (int b = 0, c = 0; b < nb; c += sizes[b], b++) src.first.push_back(c);
+    for (int c = 0; c < own; c++) src.pinned = src.pinned && host_is_pinned(cols[cb + c]);
+    src.ev.assign((size_t)nb, nullptr);
+    for (auto &e : src.ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     // the staging block may still be read by kernels already queued on the compute stream
     TRY(copy_stream_after_compute(ctx));
-    for (int b = 0, c = 0; b < nb; b++) {
-        for (int k = 0; k < sizes[b]; k++, c++)
-            CUDA_TRY(ctx, cudaMemcpyAsync(stage + (size_t)c * n_rows, cols[cb + c], n_rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CUDA_TRY(ctx, cudaEventRecord(evs.ev[b], ctx->copy_stream));
+    if (src.pinned) {
+        // page-locked columns: every copy is queued now, so the copy engine never waits for the host
+        if (nb) TRY(src.prepare(nb - 1));
+        else TRY(flush_deferred_uploads(ctx));
+    } else {
+        // pageable columns (a Rust Vec): each batch is staged through pinned memory right before its
+        // transforms are queued, the host copy of batch b + 1 running under the transfer and the NTTs of batch b
+        TRY(bulk_reserve(ctx, std::max<size_t>((size_t)16 << 20, (size_t)batch * n_rows * 8)));
+        if (!nb) TRY(flush_deferred_uploads(ctx));
     }
-    TRY(flush_deferred_uploads(ctx));  // prefetches ride behind this segment's copies, under its NTTs
     aero_status st = segment_from_device(ctx, stage, n_rows, cb, n_cols, n_rows, blowup, input_is_coeffs, out, root, batch,
-                                         nb ? evs.ev.data() : nullptr, edge);
-    if (nb) cudaEventSynchronize(evs.ev[nb - 1]);  // the caller's host buffers are free again on return
+                                         nb ? &src : nullptr, edge);
+    if (nb && src.queued == nb) cudaEventSynchronize(src.ev[nb - 1]);  // the caller's host buffers are free again on return
     return st;
 }
 
@@ -1794,19 +1872,6 @@ aero_status aero_segment_commit_polys(aero_segment *seg, uint32_t blowup, uint8_
     return segment_extend_commit(seg, ilog2(blowup), root);
 }
 
-static aero_status bulk_reserve(aero_ctx *ctx, size_t bytes) {
-    if (bytes <= ctx->bulk_bytes) return AERO_OK;
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < 2; i++) {
-        if (ctx->h_bulk[i]) cudaFreeHost(ctx->h_bulk[i]);
-        ctx->h_bulk[i] = nullptr;
-        if (!ctx->ev_bulk[i]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_bulk[i], cudaEventDisableTiming));
-    }
-    ctx->bulk_bytes = 0;
-    for (int i = 0; i < 2; i++) CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_bulk[i], bytes));
-    ctx->bulk_bytes = bytes;
-    return AERO_OK;
-}
 // The extended trace for the host-side AIR evaluator: 8 * N bytes per column, 5.4 GB for a 2^20-row Miden
 // trace -- the transfer that dominates a real proof once the rest of the path is on the GPU.
 // Columns are converted to natural order two at a time into alternating device buffers; page-locked

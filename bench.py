@@ -41,7 +41,8 @@ NTT_ALU_OPS_PER_BUTTERFLY = 21.8
 ALU_OPS_PER_COMPRESSION = 661
 # DRAM bytes of one hash_rows_kernel launch (w = 72, N = 2^23) in this round's ncu --set full capture
 # (profiles/r02_ncu_hash.txt); reported under roofline.traffic_ncu, never as a measurement of this run
-HASH_W72_NCU = None
+HASH_W72_NCU = {"bytes_per_launch": 5.100e9, "read": 4.834e9, "write": 0.266e9, "algorithmic": 5.100e9,
+                "source": "profiles/r02_ncu_hash_merkle.txt (ncu --set full, w = 72, N = 2^23)"}
 PUB = b"aero-b200 bench public inputs"
 
 
@@ -468,8 +469,9 @@ def run_aero(args) -> None:
                 "e2e": {"value": e2e_val, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e, "host_buffers": "pinned"},
                 "e2e_pageable": {"value": nproofs * n / (ms_pg * 1e-3), "unit": "rows/s", "ms_per_step": ms_pg,
-                                 "note": "same call with pageable (unpinned) host columns, cudaMemcpyAsync straight from the "
-                                         "caller's pointers: the copies stage through the driver and do not overlap compute"},
+                                 "note": "same call with pageable (unpinned) host columns -- what a Rust Vec<Vec<Felt>> is: the "
+                                         "library stages each column batch through two pinned slots, the host copy split over "
+                                         "threads and running under the transfer and the NTTs of the previous batch"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "phase_ms_per_step": phases,
                 "proof_bytes": len(proof)}
