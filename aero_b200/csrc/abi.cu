@@ -676,6 +676,70 @@ static aero_status get_pow_table(aero_ctx *ctx, const std::string &key, uint64_t
     return AERO_OK;
 }
 
+// Transforms of 2^25 / 2^26 points (the top of BASELINE's NTT sweep): one outer radix-B step (B = 2, 4) over
+// 2^24-point two-pass transforms, see large_combine in poly.cu.  kind 0: plain inverse transform with the
+// 1/n scale (interpolate_poly), kind 1: coset LDE (evaluate_poly_with_offset), both column by column.
+static aero_status dft_run_large(aero_ctx *ctx, int kind, int logn, int log_blowup, bool input_mont, const DftLaunch &l) {
+    const int logm = NTT_MAX_LOG, logB = logn - logm, B = 1 << logB;
+    if (logB < 1 || logB > 2) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "transform size 2^%d unsupported (max 2^%d)", logn, NTT_LARGE_MAX_LOG);
+    const size_t m = (size_t)1 << logm, n = m << logB;
+    const bool inverse = kind == 0;
+    const int ncosets_all = inverse ? 1 : (1 << log_blowup);
+    const int nc = inverse ? 1 : (l.coset_count ? l.coset_count : ncosets_all), cb = inverse ? 0 : l.coset_begin;
+    char key[64];
+    const DftTables *sub = nullptr;
+    uint64_t *d_shifts = nullptr;
+    uint64_t scale = 1;
+    if (inverse) {
+        TRY(plan_intt(ctx, logm, input_mont, &sub));  // carries 1/m (and 2^-64 for Montgomery input)
+        scale = gl::inv((uint64_t)B);
+    } else {
+        const std::vector<uint64_t> sh = coset_shifts(logn, log_blowup, gl::GENERATOR);
+        std::vector<uint64_t> shB(sh.size());
+        for (size_t i = 0; i < sh.size(); i++) shB[i] = gl::pow(sh[i], (uint64_t)B);
+        snprintf(key, sizeof key, "lde_sub/%d/%d/%d", logn, log_blowup, (int)input_mont);
+        TRY(get_plan(ctx, key, logm, false, shB, input_mont ? gl::MONT_R_INV : 1, 0, &sub));
+        snprintf(key, sizeof key, "shifts/%d/%d", logn, log_blowup);
+        auto it = ctx->const_tables.find(key);
+        if (it == ctx->const_tables.end()) {
+            TRY(upload_vec(ctx, &d_shifts, sh));
+            ctx->const_tables[key] = d_shifts;
+        } else {
+            d_shifts = it->second;
+        }
+    }
+    PowTable wn;
+    snprintf(key, sizeof key, "wn/%d/%d", logn, (int)inverse);
+    const uint64_t root = gl::root_of_unity(logn);
+    TRY(get_pow_table(ctx, key, inverse ? gl::inv(root) : root, logm, 1, &wn));
+    const uint64_t w4 = inverse ? gl::inv(gl::root_of_unity(2)) : gl::root_of_unity(2);
+    DevBlocks blk(ctx);
+    uint64_t *xd = nullptr, *Y = nullptr, *tmp = nullptr;
+    TRY(blk.alloc((void **)&xd, n * 8));
+    TRY(blk.alloc((void **)&Y, (size_t)B * nc * m * 8));
+    TRY(blk.alloc((void **)&tmp, (size_t)nc * m * 8));
+    for (int c = 0; c < l.ncols; c++) {
+        large_deinterleave(l.src + (size_t)c * l.src_col_stride, xd, logm, logB, ctx->stream);
+        for (int r = 0; r < B; r++) {
+            DftLaunch sl;
+            sl.src = xd + (size_t)r * m;
+            sl.dst = Y + (size_t)r * nc * m;
+            sl.tmp = tmp;
+            sl.src_col_stride = m;
+            sl.dst_col_stride = (size_t)nc * m;
+            sl.ncols = 1;
+            sl.deinterleave_log = 0;
+            sl.coset_begin = cb;
+            sl.coset_count = inverse ? 0 : nc;
+            dft_run(*sub, sl, ctx->stream);
+        }
+        large_combine(Y, l.dst + (size_t)c * l.dst_col_stride, wn, d_shifts ? d_shifts + cb : nullptr, scale, w4, logm, logB, nc,
+                      ctx->stream);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return AERO_OK;
+}
+
 // -------------------------------------------------------------------------------------------------
 // segment
 // -------------------------------------------------------------------------------------------------
@@ -694,6 +758,7 @@ struct aero_segment {
     // compactly: lde[c][q][i] with q = r - coset_begin, column stride coset_count * n.
     int coset_begin = 0, coset_count = 0;
     int logG = 0;
+    bool failed = false;  // an LDE batch could not be queued (ctx->err holds the reason)
     uint64_t n() const { return 1ULL << logn; }
     uint64_t N() const { return 1ULL << (logn + log_blowup); }
     uint64_t lde_stride() const { return (uint64_t)coset_count << logn; }
@@ -745,6 +810,8 @@ static aero_status segment_alloc_lde(aero_segment *seg, int log_blowup, const Df
     TRY(dev_alloc_shared(ctx, (void **)&seg->leaf_stage, block * 32));
     TRY(dev_alloc_shared(ctx, (void **)&seg->top, (size_t)2 * G * 32));
     TRY(dev_alloc(ctx, (void **)&seg->heap, block * 32));
+    *plan = nullptr;  // above the two-pass NTT the extension goes through dft_run_large
+    if (seg->logn > NTT_MAX_LOG) return AERO_OK;
     return plan_lde(ctx, seg->logn, log_blowup, false, plan);
 }
 static int segment_lde_batch_cols(aero_segment *seg) {
@@ -770,7 +837,8 @@ static void segment_lde_batch(aero_segment *seg, const DftTables *plan, int c0, 
     l.deinterleave_log = 0;
     l.coset_begin = seg->coset_begin;
     l.coset_count = seg->coset_count;
-    dft_run(*plan, l, ctx->stream);
+    if (plan) dft_run(*plan, l, ctx->stream);
+    else if (dft_run_large(ctx, 1, seg->logn, seg->log_blowup, false, l) != AERO_OK) seg->failed = true;
 }
 // Row hashing of columns [c0, c0 + nc) (chaining value kept in the leaf slot, see hash_rows_kernel).
 // With ctx->overlap_hash the launch goes to a second stream, ordered after the LDE batch that
@@ -824,7 +892,7 @@ static aero_status segment_extend_commit(aero_segment *seg, int log_blowup, uint
     const int batch = segment_lde_batch_cols(seg);
     DevBlocks tmp(ctx);
     uint64_t *tmp_l = nullptr;
-    if (plan->log1 != 0) TRY(tmp.alloc((void **)&tmp_l, (size_t)batch * seg->lde_stride() * 8));
+    if (plan && plan->log1 != 0) TRY(tmp.alloc((void **)&tmp_l, (size_t)batch * seg->lde_stride() * 8));
     if ((batch & 1) || !segment_hash_overlapped(seg)) {  // extend everything, then one hash launch
         for (int c0 = 0; c0 < seg->ncols; c0 += batch) segment_lde_batch(seg, plan, c0, std::min(batch, seg->ncols - c0), tmp_l);
         TRY(segment_hash_batch(seg, 0, seg->ncols));
@@ -877,7 +945,8 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
     if (n_rows < 2 || !is_pow2(n_rows)) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of rows must be a power of two >= 2, got %llu", (unsigned long long)n_rows);
     if (!is_pow2(blowup) || blowup < 2) CTX_FAIL(ctx, AERO_ERR_INVALID, "blowup factor must be a power of two >= 2, got %u", blowup);
     const int logn = ilog2(n_rows);
-    if (logn > NTT_MAX_LOG) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "trace length 2^%d unsupported (max 2^%d)", logn, NTT_MAX_LOG);
+    if (logn > NTT_LARGE_MAX_LOG) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "trace length 2^%d unsupported (max 2^%d)", logn, NTT_LARGE_MAX_LOG);
+    const bool large = logn > NTT_MAX_LOG;
     SegmentGuard seg(new aero_segment());
     seg->ctx = ctx;
     seg->ncols = (int)n_cols;
@@ -888,7 +957,7 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
     DevBlocks tmp(ctx);
     uint64_t *tmp_i = nullptr, *tmp_l = nullptr;
     TRY(dev_alloc_shared(ctx, (void **)&seg->polys, (size_t)n_cols * n_rows * 8));
-    if (!input_is_coeffs) TRY(plan_intt(ctx, logn, mont, &iplan));
+    if (!input_is_coeffs && !large) TRY(plan_intt(ctx, logn, mont, &iplan));
     TRY(segment_alloc_lde(seg.get(), ilog2(blowup), &lplan));
     int cb = 0, ce = (int)n_cols;
     own_columns(ctx, (int)n_cols, &cb, &ce);
@@ -903,7 +972,7 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
         ibatch = (int)std::min<size_t>(n_cols, std::max<size_t>(batch, fit / batch * batch));
     }
     if (iplan && iplan->log1 != 0) TRY(tmp.alloc((void **)&tmp_i, (size_t)ibatch * n_rows * 8));
-    if (lplan->log1 != 0) TRY(tmp.alloc((void **)&tmp_l, (size_t)std::max(batch, lde_batch) * seg->lde_stride() * 8));
+    if (lplan && lplan->log1 != 0) TRY(tmp.alloc((void **)&tmp_l, (size_t)std::max(batch, lde_batch) * seg->lde_stride() * 8));
     const bool per_batch_hash = !(batch & 1) && segment_hash_overlapped(seg.get());
     char nm[32];
     snprintf(nm, sizeof nm, "interpolate_w%d", (int)n_cols);
@@ -935,7 +1004,8 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
             l.dst_col_stride = n_rows;
             l.ncols = done = edge_cols > 0 ? nc : std::min(ibatch, ce - c0);
             l.deinterleave_log = 0;
-            dft_run(*iplan, l, ctx->stream);
+            if (iplan) dft_run(*iplan, l, ctx->stream);
+            else TRY(dft_run_large(ctx, 0, logn, 0, mont, l));
         } else {
             done = 0;  // part of an earlier, wider interpolation launch
         }
@@ -983,6 +1053,7 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
         }
         CUDA_TRY(ctx, cudaGetLastError());
     }
+    if (seg->failed) return AERO_ERR_UNSUPPORTED;
     if (!per_batch_hash) TRY(segment_hash_batch(seg.get(), 0, (int)n_cols));
     TRY(segment_tree_after_hash(seg.get(), root));
     *out = seg.release();

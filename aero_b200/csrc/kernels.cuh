@@ -126,6 +126,10 @@ void convert_form(const uint64_t *src, uint64_t *dst, size_t count, int to_montg
 void lde_to_natural(const uint64_t *lde_cm, uint64_t *out, int logn, int log_blowup, int to_montgomery,
                     cudaStream_t s);
 void natural_to_coset_major(const uint64_t *in, uint64_t *out, int logn, int log_blowup, cudaStream_t s);
+// outer radix-B step of transforms above 2^24 points (poly.cu)
+void large_deinterleave(const uint64_t *x, uint64_t *out, int logm, int logB, cudaStream_t s);
+void large_combine(const uint64_t *Y, uint64_t *dst, PowTable wn, const uint64_t *d_shifts, uint64_t scale, uint64_t w4, int logm,
+                   int logB, int ncosets, cudaStream_t s);
 bool coset_interp_combine(const uint64_t *a, PowTable ginv, PowTable oinv, const uint64_t *M, int logn, int log_b,
                           uint64_t *polys, cudaStream_t s);
 // out[p*2 + 0/1] partial sums; see poly.cu

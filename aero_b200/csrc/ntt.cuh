@@ -22,6 +22,7 @@ namespace aero {
 
 constexpr int NTT_SINGLE_MAX_LOG = 11;  // largest single-pass transform
 constexpr int NTT_MAX_LOG = 24;         // two passes of <= 2^12 points
+constexpr int NTT_LARGE_MAX_LOG = 26;   // with one outer radix-2 / radix-4 step over 2^24-point transforms (abi.cu)
 constexpr int NTT_MAX_ROUND_LOG = 5;    // largest register-resident round: 32 points
 
 // Round schedule of a 2^logM-point shared-memory transform, shared by the host (stage tables) and the

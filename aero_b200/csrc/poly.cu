@@ -83,6 +83,63 @@ void natural_to_coset_major(const uint64_t *in, uint64_t *out, int logn, int log
     natural_to_coset_major_kernel<<<(unsigned)blocks, 256, 0, s>>>(in, out, logn, log_blowup);
 }
 
+// Transforms beyond the two-pass NTT (n = B*m > 2^24, B = 2 or 4; the 2^25 / 2^26-row end of the NTT sweep):
+// one outer decimation-in-time step.  With x_rho[j'] = x[B j' + rho] and Y_rho the size-m transform of x_rho on
+// the coset shift s^B,
+//     X[i0 + k m] = sum_rho (s w_n^i0)^rho  w_B^(k rho)  Y_rho[i0]          (i0 < m, k < B)
+// i.e. a twist by powers of t = s w_n^i0 and a B-point DFT across the B sub-transforms.  The inverse transform
+// is the same with the inverse roots, no shift, and 1/B folded into `scale`.
+__global__ void __launch_bounds__(256) large_deinterleave_kernel(const uint64_t *__restrict__ x, uint64_t *__restrict__ out,
+                                                                 int logm, int logB) {
+    const size_t n = (size_t)1 << (logm + logB);
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x)
+        out[((j & (((size_t)1 << logB) - 1)) << logm) + (j >> logB)] = x[j];
+}
+void large_deinterleave(const uint64_t *x, uint64_t *out, int logm, int logB, cudaStream_t s) {
+    AERO_COUNT_LAUNCH(1);
+    large_deinterleave_kernel<<<148 * 16, 256, 0, s>>>(x, out, logm, logB);
+}
+// Y: [B][ncosets][m] ; dst: coset q at dst + q * n ; wn: powers of the n-th root (inverse root for INV) ;
+// shifts: per-coset s (nullptr = 1) ; w4: primitive 4th root for the direction (B = 4)
+template <int LOGB>
+__global__ void __launch_bounds__(256) large_combine_kernel(const uint64_t *__restrict__ Y, uint64_t *__restrict__ dst,
+                                                            PowTable wn, const uint64_t *__restrict__ shifts, uint64_t scale,
+                                                            uint64_t w4, int logm, int ncosets) {
+    constexpr int B = 1 << LOGB;
+    const size_t m = (size_t)1 << logm, n = m << LOGB;
+    const int q = blockIdx.y;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= m) return;
+    uint64_t t = pow_lookup(wn, (uint32_t)i0);
+    if (shifts) t = gl::mul(t, shifts[q]);
+    uint64_t z[B], pw = scale;
+#pragma unroll
+    for (int r = 0; r < B; r++) {
+        z[r] = gl::mul(Y[((size_t)r * ncosets + q) * m + i0], pw);
+        pw = gl::mul(pw, t);
+    }
+    uint64_t *o = dst + (size_t)q * n + i0;
+    if (B == 2) {
+        o[0] = gl::add(z[0], z[1]);
+        o[m] = gl::sub(z[0], z[1]);
+    } else {  // out_k = sum_r z_r w4^(k r)
+        const uint64_t a0 = gl::add(z[0], z[2]), a1 = gl::sub(z[0], z[2]);
+        const uint64_t b0 = gl::add(z[1], z[3]), b1 = gl::mul(gl::sub(z[1], z[3]), w4);
+        o[0] = gl::add(a0, b0);
+        o[m] = gl::add(a1, b1);
+        o[2 * m] = gl::sub(a0, b0);
+        o[3 * m] = gl::sub(a1, b1);
+    }
+}
+void large_combine(const uint64_t *Y, uint64_t *dst, PowTable wn, const uint64_t *d_shifts, uint64_t scale, uint64_t w4, int logm,
+                   int logB, int ncosets, cudaStream_t s) {
+    const size_t m = (size_t)1 << logm;
+    dim3 g((unsigned)((m + 255) / 256), ncosets);
+    AERO_COUNT_LAUNCH(1);
+    if (logB == 1) large_combine_kernel<1><<<g, 256, 0, s>>>(Y, dst, wn, d_shifts, scale, w4, logm, ncosets);
+    else large_combine_kernel<2><<<g, 256, 0, s>>>(Y, dst, wn, d_shifts, scale, w4, logm, ncosets);
+}
+
 // Last step of a size-N = B*n coset interpolation done as B size-n interpolations (the route taken
 // when N exceeds the two-pass NTT, i.e. for traces above 2^21 rows).  With a_r = plain inverse DFT
 // (scale 1/n) of the evaluations on coset r (x = s_r w_n^i, s_r = offset g_N^r), the residue of f

@@ -106,6 +106,14 @@ class Context:
         self._check(self.lib.aero_ctx_profile_read(self.h, buf, ctypes.byref(ln)))
         return {k: (int(v[0]), float(v[1])) for k, v in json.loads(buf.value.decode()).items()}
 
+    def shard_begin(self, shape_key: str) -> None:
+        """Brackets a sharded operation outside Context.prove (aero_ctx_shard_begin): device-side rank barriers
+        once ``shape_key`` has completed before on this context."""
+        self._check(self.lib.aero_ctx_shard_begin(self.h, shape_key.encode()))
+
+    def shard_end(self, ok: bool = True) -> None:
+        self._check(self.lib.aero_ctx_shard_end(self.h, int(ok)))
+
     def sync(self) -> None:
         self._check(self.lib.aero_device_sync(self.h))
 

@@ -25,10 +25,11 @@ def test_segment_commit_matches_oracle_large(ctx, oracle, logn, width):
     seg.destroy()
 
 
-@pytest.mark.parametrize("logn,width", [(23, 2), (24, 1)])
+@pytest.mark.parametrize("logn,width", [(23, 2), (24, 1), (25, 1), (26, 1)])
 def test_segment_commit_properties_max_size(ctx, oracle, logn, width):
-    """2^23 / 2^24 rows (LDE domain 2^26 / 2^27): interpolation, extension, row hash, tree and
-    openings tied together without a full CPU restatement of the commitment."""
+    """2^23 .. 2^26 rows (LDE domain 2^26 .. 2^29): interpolation, extension, row hash, tree and
+    openings tied together without a full CPU restatement of the commitment.  2^25 and 2^26 rows -- the
+    top of BASELINE's NTT sweep -- run one outer radix-2 / radix-4 step over 2^24-point transforms."""
     n = 1 << logn
     N = 8 * n
     trace = oracle.synthetic_trace(width, n, 0xAE2B0000 + logn)
