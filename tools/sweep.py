@@ -11,7 +11,7 @@ Per configuration it prints one JSON line:
   merkle_gbs  algorithmic bytes of the tree (read 32N + write 32N) / time
 and the fractions of the HBM roofline (MEASURED_PEAKS.json) and of the measured ALU-pipe peak.
 
-usage: python tools/sweep.py [--logs 16,18,20,22,24,26] [--cols 1,8,72,255] [--reps 3] [--out gpurun_out/sweep.jsonl]
+usage: python tools/sweep.py [--sizes 16,18,20,22,24,26] [--widths 1,8,72,255] [--reps 3] [--out gpurun_out/sweep.jsonl]
 Traces of 2^25 / 2^26 rows (LDE domain 2^28 / 2^29) take one outer radix-2 / radix-4 step over 2^24-point
 transforms.  Under torch.distributed.run (--nproc-per-node G) every rank extends and hashes its own LDE cosets
 of the same columns (the coset shard of a multi-GPU proof, without the exchange) and rank 0 reports the
@@ -32,8 +32,8 @@ sys.path.insert(0, ROOT)
 
 def main() -> None:
     ap = argparse.ArgumentParser()
-    ap.add_argument("--logs", default="16,18,20,22,24")
-    ap.add_argument("--cols", default="1,8,72,255")
+    ap.add_argument("--sizes", default="16,18,20,22,24")
+    ap.add_argument("--widths", default="1,8,72,255")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--mem-gb", type=float, default=150.0, help="skip shapes whose resident set exceeds this (per GPU)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.jsonl"))
@@ -58,8 +58,8 @@ def main() -> None:
         os.makedirs(os.path.dirname(args.out), exist_ok=True)
         out = open(args.out, "w")
     B = 8
-    logs = [int(x) for x in args.logs.split(",")]
-    cols = [int(x) for x in args.cols.split(",")]
+    logs = [int(x) for x in args.sizes.split(",")]
+    cols = [int(x) for x in args.widths.split(",")]
     if world > 1:  # one window for the largest shape of the sweep
         from aero_b200.sharded import ShardExchange, window_bytes
         fits = [(lg, w) for lg in logs for w in cols if _need_gib(lg, w, world) <= args.mem_gb]
@@ -108,6 +108,9 @@ def main() -> None:
                 dist.all_reduce(t_, op=dist.ReduceOp.MAX)
                 ms = float(t_.item())
             t = {k.rsplit("_w", 1)[0]: v[1] / args.reps for k, v in prof.items()}  # ms per commit on this rank
+            for k in ("interpolate", "lde", "hash_rows", "merkle"):  # a rank may own no column of a narrow matrix
+                t.setdefault(k, 0.0)
+            eps = 1e-9
             bfly = 9 * w * (n // 2) * logn / world
             comps = N * ((w + 1) // 2) / world
             line = {"log_rows": logn, "cols": w, "blowup": B, "n_gpus": world, "root": root.hex()[:16],
@@ -115,11 +118,11 @@ def main() -> None:
                     "interpolate_ms": t.get("interpolate"), "lde_ms": t.get("lde"), "hash_rows_ms": t.get("hash_rows"),
                     "merkle_ms": t.get("merkle"), "push_polys_ms": t.get("push_polys"),
                     # per-rank kernel rates (rank 0's share of the work / rank 0's kernel time)
-                    "lde_gbs": 72 * n * w / world / (t["lde"] * 1e-3) / 1e9,
-                    "ntt_bfly_s": bfly / ((t["lde"] + t["interpolate"]) * 1e-3),
-                    "hash_gbs": (8 * w * N + 32 * N) / world / (t["hash_rows"] * 1e-3) / 1e9,
-                    "comp_s": comps / (t["hash_rows"] * 1e-3),
-                    "merkle_gbs": 64 * N / world / (t["merkle"] * 1e-3) / 1e9}
+                    "lde_gbs": 72 * n * w / world / ((t["lde"] + eps) * 1e-3) / 1e9,
+                    "ntt_bfly_s": bfly / ((t["lde"] + t["interpolate"] + eps) * 1e-3),
+                    "hash_gbs": (8 * w * N + 32 * N) / world / ((t["hash_rows"] + eps) * 1e-3) / 1e9,
+                    "comp_s": comps / ((t["hash_rows"] + eps) * 1e-3),
+                    "merkle_gbs": 64 * N / world / ((t["merkle"] + eps) * 1e-3) / 1e9}
             line["lde_frac_hbm"] = line["lde_gbs"] / hbm
             line["hash_frac_hbm"] = line["hash_gbs"] / hbm
             line["hash_frac_alu"] = line["comp_s"] * 661 / alu_peak
