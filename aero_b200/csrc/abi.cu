@@ -105,6 +105,7 @@ struct aero_ctx {
     int upload_batch_cols = 8;                 // columns per host->device copy batch of aero_segment_commit
     int upload_edge_cols = -1;                 // size of its first / last batch (-1: half a batch, 0: uniform batches)
     size_t ntt_table_max_bytes = (size_t)1 << 30;  // largest full inter-pass twiddle table a plan may hold
+    int ntt_outer_log = -1;  // third factor of two-pass transforms: -1 = 2^(logn-20) above 2^20 points, 0 = never, k = force 2^k (tests)
     int shard_rank = 0, shard_world = 1;       // LDE coset shard of this context (multi-GPU)
     std::multimap<size_t, void *> free_blocks;  // exact-size cache of released device blocks
     std::map<void *, size_t> live_blocks;
@@ -539,9 +540,10 @@ static void fill_pow_table(std::vector<uint64_t> &lo, std::vector<uint64_t> &hi,
 
 // shifts: per-coset input shift s_r (evaluate p on s_r * <w_n>), or all 1.
 // scale_c: constant folded into the result.  post_base != 0: out[i] *= post_base^i.
-static aero_status get_plan(aero_ctx *ctx, const std::string &key, int logn, bool inverse,
+static aero_status get_plan(aero_ctx *ctx, const std::string &key_in, int logn, bool inverse,
                             const std::vector<uint64_t> &shifts, uint64_t scale_c, uint64_t post_base,
                             const DftTables **out) {
+    const std::string key = key_in + "/o" + std::to_string(ctx->ntt_outer_log);  // the split is part of the plan
     auto it = ctx->plans.find(key);
     if (it != ctx->plans.end()) {
         *out = &it->second;
@@ -574,16 +576,25 @@ static aero_status get_plan(aero_ctx *ctx, const std::string &key, int logn, boo
             TRY(upload_vec(ctx, &t.post_u, pu));
         }
     } else {
-        t.log2 = logn / 2;
-        t.log1 = logn - t.log2;
-        const uint64_t n1 = 1ULL << t.log1, n2 = 1ULL << t.log2;
-        const uint64_t w1 = gl::pow(w, n2), w2 = gl::pow(w, n1);
-        std::vector<uint64_t> st1((size_t)t.ncosets * n1), st2(n2), ib((size_t)t.ncosets * n2);
+        // Above 2^20 points a third factor n0 is split off so that both shared-memory passes stay 2^10-point
+        // transforms (ntt.cuh); plans with an output scale (the coset interpolation, which also permutes its
+        // output) keep two passes.
+        if (!post_base) {
+            if (ctx->ntt_outer_log < 0) t.log0 = logn > 20 ? logn - 20 : 0;
+            else if (ctx->ntt_outer_log <= NTT_OUTER_MAX_LOG && logn - ctx->ntt_outer_log >= 12) t.log0 = ctx->ntt_outer_log;
+        }
+        const int rem = logn - t.log0;
+        t.log2 = rem / 2;
+        t.log1 = rem - t.log2;
+        const uint64_t n1 = 1ULL << t.log1, n2 = 1ULL << t.log2, n0 = 1ULL << t.log0;
+        const uint64_t nq = n2 * n0;  // tile columns of pass 1
+        const uint64_t w1 = gl::pow(w, nq), w2 = gl::pow(w, n1 * n0);
+        std::vector<uint64_t> st1((size_t)t.ncosets * n1), st2(n2), ib((size_t)t.ncosets * nq);
         for (int r = 0; r < t.ncosets; r++) {
-            fill_stage_table(st1.data() + (size_t)r * n1, t.log1, gl::pow(shifts[r], n2), w1);
+            fill_stage_table(st1.data() + (size_t)r * n1, t.log1, gl::pow(shifts[r], nq), w1);
             uint64_t x = scale_c;
-            for (uint64_t j2 = 0; j2 < n2; j2++) {
-                ib[(size_t)r * n2 + j2] = x;
+            for (uint64_t q = 0; q < nq; q++) {
+                ib[(size_t)r * nq + q] = x;
                 x = gl::mul(x, shifts[r]);
             }
         }
@@ -591,6 +602,21 @@ static aero_status get_plan(aero_ctx *ctx, const std::string &key, int logn, boo
         TRY(upload_vec(ctx, &t.stage1, st1));
         TRY(upload_vec(ctx, &t.stage2, st2));
         TRY(upload_vec(ctx, &t.inter_b, ib));
+        if (t.log0) {
+            // pass 2 of a three-pass plan: result (i2; j0) times w_(n2 n0)^(i2 j0), w_(n2 n0) = w^n1
+            std::vector<uint64_t> pj((size_t)n0 * n2);
+            const uint64_t wq = gl::pow(w, n1);
+            uint64_t wj = 1;  // wq^j0
+            for (uint64_t j0 = 0; j0 < n0; j0++) {
+                uint64_t x = 1;
+                for (uint64_t i2 = 0; i2 < n2; i2++) {
+                    pj[j0 * n2 + i2] = x;
+                    x = gl::mul(x, wj);
+                }
+                wj = gl::mul(wj, wq);
+            }
+            TRY(upload_vec(ctx, &t.post_j, pj));
+        }
         t.lo_bits = (logn + 1) / 2;
         std::vector<uint64_t> lo, hi;
         fill_pow_table(lo, hi, w, logn, t.lo_bits, 1);
@@ -1477,6 +1503,7 @@ aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value)
     else if (k == "hash_blocks_per_sm" && value > 0) ctx->hash_blocks_per_sm = (int)value;
     else if (k == "lde_batch_bytes" && value > 0) ctx->lde_batch_bytes = (size_t)value;
     else if (k == "ntt_table_max_bytes" && value >= 0) ctx->ntt_table_max_bytes = (size_t)value;
+    else if (k == "ntt_outer_log" && value >= -1 && value <= NTT_OUTER_MAX_LOG) ctx->ntt_outer_log = (int)value;
     else if (k == "upload_batch_cols" && value >= 1 && value <= 255) ctx->upload_batch_cols = (int)value;
     else if (k == "upload_edge_cols" && value >= -1 && value <= 255) ctx->upload_edge_cols = (int)value;
     else if (k == "cache_limit_bytes" && value >= 0) {

@@ -1,7 +1,10 @@
 // Goldilocks NTT kernels for sm_100a: shared-memory DIT transforms with register radix-8 rounds,
 // four-step two-pass decomposition for n > 2^11.  See ntt.cuh for the mapping to the reference.
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is resolved through cudaGetDriverEntryPoint)
 
 #include "gl.cuh"
 #include "ntt.cuh"
@@ -22,6 +25,48 @@ __device__ __forceinline__ void cp_async8_saddr(unsigned sa, const uint64_t *gme
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ---- TMA (bulk asynchronous copies completing on an mbarrier) --------------------------------------
+// The 2^9 / 2^10-point passes (BULK instantiations) fetch their tile and twiddles with a handful of TMA
+// operations issued by one thread -- a 1-D cp.async.bulk where the tile is contiguous (pass 2, twiddles),
+// a tiled cp.async.bulk.tensor through a CUtensorMap where it is M rows of T words at a row stride
+// (pass 1) -- instead of 32 LDGSTS + BREV + 64-bit add per thread.  The tile lands DENSE and in natural
+// row order; the first DIT round reads its bit-reversed inputs from there (dit_round<DENSE>).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// Spins until the phase with the given parity has completed.  A copy that can never complete (which would
+// be a bug in the byte count) traps after ~1 s instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; spins++) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+        if (spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void *gmem_src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gmem_src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void tensor3d_g2s(unsigned smem_dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned mbar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_dst),
+                 "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 
 // Shared-memory layout of an M x T tile: row `row` starts at word row*RS + T*(row >> r1), RS = T + 1 for
 // T > 1 (so that the transposed accesses of the store stages spread over the banks), plus T words of
@@ -109,8 +154,52 @@ __host__ __device__ constexpr bool dft_need_canon(int R, int q, int e) {
 // PLAIN0: first round (s0 == 0) of a transform without coset shift: all general twiddles are 1.
 // IN_CANON: the tile holds canonical values already (pass 2 reads what pass 1 stored with
 // mul_canon), so a PLAIN0 round has nothing to canonicalise on the way in.
-template <int R, int T, int RS, bool PLAIN0, bool INV, bool IN_CANON = false, bool FIRST = PLAIN0>
+// The 2^R-point DFT network of a round on registers: x[e] holds the input of bit-reversed residue e (any
+// u64 congruent to the value; canonical where dft_need_canon(R, 0, e)), afterwards x[k] is output k
+// ("any").  All twiddles are powers of two (gl::mul_pow2), negated where the exponent is >= 96.
+template <int R, bool INV>
+__device__ __forceinline__ void dft_network(uint64_t (&x)[1 << R]) {
+    static_for<R>([&](auto Q) {
+        constexpr int q = decltype(Q)::value;
+        static_for<(1 << R)>([&](auto E) {
+            constexpr int e = decltype(E)::value;
+            if constexpr ((e & (1 << q)) == 0) {
+                constexpr int f = e | (1 << q);
+                constexpr int ex = dft_tw_exp(q, e & ((1 << q) - 1), INV);
+                constexpr bool canon_sum = dft_need_canon(R, q + 1, e);
+                const uint64_t u = x[e];
+                if constexpr (ex == 0) {
+                    const uint64_t v = x[f];
+                    x[e] = canon_sum ? gl::add_cc(u, v) : gl::add_ac(u, v);
+                    x[f] = gl::sub_ac(u, v);
+                } else if constexpr (ex < 96) {
+                    const uint64_t v = gl::mul_pow2<ex>(x[f]);
+                    x[e] = canon_sum ? gl::add_cc(u, v) : gl::add_ac(u, v);
+                    x[f] = gl::sub_ac(u, v);
+                } else {
+                    const uint64_t v = gl::mul_pow2<ex - 96>(x[f]);  // twiddle = -2^(ex-96)
+                    static_assert(!canon_sum, "only unit-twiddle butterflies feed canonical sums");
+                    x[e] = gl::sub_ac(u, v);
+                    x[f] = gl::add_ac(u, v);
+                }
+            }
+        });
+    });
+}
+
+__host__ __device__ constexpr int dft_bitrev(int e, int bits) {
+    int r = 0;
+    for (int b = 0; b < bits; b++) r |= ((e >> b) & 1) << (bits - 1 - b);
+    return r;
+}
+// DENSE (first round of a BULK pass): the tile was delivered by TMA, dense (row j at a[j*T]) and in NATURAL
+// row order.  Group p of the round (bit-reversed positions p*2^R + e) is the natural rows
+// bitrev_R(e)*G + q, G = M >> R, q = bitrev(p): thread (q, t) reads those -- a warp reads 32 consecutive
+// words per e -- and, after a barrier (every thread owns exactly one item, so all reads of the dense tile
+// precede all writes), stores its outputs to rows (p << R) + e of the padded layout, in place.
+template <int R, int T, int RS, bool PLAIN0, bool INV, bool IN_CANON = false, bool FIRST = PLAIN0, bool DENSE = false>
 __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s0, int logM, int r1) {
+    static_assert(!DENSE || FIRST, "only the first round reads the dense tile");
     if (FIRST) s0 = 0;
     const int ngroups = (1 << logM) >> R;
     const int items = ngroups * T;
@@ -120,43 +209,31 @@ __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
         const int t = it % T, g = it / T;
         const int low = g & ((1 << s0) - 1);
-        const int base = ((g >> s0) << (s0 + R)) | low;
-        uint64_t *ag = a + tile_off<T, RS>(base, r1) + t;
+        int base = ((g >> s0) << (s0 + R)) | low;
         uint64_t x[1 << R];
+        if constexpr (DENSE) {
+            const int lg = logM - R;
+            base = (lg ? (int)(__brev((uint32_t)g) >> (32 - lg)) : 0) << R;
+            const uint64_t *dg = a + g * T + t;
+            const int dstep = T << lg;
+            static_for<(1 << R)>([&](auto E) {
+                constexpr int e = decltype(E)::value;
+                x[e] = dg[dft_bitrev(e, R) * dstep];
+            });
+            __syncthreads();
+        }
+        uint64_t *ag = a + tile_off<T, RS>(base, r1) + t;
         // tile values are "any" (congruent mod p, < 2^64); products are canonical
         static_for<(1 << R)>([&](auto E) {
             constexpr int e = decltype(E)::value;
-            uint64_t v = ag[e * astep];
+            uint64_t v;
+            if constexpr (DENSE) v = x[e];
+            else v = ag[e * astep];
             if constexpr (e > 0 && !PLAIN0) v = gl::mul_canon(v, tw[(e << s0) + low]);
             else if constexpr (!IN_CANON && dft_need_canon(R, 0, e)) v = gl::canon_any(v);
             x[e] = v;
         });
-        static_for<R>([&](auto Q) {
-            constexpr int q = decltype(Q)::value;
-            static_for<(1 << R)>([&](auto E) {
-                constexpr int e = decltype(E)::value;
-                if constexpr ((e & (1 << q)) == 0) {
-                    constexpr int f = e | (1 << q);
-                    constexpr int ex = dft_tw_exp(q, e & ((1 << q) - 1), INV);
-                    constexpr bool canon_sum = dft_need_canon(R, q + 1, e);
-                    const uint64_t u = x[e];
-                    if constexpr (ex == 0) {
-                        const uint64_t v = x[f];
-                        x[e] = canon_sum ? gl::add_cc(u, v) : gl::add_ac(u, v);
-                        x[f] = gl::sub_ac(u, v);
-                    } else if constexpr (ex < 96) {
-                        const uint64_t v = gl::mul_pow2<ex>(x[f]);
-                        x[e] = canon_sum ? gl::add_cc(u, v) : gl::add_ac(u, v);
-                        x[f] = gl::sub_ac(u, v);
-                    } else {
-                        const uint64_t v = gl::mul_pow2<ex - 96>(x[f]);  // twiddle = -2^(ex-96)
-                        static_assert(!canon_sum, "only unit-twiddle butterflies feed canonical sums");
-                        x[e] = gl::sub_ac(u, v);
-                        x[f] = gl::add_ac(u, v);
-                    }
-                }
-            });
-        });
+        dft_network<R, INV>(x);
         static_for<(1 << R)>([&](auto E) {
             constexpr int e = decltype(E)::value;
             ag[e * astep] = x[e];
@@ -164,14 +241,15 @@ __device__ __forceinline__ void dit_round(uint64_t *a, const uint64_t *tw, int s
     }
 }
 
-template <int T, int RS, bool PLAIN0, bool INV, int RMAX, bool IN_CANON = false, bool FIRST = PLAIN0>
+template <int T, int RS, bool PLAIN0, bool INV, int RMAX, bool IN_CANON = false, bool FIRST = PLAIN0, bool DENSE = false>
 __device__ __forceinline__ void dit_round_dispatch(int R, uint64_t *a, const uint64_t *tw, int s0, int logM, int r1) {
     if constexpr (RMAX >= 5) {
-        if (R == 5) {
-            dit_round<5, T, RS, PLAIN0, INV, IN_CANON, FIRST>(a, tw, s0, logM, r1);
+        if (DENSE || R == 5) {  // a BULK pass starts with a 32-point round by construction (see launch_two_pass)
+            dit_round<5, T, RS, PLAIN0, INV, IN_CANON, FIRST, DENSE>(a, tw, s0, logM, r1);
             return;
         }
     }
+    static_assert(!DENSE || RMAX >= 5, "dense tiles are read by 32-point first rounds only");
     switch (R) {
     case 4: dit_round<4, T, RS, PLAIN0, INV, IN_CANON, FIRST>(a, tw, s0, logM, r1); break;
     case 3: dit_round<3, T, RS, PLAIN0, INV, IN_CANON, FIRST>(a, tw, s0, logM, r1); break;
@@ -181,12 +259,12 @@ __device__ __forceinline__ void dit_round_dispatch(int R, uint64_t *a, const uin
 }
 
 // Full M-point DIT over the tile: input in bit-reversed row order, output in natural row order.
-template <int T, int RS, bool PLAIN, bool INV, int RMAX, bool IN_CANON = false>
+template <int T, int RS, bool PLAIN, bool INV, int RMAX, bool IN_CANON = false, bool DENSE = false>
 __device__ __forceinline__ void dit_tile(uint64_t *a, const uint64_t *tw, int logM) {
     const NttRounds rounds(logM);
     const int r1 = rounds.log(0);
     // first round: s0 == 0 is a compile-time fact, which lets PLAIN transforms skip the unit twiddles
-    dit_round_dispatch<T, RS, PLAIN, INV, RMAX, IN_CANON, true>(r1, a, tw, 0, logM, r1);
+    dit_round_dispatch<T, RS, PLAIN, INV, RMAX, IN_CANON, true, DENSE>(r1, a, tw, 0, logM, r1);
     __syncthreads();
     int s0 = r1;
     for (int i = 1; i < rounds.count; i++) {
@@ -214,26 +292,50 @@ __device__ __forceinline__ size_t out_index(uint32_t i, int logn, int deint) {
 // second multiplication per element.
 // MAXT: largest block the instantiation is launched with.  The 256-thread variants have 128+ registers
 // per thread and are the only ones that contain 32-point rounds (64 data registers).
-template <int T, bool PLAIN, bool INV, bool TAB, int MAXT>
+// BULK: tile through the tensor map `tmap` ({n2, n1, ncols} words, box {T, min(n1, 256), 1}), twiddles by a 1-D
+// bulk copy, both completing on one mbarrier; one work item per thread in the first round.
+// colfast: blockIdx.x enumerates (column, coset) -- column fastest -- and blockIdx.y the tile, so that the
+// blocks resident at one time share their slice of the inter-pass table (16 columns read it from L2 for one
+// fetch from DRAM) and their source tile (8 cosets); otherwise grid = (tile, coset, column).
+template <int T, bool PLAIN, bool INV, bool TAB, int MAXT, bool BULK = false>
 __global__ void __launch_bounds__(MAXT) dft_pass1_kernel(const uint64_t *__restrict__ src, uint64_t *__restrict__ tmp,
                                                         const uint64_t *__restrict__ stage1,
                                                         const uint64_t *__restrict__ inter_b,
                                                         const uint64_t *__restrict__ inter_full,
                                                         const uint64_t *__restrict__ wlo,
                                                         const uint64_t *__restrict__ whi, int lo_bits, int log1,
-                                                        int log2, size_t src_col_stride, int ncosets) {
+                                                        int log2, size_t src_col_stride, int ncosets, int ncols, int colfast,
+                                                        const __grid_constant__ CUtensorMap tmap) {
     constexpr int RS = T + 1;
-    extern __shared__ uint64_t smem[];
+    extern __shared__ __align__(128) uint64_t smem[];
     const int n1 = 1 << log1;
     const size_t n = (size_t)1 << (log1 + log2);
     const int r1 = NttRounds(log1).log(0);
     uint64_t *a = smem;                                  // the tile (tile_words)
     uint64_t *tw = smem + tile_words<T, RS>(log1, r1);   // n1
-    const int coset = blockIdx.y, col = blockIdx.z;
-    const uint32_t j2_0 = blockIdx.x * T;
+    int coset = blockIdx.y, col = blockIdx.z;
+    uint32_t j2_0 = blockIdx.x * T;
+    if (colfast) {
+        col = blockIdx.x % ncols;
+        coset = blockIdx.x / ncols;
+        j2_0 = blockIdx.y * T;
+    }
     const uint64_t *s = src + (size_t)col * src_col_stride;
     const int nchunks = n1 / T;
     const uint64_t *ftab = nullptr;
+    unsigned mb = 0;
+    if constexpr (BULK) {
+        __shared__ __align__(8) uint64_t mbar;
+        mb = smem_u32(&mbar);
+        if (threadIdx.x == 0) mbar_init(mb, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int rows = n1 < 256 ? n1 : 256;
+            mbar_expect_tx(mb, (unsigned)((n1 * T + n1) * 8));
+            for (int r = 0; r < n1; r += rows) tensor3d_g2s(smem_u32(a + r * T), &tmap, (int)j2_0, r, col, mb);
+            bulk_g2s(smem_u32(tw), stage1 + (size_t)coset * n1, (unsigned)(n1 * 8), mb);
+        }
+    }
     if (TAB) {
         // this block's slice of the table: T*T consecutive entries in each of the nchunks tiles
         ftab = inter_full + (size_t)coset * n + (size_t)j2_0 * T;
@@ -244,11 +346,15 @@ __global__ void __launch_bounds__(MAXT) dft_pass1_kernel(const uint64_t *__restr
             asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
         }
     }
-    for (int i = threadIdx.x; i < n1; i += blockDim.x) cp_async8(tw + i, stage1 + (size_t)coset * n1 + i);
-    load_tile_bitrev<T, RS>(a, s + j2_0, log1, log2, r1);   // row j1 at s[(j1 << log2) + j2_0 + t]
-    cp_async_wait_all();
-    __syncthreads();
-    dit_tile<T, RS, PLAIN, INV, (MAXT <= 256 ? 5 : 4)>(a, tw, log1);
+    if constexpr (BULK) {
+        mbar_wait(mb, 0);
+    } else {
+        for (int i = threadIdx.x; i < n1; i += blockDim.x) cp_async8(tw + i, stage1 + (size_t)coset * n1 + i);
+        load_tile_bitrev<T, RS>(a, s + j2_0, log1, log2, r1);   // row j1 at s[(j1 << log2) + j2_0 + t]
+        cp_async_wait_all();
+        __syncthreads();
+    }
+    dit_tile<T, RS, PLAIN, INV, (MAXT <= 256 ? 5 : 4), false, BULK>(a, tw, log1);
     uint64_t *o = tmp + ((size_t)col * ncosets + coset) * n;
     const int it0 = threadIdx.x;
     const int ii = it0 % T, t = (it0 / T) % T;
@@ -319,69 +425,115 @@ __global__ void inter_table_kernel(uint64_t *__restrict__ out, const uint64_t *_
 
 // ---- pass 2 -------------------------------------------------------------------------------
 // grid: (n1/T, ncosets, ncols)
-template <int T, bool INV, int MAXT>
+// BULK: the tile is one contiguous block of tmp (T * n2 words): a single 1-D bulk copy, another for the
+// twiddles, one mbarrier.
+template <int T, bool INV, int MAXT, bool BULK = false>
 __global__ void __launch_bounds__(MAXT) dft_pass2_kernel(const uint64_t *__restrict__ tmp, uint64_t *__restrict__ dst,
                                                         const uint64_t *__restrict__ stage2,
                                                         const uint64_t *__restrict__ post_u,
                                                         const uint64_t *__restrict__ post_v, int log1, int log2,
-                                                        size_t dst_col_stride, int ncosets, int deint) {
+                                                        size_t dst_col_stride, int ncosets, int deint, int log0,
+                                                        const uint64_t *__restrict__ post_j) {
+    // log0 > 0 (three-pass plan): blockIdx.x = (tile of i1) * n0 + j0; the block transforms tile columns
+    // q = j2*n0 + j0 of pass 1's output and writes block j0 (n1*n2 words) of the destination; deint == 0.
     constexpr int RS = T + 1;
-    extern __shared__ uint64_t smem[];
+    extern __shared__ __align__(128) uint64_t smem[];
     const int n2 = 1 << log2;
-    const int logn = log1 + log2;
-    const size_t n = (size_t)1 << logn;
+    const int logn = log1 + log2;          // of one destination block
+    const size_t n = (size_t)1 << (logn + log0);
     const int r1 = NttRounds(log2).log(0);
     uint64_t *a = smem;
     uint64_t *tw = smem + tile_words<T, RS>(log2, r1);
     const int coset = blockIdx.y, col = blockIdx.z;
-    const uint32_t i1_0 = blockIdx.x * T;
-    const uint64_t *s = tmp + ((size_t)col * ncosets + coset) * n + ((size_t)blockIdx.x << log2) * T;
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) cp_async8(tw + i, stage2 + i);
-    load_tile_bitrev<T, RS>(a, s, log2, T == 8 ? 3 : 2, r1);   // row j2 at s[j2*T + t]
-    cp_async_wait_all();
-    __syncthreads();
-    dit_tile<T, RS, true, INV, (MAXT <= 256 ? 5 : 4), true>(a, tw, log2);  // tmp is canonical (pass 1's mul_canon)
-    uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n;
-    // thread (j0 = tid / T, t = tid % T) stores rows i2 = j0 + k*J of its tile column i1 = i1_0 + t
+    const uint32_t tile = blockIdx.x >> log0, j0 = blockIdx.x & ((1u << log0) - 1);
+    const uint32_t i1_0 = tile * T;
+    const uint64_t *s = tmp + ((size_t)col * ncosets + coset) * n + ((size_t)tile << (log2 + log0)) * T + (size_t)j0 * T;
+    if constexpr (BULK) {
+        __shared__ __align__(8) uint64_t mbar;
+        const unsigned mb = smem_u32(&mbar);
+        if (threadIdx.x == 0) mbar_init(mb, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(mb, (unsigned)((n2 * T + n2) * 8));
+            bulk_g2s(smem_u32(a), s, (unsigned)(n2 * T * 8), mb);
+            bulk_g2s(smem_u32(tw), stage2, (unsigned)(n2 * 8), mb);
+        }
+        mbar_wait(mb, 0);
+    } else {
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) cp_async8(tw + i, stage2 + i);
+        load_tile_bitrev<T, RS>(a, s, log2, (T == 8 ? 3 : 2) + log0, r1);   // row j2 at s[(j2*n0)*T + t]
+        cp_async_wait_all();
+        __syncthreads();
+    }
+    dit_tile<T, RS, true, INV, (MAXT <= 256 ? 5 : 4), true, BULK>(a, tw, log2);  // tmp is canonical (pass 1's mul_canon)
+    uint64_t *o = dst + (size_t)col * dst_col_stride + (size_t)coset * n + ((size_t)j0 << logn);
+    if (post_j) post_v = post_j + ((size_t)j0 << log2);   // w_(n2 n0)^(i2 j0); post_u stays null
+    // thread (r0 = tid / T, t = tid % T) stores rows i2 = r0 + k*J of its tile column i1 = i1_0 + t
     const int J = blockDim.x / T;
-    const int t = threadIdx.x % T, j0 = threadIdx.x / T;
+    const int t = threadIdx.x % T, r0 = threadIdx.x / T;
     const uint32_t i1 = i1_0 + t;
     const int K = n2 / J;
     if ((J & ((1 << r1) - 1)) != 0) {  // small transforms: rows of a thread inside one padding group
         for (int k = 0; k < K; k++) {
-            const int i2 = j0 + k * J;
+            const int i2 = r0 + k * J;
             uint64_t v = a[tile_off<T, RS>(i2, r1) + t];
             if (post_u) v = gl::mul(v, gl::mul(__ldg(post_u + i1), __ldg(post_v + i2)));
+            else if (post_v) v = gl::mul(v, __ldg(post_v + i2));
             else v = gl::canon_any(v);
             o[out_index(i1 + ((uint32_t)i2 << log1), logn, deint)] = v;
         }
         return;
     }
-    const uint64_t *ap = a + tile_off<T, RS>(j0, r1) + t;
+    const uint64_t *ap = a + tile_off<T, RS>(r0, r1) + t;
     const int astep = J * RS + tile_pad<T>() * (J >> r1);
     if (deint == 0) {
-        uint64_t *op = o + i1 + ((size_t)j0 << log1);
+        uint64_t *op = o + i1 + ((size_t)r0 << log1);
         const size_t ostep = (size_t)J << log1;
         if (post_u) {
             const uint64_t pu = __ldg(post_u + i1);
-            const uint64_t *pv = post_v + j0;
+            const uint64_t *pv = post_v + r0;
 #pragma unroll 4
             for (int k = 0; k < K; k++)
                 op[k * ostep] = gl::mul(ap[k * astep], gl::mul(pu, __ldg(pv + k * J)));
+        } else if (post_v) {
+            const uint64_t *pv = post_v + r0;
+#pragma unroll 4
+            for (int k = 0; k < K; k++) op[k * ostep] = gl::mul(ap[k * astep], __ldg(pv + k * J));
         } else {
 #pragma unroll 4
             for (int k = 0; k < K; k++) op[k * ostep] = gl::canon_any(ap[k * astep]);
         }
     } else {
         for (int k = 0; k < K; k++) {
-            const int i2 = j0 + k * J;
+            const int i2 = r0 + k * J;
             uint64_t v = ap[k * astep];
             if (post_u) v = gl::mul(v, gl::mul(__ldg(post_u + i1), __ldg(post_v + i2)));
+            else if (post_v) v = gl::mul(v, __ldg(post_v + i2));
             else v = gl::canon_any(v);
             const uint32_t i = i1 + ((uint32_t)i2 << log1);
             o[out_index(i, logn, deint)] = v;
         }
     }
+}
+
+// ---- pass 3 (three-pass plans) --------------------------------------------------------------
+// In place: for every position i < m = n1*n2 of a (column, coset) block of n = m * 2^R words, the 2^R-point
+// DFT over the values at i + j0*m (canonical, written by pass 2), output i0 stored at i + i0*m.
+// grid: (m / 256, ncosets, ncols)
+template <int R, bool INV>
+__global__ void __launch_bounds__(256) dft_pass3_kernel(uint64_t *__restrict__ dst, int logm, size_t dst_col_stride) {
+    uint64_t *o = dst + (size_t)blockIdx.z * dst_col_stride + ((size_t)blockIdx.y << (logm + R)) +
+                  (size_t)blockIdx.x * 256 + threadIdx.x;
+    uint64_t x[1 << R];
+    static_for<(1 << R)>([&](auto E) {
+        constexpr int e = decltype(E)::value;
+        x[e] = o[(size_t)dft_bitrev(e, R) << logm];
+    });
+    dft_network<R, INV>(x);
+    static_for<(1 << R)>([&](auto E) {
+        constexpr int e = decltype(E)::value;
+        o[(size_t)e << logm] = gl::canon_any(x[e]);
+    });
 }
 
 // ---- single pass (n <= 2^11) --------------------------------------------------------------
@@ -391,7 +543,7 @@ __global__ void __launch_bounds__(256) dft_single_kernel(const uint64_t *__restr
                                                          const uint64_t *__restrict__ stage,
                                                          const uint64_t *__restrict__ post_u, uint64_t scale, int logn,
                                                          size_t src_col_stride, size_t dst_col_stride, int deint) {
-    extern __shared__ uint64_t smem[];
+    extern __shared__ __align__(128) uint64_t smem[];
     const int n = 1 << logn;
     const int r1 = NttRounds(logn).log(0);
     uint64_t *a = smem;
@@ -434,38 +586,125 @@ void dft_fill_inter_table(const DftTables &t, uint64_t *out, cudaStream_t s) {
     unsigned bx = (unsigned)((n + 255) / 256);
     if (bx > 148 * 16) bx = 148 * 16;
     AERO_COUNT_LAUNCH(1);
-    inter_table_kernel<<<dim3(bx, t.ncosets), 256, 0, s>>>(out, t.inter_b, t.wlo, t.whi, t.lo_bits, t.log1, t.log2,
+    inter_table_kernel<<<dim3(bx, t.ncosets), 256, 0, s>>>(out, t.inter_b, t.wlo, t.whi, t.lo_bits, t.log1, t.log2 + t.log0,
                                                           T == 8 ? 3 : 2);
 }
 
-template <int T, bool PLAIN, bool INV, bool TAB, int MAXT>
-static void launch_pass1(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
+// ---- tensor maps for the BULK pass 1 ------------------------------------------------------------------
+// cuTensorMapEncodeTiled is host-side arithmetic on the descriptor; it is resolved through the runtime so
+// that the library does not link against libcuda.
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                           const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                           CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+    static const TensorMapEncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (TensorMapEncodeTiledFn)p;
+    }();
+    return fn;
+}
+// experiment hooks: AERO_NTT_BULK=0 keeps the LDGSTS tile copies, AERO_NTT_COLFAST=0 the (tile, coset, column) grid
+static int env_flag(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+static bool ntt_use_bulk() {
+    static const bool on = env_flag("AERO_NTT_BULK", 1) != 0;
+    return on;
+}
+static bool ntt_colfast() {
+    static const bool on = env_flag("AERO_NTT_COLFAST", 1) != 0;
+    return on;
+}
+// {n2, n1, ncols} words with strides {8, 8*n2, 8*col_stride} bytes; box {T, min(n1, 256), 1}
+static bool encode_pass1_map(CUtensorMap *m, const uint64_t *src, int log1, int log2, int ncols, size_t col_stride, int T) {
+    const TensorMapEncodeTiledFn fn = tensor_map_encoder();
+    if (!fn || ((uintptr_t)src & 15)) return false;
+    const cuuint64_t n1 = 1ULL << log1, n2 = 1ULL << log2;
+    if (ncols > 1 && ((col_stride & 1) || col_stride < n1 * n2)) return false;
+    const cuuint64_t dims[3] = {n2, n1, (cuuint64_t)ncols};
+    const cuuint64_t strides[2] = {n2 * 8, (ncols > 1 ? (cuuint64_t)col_stride : n1 * n2) * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)T, (cuuint32_t)(n1 < 256 ? n1 : 256), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void *)src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int T, bool PLAIN, bool INV, bool TAB, int MAXT, bool BULK>
+static void launch_pass1_impl(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, const CUtensorMap &map,
+                              cudaStream_t s) {
     static DeviceOnce once;  // function attributes are per device
     once.run([] {
-        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT, BULK>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     });
-    const int n1 = 1 << t.log1, n2 = 1 << t.log2;
+    const int logq = t.log2 + t.log0;   // pass 1 sees n2 * n0 tile columns
+    const int n1 = 1 << t.log1, nq = 1 << logq;
     const size_t n = (size_t)1 << t.logn;
-    dim3 g1(n2 / T, nc, l.ncols);
-    dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT><<<g1, threads, smem, s>>>(
-        l.src, l.tmp, t.stage1 + (size_t)l.coset_begin * n1, t.inter_b + (size_t)l.coset_begin * n2,
-        TAB ? t.inter_full + (size_t)l.coset_begin * n : nullptr, t.wlo, t.whi, t.lo_bits, t.log1, t.log2,
-        l.src_col_stride, nc);
+    // column-fastest block order needs (columns x cosets) in grid.x and the tiles in grid.y (<= 65535)
+    const bool colfast = ntt_colfast() && nq / T <= 65535;
+    const dim3 g1 = colfast ? dim3((unsigned)l.ncols * nc, nq / T, 1) : dim3(nq / T, nc, l.ncols);
+    dft_pass1_kernel<T, PLAIN, INV, TAB, MAXT, BULK><<<g1, threads, smem, s>>>(
+        l.src, l.tmp, t.stage1 + (size_t)l.coset_begin * n1, t.inter_b + (size_t)l.coset_begin * nq,
+        TAB ? t.inter_full + (size_t)l.coset_begin * n : nullptr, t.wlo, t.whi, t.lo_bits, t.log1, logq,
+        l.src_col_stride, nc, l.ncols, colfast ? 1 : 0, map);
 }
-template <int T, bool INV, int MAXT>
-static void launch_pass2(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
+template <int T, bool PLAIN, bool INV, bool TAB, int MAXT>
+static void launch_pass1(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
+    CUtensorMap map;
+    memset(&map, 0, sizeof map);
+    if constexpr (MAXT == 256 && T == 8) {
+        // one work item per thread in the first (32-point) round is what the dense tile needs
+        const int items = ((1 << t.log1) >> 5) * T;
+        if (ntt_use_bulk() && NttRounds(t.log1).log(0) == 5 && items == threads &&
+            encode_pass1_map(&map, l.src, t.log1, t.log2 + t.log0, l.ncols, l.src_col_stride, T)) {
+            launch_pass1_impl<T, PLAIN, INV, TAB, MAXT, true>(t, l, nc, threads, smem, map, s);
+            return;
+        }
+    }
+    launch_pass1_impl<T, PLAIN, INV, TAB, MAXT, false>(t, l, nc, threads, smem, map, s);
+}
+template <int T, bool INV, int MAXT, bool BULK>
+static void launch_pass2_impl(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
     static DeviceOnce once;
     once.run([] {
-        cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT, BULK>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     });
     const int n1 = 1 << t.log1;
-    dim3 g2(n1 / T, nc, l.ncols);
-    dft_pass2_kernel<T, INV, MAXT><<<g2, threads, smem, s>>>(l.tmp, l.dst, t.stage2, t.post_u, t.post_v, t.log1, t.log2,
-                                                       l.dst_col_stride, nc, l.deinterleave_log);
+    dim3 g2((n1 / T) << t.log0, nc, l.ncols);
+    dft_pass2_kernel<T, INV, MAXT, BULK><<<g2, threads, smem, s>>>(l.tmp, l.dst, t.stage2, t.post_u, t.post_v, t.log1, t.log2,
+                                                             l.dst_col_stride, nc, l.deinterleave_log, t.log0, t.post_j);
+}
+template <int T, bool INV, int MAXT>
+static void launch_pass2(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
+    if constexpr (MAXT == 256 && T == 8) {
+        const int items = ((1 << t.log2) >> 5) * T;
+        // the tile is T * n2 contiguous words of tmp, 16-byte aligned whenever tmp is
+        if (ntt_use_bulk() && t.log0 == 0 && NttRounds(t.log2).log(0) == 5 && items == threads && ((uintptr_t)l.tmp & 15) == 0) {
+            launch_pass2_impl<T, INV, MAXT, true>(t, l, nc, threads, smem, s);
+            return;
+        }
+    }
+    launch_pass2_impl<T, INV, MAXT, false>(t, l, nc, threads, smem, s);
+}
+
+template <bool INV>
+static void launch_pass3(const DftTables &t, const DftLaunch &l, int nc, cudaStream_t s) {
+    const int logm = t.log1 + t.log2;
+    const dim3 g(1u << (logm - 8), nc, l.ncols);
+    switch (t.log0) {
+    case 1: dft_pass3_kernel<1, INV><<<g, 256, 0, s>>>(l.dst, logm, l.dst_col_stride); break;
+    case 2: dft_pass3_kernel<2, INV><<<g, 256, 0, s>>>(l.dst, logm, l.dst_col_stride); break;
+    case 3: dft_pass3_kernel<3, INV><<<g, 256, 0, s>>>(l.dst, logm, l.dst_col_stride); break;
+    default: dft_pass3_kernel<4, INV><<<g, 256, 0, s>>>(l.dst, logm, l.dst_col_stride); break;
+    }
 }
 
 template <int T>
@@ -507,6 +746,10 @@ static void launch_two_pass(const DftTables &t, const DftLaunch &l, cudaStream_t
     (w2 ? launch_pass2<T, INV, 256>(t, l, nc, th2, smem2, s) : launch_pass2<T, INV, 1024>(t, l, nc, th2, smem2, s))
     if (t.inverse) AERO_P2(true); else AERO_P2(false);
 #undef AERO_P2
+    if (t.log0 > 0) {
+        AERO_COUNT_LAUNCH(1);
+        if (t.inverse) launch_pass3<true>(t, l, nc, s); else launch_pass3<false>(t, l, nc, s);
+    }
 }
 
 template <bool PLAIN, bool INV>

@@ -9,6 +9,12 @@
 //           times the inter-pass factor s^j2 * w_n^(i1*j2), stored in T x T tiles;
 //   pass 2: n2-point DFTs over j2, natural-order store.
 // Sizes up to 2^11 run in a single shared-memory pass.
+// Above 2^20 points a third factor n0 <= 16 is split off (n = n1*n2*n0, n1 = n2 = 2^10) so that both
+// shared-memory passes stay 2^10-point transforms (two 32-point rounds each, the fastest shape):
+//   pass 1: as above with n2*n0 in the place of n2 (tile columns q = j2*n0 + j0);
+//   pass 2: for every j0, n2-point DFTs over j2 (rows n0 tile columns apart), times w_(n2 n0)^(i2 j0),
+//           stored at i1 + n1*i2 + n1*n2*j0 of the destination;
+//   pass 3: in place, n0-point DFTs over j0 (stride n1*n2) whose twiddles are powers of two.
 //
 // Each shared-memory transform is a mixed-radix DIT of register-resident rounds of 2^R points
 // (R <= NTT_MAX_ROUND_LOG).  Only the inputs of a round are multiplied by general twiddles; the
@@ -21,7 +27,8 @@
 namespace aero {
 
 constexpr int NTT_SINGLE_MAX_LOG = 11;  // largest single-pass transform
-constexpr int NTT_MAX_LOG = 24;         // two passes of <= 2^12 points
+constexpr int NTT_MAX_LOG = 24;         // two passes of <= 2^12 points, or 2^10 x 2^10 x (<= 2^4)
+constexpr int NTT_OUTER_MAX_LOG = 4;    // largest third factor n0 of a three-pass plan
 constexpr int NTT_LARGE_MAX_LOG = 26;   // with one outer radix-2 / radix-4 step over 2^24-point transforms (abi.cu)
 constexpr int NTT_MAX_ROUND_LOG = 5;    // largest register-resident round: 32 points
 
@@ -41,7 +48,8 @@ struct NttRounds {
 
 // Device-resident tables of one transform "plan" (built on the host once per shape, cached).
 struct DftTables {
-    int logn = 0, log1 = 0, log2 = 0;  // n = n1 * n2 ; log1 == 0 means single pass (n2 = n)
+    int logn = 0, log1 = 0, log2 = 0;  // n = n1 * n2 * n0; log1 == 0 means single pass (n2 = n)
+    int log0 = 0;                     // > 0: three-pass plan (pass 1 sees n2 * n0 tile columns)
     int ncosets = 1;
     bool plain = false;               // no coset shift (all shifts == 1): unit twiddles are skipped
     bool inverse = false;             // transform root is w_n^-1 (selects the shifts inside a round)
@@ -56,6 +64,7 @@ struct DftTables {
     uint64_t *wlo = nullptr, *whi = nullptr;
     uint64_t *post_u = nullptr;       // optional output scale: out[i] *= post_u[i1] * post_v[i2]
     uint64_t *post_v = nullptr;       //   (single pass: post_u[i], post_v unused)
+    uint64_t *post_j = nullptr;       // three-pass plans: [n0][n2]  w_(n2 n0)^(i2 j0), applied by pass 2
     uint64_t single_scale = 1;        // single pass: constant output scale when post_u == nullptr
 };
 

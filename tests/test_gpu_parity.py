@@ -35,6 +35,25 @@ def test_segment_commit_matches_oracle(ctx, oracle, logn, width):
     assert seg.root == ref.root, "Merkle root mismatch"
 
 
+@pytest.mark.parametrize("logn,outer", [(13, 1), (14, 2), (15, 3), (16, 4), (16, 1), (17, 2)])
+def test_three_pass_transforms_match_oracle(oracle, logn, outer):
+    """Transforms above 2^20 points split off a third factor n0 (n = n1*n2*n0: pass 2 per j0, in-place n0-point
+    pass 3; ntt.cuh).  The same plan forced onto sizes the oracle covers must give the oracle's coefficients,
+    LDE and root -- interpolation (plain inverse) and coset extension both go through it."""
+    c = aero_b200.Context(0, form=aero_b200.AERO_FORM_CANONICAL)
+    try:
+        c.set_option("ntt_outer_log", outer)
+        n = 1 << logn
+        trace = oracle.synthetic_trace(3, n, 0xAE230000 + logn)
+        ref = oracle.build_trace_commitment(trace, 8)
+        seg = c.build_trace_commitment(trace, 8)
+        assert np.array_equal(seg.download_polys(), ref.polys), "interpolate_columns mismatch"
+        assert np.array_equal(seg.download_lde(), ref.lde), "evaluate_columns_over mismatch"
+        assert seg.root == ref.root
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("blowup", [2, 4, 16])
 def test_segment_commit_other_blowups(ctx, oracle, blowup):
     trace = oracle.synthetic_trace(3, 256, 77)
