@@ -1417,6 +1417,10 @@ aero_status aero_ctx_create(const int *device_ids, int n_devices, aero_ctx **out
     if (prop.major < 10) return AERO_ERR_UNSUPPORTED;  // kernels are built for sm_100a only
     aero_ctx *ctx = new aero_ctx();
     ctx->device = dev;
+    if (const char *e = getenv("AERO_NTT_OUTER")) {  // experiment hook: default of the "ntt_outer_log" option
+        const int v = atoi(e);
+        if (v >= -1 && v <= NTT_OUTER_MAX_LOG) ctx->ntt_outer_log = v;
+    }
     ctx->num_sms = prop.multiProcessorCount;
     size_t free_b = 0, total_b = 0;
     // released blocks stay cached up to 90 % of the device (a 2^24-row proof holds ~130 GB; with the old

@@ -62,6 +62,11 @@ __device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void *gmem_src
                  "l"(gmem_src), "r"(bytes), "r"(mbar)
                  : "memory");
 }
+__device__ __forceinline__ void tensor4d_g2s(unsigned smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, unsigned mbar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_dst),
+                 "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tensor3d_g2s(unsigned smem_dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned mbar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_dst),
                  "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
@@ -426,14 +431,16 @@ __global__ void inter_table_kernel(uint64_t *__restrict__ out, const uint64_t *_
 // ---- pass 2 -------------------------------------------------------------------------------
 // grid: (n1/T, ncosets, ncols)
 // BULK: the tile is one contiguous block of tmp (T * n2 words): a single 1-D bulk copy, another for the
-// twiddles, one mbarrier.
+// twiddles, one mbarrier.  In a three-pass plan (log0 > 0) the rows of the tile are n0 tile columns apart:
+// `tmap` describes tmp as {T, n0, n2, blocks} words and the tile arrives in boxes {T, 1, min(n2, 256), 1}.
 template <int T, bool INV, int MAXT, bool BULK = false>
 __global__ void __launch_bounds__(MAXT) dft_pass2_kernel(const uint64_t *__restrict__ tmp, uint64_t *__restrict__ dst,
                                                         const uint64_t *__restrict__ stage2,
                                                         const uint64_t *__restrict__ post_u,
                                                         const uint64_t *__restrict__ post_v, int log1, int log2,
                                                         size_t dst_col_stride, int ncosets, int deint, int log0,
-                                                        const uint64_t *__restrict__ post_j) {
+                                                        const uint64_t *__restrict__ post_j,
+                                                        const __grid_constant__ CUtensorMap tmap) {
     // log0 > 0 (three-pass plan): blockIdx.x = (tile of i1) * n0 + j0; the block transforms tile columns
     // q = j2*n0 + j0 of pass 1's output and writes block j0 (n1*n2 words) of the destination; deint == 0.
     constexpr int RS = T + 1;
@@ -455,7 +462,13 @@ __global__ void __launch_bounds__(MAXT) dft_pass2_kernel(const uint64_t *__restr
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(mb, (unsigned)((n2 * T + n2) * 8));
-            bulk_g2s(smem_u32(a), s, (unsigned)(n2 * T * 8), mb);
+            if (log0 == 0) {
+                bulk_g2s(smem_u32(a), s, (unsigned)(n2 * T * 8), mb);
+            } else {
+                const int rows = n2 < 256 ? n2 : 256;
+                const int blk = (int)(((size_t)col * ncosets + coset) * (((size_t)1 << log1) / T) + tile);
+                for (int r = 0; r < n2; r += rows) tensor4d_g2s(smem_u32(a + r * T), &tmap, 0, (int)j0, r, blk, mb);
+            }
             bulk_g2s(smem_u32(tw), stage2, (unsigned)(n2 * 8), mb);
         }
         mbar_wait(mb, 0);
@@ -669,8 +682,23 @@ static void launch_pass1(const DftTables &t, const DftLaunch &l, int nc, int thr
     }
     launch_pass1_impl<T, PLAIN, INV, TAB, MAXT, false>(t, l, nc, threads, smem, map, s);
 }
+// pass 2 of a three-pass plan: tmp as {T, n0, n2, ncols * nc * n1 / T} words; box {T, 1, min(n2, 256), 1}
+static bool encode_pass2_map(CUtensorMap *m, const uint64_t *tmp, int log1, int log2, int log0, int T, size_t nblocks) {
+    const TensorMapEncodeTiledFn fn = tensor_map_encoder();
+    if (!fn || ((uintptr_t)tmp & 15) || nblocks > 0x7fffffffULL) return false;
+    const cuuint64_t n2 = 1ULL << log2, n0 = 1ULL << log0;
+    (void)log1;
+    const cuuint64_t dims[4] = {(cuuint64_t)T, n0, n2, (cuuint64_t)nblocks};
+    const cuuint64_t strides[3] = {(cuuint64_t)T * 8, n0 * T * 8, n2 * n0 * T * 8};
+    const cuuint32_t box[4] = {(cuuint32_t)T, 1, (cuuint32_t)(n2 < 256 ? n2 : 256), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, (void *)tmp, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int T, bool INV, int MAXT, bool BULK>
-static void launch_pass2_impl(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
+static void launch_pass2_impl(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, const CUtensorMap &map,
+                              cudaStream_t s) {
     static DeviceOnce once;
     once.run([] {
         cudaFuncSetAttribute(dft_pass2_kernel<T, INV, MAXT, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -680,19 +708,23 @@ static void launch_pass2_impl(const DftTables &t, const DftLaunch &l, int nc, in
     const int n1 = 1 << t.log1;
     dim3 g2((n1 / T) << t.log0, nc, l.ncols);
     dft_pass2_kernel<T, INV, MAXT, BULK><<<g2, threads, smem, s>>>(l.tmp, l.dst, t.stage2, t.post_u, t.post_v, t.log1, t.log2,
-                                                             l.dst_col_stride, nc, l.deinterleave_log, t.log0, t.post_j);
+                                                             l.dst_col_stride, nc, l.deinterleave_log, t.log0, t.post_j, map);
 }
 template <int T, bool INV, int MAXT>
 static void launch_pass2(const DftTables &t, const DftLaunch &l, int nc, int threads, size_t smem, cudaStream_t s) {
+    CUtensorMap map;
+    memset(&map, 0, sizeof map);
     if constexpr (MAXT == 256 && T == 8) {
         const int items = ((1 << t.log2) >> 5) * T;
-        // the tile is T * n2 contiguous words of tmp, 16-byte aligned whenever tmp is
-        if (ntt_use_bulk() && t.log0 == 0 && NttRounds(t.log2).log(0) == 5 && items == threads && ((uintptr_t)l.tmp & 15) == 0) {
-            launch_pass2_impl<T, INV, MAXT, true>(t, l, nc, threads, smem, s);
+        // the tile is T * n2 contiguous words of tmp, 16-byte aligned whenever tmp is; three-pass plans go
+        // through a tensor map
+        if (ntt_use_bulk() && NttRounds(t.log2).log(0) == 5 && items == threads && ((uintptr_t)l.tmp & 15) == 0 &&
+            (t.log0 == 0 || encode_pass2_map(&map, l.tmp, t.log1, t.log2, t.log0, T, (size_t)l.ncols * nc * ((1u << t.log1) / T)))) {
+            launch_pass2_impl<T, INV, MAXT, true>(t, l, nc, threads, smem, map, s);
             return;
         }
     }
-    launch_pass2_impl<T, INV, MAXT, false>(t, l, nc, threads, smem, s);
+    launch_pass2_impl<T, INV, MAXT, false>(t, l, nc, threads, smem, map, s);
 }
 
 template <bool INV>

@@ -35,7 +35,7 @@ def test_segment_commit_matches_oracle(ctx, oracle, logn, width):
     assert seg.root == ref.root, "Merkle root mismatch"
 
 
-@pytest.mark.parametrize("logn,outer", [(13, 1), (14, 2), (15, 3), (16, 4), (16, 1), (17, 2)])
+@pytest.mark.parametrize("logn,outer", [(13, 1), (14, 2), (15, 3), (16, 4), (16, 1), (17, 2), (19, 1), (20, 2)])
 def test_three_pass_transforms_match_oracle(oracle, logn, outer):
     """Transforms above 2^20 points split off a third factor n0 (n = n1*n2*n0: pass 2 per j0, in-place n0-point
     pass 3; ntt.cuh).  The same plan forced onto sizes the oracle covers must give the oracle's coefficients,
@@ -44,7 +44,8 @@ def test_three_pass_transforms_match_oracle(oracle, logn, outer):
     try:
         c.set_option("ntt_outer_log", outer)
         n = 1 << logn
-        trace = oracle.synthetic_trace(3, n, 0xAE230000 + logn)
+        # 2^19 / 2^20 points: 2^9-point passes, whose tiles arrive through tensor maps (TMA) in both passes
+        trace = oracle.synthetic_trace(3 if logn < 19 else 2, n, 0xAE230000 + logn)
         ref = oracle.build_trace_commitment(trace, 8)
         seg = c.build_trace_commitment(trace, 8)
         assert np.array_equal(seg.download_polys(), ref.polys), "interpolate_columns mismatch"
