@@ -6,7 +6,7 @@ The Python layer is a ctypes face for tests and benchmarks; the product is libae
 from ._lib import (AERO_ERR_BUFFER, AERO_ERR_CUDA, AERO_ERR_INVALID, AERO_ERR_NOMEM, AERO_ERR_STATE,
                    AERO_ERR_UNSUPPORTED, AERO_FORM_CANONICAL, AERO_FORM_MONTGOMERY, AERO_OK, Divisor, ProofOptions,
                    load)
-from .prover import (AeroError, Context, FriProver, Group, RandomCoin, Segment, host_blake2s, host_hash_elements,
+from .prover import (AeroError, AirProgramBuilder, Context, FriProver, Group, RandomCoin, Segment, host_blake2s, host_hash_elements,
                      make_divisor, miden_options)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

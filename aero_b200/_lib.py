@@ -43,6 +43,23 @@ class ProofOptions(ctypes.Structure):
                 ("fri_max_remainder_size", c_uint16)]
 
 
+class AirNode(ctypes.Structure):
+    """aero_air_node: op (AERO_AIR_*), operands a, b."""
+
+    _fields_ = [("op", c_uint32), ("a", c_uint32), ("b", c_uint32)]
+
+
+class AirProgram(ctypes.Structure):
+    """aero_air_program: transition constraints as an arithmetic program + single-value assertions."""
+
+    _fields_ = [("nodes", POINTER(AirNode)), ("n_nodes", c_uint32), ("consts", POINTER(c_uint64)), ("n_consts", c_uint32),
+                ("n_transition", c_uint32), ("transition_out", POINTER(c_uint32)), ("transition_adj", POINTER(c_uint64)),
+                ("n_boundary", c_uint32), ("boundary_col", POINTER(c_uint32)), ("boundary_value", POINTER(c_uint64)),
+                ("boundary_adj", POINTER(c_uint64)), ("boundary_div", POINTER(c_uint32))]
+
+
+AERO_AIR_CUR, AERO_AIR_NEXT, AERO_AIR_CONST, AERO_AIR_ADD, AERO_AIR_SUB, AERO_AIR_MUL = range(6)
+
 AUX_BUILDER = ctypes.CFUNCTYPE(c_int, c_void_p, p_u64, c_uint32, pp_u64)
 CONSTRAINT_EVALUATOR = ctypes.CFUNCTYPE(c_int, c_void_p, pp_u64, c_uint32, c_uint64, p_u64, c_uint32, pp_u64)
 
@@ -56,7 +73,8 @@ class ProveInputs(ctypes.Structure):
                 ("ce_cols", pp_u64), ("divisors", POINTER(Divisor)), ("n_div", c_uint32),
                 ("n_constraint_coeffs", c_uint32), ("ce_blowup", c_uint32), ("aux_builder", AUX_BUILDER),
                 ("constraint_evaluator", CONSTRAINT_EVALUATOR), ("user", c_void_p), ("pub_inputs_bytes", p_u8),
-                ("pub_inputs_len", c_size_t), ("trace_meta", p_u8), ("trace_meta_len", c_uint16)]
+                ("pub_inputs_len", c_size_t), ("trace_meta", p_u8), ("trace_meta_len", c_uint16),
+                ("air_program", POINTER(AirProgram))]
 
 
 # name -> (restype, argtypes).  Every symbol include/*.h declares is listed here; tests assert that
@@ -103,6 +121,10 @@ PROTOTYPES = {
                                            POINTER(c_void_p)]),
     "aero_constraints_into_poly_device": (c_int, [c_void_p, c_void_p, c_size_t, POINTER(Divisor), c_uint32, c_uint64,
                                                   c_uint64, POINTER(c_void_p)]),
+    "aero_constraints_evaluate_device": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, POINTER(AirProgram), p_u64, c_uint32,
+                                                 c_uint32, c_uint32, c_void_p, c_size_t]),
+    "aero_constraints_evaluate_into_poly": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, POINTER(AirProgram), p_u64,
+                                                    c_uint32, c_uint32, POINTER(Divisor), c_uint32, POINTER(c_void_p)]),
     "aero_segment_commit_polys": (c_int, [c_void_p, c_uint32, p_u8]),
     # OOD + DEEP
     "aero_ood_eval": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, c_void_p, c_uint64, p_u64, p_u64]),

@@ -2140,6 +2140,134 @@ aero_status aero_commit_rows_device(aero_ctx *ctx, const uint64_t *d_m, size_t c
 }
 
 // ---- constraints ----------------------------------------------------------------------------
+// ---- AIR constraint evaluation on the device ---------------------------------------------------
+aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs,
+                                             const aero_air_program *prog, const uint64_t *coeffs, uint32_t n_coeffs,
+                                             uint32_t ce_blowup, uint32_t n_div, uint64_t *d_eval_cols, size_t col_stride) {
+    if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
+    if (!trace_segs || !prog || !d_eval_cols || (n_coeffs && !coeffs)) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (ctx_sharded(ctx)) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "constraint evaluation on a sharded context");
+    if (n_trace_segs == 0 || n_trace_segs > 4) CTX_FAIL(ctx, AERO_ERR_INVALID, "1..4 trace segments");
+    if (n_div == 0 || n_div > 8) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of divisors must be 1..8, got %u", n_div);
+    if (prog->n_nodes == 0 || prog->n_nodes > 1024 || !prog->nodes) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "transition program must have 1..1024 nodes");
+    if (n_coeffs != 2 * (prog->n_transition + prog->n_boundary)) CTX_FAIL(ctx, AERO_ERR_INVALID, "expected a coefficient pair per constraint (%u), got %u elements", prog->n_transition + prog->n_boundary, n_coeffs);
+    if ((prog->n_transition && (!prog->transition_out || !prog->transition_adj)) ||
+        (prog->n_boundary && (!prog->boundary_col || !prog->boundary_value || !prog->boundary_adj || !prog->boundary_div)) ||
+        (prog->n_consts && !prog->consts))
+        CTX_FAIL(ctx, AERO_ERR_INVALID, "null program array");
+    AirSegs segs{};
+    segs.nseg = (int)n_trace_segs;
+    uint32_t width = 0;
+    const aero_segment *s0 = trace_segs[0];
+    for (uint32_t k = 0; k < n_trace_segs; k++) {
+        const aero_segment *sg = trace_segs[k];
+        if (!sg || !sg->lde) CTX_FAIL(ctx, AERO_ERR_STATE, "trace segment %u has not been committed", k);
+        if (sg->logn != s0->logn || sg->log_blowup != s0->log_blowup) CTX_FAIL(ctx, AERO_ERR_INVALID, "trace segments of different shape");
+        segs.lde[k] = sg->lde;
+        segs.stride[k] = sg->lde_stride();
+        segs.ncols[k] = sg->ncols;
+        width += (uint32_t)sg->ncols;
+    }
+    const int logn = s0->logn, log_blowup = s0->log_blowup;
+    if (!is_pow2(ce_blowup) || ce_blowup < 2 || ce_blowup > (1u << log_blowup)) CTX_FAIL(ctx, AERO_ERR_INVALID, "constraint evaluation blowup must be a power of two in 2..blowup");
+    const int log_ce = ilog2(ce_blowup);
+    const uint64_t CE = (uint64_t)ce_blowup << logn;
+    if (col_stride < CE) CTX_FAIL(ctx, AERO_ERR_INVALID, "column stride smaller than the constraint evaluation domain");
+    // validate the program: operands refer to earlier nodes, columns and constants exist
+    for (uint32_t k = 0; k < prog->n_nodes; k++) {
+        const aero_air_node &nd = prog->nodes[k];
+        bool ok;
+        switch (nd.op) {
+        case AERO_AIR_CUR: case AERO_AIR_NEXT: ok = nd.a < width; break;
+        case AERO_AIR_CONST: ok = nd.a < prog->n_consts; break;
+        case AERO_AIR_ADD: case AERO_AIR_SUB: case AERO_AIR_MUL: ok = nd.a < k && nd.b < k; break;
+        default: ok = false;
+        }
+        if (!ok) CTX_FAIL(ctx, AERO_ERR_INVALID, "transition program: bad node %u (op %u, operands %u, %u)", k, nd.op, nd.a, nd.b);
+    }
+    std::vector<uint64_t> adj;  // distinct degree adjustments
+    auto adj_index = [&](uint64_t a) {
+        for (size_t i = 0; i < adj.size(); i++)
+            if (adj[i] == a) return (uint32_t)i;
+        adj.push_back(a);
+        return (uint32_t)(adj.size() - 1);
+    };
+    // one upload: [u64 section: consts, b_val, coeffs, adj][u32 section: nodes, t_out, t_adj, b_col, b_adj, b_div]
+    const uint32_t nt = prog->n_transition, nb = prog->n_boundary;
+    std::vector<uint32_t> t_adj(nt), b_adj(nb);
+    for (uint32_t t = 0; t < nt; t++) {
+        if (prog->transition_out[t] >= prog->n_nodes) CTX_FAIL(ctx, AERO_ERR_INVALID, "transition constraint %u: no such node", t);
+        t_adj[t] = adj_index(prog->transition_adj[t]);
+    }
+    for (uint32_t j = 0; j < nb; j++) {
+        if (prog->boundary_col[j] >= width) CTX_FAIL(ctx, AERO_ERR_INVALID, "boundary constraint %u: no such column", j);
+        if (prog->boundary_div[j] == 0 || prog->boundary_div[j] >= n_div) CTX_FAIL(ctx, AERO_ERR_INVALID, "boundary constraint %u: divisor column out of range", j);
+        b_adj[j] = adj_index(prog->boundary_adj[j]);
+    }
+    if (adj.size() > 8) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "more than 8 distinct degree adjustments");
+    std::vector<uint64_t> w64;
+    const size_t o_consts = 0, o_bval = o_consts + prog->n_consts, o_coeffs = o_bval + nb, o_adj = o_coeffs + n_coeffs;
+    w64.resize(o_adj + adj.size());
+    for (uint32_t i = 0; i < prog->n_consts; i++) w64[o_consts + i] = to_canon(ctx, prog->consts[i]);
+    for (uint32_t j = 0; j < nb; j++) w64[o_bval + j] = to_canon(ctx, prog->boundary_value[j]);
+    for (uint32_t i = 0; i < n_coeffs; i++) w64[o_coeffs + i] = to_canon(ctx, coeffs[i]);
+    for (size_t i = 0; i < adj.size(); i++) w64[o_adj + i] = adj[i];
+    std::vector<uint32_t> w32;
+    const size_t o_nodes = 0, o_tout = o_nodes + 3 * (size_t)prog->n_nodes, o_tadj = o_tout + nt, o_bcol = o_tadj + nt,
+                 o_badj = o_bcol + nb, o_bdiv = o_badj + nb;
+    w32.resize(o_bdiv + nb);
+    for (uint32_t k = 0; k < prog->n_nodes; k++) {
+        w32[o_nodes + 3 * k] = prog->nodes[k].op;
+        w32[o_nodes + 3 * k + 1] = prog->nodes[k].a;
+        w32[o_nodes + 3 * k + 2] = prog->nodes[k].b;
+    }
+    for (uint32_t t = 0; t < nt; t++) {
+        w32[o_tout + t] = prog->transition_out[t];
+        w32[o_tadj + t] = t_adj[t];
+    }
+    for (uint32_t j = 0; j < nb; j++) {
+        w32[o_bcol + j] = prog->boundary_col[j];
+        w32[o_badj + j] = b_adj[j];
+        w32[o_bdiv + j] = prog->boundary_div[j];
+    }
+    DevBlocks blk(ctx);
+    uint64_t *d64 = nullptr;
+    uint32_t *d32 = nullptr;
+    TRY(blk.alloc((void **)&d64, std::max<size_t>(8, w64.size() * 8)));
+    TRY(blk.alloc((void **)&d32, w32.size() * 4));
+    if (!w64.empty()) TRY(upload_small(ctx, d64, w64.data(), w64.size() * 8));
+    TRY(upload_small(ctx, d32, w32.data(), w32.size() * 4));
+    AirProgramDev p{};
+    p.nodes = d32 + o_nodes;
+    p.t_out = d32 + o_tout;
+    p.t_adj = d32 + o_tadj;
+    p.b_col = d32 + o_bcol;
+    p.b_adj = d32 + o_badj;
+    p.b_div = d32 + o_bdiv;
+    p.consts = d64 + o_consts;
+    p.b_val = d64 + o_bval;
+    p.coeffs = d64 + o_coeffs;
+    p.adj = d64 + o_adj;
+    p.n_nodes = (int)prog->n_nodes;
+    p.nt = (int)nt;
+    p.nb = (int)nb;
+    p.n_adj = (int)adj.size();
+    p.n_div = (int)n_div;
+    PowTable x_ce;  // offset * g_ce^step (StarkDomain::get_ce_x_at, domain.rs:99-101)
+    {
+        char key[32];
+        snprintf(key, sizeof key, "xce/%d", logn + log_ce);
+        TRY(get_pow_table(ctx, key, gl::root_of_unity(logn + log_ce), logn + log_ce, gl::GENERATOR, &x_ce));
+    }
+    {
+        PhaseTimer t(ctx, "constraint_evaluate");
+        air_evaluate(segs, p, logn, log_blowup, log_ce, x_ce, ctx->form == AERO_FORM_MONTGOMERY, d_eval_cols, col_stride, ctx->stream);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    return AERO_OK;
+}
+
 aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_eval_cols, size_t col_stride,
                                               const aero_divisor *divs, uint32_t n_div, uint64_t ce_domain_size,
                                               uint64_t trace_len, aero_segment **out) {
@@ -2322,6 +2450,21 @@ aero_status aero_constraints_into_poly(aero_ctx *ctx, const uint64_t *const *eva
         }
     }
     return aero_constraints_into_poly_device(ctx, cols, N, divs, n_div, ce_domain_size, trace_len, out);
+}
+
+aero_status aero_constraints_evaluate_into_poly(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs,
+                                                const aero_air_program *prog, const uint64_t *coeffs, uint32_t n_coeffs,
+                                                uint32_t ce_blowup, const aero_divisor *divs, uint32_t n_div, aero_segment **out) {
+    if (!ctx) return AERO_ERR_INVALID;
+    enter(ctx);
+    if (!trace_segs || !n_trace_segs || !trace_segs[0] || !out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    if (n_div == 0 || n_div > 8 || ce_blowup < 2 || ce_blowup > 128) CTX_FAIL(ctx, AERO_ERR_INVALID, "bad divisor count or constraint evaluation blowup");
+    const uint64_t n = trace_segs[0]->n(), CE = n * ce_blowup;
+    DevBlocks blk(ctx);
+    uint64_t *d_ce = nullptr;
+    TRY(blk.alloc((void **)&d_ce, (size_t)n_div * CE * 8));
+    TRY(aero_constraints_evaluate_device(ctx, trace_segs, n_trace_segs, prog, coeffs, n_coeffs, ce_blowup, n_div, d_ce, CE));
+    return aero_constraints_into_poly_device(ctx, d_ce, CE, divs, n_div, CE, n, out);
 }
 
 // ---- OOD + DEEP -----------------------------------------------------------------------------

@@ -186,6 +186,26 @@ void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDe
                         uint64_t offset, PowTable gN, uint32_t i_begin, uint32_t i_count, uint64_t *combined,
                         cudaStream_t s);
 
+// AIR constraint evaluation over the constraint evaluation domain (include/aero_b200.h, aero_air_program)
+struct AirSegs {  // trace segments in order: column c of segment s at lde[s] + c*stride[s], coset-major
+    const uint64_t *lde[4];
+    size_t stride[4];
+    int ncols[4];
+    int nseg;
+};
+struct AirProgramDev {       // device copies; field elements canonical
+    const uint32_t *nodes;   // 3 words per node: op, a, b
+    const uint64_t *consts;
+    const uint32_t *t_out, *t_adj;           // per transition constraint: node, index into adj
+    const uint32_t *b_col, *b_adj, *b_div;   // per boundary constraint
+    const uint64_t *b_val;
+    const uint64_t *coeffs;  // pairs: transition constraints, then boundary constraints
+    const uint64_t *adj;     // distinct degree adjustments
+    int n_nodes, nt, nb, n_adj, n_div;
+};
+void air_evaluate(const AirSegs &segs, const AirProgramDev &p, int logn, int log_blowup, int log_ce, PowTable x_ce /* 7 g_ce^s */,
+                  int to_montgomery, uint64_t *out, size_t out_stride, cudaStream_t s);
+
 // peak.cu
 double measure_alu_peak(int num_sms, uint32_t *scratch, cudaStream_t s);
 

@@ -737,4 +737,71 @@ void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDe
     constraint_combine_kernel<<<(i_count + 255) / 256, 256, 0, s>>>(cols, col_stride, ds, i_begin, i_count, offset, gN, combined);
 }
 
+// ---- AIR constraint evaluation -----------------------------------------------------
+// ConstraintEvaluator::evaluate (prover/src/constraints/evaluator.rs:121-230) for a transition program:
+// one thread per step of the constraint evaluation domain.  Threads are numbered coset-major like the LDE
+// (thread = rc * n + i for step s = i * ce_blowup + rc), so frame loads are coalesced; the next row of the
+// frame is the same LDE coset one position on (trace_lde.rs: + blowup, wrapping).  Node values live in a
+// per-thread array (local memory: coalesced across the warp for equal node indices).
+template <int MAXN>
+__global__ void __launch_bounds__(128) air_evaluate_kernel(AirSegs segs, AirProgramDev p, int logn, int log_blowup, int log_ce,
+                                                          PowTable x_ce, int to_montgomery, uint64_t *__restrict__ out,
+                                                          size_t out_stride) {
+    const uint32_t tau = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = 1u << logn;
+    if (tau >= (n << log_ce)) return;
+    const uint32_t i = tau & (n - 1), rc = tau >> logn;
+    const uint32_t step = (i << log_ce) | rc;                     // natural index in the evaluation domain
+    const size_t cur = ((size_t)(rc << (log_blowup - log_ce)) << logn) + i;   // (LDE coset, i)
+    const size_t nxt = cur - i + ((i + 1) & (n - 1));
+    auto load = [&](uint32_t col, size_t pos) -> uint64_t {
+        for (int sg = 0; sg < segs.nseg; sg++) {
+            if (col < (uint32_t)segs.ncols[sg]) return segs.lde[sg][(size_t)col * segs.stride[sg] + pos];
+            col -= segs.ncols[sg];
+        }
+        return 0;
+    };
+    const uint64_t x = pow_lookup(x_ce, step);                   // domain.rs:99-101: offset * g_ce^step
+    uint64_t xp[8];
+    for (int a = 0; a < p.n_adj; a++) xp[a] = gl::pow(x, p.adj[a]);   // domain.rs:109-117: x^adjustment
+    uint64_t val[MAXN];
+    for (int k = 0; k < p.n_nodes; k++) {
+        const uint32_t op = __ldg(p.nodes + 3 * k), a = __ldg(p.nodes + 3 * k + 1), b = __ldg(p.nodes + 3 * k + 2);
+        uint64_t v;
+        switch (op) {
+        case 0: v = load(a, cur); break;
+        case 1: v = load(a, nxt); break;
+        case 2: v = __ldg(p.consts + a); break;
+        case 3: v = gl::add(val[a], val[b]); break;
+        case 4: v = gl::sub(val[a], val[b]); break;
+        default: v = gl::mul(val[a], val[b]); break;
+        }
+        val[k] = v;
+    }
+    uint64_t acc[8];
+    for (int d = 0; d < 8; d++) acc[d] = 0;
+    // transition/mod.rs:272-283: sum (c0 + c1 * x^adj) * evaluation over the constraints of each group
+    for (int t = 0; t < p.nt; t++) {
+        const uint64_t w = gl::add(__ldg(p.coeffs + 2 * t), gl::mul(__ldg(p.coeffs + 2 * t + 1), xp[__ldg(p.t_adj + t)]));
+        acc[0] = gl::add(acc[0], gl::mul(w, val[__ldg(p.t_out + t)]));
+    }
+    // boundary.rs:255-275: (trace value - asserted value) * (c0 + c1 * x^adj), one column per divisor
+    for (int j = 0; j < p.nb; j++) {
+        const uint64_t *cc = p.coeffs + 2 * (p.nt + j);
+        const uint64_t w = gl::add(__ldg(cc), gl::mul(__ldg(cc + 1), xp[__ldg(p.b_adj + j)]));
+        const uint64_t v = gl::sub(load(__ldg(p.b_col + j), cur), __ldg(p.b_val + j));
+        const uint32_t d = __ldg(p.b_div + j);
+        acc[d] = gl::add(acc[d], gl::mul(w, v));
+    }
+    for (int d = 0; d < p.n_div; d++) out[(size_t)d * out_stride + step] = to_montgomery ? gl::canon_to_mont(acc[d]) : acc[d];
+}
+void air_evaluate(const AirSegs &segs, const AirProgramDev &p, int logn, int log_blowup, int log_ce, PowTable x_ce,
+                  int to_montgomery, uint64_t *out, size_t out_stride, cudaStream_t s) {
+    const uint64_t threads = (uint64_t)1 << (logn + log_ce);
+    const unsigned grid = (unsigned)((threads + 127) / 128);
+    AERO_COUNT_LAUNCH(1);
+    if (p.n_nodes <= 64) air_evaluate_kernel<64><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride);
+    else air_evaluate_kernel<1024><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride);
+}
+
 }  // namespace aero

@@ -312,10 +312,11 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
     if (o.fri_folding_factor != 8) P_FAIL(AERO_ERR_UNSUPPORTED, "only FRI folding factor 8 is supported");
     if (!in.main_cols || in.main_width == 0) P_FAIL(AERO_ERR_INVALID, "main trace segment is required");
     if (in.aux_width && !in.aux_builder && !in.aux_cols) P_FAIL(AERO_ERR_INVALID, "auxiliary segment columns are required");
-    if (!in.constraint_evaluator && !in.ce_cols) P_FAIL(AERO_ERR_INVALID, "constraint evaluations are required");
+    if (!in.constraint_evaluator && !in.ce_cols && !in.air_program) P_FAIL(AERO_ERR_INVALID, "constraint evaluations are required");
+    const bool device_air = in.air_program && !in.constraint_evaluator && !in.ce_cols;
     if (in.inputs_on_device && (in.aux_builder || in.constraint_evaluator)) P_FAIL(AERO_ERR_INVALID, "callbacks need host inputs");
     const bool sharded = aero_ctx_window_ranks(ctx) > 1;
-    if (sharded && (in.constraint_evaluator || in.aux_builder)) P_FAIL(AERO_ERR_UNSUPPORTED, "sharded proofs take precomputed auxiliary columns and constraint evaluations");
+    if (sharded && (in.constraint_evaluator || in.aux_builder || device_air)) P_FAIL(AERO_ERR_UNSUPPORTED, "sharded proofs take precomputed auxiliary columns and constraint evaluations");
     if (in.trace_len < 2 || (in.trace_len & (in.trace_len - 1))) P_FAIL(AERO_ERR_INVALID, "trace length must be a power of two >= 2");
     const bool mont = aero_ctx_get_form(ctx) == AERO_FORM_MONTGOMERY;
     auto to_abi = [&](uint64_t x) { return mont ? gl::canon_to_mont(x) : x; };
@@ -333,7 +334,7 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
     // Nothing on the device depends on a trace root before the OOD point is drawn unless a callback has to
     // see the randomness in between: then the three commitments are queued back to back and their roots
     // collected in ONE host round trip (aero_segments_roots), with the transcript replayed in order.
-    const bool defer_roots = !in.aux_builder && !in.constraint_evaluator;
+    const bool defer_roots = !in.aux_builder && !in.constraint_evaluator && !device_air;
     uint8_t *root_now = defer_roots ? nullptr : root;
 
     // Host inputs that are already known (no callback produces them) start travelling now: their copies
@@ -341,7 +342,7 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
     if (!in.inputs_on_device) {
         // (a sharded proof uploads only what this rank reads: its trace columns, its rows of the constraint evaluations)
         if (in.aux_width && !in.aux_builder) P_TRY(aero_upload_start(ctx, in.aux_cols, in.aux_width, n, 1, AERO_UPLOAD_OWN_COLUMNS, &H.up_aux));
-        if (!in.constraint_evaluator) P_TRY(aero_upload_start(ctx, in.ce_cols, in.n_div, CE, 1, AERO_UPLOAD_OWN_ROWS, &H.up_ce));
+        if (!in.constraint_evaluator && !device_air) P_TRY(aero_upload_start(ctx, in.ce_cols, in.n_div, CE, 1, AERO_UPLOAD_OWN_ROWS, &H.up_ce));
     }
 
     // 1 ----- commit to the execution trace (lib.rs:239-248, 269-348)
@@ -404,7 +405,15 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
 
     // 3 ----- commit to constraint evaluations (lib.rs:396-419)
     aero_segment *comp_seg = nullptr;
-    if (H.up_ce) {
+    if (device_air) {
+        // ConstraintEvaluator::evaluate on the device: the frame is read from the resident LDE
+        std::vector<uint64_t> abi(coeffs.size());
+        for (size_t i = 0; i < abi.size(); i++) abi[i] = to_abi(coeffs[i]);
+        std::vector<aero_segment *> tsegs = {main_seg};
+        if (aux_seg) tsegs.push_back(aux_seg);
+        P_TRY(aero_constraints_evaluate_into_poly(ctx, tsegs.data(), (uint32_t)tsegs.size(), in.air_program, abi.data(),
+                                                  (uint32_t)abi.size(), ce_blowup, in.divisors, in.n_div, &comp_seg));
+    } else if (H.up_ce) {
         const uint64_t *d_ce = nullptr;
         P_TRY(aero_upload_wait(H.up_ce, &d_ce));
         P_TRY(aero_constraints_into_poly_device(ctx, d_ce, CE, in.divisors, in.n_div, CE, n, &comp_seg));

@@ -47,6 +47,70 @@ def make_divisor(a: int, b: int, exemptions: Sequence[int] = ()) -> Divisor:
     return d
 
 
+class AirProgramBuilder:
+    """Records an AIR's transition constraints as an aero_air_program (include/aero_b200.h): build the
+    expression DAG with cur()/next()/const()/add()/sub()/mul(), declare each constraint's output node with
+    its group's degree adjustment, add the single-value assertions, then ``finish()``.  All field values in
+    ABI form (the context's form).  This is what a Rust caller does once per AIR by running
+    Air::evaluate_transition over a symbolic element type."""
+
+    def __init__(self):
+        self.nodes: List[Tuple[int, int, int]] = []
+        self.consts: List[int] = []
+        self.t_out: List[int] = []
+        self.t_adj: List[int] = []
+        self.boundary: List[Tuple[int, int, int, int]] = []  # column, value, degree adjustment, divisor column
+
+    def _node(self, op: int, a: int, b: int = 0) -> int:
+        self.nodes.append((op, a, b))
+        return len(self.nodes) - 1
+
+    def cur(self, col: int) -> int:
+        return self._node(_lib.AERO_AIR_CUR, col)
+
+    def next(self, col: int) -> int:
+        return self._node(_lib.AERO_AIR_NEXT, col)
+
+    def const(self, value: int) -> int:
+        self.consts.append(int(value))
+        return self._node(_lib.AERO_AIR_CONST, len(self.consts) - 1)
+
+    def add(self, a: int, b: int) -> int:
+        return self._node(_lib.AERO_AIR_ADD, a, b)
+
+    def sub(self, a: int, b: int) -> int:
+        return self._node(_lib.AERO_AIR_SUB, a, b)
+
+    def mul(self, a: int, b: int) -> int:
+        return self._node(_lib.AERO_AIR_MUL, a, b)
+
+    def transition(self, node: int, degree_adjustment: int) -> None:
+        self.t_out.append(node)
+        self.t_adj.append(int(degree_adjustment))
+
+    def assertion(self, column: int, value: int, degree_adjustment: int, divisor_column: int) -> None:
+        self.boundary.append((column, int(value), int(degree_adjustment), divisor_column))
+
+    def finish(self):
+        """-> (AirProgram struct, objects that must stay alive as long as it is used)."""
+        from ctypes import c_uint32 as u32, c_uint64 as u64
+        nodes = (_lib.AirNode * max(1, len(self.nodes)))(*[_lib.AirNode(*nd) for nd in self.nodes])
+        consts = (u64 * max(1, len(self.consts)))(*self.consts)
+        t_out = (u32 * max(1, len(self.t_out)))(*self.t_out)
+        t_adj = (u64 * max(1, len(self.t_adj)))(*self.t_adj)
+        nb = len(self.boundary)
+        b_col = (u32 * max(1, nb))(*[b[0] for b in self.boundary])
+        b_val = (u64 * max(1, nb))(*[b[1] for b in self.boundary])
+        b_adj = (u64 * max(1, nb))(*[b[2] for b in self.boundary])
+        b_div = (u32 * max(1, nb))(*[b[3] for b in self.boundary])
+        p = _lib.AirProgram()
+        p.nodes, p.n_nodes = nodes, len(self.nodes)
+        p.consts, p.n_consts = consts, len(self.consts)
+        p.n_transition, p.transition_out, p.transition_adj = len(self.t_out), t_out, t_adj
+        p.n_boundary, p.boundary_col, p.boundary_value, p.boundary_adj, p.boundary_div = nb, b_col, b_val, b_adj, b_div
+        return p, [nodes, consts, t_out, t_adj, b_col, b_val, b_adj, b_div]
+
+
 def _cols(m: np.ndarray):
     """(w, n) uint64 C-contiguous -> array of column pointers (keeps a reference to m)."""
     assert m.dtype == np.uint64 and m.ndim == 2 and m.flags["C_CONTIGUOUS"], "expected (cols, rows) uint64 C array"
@@ -159,6 +223,25 @@ class Context:
                                                         eval_cols.shape[1], trace_len, ctypes.byref(seg)))
         return Segment(self, seg, None)
 
+    def evaluate_constraints(self, trace_segs: Sequence["Segment"], program, coeffs: Sequence[int], ce_blowup: int,
+                             n_div: int) -> np.ndarray:
+        """ConstraintEvaluator::evaluate on the device (aero_constraints_evaluate_device): (n_div, n * ce_blowup)
+        merged evaluations read back for inspection.  ``program``: AirProgramBuilder.finish()[0]."""
+        n = trace_segs[0].n_rows
+        ce = n * ce_blowup
+        d = c_void_p()
+        self._check(self.lib.aero_device_alloc(self.h, n_div * ce * 8, ctypes.byref(d)))
+        try:
+            hs = (c_void_p * len(trace_segs))(*[s.h for s in trace_segs])
+            cf = np.ascontiguousarray(np.array([int(c) for c in coeffs], np.uint64))
+            self._check(self.lib.aero_constraints_evaluate_device(self.h, hs, len(trace_segs), ctypes.byref(program),
+                                                                  cf.ctypes.data_as(p_u64), len(cf), ce_blowup, n_div, d, ce))
+            out = np.empty((n_div, ce), np.uint64)
+            self._check(self.lib.aero_device_download(self.h, out.ctypes.data_as(c_void_p), d, out.nbytes))
+            return out
+        finally:
+            self.lib.aero_device_free(self.h, d)
+
     # ---- OOD / DEEP ----------------------------------------------------------------------------
     def ood_eval(self, trace_segs: Sequence["Segment"], comp: Optional["Segment"], z: int):
         W = sum(s.n_cols for s in trace_segs)
@@ -248,7 +331,7 @@ class Context:
     def prove(self, main_trace, aux_trace, ce_cols, divisors: Sequence[Divisor], pub_inputs_bytes: bytes,
               options: Optional[ProofOptions] = None, aux_rands: int = 16, n_constraint_coeffs: int = 0,
               on_device: Optional[dict] = None, shard=None, aux_builder=None, aux_width: int = 0,
-              constraint_evaluator=None, ce_blowup: int = 0) -> bytes:
+              constraint_evaluator=None, ce_blowup: int = 0, air_program=None) -> bytes:
         """Prover::prove.  Host mode: numpy matrices.  Device mode (``on_device`` = dict with
         main/aux/ce device pointers and shapes): inputs already resident in HBM.
 
@@ -257,11 +340,16 @@ class Context:
         matrix`` are the two callbacks of include/aero_prover.h (the steps the north star keeps on the
         reference's Rust path); with them ``aux_trace`` / ``ce_cols`` may be None.
 
+        ``air_program`` (AirProgramBuilder.finish()[0]): the third source of the constraint evaluations -- the
+        transition constraints as a program, evaluated on the device from the resident LDE (``ce_cols`` None).
+
         ``shard`` (aero_b200.sharded.ShardExchange): this process is one rank of a proof spread over
         several GPUs; every rank calls prove with the same inputs and gets the same bytes."""
         inp, keep, cb_err = build_prove_inputs(main_trace, aux_trace, ce_cols, divisors, pub_inputs_bytes, options,
                                                aux_rands, n_constraint_coeffs, on_device, aux_builder, aux_width,
                                                constraint_evaluator, ce_blowup)
+        if air_program is not None:
+            inp.air_program = ctypes.pointer(air_program)
         if shard is not None:
             shard.attach(self)  # set_shard + exchange window + host rendezvous, once per context
         else:

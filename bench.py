@@ -312,8 +312,10 @@ def run_aero(args) -> None:
     if args.trace:  # profiling aid: CUPTI timeline (kernels, copies, runtime calls) of one step
         from torch.profiler import ProfilerActivity, profile
         torch.cuda.synchronize()
+        if args.trace_host:
+            step_host()
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as tp:
-            step_device()
+            (step_host if args.trace_host else step_device)()
             torch.cuda.synchronize()
         tp.export_chrome_trace(args.trace)
         return
@@ -512,6 +514,7 @@ def main() -> None:
     ap.add_argument("--ntt-table-mb", type=int, default=-1,
                     help="largest full inter-pass NTT twiddle table per plan (MiB); 0 = running products; -1 = default")
     ap.add_argument("--trace", default="", help="profiling aid: write a chrome trace of one device-input step and exit")
+    ap.add_argument("--trace-host", action="store_true", help="with --trace: trace the host-buffer (e2e) step instead")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu): 1 warm-up, no e2e / cpu legs; numbers printed are NOT bench values")
     args = ap.parse_args()

@@ -186,6 +186,57 @@ aero_status aero_constraints_into_poly(aero_ctx *ctx, const uint64_t *const *eva
 aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_eval_cols, size_t col_stride,
                                               const aero_divisor *divs, uint32_t n_div, uint64_t ce_domain_size,
                                               uint64_t trace_len, aero_segment **composition_polys);
+/* ---- AIR constraint evaluation on the device ------------------------------------- */
+/* Replaces ConstraintEvaluator::evaluate (prover/src/constraints/evaluator.rs:74-230; boundary.rs:59-100,
+ * 255-275; air/src/air/transition/mod.rs:224-283 merge_evaluations; domain.rs:99-117) for an AIR whose
+ * transition constraints are handed over as an arithmetic program over the evaluation frame, so that the
+ * trace LDE never leaves the device (the callback route downloads all of it: 5.4 GB at 2^20 rows).
+ *
+ * The program is a list of nodes in evaluation order; node k may refer to nodes < k:
+ *   AERO_AIR_CUR / AERO_AIR_NEXT  a = trace column (segments concatenated: main, then auxiliary) of the
+ *                                  current / next row of the frame (EvaluationFrame, air/src/air/mod.rs)
+ *   AERO_AIR_CONST                a = index into consts (ABI form: public inputs, periodic-free constants,
+ *                                  the auxiliary segment's random elements)
+ *   AERO_AIR_ADD / SUB / MUL      a, b = operand nodes
+ * A Rust caller records it once per AIR by running Air::evaluate_transition over a symbolic element type.
+ * transition_out[i] = node holding constraint i, transition_adj[i] = its group's degree adjustment
+ * (TransitionConstraintGroup::degree_adjustment); boundary constraint j is the single-value assertion
+ * column boundary_col[j] == boundary_value[j] (ABI form) with degree adjustment boundary_adj[j], merged
+ * into evaluation column boundary_div[j] >= 1 (column 0 is the transition divisor's, evaluator.rs:66-67).
+ * coeffs: the drawn composition coefficients in ABI form, a pair per transition constraint, then a pair
+ * per boundary constraint in the order given (Air::get_constraint_composition_coefficients,
+ * air/src/air/mod.rs:511-533).  Periodic columns and sequence assertions are not covered.
+ * Output: n_div columns of trace_len * ce_blowup merged evaluations in natural order of the constraint
+ * evaluation domain (ABI form, column d at d_eval_cols + d * col_stride): the input of
+ * aero_constraints_into_poly_device.  At most 1024 nodes, 8 distinct degree adjustments. */
+enum { AERO_AIR_CUR = 0, AERO_AIR_NEXT = 1, AERO_AIR_CONST = 2, AERO_AIR_ADD = 3, AERO_AIR_SUB = 4, AERO_AIR_MUL = 5 };
+typedef struct aero_air_node {
+    uint32_t op, a, b;
+} aero_air_node;
+typedef struct aero_air_program {
+    const aero_air_node *nodes;
+    uint32_t n_nodes;
+    const uint64_t *consts;
+    uint32_t n_consts;
+    uint32_t n_transition;
+    const uint32_t *transition_out;
+    const uint64_t *transition_adj;
+    uint32_t n_boundary;
+    const uint32_t *boundary_col;
+    const uint64_t *boundary_value;
+    const uint64_t *boundary_adj;
+    const uint32_t *boundary_div;
+} aero_air_program;
+aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs,
+                                             const aero_air_program *program, const uint64_t *coeffs, uint32_t n_coeffs,
+                                             uint32_t ce_blowup, uint32_t n_div, uint64_t *d_eval_cols, size_t col_stride);
+/* ConstraintEvaluator::evaluate followed by ConstraintEvaluationTable::into_poly, the evaluation table kept in
+ * device scratch: the route aero_prove takes for aero_prove_inputs.air_program. */
+aero_status aero_constraints_evaluate_into_poly(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs,
+                                                const aero_air_program *program, const uint64_t *coeffs, uint32_t n_coeffs,
+                                                uint32_t ce_blowup, const aero_divisor *divs, uint32_t n_div,
+                                                aero_segment **composition_polys);
+
 /* Extends + commits a coefficient-only segment: CompositionPoly::evaluate + commit_to_rows
  * (prover/src/lib.rs:599-632). */
 aero_status aero_segment_commit_polys(aero_segment *seg, uint32_t blowup, uint8_t root[32]);

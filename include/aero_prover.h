@@ -68,6 +68,11 @@ typedef struct aero_prove_inputs {
     size_t pub_inputs_len;
     const uint8_t *trace_meta;         /* TraceInfo meta bytes for the proof context (may be NULL) */
     uint16_t trace_meta_len;
+    /* Third source of the constraint evaluations (used when constraint_evaluator == NULL and ce_cols == NULL):
+     * the AIR's transition constraints as a program, evaluated on the device from the resident trace LDE
+     * (aero_constraints_evaluate_device, include/aero_b200.h) -- nothing is downloaded.  Works with host and
+     * with device inputs; not on a sharded context. */
+    const aero_air_program *air_program;
 } aero_prove_inputs;
 
 /* Prover::prove: writes StarkProof::to_bytes (air/src/proof/mod.rs:122-132) into proof_out.

@@ -104,3 +104,89 @@ def test_fib2_gpu_proof_is_byte_identical_and_verifies(ctx, ctx_mont, logn, form
                   constraint_evaluator=evaluator, ce_blowup=air.ce_blowup)
     assert got == ref.proof_bytes
     so.verify(got, pub, air.ce_blowup, air=air)
+
+
+def _fib2_program(air, to_abi_int):
+    """The fib2 AIR as an aero_air_program: evaluate_transition (air.rs:41-58) recorded node by node, the
+    transition group's degree adjustment, and the assertions in the reference's coefficient order with
+    their divisor columns (oracle/air.py boundary_groups restates the grouping)."""
+    from aero_b200 import AirProgramBuilder
+
+    b = AirProgramBuilder()
+    c0, c1, n0, n1 = b.cur(0), b.cur(1), b.next(0), b.next(1)
+    t0 = b.sub(n0, b.add(c0, c1))   # next[0] - (cur[0] + cur[1])
+    t1 = b.sub(n1, b.add(c1, n0))   # next[1] - (cur[1] + next[0])
+    pairs = [(0, 0)] * (air.num_constraint_coefficients() // 2)
+    (adj_t, members), = air.transition_groups(pairs[:2])
+    assert [m[0] for m in members] == [0, 1]
+    b.transition(t0, adj_t)
+    b.transition(t1, adj_t)
+    # coefficient pairs follow the sorted assertions; each lands in its group's divisor column
+    assertions = sorted(air.get_assertions(), key=lambda a: (0, a.step, a.column))
+    groups = air.boundary_groups(pairs[2:])
+    for a in assertions:
+        for j, (div, adj, mem) in enumerate(groups):
+            if any(col == a.column and val == a.value for col, val, _ in mem) and div.b == (pow(air.g, a.step, P) if a.step else 1):
+                b.assertion(a.column, to_abi_int(a.value), adj, 1 + j)
+                break
+        else:
+            raise AssertionError("assertion without a group")
+    return b.finish()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("form", ["canonical", "montgomery"])
+@pytest.mark.parametrize("logn", [3, 6, 10, 13])
+def test_fib2_constraints_evaluated_on_the_gpu(ctx, ctx_mont, logn, form):
+    """SURVEY 8(f)3: ConstraintEvaluator::evaluate on the device (aero_constraints_evaluate_device) from the
+    resident trace LDE equals the restated evaluator column for column, and aero_prove with the program
+    (no callback, no LDE download) gives the same bytes as the oracle prover, OOD consistency check included."""
+    from aero_b200 import make_divisor
+
+    n, trace, air, divs, pub = _setup(logn)
+    mont = form == "montgomery"
+    c = ctx_mont if mont else ctx
+    to_abi = so.canon_to_mont if mont else (lambda a: a)
+    from_abi = so.mont_to_canon if mont else (lambda a: a)
+    to_abi_int = lambda v: int(to_abi(np.array([v], np.uint64))[0])
+    prog, keep = _fib2_program(air, to_abi_int)
+    # (1) the evaluation table itself, with fixed pseudo-random coefficients
+    rng = np.random.default_rng(logn)
+    coeffs = [int(v) % P for v in rng.integers(0, 2**63, air.num_constraint_coefficients(), dtype=np.uint64)]
+    seg = c.build_trace_commitment(to_abi(trace), 8)
+    lde = from_abi(seg.download_lde())
+    want = air.evaluate_constraints_over_ce_domain(lde, coeffs) if logn <= 10 else None
+    got = from_abi(c.evaluate_constraints([seg], prog, [to_abi_int(v) for v in coeffs], air.ce_blowup, len(divs)))
+    if want is not None:
+        assert np.array_equal(got, want)
+    # 2^13 rows: the pure-Python evaluator is slow; any wrong evaluation breaks the OOD consistency check below
+    seg.destroy()
+    # (2) the whole proof
+    gdivs = [make_divisor(d.a, to_abi_int(d.b), [to_abi_int(v) for v in d.exemptions]) for d in divs]
+    got_proof = c.prove(to_abi(trace), None, None, gdivs, pub, n_constraint_coeffs=air.num_constraint_coefficients(),
+                        ce_blowup=air.ce_blowup, air_program=prog)
+    if logn <= 10:
+        assert got_proof == _oracle_prove(trace, air, divs, pub).proof_bytes
+    so.verify(got_proof, pub, air.ce_blowup, air=air)
+
+
+@pytest.mark.gpu
+def test_air_program_is_validated(ctx):
+    """Malformed programs are rejected with AERO_ERR_INVALID instead of reading out of bounds."""
+    from aero_b200 import AeroError, AirProgramBuilder
+
+    n, trace, air, divs, pub = _setup(4)
+    seg = ctx.build_trace_commitment(trace, 8)
+    b = AirProgramBuilder()
+    b.transition(b.add(b.cur(0), b.cur(7)), 1)   # column 7 does not exist
+    prog, keep = b.finish()
+    with pytest.raises(AeroError):
+        ctx.evaluate_constraints([seg], prog, [1, 2], 2, 1)
+    b = AirProgramBuilder()
+    x = b.cur(0)
+    b.nodes.append((3, x, 5))                      # operand refers to a later node
+    b.transition(1, 1)
+    prog, keep = b.finish()
+    with pytest.raises(AeroError):
+        ctx.evaluate_constraints([seg], prog, [1, 2], 2, 1)
+    seg.destroy()

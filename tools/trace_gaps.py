@@ -1,11 +1,13 @@
 """Summarises a chrome trace written by `bench.py --trace`: GPU busy time, idle gaps between
-consecutive GPU activities and the runtime call the host was in while the GPU idled."""
+consecutive GPU activities and the runtime call the host was in while the GPU idled.
+usage: trace_gaps.py trace.json [top-N] [kernels]   -- `kernels`: ignore copies (idle time of the SMs while a
+host->device copy is in flight counts as a gap)."""
 import json
 import sys
 
 ev = json.load(open(sys.argv[1]))["traceEvents"]
-gpu = sorted((e for e in ev if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")),
-             key=lambda e: e["ts"])
+cats = ("kernel",) if len(sys.argv) > 3 and sys.argv[3] == "kernels" else ("kernel", "gpu_memcpy", "gpu_memset")
+gpu = sorted((e for e in ev if e.get("ph") == "X" and e.get("cat") in cats), key=lambda e: e["ts"])
 cpu = sorted((e for e in ev if e.get("ph") == "X" and e.get("cat") in ("cuda_runtime", "cuda_driver")),
              key=lambda e: e["ts"])
 t0, t1 = gpu[0]["ts"], max(e["ts"] + e["dur"] for e in gpu)
