@@ -105,6 +105,8 @@ struct aero_ctx {
     int upload_batch_cols = 8;                 // columns per host->device copy batch of aero_segment_commit
     int upload_edge_cols = -1;                 // size of its first / last batch (-1: half a batch, 0: uniform batches)
     size_t ntt_table_max_bytes = (size_t)1 << 30;  // largest full inter-pass twiddle table a plan may hold
+    int hash_early_batches = 2;  // host-buffer commits: column batches hashed right after their extension ("hash_early_batches")
+    int fri_fused = 1;       // fold a FRI layer and hash the next layer's leaves in one kernel: 0 never, 1 small layers, 2 all ("fri_fused")
     int ntt_outer_log = -1;  // third factor of two-pass transforms: -1 = 2^(logn-20) above 2^20 points, 0 = never, k = force 2^k (tests)
     int shard_rank = 0, shard_world = 1;       // LDE coset shard of this context (multi-GPU)
     std::multimap<size_t, void *> free_blocks;  // exact-size cache of released device blocks
@@ -1000,6 +1002,12 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
     if (iplan && iplan->log1 != 0) TRY(tmp.alloc((void **)&tmp_i, (size_t)ibatch * n_rows * 8));
     if (lplan && lplan->log1 != 0) TRY(tmp.alloc((void **)&tmp_l, (size_t)std::max(batch, lde_batch) * seg->lde_stride() * 8));
     const bool per_batch_hash = !(batch & 1) && segment_hash_overlapped(seg.get());
+    // Uploads in flight deliver a column batch slightly slower than it is extended, so the stream would wait
+    // a little before every batch (profiles/r02_trace_gaps_host_kernels.txt: 1.2 ms per 72-column segment).
+    // Hashing the first batches' columns early (chained row hash, same stream) builds a backlog of arrived
+    // batches instead; the rest of the columns are hashed once at the end as before.
+    const int early_batches = (ready && !per_batch_hash && !sharded && n_cols >= 32) ? ctx->hash_early_batches : 0;
+    int hashed_cols = 0;
     char nm[32];
     snprintf(nm, sizeof nm, "interpolate_w%d", (int)n_cols);
     const RankPtrs polys_all = rank_ptrs(ctx, seg->polys);
@@ -1042,6 +1050,10 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
         if (sharded && !ctx->win_host_sync && c0 + nc == ce) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_push, ctx->stream));  // all own coefficients exist
         segment_lde_batch(seg.get(), lplan, c0, nc, tmp_l);
         if (per_batch_hash) TRY(segment_hash_batch(seg.get(), c0, nc));
+        else if (b < early_batches && c0 == hashed_cols && !((c0 + nc) & 1) && c0 + nc < ce) {
+            TRY(segment_hash_batch(seg.get(), hashed_cols, c0 + nc - hashed_cols));
+            hashed_cols = c0 + nc;
+        }
     }
     if (sharded && ctx->win_host_sync) {  // the other ranks' coefficients have arrived: extend those columns too
         TRY(window_barrier(ctx));
@@ -1080,7 +1092,7 @@ static aero_status segment_from_device(aero_ctx *ctx, const uint64_t *d_src, siz
         CUDA_TRY(ctx, cudaGetLastError());
     }
     if (seg->failed) return AERO_ERR_UNSUPPORTED;
-    if (!per_batch_hash) TRY(segment_hash_batch(seg.get(), 0, (int)n_cols));
+    if (!per_batch_hash) TRY(segment_hash_batch(seg.get(), hashed_cols, (int)n_cols - hashed_cols));
     TRY(segment_tree_after_hash(seg.get(), root));
     *out = seg.release();
     return AERO_OK;
@@ -1417,6 +1429,8 @@ aero_status aero_ctx_create(const int *device_ids, int n_devices, aero_ctx **out
     if (prop.major < 10) return AERO_ERR_UNSUPPORTED;  // kernels are built for sm_100a only
     aero_ctx *ctx = new aero_ctx();
     ctx->device = dev;
+    if (const char *e = getenv("AERO_FRI_FUSED")) ctx->fri_fused = std::max(0, std::min(2, atoi(e)));  // experiment hooks
+    if (const char *e = getenv("AERO_HASH_EARLY")) ctx->hash_early_batches = std::max(0, std::min(16, atoi(e)));
     if (const char *e = getenv("AERO_NTT_OUTER")) {  // experiment hook: default of the "ntt_outer_log" option
         const int v = atoi(e);
         if (v >= -1 && v <= NTT_OUTER_MAX_LOG) ctx->ntt_outer_log = v;
@@ -1507,6 +1521,8 @@ aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value)
     else if (k == "hash_blocks_per_sm" && value > 0) ctx->hash_blocks_per_sm = (int)value;
     else if (k == "lde_batch_bytes" && value > 0) ctx->lde_batch_bytes = (size_t)value;
     else if (k == "ntt_table_max_bytes" && value >= 0) ctx->ntt_table_max_bytes = (size_t)value;
+    else if (k == "fri_fused" && value >= 0 && value <= 2) ctx->fri_fused = (int)value;
+    else if (k == "hash_early_batches" && value >= 0 && value <= 16) ctx->hash_early_batches = (int)value;
     else if (k == "ntt_outer_log" && value >= -1 && value <= NTT_OUTER_MAX_LOG) ctx->ntt_outer_log = (int)value;
     else if (k == "upload_batch_cols" && value >= 1 && value <= 255) ctx->upload_batch_cols = (int)value;
     else if (k == "upload_edge_cols" && value >= -1 && value <= 255) ctx->upload_edge_cols = (int)value;
@@ -2722,7 +2738,9 @@ aero_status aero_fri_download_evaluations(aero_fri *fri, uint64_t *out, uint64_t
 }
 
 // transpose_slice + hash_values + MerkleTree::new of the current evaluations, queued on the stream
-static aero_status fri_commit_enqueue(aero_fri *fri) {
+// next_full != nullptr: the tree array was allocated by the previous layer's fused fold-and-hash, which has
+// already written the leaf digests into it
+static aero_status fri_commit_enqueue(aero_fri *fri, uint32_t *next_full = nullptr) {
     aero_ctx *ctx = fri->ctx;
     enter(ctx);
     if (!fri->cur) CTX_FAIL(ctx, AERO_ERR_STATE, "no evaluations to commit");
@@ -2734,11 +2752,12 @@ static aero_status fri_commit_enqueue(aero_fri *fri) {
     L.evals = fri->cur;
     L.M = fri->curM;
     L.log_cosets = fri->cur_log_cosets;
-    TRY(dev_alloc(ctx, (void **)&L.full, (size_t)2 * rows * 32));
+    if (next_full) L.full = next_full;
+    else TRY(dev_alloc(ctx, (void **)&L.full, (size_t)2 * rows * 32));
     {
         PhaseTimer t(ctx, "fri_commit");
         CUDA_TRY(ctx, cudaMemsetAsync(L.full, 0, 64, ctx->stream));
-        fri_leaf_hash(L.evals, rows, L.log_cosets, L.full + (size_t)rows * 8, ctx->stream);
+        if (!next_full) fri_leaf_hash(L.evals, rows, L.log_cosets, L.full + (size_t)rows * 8, ctx->stream);
         merkle_build(L.full, rows, ctx->stream);
     }
     fri->layers.push_back(L);
@@ -2746,9 +2765,13 @@ static aero_status fri_commit_enqueue(aero_fri *fri) {
     return AERO_OK;
 }
 // apply_drp of the committed layer; the challenge comes by value or from device memory (alpha_dev)
-static aero_status fri_fold_enqueue(aero_fri *fri, uint64_t alpha_canon, const uint64_t *alpha_dev) {
+// next_full_out != nullptr (challenge on the device): fused fold-and-hash where the shape allows -- the leaf
+// digests of the folded layer go into a freshly allocated tree array returned in *next_full_out (nullptr if
+// the plain fold ran).
+static aero_status fri_fold_enqueue(aero_fri *fri, uint64_t alpha_canon, const uint64_t *alpha_dev, uint32_t **next_full_out = nullptr) {
     aero_ctx *ctx = fri->ctx;
     enter(ctx);
+    if (next_full_out) *next_full_out = nullptr;
     if (!fri->cur_committed) CTX_FAIL(ctx, AERO_ERR_STATE, "commit the layer before folding it");
     const uint32_t M = fri->curM, rows = M / 8;
     const int logM = ilog2(M);
@@ -2763,9 +2786,24 @@ static aero_status fri_fold_enqueue(aero_fri *fri, uint64_t alpha_canon, const u
     const uint64_t w[4] = {1, w8i, gl::mul(w8i, w8i), gl::mul(gl::mul(w8i, w8i), w8i)};
     uint64_t *next = nullptr;
     TRY(dev_alloc(ctx, (void **)&next, (size_t)rows * 8));
+    const uint32_t rows2 = rows / 8;  // leaves of the folded layer
+    // Fused fold-and-hash runs rows / 8 threads of eight folds + four compressions each: measured on B200 it
+    // only pays where the layer is launch-latency bound (FRI of a 2^20-row proof: 0.490 ms with separate
+    // kernels, 0.546 ms with every layer fused -- the 2^17-thread first fused layer under-fills the GPU), so
+    // layers with more than 2^14 folded leaves keep the separate fold and leaf-hash kernels unless
+    // "fri_fused" is 2.
+    const bool fuse = next_full_out && alpha_dev && ctx->fri_fused && (rows2 <= (1u << 14) || ctx->fri_fused >= 2) && rows % 8 == 0 && rows2 >= 2 &&
+                      (fri->cur_log_cosets == 0 || (rows2 >> fri->cur_log_cosets) << fri->cur_log_cosets == rows2);
     {
         PhaseTimer t(ctx, "fri_fold");
-        fri_fold(fri->cur, rows, fri->cur_log_cosets, alpha_canon, alpha_dev, xinv, w, gl::inv(8), next, ctx->stream);
+        if (fuse) {
+            uint32_t *nf = nullptr;
+            TRY(dev_alloc(ctx, (void **)&nf, (size_t)2 * rows2 * 32));
+            fri_fold_hash(fri->cur, rows, fri->cur_log_cosets, alpha_dev, xinv, w, gl::inv(8), next, nf + (size_t)rows2 * 8, ctx->stream);
+            *next_full_out = nf;
+        } else {
+            fri_fold(fri->cur, rows, fri->cur_log_cosets, alpha_canon, alpha_dev, xinv, w, gl::inv(8), next, ctx->stream);
+        }
     }
     fri->cur = next;  // the committed layer keeps ownership of the old buffer
     fri->curM = rows;
@@ -2804,12 +2842,14 @@ static aero_status fri_build_layers_impl(aero_fri *fri, const uint8_t coin_seed[
     memcpy(ctx->h_stage, coin_seed, 32);
     uint8_t *d = ctx->d_stage;
     CUDA_TRY(ctx, cudaMemcpyAsync(d, ctx->h_stage, 32, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *next_full = nullptr;  // tree array of the next layer when the fold already hashed its leaves
     for (uint32_t l = 0; l < nl; l++) {
-        TRY(fri_commit_enqueue(fri));
+        TRY(fri_commit_enqueue(fri, next_full));
+        next_full = nullptr;
         uint64_t *d_alpha = (uint64_t *)(d + off_alpha) + l;
         fri_coin((uint32_t *)d, fri->layers.back().full + 8, d_alpha, (uint32_t *)(d + off_roots + (size_t)l * 32), ctx->stream);
         // the reference also draws a challenge for the remainder layer and discards the fold (prover/mod.rs:174-183)
-        if (l < num_layers) TRY(fri_fold_enqueue(fri, 0, d_alpha));
+        if (l < num_layers) TRY(fri_fold_enqueue(fri, 0, d_alpha, &next_full));
     }
     // Grinding rides on the same round trip: the coin's seed after the last layer is already on the device
     // (draws never move it).  One batch of 2^18 nonces finds a 16-bit nonce with probability 98 %; the

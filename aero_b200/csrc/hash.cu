@@ -9,18 +9,6 @@
 
 namespace aero {
 
-__device__ __forceinline__ void store_digest(uint32_t *dst, const uint32_t h[8]) {
-    uint4 *d = reinterpret_cast<uint4 *>(dst);
-    d[0] = make_uint4(h[0], h[1], h[2], h[3]);
-    d[1] = make_uint4(h[4], h[5], h[6], h[7]);
-}
-__device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t h[8]) {
-    const uint4 *s = reinterpret_cast<const uint4 *>(src);
-    uint4 a = s[0], b = s[1];
-    h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w;
-    h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
-}
-
 // One thread per LDE row.  The LDE is stored coset-major: storage row rho = q*n + i (local coset q)
 // holds natural row k = B*i + coset_begin + q, so thread rho reads column c at lde[c*col_stride + rho]:
 // a fully coalesced 8-byte-per-lane stream.  The digest goes to the leaf stage of the rank that owns

@@ -42,6 +42,18 @@ __device__ __forceinline__ uint64_t pow_lookup(const PowTable &t, uint32_t e) {
     return gl::mul(__ldg(t.lo + (e & ((1u << t.lo_bits) - 1))), __ldg(t.hi + (e >> t.lo_bits)));
 }
 
+__device__ __forceinline__ void store_digest(uint32_t *dst, const uint32_t h[8]) {
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    d[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    d[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+__device__ __forceinline__ void load_digest(const uint32_t *src, uint32_t h[8]) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 a = s[0], b = s[1];
+    h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w;
+    h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
+}
+
 // Gather the 8 evaluations of FRI leaf j = {f[j + k*rows]} (fri transpose_slice,
 // utils/core/src/lib.rs:574-581).  Thread index tau maps to leaf j so that loads are coalesced:
 // natural layout: j = tau; coset-major layout (B = 2^log_cosets cosets of M/B entries, natural q at
@@ -213,5 +225,10 @@ double measure_alu_peak(int num_sms, uint32_t *scratch, cudaStream_t s);
 // alpha_dev != nullptr: the folding challenge is read from device memory (written by fri_coin)
 void fri_fold(const uint64_t *f, uint32_t rows, int log_cosets, uint64_t alpha, const uint64_t *alpha_dev,
               PowTable xinv /* (7 g_M^j)^-1 */, const uint64_t w8inv[4], uint64_t inv8, uint64_t *out, cudaStream_t s);
+// fused fold-and-hash: the fold above plus the leaf digests of the folded layer (rows / 8 leaves of 8 values:
+// leaf j' = {next[j' + k * rows / 8]}), written to next_leaves[j'].  rows % 8 == 0; for a coset-major layer
+// rows / 8 must be a multiple of the number of cosets.
+void fri_fold_hash(const uint64_t *f, uint32_t rows, int log_cosets, const uint64_t *alpha_dev, PowTable xinv,
+                   const uint64_t w8inv[4], uint64_t inv8, uint64_t *next, uint32_t *next_leaves, cudaStream_t s);
 
 }  // namespace aero

@@ -558,3 +558,22 @@ def test_batch_inverse(ctx, ctx_mont, oracle):
     assert np.array_equal(ctx.batch_inverse(v), ref)
     assert all(int(a) * int(b) % P == 1 for a, b in zip(v[1:17], ref[1:17])) and ref[0] == 0
     assert np.array_equal(oracle.mont_to_canon(ctx_mont.batch_inverse(oracle.canon_to_mont(v))), ref)
+
+
+@pytest.mark.parametrize("fused", [0, 2])
+def test_fri_fused_fold_and_hash_modes_give_identical_proofs(oracle, fused):
+    """fri_fold_hash_kernel (fold layer l + leaf digests of layer l+1 in one kernel) forced onto every layer,
+    and switched off entirely, against the oracle's proof bytes (the default fuses only the small layers)."""
+    c = aero_b200.Context(0, form=aero_b200.AERO_FORM_CANONICAL)
+    try:
+        c.set_option("fri_fused", fused)
+        logn, wm, wa = 14, 6, 3
+        n = 1 << logn
+        main, aux = oracle.synthetic_trace(wm, n), oracle.synthetic_trace(wa, n, 0xAE210000)
+        ce = oracle.synthetic_trace(2, 8 * n, 0xCE)
+        divs = [oracle.Divisor(n, 1, [pow(oracle.root_of_unity(logn), n - 1, P)]), oracle.Divisor(1, 1, [])]
+        ref = oracle.prove(main, aux, ce, divs, b"fused")
+        got = c.prove(main, aux, ce, [make_divisor(d.a, d.b, d.exemptions) for d in divs], b"fused")
+        assert got == ref.proof_bytes
+    finally:
+        c.close()
