@@ -456,7 +456,8 @@ def run_aero(args) -> None:
                                # ncu: executed ALU-pipe thread instructions per butterfly (profiles/)
                                "alu_ops_per_butterfly": NTT_ALU_OPS_PER_BUTTERFLY,
                                "int_frac": bps * NTT_ALU_OPS_PER_BUTTERFLY / alu_peak,
-                               "note": "INT bound: ALU pipe 71-80 % busy in ncu, DRAM 17-26 %"}
+                               "note": "INT bound: ALU pipe 76-79 % busy in ncu, DRAM 10-27 % (profiles/r02_ncu_ntt_tma.txt); "
+                                       "tiles and twiddles fetched by TMA (cp.async.bulk[.tensor] on an mbarrier)"}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cl = args.ref_log_rows if args.ref_log_rows else log_rows

@@ -577,3 +577,27 @@ def test_fri_fused_fold_and_hash_modes_give_identical_proofs(oracle, fused):
         assert got == ref.proof_bytes
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("offset_words,stride_pad", [(0, 0), (1, 0), (0, 1), (1, 1), (2, 2)])
+def test_device_columns_of_any_alignment(ctx, oracle, offset_words, stride_pad):
+    """Device-resident input columns need only 8-byte alignment and any column stride >= n: the 2^9-point
+    passes of a 2^18-row segment fetch their tiles through a TMA tensor map when the source is 16-byte
+    aligned with an even stride, and fall back to the LDGSTS tile copy otherwise -- same results."""
+    logn, w = 18, 2
+    n = 1 << logn
+    trace = oracle.synthetic_trace(w, n, 0xAE240000)
+    ref = oracle.build_trace_commitment(trace, 8)
+    stride = n + stride_pad
+    buf = np.zeros(offset_words + w * stride, np.uint64)
+    for c in range(w):
+        buf[offset_words + c * stride: offset_words + c * stride + n] = trace[c]
+    d = ctx.device_alloc(buf.nbytes)
+    try:
+        ctx.device_upload(d, buf)
+        seg = ctx.build_trace_commitment_device(d + 8 * offset_words, w, n, 8, col_stride=stride)
+        assert np.array_equal(seg.download_polys(), ref.polys)
+        assert seg.root == ref.root
+        seg.destroy()
+    finally:
+        ctx.device_free(d)

@@ -64,6 +64,23 @@ def test_group_prove_byte_identical(oracle, world, logn, wm, wa):
         g.close()
 
 
+@pytest.mark.parametrize("world,logn,outer", [(2, 14, 2), (4, 15, 1)])
+def test_group_prove_three_pass_transforms(oracle, world, logn, outer):
+    """Sharded proofs of 2^21+ rows run their (coset-sharded) extensions through three-pass NTT plans; the
+    same plans forced onto a size the oracle covers, cold and warm."""
+    main, aux, ce, divs = _inputs(oracle, logn, 10, 3)
+    pub = b"sharded three-pass"
+    ref = oracle.prove(main, aux, ce, divs, pub)
+    gdivs = [make_divisor(d.a, d.b, d.exemptions) for d in divs]
+    g = aero_b200.Group([0] * world, window_bytes(logn, 13, world), form=aero_b200.AERO_FORM_CANONICAL)
+    try:
+        g.set_option("ntt_outer_log", outer)
+        for it in range(2):
+            assert g.prove(main, aux, ce, gdivs, pub) == ref.proof_bytes, "world %d, proof %d" % (world, it)
+    finally:
+        g.close()
+
+
 def test_group_prove_montgomery_and_host_sync(oracle):
     """Montgomery ABI form, and the host-synchronised barrier mode kept on for every proof."""
     main, aux, ce, divs = _inputs(oracle, 11, 9, 2)
