@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -106,7 +107,7 @@ struct aero_ctx {
     int upload_edge_cols = -1;                 // size of its first / last batch (-1: half a batch, 0: uniform batches)
     size_t ntt_table_max_bytes = (size_t)1 << 30;  // largest full inter-pass twiddle table a plan may hold
     int hash_early_batches = 2;  // host-buffer commits: column batches hashed right after their extension ("hash_early_batches")
-    int fri_fused = 1;       // fold a FRI layer and hash the next layer's leaves in one kernel: 0 never, 1 small layers, 2 all ("fri_fused")
+    int fri_fused = 0;       // fold a FRI layer and hash the next layer's leaves in one kernel: 0 never (default: measured slower), 1 small layers, 2 all ("fri_fused")
     int ntt_outer_log = -1;  // third factor of two-pass transforms: -1 = 2^(logn-20) above 2^20 points, 0 = never, k = force 2^k (tests)
     int shard_rank = 0, shard_world = 1;       // LDE coset shard of this context (multi-GPU)
     std::multimap<size_t, void *> free_blocks;  // exact-size cache of released device blocks
@@ -2102,6 +2103,8 @@ aero_status aero_open_queries(aero_ctx *ctx, aero_fri *fri, aero_segment *const 
     enter(ctx);
     if (!positions || (fri && !fri_len) || (n_segs && (!segs || !rows_out || !batch_nodes_out || !batch_len)))
         CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
+    static const bool timing = getenv("AERO_HOST_TIMING") != nullptr;  // diagnostic: host time of the planning step
+    const auto t_begin = std::chrono::steady_clock::now();
     GatherBatch gb(ctx);
     FriOpening fo;
     std::vector<SegmentOpening> so(n_segs);
@@ -2113,7 +2116,12 @@ aero_status aero_open_queries(aero_ctx *ctx, aero_fri *fri, aero_segment *const 
         if (!segs[i] || segs[i]->ctx != ctx) CTX_FAIL(ctx, AERO_ERR_INVALID, "segment %u is null or belongs to another context", i);
         TRY(segment_open_plan(segs[i], positions, n_pos, true, gb, so[i]));
     }
+    const auto t_plan = std::chrono::steady_clock::now();
     TRY(gb.run());
+    if (timing)
+        fprintf(stderr, "aero_open_queries: plan %.1f us, gather batch (upload, %zu launches, download, sync) %.1f us\n",
+                std::chrono::duration<double, std::micro>(t_plan - t_begin).count(), gb.jobs.size(),
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_plan).count());
     aero_status worst = AERO_OK;  // report every required size before failing with AERO_ERR_BUFFER
     if (fri) {
         aero_status st = fri_open_finish(fo, gb, fri_proof_bytes, fri_len);
@@ -2787,11 +2795,11 @@ static aero_status fri_fold_enqueue(aero_fri *fri, uint64_t alpha_canon, const u
     uint64_t *next = nullptr;
     TRY(dev_alloc(ctx, (void **)&next, (size_t)rows * 8));
     const uint32_t rows2 = rows / 8;  // leaves of the folded layer
-    // Fused fold-and-hash runs rows / 8 threads of eight folds + four compressions each: measured on B200 it
-    // only pays where the layer is launch-latency bound (FRI of a 2^20-row proof: 0.490 ms with separate
-    // kernels, 0.546 ms with every layer fused -- the 2^17-thread first fused layer under-fills the GPU), so
-    // layers with more than 2^14 folded leaves keep the separate fold and leaf-hash kernels unless
-    // "fri_fused" is 2.
+    // Fused fold-and-hash (fri_fold_hash_kernel) runs rows / 8 threads of eight folds + four compressions each.
+    // Measured on B200 (FRI of a 2^20-row proof, profiles/r02_bench_x5_*.json, r02_bench_x7_*.json): 0.490 ms
+    // with separate kernels, 0.546 ms with every layer fused, 0.571 ms with only the layers of <= 2^14 folded
+    // leaves fused -- one launch per layer is saved, but every thread's dependent chain gets eight folds longer
+    // and the layers are latency-, not launch-bound.  Off by default ("fri_fused": 1 = small layers, 2 = all).
     const bool fuse = next_full_out && alpha_dev && ctx->fri_fused && (rows2 <= (1u << 14) || ctx->fri_fused >= 2) && rows % 8 == 0 && rows2 >= 2 &&
                       (fri->cur_log_cosets == 0 || (rows2 >> fri->cur_log_cosets) << fri->cur_log_cosets == rows2);
     {

@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(MAXT) dft_pass1_kernel(const uint64_t *__restr
     uint32_t i1 = c * T + ii;
     if (TAB) {
         // table loads of U chunks in flight before the first product needs one
-        constexpr int U = 4;
+        constexpr int U = 8;
         const size_t cstride = ((size_t)cstep << log2) * T;       // entries between this thread's chunks
         const uint64_t *fp = ftab + ((size_t)c << log2) * T + t * T + ii;
         uint64_t *op = o + ((size_t)c << log2) * T + (size_t)j2 * T + ii;

@@ -5,6 +5,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -305,7 +306,28 @@ aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_
     return st;
 }
 
+// Diagnostic (AERO_HOST_TIMING=1): wall-clock marks of the host-side sections of a proof, printed to stderr.
+struct HostMarks {
+    bool on = getenv("AERO_HOST_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    std::string log;
+    void mark(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof buf, "  %-28s +%8.1f us  (at %9.1f us)\n", what,
+                 std::chrono::duration<double, std::micro>(now - last).count(),
+                 std::chrono::duration<double, std::micro>(now - t0).count());
+        log += buf;
+        last = now;
+    }
+    ~HostMarks() {
+        if (on) fprintf(stderr, "aero_prove host marks:\n%s", log.c_str());
+    }
+};
+
 static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_t> *proof_bytes, std::string *err) {
+    HostMarks hm;
     const aero_proof_options &o = in.options;
     if (o.hash_fn != 4) P_FAIL(AERO_ERR_UNSUPPORTED, "only Blake2s_256 (hash_fn = 4) is supported");
     if (o.field_extension != 1) P_FAIL(AERO_ERR_UNSUPPORTED, "only FieldExtension::None is supported");
@@ -436,6 +458,7 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
         memcpy(root, roots.data() + (H.segs.size() - 1) * 32, 32);
     }
     channel.commit_constraints(Digest(root, root + 32));
+    hm.mark("commitments + roots");
 
     // 4 ----- OOD frame + DEEP composition polynomial (lib.rs:421-467)
     uint64_t z;
@@ -457,6 +480,7 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
         for (uint32_t i = 0; i < m; i++) ev[i] = from_abi(ood_comp[i]);
         channel.send_ood_constraint_evaluations(ev);
     }
+    hm.mark("ood frame");
     // get_deep_composition_coefficients (air/src/air/mod.rs:537-561): W triples, m singles, one pair
     std::vector<uint64_t> cc;
     if (!channel.draw_elements((size_t)3 * W + m + 2, &cc)) P_FAIL(AERO_ERR_STATE, "failed to draw DEEP coefficients");
@@ -464,6 +488,7 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
     P_TRY(aero_deep_compose(ctx, trace_segs.data(), (uint32_t)trace_segs.size(), comp_seg, to_abi(z), ood_trace.data(),
                             ood_comp.data(), cc.data(), &H.fri));
 
+    hm.mark("deep_compose queued");
     // 6 ----- FRI layers (fri/src/prover/mod.rs:166-191)
     const size_t num_layers = ProofOptions{o}.num_fri_layers(N);
     {
@@ -475,6 +500,7 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
         // ... and the grinding search (channel.rs:151-167) queued right behind them, on the device coin's seed
         P_TRY(aero_fri_build_layers_grind(H.fri, channel.coin().seed().data(), (uint32_t)num_layers, o.grinding_factor,
                                           roots.data(), alphas.data(), &nonce));
+        hm.mark("fri layers + grind (sync)");
         for (size_t l = 0; l < num_layers + 1; l++) {
             channel.commit_fri_layer(Digest(roots.begin() + l * 32, roots.begin() + (l + 1) * 32));
             uint64_t alpha;
@@ -485,8 +511,10 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
         if (channel.set_pow_nonce(nonce) != AERO_OK) P_FAIL(AERO_ERR_STATE, "device grinding nonce does not satisfy the channel's coin");
     }
 
+    hm.mark("channel replay + nonce");
     std::vector<uint64_t> positions;
     if (!channel.get_query_positions(&positions)) P_FAIL(AERO_ERR_STATE, "failed to draw query positions");
+    hm.mark("query positions");
 
     // 8 ----- proof object (lib.rs:518-539)
     // FriProver::build_proof + build_segment_queries (prover/src/trace/commitment.rs:115-140) for every
@@ -511,6 +539,7 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
     }
     std::vector<uint8_t> fri_bytes(256 << 10);
     size_t flen = fri_bytes.size();
+    hm.mark("opening buffers");
     aero_status ost = aero_open_queries(ctx, H.fri, open_segs.data(), (uint32_t)ns, positions.data(), (uint32_t)np,
                                         fri_bytes.data(), &flen, rows_ptr.data(), paths_ptr.data(), paths_len.data());
     if (ost == AERO_ERR_BUFFER) {  // sizes were reported: grow and repeat
@@ -523,6 +552,7 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
                                 &flen, rows_ptr.data(), paths_ptr.data(), paths_len.data());
     }
     P_TRY(ost);
+    hm.mark("open_queries (sync)");
     fri_bytes.resize(flen);
     std::vector<Queries> all_q(ns);
     for (size_t i = 0; i < ns; i++) {
@@ -534,6 +564,7 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
     all_q.pop_back();
     std::vector<Queries> tq = std::move(all_q);
     *proof_bytes = channel.build_proof(std::move(tq), std::move(cq), std::move(fri_bytes)).to_bytes();
+    hm.mark("proof bytes");
     return AERO_OK;
 }
 

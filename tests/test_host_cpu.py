@@ -170,3 +170,29 @@ def test_rust_patches_apply_and_export_what_the_shim_uses(tmp_path):
         assert not re.search(r"pub fn %s\b" % name, open(os.path.join(ref, rel)).read()), "%s exists upstream: drop the patch" % name
     main_rs = open(tmp_path / "miden-proof-generator/src/main.rs").read()
     assert "GpuExecutionProver::new(inner, 0)" in main_rs and "DumpingProver::new(inner" in main_rs
+
+
+def test_air_program_builder_marshals_the_c_struct():
+    """AirProgramBuilder -> aero_air_program (include/aero_b200.h): node order, operand indices, the constant
+    pool and the per-constraint arrays arrive in the C layout the kernel-side validation expects."""
+    from aero_b200 import AirProgramBuilder
+    from aero_b200 import _lib
+
+    b = AirProgramBuilder()
+    c0, n0, k = b.cur(0), b.next(0), b.const(7)
+    t = b.sub(n0, b.mul(c0, k))
+    b.transition(t, 5)
+    b.assertion(0, 1, 3, 1)
+    p, keep = b.finish()
+    assert p.n_nodes == 5 and p.n_consts == 1 and p.n_transition == 1 and p.n_boundary == 1
+    ops = [(p.nodes[i].op, p.nodes[i].a, p.nodes[i].b) for i in range(p.n_nodes)]
+    assert ops == [(_lib.AERO_AIR_CUR, 0, 0), (_lib.AERO_AIR_NEXT, 0, 0), (_lib.AERO_AIR_CONST, 0, 0),
+                   (_lib.AERO_AIR_MUL, c0, k), (_lib.AERO_AIR_SUB, n0, 3)]
+    assert p.consts[0] == 7 and p.transition_out[0] == t and p.transition_adj[0] == 5
+    assert (p.boundary_col[0], p.boundary_value[0], p.boundary_adj[0], p.boundary_div[0]) == (0, 1, 3, 1)
+    # the header's enum and the ctypes constants agree
+    import re, os
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "aero_b200.h")).read()
+    m = re.search(r"enum \{ AERO_AIR_CUR = (\d), AERO_AIR_NEXT = (\d), AERO_AIR_CONST = (\d), AERO_AIR_ADD = (\d), AERO_AIR_SUB = (\d), AERO_AIR_MUL = (\d) \}", hdr)
+    assert m and [int(x) for x in m.groups()] == [_lib.AERO_AIR_CUR, _lib.AERO_AIR_NEXT, _lib.AERO_AIR_CONST,
+                                                  _lib.AERO_AIR_ADD, _lib.AERO_AIR_SUB, _lib.AERO_AIR_MUL]
