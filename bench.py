@@ -40,9 +40,9 @@ MAIN_W, AUX_W, CE_COLS, BLOWUP = 72, 9, 2, 8
 NTT_ALU_OPS_PER_BUTTERFLY = 21.8
 ALU_OPS_PER_COMPRESSION = 661
 # DRAM bytes of one hash_rows_kernel launch (w = 72, N = 2^23) in this round's ncu --set full capture
-# (profiles/r02_ncu_hash.txt); reported under roofline.traffic_ncu, never as a measurement of this run
-HASH_W72_NCU = {"bytes_per_launch": 5.100e9, "read": 4.834e9, "write": 0.266e9, "algorithmic": 5.100e9,
-                "source": "profiles/r02_ncu_hash_merkle.txt (ncu --set full, w = 72, N = 2^23)"}
+# (profiles/r02_final_ncu_hash.txt); reported under roofline.traffic_ncu, never as a measurement of this run
+HASH_W72_NCU = {"bytes_per_launch": 5.100e9, "read": 4.833e9, "write": 0.267e9, "algorithmic": 5.100e9,
+                "source": "profiles/r02_final_ncu_hash.txt (ncu --set full, w = 72, N = 2^23)"}
 PUB = b"aero-b200 bench public inputs"
 
 
