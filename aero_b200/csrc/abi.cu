@@ -2174,7 +2174,7 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
     if (ctx_sharded(ctx)) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "constraint evaluation on a sharded context");
     if (n_trace_segs == 0 || n_trace_segs > 4) CTX_FAIL(ctx, AERO_ERR_INVALID, "1..4 trace segments");
     if (n_div == 0 || n_div > 8) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of divisors must be 1..8, got %u", n_div);
-    if (prog->n_nodes == 0 || prog->n_nodes > 1024 || !prog->nodes) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "transition program must have 1..1024 nodes");
+    if (prog->n_nodes == 0 || prog->n_nodes > (1u << 16) || !prog->nodes) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "transition program must have 1..65536 nodes");
     if (n_coeffs != 2 * (prog->n_transition + prog->n_boundary)) CTX_FAIL(ctx, AERO_ERR_INVALID, "expected a coefficient pair per constraint (%u), got %u elements", prog->n_transition + prog->n_boundary, n_coeffs);
     if ((prog->n_transition && (!prog->transition_out || !prog->transition_adj)) ||
         (prog->n_boundary && (!prog->boundary_col || !prog->boundary_value || !prog->boundary_adj || !prog->boundary_div)) ||
@@ -2237,17 +2237,50 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
     for (uint32_t j = 0; j < nb; j++) w64[o_bval + j] = to_canon(ctx, prog->boundary_value[j]);
     for (uint32_t i = 0; i < n_coeffs; i++) w64[o_coeffs + i] = to_canon(ctx, coeffs[i]);
     for (size_t i = 0; i < adj.size(); i++) w64[o_adj + i] = adj[i];
+    // Slots by liveness: a node's value occupies a slot from its evaluation to its last consumer; operands that
+    // die at node k free their slots before k's result is placed (the kernel reads both operands, then writes).
+    const uint32_t NN = prog->n_nodes;
+    std::vector<uint32_t> last(NN, 0), slot(NN, 0);
+    std::vector<bool> used(NN, false);
+    for (uint32_t k = 0; k < NN; k++)
+        if (prog->nodes[k].op >= AERO_AIR_ADD) {
+            last[prog->nodes[k].a] = k;
+            last[prog->nodes[k].b] = k;
+            used[prog->nodes[k].a] = used[prog->nodes[k].b] = true;
+        }
+    for (uint32_t t = 0; t < nt; t++) {
+        last[prog->transition_out[t]] = 0xFFFFFFFFu;  // constraint values live to the end
+        used[prog->transition_out[t]] = true;
+    }
+    std::vector<uint32_t> free_slots;
+    uint32_t n_slots = 0;
+    for (uint32_t k = 0; k < NN; k++) {
+        const aero_air_node &nd = prog->nodes[k];
+        if (nd.op >= AERO_AIR_ADD) {
+            if (last[nd.a] == k) free_slots.push_back(slot[nd.a]);
+            if (nd.b != nd.a && last[nd.b] == k) free_slots.push_back(slot[nd.b]);
+        }
+        if (free_slots.empty()) slot[k] = n_slots++;
+        else {
+            slot[k] = free_slots.back();
+            free_slots.pop_back();
+        }
+        if (!used[k]) free_slots.push_back(slot[k]);  // a value nobody reads
+    }
     std::vector<uint32_t> w32;
-    const size_t o_nodes = 0, o_tout = o_nodes + 3 * (size_t)prog->n_nodes, o_tadj = o_tout + nt, o_bcol = o_tadj + nt,
+    const size_t o_nodes = 0, o_tout = o_nodes + 4 * (size_t)NN, o_tadj = o_tout + nt, o_bcol = o_tadj + nt,
                  o_badj = o_bcol + nb, o_bdiv = o_badj + nb;
     w32.resize(o_bdiv + nb);
-    for (uint32_t k = 0; k < prog->n_nodes; k++) {
-        w32[o_nodes + 3 * k] = prog->nodes[k].op;
-        w32[o_nodes + 3 * k + 1] = prog->nodes[k].a;
-        w32[o_nodes + 3 * k + 2] = prog->nodes[k].b;
+    for (uint32_t k = 0; k < NN; k++) {
+        const aero_air_node &nd = prog->nodes[k];
+        const bool arith = nd.op >= AERO_AIR_ADD;
+        w32[o_nodes + 4 * k] = nd.op;
+        w32[o_nodes + 4 * k + 1] = arith ? slot[nd.a] : nd.a;
+        w32[o_nodes + 4 * k + 2] = arith ? slot[nd.b] : 0;
+        w32[o_nodes + 4 * k + 3] = slot[k];
     }
     for (uint32_t t = 0; t < nt; t++) {
-        w32[o_tout + t] = prog->transition_out[t];
+        w32[o_tout + t] = slot[prog->transition_out[t]];
         w32[o_tadj + t] = t_adj[t];
     }
     for (uint32_t j = 0; j < nb; j++) {
@@ -2255,6 +2288,7 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
         w32[o_badj + j] = b_adj[j];
         w32[o_bdiv + j] = prog->boundary_div[j];
     }
+    if (n_slots > 1024) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "transition program keeps %u values alive at once (max 1024)", n_slots);
     DevBlocks blk(ctx);
     uint64_t *d64 = nullptr;
     uint32_t *d32 = nullptr;
@@ -2274,6 +2308,7 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
     p.coeffs = d64 + o_coeffs;
     p.adj = d64 + o_adj;
     p.n_nodes = (int)prog->n_nodes;
+    p.n_slots = (int)std::max<uint32_t>(1, n_slots);
     p.nt = (int)nt;
     p.nb = (int)nb;
     p.n_adj = (int)adj.size();

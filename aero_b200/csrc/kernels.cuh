@@ -206,14 +206,15 @@ struct AirSegs {  // trace segments in order: column c of segment s at lde[s] + 
     int nseg;
 };
 struct AirProgramDev {       // device copies; field elements canonical
-    const uint32_t *nodes;   // 3 words per node: op, a, b
+    const uint32_t *nodes;   // 4 words per node (16-byte aligned): op, a, b, destination slot; operands of
+                             //   add / sub / mul and t_out are SLOTS (assigned by liveness on the host)
     const uint64_t *consts;
     const uint32_t *t_out, *t_adj;           // per transition constraint: node, index into adj
     const uint32_t *b_col, *b_adj, *b_div;   // per boundary constraint
     const uint64_t *b_val;
     const uint64_t *coeffs;  // pairs: transition constraints, then boundary constraints
     const uint64_t *adj;     // distinct degree adjustments
-    int n_nodes, nt, nb, n_adj, n_div;
+    int n_nodes, n_slots, nt, nb, n_adj, n_div;
 };
 void air_evaluate(const AirSegs &segs, const AirProgramDev &p, int logn, int log_blowup, int log_ce, PowTable x_ce /* 7 g_ce^s */,
                   int to_montgomery, uint64_t *out, size_t out_stride, cudaStream_t s);

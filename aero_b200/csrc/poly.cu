@@ -741,8 +741,10 @@ void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDe
 // ConstraintEvaluator::evaluate (prover/src/constraints/evaluator.rs:121-230) for a transition program:
 // one thread per step of the constraint evaluation domain.  Threads are numbered coset-major like the LDE
 // (thread = rc * n + i for step s = i * ce_blowup + rc), so frame loads are coalesced; the next row of the
-// frame is the same LDE coset one position on (trace_lde.rs: + blowup, wrapping).  Node values live in a
-// per-thread array (local memory: coalesced across the warp for equal node indices).
+// frame is the same LDE coset one position on (trace_lde.rs: + blowup, wrapping).  Node values live in
+// per-thread SLOTS (local memory: coalesced across the warp for equal slot indices); the host assigns slots
+// by liveness (a slot is reused once the last consumer of its value has run), so the per-thread footprint is
+// the widest cut of the expression DAG, not its size.
 template <int MAXN>
 __global__ void __launch_bounds__(128) air_evaluate_kernel(AirSegs segs, AirProgramDev p, int logn, int log_blowup, int log_ce,
                                                           PowTable x_ce, int to_montgomery, uint64_t *__restrict__ out,
@@ -766,17 +768,17 @@ __global__ void __launch_bounds__(128) air_evaluate_kernel(AirSegs segs, AirProg
     for (int a = 0; a < p.n_adj; a++) xp[a] = gl::pow(x, p.adj[a]);   // domain.rs:109-117: x^adjustment
     uint64_t val[MAXN];
     for (int k = 0; k < p.n_nodes; k++) {
-        const uint32_t op = __ldg(p.nodes + 3 * k), a = __ldg(p.nodes + 3 * k + 1), b = __ldg(p.nodes + 3 * k + 2);
+        const uint4 nd = __ldg(reinterpret_cast<const uint4 *>(p.nodes) + k);   // op, a, b, destination slot
         uint64_t v;
-        switch (op) {
-        case 0: v = load(a, cur); break;
-        case 1: v = load(a, nxt); break;
-        case 2: v = __ldg(p.consts + a); break;
-        case 3: v = gl::add(val[a], val[b]); break;
-        case 4: v = gl::sub(val[a], val[b]); break;
-        default: v = gl::mul(val[a], val[b]); break;
+        switch (nd.x) {
+        case 0: v = load(nd.y, cur); break;
+        case 1: v = load(nd.y, nxt); break;
+        case 2: v = __ldg(p.consts + nd.y); break;
+        case 3: v = gl::add(val[nd.y], val[nd.z]); break;
+        case 4: v = gl::sub(val[nd.y], val[nd.z]); break;
+        default: v = gl::mul(val[nd.y], val[nd.z]); break;
         }
-        val[k] = v;
+        val[nd.w] = v;
     }
     uint64_t acc[8];
     for (int d = 0; d < 8; d++) acc[d] = 0;
@@ -800,7 +802,8 @@ void air_evaluate(const AirSegs &segs, const AirProgramDev &p, int logn, int log
     const uint64_t threads = (uint64_t)1 << (logn + log_ce);
     const unsigned grid = (unsigned)((threads + 127) / 128);
     AERO_COUNT_LAUNCH(1);
-    if (p.n_nodes <= 64) air_evaluate_kernel<64><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride);
+    if (p.n_slots <= 32) air_evaluate_kernel<32><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride);
+    else if (p.n_slots <= 128) air_evaluate_kernel<128><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride);
     else air_evaluate_kernel<1024><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride);
 }
 

@@ -7,7 +7,8 @@ Synthetic constraint columns (random data) can never fail that check's prover si
 wrong divisor convention, a missing exemption or a swapped composition column makes `verify` fail.
 
 Restated, each with the file:line it follows (paths relative to winterfell/):
-  * the Fibonacci AIR of examples/src/fibonacci/fib2 (air.rs:15-71, prover.rs:22-40);
+  * the Fibonacci AIR of examples/src/fibonacci/fib2 (air.rs:15-71, prover.rs:22-40) and the multiplicative
+    Fibonacci AIR of examples/src/fibonacci/mulfib2 (air.rs:15-80, prover.rs:20-40: degree-2 constraints);
   * AirContext (air/src/air/context.rs:87-193): ce_blowup_factor, composition degree;
   * TransitionConstraints / TransitionConstraintGroup (air/src/air/transition/mod.rs:36-290,
     degree.rs:102-131): grouping by evaluation degree, degree adjustment, merge_evaluations;
@@ -18,7 +19,7 @@ Restated, each with the file:line it follows (paths relative to winterfell/):
     255-275, domain.rs:99-117): one column per divisor over the constraint evaluation domain;
   * the verifier's evaluate_constraints (verifier/src/evaluator.rs:14-107) and the comparison in
     verifier/src/lib.rs:248-290.
-Only what fib2 uses is covered: main segment only, single-value assertions, no periodic columns.
+Only what these two use is covered: main segment only, single-value assertions, no periodic columns.
 Pure Python big-int arithmetic: small traces only."""
 from __future__ import annotations
 
@@ -69,11 +70,12 @@ class Assertion:  # single-value assertions only (air/src/air/assertions/mod.rs:
     value: int
 
 
-class Fib2Air:
-    """examples/src/fibonacci/fib2/air.rs: two registers, two terms of the sequence per row."""
+class SimpleAir:
+    """The AIR-generic machinery (AirContext, constraint groups, prover- and verifier-side evaluation);
+    subclasses supply trace_width, transition_degrees, build_trace, evaluate_transition, get_assertions."""
 
-    trace_width = 2
-    transition_degrees = [1, 1]  # TransitionConstraintDegree::new(1) twice (air.rs:27-30)
+    trace_width = 0
+    transition_degrees: List[int] = []
     num_transition_exemptions = 1  # context.rs:159
 
     def __init__(self, trace_length: int, result: int, blowup: int = 8):
@@ -94,21 +96,11 @@ class Fib2Air:
     def trace_poly_degree(self) -> int:
         return self.n - 1
 
-    @staticmethod
-    def build_trace(n: int) -> np.ndarray:  # prover.rs:22-40
-        s0, s1 = 1, 1
-        cols = np.empty((2, n), np.uint64)
-        for i in range(n):
-            cols[0, i], cols[1, i] = s0, s1
-            s0 = (s0 + s1) % P
-            s1 = (s1 + s0) % P
-        return cols
+    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int]) -> List[int]:
+        raise NotImplementedError
 
-    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int]) -> List[int]:  # air.rs:41-58
-        return [(nxt[0] - (cur[0] + cur[1])) % P, (nxt[1] - (cur[1] + nxt[0])) % P]
-
-    def get_assertions(self) -> List[Assertion]:  # air.rs:60-70
-        return [Assertion(0, 0, 1), Assertion(1, 0, 1), Assertion(1, self.n - 1, self.result)]
+    def get_assertions(self) -> List[Assertion]:
+        raise NotImplementedError
 
     def num_constraint_coefficients(self) -> int:
         """Field elements drawn by get_constraint_composition_coefficients (air/src/air/mod.rs:511-533):
@@ -216,12 +208,60 @@ class Fib2Air:
         return result
 
 
+class Fib2Air(SimpleAir):
+    """examples/src/fibonacci/fib2/air.rs: two registers, two terms of the sequence per row."""
+
+    trace_width = 2
+    transition_degrees = [1, 1]  # TransitionConstraintDegree::new(1) twice (air.rs:27-30)
+
+    @staticmethod
+    def build_trace(n: int) -> np.ndarray:  # prover.rs:22-40
+        s0, s1 = 1, 1
+        cols = np.empty((2, n), np.uint64)
+        for i in range(n):
+            cols[0, i], cols[1, i] = s0, s1
+            s0 = (s0 + s1) % P
+            s1 = (s1 + s0) % P
+        return cols
+
+    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int]) -> List[int]:  # air.rs:41-58
+        return [(nxt[0] - (cur[0] + cur[1])) % P, (nxt[1] - (cur[1] + nxt[0])) % P]
+
+    def get_assertions(self) -> List[Assertion]:  # air.rs:60-70
+        return [Assertion(0, 0, 1), Assertion(1, 0, 1), Assertion(1, self.n - 1, self.result)]
+
+
+class MulFib2Air(SimpleAir):
+    """examples/src/fibonacci/mulfib2/air.rs: the multiplicative Fibonacci sequence, two registers --
+    transition constraints of degree 2 (a different evaluation degree, hence a different degree adjustment
+    and a composition polynomial that really needs both of its columns)."""
+
+    trace_width = 2
+    transition_degrees = [2, 2]  # air.rs:29-32
+
+    @staticmethod
+    def build_trace(n: int) -> np.ndarray:  # prover.rs:24-37 (the trace has `length / 2` rows there; n rows here)
+        s0, s1 = 1, 2
+        cols = np.empty((2, n), np.uint64)
+        for i in range(n):
+            cols[0, i], cols[1, i] = s0, s1
+            s0 = s0 * s1 % P
+            s1 = s1 * s0 % P
+        return cols
+
+    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int]) -> List[int]:  # air.rs:47-63
+        return [(nxt[0] - cur[0] * cur[1]) % P, (nxt[1] - cur[1] * nxt[0]) % P]
+
+    def get_assertions(self) -> List[Assertion]:  # air.rs:65-75: starts with 1, 2; register 0 ends with the result
+        return [Assertion(0, 0, 1), Assertion(1, 0, 2), Assertion(0, self.n - 1, self.result)]
+
+
 def _next_pow2(x: int) -> int:
     """usize::next_power_of_two: 0 and 1 map to 1."""
     return 1 if x <= 1 else 1 << (x - 1).bit_length()
 
 
-def ood_consistency_check(air: Fib2Air, coeffs: Sequence[int], ood_cur, ood_next, ood_comp: Sequence[int], z: int) -> None:
+def ood_consistency_check(air: SimpleAir, coeffs: Sequence[int], ood_cur, ood_next, ood_comp: Sequence[int], z: int) -> None:
     """verifier/src/lib.rs:248-290: constraints evaluated over the OOD frame must equal
     sum_i z^i * H_i(z^m) reduced from the composition-column evaluations the prover sent."""
     lhs = air.evaluate_constraints_at(coeffs, ood_cur, ood_next, z)

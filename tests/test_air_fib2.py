@@ -10,15 +10,19 @@ import numpy as np
 import pytest
 
 from oracle import stark_oracle as so
-from oracle.air import Fib2Air, P
+from oracle.air import Fib2Air, MulFib2Air, P
+
+AIRS = {"fib2": Fib2Air, "mulfib2": MulFib2Air}
 
 
-def _setup(logn):
+def _setup(logn, which="fib2"):
     n = 1 << logn
-    trace = Fib2Air.build_trace(n)
-    air = Fib2Air(n, int(trace[1, n - 1]))
+    cls = AIRS[which]
+    trace = cls.build_trace(n)
+    result = int(trace[1, n - 1]) if which == "fib2" else int(trace[0, n - 1])  # the asserted final value
+    air = cls(n, result)
     divs = [so.Divisor(d.a, d.b, d.exemptions) for d in air.divisors()]
-    pub = int(trace[1, n - 1]).to_bytes(8, "little")  # BaseElement::to_bytes of the public input
+    pub = result.to_bytes(8, "little")  # BaseElement::to_bytes of the public input
     return n, trace, air, divs, pub
 
 
@@ -44,9 +48,22 @@ def test_fib2_trace_and_structure():
         assert air.evaluate_transition([int(trace[0, i]), int(trace[1, i])], [int(trace[0, i + 1]), int(trace[1, i + 1])]) == [0, 0]
 
 
+def test_mulfib2_structure():
+    """The multiplicative Fibonacci AIR (degree-2 constraints): a different degree adjustment for the
+    transition group, the same boundary structure."""
+    n, trace, air, divs, _ = _setup(4, "mulfib2")
+    assert [int(v) for v in trace[0, :3]] == [1, 2, 8] and [int(v) for v in trace[1, :3]] == [2, 4, 32]
+    assert air.ce_blowup == 2 and air.composition_degree() == 2 * n - 1
+    (adj_t, members), = air.transition_groups([(1, 2), (3, 4)])
+    assert adj_t == (2 * n - 1) + (n - 1) - 2 * (n - 1)
+    for i in range(n - 1):
+        assert air.evaluate_transition([int(trace[0, i]), int(trace[1, i])], [int(trace[0, i + 1]), int(trace[1, i + 1])]) == [0, 0]
+
+
+@pytest.mark.parametrize("which", ["fib2", "mulfib2"])
 @pytest.mark.parametrize("logn", [3, 6, 8])
-def test_fib2_oracle_proof_passes_the_ood_consistency_check(logn):
-    n, trace, air, divs, pub = _setup(logn)
+def test_fib2_oracle_proof_passes_the_ood_consistency_check(logn, which):
+    n, trace, air, divs, pub = _setup(logn, which)
     ref = _oracle_prove(trace, air, divs, pub)
     rep = so.verify(ref.proof_bytes, pub, air.ce_blowup, air=air)
     assert len(rep.positions) == 27 and rep.z == ref.z
@@ -107,15 +124,20 @@ def test_fib2_gpu_proof_is_byte_identical_and_verifies(ctx, ctx_mont, logn, form
 
 
 def _fib2_program(air, to_abi_int):
-    """The fib2 AIR as an aero_air_program: evaluate_transition (air.rs:41-58) recorded node by node, the
-    transition group's degree adjustment, and the assertions in the reference's coefficient order with
-    their divisor columns (oracle/air.py boundary_groups restates the grouping)."""
+    """The fib2 / mulfib2 AIR as an aero_air_program: evaluate_transition (fib2/air.rs:41-58,
+    mulfib2/air.rs:47-63) recorded node by node, the transition group's degree adjustment, and the assertions
+    in the reference's coefficient order with their divisor columns (oracle/air.py boundary_groups restates
+    the grouping)."""
     from aero_b200 import AirProgramBuilder
 
     b = AirProgramBuilder()
     c0, c1, n0, n1 = b.cur(0), b.cur(1), b.next(0), b.next(1)
-    t0 = b.sub(n0, b.add(c0, c1))   # next[0] - (cur[0] + cur[1])
-    t1 = b.sub(n1, b.add(c1, n0))   # next[1] - (cur[1] + next[0])
+    if isinstance(air, MulFib2Air):
+        t0 = b.sub(n0, b.mul(c0, c1))   # next[0] - cur[0] * cur[1]
+        t1 = b.sub(n1, b.mul(c1, n0))   # next[1] - cur[1] * next[0]
+    else:
+        t0 = b.sub(n0, b.add(c0, c1))   # next[0] - (cur[0] + cur[1])
+        t1 = b.sub(n1, b.add(c1, n0))   # next[1] - (cur[1] + next[0])
     pairs = [(0, 0)] * (air.num_constraint_coefficients() // 2)
     (adj_t, members), = air.transition_groups(pairs[:2])
     assert [m[0] for m in members] == [0, 1]
@@ -135,15 +157,16 @@ def _fib2_program(air, to_abi_int):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("which", ["fib2", "mulfib2"])
 @pytest.mark.parametrize("form", ["canonical", "montgomery"])
 @pytest.mark.parametrize("logn", [3, 6, 10, 13])
-def test_fib2_constraints_evaluated_on_the_gpu(ctx, ctx_mont, logn, form):
+def test_fib2_constraints_evaluated_on_the_gpu(ctx, ctx_mont, logn, form, which):
     """SURVEY 8(f)3: ConstraintEvaluator::evaluate on the device (aero_constraints_evaluate_device) from the
     resident trace LDE equals the restated evaluator column for column, and aero_prove with the program
     (no callback, no LDE download) gives the same bytes as the oracle prover, OOD consistency check included."""
     from aero_b200 import make_divisor
 
-    n, trace, air, divs, pub = _setup(logn)
+    n, trace, air, divs, pub = _setup(logn, which)
     mont = form == "montgomery"
     c = ctx_mont if mont else ctx
     to_abi = so.canon_to_mont if mont else (lambda a: a)
@@ -190,3 +213,80 @@ def test_air_program_is_validated(ctx):
     with pytest.raises(AeroError):
         ctx.evaluate_constraints([seg], prog, [1, 2], 2, 1)
     seg.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_nodes,ce_blowup", [(40, 2), (600, 8), (1024, 4)])
+def test_random_transition_program_matches_a_python_evaluation(ctx, n_nodes, ce_blowup):
+    """The device evaluator on programs far larger than fib2's (the 1024-slot instantiation, two trace segments,
+    several degree adjustments and divisor columns, constraint evaluation domains of 2n..8n): every merged
+    evaluation equals a direct big-int evaluation of the same program over the oracle's LDE -- the formulas of
+    transition/mod.rs:272-283 and boundary.rs:255-275 applied verbatim."""
+    from aero_b200 import AirProgramBuilder
+
+    rng = np.random.default_rng(n_nodes)
+    logn, w_main, w_aux, blowup = 5, 5, 2, 8
+    n = 1 << logn
+    main, aux = so.synthetic_trace(w_main, n, 0xA1), so.synthetic_trace(w_aux, n, 0xA2)
+    segs = [ctx.build_trace_commitment(main, blowup), ctx.build_trace_commitment(aux, blowup)]
+    lde = [so.build_trace_commitment(main, blowup).lde, so.build_trace_commitment(aux, blowup).lde]
+    cols = [c for m in lde for c in m]                       # natural-order LDE columns, main then aux
+    W = w_main + w_aux
+    b = AirProgramBuilder()
+    kinds = []
+    for k in range(n_nodes):
+        r = rng.integers(0, 10) if k >= 4 else rng.integers(0, 3)
+        if r == 0:
+            b.cur(int(rng.integers(0, W)))
+        elif r == 1:
+            b.next(int(rng.integers(0, W)))
+        elif r == 2:
+            b.const(int(rng.integers(0, 2**63)) % P)
+        else:
+            a_, b_ = int(rng.integers(0, k)), int(rng.integers(0, k))
+            (b.add, b.sub, b.mul)[int(rng.integers(0, 3))](a_, b_)
+    n_t, n_b, n_div = 12, 5, 4
+    adjs = [int(x) for x in rng.integers(1, 4 * n, 3)]
+    for t in range(n_t):
+        b.transition(int(rng.integers(0, n_nodes)), adjs[t % 3])
+    for j in range(n_b):
+        b.assertion(int(rng.integers(0, W)), int(rng.integers(0, 2**63)) % P, adjs[j % 2], 1 + j % (n_div - 1))
+    prog, keep = b.finish()
+    coeffs = [int(x) % P for x in rng.integers(0, 2**63, 2 * (n_t + n_b), dtype=np.uint64)]
+    got = ctx.evaluate_constraints(segs, prog, coeffs, ce_blowup, n_div)
+    # direct evaluation
+    ce = n * ce_blowup
+    N = n * blowup
+    g_ce = so.root_of_unity(logn + ce_blowup.bit_length() - 1)
+    want = np.zeros((n_div, ce), np.uint64)
+    x = 7
+    for s in range(ce):
+        row = s * (blowup // ce_blowup)
+        cur = [int(c[row]) for c in cols]
+        nxt = [int(c[(row + blowup) % N]) for c in cols]
+        val = []
+        for op, a_, b_ in b.nodes:
+            if op == 0:
+                val.append(cur[a_])
+            elif op == 1:
+                val.append(nxt[a_])
+            elif op == 2:
+                val.append(b.consts[a_])
+            elif op == 3:
+                val.append((val[a_] + val[b_]) % P)
+            elif op == 4:
+                val.append((val[a_] - val[b_]) % P)
+            else:
+                val.append(val[a_] * val[b_] % P)
+        acc = [0] * n_div
+        for t in range(n_t):
+            acc[0] = (acc[0] + (coeffs[2 * t] + coeffs[2 * t + 1] * pow(x, b.t_adj[t], P)) * val[b.t_out[t]]) % P
+        for j, (col, value, adj, d) in enumerate(b.boundary):
+            cc = coeffs[2 * (n_t + j):2 * (n_t + j) + 2]
+            acc[d] = (acc[d] + (cc[0] + cc[1] * pow(x, adj, P)) * ((cur[col] - value) % P)) % P
+        for d in range(n_div):
+            want[d, s] = acc[d]
+        x = x * g_ce % P
+    assert np.array_equal(got, want)
+    for sg in segs:
+        sg.destroy()
