@@ -464,12 +464,6 @@ static aero_status window_check_result(aero_ctx *ctx, const unsigned int *word) 
     }
     return AERO_OK;
 }
-static aero_status window_check(aero_ctx *ctx) {
-    const unsigned int *word = nullptr;
-    TRY(window_check_queue(ctx, &word));
-    if (word) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    return window_check_result(ctx, word);
-}
 // device -> caller memory and the barrier check with ONE stream synchronisation
 static aero_status download_small_checked(aero_ctx *ctx, void *dst, const void *d_src, size_t bytes) {
     const unsigned int *word = nullptr;
