@@ -81,7 +81,18 @@ int aero_ctx_get_form(aero_ctx *ctx);
  *                     share a device or a process must not meet on the legacy default stream);
  *   "force_host_sync" 1: sharded proofs keep host-synchronised barriers even for warm shapes (tests);
  *   "push_parts"      1..4 (default 4): copy streams a rank's coefficient block is split over when it is sent
- *                     to a peer (one copy engine does not fill NVLink). */
+ *                     to a peer (one copy engine does not fill NVLink);
+ *   "ntt_outer_log"   -1 (default): transforms above 2^20 points split off a third factor 2^(logn-20) (three-pass
+ *                     plans); 0: two passes only; 1..4: force that factor wherever the
+ *                     transform has at least 2^(12+k) points (tests); read when a plan is first built;
+ *   "hash_early_batches" 0..16 (default 2): host-buffer commits of >= 32 columns hash this many upload
+ *                     batches right after their extension (chained row hash) so that the stream does not
+ *                     wait for later batches;
+ *   "fri_fused"       0 (default) / 1 / 2: fold a FRI layer and hash the next layer's leaves in one kernel --
+ *                     never / layers of <= 2^14 folded leaves / all layers (measured slower on B200).
+ * Environment hooks for experiments (read once): AERO_NTT_BULK=0 (LDGSTS instead of TMA tile loads),
+ * AERO_NTT_COLFAST=0 (tile-major pass-1 grid), AERO_NTT_OUTER, AERO_HASH_EARLY, AERO_FRI_FUSED (defaults of the
+ * options above), AERO_HOST_TIMING=1 (host-side section marks of aero_prove on stderr). */
 aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value);
 /* Used by the host driver layered above this ABI to report its own failures through aero_last_error. */
 void aero_ctx_set_error(aero_ctx *ctx, const char *msg);

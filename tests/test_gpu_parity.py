@@ -601,3 +601,22 @@ def test_device_columns_of_any_alignment(ctx, oracle, offset_words, stride_pad):
         seg.destroy()
     finally:
         ctx.device_free(d)
+
+
+@pytest.mark.parametrize("early", [0, 1, 2, 5])
+@pytest.mark.parametrize("logn,width", [(10, 33), (10, 40), (11, 81), (10, 32)])
+def test_segment_commit_early_hashed_batches(oracle, logn, width, early):
+    """Host-buffer commits of wide segments hash the first upload batches right after their extension
+    (hash_early_batches; chained row hash on the same stream) and the rest at the end: any number of early
+    batches, odd and even widths -- leaf digests and root equal the oracle's."""
+    c = aero_b200.Context(0, form=aero_b200.AERO_FORM_CANONICAL)
+    try:
+        c.set_option("hash_early_batches", early)
+        n = 1 << logn
+        trace = oracle.synthetic_trace(width, n, 0x0E100000 + width)
+        ref = oracle.build_trace_commitment(trace, 8)
+        seg = c.build_trace_commitment(trace, 8)
+        assert np.array_equal(seg.download_leaves(), ref.leaves), "row hashes mismatch"
+        assert seg.root == ref.root
+    finally:
+        c.close()
