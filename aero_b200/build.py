@@ -7,7 +7,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["csrc/abi.cu", "csrc/ntt.cu", "csrc/hash.cu", "csrc/poly.cu", "csrc/fri.cu", "csrc/peak.cu", "host/prover.cpp"]
-HEADERS = ["csrc/gl.cuh", "csrc/blake2s.cuh", "csrc/kernels.cuh", "csrc/ntt.cuh", "host/prover.hpp",
+HEADERS = ["csrc/gl.cuh", "csrc/blake2s.cuh", "csrc/kernels.cuh", "csrc/ntt.cuh", "host/prover.hpp", "host/copy_pool.hpp",
            "../include/aero_b200.h", "../include/aero_prover.h"]
 LIB = os.path.join(_HERE, "libaero_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

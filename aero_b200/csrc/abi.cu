@@ -5,15 +5,18 @@
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/aero_b200.h"
+#include "../host/copy_pool.hpp"
 #include "kernels.cuh"
 #include "ntt.cuh"
 
@@ -313,21 +316,25 @@ static aero_status upload_small(aero_ctx *ctx, void *d_dst, const void *src, siz
     return AERO_OK;
 }
 
-// host copy split over a few threads: one thread moves ~10 GB/s, PCIe 5 x16 ~55 GB/s
+// Host copy split over a few threads: one thread moves ~10 GB/s, PCIe 5 x16 ~55 GB/s.  The workers are a
+// process-wide pool created on first use (spawning threads per copy cost ~0.1 ms per 8 MB column, a third of
+// the copy itself); the calling thread takes chunks too.  The pool is never destroyed -- its threads sleep
+// on a condition variable and go away with the process -- so nothing runs in a static destructor.
 static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t nt = bytes < ((size_t)4 << 20) ? 1 : std::min<size_t>(std::min<unsigned>(8, hw), bytes >> 21);
-    if (nt <= 1) {
+    if (bytes < ((size_t)2 << 20)) {
         memcpy(dst, src, bytes);
         return;
     }
-    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
-    std::vector<std::thread> th;
-    for (size_t t = 0; t < nt; t++) {
-        const size_t a = std::min(bytes, per * t), b = t + 1 == nt ? bytes : std::min(bytes, per * (t + 1));
-        if (b > a) th.emplace_back([=] { memcpy((uint8_t *)dst + a, (const uint8_t *)src + a, b - a); });
-    }
-    for (auto &t : th) t.join();
+    static aero::host::CopyPool *pool = [] {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        return new aero::host::CopyPool(std::min(7u, hw > 1 ? hw - 1 : 0u));  // + the calling thread
+    }();
+    const size_t chunk = (size_t)1 << 20;  // 1 MiB pieces, handed out dynamically
+    std::vector<aero::host::CopyPool::Chunk> chunks;
+    chunks.reserve(bytes / chunk + 1);
+    for (size_t a = 0; a < bytes; a += chunk)
+        chunks.push_back({(uint8_t *)dst + a, (const uint8_t *)src + a, std::min(chunk, bytes - a)});
+    pool->run(std::move(chunks));
 }
 // is this host pointer page-locked (cudaMallocHost / cudaHostRegister)?  Async copies from or to pageable
 // memory are staged by the driver and block the caller.

@@ -473,8 +473,8 @@ def run_aero(args) -> None:
                         "ms_per_step": ms_e2e, "host_buffers": "pinned"},
                 "e2e_pageable": {"value": nproofs * n / (ms_pg * 1e-3), "unit": "rows/s", "ms_per_step": ms_pg,
                                  "note": "same call with pageable (unpinned) host columns -- what a Rust Vec<Vec<Felt>> is: the "
-                                         "library stages each column batch through two pinned slots, the host copy split over "
-                                         "threads and running under the transfer and the NTTs of the previous batch"},
+                                         "library stages each column through two pinned slots, the host copy split over a "
+                                         "persistent pool of worker threads and running under the transfer of the previous column"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "phase_ms_per_step": phases,
                 "proof_bytes": len(proof)}

@@ -196,3 +196,23 @@ def test_air_program_builder_marshals_the_c_struct():
     m = re.search(r"enum \{ AERO_AIR_CUR = (\d), AERO_AIR_NEXT = (\d), AERO_AIR_CONST = (\d), AERO_AIR_ADD = (\d), AERO_AIR_SUB = (\d), AERO_AIR_MUL = (\d) \}", hdr)
     assert m and [int(x) for x in m.groups()] == [_lib.AERO_AIR_CUR, _lib.AERO_AIR_NEXT, _lib.AERO_AIR_CONST,
                                                   _lib.AERO_AIR_ADD, _lib.AERO_AIR_SUB, _lib.AERO_AIR_MUL]
+
+
+def test_copy_pool_stress(tmp_path):
+    """aero_b200/host/copy_pool.hpp (the worker pool behind the pageable-column staging): many batches of
+    different chunk sizes and four concurrent callers copy exactly, compiled with g++ and run here."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "copy_pool_stress")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-pthread", "-I", os.path.join(root, "aero_b200", "host"),
+                           os.path.join(root, "tests", "cpp", "copy_pool_stress.cpp"), "-o", exe], env=env)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "copy pool ok" in r.stdout, r.stdout + r.stderr
