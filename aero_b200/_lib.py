@@ -55,10 +55,11 @@ class AirProgram(ctypes.Structure):
     _fields_ = [("nodes", POINTER(AirNode)), ("n_nodes", c_uint32), ("consts", POINTER(c_uint64)), ("n_consts", c_uint32),
                 ("n_transition", c_uint32), ("transition_out", POINTER(c_uint32)), ("transition_adj", POINTER(c_uint64)),
                 ("n_boundary", c_uint32), ("boundary_col", POINTER(c_uint32)), ("boundary_value", POINTER(c_uint64)),
-                ("boundary_adj", POINTER(c_uint64)), ("boundary_div", POINTER(c_uint32))]
+                ("boundary_adj", POINTER(c_uint64)), ("boundary_div", POINTER(c_uint32)),
+                ("n_periodic", c_uint32), ("periodic_len", POINTER(c_uint32)), ("periodic_values", POINTER(c_uint64))]
 
 
-AERO_AIR_CUR, AERO_AIR_NEXT, AERO_AIR_CONST, AERO_AIR_ADD, AERO_AIR_SUB, AERO_AIR_MUL = range(6)
+AERO_AIR_CUR, AERO_AIR_NEXT, AERO_AIR_CONST, AERO_AIR_ADD, AERO_AIR_SUB, AERO_AIR_MUL, AERO_AIR_PERIODIC = range(7)
 
 AUX_BUILDER = ctypes.CFUNCTYPE(c_int, c_void_p, p_u64, c_uint32, pp_u64)
 CONSTRAINT_EVALUATOR = ctypes.CFUNCTYPE(c_int, c_void_p, pp_u64, c_uint32, c_uint64, p_u64, c_uint32, pp_u64)
@@ -125,6 +126,7 @@ PROTOTYPES = {
                                                  c_uint32, c_uint32, c_void_p, c_size_t]),
     "aero_constraints_evaluate_into_poly": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, POINTER(AirProgram), p_u64,
                                                     c_uint32, c_uint32, POINTER(Divisor), c_uint32, POINTER(c_void_p)]),
+    "aero_periodic_column_table": (c_int, [p_u64, c_uint64, c_uint64, c_uint32, p_u64]),
     "aero_segment_commit_polys": (c_int, [c_void_p, c_uint32, p_u8]),
     # OOD + DEEP
     "aero_ood_eval": (c_int, [c_void_p, POINTER(c_void_p), c_uint32, c_void_p, c_uint64, p_u64, p_u64]),

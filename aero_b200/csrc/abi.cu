@@ -2166,6 +2166,60 @@ aero_status aero_commit_rows_device(aero_ctx *ctx, const uint64_t *d_m, size_t c
 
 // ---- constraints ----------------------------------------------------------------------------
 // ---- AIR constraint evaluation on the device ---------------------------------------------------
+// Host-side radix-2 transform of a small vector in place (canonical elements): out[j] = sum_k a[k] w^(jk).
+static void host_ntt(std::vector<uint64_t> &a, uint64_t w) {
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; i++) {  // bit reversal
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const uint64_t wl = gl::pow(w, n / len);
+        for (size_t i = 0; i < n; i += len) {
+            uint64_t t = 1;
+            for (size_t k = 0; k < len / 2; k++) {
+                const uint64_t u = a[i + k], v = gl::mul(a[i + k + len / 2], t);
+                a[i + k] = gl::add(u, v);
+                a[i + k + len / 2] = gl::sub(u, v);
+                t = gl::mul(t, wl);
+            }
+        }
+    }
+}
+// One column of PeriodicValueTable (prover/src/constraints/periodic_table.rs:41-56): the cycle values are
+// interpolated over the subgroup of order c (Air::get_periodic_column_polys, air/src/air/mod.rs:336-341) and the
+// polynomial is evaluated over offset^num_cycles * <w_(c * ce_blowup)> in natural order
+// (fft::evaluate_poly_with_offset); appended to `table`.
+static void periodic_column_table(std::vector<uint64_t> col /* c values */, uint64_t num_cycles, uint32_t ce_blowup,
+                                  std::vector<uint64_t> &table) {
+    const size_t c = col.size();
+    const int logc = ilog2(c);
+    host_ntt(col, gl::inv(gl::root_of_unity(logc)));
+    const uint64_t cinv = gl::inv((uint64_t)c), offset = gl::pow(gl::GENERATOR, num_cycles);
+    std::vector<uint64_t> ext(c * ce_blowup, 0);
+    uint64_t s = cinv;  // coefficient j scaled by offset^j / c
+    for (size_t j = 0; j < c; j++) {
+        ext[j] = gl::mul(col[j], s);
+        s = gl::mul(s, offset);
+    }
+    host_ntt(ext, gl::root_of_unity(logc + ilog2(ce_blowup)));
+    table.insert(table.end(), ext.begin(), ext.end());
+}
+aero_status aero_periodic_column_table(const uint64_t *cycle_values, uint64_t cycle_len, uint64_t trace_len,
+                                       uint32_t ce_blowup, uint64_t *out) {
+    if (!cycle_values || !out) return AERO_ERR_INVALID;
+    if (cycle_len < 2 || !is_pow2(cycle_len) || !is_pow2(trace_len) || cycle_len > trace_len) return AERO_ERR_INVALID;
+    if (!is_pow2(ce_blowup) || ilog2(cycle_len) + ilog2(ce_blowup) > 32) return AERO_ERR_INVALID;
+    std::vector<uint64_t> col(cycle_values, cycle_values + cycle_len), table;
+    for (uint64_t v : col)
+        if (v >= gl::P) return AERO_ERR_INVALID;
+    periodic_column_table(col, trace_len / cycle_len, ce_blowup, table);
+    std::copy(table.begin(), table.end(), out);
+    return AERO_OK;
+}
+
 aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs,
                                              const aero_air_program *prog, const uint64_t *coeffs, uint32_t n_coeffs,
                                              uint32_t ce_blowup, uint32_t n_div, uint64_t *d_eval_cols, size_t col_stride) {
@@ -2179,7 +2233,7 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
     if (n_coeffs != 2 * (prog->n_transition + prog->n_boundary)) CTX_FAIL(ctx, AERO_ERR_INVALID, "expected a coefficient pair per constraint (%u), got %u elements", prog->n_transition + prog->n_boundary, n_coeffs);
     if ((prog->n_transition && (!prog->transition_out || !prog->transition_adj)) ||
         (prog->n_boundary && (!prog->boundary_col || !prog->boundary_value || !prog->boundary_adj || !prog->boundary_div)) ||
-        (prog->n_consts && !prog->consts))
+        (prog->n_consts && !prog->consts) || (prog->n_periodic && (!prog->periodic_len || !prog->periodic_values)))
         CTX_FAIL(ctx, AERO_ERR_INVALID, "null program array");
     AirSegs segs{};
     segs.nseg = (int)n_trace_segs;
@@ -2206,10 +2260,30 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
         switch (nd.op) {
         case AERO_AIR_CUR: case AERO_AIR_NEXT: ok = nd.a < width; break;
         case AERO_AIR_CONST: ok = nd.a < prog->n_consts; break;
+        case AERO_AIR_PERIODIC: ok = nd.a < prog->n_periodic; break;
         case AERO_AIR_ADD: case AERO_AIR_SUB: case AERO_AIR_MUL: ok = nd.a < k && nd.b < k; break;
         default: ok = false;
         }
         if (!ok) CTX_FAIL(ctx, AERO_ERR_INVALID, "transition program: bad node %u (op %u, operands %u, %u)", k, nd.op, nd.a, nd.b);
+    }
+    auto is_arith = [](uint32_t op) { return op >= AERO_AIR_ADD && op <= AERO_AIR_MUL; };
+    // PeriodicValueTable::new (periodic_table.rs:25-75), one column after another
+    std::vector<uint64_t> periodic;
+    std::vector<uint32_t> per_off(prog->n_periodic), per_mask(prog->n_periodic);
+    {
+        size_t src = 0;
+        for (uint32_t k = 0; k < prog->n_periodic; k++) {
+            const uint64_t c = prog->periodic_len[k];
+            // Air::get_periodic_column_polys' assertions (air/src/air/mod.rs:319-335)
+            if (c < 2 || !is_pow2(c) || c > ((uint64_t)1 << logn)) CTX_FAIL(ctx, AERO_ERR_INVALID, "periodic column %u: cycle length %llu is not a power of two in 2..trace length", k, (unsigned long long)c);
+            std::vector<uint64_t> col(c);
+            for (uint64_t i = 0; i < c; i++) col[i] = to_canon(ctx, prog->periodic_values[src + i]);
+            src += c;
+            per_off[k] = (uint32_t)periodic.size();
+            per_mask[k] = (uint32_t)(c * ce_blowup - 1);
+            periodic_column_table(col, ((uint64_t)1 << logn) / c, ce_blowup, periodic);
+        }
+        if (periodic.size() > ((size_t)1 << 30)) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "periodic value table too large");
     }
     std::vector<uint64_t> adj;  // distinct degree adjustments
     auto adj_index = [&](uint64_t a) {
@@ -2232,8 +2306,10 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
     }
     if (adj.size() > 8) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "more than 8 distinct degree adjustments");
     std::vector<uint64_t> w64;
-    const size_t o_consts = 0, o_bval = o_consts + prog->n_consts, o_coeffs = o_bval + nb, o_adj = o_coeffs + n_coeffs;
-    w64.resize(o_adj + adj.size());
+    const size_t o_consts = 0, o_bval = o_consts + prog->n_consts, o_coeffs = o_bval + nb, o_adj = o_coeffs + n_coeffs,
+                 o_per = o_adj + adj.size();
+    w64.resize(o_per + periodic.size());
+    std::copy(periodic.begin(), periodic.end(), w64.begin() + o_per);
     for (uint32_t i = 0; i < prog->n_consts; i++) w64[o_consts + i] = to_canon(ctx, prog->consts[i]);
     for (uint32_t j = 0; j < nb; j++) w64[o_bval + j] = to_canon(ctx, prog->boundary_value[j]);
     for (uint32_t i = 0; i < n_coeffs; i++) w64[o_coeffs + i] = to_canon(ctx, coeffs[i]);
@@ -2244,7 +2320,7 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
     std::vector<uint32_t> last(NN, 0), slot(NN, 0);
     std::vector<bool> used(NN, false);
     for (uint32_t k = 0; k < NN; k++)
-        if (prog->nodes[k].op >= AERO_AIR_ADD) {
+        if (is_arith(prog->nodes[k].op)) {
             last[prog->nodes[k].a] = k;
             last[prog->nodes[k].b] = k;
             used[prog->nodes[k].a] = used[prog->nodes[k].b] = true;
@@ -2257,7 +2333,7 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
     uint32_t n_slots = 0;
     for (uint32_t k = 0; k < NN; k++) {
         const aero_air_node &nd = prog->nodes[k];
-        if (nd.op >= AERO_AIR_ADD) {
+        if (is_arith(nd.op)) {
             if (last[nd.a] == k) free_slots.push_back(slot[nd.a]);
             if (nd.b != nd.a && last[nd.b] == k) free_slots.push_back(slot[nd.b]);
         }
@@ -2274,10 +2350,10 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
     w32.resize(o_bdiv + nb);
     for (uint32_t k = 0; k < NN; k++) {
         const aero_air_node &nd = prog->nodes[k];
-        const bool arith = nd.op >= AERO_AIR_ADD;
+        const bool arith = is_arith(nd.op), per = nd.op == AERO_AIR_PERIODIC;
         w32[o_nodes + 4 * k] = nd.op;
-        w32[o_nodes + 4 * k + 1] = arith ? slot[nd.a] : nd.a;
-        w32[o_nodes + 4 * k + 2] = arith ? slot[nd.b] : 0;
+        w32[o_nodes + 4 * k + 1] = arith ? slot[nd.a] : per ? per_off[nd.a] : nd.a;
+        w32[o_nodes + 4 * k + 2] = arith ? slot[nd.b] : per ? per_mask[nd.a] : 0;
         w32[o_nodes + 4 * k + 3] = slot[k];
     }
     for (uint32_t t = 0; t < nt; t++) {
@@ -2308,6 +2384,7 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
     p.b_val = d64 + o_bval;
     p.coeffs = d64 + o_coeffs;
     p.adj = d64 + o_adj;
+    p.periodic = d64 + o_per;
     p.n_nodes = (int)prog->n_nodes;
     p.n_slots = (int)std::max<uint32_t>(1, n_slots);
     p.nt = (int)nt;

@@ -207,8 +207,10 @@ struct AirSegs {  // trace segments in order: column c of segment s at lde[s] + 
 };
 struct AirProgramDev {       // device copies; field elements canonical
     const uint32_t *nodes;   // 4 words per node (16-byte aligned): op, a, b, destination slot; operands of
-                             //   add / sub / mul and t_out are SLOTS (assigned by liveness on the host)
+                             //   add / sub / mul and t_out are SLOTS (assigned by liveness on the host); a
+                             //   periodic node carries its column's offset into `periodic` and length - 1
     const uint64_t *consts;
+    const uint64_t *periodic;  // PeriodicValueTable, column after column: cycle * ce_blowup values each
     const uint32_t *t_out, *t_adj;           // per transition constraint: node, index into adj
     const uint32_t *b_col, *b_adj, *b_div;   // per boundary constraint
     const uint64_t *b_val;

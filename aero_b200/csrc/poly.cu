@@ -774,6 +774,7 @@ __global__ void __launch_bounds__(128) air_evaluate_kernel(AirSegs segs, AirProg
         case 0: v = load(nd.y, cur); break;
         case 1: v = load(nd.y, nxt); break;
         case 2: v = __ldg(p.consts + nd.y); break;
+        case 6: v = __ldg(p.periodic + nd.y + (step & nd.z)); break;  // periodic_table.rs:84-90 (get_row: step % length)
         case 3: v = gl::add(val[nd.y], val[nd.z]); break;
         case 4: v = gl::sub(val[nd.y], val[nd.z]); break;
         default: v = gl::mul(val[nd.y], val[nd.z]); break;

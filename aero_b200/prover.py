@@ -49,7 +49,7 @@ def make_divisor(a: int, b: int, exemptions: Sequence[int] = ()) -> Divisor:
 
 class AirProgramBuilder:
     """Records an AIR's transition constraints as an aero_air_program (include/aero_b200.h): build the
-    expression DAG with cur()/next()/const()/add()/sub()/mul(), declare each constraint's output node with
+    expression DAG with cur()/next()/const()/periodic()/add()/sub()/mul(), declare each constraint's output node with
     its group's degree adjustment, add the single-value assertions, then ``finish()``.  All field values in
     ABI form (the context's form).  This is what a Rust caller does once per AIR by running
     Air::evaluate_transition over a symbolic element type."""
@@ -60,6 +60,7 @@ class AirProgramBuilder:
         self.t_out: List[int] = []
         self.t_adj: List[int] = []
         self.boundary: List[Tuple[int, int, int, int]] = []  # column, value, degree adjustment, divisor column
+        self.periodic_cols: List[List[int]] = []             # Air::get_periodic_column_values
 
     def _node(self, op: int, a: int, b: int = 0) -> int:
         self.nodes.append((op, a, b))
@@ -74,6 +75,14 @@ class AirProgramBuilder:
     def const(self, value: int) -> int:
         self.consts.append(int(value))
         return self._node(_lib.AERO_AIR_CONST, len(self.consts) - 1)
+
+    def periodic_column(self, values) -> int:
+        """Registers a periodic column by its cycle values (ABI form); -> its index for periodic()."""
+        self.periodic_cols.append([int(v) for v in values])
+        return len(self.periodic_cols) - 1
+
+    def periodic(self, col: int) -> int:
+        return self._node(_lib.AERO_AIR_PERIODIC, col)
 
     def add(self, a: int, b: int) -> int:
         return self._node(_lib.AERO_AIR_ADD, a, b)
@@ -108,7 +117,23 @@ class AirProgramBuilder:
         p.consts, p.n_consts = consts, len(self.consts)
         p.n_transition, p.transition_out, p.transition_adj = len(self.t_out), t_out, t_adj
         p.n_boundary, p.boundary_col, p.boundary_value, p.boundary_adj, p.boundary_div = nb, b_col, b_val, b_adj, b_div
-        return p, [nodes, consts, t_out, t_adj, b_col, b_val, b_adj, b_div]
+        flat = [v for col in self.periodic_cols for v in col]
+        per_len = (u32 * max(1, len(self.periodic_cols)))(*[len(col) for col in self.periodic_cols])
+        per_val = (u64 * max(1, len(flat)))(*flat)
+        p.n_periodic, p.periodic_len, p.periodic_values = len(self.periodic_cols), per_len, per_val
+        return p, [nodes, consts, t_out, t_adj, b_col, b_val, b_adj, b_div, per_len, per_val]
+
+
+def periodic_column_table(cycle_values: Sequence[int], trace_len: int, ce_blowup: int) -> np.ndarray:
+    """aero_periodic_column_table: one column of the prover's PeriodicValueTable (canonical values; host
+    arithmetic of the library, no GPU involved)."""
+    vals = np.ascontiguousarray(np.array([int(v) for v in cycle_values], np.uint64))
+    out = np.empty(len(vals) * ce_blowup, np.uint64)
+    st = _lib.load().aero_periodic_column_table(vals.ctypes.data_as(p_u64), len(vals), trace_len, ce_blowup,
+                                                out.ctypes.data_as(p_u64))
+    if st != 0:
+        raise AeroError(st, "aero_periodic_column_table")
+    return out
 
 
 def _cols(m: np.ndarray):

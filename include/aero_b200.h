@@ -208,6 +208,9 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
  *                                  current / next row of the frame (EvaluationFrame, air/src/air/mod.rs)
  *   AERO_AIR_CONST                a = index into consts (ABI form: public inputs, periodic-free constants,
  *                                  the auxiliary segment's random elements)
+ *   AERO_AIR_PERIODIC             a = periodic column (Air::get_periodic_column_values,
+ *                                  air/src/air/mod.rs:246-248): the value periodic_values[a] of
+ *                                  Air::evaluate_transition at this step
  *   AERO_AIR_ADD / SUB / MUL      a, b = operand nodes
  * A Rust caller records it once per AIR by running Air::evaluate_transition over a symbolic element type.
  * transition_out[i] = node holding constraint i, transition_adj[i] = its group's degree adjustment
@@ -216,12 +219,21 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
  * into evaluation column boundary_div[j] >= 1 (column 0 is the transition divisor's, evaluator.rs:66-67).
  * coeffs: the drawn composition coefficients in ABI form, a pair per transition constraint, then a pair
  * per boundary constraint in the order given (Air::get_constraint_composition_coefficients,
- * air/src/air/mod.rs:511-533).  Periodic columns and sequence assertions are not covered.
+ * air/src/air/mod.rs:511-533).
+ * Periodic columns are handed over as their cycle values (column k: periodic_len[k] values, a power of two
+ * in 2..trace_len, concatenated in periodic_values, ABI form); the library builds PeriodicValueTable
+ * (prover/src/constraints/periodic_table.rs:25-90): each column interpolated over its cycle
+ * (Air::get_periodic_column_polys, air/src/air/mod.rs:310-344) and evaluated over the coset
+ * offset^(trace_len / cycle) * <w_(cycle * ce_blowup)>, looked up by step modulo cycle * ce_blowup.  The degree
+ * adjustments the caller passes already reflect the cycles (TransitionConstraintDegree::with_cycles).
+ * Sequence and periodic ASSERTIONS are not covered (Miden's ProcessorAir makes single-value assertions only,
+ * miden/air/src/lib.rs:124-160).
  * Output: n_div columns of trace_len * ce_blowup merged evaluations in natural order of the constraint
  * evaluation domain (ABI form, column d at d_eval_cols + d * col_stride): the input of
  * aero_constraints_into_poly_device.  At most 65536 nodes of which at most 1024 values alive at once (slots
  * are assigned by liveness), 8 distinct degree adjustments. */
-enum { AERO_AIR_CUR = 0, AERO_AIR_NEXT = 1, AERO_AIR_CONST = 2, AERO_AIR_ADD = 3, AERO_AIR_SUB = 4, AERO_AIR_MUL = 5 };
+enum { AERO_AIR_CUR = 0, AERO_AIR_NEXT = 1, AERO_AIR_CONST = 2, AERO_AIR_ADD = 3, AERO_AIR_SUB = 4, AERO_AIR_MUL = 5,
+       AERO_AIR_PERIODIC = 6 };
 typedef struct aero_air_node {
     uint32_t op, a, b;
 } aero_air_node;
@@ -238,6 +250,9 @@ typedef struct aero_air_program {
     const uint64_t *boundary_value;
     const uint64_t *boundary_adj;
     const uint32_t *boundary_div;
+    uint32_t n_periodic;             /* 0 = none (the three fields below may then be 0 / NULL) */
+    const uint32_t *periodic_len;    /* cycle length of each periodic column */
+    const uint64_t *periodic_values; /* sum(periodic_len) values, column after column */
 } aero_air_program;
 aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs,
                                              const aero_air_program *program, const uint64_t *coeffs, uint32_t n_coeffs,
@@ -248,6 +263,13 @@ aero_status aero_constraints_evaluate_into_poly(aero_ctx *ctx, aero_segment *con
                                                 const aero_air_program *program, const uint64_t *coeffs, uint32_t n_coeffs,
                                                 uint32_t ce_blowup, const aero_divisor *divs, uint32_t n_div,
                                                 aero_segment **composition_polys);
+/* One column of PeriodicValueTable::new (prover/src/constraints/periodic_table.rs:25-75) as the evaluator above
+ * builds it: cycle_len CANONICAL values in, cycle_len * ce_blowup canonical values out (the column polynomial of
+ * Air::get_periodic_column_polys over offset^(trace_len / cycle_len) * <w_(cycle_len * ce_blowup)>; the value
+ * at constraint-evaluation step s is out[s % (cycle_len * ce_blowup)]).  Host arithmetic only: needs no context
+ * and no GPU. */
+aero_status aero_periodic_column_table(const uint64_t *cycle_values, uint64_t cycle_len, uint64_t trace_len,
+                                       uint32_t ce_blowup, uint64_t *out);
 
 /* Extends + commits a coefficient-only segment: CompositionPoly::evaluate + commit_to_rows
  * (prover/src/lib.rs:599-632). */

@@ -19,7 +19,14 @@ Restated, each with the file:line it follows (paths relative to winterfell/):
     255-275, domain.rs:99-117): one column per divisor over the constraint evaluation domain;
   * the verifier's evaluate_constraints (verifier/src/evaluator.rs:14-107) and the comparison in
     verifier/src/lib.rs:248-290.
-Only what these two use is covered: main segment only, single-value assertions, no periodic columns.
+  * periodic columns: Air::get_periodic_column_polys (air/src/air/mod.rs:310-344), the prover's
+    PeriodicValueTable (prover/src/constraints/periodic_table.rs:25-90), the verifier's evaluation of the
+    column polynomials at x^(n / cycle) (verifier/src/evaluator.rs:27-36) and
+    TransitionConstraintDegree::with_cycles (air/src/air/transition/degree.rs:57-131) -- what Miden's
+    ProcessorAir needs beyond the Fibonacci examples (miden/air/src/lib.rs:117-120: hasher and bitwise
+    chiplet columns); exercised by MaskedChainAir, built like examples/src/rescue/air.rs:60-116 (a cycle
+    mask switching between a round function with periodic round constants and a plain step).
+Only what these use is covered: main segment only, single-value assertions.
 Pure Python big-int arithmetic: small traces only."""
 from __future__ import annotations
 
@@ -75,16 +82,20 @@ class SimpleAir:
     subclasses supply trace_width, transition_degrees, build_trace, evaluate_transition, get_assertions."""
 
     trace_width = 0
-    transition_degrees: List[int] = []
+    # TransitionConstraintDegree::new(d) as the int d, ::with_cycles(d, cycles) as the pair (d, [cycles])
+    transition_degrees: list = []
+    periodic_columns: List[List[int]] = []  # Air::get_periodic_column_values (air/src/air/mod.rs:246-248)
     num_transition_exemptions = 1  # context.rs:159
 
     def __init__(self, trace_length: int, result: int, blowup: int = 8):
         self.n, self.result, self.blowup = trace_length, result, blowup
         # context.rs:124-137 with degree.rs:113-131: max over constraints of
         # max(next_power_of_two(base + cycles - 1), MIN_BLOWUP_FACTOR = 2)
-        self.ce_blowup = max(max(_next_pow2(d - 1), 2) for d in self.transition_degrees)
+        self.ce_blowup = max(max(_next_pow2(b + len(cyc) - 1), 2) for b, cyc in map(_degree, self.transition_degrees))
         assert blowup >= self.ce_blowup
         self.g = root_of_unity(log2(trace_length))
+        for col in self.periodic_columns:  # air/src/air/mod.rs:319-335
+            assert len(col) >= 2 and len(col) & (len(col) - 1) == 0 and len(col) <= trace_length
 
     # context.rs:183-193
     def ce_domain_size(self) -> int:
@@ -96,8 +107,37 @@ class SimpleAir:
     def trace_poly_degree(self) -> int:
         return self.n - 1
 
-    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int]) -> List[int]:
+    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int], periodic: Sequence[int] = ()) -> List[int]:
         raise NotImplementedError
+
+    # ---- periodic columns ---------------------------------------------------------------------
+    def periodic_column_polys(self) -> List[List[int]]:
+        """Air::get_periodic_column_polys (air/src/air/mod.rs:310-344): each column's values interpolated
+        over the subgroup of order cycle_length (fft::interpolate_poly: natural-order values in,
+        coefficients out)."""
+        polys = []
+        for col in self.periodic_columns:
+            c = len(col)
+            w_inv, c_inv = inv(root_of_unity(log2(c))), inv(c)
+            polys.append([sum(int(v) * pow(w_inv, j * k, P) for k, v in enumerate(col)) % P * c_inv % P for j in range(c)])
+        return polys
+
+    def periodic_value_table(self) -> List[List[int]]:
+        """PeriodicValueTable::new (prover/src/constraints/periodic_table.rs:25-75): every column
+        polynomial evaluated over the coset offset^(n / cycle) * <w_(cycle * ce_blowup)>
+        (fft::evaluate_poly_with_offset, natural order); column k of the table's row for step s is
+        table[k][s % len(table[k])] (get_row, :84-90, with the per-column wrap of :66)."""
+        table = []
+        for poly in self.periodic_column_polys():
+            c = len(poly)
+            offset = pow(GENERATOR, self.n // c, P)
+            w = root_of_unity(log2(c * self.ce_blowup))
+            table.append([_eval_poly(poly, offset * pow(w, i, P) % P) for i in range(c * self.ce_blowup)])
+        return table
+
+    def periodic_values_at(self, x: int) -> List[int]:
+        """verifier/src/evaluator.rs:27-36: poly(x^(n / cycle))."""
+        return [_eval_poly(poly, pow(x, self.n // len(poly), P)) for poly in self.periodic_column_polys()]
 
     def get_assertions(self) -> List[Assertion]:
         raise NotImplementedError
@@ -118,7 +158,8 @@ class SimpleAir:
         div_deg = self.transition_divisor().degree()
         groups: Dict[int, Tuple[int, list]] = {}
         for i, d in enumerate(self.transition_degrees):
-            ev_deg = d * (self.n - 1)  # degree.rs:102-108 without cycles
+            base, cycles = _degree(d)
+            ev_deg = base * (self.n - 1) + sum((self.n // c) * (c - 1) for c in cycles)  # degree.rs:102-108
             if ev_deg not in groups:
                 target = self.composition_degree() + div_deg  # transition/mod.rs:224-226
                 groups[ev_deg] = (target - ev_deg, [])
@@ -167,12 +208,13 @@ class SimpleAir:
         lde_shift = log2(self.blowup // self.ce_blowup)
         g_ce = root_of_unity(log2(ce))
         out = np.zeros((1 + len(bg), ce), np.uint64)
+        periodic = self.periodic_value_table()  # evaluator.rs:104-105
         x = GENERATOR  # domain.rs:99-101: ce_domain[step] * offset
         for step in range(ce):
             row = step << lde_shift
             cur = [int(c[row]) for c in trace_lde]
             nxt = [int(c[(row + self.blowup) % N]) for c in trace_lde]  # trace_lde.rs: next = + blowup, wrapping
-            t = self.evaluate_transition(cur, nxt)
+            t = self.evaluate_transition(cur, nxt, [col[step % len(col)] for col in periodic])  # evaluator.rs:183-186
             acc = 0
             for adj, members in tg:
                 xp = pow(x, adj, P)  # domain.rs:109-117: ce_domain[step*power mod ce] * offset^power = x^power
@@ -192,7 +234,7 @@ class SimpleAir:
     def evaluate_constraints_at(self, coeffs: Sequence[int], ood_cur: Sequence[int], ood_next: Sequence[int], z: int) -> int:
         """verifier/src/evaluator.rs:14-107."""
         t_cc, b_cc = self.split_coefficients(coeffs, len(self.transition_degrees))
-        t = self.evaluate_transition(ood_cur, ood_next)
+        t = self.evaluate_transition(ood_cur, ood_next, self.periodic_values_at(z))
         result = 0
         for adj, members in self.transition_groups(t_cc):  # transition/mod.rs:165-185
             xp = pow(z, adj, P)
@@ -224,7 +266,7 @@ class Fib2Air(SimpleAir):
             s1 = (s1 + s0) % P
         return cols
 
-    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int]) -> List[int]:  # air.rs:41-58
+    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int], periodic: Sequence[int] = ()) -> List[int]:  # air.rs:41-58
         return [(nxt[0] - (cur[0] + cur[1])) % P, (nxt[1] - (cur[1] + nxt[0])) % P]
 
     def get_assertions(self) -> List[Assertion]:  # air.rs:60-70
@@ -249,11 +291,70 @@ class MulFib2Air(SimpleAir):
             s1 = s1 * s0 % P
         return cols
 
-    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int]) -> List[int]:  # air.rs:47-63
+    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int], periodic: Sequence[int] = ()) -> List[int]:  # air.rs:47-63
         return [(nxt[0] - cur[0] * cur[1]) % P, (nxt[1] - cur[1] * nxt[0]) % P]
 
     def get_assertions(self) -> List[Assertion]:  # air.rs:65-75: starts with 1, 2; register 0 ends with the result
         return [Assertion(0, 0, 1), Assertion(1, 0, 2), Assertion(0, self.n - 1, self.result)]
+
+
+class MaskedChainAir(SimpleAir):
+    """An AIR with periodic columns, shaped like the reference's Rescue hash-chain example
+    (examples/src/rescue/air.rs:60-116, prover.rs:30-58): a periodic CYCLE MASK selects, row by row, between a
+    round function that adds periodic ROUND CONSTANTS to a non-linear map of the state and a plain step that
+    carries the state over.  Three registers: on rows where mask = 1
+        s0' = s0^3 + s1 + ark0,   s1' = s0 * s1 + ark1      (the cube is Rescue's S-box, rescue.rs:121-135)
+    and on the last row of every 4-row cycle (mask = 0) the two registers are swapped; s2 counts rows
+    (enforced through a periodic multiplier that is nowhere zero, so its constraint has a periodic degree
+    component but a different evaluation degree than the first two: three transition groups in all).  Cycle lengths 4
+    and 8, so the table lookups wrap at different periods."""
+
+    trace_width = 3
+    CYCLE_MASK = [1, 1, 1, 0]
+    ARK0 = [3, 1 << 40, 0xFFFFFFFF00000000, 17, 0x123456789ABCDEF, 5, 0, 0xDEADBEEF]
+    ARK1 = [7, 0xFFFFFFFF, 2, 0xFEDCBA9876543210 % P, 11, 1 << 63, 13, 0xC0FFEE]
+    periodic_columns = [CYCLE_MASK, ARK0, ARK1]
+    # mask * (cubic / quadratic in the trace): with_cycles(3, [4]), with_cycles(2, [4]); ark1 * (linear):
+    # with_cycles(1, [8])  (rescue/air.rs:41-46 declares its degrees the same way) -> ce_blowup 4, three groups
+    transition_degrees = [(3, [4]), (2, [4]), (1, [8])]
+    SEED = (42, 43)
+
+    @classmethod
+    def build_trace(cls, n: int) -> np.ndarray:
+        s0, s1 = cls.SEED
+        cols = np.empty((3, n), np.uint64)
+        for i in range(n):
+            cols[0, i], cols[1, i], cols[2, i] = s0, s1, i
+            if cls.CYCLE_MASK[i % 4]:
+                s0, s1 = (s0 * s0 * s0 + s1 + cls.ARK0[i % 8]) % P, (s0 * s1 + cls.ARK1[i % 8]) % P
+            else:
+                s0, s1 = s1, s0
+        return cols
+
+    def evaluate_transition(self, cur: Sequence[int], nxt: Sequence[int], periodic: Sequence[int] = ()) -> List[int]:
+        mask, ark0, ark1 = periodic
+        not_mask = (1 - mask) % P
+        round0 = (nxt[0] - (cur[0] * cur[0] * cur[0] + cur[1] + ark0)) % P
+        round1 = (nxt[1] - (cur[0] * cur[1] + ark1)) % P
+        return [(mask * round0 + not_mask * (nxt[0] - cur[1])) % P,
+                (mask * round1 + not_mask * (nxt[1] - cur[0])) % P,
+                ark1 * (nxt[2] - cur[2] - 1) % P]
+
+    def get_assertions(self) -> List[Assertion]:
+        return [Assertion(0, 0, self.SEED[0]), Assertion(1, 0, self.SEED[1]), Assertion(2, 0, 0),
+                Assertion(0, self.n - 1, self.result)]
+
+
+def _degree(d) -> Tuple[int, List[int]]:
+    """(base, cycles) of a TransitionConstraintDegree given as an int or a (base, cycles) pair."""
+    return (d, []) if isinstance(d, int) else (d[0], list(d[1]))
+
+
+def _eval_poly(poly: Sequence[int], x: int) -> int:  # polynom::eval (math/src/polynom/mod.rs:44-55), Horner
+    acc = 0
+    for c in reversed(poly):
+        acc = (acc * x + c) % P
+    return acc
 
 
 def _next_pow2(x: int) -> int:

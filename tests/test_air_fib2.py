@@ -290,3 +290,158 @@ def test_random_transition_program_matches_a_python_evaluation(ctx, n_nodes, ce_
     assert np.array_equal(got, want)
     for sg in segs:
         sg.destroy()
+
+
+# ---- periodic columns (what Miden's ProcessorAir needs beyond the Fibonacci examples) ------------------
+def _setup_chain(logn):
+    from oracle.air import MaskedChainAir
+
+    n = 1 << logn
+    trace = MaskedChainAir.build_trace(n)
+    result = int(trace[0, n - 1])
+    air = MaskedChainAir(n, result)
+    divs = [so.Divisor(d.a, d.b, d.exemptions) for d in air.divisors()]
+    return n, trace, air, divs, result.to_bytes(8, "little")
+
+
+def test_periodic_value_table_equals_polynomial_evaluation():
+    """The reference's own unit test of PeriodicValueTable (prover/src/constraints/periodic_table.rs:105-155)
+    on its columns [1, 2] and [3, 4, 5, 6] over a 32-row trace: the table looked up by constraint-evaluation
+    step equals every column polynomial evaluated at x^(n / cycle) over the shifted domain -- i.e. the
+    prover-side and the verifier-side formulation of a periodic column agree."""
+    from oracle.air import SimpleAir, root_of_unity, log2, GENERATOR
+
+    class Mock(SimpleAir):  # prover/src/tests/mod.rs MockAir::with_periodic_columns
+        trace_width = 4
+        transition_degrees = [1]
+        periodic_columns = [[1, 2], [3, 4, 5, 6]]
+
+        def get_assertions(self):
+            return []
+
+    air = Mock(32, 0)
+    table = air.periodic_value_table()
+    assert [len(c) for c in table] == [2 * air.ce_blowup, 4 * air.ce_blowup]
+    g = root_of_unity(log2(air.ce_domain_size()))
+    for s in range(air.ce_domain_size()):
+        x = GENERATOR * pow(g, s, P) % P
+        assert [col[s % len(col)] for col in table] == air.periodic_values_at(x)
+    # on the trace domain itself the polynomials reproduce the column values, cyclically
+    gt = root_of_unity(5)
+    for i in range(32):
+        assert air.periodic_values_at(pow(gt, i, P)) == [[1, 2][i % 2], [3, 4, 5, 6][i % 4]]
+
+
+def test_masked_chain_structure():
+    """MaskedChainAir: degrees with cycles (degree.rs:102-131) give ce_blowup 4 and three transition groups
+    with distinct degree adjustments; the constraints vanish on the trace."""
+    n, trace, air, divs, _ = _setup_chain(4)
+    assert air.ce_blowup == 4 and air.composition_degree() == 4 * n - 1
+    groups = air.transition_groups([(0, 0)] * 3)
+    target = (4 * n - 1) + (n - 1)
+    ev = [(n - 1) + (n // 8) * 7, 2 * (n - 1) + (n // 4) * 3, 3 * (n - 1) + (n // 4) * 3]
+    assert [gr[0] for gr in groups] == [target - e for e in ev]          # BTreeMap order: by evaluation degree
+    assert [[m[0] for m in gr[1]] for gr in groups] == [[2], [1], [0]]
+    per = air.periodic_columns
+    for i in range(n - 1):
+        row = lambda k: [int(trace[c, k]) for c in range(3)]
+        assert air.evaluate_transition(row(i), row(i + 1), [col[i % len(col)] for col in per]) == [0, 0, 0]
+    assert len(divs) == 3  # transition, first step, last step
+
+
+@pytest.mark.parametrize("logn", [3, 5, 7])
+def test_masked_chain_oracle_proof_passes_the_ood_consistency_check(logn):
+    n, trace, air, divs, pub = _setup_chain(logn)
+    ref = _oracle_prove(trace, air, divs, pub)
+    so.verify(ref.proof_bytes, pub, air.ce_blowup, air=air)
+    assert ref.comp.polys.shape == (air.ce_blowup, n)
+    # teeth: a wrong round constant on the prover side is caught by the verifier's polynomial evaluation
+    class Bad(type(air)):
+        ARK0 = list(type(air).ARK0)
+    Bad.ARK0[3] += 1
+    Bad.periodic_columns = [Bad.CYCLE_MASK, Bad.ARK0, Bad.ARK1]
+    bad = Bad(n, air.result)
+    with pytest.raises(AssertionError, match="InconsistentOodConstraintEvaluations"):
+        so.verify(_oracle_prove(trace, bad, divs, pub).proof_bytes, pub, air.ce_blowup, air=air)
+
+
+def _masked_chain_program(air, to_abi_int):
+    """MaskedChainAir.evaluate_transition recorded node by node, the periodic columns handed over by their cycle
+    values, each constraint with its group's degree adjustment (degrees with cycles)."""
+    from aero_b200 import AirProgramBuilder
+
+    b = AirProgramBuilder()
+    mask, ark0, ark1 = (b.periodic(b.periodic_column([to_abi_int(v) for v in col])) for col in air.periodic_columns)
+    c0, c1, c2, n0, n1, n2 = b.cur(0), b.cur(1), b.cur(2), b.next(0), b.next(1), b.next(2)
+    one = b.const(to_abi_int(1))
+    not_mask = b.sub(one, mask)
+    round0 = b.sub(n0, b.add(b.add(b.mul(b.mul(c0, c0), c0), c1), ark0))
+    round1 = b.sub(n1, b.add(b.mul(c0, c1), ark1))
+    t = [b.add(b.mul(mask, round0), b.mul(not_mask, b.sub(n0, c1))),
+         b.add(b.mul(mask, round1), b.mul(not_mask, b.sub(n1, c0))),
+         b.mul(ark1, b.sub(b.sub(n2, c2), one))]
+    nt = len(t)
+    pairs = [(0, 0)] * (air.num_constraint_coefficients() // 2)
+    adj_of = {idx: adj for adj, members in air.transition_groups(pairs[:nt]) for idx, _ in members}
+    for i in range(nt):
+        b.transition(t[i], adj_of[i])
+    assertions = sorted(air.get_assertions(), key=lambda a: (0, a.step, a.column))
+    groups = air.boundary_groups(pairs[nt:])
+    for a in assertions:
+        (j, adj), = [(j, adj) for j, (div, adj, mem) in enumerate(groups)
+                     if div.b == (pow(air.g, a.step, P) if a.step else 1)]
+        b.assertion(a.column, to_abi_int(a.value), adj, 1 + j)
+    return b.finish()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("form", ["canonical", "montgomery"])
+@pytest.mark.parametrize("logn", [3, 5, 8, 12])
+def test_periodic_columns_evaluated_on_the_gpu(ctx, ctx_mont, logn, form):
+    """AERO_AIR_PERIODIC: the device evaluator with periodic columns (cycles 4 and 8, constraint evaluation domain
+    4n, three transition groups) equals the restated ConstraintEvaluator column for column, and aero_prove with the
+    program gives the oracle prover's bytes, accepted by the verifier model -- whose OOD consistency check
+    evaluates the column POLYNOMIALS at z^(n / cycle) (verifier/src/evaluator.rs:27-36), independent of the
+    prover's table lookup."""
+    from aero_b200 import make_divisor
+
+    n, trace, air, divs, pub = _setup_chain(logn)
+    mont = form == "montgomery"
+    c = ctx_mont if mont else ctx
+    to_abi = so.canon_to_mont if mont else (lambda a: a)
+    from_abi = so.mont_to_canon if mont else (lambda a: a)
+    to_abi_int = lambda v: int(to_abi(np.array([v], np.uint64))[0])
+    prog, keep = _masked_chain_program(air, to_abi_int)
+    rng = np.random.default_rng(100 + logn)
+    coeffs = [int(v) % P for v in rng.integers(0, 2**63, air.num_constraint_coefficients(), dtype=np.uint64)]
+    seg = c.build_trace_commitment(to_abi(trace), 8)
+    got = from_abi(c.evaluate_constraints([seg], prog, [to_abi_int(v) for v in coeffs], air.ce_blowup, len(divs)))
+    if logn <= 8:
+        lde = from_abi(seg.download_lde())
+        assert np.array_equal(got, air.evaluate_constraints_over_ce_domain(lde, coeffs))
+    seg.destroy()
+    gdivs = [make_divisor(d.a, to_abi_int(d.b), [to_abi_int(v) for v in d.exemptions]) for d in divs]
+    got_proof = c.prove(to_abi(trace), None, None, gdivs, pub, n_constraint_coeffs=air.num_constraint_coefficients(),
+                        ce_blowup=air.ce_blowup, air_program=prog)
+    if logn <= 8:
+        assert got_proof == _oracle_prove(trace, air, divs, pub).proof_bytes
+    so.verify(got_proof, pub, air.ce_blowup, air=air)  # 2^12 rows: any wrong evaluation breaks the OOD check
+
+
+@pytest.mark.gpu
+def test_periodic_program_is_validated(ctx):
+    """A periodic node without its column, and cycle lengths the reference asserts against
+    (air/src/air/mod.rs:319-335), are rejected."""
+    from aero_b200 import AeroError, AirProgramBuilder
+
+    n, trace, air, divs, pub = _setup_chain(4)
+    seg = ctx.build_trace_commitment(trace, 8)
+    for cols, ref_col in (([], 0), ([[1, 2, 3]], 0), ([[1] * 32], 0), ([[1, 2]], 1)):
+        b = AirProgramBuilder()
+        for col in cols:
+            b.periodic_column(col)
+        b.transition(b.mul(b.periodic(ref_col), b.cur(0)), 1)
+        prog, keep = b.finish()
+        with pytest.raises(AeroError):
+            ctx.evaluate_constraints([seg], prog, [1, 2], 4, 1)
+    seg.destroy()

@@ -193,9 +193,55 @@ def test_air_program_builder_marshals_the_c_struct():
     # the header's enum and the ctypes constants agree
     import re, os
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "aero_b200.h")).read()
-    m = re.search(r"enum \{ AERO_AIR_CUR = (\d), AERO_AIR_NEXT = (\d), AERO_AIR_CONST = (\d), AERO_AIR_ADD = (\d), AERO_AIR_SUB = (\d), AERO_AIR_MUL = (\d) \}", hdr)
+    m = re.search(r"enum \{ AERO_AIR_CUR = (\d), AERO_AIR_NEXT = (\d), AERO_AIR_CONST = (\d), AERO_AIR_ADD = (\d), AERO_AIR_SUB = (\d), AERO_AIR_MUL = (\d),\s+AERO_AIR_PERIODIC = (\d) \}", hdr)
     assert m and [int(x) for x in m.groups()] == [_lib.AERO_AIR_CUR, _lib.AERO_AIR_NEXT, _lib.AERO_AIR_CONST,
-                                                  _lib.AERO_AIR_ADD, _lib.AERO_AIR_SUB, _lib.AERO_AIR_MUL]
+                                                  _lib.AERO_AIR_ADD, _lib.AERO_AIR_SUB, _lib.AERO_AIR_MUL,
+                                                  _lib.AERO_AIR_PERIODIC]
+    # periodic columns: cycle values concatenated, one length per column
+    b = AirProgramBuilder()
+    k0, k1 = b.periodic_column([1, 2]), b.periodic_column([3, 4, 5, 6])
+    b.transition(b.mul(b.periodic(k1), b.periodic(k0)), 1)
+    p, keep = b.finish()
+    assert p.n_periodic == 2 and [p.periodic_len[i] for i in range(2)] == [2, 4]
+    assert [p.periodic_values[i] for i in range(6)] == [1, 2, 3, 4, 5, 6]
+    assert (p.nodes[0].op, p.nodes[0].a) == (_lib.AERO_AIR_PERIODIC, k1)
+
+
+def test_periodic_column_table_of_the_library_equals_the_oracle():
+    """aero_periodic_column_table (the host arithmetic behind AERO_AIR_PERIODIC nodes: interpolation over the
+    cycle, evaluation over offset^(n / cycle) * <w_(cycle * ce_blowup)>) against the oracle's restatement of
+    PeriodicValueTable::new (prover/src/constraints/periodic_table.rs:25-75), on the reference's own test
+    columns (:110-120), MaskedChainAir's, and random columns up to a cycle as long as the trace."""
+    import numpy as np
+    from aero_b200.prover import periodic_column_table
+    from oracle.air import MaskedChainAir, SimpleAir, P
+
+    def oracle_table(cols, n, ce_blowup):
+        class A(SimpleAir):
+            trace_width = 1
+            transition_degrees = [ce_blowup + 1 if ce_blowup > 2 else 2]
+            periodic_columns = cols
+
+            def get_assertions(self):
+                return []
+        a = A(n, 0)
+        assert a.ce_blowup == ce_blowup
+        return a.periodic_value_table()
+
+    rng = np.random.default_rng(7)
+    cases = [([[1, 2], [3, 4, 5, 6]], 32, 2), (MaskedChainAir.periodic_columns, 64, 4),
+             ([[int(v) % P for v in rng.integers(0, 2**63, c, dtype=np.uint64)] for c in (2, 16, 64)], 64, 8)]
+    for cols, n, ceb in cases:
+        want = oracle_table(cols, n, ceb)
+        for col, w in zip(cols, want):
+            got = periodic_column_table(col, n, ceb)
+            assert [int(v) for v in got] == w
+    # Air::get_periodic_column_polys' assertions (air/src/air/mod.rs:319-335)
+    for bad in ([1], [1, 2, 3], [1] * 64):
+        with pytest.raises(aero_b200.AeroError):
+            periodic_column_table(bad, 32, 2)
+    with pytest.raises(aero_b200.AeroError):
+        periodic_column_table([1, P], 32, 2)
 
 
 def test_copy_pool_stress(tmp_path):
