@@ -206,8 +206,10 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
  * The program is a list of nodes in evaluation order; node k may refer to nodes < k:
  *   AERO_AIR_CUR / AERO_AIR_NEXT  a = trace column (segments concatenated: main, then auxiliary) of the
  *                                  current / next row of the frame (EvaluationFrame, air/src/air/mod.rs)
- *   AERO_AIR_CONST                a = index into consts (ABI form: public inputs, periodic-free constants,
- *                                  the auxiliary segment's random elements)
+ *   AERO_AIR_CONST                a = index into consts (ABI form: public inputs, constants of the AIR, the
+ *                                  auxiliary segment's random elements -- consts is read when the evaluator
+ *                                  runs, so inside aero_prove a caller stores the random elements from its
+ *                                  aux_builder callback, which has returned by then)
  *   AERO_AIR_PERIODIC             a = periodic column (Air::get_periodic_column_values,
  *                                  air/src/air/mod.rs:246-248): the value periodic_values[a] of
  *                                  Air::evaluate_transition at this step

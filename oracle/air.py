@@ -26,7 +26,14 @@ Restated, each with the file:line it follows (paths relative to winterfell/):
     ProcessorAir needs beyond the Fibonacci examples (miden/air/src/lib.rs:117-120: hasher and bitwise
     chiplet columns); exercised by MaskedChainAir, built like examples/src/rescue/air.rs:60-116 (a cycle
     mask switching between a round function with periodic round constants and a plain step).
-Only what these use is covered: main segment only, single-value assertions.
+  * one auxiliary trace segment: Air::evaluate_aux_transition / get_aux_assertions with the segment's random
+    elements (air/src/air/mod.rs:262-306), the coefficient order main transition, auxiliary transition, main
+    assertions, auxiliary assertions (mod.rs:511-533), auxiliary boundary groups merged into the main group
+    with the same divisor or appended (prover/src/constraints/boundary.rs:58-72) and the full evaluation
+    frame of the prover (evaluator.rs:210-270) and the verifier (verifier/src/evaluator.rs:38-57,77-100);
+    exercised by PermutationAir, a running-product argument of the kind Miden's auxiliary columns are
+    (miden/processor/src/trace/utils.rs:153-199; examples/src/rescue_raps/air.rs:162-240 has the same shape).
+Only what these use is covered: single-value assertions, at most one auxiliary segment.
 Pure Python big-int arithmetic: small traces only."""
 from __future__ import annotations
 
@@ -86,12 +93,18 @@ class SimpleAir:
     transition_degrees: list = []
     periodic_columns: List[List[int]] = []  # Air::get_periodic_column_values (air/src/air/mod.rs:246-248)
     num_transition_exemptions = 1  # context.rs:159
+    # auxiliary segment (TraceLayout: aux_segment_widths / aux_segment_rands, air/src/air/trace_info.rs)
+    aux_width = 0
+    num_aux_rands = 0
+    aux_transition_degrees: list = []
+    aux_rand_elements: Sequence[int] = ()  # AuxTraceRandElements: set by whoever drew them (prover / verifier)
 
     def __init__(self, trace_length: int, result: int, blowup: int = 8):
         self.n, self.result, self.blowup = trace_length, result, blowup
         # context.rs:124-137 with degree.rs:113-131: max over constraints of
         # max(next_power_of_two(base + cycles - 1), MIN_BLOWUP_FACTOR = 2)
-        self.ce_blowup = max(max(_next_pow2(b + len(cyc) - 1), 2) for b, cyc in map(_degree, self.transition_degrees))
+        self.ce_blowup = max(max(_next_pow2(b + len(cyc) - 1), 2)
+                             for b, cyc in map(_degree, list(self.transition_degrees) + list(self.aux_transition_degrees)))
         assert blowup >= self.ce_blowup
         self.g = root_of_unity(log2(trace_length))
         for col in self.periodic_columns:  # air/src/air/mod.rs:319-335
@@ -142,10 +155,32 @@ class SimpleAir:
     def get_assertions(self) -> List[Assertion]:
         raise NotImplementedError
 
+    # auxiliary segment (air/src/air/mod.rs:262-306); column indices are relative to the segment
+    def evaluate_aux_transition(self, main_cur, main_nxt, aux_cur, aux_nxt, periodic, rand) -> List[int]:
+        return []
+
+    def get_aux_assertions(self, rand) -> List[Assertion]:
+        return []
+
+    def _all_degrees(self) -> list:
+        return list(self.transition_degrees) + list(self.aux_transition_degrees)
+
+    def _num_aux_assertions(self) -> int:  # the count does not depend on the random elements (context.rs:139-157)
+        return len(self.get_aux_assertions([0] * self.num_aux_rands)) if self.aux_width else 0
+
+    def _transition_all(self, cur: Sequence[int], nxt: Sequence[int], periodic: Sequence[int]) -> List[int]:
+        """Main constraints, then auxiliary ones (the order of their coefficient pairs), over a frame whose rows
+        hold the main columns followed by the auxiliary ones."""
+        w = self.trace_width
+        t = self.evaluate_transition(cur[:w], nxt[:w], periodic)
+        if self.aux_width:
+            t = list(t) + list(self.evaluate_aux_transition(cur[:w], nxt[:w], cur[w:], nxt[w:], periodic, self.aux_rand_elements))
+        return t
+
     def num_constraint_coefficients(self) -> int:
         """Field elements drawn by get_constraint_composition_coefficients (air/src/air/mod.rs:511-533):
-        a pair per transition constraint, then a pair per assertion."""
-        return 2 * (len(self.transition_degrees) + len(self.get_assertions()))
+        a pair per transition constraint (main, then auxiliary), then a pair per assertion (likewise)."""
+        return 2 * (len(self._all_degrees()) + len(self.get_assertions()) + self._num_aux_assertions())
 
     # ---- constraint structure shared by prover and verifier ---------------------------------
     def transition_divisor(self) -> ConstraintDivisor:  # divisor.rs:36-45
@@ -154,10 +189,13 @@ class SimpleAir:
 
     def transition_groups(self, coeffs: Sequence[Tuple[int, int]]):
         """transition/mod.rs:305-343: constraints grouped by evaluation degree (BTreeMap order);
-        each group: (degree_adjustment, [(constraint index, (c0, c1))])."""
+        each group: (degree_adjustment, [(constraint index, (c0, c1))]).  Auxiliary constraints follow the
+        main ones in index and coefficient order; the reference keeps them in a second list of groups
+        (transition/mod.rs:62-79) whose merged evaluations are added to the first (:165-178), which is the
+        same sum as grouping them together."""
         div_deg = self.transition_divisor().degree()
         groups: Dict[int, Tuple[int, list]] = {}
-        for i, d in enumerate(self.transition_degrees):
+        for i, d in enumerate(self._all_degrees()):
             base, cycles = _degree(d)
             ev_deg = base * (self.n - 1) + sum((self.n // c) * (c - 1) for c in cycles)  # degree.rs:102-108
             if ev_deg not in groups:
@@ -170,25 +208,42 @@ class SimpleAir:
         """boundary/mod.rs:120-190: assertions sorted by (stride, first step, column) -- the BTreeSet
         order of assertions/mod.rs:310-322 -- zipped with the coefficient pairs, grouped by
         (stride, first step), groups sorted by degree adjustment (stable).  Each group:
-        (divisor, degree_adjustment, [(column, value, (c0, c1))])."""
-        assertions = sorted(self.get_assertions(), key=lambda a: (0, a.step, a.column))
-        groups: Dict[Tuple[int, int], Tuple[ConstraintDivisor, int, list]] = {}
-        for a, cc in zip(assertions, coeffs):
-            key = (0, a.step)
-            if key not in groups:
-                # divisor.rs:47-61 (num_steps = 1): x - g^step
-                div = ConstraintDivisor(1, pow(self.g, a.step, P) if a.step else 1, [])
-                adj = self.composition_degree() + div.degree() - self.trace_poly_degree()  # constraint_group.rs:28-30
-                groups[key] = (div, adj, [])
-            groups[key][2].append((a.column, a.value, cc))
-        out = [groups[k] for k in sorted(groups)]
-        out.sort(key=lambda gr: gr[1])
+        (divisor, degree_adjustment, [(column, value, (c0, c1))]).
+        Assertions against the auxiliary segment take the coefficient pairs after the main ones
+        (boundary/mod.rs:104-106), are grouped the same way on their own, and each of their groups joins the
+        main group with the same divisor or is appended (prover/src/constraints/boundary.rs:58-72); their
+        column index is returned offset by the main width (a row = main columns, then auxiliary)."""
+        def group(assertions, ccs, col_offset):
+            assertions = sorted(assertions, key=lambda a: (0, a.step, a.column))
+            groups: Dict[Tuple[int, int], Tuple[ConstraintDivisor, int, list]] = {}
+            for a, cc in zip(assertions, ccs):
+                key = (0, a.step)
+                if key not in groups:
+                    # divisor.rs:47-61 (num_steps = 1): x - g^step
+                    div = ConstraintDivisor(1, pow(self.g, a.step, P) if a.step else 1, [])
+                    adj = self.composition_degree() + div.degree() - self.trace_poly_degree()  # constraint_group.rs:28-30
+                    groups[key] = (div, adj, [])
+                groups[key][2].append((a.column + col_offset, a.value, cc))
+            out = [groups[k] for k in sorted(groups)]
+            out.sort(key=lambda gr: gr[1])
+            return out
+
+        main_assertions = self.get_assertions()
+        out = group(main_assertions, coeffs[:len(main_assertions)], 0)
+        if self.aux_width:
+            rand = self.aux_rand_elements if len(self.aux_rand_elements) else [0] * self.num_aux_rands
+            for g_aux in group(self.get_aux_assertions(rand), coeffs[len(main_assertions):], self.trace_width):
+                same = [g_main for g_main in out if (g_main[0].a, g_main[0].b) == (g_aux[0].a, g_aux[0].b)]
+                if same:
+                    same[0][2].extend(g_aux[2])
+                else:
+                    out.append(g_aux)
         return out
 
     def divisors(self) -> List[ConstraintDivisor]:
         """Columns of the prover's evaluation table (evaluator.rs:66-67): transition first."""
         pairs = [(0, 0)] * (self.num_constraint_coefficients() // 2)
-        nt = len(self.transition_degrees)
+        nt = len(self._all_degrees())
         return [self.transition_divisor()] + [g[0] for g in self.boundary_groups(pairs[nt:])]
 
     @staticmethod
@@ -201,7 +256,7 @@ class SimpleAir:
         """trace_lde: natural-order LDE columns (N = blowup * n values each); coeffs: the drawn
         composition coefficients, flat.  Returns (1 + boundary groups, ce_domain_size) merged
         evaluations, one column per divisor (evaluator.rs:121-160, 207-224; boundary.rs:59-72)."""
-        t_cc, b_cc = self.split_coefficients(coeffs, len(self.transition_degrees))
+        t_cc, b_cc = self.split_coefficients(coeffs, len(self._all_degrees()))
         tg, bg = self.transition_groups(t_cc), self.boundary_groups(b_cc)
         ce = self.ce_domain_size()
         N = self.blowup * self.n
@@ -214,7 +269,7 @@ class SimpleAir:
             row = step << lde_shift
             cur = [int(c[row]) for c in trace_lde]
             nxt = [int(c[(row + self.blowup) % N]) for c in trace_lde]  # trace_lde.rs: next = + blowup, wrapping
-            t = self.evaluate_transition(cur, nxt, [col[step % len(col)] for col in periodic])  # evaluator.rs:183-186
+            t = self._transition_all(cur, nxt, [col[step % len(col)] for col in periodic])  # evaluator.rs:183-186, 230-246
             acc = 0
             for adj, members in tg:
                 xp = pow(x, adj, P)  # domain.rs:109-117: ce_domain[step*power mod ce] * offset^power = x^power
@@ -233,8 +288,8 @@ class SimpleAir:
     # ---- verifier side: evaluate_constraints at the out-of-domain point ---------------------
     def evaluate_constraints_at(self, coeffs: Sequence[int], ood_cur: Sequence[int], ood_next: Sequence[int], z: int) -> int:
         """verifier/src/evaluator.rs:14-107."""
-        t_cc, b_cc = self.split_coefficients(coeffs, len(self.transition_degrees))
-        t = self.evaluate_transition(ood_cur, ood_next, self.periodic_values_at(z))
+        t_cc, b_cc = self.split_coefficients(coeffs, len(self._all_degrees()))
+        t = self._transition_all(list(ood_cur), list(ood_next), self.periodic_values_at(z))
         result = 0
         for adj, members in self.transition_groups(t_cc):  # transition/mod.rs:165-185
             xp = pow(z, adj, P)
@@ -343,6 +398,61 @@ class MaskedChainAir(SimpleAir):
     def get_assertions(self) -> List[Assertion]:
         return [Assertion(0, 0, self.SEED[0]), Assertion(1, 0, self.SEED[1]), Assertion(2, 0, 0),
                 Assertion(0, self.n - 1, self.result)]
+
+
+class PermutationAir(SimpleAir):
+    """A randomized AIR with one auxiliary column, the shape of Miden's running-product columns
+    (miden/processor/src/trace/utils.rs:153-199: col[i + 1] = col[i] * multiplicand[i]) and of the
+    reference's rescue_raps example (examples/src/rescue_raps/air.rs:162-240).  Main segment: x counts up in
+    steps of 3 from 5; y holds the first n - 1 values of x rotated by 7 rows.  Auxiliary column p proves that
+    the two multisets agree: with v(t) = alpha + beta * t for the segment's random elements (alpha, beta),
+        p[0] = 1,   p[i + 1] * v(y[i]) = p[i] * v(x[i]),   p[n - 1] = 1."""
+
+    trace_width = 2
+    transition_degrees = [1]
+    aux_width = 1
+    num_aux_rands = 2
+    aux_transition_degrees = [2]
+    X0, STEP, ROT = 5, 3, 7
+
+    @classmethod
+    def build_trace(cls, n: int) -> np.ndarray:
+        cols = np.zeros((2, n), np.uint64)
+        for i in range(n):
+            cols[0, i] = cls.X0 + cls.STEP * i
+        for i in range(n - 1):
+            cols[1, i] = cols[0, (i + cls.ROT) % (n - 1)]
+        return cols
+
+    @staticmethod
+    def multiplicands(main: np.ndarray, rand: Sequence[int]) -> Tuple[List[int], List[int]]:
+        """Row values (alpha + beta * x[i], alpha + beta * y[i]): numerators and denominators of the updates."""
+        a, b = int(rand[0]), int(rand[1])
+        return [(a + b * int(v)) % P for v in main[0]], [(a + b * int(v)) % P for v in main[1]]
+
+    @classmethod
+    def build_aux(cls, main: np.ndarray, rand: Sequence[int]) -> np.ndarray:  # Trace::build_aux_segment
+        num, den = cls.multiplicands(main, rand)
+        n = main.shape[1]
+        col = np.empty((1, n), np.uint64)
+        acc = 1
+        for i in range(n):
+            col[0, i] = acc
+            acc = acc * num[i] % P * inv(den[i]) % P
+        return col
+
+    def evaluate_transition(self, cur, nxt, periodic=()):
+        return [(nxt[0] - cur[0] - self.STEP) % P]
+
+    def evaluate_aux_transition(self, main_cur, main_nxt, aux_cur, aux_nxt, periodic, rand):
+        a, b = int(rand[0]), int(rand[1])
+        return [(aux_nxt[0] * (a + b * main_cur[1]) - aux_cur[0] * (a + b * main_cur[0])) % P]
+
+    def get_assertions(self):
+        return [Assertion(0, 0, self.X0)]
+
+    def get_aux_assertions(self, rand):
+        return [Assertion(0, 0, 1), Assertion(0, self.n - 1, 1)]
 
 
 def _degree(d) -> Tuple[int, List[int]]:

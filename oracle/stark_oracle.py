@@ -565,7 +565,9 @@ def verify(proof_bytes: bytes, pub_inputs_seed_bytes: bytes, num_comp_columns: O
     coin = RandomCoin(pub_inputs_seed_bytes)
     coin.reseed(trace_roots[0])
     for c in trace_roots[1:]:
-        [coin.draw() for _ in range(ctx.aux_rands)]
+        aux_rand = [coin.draw() for _ in range(ctx.aux_rands)]  # verifier/src/lib.rs:206-214
+        if air is not None:
+            air.aux_rand_elements = aux_rand  # AuxTraceRandElements handed to evaluate_constraints
         coin.reseed(c)
     # get_constraint_composition_coefficients (lib.rs:221-226, air/src/air/mod.rs:511-533)
     constraint_coeffs = [coin.draw() for _ in range(air.num_constraint_coefficients())] if air is not None else []
@@ -906,6 +908,8 @@ def prove(main_trace: np.ndarray, aux_trace: Optional[np.ndarray], ce_cols: np.n
     aux_rand = []
     if aux_trace is not None:
         aux_rand = [coin.draw() for _ in range(aux_rands)]  # lib.rs:313
+        if callable(aux_trace):  # Trace::build_aux_segment (lib.rs:314-316): the segment depends on the draws
+            aux_trace = np.ascontiguousarray(aux_trace(aux_rand), np.uint64)
         aux = build_trace_commitment(aux_trace, blowup)  # lib.rs:328
         commitments += aux.root
         coin.reseed(aux.root)

@@ -445,3 +445,125 @@ def test_periodic_program_is_validated(ctx):
         with pytest.raises(AeroError):
             ctx.evaluate_constraints([seg], prog, [1, 2], 4, 1)
     seg.destroy()
+
+
+# ---- an auxiliary segment with a running-product column (Miden's aux columns, SURVEY 8(f)3 + 8(f)4) ------
+def _setup_perm(logn):
+    from oracle.air import PermutationAir
+
+    n = 1 << logn
+    trace = PermutationAir.build_trace(n)
+    air = PermutationAir(n, 0)
+    divs = [so.Divisor(d.a, d.b, d.exemptions) for d in air.divisors()]
+    return n, trace, air, divs, b"permutation"
+
+
+def _oracle_prove_perm(trace, air, divs, pub, tamper=None):
+    def aux_builder(rand):
+        air.aux_rand_elements = list(rand)
+        aux = air.build_aux(trace, rand)
+        return tamper(aux) if tamper else aux
+
+    ce0 = np.zeros((len(divs), air.ce_domain_size()), np.uint64)
+    return so.prove(trace, aux_builder, ce0, divs, pub, aux_rands=air.num_aux_rands,
+                    num_constraint_coeff_draws=air.num_constraint_coefficients(),
+                    constraint_evaluator=lambda lde, cc: air.evaluate_constraints_over_ce_domain(lde, cc))
+
+
+def test_permutation_air_structure():
+    """Coefficient order and divisor columns with an auxiliary segment: the auxiliary assertion at the first step
+    joins the main group with the same divisor, the one at the last step opens a new column
+    (prover/src/constraints/boundary.rs:58-72); the running product closes at 1."""
+    n, trace, air, divs, _ = _setup_perm(5)
+    assert air.ce_blowup == 2 and air.num_constraint_coefficients() == 2 * (1 + 1 + 1 + 2)
+    rand = [1234567, 89]
+    aux = air.build_aux(trace, rand)
+    assert int(aux[0, 0]) == 1 and int(aux[0, n - 1]) == 1 and len({int(v) for v in aux[0]}) > n // 2
+    air.aux_rand_elements = rand
+    groups = air.boundary_groups([(1, 2), (3, 4), (5, 6)])
+    assert [(g[0].a, g[0].b) for g in groups] == [(1, 1), (1, pow(air.g, n - 1, P))]
+    assert [[(col, val) for col, val, _ in g[2]] for g in groups] == [[(0, 5), (2, 1)], [(2, 1)]]
+    assert [[cc for _, _, cc in g[2]] for g in groups] == [[(1, 2), (3, 4)], [(5, 6)]]
+    assert len(divs) == 3
+    for i in range(n - 1):
+        row = lambda k: [int(trace[0, k]), int(trace[1, k]), int(aux[0, k])]
+        assert air._transition_all(row(i), row(i + 1), []) == [0, 0]
+
+
+@pytest.mark.parametrize("logn", [4, 7])
+def test_permutation_air_oracle_proof_passes_the_ood_consistency_check(logn):
+    n, trace, air, divs, pub = _setup_perm(logn)
+    ref = _oracle_prove_perm(trace, air, divs, pub)
+    air.aux_rand_elements = ()  # the verifier draws its own
+    rep = so.verify(ref.proof_bytes, pub, air.ce_blowup, air=air)
+    assert len(rep.positions) == 27
+    # a running product that does not follow the recurrence is rejected
+    def tamper(aux):
+        aux = aux.copy()
+        aux[0, 3] = np.uint64((int(aux[0, 3]) + 1) % P)
+        return aux
+    with pytest.raises(AssertionError, match="InconsistentOodConstraintEvaluations"):
+        so.verify(_oracle_prove_perm(trace, air, divs, pub, tamper).proof_bytes, pub, air.ce_blowup, air=air)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("form", ["canonical", "montgomery"])
+@pytest.mark.parametrize("logn", [4, 8, 12])
+def test_aux_segment_built_and_constrained_on_the_gpu(ctx, ctx_mont, logn, form):
+    """The two steps the north star leaves on the Rust path, both on the device inside ONE aero_prove call
+    (SURVEY 8(f)4 + 8(f)3): the aux_builder callback receives the segment's random elements and builds the
+    running-product column with aero_batch_inverse + aero_running_product_columns; the AIR program then
+    constrains main and auxiliary columns together (the random elements are program constants, written by the
+    callback: constants are read when the evaluator runs).  Bytes equal the oracle prover's, and the verifier
+    model accepts them, OOD consistency check over the main + auxiliary frame included."""
+    from aero_b200 import AirProgramBuilder, make_divisor
+
+    n, trace, air, divs, pub = _setup_perm(logn)
+    mont = form == "montgomery"
+    c = ctx_mont if mont else ctx
+    to_abi = so.canon_to_mont if mont else (lambda a: a)
+    from_abi = so.mont_to_canon if mont else (lambda a: a)
+    to_abi_int = lambda v: int(to_abi(np.array([v], np.uint64))[0])
+
+    b = AirProgramBuilder()
+    x, y, x_next = b.cur(0), b.cur(1), b.next(0)
+    p_cur, p_next = b.cur(2), b.next(2)              # auxiliary column 0 = trace column main_width + 0
+    alpha, beta, step = b.const(0), b.const(0), b.const(to_abi_int(air.STEP))
+    v = lambda t: b.add(alpha, b.mul(beta, t))
+    t_main = b.sub(b.sub(x_next, x), step)
+    t_aux = b.sub(b.mul(p_next, v(y)), b.mul(p_cur, v(x)))
+    pairs = [(0, 0)] * (air.num_constraint_coefficients() // 2)
+    adj_of = {idx: adj for adj, members in air.transition_groups(pairs[:2]) for idx, _ in members}
+    b.transition(t_main, adj_of[0])
+    b.transition(t_aux, adj_of[1])
+    # assertions in coefficient order: main (sorted), then auxiliary (sorted); divisor column = group index + 1
+    groups = air.boundary_groups(pairs[2:])
+    col_of = {(col, div.b): (1 + j, adj) for j, (div, adj, mem) in enumerate(groups) for col, _, _ in mem}
+    first, last = 1, pow(air.g, n - 1, P)
+    for col, value, div_b in ((0, air.X0, first), (2, 1, first), (2, 1, last)):
+        j, adj = col_of[(col, div_b)]
+        b.assertion(col, to_abi_int(value), adj, j)
+    prog, keep = b.finish()
+    consts = keep[1]
+
+    seen = {}
+
+    def aux_builder(rands_abi):
+        rand = [int(r) for r in from_abi(rands_abi)]
+        seen["rand"] = rand
+        consts[0], consts[1] = int(rands_abi[0]), int(rands_abi[1])     # alpha, beta for the evaluator
+        num, den = air.multiplicands(trace, rand)
+        den_inv = from_abi(c.batch_inverse(to_abi(np.array(den, np.uint64))))
+        mult = np.array([a * int(d) % P for a, d in zip(num, den_inv)], np.uint64)
+        return c.running_product_columns(to_abi(mult)[None, :], [to_abi_int(1)])
+
+    gdivs = [make_divisor(d.a, to_abi_int(d.b), [to_abi_int(v) for v in d.exemptions]) for d in divs]
+    got = c.prove(to_abi(trace), None, None, gdivs, pub, aux_rands=air.num_aux_rands,
+                  n_constraint_coeffs=air.num_constraint_coefficients(), aux_builder=aux_builder, aux_width=1,
+                  ce_blowup=air.ce_blowup, air_program=prog)
+    if logn <= 8:
+        ref = _oracle_prove_perm(trace, air, divs, pub)
+        assert seen["rand"] == [int(r) for r in air.aux_rand_elements]
+        assert got == ref.proof_bytes
+    air.aux_rand_elements = ()
+    so.verify(got, pub, air.ce_blowup, air=air)
