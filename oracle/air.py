@@ -33,6 +33,10 @@ Restated, each with the file:line it follows (paths relative to winterfell/):
     frame of the prover (evaluator.rs:210-270) and the verifier (verifier/src/evaluator.rs:38-57,77-100);
     exercised by PermutationAir, a running-product argument of the kind Miden's auxiliary columns are
     (miden/processor/src/trace/utils.rs:153-199; examples/src/rescue_raps/air.rs:162-240 has the same shape).
+  * Miden's BITWISE CHIPLET (miden/air/src/chiplets/bitwise/mod.rs:25-60,78-240 with the chiplet selector
+    flags and constraints of miden/air/src/chiplets/mod.rs:100-130,178-185 and the trace rows of
+    miden/processor/src/chiplets/bitwise/mod.rs:87-150,210-224) as a stand-alone AIR, BitwiseChipletAir: a
+    piece of the ProcessorAir that the path's real caller evaluates, with its two periodic columns.
 Only what these use is covered: single-value assertions, at most one auxiliary segment.
 Pure Python big-int arithmetic: small traces only."""
 from __future__ import annotations
@@ -453,6 +457,89 @@ class PermutationAir(SimpleAir):
 
     def get_aux_assertions(self, rand):
         return [Assertion(0, 0, 1), Assertion(0, self.n - 1, 1)]
+
+
+class BitwiseChipletAir(SimpleAir):
+    """Miden's bitwise chiplet on its own: the 17 constraints of miden/air/src/chiplets/bitwise/mod.rs:78-240
+    under the chiplet flag s0 * (1 - s1') (chiplets/mod.rs:183-185), preceded by the four chiplet-selector
+    constraints that involve s0 and s1 (chiplets/mod.rs:100-130, results 0, 1, 3, 4), over the periodic columns
+    k0 = 1,0,0,0,0,0,0,0 and k1 = 1,1,1,1,1,1,1,0 (bitwise/mod.rs:395-417).  Columns (CHIPLETS_OFFSET = 0,
+    core/src/chiplets/mod.rs:17-86, core/src/chiplets/bitwise.rs:7-56): s0, s1, selector, a, b, a0..a3, b0..b3,
+    output_prev, output.  Every row belongs to the chiplet (s0 = 1, s1 = 0); each operation fills an 8-row
+    cycle, most significant 4-bit limb first (processor/src/chiplets/bitwise/mod.rs:87-150, 210-224)."""
+
+    trace_width = 15
+    S0, S1, SEL, A, B, A_BITS, B_BITS, OUT_PREV, OUT = 0, 1, 2, 3, 4, 5, 9, 13, 14
+    K0 = [1, 0, 0, 0, 0, 0, 0, 0]
+    K1 = [1, 1, 1, 1, 1, 1, 1, 0]
+    periodic_columns = [K0, K1]
+    # chiplets/mod.rs:20-23 (entries 0, 1, 3, 4), then bitwise/mod.rs:37-60
+    transition_degrees = [2, 3, 2, 3,
+                          4, (3, [8])] + [4] * 8 + [(3, [8])] * 4 + [(3, [8]), (3, [8]), 5]
+
+    @staticmethod
+    def operations(n: int) -> List[Tuple[int, int, int]]:
+        """(selector, a, b) per 8-row cycle: AND = 0, XOR = 1 (core/src/chiplets/bitwise.rs:18-24)."""
+        ops, x = [], 0x9E3779B97F4A7C15
+        for k in range(n // 8):
+            x = (x * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+            a = (x >> 32) & 0xFFFFFFFF
+            x = (x * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+            b = (x >> 32) & 0xFFFFFFFF
+            ops.append((k % 3 != 0, a, b))
+        return [(int(sel), a, b) for sel, a, b in ops]
+
+    @classmethod
+    def build_trace(cls, n: int) -> np.ndarray:
+        assert n >= 8
+        cols = np.zeros((cls.trace_width, n), np.uint64)
+        cols[cls.S0, :] = 1
+        row = 0
+        for sel, a, b in cls.operations(n):
+            result = 0
+            for bit_offset in range(28, -1, -4):  # u32and / u32xor, processor/.../bitwise/mod.rs:94-112
+                cols[cls.OUT_PREV, row] = result
+                av, bv = a >> bit_offset, b >> bit_offset
+                cols[cls.SEL, row], cols[cls.A, row], cols[cls.B, row] = sel, av, bv  # add_bitwise_trace_row :210-224
+                for i in range(4):
+                    cols[cls.A_BITS + i, row] = (av >> i) & 1
+                    cols[cls.B_BITS + i, row] = (bv >> i) & 1
+                result = (result << 4) | (((av ^ bv) if sel else (av & bv)) & 0xF)
+                cols[cls.OUT, row] = result
+                row += 1
+        return cols
+
+    def evaluate_transition(self, cur, nxt, periodic=()):
+        k0, k1 = periodic
+        is_binary = lambda v: (v * v - v) % P                      # air/src/utils.rs:14-16
+        agg = lambda r, start: sum((1 << i) * r[start + i] for i in range(4)) % P   # bitwise/mod.rs:381-391
+        s0, s1 = cur[self.S0], cur[self.S1]
+        out = [is_binary(s0), s0 * is_binary(s1) % P,              # chiplets/mod.rs:107-110
+               s0 * (s0 - nxt[self.S0]) % P, s0 * s1 * (s1 - nxt[self.S1]) % P]   # :118-121
+        flag = s0 * (1 - nxt[self.S1]) % P                         # bitwise_flag, chiplets/mod.rs:183-185
+        sel = cur[self.SEL]
+        out.append(flag * is_binary(sel) % P)                      # bitwise/mod.rs:100
+        out.append(flag * k1 * (sel - nxt[self.SEL]) % P)          # :106
+        out += [flag * is_binary(cur[self.A_BITS + i]) % P for i in range(4)]   # :134-136
+        out += [flag * is_binary(cur[self.B_BITS + i]) % P for i in range(4)]   # :140-146
+        first = flag * k0 % P
+        out.append(first * (cur[self.A] - agg(cur, self.A_BITS)) % P)           # :151-152
+        out.append(first * (cur[self.B] - agg(cur, self.B_BITS)) % P)           # :157
+        trans = flag * k1 % P
+        out.append(trans * (nxt[self.A] - (16 * cur[self.A] + agg(nxt, self.A_BITS))) % P)   # :162-164
+        out.append(trans * (nxt[self.B] - (16 * cur[self.B] + agg(nxt, self.B_BITS))) % P)   # :169-170
+        out.append(k0 * flag * cur[self.OUT_PREV] % P)             # :200
+        out.append(k1 * flag * (nxt[self.OUT_PREV] - cur[self.OUT]) % P)        # :205-206
+        shifted = cur[self.OUT_PREV] * 16
+        a_b = [(cur[self.A_BITS + i], cur[self.B_BITS + i]) for i in range(4)]
+        b_and = sum((1 << i) * a * b for i, (a, b) in enumerate(a_b))            # :231-240
+        b_xor = sum((1 << i) * (a + b - 2 * a * b) for i, (a, b) in enumerate(a_b))   # :244-253
+        and_flag, xor_flag = flag * (1 - sel) % P, flag * sel % P                # :195-196, 363-369
+        out.append((and_flag * (cur[self.OUT] - (shifted + b_and)) + xor_flag * (cur[self.OUT] - (shifted + b_xor))) % P)  # :211-221
+        return out
+
+    def get_assertions(self):
+        return [Assertion(self.S0, 0, 1), Assertion(self.OUT_PREV, 0, 0), Assertion(self.OUT, self.n - 1, self.result)]
 
 
 def _degree(d) -> Tuple[int, List[int]]:

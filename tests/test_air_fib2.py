@@ -567,3 +567,153 @@ def test_aux_segment_built_and_constrained_on_the_gpu(ctx, ctx_mont, logn, form)
         assert got == ref.proof_bytes
     air.aux_rand_elements = ()
     so.verify(got, pub, air.ce_blowup, air=air)
+
+
+# ---- Miden's bitwise chiplet: a piece of the ProcessorAir the path's real caller evaluates ------------------
+def _setup_bitwise(logn):
+    from oracle.air import BitwiseChipletAir
+
+    n = 1 << logn
+    trace = BitwiseChipletAir.build_trace(n)
+    result = int(trace[BitwiseChipletAir.OUT, n - 1])
+    air = BitwiseChipletAir(n, result)
+    divs = [so.Divisor(d.a, d.b, d.exemptions) for d in air.divisors()]
+    return n, trace, air, divs, result.to_bytes(8, "little")
+
+
+def test_bitwise_chiplet_restatement():
+    """The restated constraints against the reference's own tests (miden/air/src/chiplets/bitwise/tests.rs):
+    valid AND / XOR frames evaluate to zero at every row of a cycle (:110-127), a selector that changes inside
+    a cycle breaks exactly the second bitwise constraint (:24-39), and the frame of `output_aggregation_and`
+    (:44-104: a = 1, b = 9, AND, claimed output 1337) breaks the output aggregation constraint."""
+    from oracle.air import BitwiseChipletAir as BA
+
+    n, trace, air, divs, _ = _setup_bitwise(6)
+    assert air.ce_blowup == 4 and len(air.transition_degrees) == 4 + 17 and len(divs) == 3
+    row = lambda k: [int(trace[c, k]) for c in range(BA.trace_width)]
+    per = lambda k: [col[k % 8] for col in air.periodic_columns]
+    for i in range(n - 1):
+        assert air.evaluate_transition(row(i), row(i + 1), per(i)) == [0] * 21
+    ops = BA.operations(n)
+    assert {sel for sel, _, _ in ops} == {0, 1}
+    for k, (sel, a, b) in enumerate(ops):
+        assert int(trace[BA.OUT, 8 * k + 7]) == ((a ^ b) if sel else (a & b))
+    # selector changes inside the cycle (rows 1 -> 2 of the first operation)
+    nxt = row(2)
+    nxt[BA.SEL] ^= 1
+    bad = air.evaluate_transition(row(1), nxt, per(1))
+    assert bad[5] != 0 and all(v == 0 for j, v in enumerate(bad) if j != 5)
+    # the reference's hand-made frame, chiplet flag = 1
+    cur, nx = [0] * 15, [0] * 15
+    cur[BA.S0] = nx[BA.S0] = 1
+    cur[BA.SEL:] = [0, 1, 9, 1, 0, 0, 0, 1, 0, 0, 1, 0, 1337]
+    nx[BA.SEL:] = [0, 19, 157, 1, 1, 0, 0, 1, 0, 1, 1, 1337, 21393]
+    got = air.evaluate_transition(cur, nx, [1, 1])
+    assert got[20] != 0
+    cur[BA.OUT] = 1
+    assert air.evaluate_transition(cur, nx, [1, 1])[20] == 0
+
+
+@pytest.mark.parametrize("logn", [3, 6])
+def test_bitwise_chiplet_oracle_proof_passes_the_ood_consistency_check(logn):
+    n, trace, air, divs, pub = _setup_bitwise(logn)
+    ref = _oracle_prove(trace, air, divs, pub)
+    so.verify(ref.proof_bytes, pub, air.ce_blowup, air=air)
+    assert ref.comp.polys.shape == (4, n)
+    # a wrong output limb in the trace is caught
+    bad = trace.copy()
+    bad[air.OUT, 2] ^= np.uint64(1)
+    with pytest.raises(AssertionError, match="InconsistentOodConstraintEvaluations"):
+        so.verify(_oracle_prove(bad, air, divs, pub).proof_bytes, pub, air.ce_blowup, air=air)
+
+
+def _bitwise_program(air, to_abi_int):
+    """BitwiseChipletAir.evaluate_transition -- i.e. chiplets::enforce_selectors (s0, s1) + bitwise::enforce_constraints
+    -- recorded node by node for the device evaluator."""
+    from aero_b200 import AirProgramBuilder
+
+    A = air
+    b = AirProgramBuilder()
+    k0, k1 = (b.periodic(b.periodic_column([to_abi_int(v) for v in col])) for col in A.periodic_columns)
+    cur = [b.cur(c) for c in range(A.trace_width)]
+    nxt = [b.next(c) for c in range(A.trace_width)]
+    one, two, sixteen = (b.const(to_abi_int(v)) for v in (1, 2, 16))
+    pow2 = [one, two, b.const(to_abi_int(4)), b.const(to_abi_int(8))]
+    is_binary = lambda v: b.sub(b.mul(v, v), v)
+
+    def agg(r, start):
+        acc = b.mul(pow2[0], r[start])
+        for i in range(1, 4):
+            acc = b.add(acc, b.mul(pow2[i], r[start + i]))
+        return acc
+
+    s0, s1, sel = cur[A.S0], cur[A.S1], cur[A.SEL]
+    t = [is_binary(s0), b.mul(s0, is_binary(s1)), b.mul(s0, b.sub(s0, nxt[A.S0])),
+         b.mul(b.mul(s0, s1), b.sub(s1, nxt[A.S1]))]
+    flag = b.mul(s0, b.sub(one, nxt[A.S1]))
+    t.append(b.mul(flag, is_binary(sel)))
+    t.append(b.mul(b.mul(flag, k1), b.sub(sel, nxt[A.SEL])))
+    t += [b.mul(flag, is_binary(cur[A.A_BITS + i])) for i in range(4)]
+    t += [b.mul(flag, is_binary(cur[A.B_BITS + i])) for i in range(4)]
+    first, trans = b.mul(flag, k0), b.mul(flag, k1)
+    t.append(b.mul(first, b.sub(cur[A.A], agg(cur, A.A_BITS))))
+    t.append(b.mul(first, b.sub(cur[A.B], agg(cur, A.B_BITS))))
+    t.append(b.mul(trans, b.sub(nxt[A.A], b.add(b.mul(sixteen, cur[A.A]), agg(nxt, A.A_BITS)))))
+    t.append(b.mul(trans, b.sub(nxt[A.B], b.add(b.mul(sixteen, cur[A.B]), agg(nxt, A.B_BITS)))))
+    t.append(b.mul(b.mul(k0, flag), cur[A.OUT_PREV]))
+    t.append(b.mul(b.mul(k1, flag), b.sub(nxt[A.OUT_PREV], cur[A.OUT])))
+    shifted = b.mul(cur[A.OUT_PREV], sixteen)
+    and_acc = xor_acc = None
+    for i in range(4):
+        x, y = cur[A.A_BITS + i], cur[A.B_BITS + i]
+        xy = b.mul(x, y)
+        a_term = b.mul(pow2[i], xy)
+        x_term = b.mul(pow2[i], b.sub(b.add(x, y), b.mul(two, xy)))
+        and_acc = a_term if and_acc is None else b.add(and_acc, a_term)
+        xor_acc = x_term if xor_acc is None else b.add(xor_acc, x_term)
+    and_flag, xor_flag = b.mul(flag, b.sub(one, sel)), b.mul(flag, sel)
+    t.append(b.add(b.mul(and_flag, b.sub(cur[A.OUT], b.add(shifted, and_acc))),
+                   b.mul(xor_flag, b.sub(cur[A.OUT], b.add(shifted, xor_acc)))))
+    nt = len(t)
+    assert nt == len(A.transition_degrees)
+    pairs = [(0, 0)] * (A.num_constraint_coefficients() // 2)
+    adj_of = {idx: adj for adj, members in A.transition_groups(pairs[:nt]) for idx, _ in members}
+    for i in range(nt):
+        b.transition(t[i], adj_of[i])
+    groups = A.boundary_groups(pairs[nt:])
+    for a in sorted(A.get_assertions(), key=lambda a: (0, a.step, a.column)):
+        (j, adj), = [(j, adj) for j, (div, adj, mem) in enumerate(groups) if div.b == (pow(A.g, a.step, P) if a.step else 1)]
+        b.assertion(a.column, to_abi_int(a.value), adj, 1 + j)
+    return b.finish()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("form", ["canonical", "montgomery"])
+@pytest.mark.parametrize("logn", [3, 6, 9, 14])
+def test_bitwise_chiplet_evaluated_on_the_gpu(ctx, ctx_mont, logn, form):
+    """Miden's bitwise chiplet constraints (21 constraints of degree 2..5, two periodic columns, five transition
+    groups, evaluation domain 4n) on the device evaluator: table == the restated ConstraintEvaluator column for
+    column, aero_prove's bytes == the oracle prover's, OOD consistency check passed; at 2^14 rows (2048 bitwise
+    operations) the check alone."""
+    from aero_b200 import make_divisor
+
+    n, trace, air, divs, pub = _setup_bitwise(logn)
+    mont = form == "montgomery"
+    c = ctx_mont if mont else ctx
+    to_abi = so.canon_to_mont if mont else (lambda a: a)
+    from_abi = so.mont_to_canon if mont else (lambda a: a)
+    to_abi_int = lambda v: int(to_abi(np.array([v], np.uint64))[0])
+    prog, keep = _bitwise_program(air, to_abi_int)
+    if logn <= 6:
+        rng = np.random.default_rng(200 + logn)
+        coeffs = [int(v) % P for v in rng.integers(0, 2**63, air.num_constraint_coefficients(), dtype=np.uint64)]
+        seg = c.build_trace_commitment(to_abi(trace), 8)
+        got = from_abi(c.evaluate_constraints([seg], prog, [to_abi_int(v) for v in coeffs], air.ce_blowup, len(divs)))
+        assert np.array_equal(got, air.evaluate_constraints_over_ce_domain(from_abi(seg.download_lde()), coeffs))
+        seg.destroy()
+    gdivs = [make_divisor(d.a, to_abi_int(d.b), [to_abi_int(v) for v in d.exemptions]) for d in divs]
+    got_proof = c.prove(to_abi(trace), None, None, gdivs, pub, n_constraint_coeffs=air.num_constraint_coefficients(),
+                        ce_blowup=air.ce_blowup, air_program=prog)
+    if logn <= 6:
+        assert got_proof == _oracle_prove(trace, air, divs, pub).proof_bytes
+    so.verify(got_proof, pub, air.ce_blowup, air=air)
