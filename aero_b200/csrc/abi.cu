@@ -2220,13 +2220,14 @@ aero_status aero_periodic_column_table(const uint64_t *cycle_values, uint64_t cy
     return AERO_OK;
 }
 
-aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs,
+// tau0 / tau_count out: the coset-major range of evaluation-domain steps this rank evaluated (everything on one GPU)
+static aero_status constraints_evaluate_impl(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs,
                                              const aero_air_program *prog, const uint64_t *coeffs, uint32_t n_coeffs,
-                                             uint32_t ce_blowup, uint32_t n_div, uint64_t *d_eval_cols, size_t col_stride) {
+                                             uint32_t ce_blowup, uint32_t n_div, uint64_t *d_eval_cols, size_t col_stride,
+                                             uint32_t *tau0_out, uint32_t *tau_count_out) {
     if (!ctx) return AERO_ERR_INVALID;
     enter(ctx);
     if (!trace_segs || !prog || !d_eval_cols || (n_coeffs && !coeffs)) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
-    if (ctx_sharded(ctx)) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "constraint evaluation on a sharded context");
     if (n_trace_segs == 0 || n_trace_segs > 4) CTX_FAIL(ctx, AERO_ERR_INVALID, "1..4 trace segments");
     if (n_div == 0 || n_div > 8) CTX_FAIL(ctx, AERO_ERR_INVALID, "number of divisors must be 1..8, got %u", n_div);
     if (prog->n_nodes == 0 || prog->n_nodes > (1u << 16) || !prog->nodes) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "transition program must have 1..65536 nodes");
@@ -2242,8 +2243,11 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
     for (uint32_t k = 0; k < n_trace_segs; k++) {
         const aero_segment *sg = trace_segs[k];
         if (!sg || !sg->lde) CTX_FAIL(ctx, AERO_ERR_STATE, "trace segment %u has not been committed", k);
-        if (sg->logn != s0->logn || sg->log_blowup != s0->log_blowup) CTX_FAIL(ctx, AERO_ERR_INVALID, "trace segments of different shape");
-        segs.lde[k] = sg->lde;
+        if (sg->logn != s0->logn || sg->log_blowup != s0->log_blowup || sg->coset_begin != s0->coset_begin || sg->coset_count != s0->coset_count)
+            CTX_FAIL(ctx, AERO_ERR_INVALID, "trace segments of different shape");
+        // a coset-sharded segment stores cosets [coset_begin, coset_begin + coset_count) compactly: rebase so that
+        // the kernel's (LDE coset, i) index lands in it (only the rank's own cosets are ever read)
+        segs.lde[k] = sg->lde - ((size_t)sg->coset_begin << sg->logn);
         segs.stride[k] = sg->lde_stride();
         segs.ncols[k] = sg->ncols;
         width += (uint32_t)sg->ncols;
@@ -2397,17 +2401,37 @@ aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const 
         snprintf(key, sizeof key, "xce/%d", logn + log_ce);
         TRY(get_pow_table(ctx, key, gl::root_of_unity(logn + log_ce), logn + log_ce, gl::GENERATOR, &x_ce));
     }
+    // The evaluation-domain cosets whose LDE coset (rc << shift) this rank holds: a contiguous range, all of them
+    // on one GPU.  Step s = i * ce_blowup + rc reads LDE coset rc << shift at i and i + 1 only, so a coset-sharded
+    // rank evaluates its share of the domain without any exchange.
+    const int shift = log_blowup - log_ce;
+    const uint32_t rc_lo = (uint32_t)((s0->coset_begin + (1 << shift) - 1) >> shift);
+    const uint32_t rc_hi = (uint32_t)((s0->coset_begin + s0->coset_count + (1 << shift) - 1) >> shift);
+    const uint32_t tau0 = rc_lo << logn, tau_count = (rc_hi - rc_lo) << logn;
     {
         PhaseTimer t(ctx, "constraint_evaluate");
-        air_evaluate(segs, p, logn, log_blowup, log_ce, x_ce, ctx->form == AERO_FORM_MONTGOMERY, d_eval_cols, col_stride, ctx->stream);
+        air_evaluate(segs, p, logn, log_blowup, log_ce, x_ce, ctx->form == AERO_FORM_MONTGOMERY, d_eval_cols, col_stride, ctx->stream,
+                     tau0, tau_count);
     }
+    if (tau0_out) *tau0_out = tau0;
+    if (tau_count_out) *tau_count_out = tau_count;
     CUDA_TRY(ctx, cudaGetLastError());
     return AERO_OK;
 }
 
-aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_eval_cols, size_t col_stride,
+aero_status aero_constraints_evaluate_device(aero_ctx *ctx, aero_segment *const *trace_segs, uint32_t n_trace_segs,
+                                             const aero_air_program *prog, const uint64_t *coeffs, uint32_t n_coeffs,
+                                             uint32_t ce_blowup, uint32_t n_div, uint64_t *d_eval_cols, size_t col_stride) {
+    return constraints_evaluate_impl(ctx, trace_segs, n_trace_segs, prog, coeffs, n_coeffs, ce_blowup, n_div, d_eval_cols,
+                                     col_stride, nullptr, nullptr);
+}
+
+// own_cosets: a sharded context holds (and combines) the coset-major range [tau0, tau0 + tau_count) of the evaluation
+// columns -- what constraints_evaluate_impl left there -- instead of its block of rows.
+static aero_status constraints_into_poly_impl(aero_ctx *ctx, const uint64_t *d_eval_cols, size_t col_stride,
                                               const aero_divisor *divs, uint32_t n_div, uint64_t ce_domain_size,
-                                              uint64_t trace_len, aero_segment **out) {
+                                              uint64_t trace_len, aero_segment **out, bool own_cosets, uint32_t tau0,
+                                              uint32_t tau_count) {
     if (!ctx) return AERO_ERR_INVALID;
     enter(ctx);
     if (!d_eval_cols || !divs || !out) CTX_FAIL(ctx, AERO_ERR_INVALID, "null argument");
@@ -2458,11 +2482,16 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
             divisor_inverses(o, z, logN, gN, ctx->stream);
             o.zinv = z;
         }
-        if (st == AERO_OK) constraint_combine(cols, col_stride, dd.data(), (int)n_div, logN, gl::GENERATOR, gN, (uint32_t)row0,
-                                              (uint32_t)rows_per, combined, ctx->stream);
+        if (st == AERO_OK && !own_cosets)
+            constraint_combine(cols, col_stride, dd.data(), (int)n_div, logN, gl::GENERATOR, gN, (uint32_t)row0, (uint32_t)rows_per,
+                               combined, ctx->stream);
+        if (st == AERO_OK && own_cosets)  // `combined` is coset-major on this route
+            constraint_combine(cols, col_stride, dd.data(), (int)n_div, logN, gl::GENERATOR, gN, tau0, tau_count, combined, ctx->stream,
+                               logn, logN - logn);
     }
     if (st == AERO_OK && G > 1) {
-        peer_push_words(rank_ptrs(ctx, combined), G, ctx->shard_rank, row0, rows_per, ctx->stream);
+        if (own_cosets) peer_push_words(rank_ptrs(ctx, combined), G, ctx->shard_rank, tau0, tau_count, ctx->stream);
+        else peer_push_words(rank_ptrs(ctx, combined), G, ctx->shard_rank, row0, rows_per, ctx->stream);
         st = window_barrier(ctx);
     }
     aero_segment *seg = nullptr;
@@ -2474,7 +2503,7 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
         st = dev_alloc(ctx, (void **)&seg->polys, N * 8);
     }
     const int logB = logN - logn;
-    if (st == AERO_OK && (logN > NTT_MAX_LOG || ctx->force_split_intt)) {
+    if (st == AERO_OK && (logN > NTT_MAX_LOG || ctx->force_split_intt || own_cosets)) {
         // N = B*n beyond the two-pass NTT: B plain size-n interpolations (one per LDE coset) and a
         // B-point inverse DFT across them (coset_interp_combine in poly.cu)
         if (logB > 4 || logn > NTT_MAX_LOG) {
@@ -2514,14 +2543,14 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
                 M = it->second;
             }
         }
-        if (st == AERO_OK) st = dev_alloc(ctx, (void **)&cm, N * 8);
+        if (st == AERO_OK && !own_cosets) st = dev_alloc(ctx, (void **)&cm, N * 8);
         if (st == AERO_OK) st = dev_alloc(ctx, (void **)&a, N * 8);
         if (st == AERO_OK && plan->log1 != 0) st = dev_alloc(ctx, (void **)&tmp, N * 8);
         if (st == AERO_OK) {
             PhaseTimer t(ctx, "composition_poly");
-            natural_to_coset_major(combined, cm, logn, logB, ctx->stream);
+            if (!own_cosets) natural_to_coset_major(combined, cm, logn, logB, ctx->stream);
             DftLaunch l;
-            l.src = cm;
+            l.src = own_cosets ? combined : cm;
             l.dst = a;
             l.tmp = tmp;
             l.src_col_stride = trace_len;
@@ -2566,6 +2595,12 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
     return AERO_OK;
 }
 
+aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_eval_cols, size_t col_stride,
+                                              const aero_divisor *divs, uint32_t n_div, uint64_t ce_domain_size,
+                                              uint64_t trace_len, aero_segment **out) {
+    return constraints_into_poly_impl(ctx, d_eval_cols, col_stride, divs, n_div, ce_domain_size, trace_len, out, false, 0, 0);
+}
+
 aero_status aero_constraints_into_poly(aero_ctx *ctx, const uint64_t *const *eval_cols, const aero_divisor *divs,
                                        uint32_t n_div, uint64_t ce_domain_size, uint64_t trace_len,
                                        aero_segment **out) {
@@ -2600,8 +2635,10 @@ aero_status aero_constraints_evaluate_into_poly(aero_ctx *ctx, aero_segment *con
     DevBlocks blk(ctx);
     uint64_t *d_ce = nullptr;
     TRY(blk.alloc((void **)&d_ce, (size_t)n_div * CE * 8));
-    TRY(aero_constraints_evaluate_device(ctx, trace_segs, n_trace_segs, prog, coeffs, n_coeffs, ce_blowup, n_div, d_ce, CE));
-    return aero_constraints_into_poly_device(ctx, d_ce, CE, divs, n_div, CE, n, out);
+    uint32_t tau0 = 0, tau_count = 0;
+    TRY(constraints_evaluate_impl(ctx, trace_segs, n_trace_segs, prog, coeffs, n_coeffs, ce_blowup, n_div, d_ce, CE, &tau0, &tau_count));
+    // one GPU: the whole table is there, in natural order; several: each rank combines the cosets it evaluated
+    return constraints_into_poly_impl(ctx, d_ce, CE, divs, n_div, CE, n, out, ctx_sharded(ctx), tau0, tau_count);
 }
 
 // ---- OOD + DEEP -----------------------------------------------------------------------------

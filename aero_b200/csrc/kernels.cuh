@@ -193,10 +193,12 @@ struct DivisorDev {
     uint32_t zn;           // N / a
 };
 void divisor_inverses(const DivisorDev &d, uint64_t *zinv_out, int logN, PowTable gN, cudaStream_t s);
-// rows [i_begin, i_begin + i_count) of the constraint evaluation domain
+// rows [i_begin, i_begin + i_count) of the constraint evaluation domain; with cm_logn >= 0 the range and the output
+// are coset-major (t = r * n + k for the natural row k * B + r, n = 2^cm_logn, B = 2^cm_logb), the evaluation
+// columns stay in natural order
 void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDev *divs, int ndiv, int logN,
                         uint64_t offset, PowTable gN, uint32_t i_begin, uint32_t i_count, uint64_t *combined,
-                        cudaStream_t s);
+                        cudaStream_t s, int cm_logn = -1, int cm_logb = 0);
 
 // AIR constraint evaluation over the constraint evaluation domain (include/aero_b200.h, aero_air_program)
 struct AirSegs {  // trace segments in order: column c of segment s at lde[s] + c*stride[s], coset-major
@@ -218,8 +220,10 @@ struct AirProgramDev {       // device copies; field elements canonical
     const uint64_t *adj;     // distinct degree adjustments
     int n_nodes, n_slots, nt, nb, n_adj, n_div;
 };
+// threads [tau0, tau0 + tau_count) of the coset-major numbering (tau = rc * n + i): a coset-sharded rank passes
+// the cosets it holds, with segs.lde rebased so that (LDE coset, i) indexes its compact storage
 void air_evaluate(const AirSegs &segs, const AirProgramDev &p, int logn, int log_blowup, int log_ce, PowTable x_ce /* 7 g_ce^s */,
-                  int to_montgomery, uint64_t *out, size_t out_stride, cudaStream_t s);
+                  int to_montgomery, uint64_t *out, size_t out_stride, cudaStream_t s, uint32_t tau0, uint32_t tau_count);
 
 // peak.cu
 double measure_alu_peak(int num_sms, uint32_t *scratch, cudaStream_t s);

@@ -710,11 +710,14 @@ struct DivisorSet {
 };
 __global__ void __launch_bounds__(256) constraint_combine_kernel(const uint64_t *__restrict__ cols, size_t col_stride,
                                                                  DivisorSet ds, uint32_t i_begin, uint32_t i_count,
-                                                                 uint64_t offset, PowTable gN,
+                                                                 uint64_t offset, PowTable gN, int cm_logn, int cm_logb,
                                                                  uint64_t *__restrict__ combined) {
     const uint32_t il = blockIdx.x * blockDim.x + threadIdx.x;
     if (il >= i_count) return;
-    const uint32_t i = i_begin + il;
+    // cm_logn >= 0: the range [i_begin, i_begin + i_count) and the output are COSET-MAJOR (t = r * n + k for the
+    // natural row i = k * B + r, B = 2^cm_logb) -- the rows a coset-sharded rank evaluated itself
+    const uint32_t t = i_begin + il;
+    const uint32_t i = cm_logn < 0 ? t : (((t & ((1u << cm_logn) - 1)) << cm_logb) | (t >> cm_logn));
     const uint64_t x = gl::mul(pow_lookup(gN, i), offset);  // domain.get_ce_x_at, domain.rs:101-103
     uint64_t acc = 0;
     for (int k = 0; k < ds.n; k++) {
@@ -723,18 +726,18 @@ __global__ void __launch_bounds__(256) constraint_combine_kernel(const uint64_t 
         for (uint32_t e = 0; e < d.nex; e++) z = gl::mul(z, gl::sub(x, d.ex[e]));
         acc = gl::add(acc, gl::mul(__ldg(cols + (size_t)k * col_stride + i), z));
     }
-    combined[i] = acc;
+    combined[t] = acc;
 }
 void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDev *divs, int ndiv, int logN,
                         uint64_t offset, PowTable gN, uint32_t i_begin, uint32_t i_count, uint64_t *combined,
-                        cudaStream_t s) {
+                        cudaStream_t s, int cm_logn, int cm_logb) {
     (void)logN;
     DivisorSet ds;
     ds.n = ndiv;
     for (int i = 0; i < ndiv; i++) ds.d[i] = divs[i];
     if (!i_count) return;
     AERO_COUNT_LAUNCH(1);
-    constraint_combine_kernel<<<(i_count + 255) / 256, 256, 0, s>>>(cols, col_stride, ds, i_begin, i_count, offset, gN, combined);
+    constraint_combine_kernel<<<(i_count + 255) / 256, 256, 0, s>>>(cols, col_stride, ds, i_begin, i_count, offset, gN, cm_logn, cm_logb, combined);
 }
 
 // ---- AIR constraint evaluation -----------------------------------------------------
@@ -748,10 +751,11 @@ void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDe
 template <int MAXN>
 __global__ void __launch_bounds__(128) air_evaluate_kernel(AirSegs segs, AirProgramDev p, int logn, int log_blowup, int log_ce,
                                                           PowTable x_ce, int to_montgomery, uint64_t *__restrict__ out,
-                                                          size_t out_stride) {
-    const uint32_t tau = blockIdx.x * blockDim.x + threadIdx.x;
+                                                          size_t out_stride, uint32_t tau0, uint32_t tau_count) {
+    // [tau0, tau0 + tau_count): the cosets of the evaluation domain this rank holds (all of them on one GPU)
+    if (blockIdx.x * blockDim.x + threadIdx.x >= tau_count) return;
+    const uint32_t tau = tau0 + blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n = 1u << logn;
-    if (tau >= (n << log_ce)) return;
     const uint32_t i = tau & (n - 1), rc = tau >> logn;
     const uint32_t step = (i << log_ce) | rc;                     // natural index in the evaluation domain
     const size_t cur = ((size_t)(rc << (log_blowup - log_ce)) << logn) + i;   // (LDE coset, i)
@@ -799,13 +803,13 @@ __global__ void __launch_bounds__(128) air_evaluate_kernel(AirSegs segs, AirProg
     for (int d = 0; d < p.n_div; d++) out[(size_t)d * out_stride + step] = to_montgomery ? gl::canon_to_mont(acc[d]) : acc[d];
 }
 void air_evaluate(const AirSegs &segs, const AirProgramDev &p, int logn, int log_blowup, int log_ce, PowTable x_ce,
-                  int to_montgomery, uint64_t *out, size_t out_stride, cudaStream_t s) {
-    const uint64_t threads = (uint64_t)1 << (logn + log_ce);
-    const unsigned grid = (unsigned)((threads + 127) / 128);
+                  int to_montgomery, uint64_t *out, size_t out_stride, cudaStream_t s, uint32_t tau0, uint32_t tau_count) {
+    if (!tau_count) return;
+    const unsigned grid = (unsigned)(((uint64_t)tau_count + 127) / 128);
     AERO_COUNT_LAUNCH(1);
-    if (p.n_slots <= 32) air_evaluate_kernel<32><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride);
-    else if (p.n_slots <= 128) air_evaluate_kernel<128><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride);
-    else air_evaluate_kernel<1024><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride);
+    if (p.n_slots <= 32) air_evaluate_kernel<32><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride, tau0, tau_count);
+    else if (p.n_slots <= 128) air_evaluate_kernel<128><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride, tau0, tau_count);
+    else air_evaluate_kernel<1024><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride, tau0, tau_count);
 }
 
 }  // namespace aero

@@ -338,7 +338,9 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
     const bool device_air = in.air_program && !in.constraint_evaluator && !in.ce_cols;
     if (in.inputs_on_device && (in.aux_builder || in.constraint_evaluator)) P_FAIL(AERO_ERR_INVALID, "callbacks need host inputs");
     const bool sharded = aero_ctx_window_ranks(ctx) > 1;
-    if (sharded && (in.constraint_evaluator || in.aux_builder || device_air)) P_FAIL(AERO_ERR_UNSUPPORTED, "sharded proofs take precomputed auxiliary columns and constraint evaluations");
+    // A sharded proof evaluates the AIR on the device (each rank the cosets it holds) or takes precomputed
+    // evaluations; the evaluator callback would need the whole LDE on the host of one rank.
+    if (sharded && in.constraint_evaluator) P_FAIL(AERO_ERR_UNSUPPORTED, "sharded proofs take an AIR program or precomputed constraint evaluations, not the evaluator callback");
     if (in.trace_len < 2 || (in.trace_len & (in.trace_len - 1))) P_FAIL(AERO_ERR_INVALID, "trace length must be a power of two >= 2");
     const bool mont = aero_ctx_get_form(ctx) == AERO_FORM_MONTGOMERY;
     auto to_abi = [&](uint64_t x) { return mont ? gl::canon_to_mont(x) : x; };
@@ -385,7 +387,15 @@ static aero_status prove_inner(aero_ctx *ctx, const aero_prove_inputs &in, std::
         if (in.aux_builder) {
             std::vector<uint64_t> abi(rand_elements.size());
             for (size_t i = 0; i < abi.size(); i++) abi[i] = to_abi(rand_elements[i]);
-            aero_status st = in.aux_builder(in.user, abi.data(), (uint32_t)abi.size(), aux_ptrs.data());
+            // Every rank of a sharded proof has drawn the same elements and calls the builder itself (ranks in
+            // separate processes have no other way; the ranks of an aero_group take turns, so the callback
+            // never runs concurrently with itself); it must return the same columns every time.
+            aero_status st;
+            {
+                static std::mutex callback_mu;
+                std::lock_guard<std::mutex> lock(callback_mu);
+                st = in.aux_builder(in.user, abi.data(), (uint32_t)abi.size(), aux_ptrs.data());
+            }
             if (st != AERO_OK) P_FAIL(st, "aux_builder callback failed");
             aux_cols = aux_ptrs.data();
         }

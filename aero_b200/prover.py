@@ -487,8 +487,10 @@ class Group:
             if st != AERO_OK:
                 raise AeroError(st, "set_option(%s)" % key)
 
-    def prove(self, main_trace, aux_trace, ce_cols, divisors, pub_inputs_bytes, **kw) -> bytes:
-        inp, keep, _ = build_prove_inputs(main_trace, aux_trace, ce_cols, divisors, pub_inputs_bytes, **kw)
+    def prove(self, main_trace, aux_trace, ce_cols, divisors, pub_inputs_bytes, air_program=None, **kw) -> bytes:
+        inp, keep, cb_err = build_prove_inputs(main_trace, aux_trace, ce_cols, divisors, pub_inputs_bytes, **kw)
+        if air_program is not None:
+            inp.air_program = ctypes.pointer(air_program)
         cap = 1 << 20
         while True:
             buf = (c_uint8 * cap)()
@@ -497,6 +499,8 @@ class Group:
             if st == AERO_ERR_BUFFER and ln.value > cap:
                 cap = ln.value
                 continue
+            if st != AERO_OK and cb_err:
+                raise cb_err[0]
             if st != AERO_OK:
                 raise AeroError(st, (self.lib.aero_group_last_error(self.h) or b"").decode())
             return ctypes.string_at(buf, ln.value)

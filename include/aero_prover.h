@@ -71,7 +71,9 @@ typedef struct aero_prove_inputs {
     /* Third source of the constraint evaluations (used when constraint_evaluator == NULL and ce_cols == NULL):
      * the AIR's transition constraints as a program, evaluated on the device from the resident trace LDE
      * (aero_constraints_evaluate_device, include/aero_b200.h) -- nothing is downloaded.  Works with host and
-     * with device inputs; not on a sharded context. */
+     * with device inputs, and on a sharded context: step s = i * ce_blowup + r of the evaluation domain reads
+     * LDE coset r * blowup / ce_blowup only, so every rank evaluates and combines the cosets it holds and
+     * only the combined column (8 bytes per step) crosses the exchange window. */
     const aero_air_program *air_program;
 } aero_prove_inputs;
 
@@ -79,7 +81,10 @@ typedef struct aero_prove_inputs {
  * *len: in = capacity, out = bytes written / required (AERO_ERR_BUFFER).  Options are checked like
  * ProofOptions::new (air/src/options.rs:120-160) and rejected with AERO_ERR_INVALID.
  * On a sharded context (aero_ctx_set_shard + exchange window) every rank calls this with the same inputs
- * and gets the same bytes; the callbacks are not available there. */
+ * and gets the same bytes.  aux_builder is called by EVERY rank there (each has drawn the same random
+ * elements; the ranks of an aero_group take turns) and must return the same columns each time;
+ * constraint_evaluator is not available on a sharded context (AERO_ERR_UNSUPPORTED): the constraint
+ * evaluations come from air_program or precomputed. */
 aero_status aero_prove(aero_ctx *ctx, const aero_prove_inputs *in, uint8_t *proof_out, size_t *len);
 
 /* ONE proof on several GPUs of this process: n_ranks contexts (one per entry of device_ids; the same

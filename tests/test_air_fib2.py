@@ -506,25 +506,13 @@ def test_permutation_air_oracle_proof_passes_the_ood_consistency_check(logn):
         so.verify(_oracle_prove_perm(trace, air, divs, pub, tamper).proof_bytes, pub, air.ce_blowup, air=air)
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("form", ["canonical", "montgomery"])
-@pytest.mark.parametrize("logn", [4, 8, 12])
-def test_aux_segment_built_and_constrained_on_the_gpu(ctx, ctx_mont, logn, form):
-    """The two steps the north star leaves on the Rust path, both on the device inside ONE aero_prove call
-    (SURVEY 8(f)4 + 8(f)3): the aux_builder callback receives the segment's random elements and builds the
-    running-product column with aero_batch_inverse + aero_running_product_columns; the AIR program then
-    constrains main and auxiliary columns together (the random elements are program constants, written by the
-    callback: constants are read when the evaluator runs).  Bytes equal the oracle prover's, and the verifier
-    model accepts them, OOD consistency check over the main + auxiliary frame included."""
-    from aero_b200 import AirProgramBuilder, make_divisor
+def _permutation_program(air, to_abi_int):
+    """PermutationAir as a device program: main and auxiliary transition constraints over the concatenated frame
+    (auxiliary column 0 = trace column main_width + 0); consts[0], consts[1] = the segment's random elements
+    (alpha, beta), filled in by the aux_builder callback."""
+    from aero_b200 import AirProgramBuilder
 
-    n, trace, air, divs, pub = _setup_perm(logn)
-    mont = form == "montgomery"
-    c = ctx_mont if mont else ctx
-    to_abi = so.canon_to_mont if mont else (lambda a: a)
-    from_abi = so.mont_to_canon if mont else (lambda a: a)
-    to_abi_int = lambda v: int(to_abi(np.array([v], np.uint64))[0])
-
+    n = air.n
     b = AirProgramBuilder()
     x, y, x_next = b.cur(0), b.cur(1), b.next(0)
     p_cur, p_next = b.cur(2), b.next(2)              # auxiliary column 0 = trace column main_width + 0
@@ -544,6 +532,29 @@ def test_aux_segment_built_and_constrained_on_the_gpu(ctx, ctx_mont, logn, form)
         j, adj = col_of[(col, div_b)]
         b.assertion(col, to_abi_int(value), adj, j)
     prog, keep = b.finish()
+    return prog, keep
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("form", ["canonical", "montgomery"])
+@pytest.mark.parametrize("logn", [4, 8, 12])
+def test_aux_segment_built_and_constrained_on_the_gpu(ctx, ctx_mont, logn, form):
+    """The two steps the north star leaves on the Rust path, both on the device inside ONE aero_prove call
+    (SURVEY 8(f)4 + 8(f)3): the aux_builder callback receives the segment's random elements and builds the
+    running-product column with aero_batch_inverse + aero_running_product_columns; the AIR program then
+    constrains main and auxiliary columns together (the random elements are program constants, written by the
+    callback: constants are read when the evaluator runs).  Bytes equal the oracle prover's, and the verifier
+    model accepts them, OOD consistency check over the main + auxiliary frame included."""
+    from aero_b200 import make_divisor
+
+    n, trace, air, divs, pub = _setup_perm(logn)
+    mont = form == "montgomery"
+    c = ctx_mont if mont else ctx
+    to_abi = so.canon_to_mont if mont else (lambda a: a)
+    from_abi = so.mont_to_canon if mont else (lambda a: a)
+    to_abi_int = lambda v: int(to_abi(np.array([v], np.uint64))[0])
+
+    prog, keep = _permutation_program(air, to_abi_int)
     consts = keep[1]
 
     seen = {}

@@ -123,3 +123,95 @@ def test_group_errors(oracle):
         assert g.prove(main, aux, ce, gdivs, b"x") == ref.proof_bytes
     finally:
         g.close()
+
+
+# ---- real AIRs on a sharded proof: the AIR program evaluated by every rank on the cosets it holds -----------
+def _air_case(which, logn):
+    import test_air_fib2 as ta
+
+    if which == "bitwise":
+        n, trace, air, divs, pub = ta._setup_bitwise(logn)
+        prog = ta._bitwise_program(air, lambda v: v)
+    elif which == "masked_chain":
+        n, trace, air, divs, pub = ta._setup_chain(logn)
+        prog = ta._masked_chain_program(air, lambda v: v)
+    else:
+        n, trace, air, divs, pub = ta._setup(logn, which)
+        prog = ta._fib2_program(air, lambda v: v)
+    return ta, trace, air, divs, pub, prog
+
+
+@pytest.mark.parametrize("world,which,logn", [(2, "fib2", 6), (8, "mulfib2", 8), (4, "masked_chain", 7), (2, "bitwise", 6),
+                                              (8, "bitwise", 8)])
+def test_group_prove_with_air_program(world, which, logn):
+    """aero_prove_inputs.air_program on a sharded proof: constraint evaluation domains of 2n (only the ranks that hold
+    LDE cosets 0 and 4 have steps to evaluate) and 4n, periodic columns, up to five transition groups; the combined
+    column crosses the exchange window coset-major and goes straight into the per-coset interpolation.  Bytes equal
+    the oracle prover's, cold and warm barriers; the verifier model's OOD consistency check accepts them."""
+    from oracle import stark_oracle as so
+
+    ta, trace, air, divs, pub, (prog, keep) = _air_case(which, logn)
+    ref = ta._oracle_prove(trace, air, divs, pub)
+    gdivs = [make_divisor(d.a, d.b, d.exemptions) for d in divs]
+    main = _pin(np.ascontiguousarray(trace))
+    g = aero_b200.Group([0] * world, window_bytes(logn, trace.shape[0], world), form=aero_b200.AERO_FORM_CANONICAL)
+    try:
+        for it in range(3):
+            got = g.prove(main, None, None, gdivs, pub, n_constraint_coeffs=air.num_constraint_coefficients(),
+                          ce_blowup=air.ce_blowup, air_program=prog)
+            assert got == ref.proof_bytes, "world %d, proof %d differs from the oracle's" % (world, it)
+        so.verify(got, pub, air.ce_blowup, air=air)
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("world,logn", [(2, 6), (4, 8), (8, 8)])
+def test_group_prove_aux_builder_and_air_program(world, logn):
+    """The auxiliary segment of a sharded proof built by the aux_builder callback (every rank calls it with the
+    same random elements, one at a time) and constrained by the AIR program: bytes equal the oracle prover's."""
+    from oracle import stark_oracle as so
+    import test_air_fib2 as ta
+
+    n, trace, air, divs, pub = ta._setup_perm(logn)
+    prog, keep = ta._permutation_program(air, lambda v: v)
+    consts = keep[1]
+    calls = []
+    # page-locked result buffers made up front: the callback runs while other ranks may already be spinning in a
+    # device-side barrier, where a CUDA allocation (pinning) would wait for them
+    bufs = [_pin(np.zeros((1, n), np.uint64)) for _ in range(2 * world)]
+
+    def aux_builder(rands):
+        rand = [int(r) for r in rands]
+        out = bufs[len(calls)]
+        calls.append(rand)
+        consts[0], consts[1] = rand[0], rand[1]
+        out[:] = air.build_aux(trace, rand)
+        return out
+
+    ref = ta._oracle_prove_perm(trace, air, divs, pub)
+    gdivs = [make_divisor(d.a, d.b, d.exemptions) for d in divs]
+    main = _pin(np.ascontiguousarray(trace))
+    g = aero_b200.Group([0] * world, window_bytes(logn, 3, world), form=aero_b200.AERO_FORM_CANONICAL)
+    try:
+        for it in range(2):
+            got = g.prove(main, None, None, gdivs, pub, aux_rands=air.num_aux_rands,
+                          n_constraint_coeffs=air.num_constraint_coefficients(), aux_builder=aux_builder, aux_width=1,
+                          ce_blowup=air.ce_blowup, air_program=prog)
+            assert got == ref.proof_bytes, "world %d, proof %d" % (world, it)
+        assert len(calls) == 2 * world and all(c == calls[0] for c in calls)
+        air.aux_rand_elements = ()
+        so.verify(got, pub, air.ce_blowup, air=air)
+    finally:
+        g.close()
+
+
+def test_group_rejects_the_evaluator_callback(oracle):
+    main, aux, ce, divs = _inputs(oracle, 8, 4, 0)
+    g = aero_b200.Group([0, 0], window_bytes(8, 4, 2), form=aero_b200.AERO_FORM_CANONICAL)
+    try:
+        with pytest.raises(aero_b200.AeroError) as e:
+            g.prove(main, None, None, [make_divisor(d.a, d.b, d.exemptions) for d in divs], b"x",
+                    constraint_evaluator=lambda lde, cc: ce)
+        assert e.value.status == aero_b200.AERO_ERR_UNSUPPORTED
+    finally:
+        g.close()
