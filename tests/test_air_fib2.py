@@ -11,6 +11,8 @@ import pytest
 
 from oracle import stark_oracle as so
 from oracle.air import Fib2Air, MulFib2Air, P
+from oracle.air_programs import (bitwise_program as _bitwise_program, fib2_program as _fib2_program,
+                                 masked_chain_program as _masked_chain_program, permutation_program as _permutation_program)
 
 AIRS = {"fib2": Fib2Air, "mulfib2": MulFib2Air}
 
@@ -121,39 +123,6 @@ def test_fib2_gpu_proof_is_byte_identical_and_verifies(ctx, ctx_mont, logn, form
                   constraint_evaluator=evaluator, ce_blowup=air.ce_blowup)
     assert got == ref.proof_bytes
     so.verify(got, pub, air.ce_blowup, air=air)
-
-
-def _fib2_program(air, to_abi_int):
-    """The fib2 / mulfib2 AIR as an aero_air_program: evaluate_transition (fib2/air.rs:41-58,
-    mulfib2/air.rs:47-63) recorded node by node, the transition group's degree adjustment, and the assertions
-    in the reference's coefficient order with their divisor columns (oracle/air.py boundary_groups restates
-    the grouping)."""
-    from aero_b200 import AirProgramBuilder
-
-    b = AirProgramBuilder()
-    c0, c1, n0, n1 = b.cur(0), b.cur(1), b.next(0), b.next(1)
-    if isinstance(air, MulFib2Air):
-        t0 = b.sub(n0, b.mul(c0, c1))   # next[0] - cur[0] * cur[1]
-        t1 = b.sub(n1, b.mul(c1, n0))   # next[1] - cur[1] * next[0]
-    else:
-        t0 = b.sub(n0, b.add(c0, c1))   # next[0] - (cur[0] + cur[1])
-        t1 = b.sub(n1, b.add(c1, n0))   # next[1] - (cur[1] + next[0])
-    pairs = [(0, 0)] * (air.num_constraint_coefficients() // 2)
-    (adj_t, members), = air.transition_groups(pairs[:2])
-    assert [m[0] for m in members] == [0, 1]
-    b.transition(t0, adj_t)
-    b.transition(t1, adj_t)
-    # coefficient pairs follow the sorted assertions; each lands in its group's divisor column
-    assertions = sorted(air.get_assertions(), key=lambda a: (0, a.step, a.column))
-    groups = air.boundary_groups(pairs[2:])
-    for a in assertions:
-        for j, (div, adj, mem) in enumerate(groups):
-            if any(col == a.column and val == a.value for col, val, _ in mem) and div.b == (pow(air.g, a.step, P) if a.step else 1):
-                b.assertion(a.column, to_abi_int(a.value), adj, 1 + j)
-                break
-        else:
-            raise AssertionError("assertion without a group")
-    return b.finish()
 
 
 @pytest.mark.gpu
@@ -365,35 +334,6 @@ def test_masked_chain_oracle_proof_passes_the_ood_consistency_check(logn):
         so.verify(_oracle_prove(trace, bad, divs, pub).proof_bytes, pub, air.ce_blowup, air=air)
 
 
-def _masked_chain_program(air, to_abi_int):
-    """MaskedChainAir.evaluate_transition recorded node by node, the periodic columns handed over by their cycle
-    values, each constraint with its group's degree adjustment (degrees with cycles)."""
-    from aero_b200 import AirProgramBuilder
-
-    b = AirProgramBuilder()
-    mask, ark0, ark1 = (b.periodic(b.periodic_column([to_abi_int(v) for v in col])) for col in air.periodic_columns)
-    c0, c1, c2, n0, n1, n2 = b.cur(0), b.cur(1), b.cur(2), b.next(0), b.next(1), b.next(2)
-    one = b.const(to_abi_int(1))
-    not_mask = b.sub(one, mask)
-    round0 = b.sub(n0, b.add(b.add(b.mul(b.mul(c0, c0), c0), c1), ark0))
-    round1 = b.sub(n1, b.add(b.mul(c0, c1), ark1))
-    t = [b.add(b.mul(mask, round0), b.mul(not_mask, b.sub(n0, c1))),
-         b.add(b.mul(mask, round1), b.mul(not_mask, b.sub(n1, c0))),
-         b.mul(ark1, b.sub(b.sub(n2, c2), one))]
-    nt = len(t)
-    pairs = [(0, 0)] * (air.num_constraint_coefficients() // 2)
-    adj_of = {idx: adj for adj, members in air.transition_groups(pairs[:nt]) for idx, _ in members}
-    for i in range(nt):
-        b.transition(t[i], adj_of[i])
-    assertions = sorted(air.get_assertions(), key=lambda a: (0, a.step, a.column))
-    groups = air.boundary_groups(pairs[nt:])
-    for a in assertions:
-        (j, adj), = [(j, adj) for j, (div, adj, mem) in enumerate(groups)
-                     if div.b == (pow(air.g, a.step, P) if a.step else 1)]
-        b.assertion(a.column, to_abi_int(a.value), adj, 1 + j)
-    return b.finish()
-
-
 @pytest.mark.gpu
 @pytest.mark.parametrize("form", ["canonical", "montgomery"])
 @pytest.mark.parametrize("logn", [3, 5, 8, 12])
@@ -506,35 +446,6 @@ def test_permutation_air_oracle_proof_passes_the_ood_consistency_check(logn):
         so.verify(_oracle_prove_perm(trace, air, divs, pub, tamper).proof_bytes, pub, air.ce_blowup, air=air)
 
 
-def _permutation_program(air, to_abi_int):
-    """PermutationAir as a device program: main and auxiliary transition constraints over the concatenated frame
-    (auxiliary column 0 = trace column main_width + 0); consts[0], consts[1] = the segment's random elements
-    (alpha, beta), filled in by the aux_builder callback."""
-    from aero_b200 import AirProgramBuilder
-
-    n = air.n
-    b = AirProgramBuilder()
-    x, y, x_next = b.cur(0), b.cur(1), b.next(0)
-    p_cur, p_next = b.cur(2), b.next(2)              # auxiliary column 0 = trace column main_width + 0
-    alpha, beta, step = b.const(0), b.const(0), b.const(to_abi_int(air.STEP))
-    v = lambda t: b.add(alpha, b.mul(beta, t))
-    t_main = b.sub(b.sub(x_next, x), step)
-    t_aux = b.sub(b.mul(p_next, v(y)), b.mul(p_cur, v(x)))
-    pairs = [(0, 0)] * (air.num_constraint_coefficients() // 2)
-    adj_of = {idx: adj for adj, members in air.transition_groups(pairs[:2]) for idx, _ in members}
-    b.transition(t_main, adj_of[0])
-    b.transition(t_aux, adj_of[1])
-    # assertions in coefficient order: main (sorted), then auxiliary (sorted); divisor column = group index + 1
-    groups = air.boundary_groups(pairs[2:])
-    col_of = {(col, div.b): (1 + j, adj) for j, (div, adj, mem) in enumerate(groups) for col, _, _ in mem}
-    first, last = 1, pow(air.g, n - 1, P)
-    for col, value, div_b in ((0, air.X0, first), (2, 1, first), (2, 1, last)):
-        j, adj = col_of[(col, div_b)]
-        b.assertion(col, to_abi_int(value), adj, j)
-    prog, keep = b.finish()
-    return prog, keep
-
-
 @pytest.mark.gpu
 @pytest.mark.parametrize("form", ["canonical", "montgomery"])
 @pytest.mark.parametrize("logn", [4, 8, 12])
@@ -636,66 +547,6 @@ def test_bitwise_chiplet_oracle_proof_passes_the_ood_consistency_check(logn):
     bad[air.OUT, 2] ^= np.uint64(1)
     with pytest.raises(AssertionError, match="InconsistentOodConstraintEvaluations"):
         so.verify(_oracle_prove(bad, air, divs, pub).proof_bytes, pub, air.ce_blowup, air=air)
-
-
-def _bitwise_program(air, to_abi_int):
-    """BitwiseChipletAir.evaluate_transition -- i.e. chiplets::enforce_selectors (s0, s1) + bitwise::enforce_constraints
-    -- recorded node by node for the device evaluator."""
-    from aero_b200 import AirProgramBuilder
-
-    A = air
-    b = AirProgramBuilder()
-    k0, k1 = (b.periodic(b.periodic_column([to_abi_int(v) for v in col])) for col in A.periodic_columns)
-    cur = [b.cur(c) for c in range(A.trace_width)]
-    nxt = [b.next(c) for c in range(A.trace_width)]
-    one, two, sixteen = (b.const(to_abi_int(v)) for v in (1, 2, 16))
-    pow2 = [one, two, b.const(to_abi_int(4)), b.const(to_abi_int(8))]
-    is_binary = lambda v: b.sub(b.mul(v, v), v)
-
-    def agg(r, start):
-        acc = b.mul(pow2[0], r[start])
-        for i in range(1, 4):
-            acc = b.add(acc, b.mul(pow2[i], r[start + i]))
-        return acc
-
-    s0, s1, sel = cur[A.S0], cur[A.S1], cur[A.SEL]
-    t = [is_binary(s0), b.mul(s0, is_binary(s1)), b.mul(s0, b.sub(s0, nxt[A.S0])),
-         b.mul(b.mul(s0, s1), b.sub(s1, nxt[A.S1]))]
-    flag = b.mul(s0, b.sub(one, nxt[A.S1]))
-    t.append(b.mul(flag, is_binary(sel)))
-    t.append(b.mul(b.mul(flag, k1), b.sub(sel, nxt[A.SEL])))
-    t += [b.mul(flag, is_binary(cur[A.A_BITS + i])) for i in range(4)]
-    t += [b.mul(flag, is_binary(cur[A.B_BITS + i])) for i in range(4)]
-    first, trans = b.mul(flag, k0), b.mul(flag, k1)
-    t.append(b.mul(first, b.sub(cur[A.A], agg(cur, A.A_BITS))))
-    t.append(b.mul(first, b.sub(cur[A.B], agg(cur, A.B_BITS))))
-    t.append(b.mul(trans, b.sub(nxt[A.A], b.add(b.mul(sixteen, cur[A.A]), agg(nxt, A.A_BITS)))))
-    t.append(b.mul(trans, b.sub(nxt[A.B], b.add(b.mul(sixteen, cur[A.B]), agg(nxt, A.B_BITS)))))
-    t.append(b.mul(b.mul(k0, flag), cur[A.OUT_PREV]))
-    t.append(b.mul(b.mul(k1, flag), b.sub(nxt[A.OUT_PREV], cur[A.OUT])))
-    shifted = b.mul(cur[A.OUT_PREV], sixteen)
-    and_acc = xor_acc = None
-    for i in range(4):
-        x, y = cur[A.A_BITS + i], cur[A.B_BITS + i]
-        xy = b.mul(x, y)
-        a_term = b.mul(pow2[i], xy)
-        x_term = b.mul(pow2[i], b.sub(b.add(x, y), b.mul(two, xy)))
-        and_acc = a_term if and_acc is None else b.add(and_acc, a_term)
-        xor_acc = x_term if xor_acc is None else b.add(xor_acc, x_term)
-    and_flag, xor_flag = b.mul(flag, b.sub(one, sel)), b.mul(flag, sel)
-    t.append(b.add(b.mul(and_flag, b.sub(cur[A.OUT], b.add(shifted, and_acc))),
-                   b.mul(xor_flag, b.sub(cur[A.OUT], b.add(shifted, xor_acc)))))
-    nt = len(t)
-    assert nt == len(A.transition_degrees)
-    pairs = [(0, 0)] * (A.num_constraint_coefficients() // 2)
-    adj_of = {idx: adj for adj, members in A.transition_groups(pairs[:nt]) for idx, _ in members}
-    for i in range(nt):
-        b.transition(t[i], adj_of[i])
-    groups = A.boundary_groups(pairs[nt:])
-    for a in sorted(A.get_assertions(), key=lambda a: (0, a.step, a.column)):
-        (j, adj), = [(j, adj) for j, (div, adj, mem) in enumerate(groups) if div.b == (pow(A.g, a.step, P) if a.step else 1)]
-        b.assertion(a.column, to_abi_int(a.value), adj, 1 + j)
-    return b.finish()
 
 
 @pytest.mark.gpu
