@@ -296,10 +296,18 @@ static const char *check_options(const aero_proof_options &o) {
 // rank barriers on the host, later ones on the device (include/aero_b200.h, multi-GPU section).
 aero_status prove(aero_ctx *ctx, const aero_prove_inputs &in, std::vector<uint8_t> *proof_bytes, std::string *err) {
     if (const char *msg = check_options(in.options)) P_FAIL(AERO_ERR_INVALID, msg);
-    char key[160];
-    snprintf(key, sizeof key, "prove/%llu/%u/%u/%u/%d/q%u/b%u/g%u/r%u/c%u", (unsigned long long)in.trace_len, in.main_width, in.aux_width,
-             in.n_div, in.inputs_on_device, in.options.num_queries, in.options.blowup_factor, in.options.grinding_factor,
-             in.options.fri_max_remainder_size, in.ce_blowup);
+    // everything that decides which device blocks a proof asks for (the first proof of a key may call cudaMalloc)
+    char key[224];
+    const bool device_air = in.air_program && !in.constraint_evaluator && !in.ce_cols;
+    unsigned long long prog_size = 0;
+    if (device_air) {
+        prog_size = (unsigned long long)in.air_program->n_nodes * 131 + in.air_program->n_consts * 17 + in.air_program->n_transition * 5 +
+                    in.air_program->n_boundary;
+        for (uint32_t k = 0; k < in.air_program->n_periodic && in.air_program->periodic_len; k++) prog_size = prog_size * 31 + in.air_program->periodic_len[k];
+    }
+    snprintf(key, sizeof key, "prove/%llu/%u/%u/%u/%d/q%u/b%u/g%u/r%u/c%u/m%d%d/p%llu", (unsigned long long)in.trace_len, in.main_width,
+             in.aux_width, in.n_div, in.inputs_on_device, in.options.num_queries, in.options.blowup_factor, in.options.grinding_factor,
+             in.options.fri_max_remainder_size, in.ce_blowup, device_air ? 1 : 0, in.aux_builder ? 1 : 0, prog_size);
     P_TRY(aero_ctx_shard_begin(ctx, key));
     aero_status st = prove_inner(ctx, in, proof_bytes, err);
     aero_ctx_shard_end(ctx, st == AERO_OK);
