@@ -69,6 +69,7 @@ struct aero_ctx {
     cudaEvent_t ev_lde = nullptr, ev_hash = nullptr, ev_copy_order = nullptr;
     bool overlap_hash = false;           // aero_ctx_set_option("overlap_hash"); measured slower on B200, see DESIGN.md
     bool force_split_intt = false;       // test hook: take the B x size-n route of constraints_into_poly at any size
+    int air_blocks_per_sm = 0;           // experiment hook: resident blocks per SM of the AIR evaluator, threads looping over steps (0 = one thread per step)
     std::map<std::string, uint64_t *> const_tables;
     std::vector<aero_upload *> deferred_uploads;  // queued behind the next segment commit's own copies
     // Exchange window (multi-GPU): one allocation per rank, the same size everywhere, mapped by every
@@ -1520,6 +1521,7 @@ aero_status aero_ctx_set_option(aero_ctx *ctx, const char *key, long long value)
     else if (k == "force_host_sync") ctx->force_host_sync = value != 0;
     else if (k == "push_parts" && value >= 1 && value <= PUSH_PARTS) ctx->push_parts = (int)value;
     else if (k == "force_split_intt") ctx->force_split_intt = value != 0;
+    else if (k == "air_blocks_per_sm") ctx->air_blocks_per_sm = (int)value;
     else if (k == "hash_blocks_per_sm" && value > 0) ctx->hash_blocks_per_sm = (int)value;
     else if (k == "lde_batch_bytes" && value > 0) ctx->lde_batch_bytes = (size_t)value;
     else if (k == "ntt_table_max_bytes" && value >= 0) ctx->ntt_table_max_bytes = (size_t)value;
@@ -2311,13 +2313,17 @@ static aero_status constraints_evaluate_impl(aero_ctx *ctx, aero_segment *const 
     if (adj.size() > 8) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "more than 8 distinct degree adjustments");
     std::vector<uint64_t> w64;
     const size_t o_consts = 0, o_bval = o_consts + prog->n_consts, o_coeffs = o_bval + nb, o_adj = o_coeffs + n_coeffs,
-                 o_per = o_adj + adj.size();
+                 o_adjoff = o_adj + adj.size(), o_per = o_adjoff + adj.size();
     w64.resize(o_per + periodic.size());
     std::copy(periodic.begin(), periodic.end(), w64.begin() + o_per);
     for (uint32_t i = 0; i < prog->n_consts; i++) w64[o_consts + i] = to_canon(ctx, prog->consts[i]);
     for (uint32_t j = 0; j < nb; j++) w64[o_bval + j] = to_canon(ctx, prog->boundary_value[j]);
     for (uint32_t i = 0; i < n_coeffs; i++) w64[o_coeffs + i] = to_canon(ctx, coeffs[i]);
-    for (size_t i = 0; i < adj.size(); i++) w64[o_adj + i] = adj[i];
+    for (size_t i = 0; i < adj.size(); i++) {
+        if (adj[i] >> 32) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "degree adjustment %llu does not fit 32 bits", (unsigned long long)adj[i]);
+        w64[o_adj + i] = adj[i];
+        w64[o_adjoff + i] = gl::pow(gl::GENERATOR, adj[i]);  // domain offset^adjustment (domain.rs:109-117)
+    }
     // Slots by liveness: a node's value occupies a slot from its evaluation to its last consumer; operands that
     // die at node k free their slots before k's result is placed (the kernel reads both operands, then writes).
     const uint32_t NN = prog->n_nodes;
@@ -2388,6 +2394,7 @@ static aero_status constraints_evaluate_impl(aero_ctx *ctx, aero_segment *const 
     p.b_val = d64 + o_bval;
     p.coeffs = d64 + o_coeffs;
     p.adj = d64 + o_adj;
+    p.adj_off = d64 + o_adjoff;
     p.periodic = d64 + o_per;
     p.n_nodes = (int)prog->n_nodes;
     p.n_slots = (int)std::max<uint32_t>(1, n_slots);
@@ -2395,11 +2402,11 @@ static aero_status constraints_evaluate_impl(aero_ctx *ctx, aero_segment *const 
     p.nb = (int)nb;
     p.n_adj = (int)adj.size();
     p.n_div = (int)n_div;
-    PowTable x_ce;  // offset * g_ce^step (StarkDomain::get_ce_x_at, domain.rs:99-101)
+    PowTable g_ce;  // g_ce^e: the constraint evaluation domain without its offset (StarkDomain::ce_domain, domain.rs:53-60)
     {
         char key[32];
-        snprintf(key, sizeof key, "xce/%d", logn + log_ce);
-        TRY(get_pow_table(ctx, key, gl::root_of_unity(logn + log_ce), logn + log_ce, gl::GENERATOR, &x_ce));
+        snprintf(key, sizeof key, "g/%d", logn + log_ce);
+        TRY(get_pow_table(ctx, key, gl::root_of_unity(logn + log_ce), logn + log_ce, 1, &g_ce));
     }
     // The evaluation-domain cosets whose LDE coset (rc << shift) this rank holds: a contiguous range, all of them
     // on one GPU.  Step s = i * ce_blowup + rc reads LDE coset rc << shift at i and i + 1 only, so a coset-sharded
@@ -2410,8 +2417,8 @@ static aero_status constraints_evaluate_impl(aero_ctx *ctx, aero_segment *const 
     const uint32_t tau0 = rc_lo << logn, tau_count = (rc_hi - rc_lo) << logn;
     {
         PhaseTimer t(ctx, "constraint_evaluate");
-        air_evaluate(segs, p, logn, log_blowup, log_ce, x_ce, ctx->form == AERO_FORM_MONTGOMERY, d_eval_cols, col_stride, ctx->stream,
-                     tau0, tau_count);
+        air_evaluate(segs, p, logn, log_blowup, log_ce, g_ce, ctx->form == AERO_FORM_MONTGOMERY, d_eval_cols, col_stride, ctx->stream,
+                     tau0, tau_count, ctx->num_sms, ctx->air_blocks_per_sm);
     }
     if (tau0_out) *tau0_out = tau0;
     if (tau_count_out) *tau_count_out = tau_count;

@@ -218,12 +218,14 @@ struct AirProgramDev {       // device copies; field elements canonical
     const uint64_t *b_val;
     const uint64_t *coeffs;  // pairs: transition constraints, then boundary constraints
     const uint64_t *adj;     // distinct degree adjustments
+    const uint64_t *adj_off; // offset^adj for each of them (canonical)
     int n_nodes, n_slots, nt, nb, n_adj, n_div;
 };
 // threads [tau0, tau0 + tau_count) of the coset-major numbering (tau = rc * n + i): a coset-sharded rank passes
 // the cosets it holds, with segs.lde rebased so that (LDE coset, i) indexes its compact storage
-void air_evaluate(const AirSegs &segs, const AirProgramDev &p, int logn, int log_blowup, int log_ce, PowTable x_ce /* 7 g_ce^s */,
-                  int to_montgomery, uint64_t *out, size_t out_stride, cudaStream_t s, uint32_t tau0, uint32_t tau_count);
+void air_evaluate(const AirSegs &segs, const AirProgramDev &p, int logn, int log_blowup, int log_ce, PowTable g_ce /* g_ce^s */,
+                  int to_montgomery, uint64_t *out, size_t out_stride, cudaStream_t s, uint32_t tau0, uint32_t tau_count,
+                  int num_sms, int blocks_per_sm /* 0 = one thread per step */);
 
 // peak.cu
 double measure_alu_peak(int num_sms, uint32_t *scratch, cudaStream_t s);

@@ -750,12 +750,16 @@ void constraint_combine(const uint64_t *cols, size_t col_stride, const DivisorDe
 // the widest cut of the expression DAG, not its size.
 template <int MAXN>
 __global__ void __launch_bounds__(128) air_evaluate_kernel(AirSegs segs, AirProgramDev p, int logn, int log_blowup, int log_ce,
-                                                          PowTable x_ce, int to_montgomery, uint64_t *__restrict__ out,
+                                                          PowTable g_ce, int to_montgomery, uint64_t *__restrict__ out,
                                                           size_t out_stride, uint32_t tau0, uint32_t tau_count) {
-    // [tau0, tau0 + tau_count): the cosets of the evaluation domain this rank holds (all of them on one GPU)
-    if (blockIdx.x * blockDim.x + threadIdx.x >= tau_count) return;
-    const uint32_t tau = tau0 + blockIdx.x * blockDim.x + threadIdx.x;
+    // [tau0, tau0 + tau_count): the cosets of the evaluation domain this rank holds (all of them on one GPU).
+    // One thread per step by default (the loop runs once).  The grid-stride form exists for the experiment
+    // recorded in DESIGN.md: fewer resident threads whose slots stay in L2 remove the slots' DRAM traffic (ncu: 6.2 GB
+    // for 0.6 GB of frame and result) but lose more to the lower occupancy than they gain (2.25 vs 1.83 ms).
     const uint32_t n = 1u << logn;
+    uint64_t val[MAXN];
+    for (uint32_t t_ = blockIdx.x * blockDim.x + threadIdx.x; t_ < tau_count; t_ += gridDim.x * blockDim.x) {
+    const uint32_t tau = tau0 + t_;
     const uint32_t i = tau & (n - 1), rc = tau >> logn;
     const uint32_t step = (i << log_ce) | rc;                     // natural index in the evaluation domain
     const size_t cur = ((size_t)(rc << (log_blowup - log_ce)) << logn) + i;   // (LDE coset, i)
@@ -767,10 +771,13 @@ __global__ void __launch_bounds__(128) air_evaluate_kernel(AirSegs segs, AirProg
         }
         return 0;
     };
-    const uint64_t x = pow_lookup(x_ce, step);                   // domain.rs:99-101: offset * g_ce^step
+    // x^adjustment for x = offset * g_ce^step, the way StarkDomain::get_ce_x_power_at does it (domain.rs:109-117):
+    // g_ce^(step * adj mod CE) from the domain's table, times offset^adj from the host -- two products instead of
+    // a square-and-multiply chain per adjustment
     uint64_t xp[8];
-    for (int a = 0; a < p.n_adj; a++) xp[a] = gl::pow(x, p.adj[a]);   // domain.rs:109-117: x^adjustment
-    uint64_t val[MAXN];
+    const uint32_t ce_mask = (n << log_ce) - 1;
+    for (int a = 0; a < p.n_adj; a++)
+        xp[a] = gl::mul(pow_lookup(g_ce, (uint32_t)(((uint64_t)step * __ldg(p.adj + a)) & ce_mask)), __ldg(p.adj_off + a));
     for (int k = 0; k < p.n_nodes; k++) {
         const uint4 nd = __ldg(reinterpret_cast<const uint4 *>(p.nodes) + k);   // op, a, b, destination slot
         uint64_t v;
@@ -801,15 +808,20 @@ __global__ void __launch_bounds__(128) air_evaluate_kernel(AirSegs segs, AirProg
         acc[d] = gl::add(acc[d], gl::mul(w, v));
     }
     for (int d = 0; d < p.n_div; d++) out[(size_t)d * out_stride + step] = to_montgomery ? gl::canon_to_mont(acc[d]) : acc[d];
+    }
 }
-void air_evaluate(const AirSegs &segs, const AirProgramDev &p, int logn, int log_blowup, int log_ce, PowTable x_ce,
-                  int to_montgomery, uint64_t *out, size_t out_stride, cudaStream_t s, uint32_t tau0, uint32_t tau_count) {
+void air_evaluate(const AirSegs &segs, const AirProgramDev &p, int logn, int log_blowup, int log_ce, PowTable g_ce,
+                  int to_montgomery, uint64_t *out, size_t out_stride, cudaStream_t s, uint32_t tau0, uint32_t tau_count,
+                  int num_sms, int blocks_per_sm) {
     if (!tau_count) return;
-    const unsigned grid = (unsigned)(((uint64_t)tau_count + 127) / 128);
+    // blocks_per_sm <= 0: one thread per step; n > 0: n resident blocks per SM, each thread looping over steps
+    const uint64_t need = ((uint64_t)tau_count + 127) / 128;
+    const uint64_t cap = blocks_per_sm > 0 ? (uint64_t)num_sms * blocks_per_sm : need;
+    const unsigned grid = (unsigned)(need < cap ? need : cap);
     AERO_COUNT_LAUNCH(1);
-    if (p.n_slots <= 32) air_evaluate_kernel<32><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride, tau0, tau_count);
-    else if (p.n_slots <= 128) air_evaluate_kernel<128><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride, tau0, tau_count);
-    else air_evaluate_kernel<1024><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, x_ce, to_montgomery, out, out_stride, tau0, tau_count);
+    if (p.n_slots <= 32) air_evaluate_kernel<32><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, g_ce, to_montgomery, out, out_stride, tau0, tau_count);
+    else if (p.n_slots <= 128) air_evaluate_kernel<128><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, g_ce, to_montgomery, out, out_stride, tau0, tau_count);
+    else air_evaluate_kernel<1024><<<grid, 128, 0, s>>>(segs, p, logn, log_blowup, log_ce, g_ce, to_montgomery, out, out_stride, tau0, tau_count);
 }
 
 }  // namespace aero

@@ -89,7 +89,9 @@ int aero_ctx_get_form(aero_ctx *ctx);
  *                     batches right after their extension (chained row hash) so that the stream does not
  *                     wait for later batches;
  *   "fri_fused"       0 (default) / 1 / 2: fold a FRI layer and hash the next layer's leaves in one kernel --
- *                     never / layers of <= 2^14 folded leaves / all layers (measured slower on B200).
+ *                     never / layers of <= 2^14 folded leaves / all layers (measured slower on B200);
+ *   "air_blocks_per_sm" 0 (default): the AIR evaluator runs one thread per evaluation step; n > 0: n resident blocks
+ *                     per SM, each thread looping over steps (keeps the value slots in L2; measured slower).
  * Environment hooks for experiments (read once): AERO_NTT_BULK=0 (LDGSTS instead of TMA tile loads),
  * AERO_NTT_COLFAST=0 (tile-major pass-1 grid), AERO_NTT_OUTER, AERO_HASH_EARLY, AERO_FRI_FUSED (defaults of the
  * options above), AERO_HOST_TIMING=1 (host-side section marks of aero_prove on stderr). */

@@ -27,6 +27,7 @@ def main() -> None:
     ap.add_argument("--air", default="random", choices=["random", "bitwise"],
                     help="bitwise: the program of Miden's bitwise chiplet (oracle/air_programs.py; 21 constraints, two "
                          "periodic columns, evaluation domain 4n) over a 15-column trace instead of a random program")
+    ap.add_argument("--blocks-per-sm", type=int, default=0, help="context option air_blocks_per_sm (experiments)")
     ap.add_argument("--prove", action="store_true",
                     help="with --air bitwise: also time complete proofs (aero_prove with the program) of a VALID chiplet "
                          "trace and check the last one with the verifier model, OOD consistency check included")
@@ -36,6 +37,7 @@ def main() -> None:
     from bench import splitmix_matrix
 
     ctx = aero_b200.Context(0, form=aero_b200.AERO_FORM_CANONICAL)
+    ctx.set_option("air_blocks_per_sm", args.blocks_per_sm)
     n = 1 << args.log_rows
     if args.air == "bitwise":
         return bitwise(ctx, args, n)
@@ -75,7 +77,7 @@ def main() -> None:
         each.append(ms)
     per = min(each)   # the first call also loads the kernel and sizes its local memory
     ops = sum(1 for nd in b.nodes if nd[0] >= 3)
-    print(json.dumps({"log_rows": args.log_rows, "nodes": args.nodes, "field_ops": ops, "constraints": n_t + n_b,
+    print(json.dumps({"blocks_per_sm": args.blocks_per_sm, "log_rows": args.log_rows, "nodes": args.nodes, "field_ops": ops, "constraints": n_t + n_b,
                       "ce_domain": ce, "ms": per, "ms_each_call": [round(x, 3) for x in each], "steps_per_s": ce / (per * 1e-3), "field_ops_per_s": ops * ce / (per * 1e-3),
                       "note": "compare: downloading the 81-column LDE for a host-side evaluator moves %.1f GB (%.0f ms at 57 GB/s)"
                               % (81 * n * 8 * 8 / 1e9, 81 * n * 8 * 8 / 57e9 * 1e3)}))
@@ -106,7 +108,7 @@ def bitwise(ctx, args, n: int) -> None:
         each.append(ctx.profile_read()["constraint_evaluate"][1])
     per = min(each)
     ops = sum(1 for i in range(prog.n_nodes) if 3 <= prog.nodes[i].op <= 5)
-    print(json.dumps({"air": "Miden bitwise chiplet", "log_rows": args.log_rows, "nodes": prog.n_nodes, "field_ops": ops,
+    print(json.dumps({"air": "Miden bitwise chiplet", "blocks_per_sm": args.blocks_per_sm, "log_rows": args.log_rows, "nodes": prog.n_nodes, "field_ops": ops,
                       "constraints": prog.n_transition + prog.n_boundary, "periodic_columns": prog.n_periodic, "ce_domain": ce,
                       "ms": per, "ms_each_call": [round(x, 3) for x in each], "steps_per_s": ce / (per * 1e-3),
                       "field_ops_per_s": ops * ce / (per * 1e-3)}))
