@@ -2,7 +2,7 @@
 # the device AIR evaluator on Miden's bitwise chiplet, memcheck over the AIR evaluator cases.
 set -x
 mkdir -p gpurun_out
-TAG=${TAG:-r02_y5}
+TAG=${TAG:-r02_last}
 export AERO_B200_NO_BUILD=1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_gpu_tests.log 2>&1; echo "tests rc=$?"
 tail -6 gpurun_out/${TAG}_gpu_tests.log
