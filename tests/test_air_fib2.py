@@ -579,3 +579,34 @@ def test_bitwise_chiplet_evaluated_on_the_gpu(ctx, ctx_mont, logn, form):
     if logn <= 6:
         assert got_proof == _oracle_prove(trace, air, divs, pub).proof_bytes
     so.verify(got_proof, pub, air.ce_blowup, air=air)
+
+
+def test_boundary_groups_follow_the_reference_unit_test():
+    """The single-value part of the reference's own `get_boundary_constraints` test (air/src/air/tests.rs:67-170,
+    trace length 16): assertions (column 0, step 0), (0, 9), (1, 9) fall into two groups with divisors x - g^0 and
+    x - g^9 of degree 1, the coefficient pairs are handed out in the assertions' natural order (stride, first step,
+    column) whatever order they were declared in, and the value polynomial of a single-value assertion is the
+    constant itself."""
+    from oracle.air import Assertion, SimpleAir
+
+    class Mock(SimpleAir):  # air/src/air/tests.rs MockAir::with_assertions
+        trace_width = 4
+        transition_degrees = [1]
+
+        def get_assertions(self):
+            return [Assertion(1, 9, 9), Assertion(0, 0, 3), Assertion(0, 9, 5)]   # declared out of order
+
+    air = Mock(16, 0)
+    cc = [(11, 12), (21, 22), (31, 32)]
+    groups = air.boundary_groups(cc)
+    assert len(groups) == 2
+    g = air.g
+    (d0, adj0, m0), (d1, adj1, m1) = groups
+    assert (d0.a, d0.b, d0.degree()) == (1, pow(g, 0, P), 1) and (d1.a, d1.b, d1.degree()) == (1, pow(g, 9, P), 1)
+    assert m0 == [(0, 3, (11, 12))]
+    assert m1 == [(0, 5, (21, 22)), (1, 9, (31, 32))]
+    # BoundaryConstraintGroup::new (constraint_group.rs:28-30): composition degree + divisor degree - trace poly degree
+    assert adj0 == adj1 == air.composition_degree() + 1 - (16 - 1)
+    # the divisors vanish exactly at the asserted steps
+    for step, d in ((0, d0), (9, d1)):
+        assert (pow(pow(g, step, P), d.a, P) - d.b) % P == 0
