@@ -2310,7 +2310,7 @@ static aero_status constraints_evaluate_impl(aero_ctx *ctx, aero_segment *const 
         if (prog->boundary_div[j] == 0 || prog->boundary_div[j] >= n_div) CTX_FAIL(ctx, AERO_ERR_INVALID, "boundary constraint %u: divisor column out of range", j);
         b_adj[j] = adj_index(prog->boundary_adj[j]);
     }
-    if (adj.size() > 8) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "more than 8 distinct degree adjustments");
+    if (adj.size() > (size_t)AIR_MAX_ADJ) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "more than %d distinct degree adjustments", AIR_MAX_ADJ);
     std::vector<uint64_t> w64;
     const size_t o_consts = 0, o_bval = o_consts + prog->n_consts, o_coeffs = o_bval + nb, o_adj = o_coeffs + n_coeffs,
                  o_adjoff = o_adj + adj.size(), o_per = o_adjoff + adj.size();

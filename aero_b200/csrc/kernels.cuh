@@ -207,6 +207,7 @@ struct AirSegs {  // trace segments in order: column c of segment s at lde[s] + 
     int ncols[4];
     int nseg;
 };
+constexpr int AIR_MAX_ADJ = 32;  // distinct degree adjustments of one AIR (Miden's ProcessorAir has about twenty)
 struct AirProgramDev {       // device copies; field elements canonical
     const uint32_t *nodes;   // 4 words per node (16-byte aligned): op, a, b, destination slot; operands of
                              //   add / sub / mul and t_out are SLOTS (assigned by liveness on the host); a

@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(128) air_evaluate_kernel(AirSegs segs, AirProg
     // x^adjustment for x = offset * g_ce^step, the way StarkDomain::get_ce_x_power_at does it (domain.rs:109-117):
     // g_ce^(step * adj mod CE) from the domain's table, times offset^adj from the host -- two products instead of
     // a square-and-multiply chain per adjustment
-    uint64_t xp[8];
+    uint64_t xp[AIR_MAX_ADJ];
     const uint32_t ce_mask = (n << log_ce) - 1;
     for (int a = 0; a < p.n_adj; a++)
         xp[a] = gl::mul(pow_lookup(g_ce, (uint32_t)(((uint64_t)step * __ldg(p.adj + a)) & ce_mask)), __ldg(p.adj_off + a));

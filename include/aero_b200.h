@@ -236,7 +236,7 @@ aero_status aero_constraints_into_poly_device(aero_ctx *ctx, const uint64_t *d_e
  * evaluation domain (ABI form, column d at d_eval_cols + d * col_stride): the input of
  * aero_constraints_into_poly_device.  On a sharded context only the steps s with s mod ce_blowup among the
  * rank's cosets are written (aero_constraints_evaluate_into_poly combines and exchanges them).  At most 65536 nodes of which at most 1024 values alive at once (slots
- * are assigned by liveness), 8 distinct degree adjustments. */
+ * are assigned by liveness), 32 distinct degree adjustments. */
 enum { AERO_AIR_CUR = 0, AERO_AIR_NEXT = 1, AERO_AIR_CONST = 2, AERO_AIR_ADD = 3, AERO_AIR_SUB = 4, AERO_AIR_MUL = 5,
        AERO_AIR_PERIODIC = 6 };
 typedef struct aero_air_node {

@@ -181,12 +181,26 @@ def test_air_program_is_validated(ctx):
     prog, keep = b.finish()
     with pytest.raises(AeroError):
         ctx.evaluate_constraints([seg], prog, [1, 2], 2, 1)
+    b = AirProgramBuilder()                        # more distinct degree adjustments than the evaluator keeps
+    x = b.cur(0)
+    for k in range(33):
+        b.transition(x, 1 + k)
+    prog, keep = b.finish()
+    with pytest.raises(AeroError) as e:
+        ctx.evaluate_constraints([seg], prog, list(range(66)), 2, 1)
+    assert e.value.status == aero_b200_unsupported()
     seg.destroy()
 
 
+def aero_b200_unsupported():
+    import aero_b200
+
+    return aero_b200.AERO_ERR_UNSUPPORTED
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_nodes,ce_blowup", [(40, 2), (600, 8), (1024, 4)])
-def test_random_transition_program_matches_a_python_evaluation(ctx, n_nodes, ce_blowup):
+@pytest.mark.parametrize("n_nodes,ce_blowup,n_adj", [(40, 2, 3), (600, 8, 3), (1024, 4, 3), (300, 8, 30)])
+def test_random_transition_program_matches_a_python_evaluation(ctx, n_nodes, ce_blowup, n_adj):
     """The device evaluator on programs far larger than fib2's (the 1024-slot instantiation, two trace segments,
     several degree adjustments and divisor columns, constraint evaluation domains of 2n..8n): every merged
     evaluation equals a direct big-int evaluation of the same program over the oracle's LDE -- the formulas of
@@ -214,10 +228,10 @@ def test_random_transition_program_matches_a_python_evaluation(ctx, n_nodes, ce_
         else:
             a_, b_ = int(rng.integers(0, k)), int(rng.integers(0, k))
             (b.add, b.sub, b.mul)[int(rng.integers(0, 3))](a_, b_)
-    n_t, n_b, n_div = 12, 5, 4
-    adjs = [int(x) for x in rng.integers(1, 4 * n, 3)]
+    n_t, n_b, n_div = max(12, n_adj), 5, 4
+    adjs = [int(x) for x in rng.choice(np.arange(1, 4 * n), n_adj, replace=False)]   # distinct degree adjustments
     for t in range(n_t):
-        b.transition(int(rng.integers(0, n_nodes)), adjs[t % 3])
+        b.transition(int(rng.integers(0, n_nodes)), adjs[t % n_adj])
     for j in range(n_b):
         b.assertion(int(rng.integers(0, W)), int(rng.integers(0, 2**63)) % P, adjs[j % 2], 1 + j % (n_div - 1))
     prog, keep = b.finish()
