@@ -449,7 +449,7 @@ class PermutationAir(SimpleAir):
         return [(nxt[0] - cur[0] - self.STEP) % P]
 
     def evaluate_aux_transition(self, main_cur, main_nxt, aux_cur, aux_nxt, periodic, rand):
-        a, b = int(rand[0]), int(rand[1])
+        a, b = rand[0], rand[1]
         return [(aux_nxt[0] * (a + b * main_cur[1]) - aux_cur[0] * (a + b * main_cur[0])) % P]
 
     def get_assertions(self):

@@ -158,3 +158,112 @@ def permutation_program(air, to_abi_int):
         b.assertion(col, to_abi_int(value), adj, j)
     prog, keep = b.finish()
     return prog, keep
+
+
+# ---- a program interpreter and a symbolic recorder (CPU side) -----------------------------------------------
+def interpret_program(builder_or_nodes, consts, cur, nxt, periodic=()):
+    """Node values of a transition program over one evaluation frame, in canonical big-int arithmetic: what
+    air_evaluate_kernel computes per step (aero_b200/csrc/poly.cu), restated for CPU-side checks of the recorded
+    programs.  `builder_or_nodes`: AirProgramBuilder.nodes (op, a, b triples); consts / frame rows / periodic values
+    canonical."""
+    val = []
+    for op, a, b in builder_or_nodes:
+        if op == 0:
+            val.append(cur[a] % P)
+        elif op == 1:
+            val.append(nxt[a] % P)
+        elif op == 2:
+            val.append(consts[a] % P)
+        elif op == 6:
+            val.append(periodic[a] % P)
+        elif op == 3:
+            val.append((val[a] + val[b]) % P)
+        elif op == 4:
+            val.append((val[a] - val[b]) % P)
+        elif op == 5:
+            val.append(val[a] * val[b] % P)
+        else:
+            raise ValueError("unknown node op %r" % op)
+    return val
+
+
+class _Sym:
+    """A field element that records instead of computing: the Python twin of the symbolic FieldElement a Rust
+    caller runs through Air::evaluate_transition (INTEGRATION.md).  Integers met in the arithmetic become
+    constants of the program; `% P` is the identity (the device reduces)."""
+
+    __slots__ = ("rec", "node")
+
+    def __init__(self, rec, node):
+        self.rec, self.node = rec, node
+
+    def _lift(self, other):
+        return other if isinstance(other, _Sym) else self.rec.const(int(other))
+
+    def __add__(self, o):
+        return _Sym(self.rec, self.rec.b.add(self.node, self._lift(o).node))
+
+    def __radd__(self, o):
+        return _Sym(self.rec, self.rec.b.add(self._lift(o).node, self.node))
+
+    def __sub__(self, o):
+        return _Sym(self.rec, self.rec.b.sub(self.node, self._lift(o).node))
+
+    def __rsub__(self, o):
+        return _Sym(self.rec, self.rec.b.sub(self._lift(o).node, self.node))
+
+    def __mul__(self, o):
+        return _Sym(self.rec, self.rec.b.mul(self.node, self._lift(o).node))
+
+    def __rmul__(self, o):
+        return _Sym(self.rec, self.rec.b.mul(self._lift(o).node, self.node))
+
+    def __mod__(self, m):
+        assert m == P
+        return self
+
+
+class _Recorder:
+    def __init__(self, builder, to_abi_int):
+        self.b, self.to_abi_int, self.const_nodes = builder, to_abi_int, {}
+
+    def const(self, v: int) -> _Sym:
+        v %= P
+        if v not in self.const_nodes:          # one constant node per distinct value
+            self.const_nodes[v] = self.b.const(self.to_abi_int(v))
+        return _Sym(self, self.const_nodes[v])
+
+
+def record_program(air, to_abi_int, aux_rand_const_slots: int = 0):
+    """Runs air.evaluate_transition (and evaluate_aux_transition) ONCE over symbolic frame rows and returns the
+    recorded aero_air_program with the degree adjustments and assertions of the restated constraint groups --
+    no hand-written node list.  The auxiliary segment's random elements become the first `aux_rand_const_slots`
+    constants (value 0 until the aux_builder callback fills them in).  Returns (program, keep-alive, builder)."""
+    from aero_b200 import AirProgramBuilder
+
+    b = AirProgramBuilder()
+    rec = _Recorder(b, to_abi_int)
+    rand = [_Sym(rec, b.const(0)) for _ in range(aux_rand_const_slots)]   # consts[0 .. k): the random elements
+    periodic = [_Sym(rec, b.periodic(b.periodic_column([to_abi_int(v) for v in col]))) for col in air.periodic_columns]
+    w, wa = air.trace_width, air.aux_width
+    cur = [_Sym(rec, b.cur(c)) for c in range(w + wa)]
+    nxt = [_Sym(rec, b.next(c)) for c in range(w + wa)]
+    outs = list(air.evaluate_transition(cur[:w], nxt[:w], periodic))
+    if wa:
+        outs += list(air.evaluate_aux_transition(cur[:w], nxt[:w], cur[w:], nxt[w:], periodic, rand))
+    nt = len(outs)
+    assert nt == len(air._all_degrees())
+    pairs = [(0, 0)] * (air.num_constraint_coefficients() // 2)
+    adj_of = {idx: adj for adj, members in air.transition_groups(pairs[:nt]) for idx, _ in members}
+    for i, o in enumerate(outs):
+        b.transition(rec.const(o).node if not isinstance(o, _Sym) else o.node, adj_of[i])
+    # assertions in coefficient order (main sorted, then auxiliary sorted), each with its group's divisor column
+    groups = air.boundary_groups(pairs[nt:])
+    main_as = sorted(air.get_assertions(), key=lambda a: (0, a.step, a.column))
+    aux_as = sorted(air.get_aux_assertions([0] * air.num_aux_rands), key=lambda a: (0, a.step, a.column)) if wa else []
+    for a, off in [(a, 0) for a in main_as] + [(a, w) for a in aux_as]:
+        div_b = pow(air.g, a.step, P) if a.step else 1
+        (j, adj), = [(j, adj) for j, (div, adj, mem) in enumerate(groups) if div.b == div_b]
+        b.assertion(a.column + off, to_abi_int(a.value), adj, 1 + j)
+    prog, keep = b.finish()
+    return prog, keep, b

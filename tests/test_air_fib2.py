@@ -624,3 +624,90 @@ def test_boundary_groups_follow_the_reference_unit_test():
     # the divisors vanish exactly at the asserted steps
     for step, d in ((0, d0), (9, d1)):
         assert (pow(pow(g, step, P), d.a, P) - d.b) % P == 0
+
+
+# ---- the programs themselves, checked on the CPU ------------------------------------------------------------
+def _all_air_cases():
+    from oracle.air import BitwiseChipletAir, MaskedChainAir, PermutationAir
+
+    n = 32
+    return [("fib2", Fib2Air(n, 1), _fib2_program, 0), ("mulfib2", MulFib2Air(n, 1), _fib2_program, 0),
+            ("masked_chain", MaskedChainAir(n, 1), _masked_chain_program, 0),
+            ("bitwise", BitwiseChipletAir(n, 1), _bitwise_program, 0), ("permutation", PermutationAir(n, 0), _permutation_program, 2)]
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_programs_interpreted_on_the_cpu_equal_the_restated_constraints(case):
+    """Every hand-recorded program AND the program recorded automatically by running the AIR's evaluate_transition
+    over symbolic elements (oracle/air_programs.py: record_program, the Python twin of the Rust-side recorder of
+    INTEGRATION.md), interpreted node by node over random frames, equal the restated constraint functions -- and the
+    two programs declare the same degree adjustments, assertions and periodic columns."""
+    from oracle.air_programs import interpret_program, record_program
+    from aero_b200 import AirProgramBuilder
+
+    name, air, hand, n_rand = _all_air_cases()[case]
+    rng = np.random.default_rng(case)
+    W = air.trace_width + air.aux_width
+    hand_prog, hand_keep = hand(air, lambda v: v)
+    rec_prog, rec_keep, rec_b = record_program(air, lambda v: v, aux_rand_const_slots=n_rand)
+    rand = [int(x) % P for x in rng.integers(1, 2**63, n_rand, dtype=np.uint64)]
+    air.aux_rand_elements = rand
+
+    def nodes_consts(prog):
+        nodes = [(prog.nodes[i].op, prog.nodes[i].a, prog.nodes[i].b) for i in range(prog.n_nodes)]
+        consts = [int(prog.consts[i]) for i in range(prog.n_consts)]
+        consts[:n_rand] = rand                         # what the aux_builder callback writes
+        return nodes, consts
+
+    for _ in range(20):
+        cur = [int(x) % P for x in rng.integers(0, 2**63, W, dtype=np.uint64)]
+        nxt = [int(x) % P for x in rng.integers(0, 2**63, W, dtype=np.uint64)]
+        per = [int(x) % P for x in rng.integers(0, 2**63, len(air.periodic_columns), dtype=np.uint64)]
+        want = air._transition_all(cur, nxt, per)
+        for prog in (hand_prog, rec_prog):
+            nodes, consts = nodes_consts(prog)
+            val = interpret_program(nodes, consts, cur, nxt, per)
+            assert [val[prog.transition_out[t]] for t in range(prog.n_transition)] == want, name
+    meta = lambda p: ([int(p.transition_adj[t]) for t in range(p.n_transition)],
+                      [(int(p.boundary_col[j]), int(p.boundary_value[j]), int(p.boundary_adj[j]), int(p.boundary_div[j]))
+                       for j in range(p.n_boundary)],
+                      [int(p.periodic_len[k]) for k in range(p.n_periodic)])
+    assert meta(hand_prog) == meta(rec_prog), name
+    air.aux_rand_elements = ()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["bitwise", "masked_chain", "permutation"])
+def test_automatically_recorded_programs_on_the_gpu(ctx, which):
+    """record_program's output -- the AIR's own evaluate_transition run over symbolic elements, no hand-written node
+    list -- through aero_prove: the oracle prover's bytes, OOD consistency check included."""
+    from aero_b200 import make_divisor
+    from oracle.air_programs import record_program
+
+    logn = 6
+    if which == "permutation":
+        n, trace, air, divs, pub = _setup_perm(logn)
+    elif which == "bitwise":
+        n, trace, air, divs, pub = _setup_bitwise(logn)
+    else:
+        n, trace, air, divs, pub = _setup_chain(logn)
+    n_rand = air.num_aux_rands if air.aux_width else 0
+    prog, keep, builder = record_program(air, lambda v: v, aux_rand_const_slots=n_rand)
+    consts = keep[1]
+    gdivs = [make_divisor(d.a, d.b, d.exemptions) for d in divs]
+    kw = {}
+    if air.aux_width:
+        def aux_builder(rands):
+            rand = [int(r) for r in rands]
+            for k in range(n_rand):
+                consts[k] = rand[k]
+            return air.build_aux(trace, rand)
+        kw = dict(aux_rands=n_rand, aux_builder=aux_builder, aux_width=air.aux_width)
+        ref = _oracle_prove_perm(trace, air, divs, pub)
+    else:
+        ref = _oracle_prove(trace, air, divs, pub)
+    got = ctx.prove(trace, None, None, gdivs, pub, n_constraint_coeffs=air.num_constraint_coefficients(),
+                    ce_blowup=air.ce_blowup, air_program=prog, **kw)
+    assert got == ref.proof_bytes
+    air.aux_rand_elements = ()
+    so.verify(got, pub, air.ce_blowup, air=air)
