@@ -2277,11 +2277,16 @@ static aero_status constraints_evaluate_impl(aero_ctx *ctx, aero_segment *const 
     std::vector<uint64_t> periodic;
     std::vector<uint32_t> per_off(prog->n_periodic), per_mask(prog->n_periodic);
     {
-        size_t src = 0;
+        size_t src = 0, total = 0;
         for (uint32_t k = 0; k < prog->n_periodic; k++) {
             const uint64_t c = prog->periodic_len[k];
             // Air::get_periodic_column_polys' assertions (air/src/air/mod.rs:319-335)
             if (c < 2 || !is_pow2(c) || c > ((uint64_t)1 << logn)) CTX_FAIL(ctx, AERO_ERR_INVALID, "periodic column %u: cycle length %llu is not a power of two in 2..trace length", k, (unsigned long long)c);
+            total += (size_t)c * ce_blowup;
+        }
+        if (total > ((size_t)1 << 28)) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "periodic value table too large (%zu values)", total);
+        for (uint32_t k = 0; k < prog->n_periodic; k++) {
+            const uint64_t c = prog->periodic_len[k];
             std::vector<uint64_t> col(c);
             for (uint64_t i = 0; i < c; i++) col[i] = to_canon(ctx, prog->periodic_values[src + i]);
             src += c;
@@ -2289,7 +2294,6 @@ static aero_status constraints_evaluate_impl(aero_ctx *ctx, aero_segment *const 
             per_mask[k] = (uint32_t)(c * ce_blowup - 1);
             periodic_column_table(col, ((uint64_t)1 << logn) / c, ce_blowup, periodic);
         }
-        if (periodic.size() > ((size_t)1 << 30)) CTX_FAIL(ctx, AERO_ERR_UNSUPPORTED, "periodic value table too large");
     }
     std::vector<uint64_t> adj;  // distinct degree adjustments
     auto adj_index = [&](uint64_t a) {
